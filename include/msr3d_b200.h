@@ -1,0 +1,93 @@
+/*
+ * msr3d_b200 — C ABI of the B200-native MSR3D hot path (libmsr3d_b200.so).
+ *
+ * Plain pointers and sizes only; all pointers are DEVICE pointers unless a
+ * parameter is documented as host.  Every entry point is asynchronous on the
+ * given stream, allocates nothing the caller can see, never calls exit(), and
+ * returns an int status (MSR3D_OK == 0).  msr3d_last_error() returns a
+ * thread-local human-readable string for the last non-zero status.
+ *
+ * Reference interfaces replaced (paths relative to the MSR3D reference tree):
+ *   group A  modules/third_party/pointnet2/_ext_src/src/bindings.cpp:6-19
+ *            (pybind module `pointnet2._ext`, nine functions) and the host
+ *            wrappers in sampling.cpp:15-87, ball_query.cpp:8-32,
+ *            group_points.cpp:12-62, interpolate.cpp:14-99.
+ *   group B  modules/third_party/pointnet2/pointnet2_modules.py:34-75
+ *            (_PointnetSAModuleBase.forward) + pytorch_utils.py:11-36,157-188
+ *            (SharedMLP = conv1x1 + eval-BN + ReLU) + modules/layers/pointnet.py:55-63.
+ *   group C  modules/layers/transformers.py:200-252,314-329,
+ *            modules/utils.py:60-137, model/ose3d_situation.py:31-59,368-435.
+ *   group D  trainer/leo_trainer.py:189-195 + optim/build.py:7-17 (clip + AdamW).
+ *
+ * Contract differences from the reference, on purpose:
+ *   - the caller owns every buffer (the reference allocates with torch::zeros);
+ *     entry points that need zero-initialised outputs do the memset themselves;
+ *   - errors come back as status codes (cuda_utils.h:30-39 calls exit(-1));
+ *   - furthest_point_sampling needs no `temp` scratch (kept in registers).
+ */
+#ifndef MSR3D_B200_H
+#define MSR3D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cudaStream_t without pulling cuda_runtime.h into C callers */
+typedef void *msr3d_stream_t;
+
+enum {
+  MSR3D_OK = 0,
+  MSR3D_ERR_INVALID_ARG = 1,
+  MSR3D_ERR_UNSUPPORTED = 2,
+  MSR3D_ERR_CUDA = 3
+};
+
+const char *msr3d_last_error(void);
+/* ABI version of this header; bumped on any signature change. */
+int msr3d_abi_version(void);
+/* Number of kernel launches issued through this library by the calling process. */
+unsigned long long msr3d_launch_count(void);
+
+/* ------------------------------------------------------------------ group A
+ * The nine pointnet2._ext operators.  Layouts and semantics are exactly the
+ * reference's; int32 outputs are bit-identical to the reference CUDA kernels
+ * built with nvcc's default -fmad=true.                                     */
+
+/* sampling.cpp:66-87 / sampling_gpu.cu:69-173.  xyz (B,N,3) -> idx (B,m). */
+int msr3d_furthest_point_sampling_f32(const float *xyz, int32_t *idx, int B, int N,
+                                      int m, msr3d_stream_t stream);
+/* sampling.cpp:15-38 / sampling_gpu.cu:8-20.  points (B,C,N), idx (B,M) -> out (B,C,M). */
+int msr3d_gather_points_f32(const float *points, const int32_t *idx, float *out, int B,
+                            int C, int N, int M, msr3d_stream_t stream);
+/* sampling.cpp:40-65 / sampling_gpu.cu:34-47.  grad_out (B,C,M) -> grad_points (B,C,N), zeroed here. */
+int msr3d_gather_points_grad_f32(const float *grad_out, const int32_t *idx,
+                                 float *grad_points, int B, int C, int N, int M,
+                                 msr3d_stream_t stream);
+/* ball_query.cpp:8-32 / ball_query_gpu.cu:9-44.  new_xyz (B,M,3), xyz (B,N,3) -> idx (B,M,nsample). */
+int msr3d_ball_query_f32(const float *new_xyz, const float *xyz, int32_t *idx, int B,
+                         int N, int M, float radius, int nsample, msr3d_stream_t stream);
+/* group_points.cpp:12-36 / group_points_gpu.cu:8-28.  points (B,C,N), idx (B,P,S) -> out (B,C,P,S). */
+int msr3d_group_points_f32(const float *points, const int32_t *idx, float *out, int B,
+                           int C, int N, int npoint, int nsample, msr3d_stream_t stream);
+/* group_points.cpp:38-62 / group_points_gpu.cu:43-64.  grad_out (B,C,P,S) -> grad_points (B,C,N), zeroed here. */
+int msr3d_group_points_grad_f32(const float *grad_out, const int32_t *idx,
+                                float *grad_points, int B, int C, int N, int npoint,
+                                int nsample, msr3d_stream_t stream);
+/* interpolate.cpp:14-40 / interpolate_gpu.cu:9-59.  unknown (B,n,3), known (B,m,3) -> dist2 (B,n,3), idx (B,n,3). */
+int msr3d_three_nn_f32(const float *unknown, const float *known, float *dist2,
+                       int32_t *idx, int B, int n, int m, msr3d_stream_t stream);
+/* interpolate.cpp:42-69 / interpolate_gpu.cu:72-101.  points (B,c,m), idx/weight (B,n,3) -> out (B,c,n). */
+int msr3d_three_interpolate_f32(const float *points, const int32_t *idx,
+                                const float *weight, float *out, int B, int c, int m,
+                                int n, msr3d_stream_t stream);
+/* interpolate.cpp:71-99 / interpolate_gpu.cu:116-143.  grad_out (B,c,n) -> grad_points (B,c,m), zeroed here. */
+int msr3d_three_interpolate_grad_f32(const float *grad_out, const int32_t *idx,
+                                     const float *weight, float *grad_points, int B,
+                                     int c, int n, int m, msr3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSR3D_B200_H */

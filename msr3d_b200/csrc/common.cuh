@@ -1,0 +1,62 @@
+// Shared host/device helpers for libmsr3d_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/msr3d_b200.h"
+
+#define MSR3D_API extern "C" __attribute__((visibility("default")))
+
+namespace msr3d {
+
+extern thread_local char g_err[512];
+extern std::atomic<unsigned long long> g_launches;
+
+int set_error(int code, const char *fmt, ...);
+
+// Call after every launch: converts a launch failure into a status code.
+inline int check_launch(const char *what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(MSR3D_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return MSR3D_OK;
+}
+
+#define MSR3D_REQUIRE(cond, ...)                                          \
+  do {                                                                    \
+    if (!(cond)) return msr3d::set_error(MSR3D_ERR_INVALID_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define MSR3D_CUDA(call)                                                              \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess)                                                           \
+      return msr3d::set_error(MSR3D_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- squared distance with the contraction the reference binary uses ----
+// nvcc 12.9 compiles `(ax-bx)*(ax-bx) + (ay-by)*(ay-by) + (az-bz)*(az-bz)` of the
+// reference (ball_query_gpu.cu:31-32, sampling_gpu.cu:103-104, interpolate_gpu.cu:35)
+// to  t = dy*dy; t = fma(dx,dx,t); t = fma(dz,dz,t).  Pinned with intrinsics so
+// that this translation unit can never re-contract it differently.
+__device__ __forceinline__ float sqdist3_ref(float ax, float ay, float az, float bx,
+                                             float by, float bz) {
+  const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  float t = __fmul_rn(dy, dy);
+  t = __fmaf_rn(dx, dx, t);
+  return __fmaf_rn(dz, dz, t);
+}
+__device__ __forceinline__ float sqnorm3_ref(float x, float y, float z) {
+  float t = __fmul_rn(y, y);
+  t = __fmaf_rn(x, x, t);
+  return __fmaf_rn(z, z, t);
+}
+
+}  // namespace msr3d

@@ -1,0 +1,23 @@
+// Error reporting, ABI version and launch accounting for libmsr3d_b200.so.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace msr3d {
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int set_error(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+}  // namespace msr3d
+
+MSR3D_API const char *msr3d_last_error(void) { return msr3d::g_err; }
+MSR3D_API int msr3d_abi_version(void) { return 1; }
+MSR3D_API unsigned long long msr3d_launch_count(void) {
+  return msr3d::g_launches.load(std::memory_order_relaxed);
+}

@@ -1,0 +1,101 @@
+"""CPU: the oracle (oracle/*.py + oracle/pointnet2_oracle.c) against fixtures produced by
+the UNMODIFIED reference Python modules (tests/golden/gen_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from msr3d_b200 import synthetic
+from oracle import ext_oracle, modules_oracle as mo
+
+CASES = {
+    "prompter_cfg1": "as_transform_for_objects",
+    "prompter_mid": "as_transform_for_objects",
+    "prompter_as_object": "as_object",
+    "prompter_add_loc": "as_object_add_loc",
+}
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_prompter_forward_matches_reference(golden_dir, sd_spec, name):
+    fx = _load(golden_dir, name)
+    seed = int(fx["seed"])
+    sd = synthetic.make_state_dict(sd_spec, seed)
+    batch = synthetic.make_batch(int(fx["B"]), int(fx["O"]), int(fx["P"]), seed=seed)
+    trace = {}
+    ext_oracle.set_threads(4)
+    with torch.no_grad():
+        tokens, masks = mo.ose3d_situation(sd, batch.as_dict(), situation_type=CASES[name], trace=trace)
+    # index outputs of the native ops: exact
+    np.testing.assert_array_equal(trace["obj_encoder.pcd_net.encoder.0.fps_idx"].numpy(), fx["fps_idx_0"])
+    np.testing.assert_array_equal(trace["obj_encoder.pcd_net.encoder.0.ball_idx"].numpy(), fx["ball_idx_0"])
+    np.testing.assert_array_equal(trace["obj_encoder.pcd_net.encoder.1.fps_idx"].numpy(), fx["fps_idx_1"])
+    np.testing.assert_array_equal(trace["obj_encoder.pcd_net.encoder.1.ball_idx"].numpy(), fx["ball_idx_1"])
+    for i in range(3):
+        np.testing.assert_allclose(trace[f"layer{i}.out"].numpy(), fx[f"layer{i}_out"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(tokens.numpy(), fx["obj_tokens"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_array_equal(masks.numpy(), fx["obj_masks_out"])
+
+
+def test_encoder_outputs_match_reference(golden_dir, sd_spec):
+    fx = _load(golden_dir, "prompter_cfg1")
+    seed = int(fx["seed"])
+    sd = synthetic.make_state_dict(sd_spec, seed)
+    batch = synthetic.make_batch(int(fx["B"]), int(fx["O"]), int(fx["P"]), seed=seed)
+    with torch.no_grad():
+        emb, cls = mo.pcd_obj_encoder(sd, "obj_encoder", batch.obj_fts)
+    scale = np.abs(fx["obj_embeds"]).max()
+    assert np.abs(emb.numpy() - fx["obj_embeds"]).max() <= 1e-5 * scale
+    np.testing.assert_allclose(cls.numpy(), fx["obj_sem_cls"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["prompter_cfg1", "prompter_as_object"])
+def test_prompter_backward_matches_reference(golden_dir, sd_spec, name):
+    fx = _load(golden_dir, name)
+    seed = int(fx["seed"])
+    sd = synthetic.make_state_dict(sd_spec, seed)
+    frozen = lambda k: k.startswith("obj_encoder.") or k == "anchor_size"
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not frozen(k) else v)
+          for k, v in sd.items()}
+    batch = synthetic.make_batch(int(fx["B"]), int(fx["O"]), int(fx["P"]), seed=seed)
+    tokens, _ = mo.ose3d_situation(sd, batch.as_dict(), situation_type=CASES[name])
+    G = torch.randn(tokens.shape, generator=torch.Generator().manual_seed(seed + 77))
+    (tokens * G).sum().backward()
+    names = [str(n) for n in fx["grad_names"]]
+    for n, norm in zip(names, fx["grad_norms"]):
+        g = sd[n].grad
+        assert g is not None, n
+        assert abs(float(g.norm()) - norm) <= 1e-3 * max(norm, 1e-3), n
+    for key in fx.files:
+        if key.startswith("grad:"):
+            n = key[5:]
+            ref = fx[key]
+            tol = 1e-4 * max(np.abs(ref).max(), 1e-3)
+            assert np.abs(sd[n].grad.numpy() - ref).max() <= tol, n
+    # parameters the reference leaves without gradient stay that way
+    with_grad = {n for n in sd if isinstance(sd[n], torch.Tensor) and sd[n].requires_grad and sd[n].grad is not None}
+    assert with_grad == set(names)
+
+
+@pytest.mark.parametrize("fusion", ["cond", "mul", "bias", "ctx", "add"])
+def test_spatial_mha_all_fusions(golden_dir, fusion):
+    fx = _load(golden_dir, "mha_fusions")
+    spec = [tuple(x) for x in json.loads(str(fx[f"{fusion}_spec"]))]
+    sd = {"a." + k: v for k, v in synthetic.make_state_dict(spec, 11).items()}
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 7, 64, generator=g)
+    centers = torch.rand(2, 7, 3, generator=g) * 4
+    np.testing.assert_allclose(centers.numpy(), fx["centers"])
+    pw = mo.pairwise_locs_center(centers)
+    np.testing.assert_allclose(pw.numpy(), fx["pairwise"], rtol=1e-5, atol=1e-6)
+    mask = torch.zeros(2, 7, dtype=torch.bool)
+    mask[1, 5:] = True
+    out, att = mo.spatial_mha(sd, "a", x, pw, mask, 4, fusion)
+    np.testing.assert_allclose(out.numpy(), fx[f"{fusion}_out"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(att.numpy(), fx[f"{fusion}_attn"], rtol=1e-4, atol=1e-6)
