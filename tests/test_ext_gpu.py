@@ -1,0 +1,164 @@
+"""GPU parity of group A (the nine pointnet2._ext operators) through the C ABI.
+
+Checkers: the CPU oracle (always) and the reference's own .cu files compiled for
+sm_100 (oracle/_ref, when present).  int32 outputs must be bit-exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from msr3d_b200 import synthetic
+from oracle import ext_oracle as eo
+from tests import refcuda
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ext():
+    from msr3d_b200 import ext as e
+    return e
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return refcuda.load()
+
+
+def clouds(B, N, seed, kind="mixed"):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, N, 3, generator=g) * 0.35
+    if kind in ("mixed", "dups"):
+        for b in range(0, B, 2):  # duplicated points => exact distance ties
+            uniq = min(N, max(2, N // 4))
+            x[b] = x[b, :uniq][torch.randint(0, uniq, (N,), generator=g)]
+    if kind == "mixed" and B >= 3:
+        x[-1] = 1.0                       # padded object: all-ones points
+        x[-2, : N // 3] *= 0.01           # many points under the 1e-3 norm cut
+    if kind == "grid":                    # lattice: massive ties
+        side = max(2, round(N ** (1 / 3)))
+        pts = torch.stack(torch.meshgrid(*[torch.arange(side)] * 3, indexing="ij"), -1).reshape(-1, 3).float() / side - 0.45
+        x = pts[torch.arange(N) % pts.shape[0]].unsqueeze(0).repeat(B, 1, 1).contiguous()
+    return x.contiguous()
+
+
+FPS_CASES = [(6, 1024, 32, "mixed"), (6, 32, 16, "mixed"), (4, 256, 32, "dups"), (3, 2048, 32, "mixed"),
+             (3, 100, 20, "mixed"), (2, 33, 10, "dups"), (2, 700, 64, "mixed"), (2, 4096, 16, "dups"),
+             (2, 5000, 8, "mixed"), (3, 1024, 32, "grid"), (2, 1, 1, "dups"), (2, 17, 17, "grid")]
+
+
+@pytest.mark.parametrize("B,N,m,kind", FPS_CASES)
+def test_fps_bit_exact(ext, ref, B, N, m, kind):
+    x = clouds(B, N, 7 * N + m, kind)
+    want = eo.furthest_point_sampling(x, m)
+    got = ext.furthest_point_sampling(x.cuda(), m)
+    assert got.dtype == torch.int32 and tuple(got.shape) == (B, m)
+    np.testing.assert_array_equal(got.cpu().numpy(), want.numpy())
+    if ref is not None:
+        r = ref.furthest_point_sampling(x.cuda(), m)
+        np.testing.assert_array_equal(got.cpu().numpy(), r.cpu().numpy())
+
+
+BQ_CASES = [(6, 1024, 32, 0.2, 32), (6, 32, 16, 0.4, 32), (4, 256, 32, 0.2, 32), (3, 2048, 32, 0.2, 32),
+            (3, 100, 7, 0.3, 5), (2, 77, 9, 0.05, 40), (2, 1024, 32, 1e-4, 8), (2, 50, 4, 10.0, 64)]
+
+
+@pytest.mark.parametrize("B,N,M,radius,ns", BQ_CASES)
+def test_ball_query_bit_exact(ext, ref, B, N, M, radius, ns):
+    x = clouds(B, N, 11 * N + M, "mixed")
+    centres = x[:, torch.randperm(N, generator=torch.Generator().manual_seed(M))[:M]].contiguous()
+    centres[:, 0] += 5.0  # an empty ball -> all-zero row
+    want = eo.ball_query(centres, x, radius, ns)
+    got = ext.ball_query(centres.cuda(), x.cuda(), radius, ns)
+    np.testing.assert_array_equal(got.cpu().numpy(), want.numpy())
+    if ref is not None:
+        r = ref.ball_query(centres.cuda(), x.cuda(), radius, ns)
+        np.testing.assert_array_equal(got.cpu().numpy(), r.cpu().numpy())
+
+
+def test_ball_query_points_on_the_sphere(ext, ref):
+    # distances engineered to sit within an ulp of r^2: the FMA contraction decides
+    g = torch.Generator().manual_seed(5)
+    N, M, r = 4096, 8, 0.2
+    d = torch.randn(1, N, 3, generator=g)
+    d = d / d.norm(dim=2, keepdim=True) * r * (1 + (torch.rand(1, N, 1, generator=g) - 0.5) * 4e-7)
+    c = torch.rand(1, M, 3, generator=g)
+    x = (c[:, :1] + d).contiguous()
+    want = eo.ball_query(c.contiguous(), x, r, 64)
+    got = ext.ball_query(c.cuda().contiguous(), x.cuda(), r, 64)
+    np.testing.assert_array_equal(got.cpu().numpy(), want.numpy())
+    if ref is not None:
+        np.testing.assert_array_equal(got.cpu().numpy(), ref.ball_query(c.cuda().contiguous(), x.cuda(), r, 64).cpu().numpy())
+
+
+def test_gather_group_and_grads(ext, ref):
+    g = torch.Generator().manual_seed(9)
+    B, C, N, P, S = 3, 5, 200, 12, 7
+    pts = torch.randn(B, C, N, generator=g)
+    idx2 = torch.randint(0, N, (B, P), generator=g, dtype=torch.int32)
+    idx3 = torch.randint(0, N, (B, P, S), generator=g, dtype=torch.int32)
+    assert torch.equal(ext.gather_points(pts.cuda(), idx2.cuda()).cpu(), eo.gather_points(pts, idx2))
+    assert torch.equal(ext.group_points(pts.cuda(), idx3.cuda()).cpu(), eo.group_points(pts, idx3))
+    go2 = torch.randn(B, C, P, generator=g)
+    go3 = torch.randn(B, C, P, S, generator=g)
+    torch.testing.assert_close(ext.gather_points_grad(go2.cuda(), idx2.cuda(), N).cpu(),
+                               eo.gather_points_grad(go2, idx2, N), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(ext.group_points_grad(go3.cuda(), idx3.cuda(), N).cpu(),
+                               eo.group_points_grad(go3, idx3, N), rtol=1e-5, atol=1e-5)
+    if ref is not None:
+        assert torch.equal(ext.group_points(pts.cuda(), idx3.cuda()), ref.group_points(pts.cuda(), idx3.cuda()))
+        assert torch.equal(ext.gather_points(pts.cuda(), idx2.cuda()), ref.gather_points(pts.cuda(), idx2.cuda()))
+
+
+def test_three_nn_and_interpolate(ext, ref):
+    g = torch.Generator().manual_seed(13)
+    B, n, m, c = 2, 150, 40, 6
+    unknown = torch.randn(B, n, 3, generator=g)
+    known = torch.randn(B, m, 3, generator=g)
+    known[:, 5] = known[:, 4]  # a tie
+    d_w, i_w = eo.three_nn(unknown, known)
+    d_g, i_g = ext.three_nn(unknown.cuda(), known.cuda())
+    np.testing.assert_array_equal(i_g.cpu().numpy(), i_w.numpy())
+    assert torch.equal(d_g.cpu(), d_w)
+    w = torch.rand(B, n, 3, generator=g)
+    w = w / w.sum(2, keepdim=True)
+    feats = torch.randn(B, c, m, generator=g)
+    out_w = eo.three_interpolate(feats, i_w, w)
+    out_g = ext.three_interpolate(feats.cuda(), i_g, w.cuda())
+    assert torch.equal(out_g.cpu(), out_w)
+    go = torch.randn(B, c, n, generator=g)
+    torch.testing.assert_close(ext.three_interpolate_grad(go.cuda(), i_g, w.cuda(), m).cpu(),
+                               eo.three_interpolate_grad(go, i_w, w, m), rtol=1e-5, atol=1e-5)
+    if ref is not None:
+        d_r, i_r = ref.three_nn(unknown.cuda(), known.cuda())
+        assert torch.equal(i_r, i_g) and torch.equal(d_r, d_g)
+        assert torch.equal(ref.three_interpolate(feats.cuda(), i_g, w.cuda()), out_g)
+
+
+def test_ext_contract_errors(ext):
+    x = torch.randn(2, 64, 3)
+    with pytest.raises(RuntimeError, match="CPU not supported"):
+        ext.furthest_point_sampling(x, 4)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        ext.furthest_point_sampling(torch.randn(2, 3, 64).cuda().transpose(1, 2), 4)
+    with pytest.raises(RuntimeError, match="int tensor"):
+        ext.gather_points(torch.randn(2, 3, 64).cuda(), torch.zeros(2, 4, dtype=torch.int64).cuda())
+    from msr3d_b200 import _C
+    with pytest.raises(_C.Msr3dError):
+        ext.furthest_point_sampling(torch.randn(1, 9000, 3).cuda(), 4)  # > 8192 points: status, not exit()
+
+
+def test_scene_distribution_full_size(ext, ref):
+    """config-2 sized batch (240 clouds x 1024): CUDA vs oracle on the real input distribution."""
+    batch = synthetic.make_batch(4, 60, 1024, seed=2)
+    xyz = batch.obj_fts[..., :3].reshape(240, 1024, 3).contiguous()
+    eo.set_threads(8)
+    want = eo.furthest_point_sampling(xyz, 32)
+    got = ext.furthest_point_sampling(xyz.cuda(), 32)
+    np.testing.assert_array_equal(got.cpu().numpy(), want.numpy())
+    new_xyz = torch.gather(xyz, 1, want.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    np.testing.assert_array_equal(ext.ball_query(new_xyz.cuda(), xyz.cuda(), 0.2, 32).cpu().numpy(),
+                                  eo.ball_query(new_xyz, xyz, 0.2, 32).numpy())
+    if ref is not None:
+        np.testing.assert_array_equal(got.cpu().numpy(), ref.furthest_point_sampling(xyz.cuda(), 32).cpu().numpy())
