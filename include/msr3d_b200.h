@@ -87,6 +87,53 @@ int msr3d_three_interpolate_grad_f32(const float *grad_out, const int32_t *idx,
                                      const float *weight, float *grad_points, int B,
                                      int c, int n, int m, msr3d_stream_t stream);
 
+/* ------------------------------------------------------------------ group B
+ * PointNet++ set abstraction on the tensor cores (tcgen05, bf16 hi/lo split
+ * operands, f32 accumulation in TMEM).  Replaces _PointnetSAModuleBase.forward
+ * (pointnet2_modules.py:34-75), QueryAndGroup (pointnet2_utils.py:314-373) and
+ * SharedMLP (pytorch_utils.py:11-36) with BatchNorm in eval mode folded into
+ * the packed weights (scale) and the bias (shift).                           */
+
+/* Bytes of the packed image of an (N x K) weight for tiles of BN rows x BK k. */
+long long msr3d_packed_weight_bytes(int N, int K, int BN, int BK);
+/* Packs W (element (n,k) at W[n*stride_n + k*stride_k]) into the shared-memory
+ * image tcgen05.mma consumes: blocks [n_tile][k_block] of (BN x BK) bf16 hi tile
+ * followed by the lo tile.  row_scale (N, nullable) multiplies row n first
+ * (BatchNorm fold); col_perm (Kp int32, nullable) maps packed column -> source
+ * column, -1 = zero.  nn.Linear / 1x1-conv weights are (N=out, K=in).         */
+int msr3d_pack_weight_f32(const float *W, int N, int K, long long stride_n, long long stride_k,
+                          const float *row_scale, const int32_t *col_perm, int BN, int BK,
+                          void *packed, msr3d_stream_t stream);
+/* out[M,N] (+)= act(A[M,K] * W^T + bias), W packed with BN=128, BK=64.
+ * A element (m,k) at A[m*stride_am + k*stride_ak].  act: 0 none, 1 ReLU, 2 GELU(erf).
+ * pool > 1: max over groups of `pool` consecutive rows (power of two <= 32), out is
+ * (M/pool, N).  split: 3 = fp32-grade split-bf16, 1 = single bf16 pass.
+ * accumulate: out += result (act 0, no pool).  Replaces cuDNN conv1x1 / cuBLAS
+ * calls of pytorch_utils.py:157-188 and modules/layers/pointnet.py:53,63.    */
+int msr3d_linear_tc_f32(const float *A, long long stride_am, long long stride_ak, int M, int K,
+                        const void *packed_w, const float *bias, float *out, long long ldo, int N,
+                        int act, int pool, int split, int accumulate, msr3d_stream_t stream);
+/* FPS + centre gather + ball query of one SA level (pointnet2_modules.py:54-58,
+ * pointnet2_utils.py:331).  xyz: (B,N,ld) records whose first 3 floats are the
+ * coordinates.  Outputs fps_idx (B,m) i32, new_xyz (B,m,3), ball_idx (B,m,nsample) i32. */
+int msr3d_sa_group_f32(const float *xyz, int ld, int B, int N, int m, float radius, int nsample,
+                       int32_t *fps_idx, float *new_xyz, int32_t *ball_idx, msr3d_stream_t stream);
+/* Writes xyz (rows,3) into columns [col0,col0+3) of a (rows, ld_dst) matrix: the xyz
+ * channels GroupAll concatenates (pointnet2_utils.py:407), in the operand of SA3. */
+int msr3d_scatter_xyz_cols_f32(const float *xyz, float *dst, long long ld_dst, int col0, int rows,
+                               msr3d_stream_t stream);
+/* Gather + 3 x (conv1x1+BN+ReLU) + max-pool over nsample as one kernel.
+ * feat (B,Nsrc,ld_feat) with nfeat channels used, xyz (B,Nsrc,ld_xyz), new_xyz (B,npoint,3),
+ * ball_idx (B,npoint,32).  Layer-1 weights are packed with K order [feat | dxyz | 0]
+ * (BN = min(c,128), BK = padded K of that layer).  out (B,npoint,ld_out), point-major.
+ * Fused instances: (nfeat+3 <= 16, 64,64,128) and (nfeat+3 in (128,144], 128,128,256);
+ * anything else returns MSR3D_ERR_UNSUPPORTED (callers use the layer-wise path). */
+int msr3d_sa_mlp_fused_f32(const float *feat, int ld_feat, int nfeat, const float *xyz, int ld_xyz,
+                           const float *new_xyz, const int32_t *ball_idx, int B, int Nsrc,
+                           int npoint, int nsample, const void *w1, const void *w2, const void *w3,
+                           const float *b1, const float *b2, const float *b3, int c1, int c2, int c3,
+                           float *out, long long ld_out, int split, msr3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

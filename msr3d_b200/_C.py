@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libmsr3d_b200.so")
 c_int = ctypes.c_int
 c_float = ctypes.c_float
 c_void_p = ctypes.c_void_p
+c_ll = ctypes.c_longlong
 
 
 class Msr3dError(RuntimeError):
@@ -47,6 +48,14 @@ _PROTOS = {
     "msr3d_three_nn_f32": [_P, _P, _P, _P, c_int, c_int, c_int, _P],
     "msr3d_three_interpolate_f32": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
     "msr3d_three_interpolate_grad_f32": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
+    # group B
+    "msr3d_pack_weight_f32": [_P, c_int, c_int, c_ll, c_ll, _P, _P, c_int, c_int, _P, _P],
+    "msr3d_linear_tc_f32": [_P, c_ll, c_ll, c_int, c_int, _P, _P, _P, c_ll, c_int, c_int, c_int,
+                            c_int, c_int, _P],
+    "msr3d_sa_group_f32": [_P, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P],
+    "msr3d_scatter_xyz_cols_f32": [_P, _P, c_ll, c_int, c_int, _P],
+    "msr3d_sa_mlp_fused_f32": [_P, c_int, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int,
+                               _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_ll, c_int, _P],
 }
 
 
@@ -75,6 +84,8 @@ def lib() -> ctypes.CDLL:
         _lib.msr3d_last_error.restype = ctypes.c_char_p
         _lib.msr3d_abi_version.restype = c_int
         _lib.msr3d_launch_count.restype = ctypes.c_ulonglong
+        _lib.msr3d_packed_weight_bytes.restype = ctypes.c_longlong
+        _lib.msr3d_packed_weight_bytes.argtypes = [c_int, c_int, c_int, c_int]
         _bind(_lib, _PROTOS)
     return _lib
 

@@ -44,7 +44,7 @@ __device__ __forceinline__ int fps_unrank(uint32_t r, int log2bs, int nper) {
 // (double-buffered partials), a redundant NW-way merge in every thread.
 template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS)
-fps_kernel(const float *__restrict__ xyz, int32_t *__restrict__ idx,
+fps_kernel(const float *__restrict__ xyz, int ld, int32_t *__restrict__ idx,
            float *__restrict__ new_xyz, int N, int m, int log2bs, int nper) {
   extern __shared__ float s_xyz[];  // N*3 floats, then m int32 picks
   int32_t *s_pick = reinterpret_cast<int32_t *>(s_xyz + (size_t)N * 3);
@@ -52,8 +52,18 @@ fps_kernel(const float *__restrict__ xyz, int32_t *__restrict__ idx,
   __shared__ uint2 s_part[2][NW];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float *cloud = xyz + (size_t)blockIdx.x * N * 3;
-  for (int i = tid; i < N * 3; i += THREADS) s_xyz[i] = cloud[i];
+  // `ld` floats per point (3 for a packed xyz tensor, 6 when xyz is the head of an
+  // (x,y,z,r,g,b) record: the break_up_pc copy of modules/layers/pointnet.py:6-19 is skipped)
+  const float *cloud = xyz + (size_t)blockIdx.x * N * ld;
+  if (ld == 3) {
+    for (int i = tid; i < N * 3; i += THREADS) s_xyz[i] = cloud[i];
+  } else {
+    for (int i = tid; i < N; i += THREADS) {
+      s_xyz[i * 3 + 0] = cloud[(size_t)i * ld + 0];
+      s_xyz[i * 3 + 1] = cloud[(size_t)i * ld + 1];
+      s_xyz[i * 3 + 2] = cloud[(size_t)i * ld + 2];
+    }
+  }
   __syncthreads();
 
   float px[PPT], py[PPT], pz[PPT], dmin[PPT];
@@ -134,9 +144,9 @@ static int ilog2_floor(int v) {
 }
 
 // Host side of FPS, shared with the fused SA entry points (sa_fused.cu).
-int launch_fps(const float *xyz, int32_t *idx, float *new_xyz, int B, int N, int m,
+int launch_fps(const float *xyz, int ld, int32_t *idx, float *new_xyz, int B, int N, int m,
                cudaStream_t stream) {
-  MSR3D_REQUIRE(B >= 0 && N >= 1 && m >= 0, "fps: bad sizes B=%d N=%d m=%d", B, N, m);
+  MSR3D_REQUIRE(B >= 0 && N >= 1 && m >= 0 && ld >= 3, "fps: bad sizes B=%d N=%d m=%d ld=%d", B, N, m, ld);
   if (B == 0 || m == 0) return MSR3D_OK;
   // reference block size: largest power of two <= N, capped at 512 (cuda_utils.h:13-19)
   int log2bs = ilog2_floor(N);
@@ -149,7 +159,7 @@ int launch_fps(const float *xyz, int32_t *idx, float *new_xyz, int B, int N, int
     if (smem > 48 * 1024)                                                                 \
       MSR3D_CUDA(cudaFuncSetAttribute(fps_kernel<T, P>,                                   \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    fps_kernel<T, P><<<B, T, smem, stream>>>(xyz, idx, new_xyz, N, m, log2bs, nper);      \
+    fps_kernel<T, P><<<B, T, smem, stream>>>(xyz, ld, idx, new_xyz, N, m, log2bs, nper);  \
   } while (0)
   if (N <= 32) FPS_LAUNCH(32, 1);
   else if (N <= 64) FPS_LAUNCH(32, 2);
@@ -173,7 +183,7 @@ int launch_fps(const float *xyz, int32_t *idx, float *new_xyz, int B, int N, int
 // ----------------------------------------------------------------------------
 constexpr int kBqWarps = 4;
 __global__ void __launch_bounds__(kBqWarps * 32)
-ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz,
+ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int ld,
                   int32_t *__restrict__ idx, int N, int M, float radius2, int nsample) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * kBqWarps + warp;
@@ -181,14 +191,15 @@ ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
   if (j >= M) return;
   const float *q = new_xyz + ((size_t)b * M + j) * 3;
   const float qx = q[0], qy = q[1], qz = q[2];
-  const float *P = xyz + (size_t)b * N * 3;
+  const float *P = xyz + (size_t)b * N * ld;
   int32_t *row = idx + ((size_t)b * M + j) * nsample;
   int cnt = 0, first = -1;
   for (int base = 0; base < N && cnt < nsample; base += 32) {
     const int k = base + lane;
     bool hit = false;
     if (k < N) {
-      const float d2 = sqdist3_ref(qx, qy, qz, P[k * 3 + 0], P[k * 3 + 1], P[k * 3 + 2]);
+      const float *pk = P + (size_t)k * ld;
+      const float d2 = sqdist3_ref(qx, qy, qz, pk[0], pk[1], pk[2]);
       hit = d2 < radius2;  // strict, NaN rejects
     }
     const unsigned bal = __ballot_sync(0xffffffffu, hit);
@@ -326,7 +337,7 @@ using namespace msr3d;
 MSR3D_API int msr3d_furthest_point_sampling_f32(const float *xyz, int32_t *idx, int B, int N,
                                                 int m, msr3d_stream_t stream) {
   MSR3D_REQUIRE(xyz && idx, "fps: null pointer");
-  return launch_fps(xyz, idx, nullptr, B, N, m, (cudaStream_t)stream);
+  return launch_fps(xyz, 3, idx, nullptr, B, N, m, (cudaStream_t)stream);
 }
 
 MSR3D_API int msr3d_gather_points_f32(const float *points, const int32_t *idx, float *out,
@@ -364,10 +375,25 @@ MSR3D_API int msr3d_ball_query_f32(const float *new_xyz, const float *xyz, int32
   if (B == 0 || M == 0 || nsample == 0) return MSR3D_OK;
   const float radius2 = radius * radius;  // ball_query_gpu.cu:22, f32 product
   dim3 grid(ceil_div(M, kBqWarps), B);
-  ball_query_kernel<<<grid, kBqWarps * 32, 0, (cudaStream_t)stream>>>(new_xyz, xyz, idx, N, M,
+  ball_query_kernel<<<grid, kBqWarps * 32, 0, (cudaStream_t)stream>>>(new_xyz, xyz, 3, idx, N, M,
                                                                       radius2, nsample);
   return check_launch("ball_query");
 }
+
+// Strided variants used by the fused encoder (sa_fused.cu): xyz is the head of a
+// record of `ld` floats per point.
+namespace msr3d {
+int launch_ball_query(const float *new_xyz, const float *xyz, int ld, int32_t *idx, int B, int N,
+                      int M, float radius, int nsample, cudaStream_t stream) {
+  MSR3D_REQUIRE(B >= 0 && N >= 1 && M >= 0 && nsample >= 0 && ld >= 3 && B <= 65535,
+                "ball_query: bad sizes");
+  if (B == 0 || M == 0 || nsample == 0) return MSR3D_OK;
+  const float radius2 = radius * radius;
+  dim3 grid(ceil_div(M, kBqWarps), B);
+  ball_query_kernel<<<grid, kBqWarps * 32, 0, stream>>>(new_xyz, xyz, ld, idx, N, M, radius2, nsample);
+  return check_launch("ball_query");
+}
+}  // namespace msr3d
 
 MSR3D_API int msr3d_group_points_f32(const float *points, const int32_t *idx, float *out, int B,
                                      int C, int N, int npoint, int nsample,
