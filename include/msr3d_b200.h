@@ -113,6 +113,35 @@ int msr3d_pack_weight_f32(const float *W, int N, int K, long long stride_n, long
 int msr3d_linear_tc_f32(const float *A, long long stride_am, long long stride_ak, int M, int K,
                         const void *packed_w, const float *bias, float *out, long long ldo, int N,
                         int act, int pool, int split, int accumulate, msr3d_stream_t stream);
+/* General tensor-core GEMM with fp32 (strided) operands on both sides:
+ *   out[M,N] (+)= epilogue( act( xa(A)[M,K] * xb(B)[N,K]^T + bias ) ) + residual
+ * Used by the spatial transformer's forward and backward (weights and their transposes are
+ * read in place through strides; nothing is pre-packed).  Element (m,k) of A at
+ * A[m*stride_am + k*stride_ak]; element (n,k) of B at B[n*stride_bn + k*stride_bk].
+ *   a_xform / b_xform: 0 none, 1 GELU, 2 GELU then dropout(site, memory offset as counter)
+ *   epilogue: 0 plain, 1 multiply by gelu'(aux[m,n]) * dropout_mask(epi_site)  (FFN backward)
+ *   accumulate: 0 store, 1 out += (single CTA per element), 2 atomicAdd (required for ksplit > 1)
+ *   ksplit: number of CTAs along K (split-K)
+ *   split: 1 = one bf16 MMA per K slice, 3 = two-way split operands (hh+hm+mh, ~2^-17),
+ *          6 = three-way split (adds hl+lh+mm, fp32-grade; used for weight gradients) */
+typedef struct msr3d_gemm_desc {
+  const float *A; long long stride_am, stride_ak;
+  const float *B; long long stride_bn, stride_bk;
+  const float *bias;       /* [N] or NULL */
+  const float *residual;   /* [M, ld_residual] or NULL */
+  long long ld_residual;
+  const float *aux;        /* [M, ld_aux] for epilogue 1 */
+  long long ld_aux;
+  float *out; long long ld_out;
+  int M, N, K;
+  int act, split, accumulate, epilogue, ksplit;
+  int a_xform, b_xform;
+  unsigned a_site, b_site, epi_site;
+  float dropout_p;
+  unsigned long long seed;
+  const unsigned long long *seed_ptr; /* optional device counter added to seed (graph replays) */
+} msr3d_gemm_desc;
+int msr3d_gemm_tc_f32(const msr3d_gemm_desc *desc, msr3d_stream_t stream);
 /* FPS + centre gather + ball query of one SA level (pointnet2_modules.py:54-58,
  * pointnet2_utils.py:331).  xyz: (B,N,ld) records whose first 3 floats are the
  * coordinates.  Outputs fps_idx (B,m) i32, new_xyz (B,m,3), ball_idx (B,m,nsample) i32. */
@@ -133,6 +162,76 @@ int msr3d_sa_mlp_fused_f32(const float *feat, int ld_feat, int nfeat, const floa
                            int npoint, int nsample, const void *w1, const void *w2, const void *w3,
                            const float *b1, const float *b2, const float *b3, int c1, int c2, int c3,
                            float *out, long long ld_out, int split, msr3d_stream_t stream);
+
+/* ------------------------------------------------------------------ group C
+ * Situated spatial-attention transformer, everything that is not a GEMM
+ * (modules/layers/transformers.py:200-252,314-329; modules/utils.py:60-137;
+ * model/ose3d_situation.py:31-59,399-410).  Hidden size 256, head dim 32, L <= 128.
+ * Dropout masks are Philox(seed, site, element offset) and are regenerated, never stored. */
+
+/* calc_pairwise_locs('center', dim 5) + agent-frame Fourier features.  loc (B,L,6);
+ * anchor (B,3), quat (B,4 xyzw) used when use_agent_frame; pw (B,L,L,5), ff (B*L,64), sz (B*L,3). */
+int msr3d_spatial_geometry_f32(const float *loc, const float *anchor, const float *quat, int B, int L,
+                               int dist_norm, int use_agent_frame, float *pw, float *ff, float *sz,
+                               msr3d_stream_t stream);
+/* qpos = LN_l(h1) + LN_s(Ws sz + bs); qpos0 = qpos + extra_a + extra_b (ose3d_situation.py:399-404,359-363). */
+int msr3d_qpos_fwd_f32(const float *h1, const float *sz, int M, const float *Ws, const float *bs,
+                       const float *gamma_l, const float *beta_l, const float *gamma_s,
+                       const float *beta_s, const float *extra_a, const float *extra_b, float *xhat_l,
+                       float *rstd_l, float *xhat_s, float *rstd_s, float *qpos, float *qpos0,
+                       msr3d_stream_t stream);
+/* dq, dq1, dq2: per-layer gradients wrt qpos, summed on load (dq1/dq2 nullable). */
+int msr3d_qpos_bwd_f32(const float *dq, const float *dq1, const float *dq2, const float *sz, int M,
+                       const float *gamma_l,
+                       const float *gamma_s, const float *xhat_l, const float *rstd_l,
+                       const float *xhat_s, const float *rstd_s, float *dh1, float *dgamma_l,
+                       float *dbeta_l, float *dgamma_s, float *dbeta_s, float *dWs, float *dbs,
+                       float *dbl, msr3d_stream_t stream);
+/* Attention core with `cond` fusion (transformers.py:205-248).  qkvc (B*L, ldq) rows
+ * [q | k | v | cond(H x 6)]; key_pad (B,L) bytes, 1 = padded key (nullable).
+ * Outputs P, LOC (B,H,L,L) and ctx (B*L, ldc). */
+int msr3d_attn_fwd_f32(const float *qkvc, int ldq, const float *pw, const unsigned char *key_pad, int B,
+                       int L, int H, float *P, float *LOC, float *ctx, int ldc, msr3d_stream_t stream);
+int msr3d_attn_bwd_f32(const float *dctx, int ldc, const float *qkvc, int ldq, const float *pw,
+                       const float *P, const float *LOC, int B, int L, int H, float *dqkvc,
+                       msr3d_stream_t stream);
+/* y2 = LN_1(x + drop_1(LN_a(drop_fc(o) + x)))  — transformers.py:250-251 then :324-325. */
+int msr3d_attn_tail_fwd_f32(const float *o, const float *x, int M, const float *gamma_a,
+                            const float *beta_a, const float *gamma_1, const float *beta_1,
+                            unsigned long long seed, const unsigned long long *seed_ptr, float p,
+                            unsigned site_fc, unsigned site_1, float *xhat_a, float *rstd_a, float *xhat_1, float *rstd_1, float *y2,
+                            msr3d_stream_t stream);
+int msr3d_attn_tail_bwd_f32(const float *dy2, int M, const float *gamma_a, const float *gamma_1,
+                            unsigned long long seed, const unsigned long long *seed_ptr, float p,
+                            unsigned site_fc, unsigned site_1, const float *xhat_a, const float *rstd_a, const float *xhat_1,
+                            const float *rstd_1, float *dx, float *d_o, float *dgamma_a, float *dbeta_a,
+                            float *dgamma_1, float *dbeta_1, float *dbias_o, msr3d_stream_t stream);
+/* y3 = LN_2(y2 + drop_2(f)); x_next = y3 + add  — transformers.py:326-328, ose3d_situation.py:409-410. */
+int msr3d_ffn_tail_fwd_f32(const float *f, const float *y2, int M, const float *gamma_2,
+                           const float *beta_2, unsigned long long seed,
+                           const unsigned long long *seed_ptr, float p, unsigned site_2,
+                           const float *add, float *xhat_2, float *rstd_2, float *y3, float *x_next,
+                           msr3d_stream_t stream);
+int msr3d_ffn_tail_bwd_f32(const float *dy3, int M, const float *gamma_2, unsigned long long seed,
+                           const unsigned long long *seed_ptr, float p, unsigned site_2, const float *xhat_2, const float *rstd_2,
+                           float *dy2, float *df, float *dgamma_2, float *dbeta_2, float *dbias_2,
+                           msr3d_stream_t stream);
+/* Test hook: the multiplicative dropout mask (0 or 1/(1-p)) applied at `site` to offsets [0,n). */
+int msr3d_dropout_mask_f32(unsigned long long seed, const unsigned long long *seed_ptr, float p,
+                           unsigned site, long long n, float *out, msr3d_stream_t stream);
+/* dst_i[n] += sum_m src[m, n] for up to three destinations (dst1, dst2 nullable). */
+int msr3d_colsum_add_f32(const float *src, long long ld, int M, int N, float *dst0, float *dst1,
+                         float *dst2, msr3d_stream_t stream);
+
+/* ------------------------------------------------------------------ group D
+ * Global-norm clip + AdamW on one flat buffer (trainer/leo_trainer.py:192-195,
+ * optim/build.py:7-17).  state: 8 device floats {sumsq, step, lr, beta1, beta2, eps,
+ * weight_decay, max_norm}; ticket: one zeroed device uint32; seed_counter (nullable): device
+ * uint64 incremented once per step (the dropout seed offset).  Elements [0, n_decay) decay. */
+int msr3d_adamw_clip_step_f32(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
+                              long long n, long long n_decay, float grad_scale, float *state,
+                              unsigned int *ticket, unsigned long long *seed_counter,
+                              msr3d_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,7 @@
 //   D : 128 lanes x BN columns of TMEM; epilogue = tcgen05.ld -> bias -> act
 //       (-> row-group max) -> global.
 #include "common.cuh"
+#include "rng.cuh"
 #include "umma.cuh"
 
 namespace msr3d {
@@ -73,27 +74,129 @@ pack_weight_kernel(const float *__restrict__ W, int N, int K, long long sn, long
   }
 }
 
+// NOTE on code size: these GEMMs are tiny (M ~ 240 rows) and latency bound.  The first version of
+// this kernel was 64 KB of fully unrolled SASS executed once per launch and spent ~95% of its time
+// in instruction-fetch stalls (ncu: stall_no_instructions).  Everything that is not on the
+// critical path is therefore kept out of line (__noinline__) or in rolled loops.
+
+// Operand element transforms applied while loading fp32 operands (before the bf16 split).
+enum { XF_NONE = 0, XF_GELU = 1, XF_GELU_DROPOUT = 2 };
+// Epilogue modes.
+enum { EPI_PLAIN = 0, EPI_GELU_GRAD = 1 };
+
+struct GemmArgs {
+  const float *A; long long sam, sak; int a_xform; unsigned a_site;
+  const uint8_t *PW;                                   // packed B (b_mode 0)
+  const float *Bf; long long sbn, sbk; int b_xform; unsigned b_site;  // fp32 B (b_mode 1)
+  int b_mode;
+  int M, N, K, Kp;
+  const float *bias;                                   // [N] nullable
+  const float *res; long long ldr;                     // residual [M,N] added after act, nullable
+  const float *aux; long long ldaux; unsigned epi_site;  // EPI_GELU_GRAD: pre-activation u[M,N]
+  float *out; long long ldo;
+  int act, pool, split, accumulate, epi;               // accumulate: 0 store, 1 +=, 2 atomicAdd
+  Dropout drop;
+};
+
+__device__ __noinline__ float act_slow(float v, int act) {  // GELU (erf) is a long polynomial
+  return act == ACT_GELU ? gelu_f(v) : fmaxf(v, 0.f);
+}
 __device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_NONE) return v;
   if (act == ACT_RELU) return fmaxf(v, 0.f);
-  if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  return act_slow(v, act);
+}
+__device__ __noinline__ float xform_slow(float v, int mode, const Dropout *d, unsigned site, long long off) {
+  v = gelu_f(v);
+  if (mode == XF_GELU_DROPOUT) v = d->apply(v, (uint64_t)off, site);
   return v;
+}
+__device__ __noinline__ float gelu_grad_masked(float x, float u, const Dropout *d, unsigned site, long long off) {
+  return x * gelu_grad_f(u) * d->mask((uint64_t)off, site);
+}
+
+// Loads an (R x 64) fp32 operand chunk (rows r0.., k from k0), applies the transform, splits to
+// bf16 and stores it in the canonical layout: tiles [h | m | l] `tile_bytes` apart (l only when
+// three_way).  Thread t: row = t % R, the threads sharing a row split the eight 8-wide k groups.
+// Lanes map to consecutive rows: conflict-free 16 B shared stores, and for transposed operands
+// (k stride != 1, row stride 1) fully coalesced global loads.
+template <int R>
+__device__ __noinline__ void load_operand_chunk(const float *__restrict__ base, long long sr, long long sk,
+                                                int r0, int rmax, int k0, int K, int xmode,
+                                                const Dropout *drop, unsigned site, uint8_t *tiles,
+                                                uint32_t tile_bytes, bool three_way, int tid) {
+  constexpr int kThreadsPerRow = 256 / R;       // R = 128 -> 2
+  constexpr int kPer = 8 / kThreadsPerRow;      // 8-wide k groups per thread
+  const int row = tid % R, part = tid / R;
+  const bool row_ok = (r0 + row) < rmax;
+  const float *rp = base + (long long)(r0 + row) * sr;
+  const bool vec_ok = (sk == 1) && ((sr & 3) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+  float v[kPer][8];
+  // all global loads first (memory-level parallelism), then convert
+#pragma unroll
+  for (int c = 0; c < kPer; ++c) {
+    const int kk = k0 + (part * kPer + c) * 8;
+    if (row_ok && vec_ok && kk + 8 <= K) {
+      const float4 a = *reinterpret_cast<const float4 *>(rp + kk);
+      const float4 b = *reinterpret_cast<const float4 *>(rp + kk + 4);
+      v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
+      v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[c][j] = (row_ok && kk + j < K) ? rp[(long long)(kk + j) * sk] : 0.f;
+    }
+  }
+  if (xmode != XF_NONE) {
+#pragma unroll
+    for (int c = 0; c < kPer; ++c) {
+      const int kk = k0 + (part * kPer + c) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (row_ok && kk + j < K)
+          v[c][j] = xform_slow(v[c][j], xmode, drop, site, (long long)(r0 + row) * sr + (long long)(kk + j) * sk);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kPer; ++c) {
+    uint32_t h[4], m[4], l[4];
+    const uint32_t off = chunk_offset(R, row, part * kPer + c);
+    if (three_way) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split_pack2_3way(v[c][2 * j], v[c][2 * j + 1], h[j], m[j], l[j]);
+      *reinterpret_cast<uint4 *>(tiles + 2 * tile_bytes + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split_pack2(v[c][2 * j], v[c][2 * j + 1], h[j], m[j]);
+    }
+    *reinterpret_cast<uint4 *>(tiles + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(tiles + tile_bytes + off) = make_uint4(m[0], m[1], m[2], m[3]);
+  }
+}
+
+// 32 lanes x 8 columns of f32 (smaller epilogue step than x32: the column loop stays rolled)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 
 // ---------------------------------------------------------------------------
-// The GEMM.  256 threads: every thread loads/splits A; thread 0 drives TMA and
+// The GEMM.  256 threads: every thread loads/splits operands; thread 0 drives TMA and
 // the tensor core; all 8 warps run the epilogue (warp w owns TMEM lanes
-// 32*(w%4).., column half w/4).
+// 32*(w%4).., column half w/4).  gridDim = (M tiles, N tiles, K splits).
 // ---------------------------------------------------------------------------
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
-linear_tc_kernel(const float *__restrict__ A, long long sam, long long sak, int M, int K,
-                 const uint8_t *__restrict__ PW, int Kp, const float *__restrict__ bias,
-                 float *__restrict__ out, long long ldo, int N, int act, int pool, int split,
-                 int accumulate) {
+linear_tc_kernel(GemmArgs g) {
+  g.drop.resolve();
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr uint32_t kATile = kTileM * kChunkK * 2;  // one of hi / lo
-  constexpr uint32_t kBBlock = BN * kChunkK * 4;     // hi + lo
-  constexpr uint32_t kStage = 2 * kATile + kBBlock;
+  constexpr uint32_t kATile = kTileM * kChunkK * 2;  // one of h / m / l
+  constexpr uint32_t kBTile = BN * kChunkK * 2;
+  constexpr uint32_t kBBlock = 2 * kBTile;           // h + m (packed image)
+  // stage = A tiles [h | m | l] then B tiles [h | m | l]; the third tiles only exist for split 6
+  constexpr uint32_t kAOff = 0, kBOff = 3 * kATile;
+  constexpr uint32_t kStage = 3 * kATile + 3 * kBTile;
   __shared__ __align__(8) uint64_t b_full[2];
   __shared__ __align__(8) uint64_t mma_done[2];
   __shared__ uint32_t s_tmem;
@@ -101,7 +204,13 @@ linear_tc_kernel(const float *__restrict__ A, long long sam, long long sak, int 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.x * kTileM;
   const int nt = blockIdx.y;
-  const int nkc = Kp / kChunkK;
+  const int nkc_total = g.Kp / kChunkK;
+  // K split: contiguous chunk ranges per blockIdx.z
+  const int per = (nkc_total + gridDim.z - 1) / gridDim.z;
+  const int kc_begin = blockIdx.z * per;
+  const int kc_end = min(nkc_total, kc_begin + per);
+  const int nkc = kc_end - kc_begin;
+  if (nkc <= 0) return;  // uniform per CTA: nothing allocated yet
 
   if (tid == 0) {
     mbar_init(&b_full[0], 1);
@@ -116,118 +225,139 @@ linear_tc_kernel(const float *__restrict__ A, long long sam, long long sak, int 
   fence_after_sync();
   const uint32_t tmem_d = s_tmem;
   const uint32_t idesc = make_idesc_bf16(kTileM, BN);
+  const bool three_way = g.split == 6;
 
-  const int row = tid & 127;        // A row handled by this thread
-  const int khalf = tid >> 7;       // which 32-wide half of the 64-wide chunk
-  const bool row_ok = (m0 + row) < M;
-  const float *arow = A + (long long)(m0 + row) * sam;
-  const bool vec_ok = (sak == 1) && ((sam & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-
-  for (int kc = 0; kc < nkc; ++kc) {
-    const int s = kc & 1;
+#pragma unroll 1
+  for (int i = 0; i < nkc; ++i) {
+    const int kc = kc_begin + i;
+    const int s = i & 1;
     uint8_t *st = smem + (size_t)s * kStage;
-    if (kc >= 2) mbar_wait(&mma_done[s], ((kc >> 1) - 1) & 1);  // stage free again
-    if (tid == 0) {
-      mbar_expect_tx(&b_full[s], kBBlock);
-      bulk_g2s(st + 2 * kATile, PW + ((size_t)nt * nkc + kc) * kBBlock, kBBlock, &b_full[s]);
-    }
-    // ---- A chunk: 4 x (8 floats -> 16 B hi + 16 B lo) per thread
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int kchunk = khalf * 4 + c;  // 0..7 inside the stage
-      const int k0 = kc * kChunkK + kchunk * 8;
-      float v[8];
-      if (row_ok && vec_ok && k0 + 8 <= K) {
-        const float4 a = *reinterpret_cast<const float4 *>(arow + k0);
-        const float4 b = *reinterpret_cast<const float4 *>(arow + k0 + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          v[j] = (row_ok && k0 + j < K) ? arow[(long long)(k0 + j) * sak] : 0.f;
+    if (i >= 2) mbar_wait(&mma_done[s], ((i >> 1) - 1) & 1);  // stage free again
+    if (g.b_mode == 0) {
+      if (tid == 0) {
+        mbar_expect_tx(&b_full[s], kBBlock);
+        bulk_g2s(st + kBOff, g.PW + ((size_t)nt * nkc_total + kc) * kBBlock, kBBlock, &b_full[s]);
       }
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) split_pack2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-      const uint32_t off = chunk_offset(kTileM, row, kchunk);
-      *reinterpret_cast<uint4 *>(st + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4 *>(st + kATile + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    } else {
+      load_operand_chunk<BN>(g.Bf, g.sbn, g.sbk, nt * BN, g.N, kc * kChunkK, g.K, g.b_xform, &g.drop,
+                             g.b_site, st + kBOff, kBTile, three_way, tid);
     }
+    load_operand_chunk<kTileM>(g.A, g.sam, g.sak, m0, g.M, kc * kChunkK, g.K, g.a_xform, &g.drop,
+                               g.a_site, st + kAOff, kATile, three_way, tid);
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
-      mbar_wait(&b_full[s], (kc >> 1) & 1);
+      if (g.b_mode == 0) mbar_wait(&b_full[s], (i >> 1) & 1);
       fence_after_sync();
-      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + kATile;
-      const uint32_t b_hi = a_hi + 2 * kATile, b_lo = b_hi + BN * kChunkK * 2;
-#pragma unroll
+      const uint32_t a_h = smem_u32(st) + kAOff, b_h = smem_u32(st) + kBOff;
+      // products issued smallest-first: (m,m) (h,l) (l,h) (h,m) (m,h) (h,h); tile index 0=h 1=m 2=l
+      const int n_terms = g.split == 6 ? 6 : (g.split == 3 ? 3 : 1);
+#pragma unroll 1
       for (int ks = 0; ks < kChunkK / 16; ++ks) {
-        const uint64_t dah = kslice_desc(a_hi, kTileM, ks), dal = kslice_desc(a_lo, kTileM, ks);
-        const uint64_t dbh = kslice_desc(b_hi, BN, ks), dbl = kslice_desc(b_lo, BN, ks);
-        mma_bf16(tmem_d, dah, dbh, idesc, (kc | ks) ? 1u : 0u);
-        if (split == 3) {
-          mma_bf16(tmem_d, dah, dbl, idesc, 1u);
-          mma_bf16(tmem_d, dal, dbh, idesc, 1u);
+#pragma unroll 1
+        for (int t = 0; t < n_terms; ++t) {
+          int ta, tb;
+          if (g.split == 6) {   // t: 0 (m,m) 1 (h,l) 2 (l,h) 3 (h,m) 4 (m,h) 5 (h,h)
+            ta = (t == 0 || t == 4) ? 1 : (t == 2 ? 2 : 0);
+            tb = (t == 0 || t == 3) ? 1 : (t == 1 ? 2 : 0);
+          } else {              // t: 0 (h,h) 1 (h,m) 2 (m,h)
+            ta = t == 2 ? 1 : 0;
+            tb = t == 1 ? 1 : 0;
+          }
+          mma_bf16(tmem_d, kslice_desc(a_h + ta * kATile, kTileM, ks), kslice_desc(b_h + tb * kBTile, BN, ks),
+                   idesc, (i | ks | t) ? 1u : 0u);
         }
       }
       mma_commit(&mma_done[s]);
     }
   }
-  // the last commit covers every MMA issued before it
-  {
+  {  // the last commit covers every MMA issued before it
     const int last = nkc - 1;
     mbar_wait(&mma_done[last & 1], (last >> 1) & 1);
     fence_after_sync();
   }
 
-  // ---- epilogue
+  // ---- epilogue: 8 columns at a time, rolled
   const int q = warp & 3, h = warp >> 2;
   const int grow = m0 + q * 32 + lane;  // global row of this thread's TMEM lane
   constexpr int kColsPerHalf = BN / 2;
+  const bool first_split = blockIdx.z == 0;
+  const bool row_ok = grow < g.M;
 #pragma unroll 1
-  for (int c0 = h * kColsPerHalf; c0 < (h + 1) * kColsPerHalf; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-    tmem_ld_wait();
+  for (int c0 = h * kColsPerHalf; c0 < (h + 1) * kColsPerHalf; c0 += 8) {
     const int n0 = nt * BN + c0;
-    float v[32];
+    if (n0 >= g.N) break;  // warp-uniform
+    uint32_t r[8];
+    tmem_ld8(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+    tmem_ld_wait();
+    float v[8];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const int n = n0 + j;
       float x = __uint_as_float(r[j]);
-      if (bias != nullptr && n < N) x += bias[n];
-      v[j] = apply_act(x, act);
-    }
-    if (pool > 1) {
-      // max over groups of `pool` consecutive rows (pool divides 32); rows beyond M
-      // never win because whole groups are either inside or outside M.
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        for (int o = 1; o < pool; o <<= 1) v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], o));
-      if ((lane % pool) == 0 && grow < M) {
-        float *o = out + (long long)(grow / pool) * ldo + n0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + j < N) o[j] = v[j];
+      if (n < g.N) {
+        if (g.bias != nullptr && first_split) x += g.bias[n];
+        x = apply_act(x, g.act);
+        if (row_ok) {
+          if (g.epi == EPI_GELU_GRAD) {
+            const long long off = (long long)grow * g.ldaux + n;
+            x = gelu_grad_masked(x, g.aux[off], &g.drop, g.epi_site, off);
+          }
+          if (g.res != nullptr && first_split) x += g.res[(long long)grow * g.ldr + n];
+        }
       }
-    } else if (grow < M) {
-      float *o = out + (long long)grow * ldo + n0;
-      const bool vst = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (n0 + 32 <= N);
-      if (vst && !accumulate) {
+      v[j] = x;
+    }
+    if (g.pool > 1) {
+      // max over groups of `pool` consecutive rows (pool divides 32); whole groups are
+      // either inside or outside M.
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int j = 0; j < 8; ++j)
+        for (int o = 1; o < g.pool; o <<= 1) v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], o));
+      if ((lane % g.pool) == 0 && row_ok) {
+        float *o = g.out + (long long)(grow / g.pool) * g.ldo + n0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (n0 + j < g.N) o[j] = v[j];
+      }
+    } else if (row_ok) {
+      float *o = g.out + (long long)grow * g.ldo + n0;
+      const bool vst = ((g.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.out) & 15) == 0) && (n0 + 8 <= g.N);
+      if (vst && g.accumulate == 0) {
+        *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      } else if (g.accumulate == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (n0 + j < g.N) atomicAdd(o + j, v[j]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + j < N) o[j] = accumulate ? o[j] + v[j] : v[j];
+        for (int j = 0; j < 8; ++j)
+          if (n0 + j < g.N) o[j] = g.accumulate ? o[j] + v[j] : v[j];
       }
     }
   }
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, BN);
+}
+
+static int launch_gemm(GemmArgs &g, int ksplit, cudaStream_t stream) {
+  constexpr int BN = 128;
+  g.Kp = ceil_div(g.K, kChunkK) * kChunkK;
+  const size_t smem = 2 * (3 * (size_t)kTileM * kChunkK * 2 + 3 * (size_t)BN * kChunkK * 2) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    MSR3D_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+    configured = true;
+  }
+  const int nkc = g.Kp / kChunkK;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > nkc) ksplit = nkc;
+  dim3 grid(ceil_div(g.M, kTileM), ceil_div(g.N, BN), ksplit);
+  linear_tc_kernel<BN><<<grid, 256, smem, stream>>>(g);
+  return check_launch("linear_tc");
 }
 
 }  // namespace msr3d
@@ -269,18 +399,31 @@ MSR3D_API int msr3d_linear_tc_f32(const float *A, long long stride_am, long long
                 "linear_tc: pool=%d must be a power of two <= 32 dividing M", pool);
   MSR3D_REQUIRE(!(accumulate && (pool > 1 || act != 0)), "linear_tc: accumulate needs act=0, pool<=1");
   if (M == 0) return MSR3D_OK;
-  constexpr int BN = 128;
-  const int Kp = ceil_div(K, kChunkK) * kChunkK;
-  const size_t smem = 2 * (2 * (size_t)kTileM * kChunkK * 2 + (size_t)BN * kChunkK * 4) + 1024;
-  static bool configured = false;
-  if (!configured) {
-    MSR3D_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-    configured = true;
-  }
-  dim3 grid(ceil_div(M, kTileM), ceil_div(N, BN));
-  linear_tc_kernel<BN><<<grid, 256, smem, (cudaStream_t)stream>>>(
-      A, stride_am, stride_ak, M, K, (const uint8_t *)packed_w, Kp, bias, out, ldo, N, act, pool,
-      split, accumulate);
-  return check_launch("linear_tc");
+  GemmArgs g{};
+  g.A = A; g.sam = stride_am; g.sak = stride_ak; g.PW = (const uint8_t *)packed_w; g.b_mode = 0;
+  g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo; g.act = act; g.pool = pool;
+  g.split = split; g.accumulate = accumulate ? 1 : 0; g.drop = make_dropout(0, 0.f);
+  return launch_gemm(g, 1, (cudaStream_t)stream);
+}
+
+MSR3D_API int msr3d_gemm_tc_f32(const msr3d_gemm_desc *d, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(d != nullptr, "gemm_tc: null descriptor");
+  MSR3D_REQUIRE(d->A && d->B && d->out, "gemm_tc: null pointer");
+  MSR3D_REQUIRE(d->M >= 0 && d->K > 0 && d->N > 0, "gemm_tc: bad sizes M=%d K=%d N=%d", d->M, d->K, d->N);
+  MSR3D_REQUIRE(d->act >= 0 && d->act <= 2 && (d->split == 1 || d->split == 3 || d->split == 6), "gemm_tc: bad act/split");
+  MSR3D_REQUIRE(d->a_xform >= 0 && d->a_xform <= 2 && d->b_xform >= 0 && d->b_xform <= 2, "gemm_tc: bad xform");
+  MSR3D_REQUIRE(d->epilogue == 0 || (d->epilogue == 1 && d->aux), "gemm_tc: EPI_GELU_GRAD needs aux");
+  MSR3D_REQUIRE(d->ksplit <= 1 || (d->accumulate == 2 && d->act == 0 && d->epilogue == 0),
+                "gemm_tc: split-K needs atomic accumulation (accumulate=2), act=0, plain epilogue");
+  MSR3D_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, "gemm_tc: bad dropout p");
+  if (d->M == 0) return MSR3D_OK;
+  GemmArgs g{};
+  g.A = d->A; g.sam = d->stride_am; g.sak = d->stride_ak; g.a_xform = d->a_xform; g.a_site = d->a_site;
+  g.Bf = d->B; g.sbn = d->stride_bn; g.sbk = d->stride_bk; g.b_xform = d->b_xform; g.b_site = d->b_site;
+  g.b_mode = 1;
+  g.M = d->M; g.N = d->N; g.K = d->K; g.bias = d->bias; g.res = d->residual; g.ldr = d->ld_residual;
+  g.aux = d->aux; g.ldaux = d->ld_aux; g.epi_site = d->epi_site; g.out = d->out; g.ldo = d->ld_out;
+  g.act = d->act; g.pool = 0; g.split = d->split; g.accumulate = d->accumulate; g.epi = d->epilogue;
+  g.drop = make_dropout(d->seed, d->dropout_p, d->seed_ptr);
+  return launch_gemm(g, d->ksplit, (cudaStream_t)stream);
 }

@@ -1,0 +1,99 @@
+// Group D: the optimiser step around the collective, on ONE flat fp32 buffer.
+// Replaces accelerator.clip_grad_norm_(5.0) + torch.optim.AdamW.step()
+// (trainer/leo_trainer.py:192-195, optim/build.py:7-17) — per-tensor launches in the
+// reference — with two launches: a sum-of-squares reduction and a fused clip+AdamW update.
+// Hyper-parameters live in a small device struct so the whole training step can be replayed
+// as a CUDA graph while the host changes the learning rate between replays.
+#include "common.cuh"
+
+namespace msr3d {
+
+struct OptState {   // device-resident, 8 floats
+  float sumsq;      // written by sumsq_kernel (zeroed by adamw_kernel for the next step)
+  float step;       // incremented once per step by sumsq_kernel's last block
+  float lr, beta1, beta2, eps, weight_decay, max_norm;
+};
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float *__restrict__ g, long long n, float grad_scale, OptState *st,
+             unsigned int *ticket, unsigned long long *seed_counter) {
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = g[i] * grad_scale;
+    s += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float w[8];
+  if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += w[i];
+    atomicAdd(&st->sumsq, t);
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {  // last block: advance the step counter
+      st->step += 1.f;
+      if (seed_counter != nullptr) *seed_counter += 1ull;  // next step draws fresh dropout masks
+      *ticket = 0u;
+    }
+  }
+}
+
+// p -= lr * ( m_hat / (sqrt(v_hat) + eps) + wd * p ), grads first scaled by grad_scale (1/world)
+// and by the global-norm clip coefficient min(1, max_norm / (norm + 1e-6)).
+// Elements [0, n_decay) get weight decay, the rest (biases, LayerNorm) do not.
+__global__ void __launch_bounds__(256)
+adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+             float *__restrict__ v, long long n, long long n_decay, float grad_scale,
+             OptState *st) {
+  const float norm = sqrtf(st->sumsq);
+  const float clip = st->max_norm > 0.f ? fminf(1.f, st->max_norm / (norm + 1e-6f)) : 1.f;
+  const float gs = grad_scale * clip;
+  const float b1 = st->beta1, b2 = st->beta2, lr = st->lr, eps = st->eps, wd = st->weight_decay;
+  const float bc1 = 1.f - powf(b1, st->step), bc2 = 1.f - powf(b2, st->step);
+  const float step_size = lr / bc1;
+  const float inv_bc2_sqrt = rsqrtf(bc2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    float pi = p[i];
+    if (i < n_decay) pi *= 1.f - lr * wd;  // decoupled weight decay (torch AdamW order)
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+
+__global__ void reset_sumsq_kernel(OptState *st) { st->sumsq = 0.f; }
+
+}  // namespace msr3d
+
+using namespace msr3d;
+
+/* state: 8 floats on the device {sumsq, step, lr, beta1, beta2, eps, weight_decay, max_norm};
+ * ticket: one zero-initialised uint32 on the device. */
+MSR3D_API int msr3d_adamw_clip_step_f32(float *params, const float *grads, float *exp_avg,
+                                        float *exp_avg_sq, long long n, long long n_decay,
+                                        float grad_scale, float *state, unsigned int *ticket,
+                                        unsigned long long *seed_counter, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(params && grads && exp_avg && exp_avg_sq && state && ticket, "adamw: null pointer");
+  MSR3D_REQUIRE(n >= 0 && n_decay >= 0 && n_decay <= n, "adamw: bad sizes");
+  if (n == 0) return MSR3D_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  OptState *st = reinterpret_cast<OptState *>(state);
+  int grid = (int)((n + 255) / 256);
+  if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+  reset_sumsq_kernel<<<1, 1, 0, s>>>(st);
+  int rc = check_launch("reset_sumsq");
+  if (rc) return rc;
+  sumsq_kernel<<<grid, 256, 0, s>>>(grads, n, grad_scale, st, ticket, seed_counter);
+  rc = check_launch("sumsq");
+  if (rc) return rc;
+  adamw_kernel<<<grid, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, n_decay, grad_scale, st);
+  return check_launch("adamw");
+}

@@ -1,0 +1,846 @@
+// Group C: the pieces of the situated spatial-attention transformer that are not GEMMs.
+// (The GEMMs — QKV+cond, out-proj, FFN and every weight/data gradient — run on the tensor
+// cores through msr3d_gemm_tc_f32, linear_tc.cu.)  All fp32, all tiny (M = B*L ~ 240 tokens):
+// the point is to collapse the ~45 elementwise/reduction launches per layer of the reference
+// (modules/layers/transformers.py:200-252,314-329; modules/utils.py:88-137) into a handful and
+// to drop its per-layer host sync.
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace msr3d {
+
+constexpr int kD = 256;        // hidden size of the spatial encoder (configs/msr3d.yaml:181)
+constexpr int kMaxL = 128;     // tokens per scene supported by the attention kernels
+constexpr float kLnEps = 1e-5f;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// Geometry: pairwise relative locations (calc_pairwise_locs, 'center', spatial_dim 5,
+// modules/utils.py:88-137) and Fourier features of agent-frame centres
+// (transform_to_agent_coor :60-82 + generate_fourier_features, ose3d_situation.py:31-59).
+// One CTA per scene, one thread per object.
+//   loc   (B, L, 6)   centre xyz + size whl
+//   anchor(B, 3), quat (B, 4) (x,y,z,w); use_agent_frame = 0 -> features of the raw centres
+//   pw    (B, L, L, 5), ff (B*L, 64) [p'(3) | sin(pi p'_d f_j) d-major (30) | cos (30) | 0], sz (B*L, 3)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMaxL)
+geometry_kernel(const float *__restrict__ loc, const float *__restrict__ anchor,
+                const float *__restrict__ quat, int L, int dist_norm, int use_agent_frame,
+                float *__restrict__ pw, float *__restrict__ ff, float *__restrict__ sz) {
+  __shared__ float cx[kMaxL], cy[kMaxL], cz[kMaxL];
+  __shared__ float s_red[kMaxL / 32];
+  const int b = blockIdx.x, l = threadIdx.x;
+  const float eps = 1e-10f;
+  if (l < L) {
+    const float *p = loc + ((size_t)b * L + l) * 6;
+    cx[l] = p[0]; cy[l] = p[1]; cz[l] = p[2];
+  }
+  __syncthreads();
+  float mymax = 0.f;
+  if (l < L) {
+    for (int t = 0; t < L; ++t) {
+      const float dx = cx[l] - cx[t], dy = cy[l] - cy[t], dz = cz[l] - cz[t];
+      mymax = fmaxf(mymax, sqrtf((dx * dx + dy * dy) + dz * dz + eps));
+    }
+  }
+  mymax = warp_max(mymax);
+  if ((l & 31) == 0) s_red[l >> 5] = mymax;
+  __syncthreads();
+  float gmax = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) gmax = fmaxf(gmax, s_red[w]);
+  if (l < L) {
+    const float inv = dist_norm ? 1.f / gmax : 1.f;
+    for (int t = 0; t < L; ++t) {
+      const float dx = cx[l] - cx[t], dy = cy[l] - cy[t], dz = cz[l] - cz[t];
+      const float d = sqrtf((dx * dx + dy * dy) + dz * dz + eps);
+      const float d2 = sqrtf(dx * dx + dy * dy + eps);
+      float *o = pw + (((size_t)b * L + l) * L + t) * 5;
+      o[0] = dist_norm ? d / gmax : d;
+      o[1] = dz / d;
+      o[2] = d2 / d;
+      o[3] = dy / d2;
+      o[4] = dx / d2;
+      (void)inv;
+    }
+    // agent frame: p' = (p - anchor) R, R from the conjugate quaternion
+    float px = cx[l], py = cy[l], pz = cz[l];
+    if (use_agent_frame) {
+      const float *a = anchor + (size_t)b * 3;
+      const float *qq = quat + (size_t)b * 4;
+      const float x = -qq[0], y = -qq[1], z = -qq[2], w = qq[3];
+      const float xx = x * x, yy = y * y, zz = z * z;
+      const float xy = x * y, xz = x * z, xw = x * w, yz = y * z, yw = y * w, zw = z * w;
+      const float r00 = 1 - 2 * (yy + zz), r01 = 2 * (xy + zw), r02 = 2 * (xz - yw);
+      const float r10 = 2 * (xy - zw), r11 = 1 - 2 * (xx + zz), r12 = 2 * (yz + xw);
+      const float r20 = 2 * (xz + yw), r21 = 2 * (yz - xw), r22 = 1 - 2 * (xx + yy);
+      const float ux = px - a[0], uy = py - a[1], uz = pz - a[2];
+      px = (ux * r00 + uy * r10) + uz * r20;
+      py = (ux * r01 + uy * r11) + uz * r21;
+      pz = (ux * r02 + uy * r12) + uz * r22;
+    }
+    float *f = ff + ((size_t)b * L + l) * 64;
+    f[0] = px; f[1] = py; f[2] = pz;
+    const float kPi = 3.14159265358979323846f;
+    // rolled on purpose: sincosf's slow-path range reduction is large, and this kernel runs once
+#pragma unroll 1
+    for (int e = 0; e < 30; ++e) {
+      const int d = e / 10, j = e % 10;
+      // torch.linspace(1, 15, 10): start + j*step below the midpoint, end - (9-j)*step above
+      const float step = 14.f / 9.f;
+      const float fr = j < 5 ? 1.f + j * step : 15.f - (9 - j) * step;
+      const float arg = kPi * ((d == 0 ? px : (d == 1 ? py : pz)) * fr);
+      float sn, cs;
+      sincosf(arg, &sn, &cs);
+      f[3 + e] = sn;
+      f[33 + e] = cs;
+    }
+    f[63] = 0.f;
+    const float *p = loc + ((size_t)b * L + l) * 6;
+    float *s = sz + ((size_t)b * L + l) * 3;
+    s[0] = p[3]; s[1] = p[4]; s[2] = p[5];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm helpers: one warp per row of kD = 256 values (8 per lane, lane-strided).
+// ---------------------------------------------------------------------------
+struct Row8 { float v[8]; };
+__device__ __forceinline__ Row8 row_load(const float *p, int lane) {
+  Row8 r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = p[lane + 32 * i];
+  return r;
+}
+__device__ __forceinline__ void row_store(float *p, int lane, const Row8 &r) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p[lane + 32 * i] = r.v[i];
+}
+// y = gamma * xhat + beta; returns xhat in `x`, rstd via out param
+__device__ __forceinline__ Row8 ln_forward(Row8 &x, const float *gamma, const float *beta, int lane,
+                                           float &rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x.v[i];
+  const float mean = warp_sum(s) * (1.f / kD);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { x.v[i] -= mean; q += x.v[i] * x.v[i]; }
+  rstd = rsqrtf(warp_sum(q) * (1.f / kD) + kLnEps);
+  Row8 y;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    x.v[i] *= rstd;
+    y.v[i] = x.v[i] * gamma[lane + 32 * i] + beta[lane + 32 * i];
+  }
+  return y;
+}
+// dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy * gamma
+__device__ __forceinline__ Row8 ln_backward(const Row8 &dy, const Row8 &xhat, const float *gamma,
+                                            int lane, float rstd) {
+  Row8 g;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    g.v[i] = dy.v[i] * gamma[lane + 32 * i];
+    s1 += g.v[i];
+    s2 += g.v[i] * xhat.v[i];
+  }
+  s1 = warp_sum(s1) * (1.f / kD);
+  s2 = warp_sum(s2) * (1.f / kD);
+  Row8 dx;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dx.v[i] = rstd * (g.v[i] - s1 - xhat.v[i] * s2);
+  return dx;
+}
+
+constexpr int kLnWarps = 8;
+// Block-level accumulation of per-column sums (for dgamma/dbeta/bias grads): each warp adds its
+// row's contribution into shared partials, the CTA flushes them with one atomic per column.
+struct ColAcc {
+  float *s;  // [n_acc][kD] shared
+  __device__ void zero(int n_acc, int tid) {
+    for (int i = tid; i < n_acc * kD; i += kLnWarps * 32) s[i] = 0.f;
+  }
+  __device__ void add(int which, int lane, const Row8 &r) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&s[which * kD + lane + 32 * i], r.v[i]);
+  }
+  __device__ void flush(int which, float *dst, int tid) {
+    if (dst == nullptr) return;
+    for (int i = tid; i < kD; i += kLnWarps * 32) atomicAdd(dst + i, s[which * kD + i]);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Attention block tail (transformers.py:250-251 then :324-325), fused:
+//   v  = dropout_fc(o) + x          y1 = LN_a(v)
+//   w  = x + dropout_1(y1)          y2 = LN_1(w)
+// saves xhat/rstd of both norms for the backward pass.
+// ---------------------------------------------------------------------------
+struct LnParams { const float *gamma, *beta; };
+
+__global__ void __launch_bounds__(kLnWarps * 32)
+attn_tail_fwd_kernel(const float *__restrict__ o, const float *__restrict__ x, int M, LnParams lna,
+                     LnParams ln1, Dropout drop, unsigned site_fc, unsigned site_1,
+                     float *__restrict__ xhat_a, float *__restrict__ rstd_a,
+                     float *__restrict__ xhat_1, float *__restrict__ rstd_1,
+                     float *__restrict__ y2) {
+  drop.resolve();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const size_t base = (size_t)row * kD;
+  Row8 xo = row_load(o + base, lane), xr = row_load(x + base, lane), v;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    v.v[i] = drop.apply(xo.v[i], base + lane + 32 * i, site_fc) + xr.v[i];
+  float ra, r1;
+  Row8 y1 = ln_forward(v, lna.gamma, lna.beta, lane, ra);
+  row_store(xhat_a + base, lane, v);
+  Row8 w;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w.v[i] = xr.v[i] + drop.apply(y1.v[i], base + lane + 32 * i, site_1);
+  Row8 out = ln_forward(w, ln1.gamma, ln1.beta, lane, r1);
+  row_store(xhat_1 + base, lane, w);
+  row_store(y2 + base, lane, out);
+  if (lane == 0) { rstd_a[row] = ra; rstd_1[row] = r1; }
+}
+
+// backward of the above.  In: dy2 (grad wrt y2, already including the FFN data gradient).
+// Out: dx (grad wrt x through both residual branches), do_ (grad wrt the out-proj output),
+// atomically accumulated: dgamma/dbeta of both norms and the out-proj bias gradient (colsum do_).
+__global__ void __launch_bounds__(kLnWarps * 32)
+attn_tail_bwd_kernel(const float *__restrict__ dy2, int M, LnParams lna, LnParams ln1, Dropout drop,
+                     unsigned site_fc, unsigned site_1, const float *__restrict__ xhat_a,
+                     const float *__restrict__ rstd_a, const float *__restrict__ xhat_1,
+                     const float *__restrict__ rstd_1, float *__restrict__ dx,
+                     float *__restrict__ do_, float *__restrict__ dgamma_a,
+                     float *__restrict__ dbeta_a, float *__restrict__ dgamma_1,
+                     float *__restrict__ dbeta_1, float *__restrict__ dbias_o) {
+  drop.resolve();
+  __shared__ float s_acc[5 * kD];
+  ColAcc acc{s_acc};
+  acc.zero(5, threadIdx.x);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row < M) {
+    const size_t base = (size_t)row * kD;
+    const Row8 g2 = row_load(dy2 + base, lane);
+    const Row8 h1 = row_load(xhat_1 + base, lane), ha = row_load(xhat_a + base, lane);
+    Row8 t;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t.v[i] = g2.v[i] * h1.v[i];
+    acc.add(2, lane, t);   // dgamma_1
+    acc.add(3, lane, g2);  // dbeta_1
+    const Row8 dw = ln_backward(g2, h1, ln1.gamma, lane, rstd_1[row]);
+    Row8 dy1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dy1.v[i] = dw.v[i] * drop.mask(base + lane + 32 * i, site_1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t.v[i] = dy1.v[i] * ha.v[i];
+    acc.add(0, lane, t);    // dgamma_a
+    acc.add(1, lane, dy1);  // dbeta_a
+    const Row8 dv = ln_backward(dy1, ha, lna.gamma, lane, rstd_a[row]);
+    Row8 dxr, dor;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dxr.v[i] = dw.v[i] + dv.v[i];
+      dor.v[i] = dv.v[i] * drop.mask(base + lane + 32 * i, site_fc);
+    }
+    acc.add(4, lane, dor);  // bias gradient of the out projection
+    row_store(dx + base, lane, dxr);
+    row_store(do_ + base, lane, dor);
+  }
+  __syncthreads();
+  acc.flush(0, dgamma_a, threadIdx.x);
+  acc.flush(1, dbeta_a, threadIdx.x);
+  acc.flush(2, dgamma_1, threadIdx.x);
+  acc.flush(3, dbeta_1, threadIdx.x);
+  acc.flush(4, dbias_o, threadIdx.x);
+}
+
+// ---------------------------------------------------------------------------
+// FFN tail:  w = y2 + dropout_2(f);  y3 = LN_2(w);  x_next = y3 + add (add = qpos of the next
+// layer, nullable).  Backward: dw = LNbwd(dy3); df = mask_2 * dw (+ colsum -> dbias_2).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLnWarps * 32)
+ffn_tail_fwd_kernel(const float *__restrict__ f, const float *__restrict__ y2, int M, LnParams ln2,
+                    Dropout drop, unsigned site_2, const float *__restrict__ add,
+                    float *__restrict__ xhat_2, float *__restrict__ rstd_2, float *__restrict__ y3,
+                    float *__restrict__ x_next) {
+  drop.resolve();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const size_t base = (size_t)row * kD;
+  Row8 xf = row_load(f + base, lane), xr = row_load(y2 + base, lane), w;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w.v[i] = xr.v[i] + drop.apply(xf.v[i], base + lane + 32 * i, site_2);
+  float r2;
+  Row8 out = ln_forward(w, ln2.gamma, ln2.beta, lane, r2);
+  row_store(xhat_2 + base, lane, w);
+  if (y3 != nullptr) row_store(y3 + base, lane, out);
+  if (x_next != nullptr) {
+    if (add != nullptr) {
+      const Row8 a = row_load(add + base, lane);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) out.v[i] += a.v[i];
+    }
+    row_store(x_next + base, lane, out);
+  }
+  if (lane == 0) rstd_2[row] = r2;
+}
+
+__global__ void __launch_bounds__(kLnWarps * 32)
+ffn_tail_bwd_kernel(const float *__restrict__ dy3, int M, LnParams ln2, Dropout drop, unsigned site_2,
+                    const float *__restrict__ xhat_2, const float *__restrict__ rstd_2,
+                    float *__restrict__ dy2, float *__restrict__ df, float *__restrict__ dgamma_2,
+                    float *__restrict__ dbeta_2, float *__restrict__ dbias_2) {
+  drop.resolve();
+  __shared__ float s_acc[3 * kD];
+  ColAcc acc{s_acc};
+  acc.zero(3, threadIdx.x);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row < M) {
+    const size_t base = (size_t)row * kD;
+    const Row8 g = row_load(dy3 + base, lane), h = row_load(xhat_2 + base, lane);
+    Row8 t;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t.v[i] = g.v[i] * h.v[i];
+    acc.add(0, lane, t);
+    acc.add(1, lane, g);
+    const Row8 dw = ln_backward(g, h, ln2.gamma, lane, rstd_2[row]);
+    Row8 dfr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dfr.v[i] = dw.v[i] * drop.mask(base + lane + 32 * i, site_2);
+    acc.add(2, lane, dfr);
+    row_store(dy2 + base, lane, dw);
+    row_store(df + base, lane, dfr);
+  }
+  __syncthreads();
+  acc.flush(0, dgamma_2, threadIdx.x);
+  acc.flush(1, dbeta_2, threadIdx.x);
+  acc.flush(2, dbias_2, threadIdx.x);
+}
+
+// ---------------------------------------------------------------------------
+// Query position (ose3d_situation.py:399-404):
+//   qpos = LN_l(h1) + LN_s(Ws sz + bs),  h1 = Wl ff + bl comes from the tensor-core GEMM.
+//   qpos0 = qpos + extra   (extra = object_orientation_feat + type_embedding[0], layer-0 input)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLnWarps * 32)
+qpos_fwd_kernel(const float *__restrict__ h1, const float *__restrict__ sz, int M,
+                const float *__restrict__ Ws, const float *__restrict__ bs, LnParams lnl, LnParams lns,
+                const float *__restrict__ extra_a, const float *__restrict__ extra_b,
+                float *__restrict__ xhat_l, float *__restrict__ rstd_l, float *__restrict__ xhat_s,
+                float *__restrict__ rstd_s, float *__restrict__ qpos, float *__restrict__ qpos0) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const size_t base = (size_t)row * kD;
+  Row8 a = row_load(h1 + base, lane), b;
+  const float s0 = sz[row * 3 + 0], s1 = sz[row * 3 + 1], s2 = sz[row * 3 + 2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + 32 * i;
+    b.v[i] = (Ws[c * 3 + 0] * s0 + Ws[c * 3 + 1] * s1) + Ws[c * 3 + 2] * s2 + bs[c];
+  }
+  float rl, rs;
+  Row8 ya = ln_forward(a, lnl.gamma, lnl.beta, lane, rl);
+  Row8 yb = ln_forward(b, lns.gamma, lns.beta, lane, rs);
+  row_store(xhat_l + base, lane, a);
+  row_store(xhat_s + base, lane, b);
+  Row8 q, q0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + 32 * i;
+    q.v[i] = ya.v[i] + yb.v[i];
+    q0.v[i] = q.v[i] + (extra_a ? extra_a[c] : 0.f) + (extra_b ? extra_b[c] : 0.f);
+  }
+  row_store(qpos + base, lane, q);
+  row_store(qpos0 + base, lane, q0);
+  if (lane == 0) { rstd_l[row] = rl; rstd_s[row] = rs; }
+}
+
+// dqpos -> dh1 (for the Wl GEMMs), and in place: dgamma/dbeta of both norms, dWs (256x3), dbs,
+// and the bias gradient of the loc linear (colsum dh1).
+__global__ void __launch_bounds__(kLnWarps * 32)
+qpos_bwd_kernel(const float *__restrict__ dq, const float *__restrict__ dq1,
+                const float *__restrict__ dq2, const float *__restrict__ sz, int M, LnParams lnl,
+                LnParams lns, const float *__restrict__ xhat_l, const float *__restrict__ rstd_l,
+                const float *__restrict__ xhat_s, const float *__restrict__ rstd_s,
+                float *__restrict__ dh1, float *__restrict__ dgamma_l, float *__restrict__ dbeta_l,
+                float *__restrict__ dgamma_s, float *__restrict__ dbeta_s, float *__restrict__ dWs,
+                float *__restrict__ dbs, float *__restrict__ dbl) {
+  __shared__ float s_acc[8 * kD];
+  ColAcc acc{s_acc};
+  acc.zero(8, threadIdx.x);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row < M) {
+    const size_t base = (size_t)row * kD;
+    Row8 g = row_load(dq + base, lane);   // qpos is added at every layer: sum the per-layer grads
+    if (dq1 != nullptr) {
+      const Row8 e = row_load(dq1 + base, lane);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g.v[i] += e.v[i];
+    }
+    if (dq2 != nullptr) {
+      const Row8 e = row_load(dq2 + base, lane);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g.v[i] += e.v[i];
+    }
+    const Row8 hl = row_load(xhat_l + base, lane), hs = row_load(xhat_s + base, lane);
+    Row8 t;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t.v[i] = g.v[i] * hl.v[i];
+    acc.add(0, lane, t);
+    acc.add(1, lane, g);   // dbeta_l == dbeta_s == colsum(dq)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t.v[i] = g.v[i] * hs.v[i];
+    acc.add(2, lane, t);
+    const Row8 d1 = ln_backward(g, hl, lnl.gamma, lane, rstd_l[row]);
+    const Row8 d2 = ln_backward(g, hs, lns.gamma, lane, rstd_s[row]);
+    row_store(dh1 + base, lane, d1);
+    acc.add(3, lane, d1);  // dbl
+    acc.add(4, lane, d2);  // dbs
+    const float s0 = sz[row * 3 + 0], s1 = sz[row * 3 + 1], s2 = sz[row * 3 + 2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t.v[i] = d2.v[i] * s0;
+    acc.add(5, lane, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t.v[i] = d2.v[i] * s1;
+    acc.add(6, lane, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t.v[i] = d2.v[i] * s2;
+    acc.add(7, lane, t);
+  }
+  __syncthreads();
+  acc.flush(0, dgamma_l, threadIdx.x);
+  acc.flush(1, dbeta_l, threadIdx.x);
+  acc.flush(2, dgamma_s, threadIdx.x);
+  acc.flush(1, dbeta_s, threadIdx.x);
+  acc.flush(3, dbl, threadIdx.x);
+  acc.flush(4, dbs, threadIdx.x);
+  if (dWs != nullptr)
+    for (int c = threadIdx.x; c < kD; c += kLnWarps * 32) {
+      atomicAdd(dWs + c * 3 + 0, s_acc[5 * kD + c]);
+      atomicAdd(dWs + c * 3 + 1, s_acc[6 * kD + c]);
+      atomicAdd(dWs + c * 3 + 2, s_acc[7 * kD + c]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// dst[n] += sum_m src[m, n]   (bias gradients, d(orientation_feat), d(type_embedding[0]), ...)
+// up to three destinations receive the same column sums.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float *__restrict__ src, long long ld, int M, int N, float *__restrict__ d0,
+              float *__restrict__ d1, float *__restrict__ d2, int rows_per_cta) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int m0 = blockIdx.y * rows_per_cta;
+  const int m1 = min(M, m0 + rows_per_cta);
+  float s = 0.f;
+  for (int m = m0; m < m1; ++m) s += src[(long long)m * ld + n];
+  if (d0) atomicAdd(d0 + n, s);
+  if (d1) atomicAdd(d1 + n, s);
+  if (d2) atomicAdd(d2 + n, s);
+}
+
+// ---------------------------------------------------------------------------
+// Attention core, `cond` fusion (transformers.py:205-248).  qkvc rows:
+// [q(256) | k(256) | v(256) | cond(8 heads x 6)].
+//   S = q k^T / sqrt(dh);  loc = sigmoid(sw[1:] . pw[l,t,:] + sw[0]);
+//   masked key: S = -inf, loc = 0;  P = softmax(log(max(loc, 1e-6)) + S);  ctx = P v
+// One CTA per (head, scene, row block); ONE WARP PER QUERY ROW with the keys spread over the
+// lanes (key t = lane + 32 j), so every global access is coalesced and nothing is serial over
+// the keys: the first version (one thread per row) was a chain of ~60 dependent L2 round trips.
+// K is staged transposed in shared memory (lane = key -> conflict-free), V row-major (lane = dim).
+// Saves P and loc (B,H,L,L) for the backward pass.
+// ---------------------------------------------------------------------------
+constexpr int kDh = 32;
+constexpr int kAttnWarps = 8;
+constexpr int kKeysPerLane = kMaxL / 32;  // 4
+
+__global__ void __launch_bounds__(kAttnWarps * 32)
+attn_fwd_kernel(const float *__restrict__ qkvc, int ldq, const float *__restrict__ pw,
+                const unsigned char *__restrict__ key_pad, int L, int H, float *__restrict__ P,
+                float *__restrict__ LOC, float *__restrict__ ctx, int ldc) {
+  extern __shared__ float sm[];
+  const int LT = ((L + 31) / 32) * 32;
+  float *kT = sm;                 // [32][LT]
+  float *vs = sm + kDh * LT;      // [L][32]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int D = H * kDh;
+  for (int i = threadIdx.x; i < L * kDh; i += blockDim.x) {
+    const int t = i / kDh, d = i % kDh;
+    const float *r = qkvc + ((size_t)b * L + t) * ldq;
+    kT[d * LT + t] = r[D + h * kDh + d];
+    vs[i] = r[2 * D + h * kDh + d];
+  }
+  __syncthreads();
+  const float scale = rsqrtf((float)kDh);
+  const int nj = LT / 32;
+  for (int l = blockIdx.z * kAttnWarps + warp; l < L; l += gridDim.z * kAttnWarps) {
+    const float *r = qkvc + ((size_t)b * L + l) * ldq;
+    const float qd = r[h * kDh + lane];
+    const float swl = lane < 6 ? r[3 * D + h * 6 + lane] : 0.f;
+    float sw[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) sw[d] = __shfl_sync(0xffffffffu, swl, d);
+    float s[kKeysPerLane], loc[kKeysPerLane];
+#pragma unroll
+    for (int j = 0; j < kKeysPerLane; ++j) s[j] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < kDh; ++d) {
+      const float q = __shfl_sync(0xffffffffu, qd, d);
+#pragma unroll
+      for (int j = 0; j < kKeysPerLane; ++j)
+        if (j < nj) s[j] += q * kT[d * LT + lane + 32 * j];
+    }
+    const float *pwr = pw + ((size_t)b * L + l) * L * 5;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kKeysPerLane; ++j) {
+      const int t = lane + 32 * j;
+      if (j < nj && t < L) {
+        const float *g = pwr + t * 5;
+        float z = sw[0];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) z += sw[1 + d] * g[d];
+        float lc = 1.f / (1.f + __expf(-z));
+        float sc = s[j] * scale;
+        if (key_pad != nullptr && key_pad[(size_t)b * L + t]) { sc = -INFINITY; lc = 0.f; }
+        s[j] = __logf(fmaxf(lc, 1e-6f)) + sc;
+        loc[j] = lc;
+        mx = fmaxf(mx, s[j]);
+      } else {
+        s[j] = -INFINITY;
+        loc[j] = 0.f;
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kKeysPerLane; ++j) {
+      s[j] = __expf(s[j] - mx);   // exp(-inf) = 0 for masked / out-of-range keys
+      sum += s[j];
+    }
+    const float inv = 1.f / warp_sum(sum);
+    float *Pr = P + (((size_t)b * H + h) * L + l) * L;
+    float *Lr = LOC + (((size_t)b * H + h) * L + l) * L;
+#pragma unroll
+    for (int j = 0; j < kKeysPerLane; ++j) {
+      s[j] *= inv;
+      const int t = lane + 32 * j;
+      if (j < nj && t < L) { Pr[t] = s[j]; Lr[t] = loc[j]; }
+    }
+    float acc = 0.f;  // lane = output dim
+#pragma unroll
+    for (int j = 0; j < kKeysPerLane; ++j) {
+      if (j < nj) {
+        const int tmax = min(32, L - 32 * j);
+        for (int tt = 0; tt < tmax; ++tt)
+          acc += __shfl_sync(0xffffffffu, s[j], tt) * vs[(32 * j + tt) * kDh + lane];
+      }
+    }
+    ctx[((size_t)b * L + l) * ldc + h * kDh + lane] = acc;
+  }
+}
+
+// Backward of the attention core.  In: dctx (M,256), P, LOC, qkvc, pw.  Out: dqkvc (M,816),
+// every column written exactly once (the cond gradient goes to columns 768..815).
+// One CTA per (head, scene).  Phase 1: warp per query row (keys over lanes) -> dlogits into shared
+// memory, dq and d(cond).  Phase 2: warp per key row (dims over lanes) -> dk, dv.
+__global__ void __launch_bounds__(kAttnWarps * 32)
+attn_bwd_kernel(const float *__restrict__ dctx, int ldc, const float *__restrict__ qkvc, int ldq,
+                const float *__restrict__ pw, const float *__restrict__ P,
+                const float *__restrict__ LOC, int L, int H, float *__restrict__ dqkvc) {
+  extern __shared__ float sm[];
+  const int LT = ((L + 31) / 32) * 32;
+  const int LP = LT + 1;
+  float *qs = sm;                 // [L][32]
+  float *ks = qs + L * kDh;       // [L][32]
+  float *gs = ks + L * kDh;       // dctx [L][32]
+  float *vT = gs + L * kDh;       // [32][LT]
+  float *dS = vT + kDh * LT;      // [L][LP]
+  float *Ps = dS + L * LP;        // [L][LP]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int D = H * kDh;
+  for (int i = threadIdx.x; i < L * kDh; i += blockDim.x) {
+    const int t = i / kDh, d = i % kDh;
+    const float *r = qkvc + ((size_t)b * L + t) * ldq;
+    qs[i] = r[h * kDh + d];
+    ks[i] = r[D + h * kDh + d];
+    vT[d * LT + t] = r[2 * D + h * kDh + d];
+    gs[i] = dctx[((size_t)b * L + t) * ldc + h * kDh + d];
+  }
+  __syncthreads();
+  const float scale = rsqrtf((float)kDh);
+  const int nj = LT / 32;
+  for (int l = warp; l < L; l += kAttnWarps) {
+    const float *r = qkvc + ((size_t)b * L + l) * ldq;
+    const float swl = lane < 6 ? r[3 * D + h * 6 + lane] : 0.f;
+    float sw[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) sw[d] = __shfl_sync(0xffffffffu, swl, d);
+    const float gd = gs[l * kDh + lane];
+    float dp[kKeysPerLane], p[kKeysPerLane];
+#pragma unroll
+    for (int j = 0; j < kKeysPerLane; ++j) dp[j] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < kDh; ++d) {
+      const float g = __shfl_sync(0xffffffffu, gd, d);
+#pragma unroll
+      for (int j = 0; j < kKeysPerLane; ++j)
+        if (j < nj) dp[j] += g * vT[d * LT + lane + 32 * j];
+    }
+    const float *Pr = P + (((size_t)b * H + h) * L + l) * L;
+    const float *Lr = LOC + (((size_t)b * H + h) * L + l) * L;
+    const float *pwr = pw + ((size_t)b * L + l) * L * 5;
+    float rowdot = 0.f;
+#pragma unroll
+    for (int j = 0; j < kKeysPerLane; ++j) {
+      const int t = lane + 32 * j;
+      p[j] = (j < nj && t < L) ? Pr[t] : 0.f;
+      rowdot += dp[j] * p[j];
+    }
+    rowdot = warp_sum(rowdot);
+    float dsw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < kKeysPerLane; ++j) {
+      const int t = lane + 32 * j;
+      const float dl = p[j] * (dp[j] - rowdot);   // d logits
+      dp[j] = dl;
+      if (j < nj && t < L) {
+        dS[l * LP + t] = dl;
+        Ps[l * LP + t] = p[j];
+        const float lc = Lr[t];
+        const float *g = pwr + t * 5;
+        // log(clamp(sigmoid(z), 1e-6)): d/dz = (loc >= 1e-6) * (1 - loc); 1 - sigmoid(z) is evaluated as
+        // sigmoid(-z) from the recomputed z (no cancellation near loc ~ 1); masked keys have loc = 0
+        float z = sw[0];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) z += sw[1 + d] * g[d];
+        const float gz = lc >= 1e-6f ? dl / (1.f + __expf(z)) : 0.f;
+        dsw[0] += gz;
+#pragma unroll
+        for (int d = 0; d < 5; ++d) dsw[1 + d] += gz * g[d];
+      }
+    }
+    float *o = dqkvc + ((size_t)b * L + l) * ldq;
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+      const float tsum = warp_sum(dsw[d]);
+      if (lane == d) o[3 * D + h * 6 + d] = tsum;
+    }
+    float dq = 0.f;  // lane = dim
+#pragma unroll
+    for (int j = 0; j < kKeysPerLane; ++j) {
+      if (j < nj) {
+        const int tmax = min(32, L - 32 * j);
+        for (int tt = 0; tt < tmax; ++tt)
+          dq += __shfl_sync(0xffffffffu, dp[j], tt) * ks[(32 * j + tt) * kDh + lane];
+      }
+    }
+    o[h * kDh + lane] = dq * scale;
+  }
+  __syncthreads();
+  for (int t = warp; t < L; t += kAttnWarps) {  // lane = dim
+    float dk = 0.f, dv = 0.f;
+    for (int i = 0; i < L; ++i) {
+      dk += dS[i * LP + t] * qs[i * kDh + lane];
+      dv += Ps[i * LP + t] * gs[i * kDh + lane];
+    }
+    float *o = dqkvc + ((size_t)b * L + t) * ldq;
+    o[D + h * kDh + lane] = dk * scale;
+    o[2 * D + h * kDh + lane] = dv;
+  }
+}
+
+__global__ void dropout_mask_kernel(Dropout drop, unsigned site, long long n, float *out) {
+  drop.resolve();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = drop.mask((uint64_t)i, site);
+}
+
+}  // namespace msr3d
+
+using namespace msr3d;
+
+static inline Dropout mk(unsigned long long seed, float p, const unsigned long long *sp) {
+  return make_dropout(seed, p, sp);
+}
+static inline int ln_grid(int M) { return ceil_div(M, kLnWarps); }
+
+MSR3D_API int msr3d_spatial_geometry_f32(const float *loc, const float *anchor, const float *quat,
+                                         int B, int L, int dist_norm, int use_agent_frame, float *pw,
+                                         float *ff, float *sz, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(loc && pw && ff && sz, "geometry: null pointer");
+  MSR3D_REQUIRE(!use_agent_frame || (anchor && quat), "geometry: agent frame needs anchor + quaternion");
+  MSR3D_REQUIRE(B >= 0 && L >= 1 && L <= kMaxL, "geometry: L=%d must be in [1,%d]", L, kMaxL);
+  if (B == 0) return MSR3D_OK;
+  geometry_kernel<<<B, kMaxL, 0, (cudaStream_t)stream>>>(loc, anchor, quat, L, dist_norm,
+                                                        use_agent_frame, pw, ff, sz);
+  return check_launch("geometry");
+}
+
+MSR3D_API int msr3d_attn_tail_fwd_f32(const float *o, const float *x, int M, const float *gamma_a,
+                                      const float *beta_a, const float *gamma_1, const float *beta_1,
+                                      unsigned long long seed, const unsigned long long *seed_ptr,
+                                      float p, unsigned site_fc, unsigned site_1, float *xhat_a, float *rstd_a, float *xhat_1,
+                                      float *rstd_1, float *y2, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(o && x && gamma_a && beta_a && gamma_1 && beta_1 && xhat_a && rstd_a && xhat_1 && rstd_1 && y2,
+                "attn_tail_fwd: null pointer");
+  if (M <= 0) return MSR3D_OK;
+  attn_tail_fwd_kernel<<<ln_grid(M), kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+      o, x, M, LnParams{gamma_a, beta_a}, LnParams{gamma_1, beta_1}, mk(seed, p, seed_ptr), site_fc, site_1,
+      xhat_a, rstd_a, xhat_1, rstd_1, y2);
+  return check_launch("attn_tail_fwd");
+}
+
+MSR3D_API int msr3d_attn_tail_bwd_f32(const float *dy2, int M, const float *gamma_a,
+                                      const float *gamma_1, unsigned long long seed,
+                                      const unsigned long long *seed_ptr, float p,
+                                      unsigned site_fc, unsigned site_1, const float *xhat_a,
+                                      const float *rstd_a, const float *xhat_1, const float *rstd_1,
+                                      float *dx, float *do_, float *dgamma_a, float *dbeta_a,
+                                      float *dgamma_1, float *dbeta_1, float *dbias_o,
+                                      msr3d_stream_t stream) {
+  MSR3D_REQUIRE(dy2 && gamma_a && gamma_1 && xhat_a && rstd_a && xhat_1 && rstd_1 && dx && do_,
+                "attn_tail_bwd: null pointer");
+  if (M <= 0) return MSR3D_OK;
+  attn_tail_bwd_kernel<<<ln_grid(M), kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+      dy2, M, LnParams{gamma_a, nullptr}, LnParams{gamma_1, nullptr}, mk(seed, p, seed_ptr), site_fc, site_1,
+      xhat_a, rstd_a, xhat_1, rstd_1, dx, do_, dgamma_a, dbeta_a, dgamma_1, dbeta_1, dbias_o);
+  return check_launch("attn_tail_bwd");
+}
+
+MSR3D_API int msr3d_ffn_tail_fwd_f32(const float *f, const float *y2, int M, const float *gamma_2,
+                                     const float *beta_2, unsigned long long seed,
+                                     const unsigned long long *seed_ptr, float p,
+                                     unsigned site_2, const float *add, float *xhat_2, float *rstd_2,
+                                     float *y3, float *x_next, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(f && y2 && gamma_2 && beta_2 && xhat_2 && rstd_2, "ffn_tail_fwd: null pointer");
+  if (M <= 0) return MSR3D_OK;
+  ffn_tail_fwd_kernel<<<ln_grid(M), kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+      f, y2, M, LnParams{gamma_2, beta_2}, mk(seed, p, seed_ptr), site_2, add, xhat_2, rstd_2, y3, x_next);
+  return check_launch("ffn_tail_fwd");
+}
+
+MSR3D_API int msr3d_ffn_tail_bwd_f32(const float *dy3, int M, const float *gamma_2,
+                                     unsigned long long seed, const unsigned long long *seed_ptr, float p,
+                                     unsigned site_2, const float *xhat_2, const float *rstd_2, float *dy2, float *df,
+                                     float *dgamma_2, float *dbeta_2, float *dbias_2,
+                                     msr3d_stream_t stream) {
+  MSR3D_REQUIRE(dy3 && gamma_2 && xhat_2 && rstd_2 && dy2 && df, "ffn_tail_bwd: null pointer");
+  if (M <= 0) return MSR3D_OK;
+  ffn_tail_bwd_kernel<<<ln_grid(M), kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+      dy3, M, LnParams{gamma_2, nullptr}, mk(seed, p, seed_ptr), site_2, xhat_2, rstd_2, dy2, df, dgamma_2,
+      dbeta_2, dbias_2);
+  return check_launch("ffn_tail_bwd");
+}
+
+MSR3D_API int msr3d_qpos_fwd_f32(const float *h1, const float *sz, int M, const float *Ws,
+                                 const float *bs, const float *gamma_l, const float *beta_l,
+                                 const float *gamma_s, const float *beta_s, const float *extra_a,
+                                 const float *extra_b, float *xhat_l, float *rstd_l, float *xhat_s,
+                                 float *rstd_s, float *qpos, float *qpos0, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(h1 && sz && Ws && bs && gamma_l && beta_l && gamma_s && beta_s && xhat_l && rstd_l &&
+                    xhat_s && rstd_s && qpos && qpos0, "qpos_fwd: null pointer");
+  if (M <= 0) return MSR3D_OK;
+  qpos_fwd_kernel<<<ln_grid(M), kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+      h1, sz, M, Ws, bs, LnParams{gamma_l, beta_l}, LnParams{gamma_s, beta_s}, extra_a, extra_b,
+      xhat_l, rstd_l, xhat_s, rstd_s, qpos, qpos0);
+  return check_launch("qpos_fwd");
+}
+
+MSR3D_API int msr3d_qpos_bwd_f32(const float *dq, const float *dq1, const float *dq2,
+                                 const float *sz, int M, const float *gamma_l,
+                                 const float *gamma_s, const float *xhat_l, const float *rstd_l,
+                                 const float *xhat_s, const float *rstd_s, float *dh1,
+                                 float *dgamma_l, float *dbeta_l, float *dgamma_s, float *dbeta_s,
+                                 float *dWs, float *dbs, float *dbl, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(dq && sz && gamma_l && gamma_s && xhat_l && rstd_l && xhat_s && rstd_s && dh1,
+                "qpos_bwd: null pointer");
+  if (M <= 0) return MSR3D_OK;
+  qpos_bwd_kernel<<<ln_grid(M), kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+      dq, dq1, dq2, sz, M, LnParams{gamma_l, nullptr}, LnParams{gamma_s, nullptr}, xhat_l, rstd_l, xhat_s,
+      rstd_s, dh1, dgamma_l, dbeta_l, dgamma_s, dbeta_s, dWs, dbs, dbl);
+  return check_launch("qpos_bwd");
+}
+
+MSR3D_API int msr3d_colsum_add_f32(const float *src, long long ld, int M, int N, float *dst0,
+                                   float *dst1, float *dst2, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(src && dst0 && M >= 0 && N >= 0, "colsum: bad args");
+  if (M == 0 || N == 0) return MSR3D_OK;
+  const int rows = 32;
+  dim3 grid(ceil_div(N, 256), ceil_div(M, rows));
+  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld, M, N, dst0, dst1, dst2, rows);
+  return check_launch("colsum");
+}
+
+MSR3D_API int msr3d_attn_fwd_f32(const float *qkvc, int ldq, const float *pw,
+                                 const unsigned char *key_pad, int B, int L, int H, float *P,
+                                 float *LOC, float *ctx, int ldc, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(qkvc && pw && P && LOC && ctx, "attn_fwd: null pointer");
+  MSR3D_REQUIRE(L >= 1 && L <= kMaxL && H >= 1 && ldq >= 3 * H * kDh + H * 6 && ldc >= H * kDh,
+                "attn_fwd: bad sizes L=%d H=%d", L, H);
+  if (B == 0) return MSR3D_OK;
+  const int LT = ((L + 31) / 32) * 32;
+  const size_t smem = ((size_t)kDh * LT + (size_t)L * kDh) * sizeof(float);
+  const int zr = L > 2 * kAttnWarps ? 2 : 1;
+  attn_fwd_kernel<<<dim3(H, B, zr), kAttnWarps * 32, smem, (cudaStream_t)stream>>>(
+      qkvc, ldq, pw, key_pad, L, H, P, LOC, ctx, ldc);
+  return check_launch("attn_fwd");
+}
+
+MSR3D_API int msr3d_attn_bwd_f32(const float *dctx, int ldc, const float *qkvc, int ldq,
+                                 const float *pw, const float *P, const float *LOC, int B, int L,
+                                 int H, float *dqkvc, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(dctx && qkvc && pw && P && LOC && dqkvc, "attn_bwd: null pointer");
+  MSR3D_REQUIRE(L >= 1 && L <= kMaxL && H >= 1, "attn_bwd: bad sizes");
+  if (B == 0) return MSR3D_OK;
+  auto bytes = [](int l) {
+    const int lt = ((l + 31) / 32) * 32;
+    return ((size_t)3 * l * kDh + (size_t)kDh * lt + (size_t)2 * l * (lt + 1)) * sizeof(float);
+  };
+  static bool configured = false;
+  if (!configured) {
+    MSR3D_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)bytes(kMaxL)));
+    configured = true;
+  }
+  attn_bwd_kernel<<<dim3(H, B), kAttnWarps * 32, bytes(L), (cudaStream_t)stream>>>(
+      dctx, ldc, qkvc, ldq, pw, P, LOC, L, H, dqkvc);
+  return check_launch("attn_bwd");
+}
+
+/* Test hook: the multiplicative mask (0 or 1/(1-p)) every kernel applies at `site` to element
+ * offsets [0, n). */
+MSR3D_API int msr3d_dropout_mask_f32(unsigned long long seed, const unsigned long long *seed_ptr,
+                                     float p, unsigned site, long long n, float *out,
+                                     msr3d_stream_t stream) {
+  MSR3D_REQUIRE(out && n >= 0 && p >= 0.f && p < 1.f, "dropout_mask: bad args");
+  if (n == 0) return MSR3D_OK;
+  dropout_mask_kernel<<<kNumSMs * 2, 256, 0, (cudaStream_t)stream>>>(mk(seed, p, seed_ptr), site, n, out);
+  return check_launch("dropout_mask");
+}

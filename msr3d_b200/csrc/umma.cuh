@@ -177,5 +177,18 @@ __device__ __forceinline__ void split_pack2(float a, float b, uint32_t &hi, uint
   lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
 }
 
+// three-way split x = h + m + l (24 mantissa bits): with the six products hh, hm, mh, hl, lh, mm the
+// tensor-core result is fp32-grade even for badly conditioned sums (weight gradients).
+__device__ __forceinline__ void split_pack2_3way(float a, float b, uint32_t &h, uint32_t &m, uint32_t &l) {
+  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+  const float ar = a - __bfloat162float(ah), br = b - __bfloat162float(bh);
+  const __nv_bfloat16 am = __float2bfloat16_rn(ar), bm = __float2bfloat16_rn(br);
+  const __nv_bfloat16 al = __float2bfloat16_rn(ar - __bfloat162float(am));
+  const __nv_bfloat16 bl = __float2bfloat16_rn(br - __bfloat162float(bm));
+  h = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+  m = (uint32_t)__bfloat16_as_ushort(am) | ((uint32_t)__bfloat16_as_ushort(bm) << 16);
+  l = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+}
+
 }  // namespace umma
 }  // namespace msr3d

@@ -361,7 +361,8 @@ class PointNetPP(nn.Module):
         return t
 
     @torch.no_grad()
-    def forward_fused(self, pc, split: Optional[int] = None, trace: Optional[dict] = None):
+    def forward_fused(self, pc, split: Optional[int] = None, trace: Optional[dict] = None,
+                      out: Optional[torch.Tensor] = None):
         """pc: (B', P, 6) contiguous CUDA f32 -> (B', C_out).  10 kernel launches."""
         pk = self._packed_weights()
         Bc, P, _ = pc.shape
@@ -369,27 +370,27 @@ class PointNetPP(nn.Module):
         np1, np2 = self.sa_n_points[0], self.sa_n_points[1]
         w1, w2, w3 = self._widths(0), self._widths(1), self._widths(2)
         # level 1: neighbours are the raw (x,y,z,r,g,b) records
-        fps1, xyz1, ball1 = ops.sa_group(pc, np1, self.sa_radii[0], 32)
+        fps1, xyz1, ball1 = ops.sa_group(pc, np1, self.sa_radii[0], 32, tag="sa1_group")
         f1 = self._workspace("f1", (Bc, np1, w1[-1]), dev)
-        ops.sa_mlp_fused(pc[..., 3:], 3, pc, xyz1, ball1, pk["sa1"][0], pk["sa1"][1], w1[1:], f1, split)
+        ops.sa_mlp_fused(pc[..., 3:], 3, pc, xyz1, ball1, pk["sa1"][0], pk["sa1"][1], w1[1:], f1, split, tag="sa1_mlp")
         # level 2
-        fps2, xyz2, ball2 = ops.sa_group(xyz1, np2, self.sa_radii[1], 32)
+        fps2, xyz2, ball2 = ops.sa_group(xyz1, np2, self.sa_radii[1], 32, tag="sa2_group")
         k3 = w2[-1] + 3
         ld3 = -(-k3 // 16) * 16
         x3 = self._workspace("x3", (Bc, np2, ld3), dev, zero=True)   # [feat | xyz | 0]: GroupAll operand
-        ops.sa_mlp_fused(f1, w1[-1], xyz1, xyz2, ball2, pk["sa2"][0], pk["sa2"][1], w2[1:], x3, split)
+        ops.sa_mlp_fused(f1, w1[-1], xyz1, xyz2, ball2, pk["sa2"][0], pk["sa2"][1], w2[1:], x3, split, tag="sa2_mlp")
         from . import _C
         _C.call("msr3d_scatter_xyz_cols_f32", xyz2.data_ptr(), x3.data_ptr(), ld3, w2[-1], Bc * np2,
                 torch.cuda.current_stream().cuda_stream)
         # level 3 (GroupAll): three GEMMs, max over the np2 points of a cloud in the last epilogue
         a = x3.view(Bc * np2, ld3)[:, :k3]
         h1 = ops.linear_tc(a, pk["sa3"][0][0], pk["sa3"][1][0], act="relu", split=split,
-                           out=self._workspace("h1", (Bc * np2, w3[1]), dev))
+                           out=self._workspace("h1", (Bc * np2, w3[1]), dev), tag="sa3_l1")
         h2 = ops.linear_tc(h1, pk["sa3"][0][1], pk["sa3"][1][1], act="relu", split=split,
-                           out=self._workspace("h2", (Bc * np2, w3[2]), dev))
+                           out=self._workspace("h2", (Bc * np2, w3[2]), dev), tag="sa3_l2")
         g = ops.linear_tc(h2, pk["sa3"][0][2], pk["sa3"][1][2], act="relu", pool=np2, split=split,
-                          out=self._workspace("g", (Bc, w3[3]), dev))
-        out = ops.linear_tc(g, pk["fc"][0], pk["fc"][1], split=split)
+                          out=self._workspace("g", (Bc, w3[3]), dev), tag="sa3_l3")
+        out = ops.linear_tc(g, pk["fc"][0], pk["fc"][1], split=split, tag="fc", out=out)
         if trace is not None:
             trace.update(fps1=fps1, ball1=ball1, xyz1=xyz1, f1=f1, fps2=fps2, ball2=ball2, xyz2=xyz2,
                          x3=x3, g=g)

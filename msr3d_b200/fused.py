@@ -1,0 +1,504 @@
+"""Fused execution engine for the trainable half of the MSR3D prompter.
+
+`FusedPrompter` takes a (drop-in) `OSE3DSituation` and runs its forward, backward and optimiser
+step as a fixed program of ~85 launches of this repo's kernels (tensor-core GEMMs from
+csrc/linear_tc.cu, everything else from csrc/spatial.cu, csrc/optim.cu, and the fused PointNet++
+encoder), optionally replayed as ONE CUDA graph per step.  It replaces what the reference does
+with ~500 ATen launches plus a host sync per layer.
+
+Parameters are re-homed into one flat fp32 buffer (each `p.data` becomes a view) laid out as
+[ weights (decayed) | biases (not decayed) | parameters the shipped mode never touches ] with the
+four input projections of every attention block (w_qs, w_ks, w_vs, lang_cond_fc) adjacent, so
+that QKV+cond is a single (816 x 256) GEMM, its weight gradient another one, and the gradient
+all-reduce and AdamW are single flat operations.  State-dict keys and shapes are unchanged.
+
+Supported (= every shipped config, configs/*.yaml): situation_type as_transform_for_objects or
+as_object_add_loc-style query positions are NOT both covered — see `supported()`; anything else
+keeps running through the module tree in spatial.py / prompter.py.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _C, ops
+
+c_int, c_uint, c_ll, c_float, c_vp = ctypes.c_int, ctypes.c_uint, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
+c_ull = ctypes.c_ulonglong
+
+
+class GemmDesc(ctypes.Structure):
+    """Mirror of `msr3d_gemm_desc` (include/msr3d_b200.h)."""
+    _fields_ = [("A", c_vp), ("stride_am", c_ll), ("stride_ak", c_ll),
+                ("B", c_vp), ("stride_bn", c_ll), ("stride_bk", c_ll),
+                ("bias", c_vp), ("residual", c_vp), ("ld_residual", c_ll),
+                ("aux", c_vp), ("ld_aux", c_ll), ("out", c_vp), ("ld_out", c_ll),
+                ("M", c_int), ("N", c_int), ("K", c_int),
+                ("act", c_int), ("split", c_int), ("accumulate", c_int), ("epilogue", c_int), ("ksplit", c_int),
+                ("a_xform", c_int), ("b_xform", c_int),
+                ("a_site", c_uint), ("b_site", c_uint), ("epi_site", c_uint),
+                ("dropout_p", c_float), ("seed", c_ull), ("seed_ptr", c_vp)]
+
+
+_C.register_protos({
+    "msr3d_gemm_tc_f32": [ctypes.POINTER(GemmDesc), c_vp],
+    "msr3d_spatial_geometry_f32": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "msr3d_qpos_fwd_f32": [c_vp, c_vp, c_int] + [c_vp] * 14 + [c_vp],
+    "msr3d_qpos_bwd_f32": [c_vp, c_vp, c_vp, c_vp, c_int] + [c_vp] * 14 + [c_vp],
+    "msr3d_attn_fwd_f32": [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp],
+    "msr3d_attn_bwd_f32": [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp],
+    "msr3d_attn_tail_fwd_f32": [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_ull, c_vp, c_float, c_uint, c_uint,
+                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "msr3d_attn_tail_bwd_f32": [c_vp, c_int, c_vp, c_vp, c_ull, c_vp, c_float, c_uint, c_uint,
+                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "msr3d_ffn_tail_fwd_f32": [c_vp, c_vp, c_int, c_vp, c_vp, c_ull, c_vp, c_float, c_uint,
+                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "msr3d_ffn_tail_bwd_f32": [c_vp, c_int, c_vp, c_ull, c_vp, c_float, c_uint, c_vp, c_vp,
+                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "msr3d_colsum_add_f32": [c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "msr3d_dropout_mask_f32": [c_ull, c_vp, c_float, c_uint, c_ll, c_vp, c_vp],
+    "msr3d_adamw_clip_step_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp],
+})
+
+H = 256          # hidden size the fused kernels are built for
+NHEAD = 8
+QKVC = 3 * H + NHEAD * 6
+UNUSED_IN_SHIPPED_MODE = ("anchor_feat", "orientation_encoder.", "loc_layers.")
+
+
+def supported(model) -> Optional[str]:
+    """None if `model` (an OSE3DSituation) can run on the fused engine, else the reason."""
+    c = model.cfg
+    se = c.spatial_encoder
+    checks = [
+        (c.hidden_size == H, "hidden_size != 256"),
+        (se.num_attention_heads == NHEAD, "heads != 8"),
+        (bool(c.use_spatial_attn), "use_spatial_attn is off"),
+        (se.spatial_attn_fusion == "cond" and bool(se.spatial_multihead) and se.spatial_dim == 5, "fusion != cond/multihead/dim5"),
+        (se.pairwise_rel_type == "center", "pairwise_rel_type != center"),
+        (se.activation == "gelu", "activation != gelu"),
+        (se.obj_loc_encoding in ("same_all", "same_0"), "obj_loc_encoding == diff_all"),
+        (model.situation_type == "as_transform_for_objects", f"situation_type {model.situation_type}"),
+        (not c.attn_flat.use_attn_flat, "attn_flat on"),
+        (bool(c.use_orientation), "use_orientation off"),
+        (c.vision.name == "PcdObjEncoder", "vision backbone is not PcdObjEncoder"),
+        (c.loc_fourier_dim == 63, "loc_fourier_dim != 63"),
+        (se.dim_feedforward % 4 == 0, "dim_feedforward % 4"),
+    ]
+    for ok, why in checks:
+        if not ok:
+            return why
+    return None
+
+
+class FusedPrompter:
+    def __init__(self, model, lr=3e-5, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
+                 grad_norm: Optional[float] = 5.0, world_size: int = 1, split: int = 3,
+                 grad_split: int = 6):
+        why = supported(model)
+        if why is not None:
+            raise NotImplementedError(f"fused prompter: unsupported configuration ({why})")
+        self.model = model
+        self.split = split                    # transformer GEMMs (forward + data gradients)
+        self.enc_split = 3 if split == 6 else split   # frozen encoder: two-way split is ample (1.5e-5)
+        self.grad_split = grad_split if split >= 3 else split
+        self.world_size = world_size
+        self.dev = next(model.parameters()).device
+        assert self.dev.type == "cuda", "the fused engine runs on CUDA tensors only"
+        se = model.cfg.spatial_encoder
+        self.nl, self.F = se.num_layers, se.dim_feedforward
+        self.same_all = se.obj_loc_encoding == "same_all"
+        self.dist_norm = int(bool(se.spatial_dist_norm))
+        self.p_drop = float(se.dropout)
+        self._rehome()
+        dev = self.dev
+        self.m = torch.zeros_like(self.flat_p[:self.n_opt])
+        self.v = torch.zeros_like(self.flat_p[:self.n_opt])
+        # {sumsq, step, lr, beta1, beta2, eps, weight_decay, max_norm}
+        self.opt_state = torch.tensor([0.0, 0.0, lr, betas[0], betas[1], eps, weight_decay,
+                                       grad_norm if grad_norm else 0.0], dtype=torch.float32, device=dev)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.seed_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.seed = 0x5EED
+        self._shape = None
+        self._keep = []          # ctypes descriptors must outlive the program
+        self.graph = None
+
+    # ------------------------------------------------------------------ parameters
+    def _rehome(self):
+        named = [(n, p) for n, p in self.model.named_parameters() if p.requires_grad]
+        by_name = dict(named)
+
+        def unused(n):
+            return n.startswith(UNUSED_IN_SHIPPED_MODE)
+
+        order_w, order_b, order_u = [], [], []
+        taken = set()
+        for i in range(self.nl):
+            pre = f"spatial_encoder.{i}.self_attn."
+            for kind, dst in (("weight", order_w), ("bias", order_b)):
+                for nm in ("w_qs", "w_ks", "w_vs", "lang_cond_fc"):
+                    dst.append(f"{pre}{nm}.{kind}")
+                    taken.add(f"{pre}{nm}.{kind}")
+        for n, _ in named:
+            if n in taken:
+                continue
+            (order_u if unused(n) else (order_b if "bias" in n else order_w)).append(n)
+        self.order = order_w + order_b + order_u
+        offs, off = {}, 0
+        for n in self.order:
+            offs[n] = off
+            off += (by_name[n].numel() + 3) // 4 * 4
+            if n == order_w[-1]:
+                pass
+        self.n_decay = offs[order_b[0]] if order_b else off
+        self.n_opt = offs[order_u[0]] if order_u else off
+        self.flat_p = torch.zeros(off, dtype=torch.float32, device=self.dev)
+        self.flat_g = torch.zeros(off, dtype=torch.float32, device=self.dev)
+        self.offs = offs
+        for n in self.order:
+            p = by_name[n]
+            view = self.flat_p[offs[n]:offs[n] + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.flat_g[offs[n]:offs[n] + p.numel()].view_as(p)
+        self.n_trainable = sum(p.numel() for _, p in named)
+
+    def P(self, name):  # device pointer of a parameter / its gradient
+        return self.flat_p.data_ptr() + 4 * self.offs[name]
+
+    def G(self, name):
+        return self.flat_g.data_ptr() + 4 * self.offs[name]
+
+    # ------------------------------------------------------------------ workspaces + program
+    def _buf(self, *shape, dtype=torch.float32, zero=False):
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.dev)
+        return t
+
+    def _build(self, B, L, O_pts):
+        """Allocate static buffers and pre-bind every launch for (B scenes, L objects, P points)."""
+        M, F, nl = B * L, self.F, self.nl
+        f = self._buf
+        w = self.ws = {}
+        w["obj_fts"] = f(B, L, O_pts, 6)
+        w["obj_locs"] = f(B, L, 6)
+        w["obj_masks"] = torch.ones(B, L, dtype=torch.bool, device=self.dev)
+        w["key_pad"] = torch.zeros(B, L, dtype=torch.uint8, device=self.dev)
+        w["anchor_locs"] = f(B, 3)
+        w["anchor_ori"] = f(B, 4)
+        w["upstream"] = f(M, H)
+        w["pw"], w["ff"], w["sz"] = f(B, L, L, 5), f(M, 64), f(M, 3)
+        w["h1"], w["qpos"], w["qpos0"] = f(M, H), f(M, H), f(M, H)
+        for k in ("xhat_l", "xhat_s"):
+            w[k] = f(M, H)
+        for k in ("rstd_l", "rstd_s"):
+            w[k] = f(M)
+        w["x_in"] = [f(M, H) for _ in range(nl)]
+        w["qkvc"] = [f(M, QKVC) for _ in range(nl)]
+        w["P"] = [f(B, NHEAD, L, L) for _ in range(nl)]
+        w["LOC"] = [f(B, NHEAD, L, L) for _ in range(nl)]
+        w["ctx"] = [f(M, H) for _ in range(nl)]
+        w["o"] = f(M, H)
+        for k in ("xhat_a", "xhat_1", "xhat_2", "y2"):
+            w[k] = [f(M, H) for _ in range(nl)]
+        for k in ("rstd_a", "rstd_1", "rstd_2"):
+            w[k] = [f(M) for _ in range(nl)]
+        w["u"] = [f(M, F) for _ in range(nl)]
+        w["f"] = f(M, H)
+        w["tokens"] = f(M, H)
+        # backward
+        w["dy2"], w["df"], w["do"], w["dctx"] = f(M, H), f(M, H), f(M, H), f(M, H)
+        w["du"], w["dqkvc"], w["dh1"] = f(M, F), f(M, QKVC), f(M, H)
+        w["dx"] = [f(M, H) for _ in range(nl)]
+        self._shape = (B, L, O_pts)
+        self.graph = None
+
+    def _gemm(self, prog, A, sa, Bm, sb, M, N, K, out, ldo, bias=0, residual=0, ldr=0, aux=0, ldaux=0,
+              act=0, accumulate=0, epilogue=0, ksplit=1, a_xform=0, b_xform=0, a_site=0, b_site=0,
+              epi_site=0, tag=None, wgrad=False):
+        d = GemmDesc()
+        d.A, d.stride_am, d.stride_ak = A, sa[0], sa[1]
+        d.B, d.stride_bn, d.stride_bk = Bm, sb[0], sb[1]
+        d.bias, d.residual, d.ld_residual, d.aux, d.ld_aux = bias or None, residual or None, ldr, aux or None, ldaux
+        d.out, d.ld_out, d.M, d.N, d.K = out, ldo, M, N, K
+        d.act, d.accumulate, d.epilogue, d.ksplit = act, accumulate, epilogue, ksplit
+        # weight gradients contract over tokens and cancel heavily: three-way split (fp32-grade)
+        d.split = self.grad_split if wgrad else self.split
+        d.a_xform, d.b_xform, d.a_site, d.b_site, d.epi_site = a_xform, b_xform, a_site, b_site, epi_site
+        d.dropout_p = self._p
+        d.seed = self.seed
+        d.seed_ptr = self.seed_counter.data_ptr()
+        self._keep.append(d)
+        fn = _C.lib().msr3d_gemm_tc_f32
+        ref = ctypes.byref(d)
+        prog.append(("msr3d_gemm_tc_f32", fn, (ref,), tag))
+
+    def _call(self, prog, name, *args, tag=None):
+        prog.append((name, getattr(_C.lib(), name), args, tag))
+
+    def _programs(self, training: bool):
+        """(forward, backward) launch lists for the current static buffers."""
+        B, L, _ = self._shape
+        M, F, nl, w = B * L, self.F, self.nl, self.ws
+        self._p = self.p_drop if training else 0.0
+        p, seed, sptr = self._p, self.seed, self.seed_counter.data_ptr()
+        P, G = self.P, self.G
+        ptr = lambda t: t.data_ptr()  # noqa: E731
+        fwd: List = []
+        bwd: List = []
+        # ---------------- forward
+        self._call(fwd, "msr3d_spatial_geometry_f32", ptr(w["obj_locs"]), ptr(w["anchor_locs"]), ptr(w["anchor_ori"]),
+                   B, L, self.dist_norm, 1, ptr(w["pw"]), ptr(w["ff"]), ptr(w["sz"]), tag="geometry")
+        self._gemm(fwd, ptr(w["ff"]), (64, 1), P("loc_embedding_encoder.0.weight"), (63, 1), M, H, 63, ptr(w["h1"]), H,
+                   bias=P("loc_embedding_encoder.0.bias"), tag="loc_fc")
+        self._call(fwd, "msr3d_qpos_fwd_f32", ptr(w["h1"]), ptr(w["sz"]), M, P("size_embedding_encoder.0.weight"),
+                   P("size_embedding_encoder.0.bias"), P("loc_embedding_encoder.1.weight"), P("loc_embedding_encoder.1.bias"),
+                   P("size_embedding_encoder.1.weight"), P("size_embedding_encoder.1.bias"),
+                   P("object_orientation_feat"), P("object_type_embedding.weight"),
+                   ptr(w["xhat_l"]), ptr(w["rstd_l"]), ptr(w["xhat_s"]), ptr(w["rstd_s"]), ptr(w["qpos"]), ptr(w["qpos0"]),
+                   tag="qpos")
+        E = self.emb_dim
+        self._gemm(fwd, self.emb_ptr, (E, 1), P("obj_linear_projection.weight"), (E, 1), M, H, E, ptr(w["x_in"][0]), H,
+                   bias=P("obj_linear_projection.bias"), residual=ptr(w["qpos0"]), ldr=H, tag="obj_proj")
+        for i in range(nl):
+            pre = f"spatial_encoder.{i}."
+            sa = pre + "self_attn."
+            s0 = i * 8
+            x_in = ptr(w["x_in"][i])
+            self._gemm(fwd, x_in, (H, 1), P(sa + "w_qs.weight"), (H, 1), M, QKVC, H, ptr(w["qkvc"][i]), QKVC,
+                       bias=P(sa + "w_qs.bias"), tag="qkvc")
+            self._call(fwd, "msr3d_attn_fwd_f32", ptr(w["qkvc"][i]), QKVC, ptr(w["pw"]), ptr(w["key_pad"]), B, L, NHEAD,
+                       ptr(w["P"][i]), ptr(w["LOC"][i]), ptr(w["ctx"][i]), H, tag="attn_core")
+            self._gemm(fwd, ptr(w["ctx"][i]), (H, 1), P(sa + "fc.weight"), (H, 1), M, H, H, ptr(w["o"]), H,
+                       bias=P(sa + "fc.bias"), tag="out_proj")
+            self._call(fwd, "msr3d_attn_tail_fwd_f32", ptr(w["o"]), x_in, M, P(sa + "layer_norm.weight"),
+                       P(sa + "layer_norm.bias"), P(pre + "norm1.weight"), P(pre + "norm1.bias"), seed, sptr, p,
+                       s0 + 0, s0 + 1, ptr(w["xhat_a"][i]), ptr(w["rstd_a"][i]), ptr(w["xhat_1"][i]),
+                       ptr(w["rstd_1"][i]), ptr(w["y2"][i]), tag="attn_tail")
+            self._gemm(fwd, ptr(w["y2"][i]), (H, 1), P(pre + "linear1.weight"), (H, 1), M, F, H, ptr(w["u"][i]), F,
+                       bias=P(pre + "linear1.bias"), tag="ffn1")
+            fwd.append(("memset", None, (w["f"],), None))
+            self._gemm(fwd, ptr(w["u"][i]), (F, 1), P(pre + "linear2.weight"), (F, 1), M, H, F, ptr(w["f"]), H,
+                       bias=P(pre + "linear2.bias"), accumulate=2, ksplit=8, a_xform=2, a_site=s0 + 2, tag="ffn2")
+            last = i == nl - 1
+            add = 0 if (last or not self.same_all) else ptr(w["qpos"])
+            self._call(fwd, "msr3d_ffn_tail_fwd_f32", ptr(w["f"]), ptr(w["y2"][i]), M, P(pre + "norm2.weight"),
+                       P(pre + "norm2.bias"), seed, sptr, p, s0 + 3, add or None, ptr(w["xhat_2"][i]),
+                       ptr(w["rstd_2"][i]), ptr(w["tokens"]) if last else None,
+                       None if last else ptr(w["x_in"][i + 1]), tag="ffn_tail")
+        # ---------------- backward (gradients accumulate into the flat buffer)
+        dy3 = ptr(w["upstream"])
+        for i in reversed(range(nl)):
+            pre = f"spatial_encoder.{i}."
+            sa = pre + "self_attn."
+            s0 = i * 8
+            dx = ptr(w["dx"][i])
+            self._call(bwd, "msr3d_ffn_tail_bwd_f32", dy3, M, P(pre + "norm2.weight"), seed, sptr, p, s0 + 3,
+                       ptr(w["xhat_2"][i]), ptr(w["rstd_2"][i]), ptr(w["dy2"]), ptr(w["df"]), G(pre + "norm2.weight"),
+                       G(pre + "norm2.bias"), G(pre + "linear2.bias"), tag="ffn_tail_bwd")
+            # dW2 (H x F) += df^T . dropout(gelu(u))
+            self._gemm(bwd, ptr(w["df"]), (1, H), ptr(w["u"][i]), (1, F), H, F, M, G(pre + "linear2.weight"), F,
+                       accumulate=1, b_xform=2, b_site=s0 + 2, tag="dW2", wgrad=True)
+            # du = (df . W2) * gelu'(u) * mask
+            self._gemm(bwd, ptr(w["df"]), (H, 1), P(pre + "linear2.weight"), (1, F), M, F, H, ptr(w["du"]), F,
+                       epilogue=1, aux=ptr(w["u"][i]), ldaux=F, epi_site=s0 + 2, tag="du")
+            # dW1 (F x H) += du^T . y2
+            self._gemm(bwd, ptr(w["du"]), (1, F), ptr(w["y2"][i]), (1, H), F, H, M, G(pre + "linear1.weight"), H,
+                       accumulate=1, tag="dW1", wgrad=True)
+            self._call(bwd, "msr3d_colsum_add_f32", ptr(w["du"]), F, M, F, G(pre + "linear1.bias"), None, None, tag="db1")
+            # dy2 += du . W1
+            self._gemm(bwd, ptr(w["du"]), (F, 1), P(pre + "linear1.weight"), (1, H), M, H, F, ptr(w["dy2"]), H,
+                       accumulate=2, ksplit=8, tag="dy2")
+            self._call(bwd, "msr3d_attn_tail_bwd_f32", ptr(w["dy2"]), M, P(sa + "layer_norm.weight"),
+                       P(pre + "norm1.weight"), seed, sptr, p, s0 + 0, s0 + 1, ptr(w["xhat_a"][i]),
+                       ptr(w["rstd_a"][i]), ptr(w["xhat_1"][i]), ptr(w["rstd_1"][i]), dx, ptr(w["do"]),
+                       G(sa + "layer_norm.weight"), G(sa + "layer_norm.bias"), G(pre + "norm1.weight"),
+                       G(pre + "norm1.bias"), G(sa + "fc.bias"), tag="attn_tail_bwd")
+            # dWo (H x H) += do^T . ctx ;  dctx = do . Wo
+            self._gemm(bwd, ptr(w["do"]), (1, H), ptr(w["ctx"][i]), (1, H), H, H, M, G(sa + "fc.weight"), H,
+                       accumulate=1, tag="dWo", wgrad=True)
+            self._gemm(bwd, ptr(w["do"]), (H, 1), P(sa + "fc.weight"), (1, H), M, H, H, ptr(w["dctx"]), H, tag="dctx")
+            self._call(bwd, "msr3d_attn_bwd_f32", ptr(w["dctx"]), H, ptr(w["qkvc"][i]), QKVC, ptr(w["pw"]),
+                       ptr(w["P"][i]), ptr(w["LOC"][i]), B, L, NHEAD, ptr(w["dqkvc"]), tag="attn_core_bwd")
+            # dWqkvc (816 x H) += dqkvc^T . x_in ; bias ; dx += dqkvc . Wqkvc
+            self._gemm(bwd, ptr(w["dqkvc"]), (1, QKVC), ptr(w["x_in"][i]), (1, H), QKVC, H, M, G(sa + "w_qs.weight"), H,
+                       accumulate=1, tag="dWqkvc", wgrad=True)
+            self._call(bwd, "msr3d_colsum_add_f32", ptr(w["dqkvc"]), QKVC, M, QKVC, G(sa + "w_qs.bias"), None, None,
+                       tag="dbqkvc")
+            self._gemm(bwd, ptr(w["dqkvc"]), (QKVC, 1), P(sa + "w_qs.weight"), (1, H), M, H, QKVC, dx, H,
+                       accumulate=2, ksplit=4, tag="dx")
+            dy3 = dx
+        dx0 = ptr(w["dx"][0])
+        # x_in0 = emb Wp^T + bp + orientation_feat + type_emb[0] + qpos
+        self._call(bwd, "msr3d_colsum_add_f32", dx0, H, M, H, G("obj_linear_projection.bias"),
+                   G("object_orientation_feat"), G("object_type_embedding.weight"), tag="dbias_proj")
+        E = self.emb_dim
+        self._gemm(bwd, dx0, (1, H), self.emb_ptr, (1, E), H, E, M, G("obj_linear_projection.weight"), E,
+                   accumulate=1, tag="dWproj", wgrad=True)
+        dq = [ptr(w["dx"][i]) for i in range(nl)] if self.same_all else [dx0]
+        dq += [None] * (3 - len(dq))
+        assert len(dq) == 3, "fused qpos backward sums at most three layers"
+        self._call(bwd, "msr3d_qpos_bwd_f32", dq[0], dq[1], dq[2], ptr(w["sz"]), M, P("loc_embedding_encoder.1.weight"),
+                   P("size_embedding_encoder.1.weight"), ptr(w["xhat_l"]), ptr(w["rstd_l"]), ptr(w["xhat_s"]),
+                   ptr(w["rstd_s"]), ptr(w["dh1"]), G("loc_embedding_encoder.1.weight"), G("loc_embedding_encoder.1.bias"),
+                   G("size_embedding_encoder.1.weight"), G("size_embedding_encoder.1.bias"),
+                   G("size_embedding_encoder.0.weight"), G("size_embedding_encoder.0.bias"),
+                   G("loc_embedding_encoder.0.bias"), tag="qpos_bwd")
+        self._gemm(bwd, ptr(w["dh1"]), (1, H), ptr(w["ff"]), (1, 64), H, 63, M, G("loc_embedding_encoder.0.weight"), 63,
+                   accumulate=1, tag="dWloc", wgrad=True)
+        return fwd, bwd
+
+    def _run(self, prog):
+        stream = torch.cuda.current_stream().cuda_stream
+        timer = ops.TIMER
+        for name, fn, args, tag in prog:
+            if fn is None:                  # memset of a workspace tensor
+                args[0].zero_()
+                continue
+            if timer is not None and tag:
+                with timer.range(tag):
+                    rc = fn(*args, stream)
+            else:
+                rc = fn(*args, stream)
+            if rc != 0:
+                raise _C.Msr3dError(f"{name} [{tag}] failed ({rc}): {_C.lib().msr3d_last_error().decode()}")
+
+    # ------------------------------------------------------------------ public API
+    def prepare(self, B, L, n_points, training=True):
+        """(Re)build buffers and launch programs for a batch geometry / train-eval mode."""
+        key = (B, L, n_points, bool(training), self.split)
+        if getattr(self, "_key", None) == key:
+            return
+        enc = self.model.obj_encoder
+        self.emb_dim = enc.pcd_net.fc.out_features
+        if self._shape != (B, L, n_points):
+            self._build(B, L, n_points)
+            self.ws["emb"] = self._buf(B * L, self.emb_dim)
+        self.emb_ptr = self.ws["emb"].data_ptr()
+        self._keep = []
+        self.fwd_prog, self.bwd_prog = self._programs(training)
+        self._key = key
+        self.graph = None
+
+    def load_inputs(self, batch, upstream: Optional[torch.Tensor] = None, non_blocking=True):
+        """Copy a SceneBatch (host pinned or device) into the static input buffers."""
+        w = self.ws
+        w["obj_fts"].copy_(batch.obj_fts, non_blocking=non_blocking)
+        w["obj_locs"].copy_(batch.obj_locs, non_blocking=non_blocking)
+        w["obj_masks"].copy_(batch.obj_masks, non_blocking=non_blocking)
+        w["anchor_locs"].copy_(batch.anchor_locs, non_blocking=non_blocking)
+        w["anchor_ori"].copy_(batch.anchor_orientation, non_blocking=non_blocking)
+        if upstream is not None:
+            w["upstream"].copy_(upstream.reshape(w["upstream"].shape), non_blocking=non_blocking)
+
+    def _encode(self):
+        w = self.ws
+        enc = self.model.obj_encoder
+        B, L, Pn, _ = w["obj_fts"].shape
+        enc.freeze_bn(enc.pcd_net)
+        enc.pcd_net.forward_fused(w["obj_fts"].view(B * L, Pn, 6), self.enc_split, out=w["emb"])
+
+    def forward(self):
+        """Encoder + transformer forward on the static buffers; returns tokens (B, L, 256) view."""
+        w = self.ws
+        torch.logical_not(w["obj_masks"], out=w["key_pad"].view(torch.bool))
+        self._encode()
+        self._run(self.fwd_prog)
+        B, L = w["obj_locs"].shape[:2]
+        return w["tokens"].view(B, L, H)
+
+    def backward(self):
+        """Backward from ws['upstream']; accumulates into the flat gradient buffer."""
+        self._run(self.bwd_prog)
+
+    def optimizer_step(self):
+        n, nd = self.n_opt, self.n_decay
+        _C.call("msr3d_adamw_clip_step_f32", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(),
+                self.v.data_ptr(), n, nd, 1.0 / self.world_size, self.opt_state.data_ptr(),
+                self.ticket.data_ptr(), self.seed_counter.data_ptr(), torch.cuda.current_stream().cuda_stream)
+
+    def set_lr(self, lr: float):
+        self.opt_state[2] = lr
+
+    @property
+    def launches_per_step(self) -> int:
+        """Kernel launches of this library in one training step (counted on the first eager step)."""
+        return getattr(self, "_launches", 0)
+
+    def train_step_eager(self):
+        """zero grads -> fwd -> bwd -> (all-reduce) -> clip + AdamW, on whatever is in the input buffers."""
+        n0 = _C.launch_count()
+        self._train_step_eager()
+        self._launches = _C.launch_count() - n0
+        B, L = self.ws["obj_locs"].shape[:2]
+        return self.ws["tokens"].view(B, L, H)
+
+    def _train_step_eager(self):
+        self.flat_g.zero_()
+        tokens = self.forward()
+        self.backward()
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_g[:self.n_opt])
+        self.optimizer_step()
+        return tokens
+
+    def capture(self):
+        """Capture forward+backward (and, single-GPU, the optimiser) into one CUDA graph."""
+        for _ in range(2):       # warm-up on a side stream: lazy attribute setup must not happen in capture
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self.flat_g.zero_()
+                self.forward()
+                self.backward()
+            torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.flat_g.zero_()
+            self.forward()
+            self.backward()
+            if self.world_size == 1:
+                self.optimizer_step()
+        self.graph = g
+
+    def train_step(self):
+        if self.graph is None:
+            return self.train_step_eager()
+        self.graph.replay()
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_g[:self.n_opt])
+            self.optimizer_step()
+        B, L = self.ws["obj_locs"].shape[:2]
+        return self.ws["tokens"].view(B, L, H)
+
+    def loss(self):
+        """Surrogate scalar <tokens, upstream> (what bench.py reads back)."""
+        return (self.ws["tokens"] * self.ws["upstream"]).sum()
+
+
+def gemm_tc(A: torch.Tensor, Bm: torch.Tensor, bias: Optional[torch.Tensor] = None, split: int = 3,
+            out: Optional[torch.Tensor] = None, accumulate: int = 0, ksplit: int = 1,
+            residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = A[M,K] @ Bm[N,K]^T (+ bias + residual) on the tensor cores; A and Bm are any 2-D
+    fp32 CUDA views (strides are passed through, nothing is packed or copied)."""
+    M, K = A.shape
+    N = Bm.shape[0]
+    assert Bm.shape[1] == K
+    if out is None:
+        out = torch.zeros(M, N, device=A.device) if accumulate else torch.empty(M, N, device=A.device)
+    d = GemmDesc()
+    d.A, d.stride_am, d.stride_ak = A.data_ptr(), A.stride(0), A.stride(1)
+    d.B, d.stride_bn, d.stride_bk = Bm.data_ptr(), Bm.stride(0), Bm.stride(1)
+    d.bias = bias.data_ptr() if bias is not None else None
+    if residual is not None:
+        d.residual, d.ld_residual = residual.data_ptr(), residual.stride(0)
+    d.out, d.ld_out, d.M, d.N, d.K = out.data_ptr(), out.stride(0), M, N, K
+    d.split, d.accumulate, d.ksplit = split, accumulate, ksplit
+    with torch.cuda.device(A.device):
+        _C.call("msr3d_gemm_tc_f32", ctypes.byref(d), torch.cuda.current_stream().cuda_stream)
+    return out

@@ -12,6 +12,20 @@ from . import _C
 ACT = {"none": 0, None: 0, "relu": 1, "gelu": 2}
 #: 3 = split-bf16 (fp32-grade), 1 = single bf16 pass.  Module default; tests flip it.
 DEFAULT_SPLIT = 3
+#: roofline.KernelTimer or None; when set, launches are bracketed by CUDA events on the current stream
+TIMER = None
+
+
+class _NoRange:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def _range(name):
+    return TIMER.range(name) if (TIMER is not None and name) else _NoRange()
 
 
 def _stream() -> int:
@@ -56,7 +70,8 @@ def pack_weight(W: torch.Tensor, row_scale: Optional[torch.Tensor] = None,
 
 def linear_tc(A: torch.Tensor, W: PackedWeight, bias: Optional[torch.Tensor] = None,
               act: str = "none", pool: int = 1, split: Optional[int] = None,
-              out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, accumulate: bool = False,
+              tag: Optional[str] = None) -> torch.Tensor:
     """out[M,N] = act(A[M,K] @ W^T + bias) on the tensor cores; A may be any 2-D view."""
     assert A.is_cuda and A.dtype == torch.float32 and A.dim() == 2
     assert W.BN == 128 and W.BK == 64
@@ -66,14 +81,14 @@ def linear_tc(A: torch.Tensor, W: PackedWeight, bias: Optional[torch.Tensor] = N
     if out is None:
         out = torch.empty(rows, W.N, dtype=torch.float32, device=A.device)
     assert out.stride(1) == 1 and out.shape[0] == rows and out.shape[1] >= W.N
-    with torch.cuda.device(A.device):
+    with torch.cuda.device(A.device), _range(tag):
         _C.call("msr3d_linear_tc_f32", A.data_ptr(), A.stride(0), A.stride(1), M, K,
                 W.data.data_ptr(), _ptr(bias), out.data_ptr(), out.stride(0), W.N, ACT[act],
                 int(pool), int(split or DEFAULT_SPLIT), int(accumulate), _stream())
     return out
 
 
-def sa_group(xyz_records: torch.Tensor, npoint: int, radius: float, nsample: int):
+def sa_group(xyz_records: torch.Tensor, npoint: int, radius: float, nsample: int, tag: Optional[str] = None):
     """FPS + centre gather + ball query.  xyz_records: (B, N, ld) f32, xyz = first 3 floats."""
     assert xyz_records.is_cuda and xyz_records.dtype == torch.float32 and xyz_records.is_contiguous()
     B, N, ld = xyz_records.shape
@@ -81,7 +96,7 @@ def sa_group(xyz_records: torch.Tensor, npoint: int, radius: float, nsample: int
     fps_idx = torch.empty(B, npoint, dtype=torch.int32, device=dev)
     new_xyz = torch.empty(B, npoint, 3, dtype=torch.float32, device=dev)
     ball = torch.empty(B, npoint, nsample, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _range(tag):
         _C.call("msr3d_sa_group_f32", xyz_records.data_ptr(), ld, B, N, int(npoint), float(radius),
                 int(nsample), fps_idx.data_ptr(), new_xyz.data_ptr(), ball.data_ptr(), _stream())
     return fps_idx, new_xyz, ball
@@ -89,14 +104,14 @@ def sa_group(xyz_records: torch.Tensor, npoint: int, radius: float, nsample: int
 
 def sa_mlp_fused(feat: torch.Tensor, nfeat: int, xyz: torch.Tensor, new_xyz: torch.Tensor,
                  ball: torch.Tensor, weights, biases, widths, out: torch.Tensor,
-                 split: Optional[int] = None) -> torch.Tensor:
+                 split: Optional[int] = None, tag: Optional[str] = None) -> torch.Tensor:
     """Gather + 3 x (conv+BN+ReLU) + max-pool; feat (B,Nsrc,ld_feat) and xyz (B,Nsrc,ld_xyz) may
     be views into the same record tensor (last-dim stride 1)."""
     B, npoint, nsample = ball.shape
     Nsrc = feat.shape[1]
     assert feat.stride(2) == 1 and xyz.stride(2) == 1 and feat.stride(0) == Nsrc * feat.stride(1)
     assert out.stride(2) == 1 and out.shape[:2] == (B, npoint)
-    with torch.cuda.device(feat.device):
+    with torch.cuda.device(feat.device), _range(tag):
         _C.call("msr3d_sa_mlp_fused_f32", feat.data_ptr(), feat.stride(1), int(nfeat), xyz.data_ptr(),
                 xyz.stride(1), new_xyz.data_ptr(), ball.data_ptr(), B, Nsrc, npoint, nsample,
                 weights[0].data.data_ptr(), weights[1].data.data_ptr(), weights[2].data.data_ptr(),

@@ -1,0 +1,99 @@
+"""Per-kernel live timing (CUDA events on the launching stream) and the roofline arithmetic of
+DESIGN.md §Kernels.  bench.py switches the timer on for the timed region; ops.* wrap their
+launches in `timer.range(name)` when a timer is installed."""
+from __future__ import annotations
+
+import json
+import os
+from contextlib import contextmanager
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def measured_peaks():
+    """MEASURED_PEAKS.json (driver-written) or the profiling guide's stated fallback."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class KernelTimer:
+    def __init__(self):
+        self.events = {}
+
+    @contextmanager
+    def range(self, name):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        try:
+            yield
+        finally:
+            b.record()
+            self.events.setdefault(name, []).append((a, b))
+
+    def mean_ms(self):
+        torch.cuda.synchronize()
+        return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in self.events.items()}
+
+    def counts(self):
+        return {k: len(v) for k, v in self.events.items()}
+
+
+def sa_level_flops(rows: int, widths) -> float:
+    """2*M*K*N over the layers of one SharedMLP applied to `rows` (centre,sample) positions."""
+    return float(sum(2.0 * rows * widths[i] * widths[i + 1] for i in range(len(widths) - 1)))
+
+
+def algorithmic_work(B: int, O: int, P: int):
+    """Algorithmic FLOPs / bytes per launch of each encoder kernel for (B,O,P) scenes
+    (25.95 / 67.50 / 18.90 MFLOP per cloud for SA1 / SA2 / SA3, 1.18 for fc)."""
+    Bc = B * O
+    return {
+        "sa1_mlp": {"flops": Bc * sa_level_flops(32 * 32, (6, 64, 64, 128)),
+                    "bytes": Bc * (P * 24 + 32 * 32 * 4 + 32 * 128 * 4)},
+        "sa2_mlp": {"flops": Bc * sa_level_flops(16 * 32, (131, 128, 128, 256)),
+                    "bytes": Bc * (32 * 128 * 4 + 16 * 32 * 4 + 16 * 256 * 4)},
+        "sa3_l1": {"flops": Bc * sa_level_flops(16, (259, 256))}, "sa3_l2": {"flops": Bc * sa_level_flops(16, (256, 512))},
+        "sa3_l3": {"flops": Bc * sa_level_flops(16, (512, 768))}, "fc": {"flops": Bc * 2.0 * 768 * 768},
+        # index kernels: compulsory traffic = xyz read + index/centre writes
+        "sa1_group": {"bytes": Bc * (P * 12 + 32 * 4 + 32 * 12 + 32 * 32 * 4)},
+        "sa2_group": {"bytes": Bc * (32 * 12 + 16 * 4 + 16 * 12 + 16 * 32 * 4)},
+    }
+
+
+def summarize(timer: KernelTimer, B: int, O: int, P: int, split: int, in_long_step: bool = True):
+    """roofline object for the dominant kernel + a per-kernel table."""
+    ms = timer.mean_ms()
+    work = algorithmic_work(B, O, P)
+    peaks = measured_peaks()
+    tf_peak = peaks["bf16_tflops_sustained"] if in_long_step else peaks["bf16_tflops"]
+    table = {}
+    for name, t in ms.items():
+        w = work.get(name, {})
+        row = {"ms": t, "launches": timer.counts()[name]}
+        if "flops" in w:
+            row["tflops"] = w["flops"] / (t * 1e-3) / 1e12
+            row["frac_tensor"] = row["tflops"] / tf_peak
+        if "bytes" in w:
+            row["gbs"] = w["bytes"] / (t * 1e-3) / 1e9
+            row["frac_hbm"] = row["gbs"] / peaks["hbm_gbs"]
+        table[name] = row
+    if not table:
+        return {"error": "no kernels timed"}, {}
+    top = max(table, key=lambda k: table[k]["ms"])
+    r = table[top]
+    if "tflops" in r:
+        roof = {"kernel": top, "bound": "tensor", "achieved": r["tflops"], "peak": tf_peak,
+                "unit": "TFLOP/s", "frac": r["frac_tensor"], "traffic": None,
+                "peak_source": f"{peaks['source']} bf16 {'sustained' if in_long_step else 'burst'} (MEASURED_PEAKS.json)",
+                "note": f"algorithmic fp32-equivalent FLOPs; the kernel issues {split}x that in bf16 MMAs (split-bf16)"}
+    else:
+        roof = {"kernel": top, "bound": "hbm", "achieved": r["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": r["frac_hbm"], "traffic": None, "peak_source": f"{peaks['source']} (MEASURED_PEAKS.json)"}
+    return roof, table

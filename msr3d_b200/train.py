@@ -1,0 +1,48 @@
+"""Hot-path training step: prompter forward/backward, gradient all-reduce of the trainable
+prompter parameters over NCCL, global-norm clip and AdamW.
+
+Mirrors what the reference trainer does around the path (trainer/leo_trainer.py:189-247:
+zero_grad -> backward (DDP all-reduce, find_unused_parameters=True) -> clip_grad_norm_(5.0)
+-> AdamW(lr 3e-5, wd 0.05, betas (0.9, 0.999)) per configs/msr3d.yaml:38-51), with the LLM
+replaced by a fixed upstream gradient dL/d(obj_tokens): the frozen LLM is out of scope and
+only ever hands the prompter that tensor.
+
+Execution is the fused engine of msr3d_b200/fused.py: ~85 launches of this repo's kernels per
+step, replayed as one CUDA graph.  Gradients live in ONE flat fp32 buffer, so the data-parallel
+exchange is a single all-reduce and parameters that receive no gradient in the shipped mode
+(anchor_feat, orientation_encoder.*, loc_layers.* — SURVEY.md §8a) need no unused-parameter
+graph walk: they sit in a tail segment that neither the collective nor the optimiser touches."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import synthetic
+from .fused import FusedPrompter
+
+
+class HotPathTrainer:
+    def __init__(self, model: torch.nn.Module, B: int, O: int, P: int, lr: float = 3e-5,
+                 weight_decay: float = 0.05, betas=(0.9, 0.999), grad_norm: float = 5.0,
+                 world_size: int = 1, split: int = 6, use_graph: bool = True):
+        self.engine = FusedPrompter(model, lr=lr, weight_decay=weight_decay, betas=betas,
+                                    grad_norm=grad_norm, world_size=world_size, split=split)
+        self.engine.prepare(B, O, P, training=model.training)
+        self.use_graph = use_graph
+        self.n_trainable = self.engine.n_trainable
+
+    def warmup(self, batch: synthetic.SceneBatch, upstream: torch.Tensor):
+        """First eager step (lazy kernel attribute setup), then graph capture."""
+        self.engine.load_inputs(batch, upstream)
+        self.engine.train_step_eager()
+        torch.cuda.synchronize()
+        if self.use_graph:
+            self.engine.capture()
+
+    def step(self, batch: synthetic.SceneBatch, upstream: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One micro-step on `batch` (device or pinned-host tensors; copied into the engine's static
+        input buffers).  Returns the surrogate loss <obj_tokens, upstream> as a device scalar."""
+        self.engine.load_inputs(batch, upstream)
+        self.engine.train_step()
+        return self.engine.loss()

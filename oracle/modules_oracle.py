@@ -173,7 +173,7 @@ def linear_ln(sd: SD, prefix: str, x: torch.Tensor) -> torch.Tensor:
 
 def spatial_mha(sd: SD, prefix: str, x: torch.Tensor, pairwise: torch.Tensor,
                 key_padding_mask: Optional[torch.Tensor], n_head: int, fusion: str = "cond",
-                spatial_multihead: bool = True):
+                spatial_multihead: bool = True, drop_fc: Optional[torch.Tensor] = None):
     """MultiHeadAttentionSpatial.forward with q=k=v=x (modules/layers/transformers.py:200-252)."""
     B, L, D = x.shape
     dh = D // n_head
@@ -220,6 +220,8 @@ def spatial_mha(sd: SD, prefix: str, x: torch.Tensor, pairwise: torch.Tensor,
         fused = torch.softmax(fused, 3)
     out = torch.matmul(fused, v).permute(1, 2, 0, 3).reshape(B, L, D)
     out = F.linear(out, sd[f"{prefix}.fc.weight"], sd[f"{prefix}.fc.bias"])
+    if drop_fc is not None:  # explicit multiplicative dropout mask (training-mode checks)
+        out = out * drop_fc
     out = F.layer_norm(out + x, (D,), sd[f"{prefix}.layer_norm.weight"],
                        sd[f"{prefix}.layer_norm.bias"], 1e-5)
     return out, fused
@@ -227,17 +229,24 @@ def spatial_mha(sd: SD, prefix: str, x: torch.Tensor, pairwise: torch.Tensor,
 
 def spatial_encoder_layer(sd: SD, prefix: str, x, pairwise, key_padding_mask, n_head: int,
                           fusion: str = "cond", activation: str = "gelu",
-                          spatial_multihead: bool = True):
+                          spatial_multihead: bool = True, masks: Optional[dict] = None):
     """TransformerSpatialEncoderLayer.forward (transformers.py:314-329).
 
     Note the double residual: self_attn already returns LN(out + x) (:250-251)."""
     D = x.shape[-1]
+    mk = masks or {}
     t2, att = spatial_mha(sd, f"{prefix}.self_attn", x, pairwise, key_padding_mask, n_head,
-                          fusion, spatial_multihead)
+                          fusion, spatial_multihead, mk.get("fc"))
+    if "d1" in mk:
+        t2 = t2 * mk["d1"]
     x = F.layer_norm(x + t2, (D,), sd[f"{prefix}.norm1.weight"], sd[f"{prefix}.norm1.bias"], 1e-5)
     act = {"gelu": F.gelu, "relu": F.relu}[activation]
-    h = F.linear(act(F.linear(x, sd[f"{prefix}.linear1.weight"], sd[f"{prefix}.linear1.bias"])),
-                 sd[f"{prefix}.linear2.weight"], sd[f"{prefix}.linear2.bias"])
+    hid = act(F.linear(x, sd[f"{prefix}.linear1.weight"], sd[f"{prefix}.linear1.bias"]))
+    if "ffn" in mk:
+        hid = hid * mk["ffn"]
+    h = F.linear(hid, sd[f"{prefix}.linear2.weight"], sd[f"{prefix}.linear2.bias"])
+    if "d2" in mk:
+        h = h * mk["d2"]
     x = F.layer_norm(x + h, (D,), sd[f"{prefix}.norm2.weight"], sd[f"{prefix}.norm2.bias"], 1e-5)
     return x, att
 
@@ -248,7 +257,7 @@ def ose3d_situation(sd: SD, data: dict, *, n_head: int = 8, num_layers: int = 3,
                     activation: str = "gelu", spatial_dist_norm: bool = True,
                     sa_n_points=(32, 16, None), sa_n_samples=(32, 32, None),
                     sa_radii=(0.2, 0.4, None), obj_embeds: Optional[torch.Tensor] = None,
-                    trace: Optional[dict] = None):
+                    trace: Optional[dict] = None, layer_masks: Optional[list] = None):
     """OSE3DSituation.forward (model/ose3d_situation.py:288-454) for vision_backbone
     'gtpcd', use_spatial_attn/use_anchor/use_orientation True, attn_flat off, and
     situation_type in {'as_transform_for_objects' (shipped, configs/msr3d.yaml:177),
@@ -293,7 +302,7 @@ def ose3d_situation(sd: SD, data: dict, *, n_head: int = 8, num_layers: int = 3,
         if obj_loc_encoding in ("same_all", "diff_all") or i == 0:
             x = x + qpos
         x, att = spatial_encoder_layer(sd, f"spatial_encoder.{i}", x, pairwise, mask, n_head,
-                                       fusion, activation)
+                                       fusion, activation, masks=layer_masks[i] if layer_masks else None)
         if trace is not None:
             trace[f"layer{i}.out"] = x
             trace[f"layer{i}.attn"] = att

@@ -115,3 +115,27 @@ def test_sa_level_fused_matches_oracle(ops, level, sd_spec):
     rel = _rel(got.double(), want.double())
     print(level, "fused rel err", rel)
     assert rel < 1e-4
+
+
+def test_gemm_tc_strided_operands_and_three_way_split():
+    """fp32 operands on both sides through strides; split 6 is fp32-grade on a cancelling sum."""
+    from msr3d_b200.fused import gemm_tc
+    g = torch.Generator().manual_seed(17)
+    dY = torch.randn(240, 816, generator=g)
+    X = torch.randn(240, 256, generator=g)
+    X = X + 50.0                                  # large common offset: sum over tokens cancels heavily
+    dY = dY - dY.mean(0, keepdim=True)
+    want = dY.double().t() @ X.double()           # dW = dY^T X   (816 x 256), contraction over tokens
+    a, b = dY.cuda().t(), X.cuda().t()            # (816 x 240) and (256 x 240) views, k-stride != 1
+    e3 = _rel(gemm_tc(a, b, split=3).cpu().double(), want)
+    e6 = _rel(gemm_tc(a, b, split=6).cpu().double(), want)
+    e32 = _rel((dY.t() @ X).double(), want)
+    print(f"cancelling dW: split3 {e3:.2e}  split6 {e6:.2e}  torch-fp32-cpu {e32:.2e}")
+    assert e6 < e3 / 5 and e6 < 4 * e32 + 1e-6     # within a small factor of fp32 accumulation itself
+    # split-K with atomics + bias/residual only once
+    W = torch.randn(256, 2048, generator=g) * 0.02
+    A = torch.randn(240, 2048, generator=g)
+    bias, res = torch.randn(256, generator=g), torch.randn(240, 256, generator=g)
+    out = torch.zeros(240, 256).cuda()
+    gemm_tc(A.cuda(), W.cuda(), bias=bias.cuda(), residual=res.cuda(), out=out, accumulate=2, ksplit=8)
+    assert _rel(out.cpu().double(), A.double() @ W.double().t() + bias.double() + res.double()) < 2e-5
