@@ -238,12 +238,16 @@ def main():
             "clocks": sampler.result(),
         }
         # per-kernel durations: the same step launched eagerly with CUDA events around every kernel
-        # (a graph replay cannot be instrumented from the host); L2 flushed before each step
+        # (a graph replay cannot be instrumented from the host).  A spin kernel keeps the stream busy
+        # while the host enqueues the whole step, so the events bracket back-to-back kernels and do
+        # not include host launch gaps; L2 is flushed before each step.
         ops.TIMER = ktimer = roofline.KernelTimer()
         for i in range(min(args.steps, 20)):
-            flush.zero_()
             trainer.engine.load_inputs(devb[i % 4], up)
+            flush.zero_()
+            torch.cuda._sleep(40_000_000)                     # ~20 ms of GPU spin
             trainer.engine.train_step_eager()
+            torch.cuda.synchronize()
         ops.TIMER = None
         roof, table = roofline.summarize(ktimer, B, O, P, 3 if args.split == 6 else args.split)
         line["roofline"] = roof

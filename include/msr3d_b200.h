@@ -119,7 +119,8 @@ int msr3d_linear_tc_f32(const float *A, long long stride_am, long long stride_ak
  * read in place through strides; nothing is pre-packed).  Element (m,k) of A at
  * A[m*stride_am + k*stride_ak]; element (n,k) of B at B[n*stride_bn + k*stride_bk].
  *   a_xform / b_xform: 0 none, 1 GELU, 2 GELU then dropout(site, memory offset as counter)
- *   epilogue: 0 plain, 1 multiply by gelu'(aux[m,n]) * dropout_mask(epi_site)  (FFN backward)
+ *   epilogue: 0 plain; 1 x *= gelu'(aux[m,n]) * dropout_mask(epi_site);
+ *             2 (FFN forward) out = dropout(gelu(x)), aux_out = gelu'(x) * mask;  3 x *= aux[m,n]
  *   accumulate: 0 store, 1 out += (single CTA per element), 2 atomicAdd (required for ksplit > 1)
  *   ksplit: number of CTAs along K (split-K)
  *   split: 1 = one bf16 MMA per K slice, 3 = two-way split operands (hh+hm+mh, ~2^-17),
@@ -130,8 +131,9 @@ typedef struct msr3d_gemm_desc {
   const float *bias;       /* [N] or NULL */
   const float *residual;   /* [M, ld_residual] or NULL */
   long long ld_residual;
-  const float *aux;        /* [M, ld_aux] for epilogue 1 */
+  const float *aux;        /* [M, ld_aux] for epilogues 1 and 3 */
   long long ld_aux;
+  float *aux_out;          /* [M, ld_aux] second output of epilogue 2 */
   float *out; long long ld_out;
   int M, N, K;
   int act, split, accumulate, epilogue, ksplit;

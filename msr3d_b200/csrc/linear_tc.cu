@@ -82,7 +82,11 @@ pack_weight_kernel(const float *__restrict__ W, int N, int K, long long sn, long
 // Operand element transforms applied while loading fp32 operands (before the bf16 split).
 enum { XF_NONE = 0, XF_GELU = 1, XF_GELU_DROPOUT = 2 };
 // Epilogue modes.
-enum { EPI_PLAIN = 0, EPI_GELU_GRAD = 1 };
+//   EPI_GELU_GRAD: x *= gelu'(aux) * dropout_mask            (generic FFN backward, recomputes from u)
+//   EPI_FFN1     : out = dropout(gelu(x)), aux_out = gelu'(x) * dropout_mask   (FFN forward: both the
+//                  hidden activation and its local derivative are materialised once, 2 MB each)
+//   EPI_MUL_AUX  : x *= aux                                   (FFN backward using the stored derivative)
+enum { EPI_PLAIN = 0, EPI_GELU_GRAD = 1, EPI_FFN1 = 2, EPI_MUL_AUX = 3 };
 
 struct GemmArgs {
   const float *A; long long sam, sak; int a_xform; unsigned a_site;
@@ -92,7 +96,8 @@ struct GemmArgs {
   int M, N, K, Kp;
   const float *bias;                                   // [N] nullable
   const float *res; long long ldr;                     // residual [M,N] added after act, nullable
-  const float *aux; long long ldaux; unsigned epi_site;  // EPI_GELU_GRAD: pre-activation u[M,N]
+  const float *aux; long long ldaux; unsigned epi_site;  // EPI_GELU_GRAD: pre-activation u[M,N]; EPI_MUL_AUX: factor
+  float *aux_out;                                        // EPI_FFN1: second output [M, ldaux]
   float *out; long long ldo;
   int act, pool, split, accumulate, epi;               // accumulate: 0 store, 1 +=, 2 atomicAdd
   Dropout drop;
@@ -114,71 +119,111 @@ __device__ __noinline__ float xform_slow(float v, int mode, const Dropout *d, un
 __device__ __noinline__ float gelu_grad_masked(float x, float u, const Dropout *d, unsigned site, long long off) {
   return x * gelu_grad_f(u) * d->mask((uint64_t)off, site);
 }
+// (dropout(gelu(x)), gelu'(x) * mask)
+__device__ __noinline__ float2 ffn1_pair(float x, const Dropout *d, unsigned site, long long off) {
+  const float m = d->mask((uint64_t)off, site);
+  return make_float2(gelu_f(x) * m, gelu_grad_f(x) * m);
+}
 
-// Loads an (R x 64) fp32 operand chunk (rows r0.., k from k0), applies the transform, splits to
-// bf16 and stores it in the canonical layout: tiles [h | m | l] `tile_bytes` apart (l only when
-// three_way).  Thread t: row = t % R, the threads sharing a row split the eight 8-wide k groups.
-// Lanes map to consecutive rows: conflict-free 16 B shared stores, and for transposed operands
-// (k stride != 1, row stride 1) fully coalesced global loads.
+// An (R x 64) fp32 operand chunk in registers: thread t holds row t % R, and the threads sharing a
+// row split the eight 8-wide k groups.  Lanes map to consecutive rows: conflict-free 16 B shared
+// stores, and for transposed operands (k stride != 1, row stride 1) fully coalesced global loads.
+// Loading (op_load) and converting (op_store) are separate so that chunk i+1 is in flight while
+// chunk i is converted, fenced and multiplied: these GEMMs are latency bound, not bandwidth bound.
 template <int R>
-__device__ __noinline__ void load_operand_chunk(const float *__restrict__ base, long long sr, long long sk,
-                                                int r0, int rmax, int k0, int K, int xmode,
-                                                const Dropout *drop, unsigned site, uint8_t *tiles,
-                                                uint32_t tile_bytes, bool three_way, int tid) {
-  constexpr int kThreadsPerRow = 256 / R;       // R = 128 -> 2
-  constexpr int kPer = 8 / kThreadsPerRow;      // 8-wide k groups per thread
+struct OperandRegs {
+  static constexpr int kThreadsPerRow = 256 / R;       // R = 128 -> 2
+  static constexpr int kPer = 8 / kThreadsPerRow;      // 8-wide k groups per thread
+  float v[kPer][8];
+};
+
+template <int R>
+__device__ __forceinline__ void op_load(OperandRegs<R> &o, const float *__restrict__ base, long long sr,
+                                        long long sk, int r0, int rmax, int k0, int K, int tid) {
+  constexpr int kPer = OperandRegs<R>::kPer;
   const int row = tid % R, part = tid / R;
   const bool row_ok = (r0 + row) < rmax;
   const float *rp = base + (long long)(r0 + row) * sr;
   const bool vec_ok = (sk == 1) && ((sr & 3) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
-  float v[kPer][8];
-  // all global loads first (memory-level parallelism), then convert
 #pragma unroll
   for (int c = 0; c < kPer; ++c) {
     const int kk = k0 + (part * kPer + c) * 8;
     if (row_ok && vec_ok && kk + 8 <= K) {
       const float4 a = *reinterpret_cast<const float4 *>(rp + kk);
       const float4 b = *reinterpret_cast<const float4 *>(rp + kk + 4);
-      v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
-      v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+      o.v[c][0] = a.x; o.v[c][1] = a.y; o.v[c][2] = a.z; o.v[c][3] = a.w;
+      o.v[c][4] = b.x; o.v[c][5] = b.y; o.v[c][6] = b.z; o.v[c][7] = b.w;
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[c][j] = (row_ok && kk + j < K) ? rp[(long long)(kk + j) * sk] : 0.f;
+      for (int j = 0; j < 8; ++j) o.v[c][j] = (row_ok && kk + j < K) ? rp[(long long)(kk + j) * sk] : 0.f;
     }
   }
-  if (xmode != XF_NONE) {
+}
+
+// FFN variant only: GELU (+ dropout) on the loaded hidden activations.  Unrolled (the values must stay
+// in registers) around an out-of-line scalar function.
+template <int R>
+__device__ __forceinline__ void op_xform(OperandRegs<R> &o, long long sr, long long sk, int r0, int rmax,
+                                         int k0, int K, int xmode, const Dropout *drop, unsigned site, int tid) {
+  constexpr int kPer = OperandRegs<R>::kPer;
+  const int row = tid % R, part = tid / R;
+  if ((r0 + row) >= rmax) return;
 #pragma unroll
-    for (int c = 0; c < kPer; ++c) {
-      const int kk = k0 + (part * kPer + c) * 8;
+  for (int c = 0; c < kPer; ++c)
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (row_ok && kk + j < K)
-          v[c][j] = xform_slow(v[c][j], xmode, drop, site, (long long)(r0 + row) * sr + (long long)(kk + j) * sk);
+    for (int j = 0; j < 8; ++j) {
+      const int kk = k0 + (part * kPer + c) * 8 + j;
+      if (kk < K)
+        o.v[c][j] = xform_slow(o.v[c][j], xmode, drop, site, (long long)(r0 + row) * sr + (long long)kk * sk);
     }
-  }
+}
+
+// split to bf16 and store in the canonical layout: tiles [h | m | l] `tile_bytes` apart
+template <int R>
+__device__ __forceinline__ void op_store(const OperandRegs<R> &o, uint8_t *tiles, uint32_t tile_bytes,
+                                         bool three_way, int tid) {
+  constexpr int kPer = OperandRegs<R>::kPer;
+  const int row = tid % R, part = tid / R;
 #pragma unroll
   for (int c = 0; c < kPer; ++c) {
     uint32_t h[4], m[4], l[4];
     const uint32_t off = chunk_offset(R, row, part * kPer + c);
     if (three_way) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) split_pack2_3way(v[c][2 * j], v[c][2 * j + 1], h[j], m[j], l[j]);
+      for (int j = 0; j < 4; ++j) split_pack2_3way(o.v[c][2 * j], o.v[c][2 * j + 1], h[j], m[j], l[j]);
       *reinterpret_cast<uint4 *>(tiles + 2 * tile_bytes + off) = make_uint4(l[0], l[1], l[2], l[3]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) split_pack2(v[c][2 * j], v[c][2 * j + 1], h[j], m[j]);
+      for (int j = 0; j < 4; ++j) split_pack2(o.v[c][2 * j], o.v[c][2 * j + 1], h[j], m[j]);
     }
     *reinterpret_cast<uint4 *>(tiles + off) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4 *>(tiles + tile_bytes + off) = make_uint4(m[0], m[1], m[2], m[3]);
   }
 }
 
-// 32 lanes x 8 columns of f32 (smaller epilogue step than x32: the column loop stays rolled)
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
+// 32 lanes x 16 columns of f32
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// 16 consecutive floats of a row (vector loads when `vec`), zero outside [0, n_valid)
+__device__ __forceinline__ void row_load16(const float *p, bool vec, int n_valid, float (&d)[16]) {
+  if (vec) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 t = *reinterpret_cast<const float4 *>(p + j);
+      d[j] = t.x; d[j + 1] = t.y; d[j + 2] = t.z; d[j + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) d[j] = j < n_valid ? p[j] : 0.f;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -186,7 +231,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 // the tensor core; all 8 warps run the epilogue (warp w owns TMEM lanes
 // 32*(w%4).., column half w/4).  gridDim = (M tiles, N tiles, K splits).
 // ---------------------------------------------------------------------------
-template <int BN>
+// FFN = true adds the operand transforms (GELU / dropout on load) and the gelu'(u) epilogue: only the
+// three FFN GEMMs need them, everything else runs the smaller FFN = false instance.
+template <int BN, bool FFN>
 __global__ void __launch_bounds__(256, 1)
 linear_tc_kernel(GemmArgs g) {
   g.drop.resolve();
@@ -211,6 +258,12 @@ linear_tc_kernel(GemmArgs g) {
   const int kc_end = min(nkc_total, kc_begin + per);
   const int nkc = kc_end - kc_begin;
   if (nkc <= 0) return;  // uniform per CTA: nothing allocated yet
+
+  // first operand chunk goes in flight before any set-up work
+  OperandRegs<kTileM> ra;
+  OperandRegs<BN> rb;
+  op_load<kTileM>(ra, g.A, g.sam, g.sak, m0, g.M, kc_begin * kChunkK, g.K, tid);
+  if (g.b_mode == 1) op_load<BN>(rb, g.Bf, g.sbn, g.sbk, nt * BN, g.N, kc_begin * kChunkK, g.K, tid);
 
   if (tid == 0) {
     mbar_init(&b_full[0], 1);
@@ -239,33 +292,50 @@ linear_tc_kernel(GemmArgs g) {
         bulk_g2s(st + kBOff, g.PW + ((size_t)nt * nkc_total + kc) * kBBlock, kBBlock, &b_full[s]);
       }
     } else {
-      load_operand_chunk<BN>(g.Bf, g.sbn, g.sbk, nt * BN, g.N, kc * kChunkK, g.K, g.b_xform, &g.drop,
-                             g.b_site, st + kBOff, kBTile, three_way, tid);
+      if (FFN && g.b_xform != XF_NONE)
+        op_xform<BN>(rb, g.sbn, g.sbk, nt * BN, g.N, kc * kChunkK, g.K, g.b_xform, &g.drop, g.b_site, tid);
+      op_store<BN>(rb, st + kBOff, kBTile, three_way, tid);
     }
-    load_operand_chunk<kTileM>(g.A, g.sam, g.sak, m0, g.M, kc * kChunkK, g.K, g.a_xform, &g.drop,
-                               g.a_site, st + kAOff, kATile, three_way, tid);
+    if (FFN && g.a_xform != XF_NONE)
+      op_xform<kTileM>(ra, g.sam, g.sak, m0, g.M, kc * kChunkK, g.K, g.a_xform, &g.drop, g.a_site, tid);
+    op_store<kTileM>(ra, st + kAOff, kATile, three_way, tid);
+    if (i + 1 < nkc) {  // next chunk in flight while this one is fenced, synchronised and multiplied
+      op_load<kTileM>(ra, g.A, g.sam, g.sak, m0, g.M, (kc + 1) * kChunkK, g.K, tid);
+      if (g.b_mode == 1) op_load<BN>(rb, g.Bf, g.sbn, g.sbk, nt * BN, g.N, (kc + 1) * kChunkK, g.K, tid);
+    }
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
       if (g.b_mode == 0) mbar_wait(&b_full[s], (i >> 1) & 1);
       fence_after_sync();
+      // descriptors of K-slice 0 of every tile; a K slice (two 16 B chunks) advances the 16 B-unit
+      // address field by 2*rows, so the issue loop is pure adds (one thread issues: keep it short)
       const uint32_t a_h = smem_u32(st) + kAOff, b_h = smem_u32(st) + kBOff;
-      // products issued smallest-first: (m,m) (h,l) (l,h) (h,m) (m,h) (h,h); tile index 0=h 1=m 2=l
-      const int n_terms = g.split == 6 ? 6 : (g.split == 3 ? 3 : 1);
-#pragma unroll 1
-      for (int ks = 0; ks < kChunkK / 16; ++ks) {
-#pragma unroll 1
-        for (int t = 0; t < n_terms; ++t) {
-          int ta, tb;
-          if (g.split == 6) {   // t: 0 (m,m) 1 (h,l) 2 (l,h) 3 (h,m) 4 (m,h) 5 (h,h)
-            ta = (t == 0 || t == 4) ? 1 : (t == 2 ? 2 : 0);
-            tb = (t == 0 || t == 3) ? 1 : (t == 1 ? 2 : 0);
-          } else {              // t: 0 (h,h) 1 (h,m) 2 (m,h)
-            ta = t == 2 ? 1 : 0;
-            tb = t == 1 ? 1 : 0;
+      uint64_t da[3], db[3];
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        da[t] = kslice_desc(a_h + t * kATile, kTileM, 0);
+        db[t] = kslice_desc(b_h + t * kBTile, BN, 0);
+      }
+      constexpr uint64_t kStepA = 2 * kTileM, kStepB = 2 * BN;
+      if (g.split == 6) {
+#pragma unroll
+        for (int ks = 0; ks < kChunkK / 16; ++ks) {   // smallest products first
+          mma_bf16(tmem_d, da[1] + ks * kStepA, db[1] + ks * kStepB, idesc, (i | ks) ? 1u : 0u);
+          mma_bf16(tmem_d, da[0] + ks * kStepA, db[2] + ks * kStepB, idesc, 1u);
+          mma_bf16(tmem_d, da[2] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
+          mma_bf16(tmem_d, da[0] + ks * kStepA, db[1] + ks * kStepB, idesc, 1u);
+          mma_bf16(tmem_d, da[1] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
+          mma_bf16(tmem_d, da[0] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
+        }
+      } else {
+#pragma unroll
+        for (int ks = 0; ks < kChunkK / 16; ++ks) {
+          mma_bf16(tmem_d, da[0] + ks * kStepA, db[0] + ks * kStepB, idesc, (i | ks) ? 1u : 0u);
+          if (g.split == 3) {
+            mma_bf16(tmem_d, da[0] + ks * kStepA, db[1] + ks * kStepB, idesc, 1u);
+            mma_bf16(tmem_d, da[1] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
           }
-          mma_bf16(tmem_d, kslice_desc(a_h + ta * kATile, kTileM, ks), kslice_desc(b_h + tb * kBTile, BN, ks),
-                   idesc, (i | ks | t) ? 1u : 0u);
         }
       }
       mma_commit(&mma_done[s]);
@@ -277,63 +347,112 @@ linear_tc_kernel(GemmArgs g) {
     fence_after_sync();
   }
 
-  // ---- epilogue: 8 columns at a time, rolled
+  // ---- epilogue: 16 columns per step; every global operand of the step is loaded up front
+  // (vectorised) so nothing inside the element loops waits on memory or branches per element
   const int q = warp & 3, h = warp >> 2;
   const int grow = m0 + q * 32 + lane;  // global row of this thread's TMEM lane
   constexpr int kColsPerHalf = BN / 2;
   const bool first_split = blockIdx.z == 0;
   const bool row_ok = grow < g.M;
+  const bool use_bias = g.bias != nullptr && first_split;
+  const bool use_res = g.res != nullptr && first_split && row_ok;
+  const bool use_aux = ((FFN && g.epi == EPI_GELU_GRAD) || g.epi == EPI_MUL_AUX) && row_ok;
+  const bool bias_vec = (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0;
+  const bool res_vec = ((g.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.res) & 15) == 0);
+  const bool aux_vec = ((g.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.aux) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(g.aux_out) & 15) == 0);
+  const bool out_vec = ((g.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.out) & 15) == 0);
 #pragma unroll 1
-  for (int c0 = h * kColsPerHalf; c0 < (h + 1) * kColsPerHalf; c0 += 8) {
+  for (int c0 = h * kColsPerHalf; c0 < (h + 1) * kColsPerHalf; c0 += 16) {
     const int n0 = nt * BN + c0;
     if (n0 >= g.N) break;  // warp-uniform
-    uint32_t r[8];
-    tmem_ld8(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+    const int nv = min(16, g.N - n0);
+    const bool full = nv == 16;
+    uint32_t r[16];
+    tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+    float bv[16], rv[16], av[16];
+    if (use_bias) row_load16(g.bias + n0, full && bias_vec, nv, bv);
+    if (use_res) row_load16(g.res + (long long)grow * g.ldr + n0, full && res_vec, nv, rv);
+    if (use_aux) row_load16(g.aux + (long long)grow * g.ldaux + n0, full && aux_vec, nv, av);
     tmem_ld_wait();
-    float v[8];
+    float v[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = n0 + j;
-      float x = __uint_as_float(r[j]);
-      if (n < g.N) {
-        if (g.bias != nullptr && first_split) x += g.bias[n];
-        x = apply_act(x, g.act);
-        if (row_ok) {
-          if (g.epi == EPI_GELU_GRAD) {
-            const long long off = (long long)grow * g.ldaux + n;
-            x = gelu_grad_masked(x, g.aux[off], &g.drop, g.epi_site, off);
-          }
-          if (g.res != nullptr && first_split) x += g.res[(long long)grow * g.ldr + n];
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (use_bias ? bv[j] : 0.f);
+    if (g.act == ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (g.act == ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = act_slow(v[j], ACT_GELU);
+    }
+    if (g.epi == EPI_MUL_AUX) {
+      if (use_aux) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= av[j];
+      }
+    } else if (FFN && use_aux) {
+      const long long off0 = (long long)grow * g.ldaux + n0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nv) v[j] = gelu_grad_masked(v[j], av[j], &g.drop, g.epi_site, off0 + j);
+    } else if (FFN && g.epi == EPI_FFN1) {
+      float gp[16];
+      const long long off0 = (long long)grow * g.ldaux + n0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float2 t = ffn1_pair(v[j], &g.drop, g.epi_site, off0 + j);
+        v[j] = t.x;
+        gp[j] = t.y;
+      }
+      if (row_ok) {
+        float *ao = g.aux_out + off0;
+        if (full && aux_vec) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4 *>(ao + j) = make_float4(gp[j], gp[j + 1], gp[j + 2], gp[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nv) ao[j] = gp[j];
         }
       }
-      v[j] = x;
+    }
+    if (use_res) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += rv[j];
     }
     if (g.pool > 1) {
       // max over groups of `pool` consecutive rows (pool divides 32); whole groups are
       // either inside or outside M.
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 16; ++j)
         for (int o = 1; o < g.pool; o <<= 1) v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], o));
       if ((lane % g.pool) == 0 && row_ok) {
         float *o = g.out + (long long)(grow / g.pool) * g.ldo + n0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (n0 + j < g.N) o[j] = v[j];
+        for (int j = 0; j < 16; ++j)
+          if (j < nv) o[j] = v[j];
       }
     } else if (row_ok) {
       float *o = g.out + (long long)grow * g.ldo + n0;
-      const bool vst = ((g.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.out) & 15) == 0) && (n0 + 8 <= g.N);
-      if (vst && g.accumulate == 0) {
-        *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4 *>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      if (g.accumulate == 0 && full && out_vec) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       } else if (g.accumulate == 2) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (n0 + j < g.N) atomicAdd(o + j, v[j]);
+        for (int j = 0; j < 16; ++j)
+          if (j < nv) atomicAdd(o + j, v[j]);
+      } else if (g.accumulate == 1) {
+        float ov[16];
+        row_load16(o, full && out_vec, nv, ov);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nv) o[j] = ov[j] + v[j];
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (n0 + j < g.N) o[j] = g.accumulate ? o[j] + v[j] : v[j];
+        for (int j = 0; j < 16; ++j)
+          if (j < nv) o[j] = v[j];
       }
     }
   }
@@ -348,7 +467,9 @@ static int launch_gemm(GemmArgs &g, int ksplit, cudaStream_t stream) {
   const size_t smem = 2 * (3 * (size_t)kTileM * kChunkK * 2 + 3 * (size_t)BN * kChunkK * 2) + 1024;
   static bool configured = false;
   if (!configured) {
-    MSR3D_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MSR3D_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+    MSR3D_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
     configured = true;
   }
@@ -356,7 +477,9 @@ static int launch_gemm(GemmArgs &g, int ksplit, cudaStream_t stream) {
   if (ksplit < 1) ksplit = 1;
   if (ksplit > nkc) ksplit = nkc;
   dim3 grid(ceil_div(g.M, kTileM), ceil_div(g.N, BN), ksplit);
-  linear_tc_kernel<BN><<<grid, 256, smem, stream>>>(g);
+  const bool ffn = g.a_xform != XF_NONE || g.b_xform != XF_NONE || g.epi == EPI_GELU_GRAD || g.epi == EPI_FFN1;
+  if (ffn) linear_tc_kernel<BN, true><<<grid, 256, smem, stream>>>(g);
+  else linear_tc_kernel<BN, false><<<grid, 256, smem, stream>>>(g);
   return check_launch("linear_tc");
 }
 
@@ -412,7 +535,9 @@ MSR3D_API int msr3d_gemm_tc_f32(const msr3d_gemm_desc *d, msr3d_stream_t stream)
   MSR3D_REQUIRE(d->M >= 0 && d->K > 0 && d->N > 0, "gemm_tc: bad sizes M=%d K=%d N=%d", d->M, d->K, d->N);
   MSR3D_REQUIRE(d->act >= 0 && d->act <= 2 && (d->split == 1 || d->split == 3 || d->split == 6), "gemm_tc: bad act/split");
   MSR3D_REQUIRE(d->a_xform >= 0 && d->a_xform <= 2 && d->b_xform >= 0 && d->b_xform <= 2, "gemm_tc: bad xform");
-  MSR3D_REQUIRE(d->epilogue == 0 || (d->epilogue == 1 && d->aux), "gemm_tc: EPI_GELU_GRAD needs aux");
+  MSR3D_REQUIRE(d->epilogue >= 0 && d->epilogue <= 3, "gemm_tc: bad epilogue %d", d->epilogue);
+  MSR3D_REQUIRE(d->epilogue == 0 || d->epilogue == 2 || d->aux, "gemm_tc: epilogue %d needs aux", d->epilogue);
+  MSR3D_REQUIRE(d->epilogue != 2 || d->aux_out, "gemm_tc: EPI_FFN1 needs aux_out");
   MSR3D_REQUIRE(d->ksplit <= 1 || (d->accumulate == 2 && d->act == 0 && d->epilogue == 0),
                 "gemm_tc: split-K needs atomic accumulation (accumulate=2), act=0, plain epilogue");
   MSR3D_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, "gemm_tc: bad dropout p");
@@ -423,6 +548,7 @@ MSR3D_API int msr3d_gemm_tc_f32(const msr3d_gemm_desc *d, msr3d_stream_t stream)
   g.b_mode = 1;
   g.M = d->M; g.N = d->N; g.K = d->K; g.bias = d->bias; g.res = d->residual; g.ldr = d->ld_residual;
   g.aux = d->aux; g.ldaux = d->ld_aux; g.epi_site = d->epi_site; g.out = d->out; g.ldo = d->ld_out;
+  g.aux_out = d->aux_out;
   g.act = d->act; g.pool = 0; g.split = d->split; g.accumulate = d->accumulate; g.epi = d->epilogue;
   g.drop = make_dropout(d->seed, d->dropout_p, d->seed_ptr);
   return launch_gemm(g, d->ksplit, (cudaStream_t)stream);

@@ -69,17 +69,20 @@ struct SaLayout {
 // issue one layer: D[:, dcol .. dcol+N) = A[128 x K] * Wblock[N x K]^T
 __device__ __forceinline__ void issue_layer(uint32_t a_addr, int K, uint32_t w_addr, int N,
                                             uint32_t tmem_d, int split) {
-  const uint32_t a_hi = a_addr, a_lo = a_addr + 128u * K * 2u;
-  const uint32_t b_hi = w_addr, b_lo = w_addr + (uint32_t)N * K * 2u;
+  // K-slice descriptors advance by a constant (2*rows in 16 B units): the single issuing thread
+  // does two 64-bit adds per MMA instead of rebuilding descriptors
+  uint64_t dah = kslice_desc(a_addr, 128, 0), dal = kslice_desc(a_addr + 128u * K * 2u, 128, 0);
+  uint64_t dbh = kslice_desc(w_addr, N, 0), dbl = kslice_desc(w_addr + (uint32_t)N * K * 2u, N, 0);
   const uint32_t idesc = make_idesc_bf16(128, N);
+  const uint64_t step_a = 2 * 128, step_b = 2 * (uint64_t)N;
+#pragma unroll 2
   for (int ks = 0; ks < K / 16; ++ks) {
-    const uint64_t dah = kslice_desc(a_hi, 128, ks), dal = kslice_desc(a_lo, 128, ks);
-    const uint64_t dbh = kslice_desc(b_hi, N, ks), dbl = kslice_desc(b_lo, N, ks);
     mma_bf16(tmem_d, dah, dbh, idesc, ks ? 1u : 0u);
     if (split == 3) {
       mma_bf16(tmem_d, dah, dbl, idesc, 1u);
       mma_bf16(tmem_d, dal, dbh, idesc, 1u);
     }
+    dah += step_a; dal += step_a; dbh += step_b; dbl += step_b;
   }
 }
 

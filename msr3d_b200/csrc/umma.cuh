@@ -163,31 +163,32 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // ---------------------------------------------------------------- split-bf16 arithmetic
 // x = hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits survive.
 // A*B ~= Ah*Bh + Ah*Bl + Al*Bh (the dropped Al*Bl term is ~2^-16 relative), all
-// accumulated in f32 by the tensor core: three bf16 MMAs give fp32-grade results.
+// accumulated in f32 by the tensor core: three bf16 MMAs give near-fp32 results.
+// cvt.rn.bf16x2.f32 packs two values per instruction; widening back is a shift / mask.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_k, float hi_k) {  // lower k in the low half
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_k), "f"(lo_k));
+  return r;
+}
+__device__ __forceinline__ float bf16_lo_as_f32(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16_hi_as_f32(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
+
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
-// packs two consecutive-k values into one 32-bit word (lower k in the low half)
+// packs two consecutive-k values into one 32-bit word per split level
 __device__ __forceinline__ void split_pack2(float a, float b, uint32_t &hi, uint32_t &lo) {
-  __nv_bfloat16 ah, al, bh, bl;
-  split_bf16(a, ah, al);
-  split_bf16(b, bh, bl);
-  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-  lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+  hi = pack_bf16x2(a, b);
+  lo = pack_bf16x2(a - bf16_lo_as_f32(hi), b - bf16_hi_as_f32(hi));
 }
-
 // three-way split x = h + m + l (24 mantissa bits): with the six products hh, hm, mh, hl, lh, mm the
 // tensor-core result is fp32-grade even for badly conditioned sums (weight gradients).
 __device__ __forceinline__ void split_pack2_3way(float a, float b, uint32_t &h, uint32_t &m, uint32_t &l) {
-  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-  const float ar = a - __bfloat162float(ah), br = b - __bfloat162float(bh);
-  const __nv_bfloat16 am = __float2bfloat16_rn(ar), bm = __float2bfloat16_rn(br);
-  const __nv_bfloat16 al = __float2bfloat16_rn(ar - __bfloat162float(am));
-  const __nv_bfloat16 bl = __float2bfloat16_rn(br - __bfloat162float(bm));
-  h = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-  m = (uint32_t)__bfloat16_as_ushort(am) | ((uint32_t)__bfloat16_as_ushort(bm) << 16);
-  l = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+  h = pack_bf16x2(a, b);
+  const float ar = a - bf16_lo_as_f32(h), br = b - bf16_hi_as_f32(h);
+  m = pack_bf16x2(ar, br);
+  l = pack_bf16x2(ar - bf16_lo_as_f32(m), br - bf16_hi_as_f32(m));
 }
 
 }  // namespace umma

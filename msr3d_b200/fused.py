@@ -34,7 +34,7 @@ class GemmDesc(ctypes.Structure):
     _fields_ = [("A", c_vp), ("stride_am", c_ll), ("stride_ak", c_ll),
                 ("B", c_vp), ("stride_bn", c_ll), ("stride_bk", c_ll),
                 ("bias", c_vp), ("residual", c_vp), ("ld_residual", c_ll),
-                ("aux", c_vp), ("ld_aux", c_ll), ("out", c_vp), ("ld_out", c_ll),
+                ("aux", c_vp), ("ld_aux", c_ll), ("aux_out", c_vp), ("out", c_vp), ("ld_out", c_ll),
                 ("M", c_int), ("N", c_int), ("K", c_int),
                 ("act", c_int), ("split", c_int), ("accumulate", c_int), ("epilogue", c_int), ("ksplit", c_int),
                 ("a_xform", c_int), ("b_xform", c_int),
@@ -97,6 +97,7 @@ class FusedPrompter:
     def __init__(self, model, lr=3e-5, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
                  grad_norm: Optional[float] = 5.0, world_size: int = 1, split: int = 3,
                  grad_split: int = 6):
+        # NOTE: weight-gradient GEMMs and bias reductions are issued on a side stream (see _run)
         why = supported(model)
         if why is not None:
             raise NotImplementedError(f"fused prompter: unsupported configuration ({why})")
@@ -125,6 +126,9 @@ class FusedPrompter:
         self._shape = None
         self._keep = []          # ctypes descriptors must outlive the program
         self.graph = None
+        self.side_stream = torch.cuda.Stream(device=dev)
+        self.use_side = True
+        self._side_pending = False
 
     # ------------------------------------------------------------------ parameters
     def _rehome(self):
@@ -205,23 +209,30 @@ class FusedPrompter:
             w[k] = [f(M, H) for _ in range(nl)]
         for k in ("rstd_a", "rstd_1", "rstd_2"):
             w[k] = [f(M) for _ in range(nl)]
-        w["u"] = [f(M, F) for _ in range(nl)]
+        w["h"] = [f(M, F) for _ in range(nl)]     # dropout(gelu(u))
+        w["gp"] = [f(M, F) for _ in range(nl)]    # gelu'(u) * dropout mask
         w["f"] = f(M, H)
         w["tokens"] = f(M, H)
         # backward
-        w["dy2"], w["df"], w["do"], w["dctx"] = f(M, H), f(M, H), f(M, H), f(M, H)
-        w["du"], w["dqkvc"], w["dh1"] = f(M, F), f(M, QKVC), f(M, H)
+        # per-layer copies of everything a weight-gradient GEMM reads: those GEMMs run on a side
+        # stream, off the critical path, while the main stream moves on to the next layer
+        w["dy2"], w["dctx"], w["dh1"] = f(M, H), f(M, H), f(M, H)
+        w["df"] = [f(M, H) for _ in range(nl)]
+        w["do"] = [f(M, H) for _ in range(nl)]
+        w["du"] = [f(M, F) for _ in range(nl)]
+        w["dqkvc"] = [f(M, QKVC) for _ in range(nl)]
         w["dx"] = [f(M, H) for _ in range(nl)]
         self._shape = (B, L, O_pts)
         self.graph = None
 
     def _gemm(self, prog, A, sa, Bm, sb, M, N, K, out, ldo, bias=0, residual=0, ldr=0, aux=0, ldaux=0,
               act=0, accumulate=0, epilogue=0, ksplit=1, a_xform=0, b_xform=0, a_site=0, b_site=0,
-              epi_site=0, tag=None, wgrad=False):
+              epi_site=0, tag=None, wgrad=False, aux_out=0, side=False):
         d = GemmDesc()
         d.A, d.stride_am, d.stride_ak = A, sa[0], sa[1]
         d.B, d.stride_bn, d.stride_bk = Bm, sb[0], sb[1]
         d.bias, d.residual, d.ld_residual, d.aux, d.ld_aux = bias or None, residual or None, ldr, aux or None, ldaux
+        d.aux_out = aux_out or None
         d.out, d.ld_out, d.M, d.N, d.K = out, ldo, M, N, K
         d.act, d.accumulate, d.epilogue, d.ksplit = act, accumulate, epilogue, ksplit
         # weight gradients contract over tokens and cancel heavily: three-way split (fp32-grade)
@@ -233,10 +244,10 @@ class FusedPrompter:
         self._keep.append(d)
         fn = _C.lib().msr3d_gemm_tc_f32
         ref = ctypes.byref(d)
-        prog.append(("msr3d_gemm_tc_f32", fn, (ref,), tag))
+        prog.append(("msr3d_gemm_tc_f32", fn, (ref,), tag, side))
 
-    def _call(self, prog, name, *args, tag=None):
-        prog.append((name, getattr(_C.lib(), name), args, tag))
+    def _call(self, prog, name, *args, tag=None, side=False):
+        prog.append((name, getattr(_C.lib(), name), args, tag, side))
 
     def _programs(self, training: bool):
         """(forward, backward) launch lists for the current static buffers."""
@@ -246,19 +257,22 @@ class FusedPrompter:
         p, seed, sptr = self._p, self.seed, self.seed_counter.data_ptr()
         P, G = self.P, self.G
         ptr = lambda t: t.data_ptr()  # noqa: E731
+        pre_prog: List = []
         fwd: List = []
         bwd: List = []
-        # ---------------- forward
-        self._call(fwd, "msr3d_spatial_geometry_f32", ptr(w["obj_locs"]), ptr(w["anchor_locs"]), ptr(w["anchor_ori"]),
-                   B, L, self.dist_norm, 1, ptr(w["pw"]), ptr(w["ff"]), ptr(w["sz"]), tag="geometry")
-        self._gemm(fwd, ptr(w["ff"]), (64, 1), P("loc_embedding_encoder.0.weight"), (63, 1), M, H, 63, ptr(w["h1"]), H,
-                   bias=P("loc_embedding_encoder.0.bias"), tag="loc_fc")
-        self._call(fwd, "msr3d_qpos_fwd_f32", ptr(w["h1"]), ptr(w["sz"]), M, P("size_embedding_encoder.0.weight"),
+        # ---------------- forward.  geometry -> loc_fc -> qpos depend only on the inputs: side stream,
+        # concurrent with the PointNet++ encoder on the main stream
+        self._call(pre_prog, "msr3d_spatial_geometry_f32", ptr(w["obj_locs"]), ptr(w["anchor_locs"]), ptr(w["anchor_ori"]),
+                   B, L, self.dist_norm, 1, ptr(w["pw"]), ptr(w["ff"]), ptr(w["sz"]), tag="geometry", side=True)
+        self._gemm(pre_prog, ptr(w["ff"]), (64, 1), P("loc_embedding_encoder.0.weight"), (63, 1), M, H, 63, ptr(w["h1"]), H,
+                   bias=P("loc_embedding_encoder.0.bias"), tag="loc_fc", side=True)
+        self._call(pre_prog, "msr3d_qpos_fwd_f32", ptr(w["h1"]), ptr(w["sz"]), M, P("size_embedding_encoder.0.weight"),
                    P("size_embedding_encoder.0.bias"), P("loc_embedding_encoder.1.weight"), P("loc_embedding_encoder.1.bias"),
                    P("size_embedding_encoder.1.weight"), P("size_embedding_encoder.1.bias"),
                    P("object_orientation_feat"), P("object_type_embedding.weight"),
                    ptr(w["xhat_l"]), ptr(w["rstd_l"]), ptr(w["xhat_s"]), ptr(w["rstd_s"]), ptr(w["qpos"]), ptr(w["qpos0"]),
-                   tag="qpos")
+                   tag="qpos", side=True)
+        fwd.append(("join", None, (), None, False))
         E = self.emb_dim
         self._gemm(fwd, self.emb_ptr, (E, 1), P("obj_linear_projection.weight"), (E, 1), M, H, E, ptr(w["x_in"][0]), H,
                    bias=P("obj_linear_projection.bias"), residual=ptr(w["qpos0"]), ldr=H, tag="obj_proj")
@@ -277,11 +291,13 @@ class FusedPrompter:
                        P(sa + "layer_norm.bias"), P(pre + "norm1.weight"), P(pre + "norm1.bias"), seed, sptr, p,
                        s0 + 0, s0 + 1, ptr(w["xhat_a"][i]), ptr(w["rstd_a"][i]), ptr(w["xhat_1"][i]),
                        ptr(w["rstd_1"][i]), ptr(w["y2"][i]), tag="attn_tail")
-            self._gemm(fwd, ptr(w["y2"][i]), (H, 1), P(pre + "linear1.weight"), (H, 1), M, F, H, ptr(w["u"][i]), F,
-                       bias=P(pre + "linear1.bias"), tag="ffn1")
-            fwd.append(("memset", None, (w["f"],), None))
-            self._gemm(fwd, ptr(w["u"][i]), (F, 1), P(pre + "linear2.weight"), (F, 1), M, H, F, ptr(w["f"]), H,
-                       bias=P(pre + "linear2.bias"), accumulate=2, ksplit=8, a_xform=2, a_site=s0 + 2, tag="ffn2")
+            # FFN: the first GEMM's epilogue materialises h = dropout(gelu(u)) and gelu'(u)*mask once
+            self._gemm(fwd, ptr(w["y2"][i]), (H, 1), P(pre + "linear1.weight"), (H, 1), M, F, H, ptr(w["h"][i]), F,
+                       bias=P(pre + "linear1.bias"), epilogue=2, aux_out=ptr(w["gp"][i]), ldaux=F,
+                       epi_site=s0 + 2, tag="ffn1")
+            fwd.append(("memset", None, (w["f"],), None, False))
+            self._gemm(fwd, ptr(w["h"][i]), (F, 1), P(pre + "linear2.weight"), (F, 1), M, H, F, ptr(w["f"]), H,
+                       bias=P(pre + "linear2.bias"), accumulate=2, ksplit=8, tag="ffn2")
             last = i == nl - 1
             add = 0 if (last or not self.same_all) else ptr(w["qpos"])
             self._call(fwd, "msr3d_ffn_tail_fwd_f32", ptr(w["f"]), ptr(w["y2"][i]), M, P(pre + "norm2.weight"),
@@ -295,48 +311,50 @@ class FusedPrompter:
             sa = pre + "self_attn."
             s0 = i * 8
             dx = ptr(w["dx"][i])
+            df, du, do_, dqkvc = ptr(w["df"][i]), ptr(w["du"][i]), ptr(w["do"][i]), ptr(w["dqkvc"][i])
             self._call(bwd, "msr3d_ffn_tail_bwd_f32", dy3, M, P(pre + "norm2.weight"), seed, sptr, p, s0 + 3,
-                       ptr(w["xhat_2"][i]), ptr(w["rstd_2"][i]), ptr(w["dy2"]), ptr(w["df"]), G(pre + "norm2.weight"),
+                       ptr(w["xhat_2"][i]), ptr(w["rstd_2"][i]), ptr(w["dy2"]), df, G(pre + "norm2.weight"),
                        G(pre + "norm2.bias"), G(pre + "linear2.bias"), tag="ffn_tail_bwd")
-            # dW2 (H x F) += df^T . dropout(gelu(u))
-            self._gemm(bwd, ptr(w["df"]), (1, H), ptr(w["u"][i]), (1, F), H, F, M, G(pre + "linear2.weight"), F,
-                       accumulate=1, b_xform=2, b_site=s0 + 2, tag="dW2", wgrad=True)
+            # dW2 (H x F) += df^T . h                                   [side stream]
+            self._gemm(bwd, df, (1, H), ptr(w["h"][i]), (1, F), H, F, M, G(pre + "linear2.weight"), F,
+                       accumulate=1, tag="dW2", wgrad=True, side=True)
             # du = (df . W2) * gelu'(u) * mask
-            self._gemm(bwd, ptr(w["df"]), (H, 1), P(pre + "linear2.weight"), (1, F), M, F, H, ptr(w["du"]), F,
-                       epilogue=1, aux=ptr(w["u"][i]), ldaux=F, epi_site=s0 + 2, tag="du")
-            # dW1 (F x H) += du^T . y2
-            self._gemm(bwd, ptr(w["du"]), (1, F), ptr(w["y2"][i]), (1, H), F, H, M, G(pre + "linear1.weight"), H,
-                       accumulate=1, tag="dW1", wgrad=True)
-            self._call(bwd, "msr3d_colsum_add_f32", ptr(w["du"]), F, M, F, G(pre + "linear1.bias"), None, None, tag="db1")
+            self._gemm(bwd, df, (H, 1), P(pre + "linear2.weight"), (1, F), M, F, H, du, F,
+                       epilogue=3, aux=ptr(w["gp"][i]), ldaux=F, tag="du")
+            # dW1 (F x H) += du^T . y2 ; db1                            [side stream]
+            self._gemm(bwd, du, (1, F), ptr(w["y2"][i]), (1, H), F, H, M, G(pre + "linear1.weight"), H,
+                       accumulate=1, tag="dW1", wgrad=True, side=True)
+            self._call(bwd, "msr3d_colsum_add_f32", du, F, M, F, G(pre + "linear1.bias"), None, None, tag="db1",
+                       side=True)
             # dy2 += du . W1
-            self._gemm(bwd, ptr(w["du"]), (F, 1), P(pre + "linear1.weight"), (1, H), M, H, F, ptr(w["dy2"]), H,
+            self._gemm(bwd, du, (F, 1), P(pre + "linear1.weight"), (1, H), M, H, F, ptr(w["dy2"]), H,
                        accumulate=2, ksplit=8, tag="dy2")
             self._call(bwd, "msr3d_attn_tail_bwd_f32", ptr(w["dy2"]), M, P(sa + "layer_norm.weight"),
                        P(pre + "norm1.weight"), seed, sptr, p, s0 + 0, s0 + 1, ptr(w["xhat_a"][i]),
-                       ptr(w["rstd_a"][i]), ptr(w["xhat_1"][i]), ptr(w["rstd_1"][i]), dx, ptr(w["do"]),
+                       ptr(w["rstd_a"][i]), ptr(w["xhat_1"][i]), ptr(w["rstd_1"][i]), dx, do_,
                        G(sa + "layer_norm.weight"), G(sa + "layer_norm.bias"), G(pre + "norm1.weight"),
                        G(pre + "norm1.bias"), G(sa + "fc.bias"), tag="attn_tail_bwd")
-            # dWo (H x H) += do^T . ctx ;  dctx = do . Wo
-            self._gemm(bwd, ptr(w["do"]), (1, H), ptr(w["ctx"][i]), (1, H), H, H, M, G(sa + "fc.weight"), H,
-                       accumulate=1, tag="dWo", wgrad=True)
-            self._gemm(bwd, ptr(w["do"]), (H, 1), P(sa + "fc.weight"), (1, H), M, H, H, ptr(w["dctx"]), H, tag="dctx")
+            # dWo (H x H) += do^T . ctx [side] ;  dctx = do . Wo
+            self._gemm(bwd, do_, (1, H), ptr(w["ctx"][i]), (1, H), H, H, M, G(sa + "fc.weight"), H,
+                       accumulate=1, tag="dWo", wgrad=True, side=True)
+            self._gemm(bwd, do_, (H, 1), P(sa + "fc.weight"), (1, H), M, H, H, ptr(w["dctx"]), H, tag="dctx")
             self._call(bwd, "msr3d_attn_bwd_f32", ptr(w["dctx"]), H, ptr(w["qkvc"][i]), QKVC, ptr(w["pw"]),
-                       ptr(w["P"][i]), ptr(w["LOC"][i]), B, L, NHEAD, ptr(w["dqkvc"]), tag="attn_core_bwd")
-            # dWqkvc (816 x H) += dqkvc^T . x_in ; bias ; dx += dqkvc . Wqkvc
-            self._gemm(bwd, ptr(w["dqkvc"]), (1, QKVC), ptr(w["x_in"][i]), (1, H), QKVC, H, M, G(sa + "w_qs.weight"), H,
-                       accumulate=1, tag="dWqkvc", wgrad=True)
-            self._call(bwd, "msr3d_colsum_add_f32", ptr(w["dqkvc"]), QKVC, M, QKVC, G(sa + "w_qs.bias"), None, None,
-                       tag="dbqkvc")
-            self._gemm(bwd, ptr(w["dqkvc"]), (QKVC, 1), P(sa + "w_qs.weight"), (1, H), M, H, QKVC, dx, H,
+                       ptr(w["P"][i]), ptr(w["LOC"][i]), B, L, NHEAD, dqkvc, tag="attn_core_bwd")
+            # dWqkvc (816 x H) += dqkvc^T . x_in ; bias [side] ; dx += dqkvc . Wqkvc
+            self._gemm(bwd, dqkvc, (1, QKVC), ptr(w["x_in"][i]), (1, H), QKVC, H, M, G(sa + "w_qs.weight"), H,
+                       accumulate=1, tag="dWqkvc", wgrad=True, side=True)
+            self._call(bwd, "msr3d_colsum_add_f32", dqkvc, QKVC, M, QKVC, G(sa + "w_qs.bias"), None, None,
+                       tag="dbqkvc", side=True)
+            self._gemm(bwd, dqkvc, (QKVC, 1), P(sa + "w_qs.weight"), (1, H), M, H, QKVC, dx, H,
                        accumulate=2, ksplit=4, tag="dx")
             dy3 = dx
         dx0 = ptr(w["dx"][0])
         # x_in0 = emb Wp^T + bp + orientation_feat + type_emb[0] + qpos
         self._call(bwd, "msr3d_colsum_add_f32", dx0, H, M, H, G("obj_linear_projection.bias"),
-                   G("object_orientation_feat"), G("object_type_embedding.weight"), tag="dbias_proj")
+                   G("object_orientation_feat"), G("object_type_embedding.weight"), tag="dbias_proj", side=True)
         E = self.emb_dim
         self._gemm(bwd, dx0, (1, H), self.emb_ptr, (1, E), H, E, M, G("obj_linear_projection.weight"), E,
-                   accumulate=1, tag="dWproj", wgrad=True)
+                   accumulate=1, tag="dWproj", wgrad=True, side=True)
         dq = [ptr(w["dx"][i]) for i in range(nl)] if self.same_all else [dx0]
         dq += [None] * (3 - len(dq))
         assert len(dq) == 3, "fused qpos backward sums at most three layers"
@@ -348,20 +366,39 @@ class FusedPrompter:
                    G("loc_embedding_encoder.0.bias"), tag="qpos_bwd")
         self._gemm(bwd, ptr(w["dh1"]), (1, H), ptr(w["ff"]), (1, 64), H, 63, M, G("loc_embedding_encoder.0.weight"), 63,
                    accumulate=1, tag="dWloc", wgrad=True)
-        return fwd, bwd
+        bwd.append(("join", None, (), None, False))
+        return pre_prog, fwd, bwd
 
     def _run(self, prog):
-        stream = torch.cuda.current_stream().cuda_stream
+        """Issue a launch list.  Entries flagged `side` go to the side stream after it has caught up
+        with the main stream (fork); a "join" entry (and the end of the list) makes the main stream
+        wait for the side stream.  Under CUDA-graph capture this becomes parallel graph branches."""
+        main = torch.cuda.current_stream()
+        side = self.side_stream
         timer = ops.TIMER
-        for name, fn, args, tag in prog:
+        forked = False
+        for name, fn, args, tag, on_side in prog:
+            if name == "join":
+                if forked or self._side_pending:
+                    main.wait_stream(side)
+                    forked = self._side_pending = False
+                continue
             if fn is None:                  # memset of a workspace tensor
                 args[0].zero_()
                 continue
-            if timer is not None and tag:
+            if on_side and self.use_side:
+                side.wait_stream(main)
+                forked = self._side_pending = True
+                if timer is not None and tag:
+                    with torch.cuda.stream(side), timer.range(tag):
+                        rc = fn(*args, side.cuda_stream)
+                else:
+                    rc = fn(*args, side.cuda_stream)
+            elif timer is not None and tag:
                 with timer.range(tag):
-                    rc = fn(*args, stream)
+                    rc = fn(*args, main.cuda_stream)
             else:
-                rc = fn(*args, stream)
+                rc = fn(*args, main.cuda_stream)
             if rc != 0:
                 raise _C.Msr3dError(f"{name} [{tag}] failed ({rc}): {_C.lib().msr3d_last_error().decode()}")
 
@@ -378,7 +415,7 @@ class FusedPrompter:
             self.ws["emb"] = self._buf(B * L, self.emb_dim)
         self.emb_ptr = self.ws["emb"].data_ptr()
         self._keep = []
-        self.fwd_prog, self.bwd_prog = self._programs(training)
+        self.pre_prog, self.fwd_prog, self.bwd_prog = self._programs(training)
         self._key = key
         self.graph = None
 
@@ -404,8 +441,9 @@ class FusedPrompter:
         """Encoder + transformer forward on the static buffers; returns tokens (B, L, 256) view."""
         w = self.ws
         torch.logical_not(w["obj_masks"], out=w["key_pad"].view(torch.bool))
-        self._encode()
-        self._run(self.fwd_prog)
+        self._run(self.pre_prog)      # geometry + query positions on the side stream ...
+        self._encode()                # ... while the encoder runs on the main stream
+        self._run(self.fwd_prog)      # starts with a join
         B, L = w["obj_locs"].shape[:2]
         return w["tokens"].view(B, L, H)
 
