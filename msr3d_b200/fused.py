@@ -65,7 +65,6 @@ _C.register_protos({
 H = 256          # hidden size the fused kernels are built for
 NHEAD = 8
 QKVC = 3 * H + NHEAD * 6
-UNUSED_IN_SHIPPED_MODE = ("anchor_feat", "orientation_encoder.", "loc_layers.")
 
 
 def supported(model) -> Optional[str]:
@@ -132,35 +131,16 @@ class FusedPrompter:
 
     # ------------------------------------------------------------------ parameters
     def _rehome(self):
+        from . import dist as _dist
         named = [(n, p) for n, p in self.model.named_parameters() if p.requires_grad]
         by_name = dict(named)
-
-        def unused(n):
-            return n.startswith(UNUSED_IN_SHIPPED_MODE)
-
-        order_w, order_b, order_u = [], [], []
-        taken = set()
-        for i in range(self.nl):
-            pre = f"spatial_encoder.{i}.self_attn."
-            for kind, dst in (("weight", order_w), ("bias", order_b)):
-                for nm in ("w_qs", "w_ks", "w_vs", "lang_cond_fc"):
-                    dst.append(f"{pre}{nm}.{kind}")
-                    taken.add(f"{pre}{nm}.{kind}")
-        for n, _ in named:
-            if n in taken:
-                continue
-            (order_u if unused(n) else (order_b if "bias" in n else order_w)).append(n)
+        order_w, order_b, order_u = _dist.flat_order([n for n, _ in named], self.nl)
         self.order = order_w + order_b + order_u
-        offs, off = {}, 0
-        for n in self.order:
-            offs[n] = off
-            off += (by_name[n].numel() + 3) // 4 * 4
-            if n == order_w[-1]:
-                pass
-        self.n_decay = offs[order_b[0]] if order_b else off
-        self.n_opt = offs[order_u[0]] if order_u else off
-        self.flat_p = torch.zeros(off, dtype=torch.float32, device=self.dev)
-        self.flat_g = torch.zeros(off, dtype=torch.float32, device=self.dev)
+        offs, total = _dist.flat_offsets(self.order, {n: p.numel() for n, p in named})
+        self.n_decay = offs[order_b[0]] if order_b else total
+        self.n_opt = offs[order_u[0]] if order_u else total
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=self.dev)
         self.offs = offs
         for n in self.order:
             p = by_name[n]
@@ -169,6 +149,8 @@ class FusedPrompter:
             p.data = view
             p.grad = self.flat_g[offs[n]:offs[n] + p.numel()].view_as(p)
         self.n_trainable = sum(p.numel() for _, p in named)
+        if self.world_size > 1:
+            _dist.broadcast_(self.flat_p)     # identical replicas, as DDP's constructor guarantees
 
     def P(self, name):  # device pointer of a parameter / its gradient
         return self.flat_p.data_ptr() + 4 * self.offs[name]
@@ -508,8 +490,8 @@ class FusedPrompter:
             return self.train_step_eager()
         self.graph.replay()
         if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat_g[:self.n_opt])
+            from . import dist as _dist
+            _dist.allreduce_sum_(self.flat_g[:self.n_opt])
             self.optimizer_step()
         B, L = self.ws["obj_locs"].shape[:2]
         return self.ws["tokens"].view(B, L, H)

@@ -1,0 +1,97 @@
+"""CPU, world_size 2, gloo: the N>1 path of the hot-path trainer — flat gradient layout, one
+all-reduce, averaged update — checked against a single process that sees both ranks' batches."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from msr3d_b200 import dist as mdist, synthetic
+from tests import helpers
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _flat_grads(sd_spec, seed, batch, up):
+    """Oracle gradients of one rank, laid out in the engine's flat order."""
+    from oracle import modules_oracle as mo
+    sd = synthetic.make_state_dict(sd_spec, seed)
+    emb = torch.randn(batch.obj_fts.shape[0], batch.obj_fts.shape[1], 768,
+                      generator=torch.Generator().manual_seed(99))       # stands in for the frozen encoder
+    frozen = lambda k: k.startswith("obj_encoder.") or k == "anchor_size"
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not frozen(k) else v)
+           for k, v in sd.items() if not k.startswith("obj_encoder.")}
+    tokens, _ = mo.ose3d_situation(sdg, batch.as_dict(), obj_embeds=emb)
+    (tokens * up).sum().backward()
+    names = [k for k, v in sdg.items() if v.requires_grad]
+    w, b, u = mdist.flat_order(names, 3)
+    order = w + b + u
+    offs, total = mdist.flat_offsets(order, {k: sdg[k].numel() for k in names})
+    flat = torch.zeros(total)
+    for k in order:
+        if sdg[k].grad is not None:
+            flat[offs[k]:offs[k] + sdg[k].numel()] = sdg[k].grad.flatten()
+    n_opt = offs[u[0]] if u else total
+    return flat, n_opt, (w, b, u), offs
+
+
+def _worker(rank, world, port, spec, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    try:
+        batch = synthetic.make_batch(1, 6, 32, seed=mdist.rank_seed(7, rank))   # different scenes per rank
+        up = torch.randn(1, 6, 256, generator=torch.Generator().manual_seed(5))
+        flat, n_opt, _, _ = _flat_grads(spec, 3, batch, up)
+        params = torch.full((n_opt,), float(rank))            # deliberately different replicas
+        mdist.broadcast_(params)                               # -> identical
+        mdist.allreduce_sum_(flat[:n_opt])
+        flat[:n_opt] *= 1.0 / world                            # grad_scale of the optimiser kernel
+        out[rank] = (flat.clone(), params.clone(), mdist.world())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_exchange_matches_single_process(sd_spec):
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, sd_spec, out), nprocs=world, join=True)
+    f0, p0, w0 = out[0]
+    f1, p1, w1 = out[1]
+    assert w0 == (0, 2) and w1 == (1, 2)
+    assert torch.equal(p0, p1) and float(p0[0]) == 0.0          # broadcast from rank 0
+    up = torch.randn(1, 6, 256, generator=torch.Generator().manual_seed(5))
+    singles = [_flat_grads(sd_spec, 3, synthetic.make_batch(1, 6, 32, seed=mdist.rank_seed(7, r)), up) for r in range(world)]
+    n_opt = singles[0][1]
+    want = (singles[0][0] + singles[1][0]) / world
+    assert torch.equal(f0[:n_opt], f1[:n_opt])                  # every rank holds the same reduced gradient
+    torch.testing.assert_close(f0[:n_opt], want[:n_opt], rtol=1e-4, atol=1e-4)   # intra-op thread counts differ
+    # the never-used tail is not exchanged and stays zero
+    assert float(f0[n_opt:].abs().max()) == 0.0 and f0[n_opt:].numel() > 0
+
+
+def test_flat_layout_groups_attention_projections(sd_spec):
+    names = [k for k, _, _ in sd_spec if not k.startswith("obj_encoder.") and k != "anchor_size"
+             and "running" not in k and "num_batches" not in k]
+    w, b, u = mdist.flat_order(names, 3)
+    assert w[:4] == [f"spatial_encoder.0.self_attn.{n}.weight" for n in ("w_qs", "w_ks", "w_vs", "lang_cond_fc")]
+    assert b[:4] == [f"spatial_encoder.0.self_attn.{n}.bias" for n in ("w_qs", "w_ks", "w_vs", "lang_cond_fc")]
+    assert set(u) == {"anchor_feat", "orientation_encoder.weight", "orientation_encoder.bias",
+                      "loc_layers.0.0.weight", "loc_layers.0.0.bias", "loc_layers.0.1.weight", "loc_layers.0.1.bias"}
+    assert all("bias" in n for n in b) and not any("bias" in n for n in w)
+    numel = {k: int(torch.tensor(s).prod()) for k, s, _ in sd_spec}
+    offs, total = mdist.flat_offsets(w + b + u, numel)
+    assert all(o % 4 == 0 for o in offs.values())
+    # QKV+cond weights are one contiguous (816 x 256) block
+    assert offs[w[3]] + numel[w[3]] - offs[w[0]] == 816 * 256
+    assert sorted(w + b + u) == sorted(names)
