@@ -166,7 +166,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     ops.DEFAULT_SPLIT = 3 if args.split == 6 else args.split
     B, O, P = synthetic.CONFIGS[args.config]
     model = msr3d_b200.build_model(prompter_cfg())

@@ -477,7 +477,9 @@ class FusedPrompter:
             torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # thread_local: NCCL's watchdog thread polls CUDA events concurrently, which a "global"
+        # capture would treat as an illegal call during capture
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self.flat_g.zero_()
             self.forward()
             self.backward()
