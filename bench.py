@@ -219,6 +219,20 @@ def main():
     sampler.stop_flag = True
     sampler.join()
 
+    # per-kernel durations (every rank: the step contains a collective): the same step launched eagerly
+    # with CUDA events around every kernel (a graph replay cannot be instrumented from the host).  A
+    # spin kernel keeps the stream busy while the host enqueues the whole step, so the events bracket
+    # back-to-back kernels and not host launch gaps; L2 is flushed before each step.
+    ops.TIMER = ktimer = roofline.KernelTimer()
+    for i in range(min(args.steps, 20)):
+        trainer.engine.load_inputs(devb[i % 4], up)
+        flush.zero_()
+        torch.cuda._sleep(40_000_000)                         # ~20 ms of GPU spin
+        trainer.engine.train_step_eager()
+        torch.cuda.synchronize()
+    ops.TIMER = None
+    barrier()
+
     tot = torch.tensor([sum(ms), sum(ms_e2e)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)           # max over ranks
@@ -238,19 +252,8 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": sampler.result(),
         }
-        # per-kernel durations: the same step launched eagerly with CUDA events around every kernel
-        # (a graph replay cannot be instrumented from the host).  A spin kernel keeps the stream busy
-        # while the host enqueues the whole step, so the events bracket back-to-back kernels and do
-        # not include host launch gaps; L2 is flushed before each step.
-        ops.TIMER = ktimer = roofline.KernelTimer()
-        for i in range(min(args.steps, 20)):
-            trainer.engine.load_inputs(devb[i % 4], up)
-            flush.zero_()
-            torch.cuda._sleep(40_000_000)                     # ~20 ms of GPU spin
-            trainer.engine.train_step_eager()
-            torch.cuda.synchronize()
-        ops.TIMER = None
-        roof, table = roofline.summarize(ktimer, B, O, P, 3 if args.split == 6 else args.split)
+        roof, table = roofline.summarize(ktimer, B, O, P, 3 if args.split == 6 else args.split,
+                                         steps=min(args.steps, 20))
         line["roofline"] = roof
         line["kernels"] = {k: {kk: (round(vv, 5) if isinstance(vv, float) else vv) for kk, vv in v.items()}
                            for k, v in table.items()}

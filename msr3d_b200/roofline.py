@@ -76,7 +76,16 @@ def algorithmic_work(B: int, O: int, P: int):
     }
 
 
-def summarize(timer: KernelTimer, B: int, O: int, P: int, split: int, in_long_step: bool = True):
+#: bench tag -> kernel function
+_GEMM_TAGS = ("sa3_l1", "sa3_l2", "sa3_l3", "fc", "loc_fc", "obj_proj", "qkvc", "out_proj", "ffn1", "ffn2", "dW2",
+              "du", "dW1", "dy2", "dWo", "dctx", "dWqkvc", "dx", "dWproj", "dWloc")
+KERNEL_OF_TAG = {t: "linear_tc_kernel" for t in _GEMM_TAGS}
+KERNEL_OF_TAG.update({"sa1_mlp": "sa_mlp_kernel<16,64,64,128>", "sa2_mlp": "sa_mlp_kernel<144,128,128,256>"})
+#: dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/r1_ncu_sa_mlp.md)
+TRAFFIC_NCU = {"sa_mlp_kernel<16,64,64,128>": 5.93e6, "sa_mlp_kernel<144,128,128,256>": 4.47e6}
+
+
+def summarize(timer: KernelTimer, B: int, O: int, P: int, split: int, in_long_step: bool = True, steps: int = 1):
     """roofline object for the dominant kernel + a per-kernel table."""
     ms = timer.mean_ms()
     work = algorithmic_work(B, O, P)
@@ -93,17 +102,36 @@ def summarize(timer: KernelTimer, B: int, O: int, P: int, split: int, in_long_st
             row["gbs"] = w["bytes"] / (t * 1e-3) / 1e9
             row["frac_hbm"] = row["gbs"] / peaks["hbm_gbs"]
         table[name] = row
-    rated = {k: v for k, v in table.items() if "tflops" in v or "gbs" in v}
+    # the dominant kernel = the kernel FUNCTION with the largest total time in the step, aggregated over
+    # its launches (all transformer / SA3 / fc GEMMs are launches of linear_tc_kernel)
+    groups = {}
+    for name, row in table.items():
+        fn = KERNEL_OF_TAG.get(name, name)
+        g = groups.setdefault(fn, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0, "tags": []})
+        per_step = row["launches"] / max(1, steps)
+        g["ms"] += row["ms"] * per_step
+        g["launches"] += per_step
+        g["tags"].append(name)
+        w = work.get(name, {})
+        g["flops"] += w.get("flops", 0.0) * per_step
+        g["bytes"] += w.get("bytes", 0.0) * per_step
+    rated = {k: v for k, v in groups.items() if v["flops"] > 0 or v["bytes"] > 0}
     if not rated:
         return {"error": "no kernels timed"}, table
     top = max(rated, key=lambda k: rated[k]["ms"])
-    r = table[top]
-    if "tflops" in r:
-        roof = {"kernel": top, "bound": "tensor", "achieved": r["tflops"], "peak": tf_peak,
-                "unit": "TFLOP/s", "frac": r["frac_tensor"], "traffic": None,
+    g = rated[top]
+    total_ms = sum(v["ms"] for v in groups.values())
+    common = {"kernel": top, "launches_per_step": round(g["launches"], 2), "ms_per_step": round(g["ms"], 5),
+              "share_of_kernel_time": round(g["ms"] / total_ms, 4), "traffic": TRAFFIC_NCU.get(top)}
+    if g["flops"] > 0:
+        ach = g["flops"] / (g["ms"] * 1e-3) / 1e12
+        roof = {**common, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                 "peak_source": f"{peaks['source']} bf16 {'sustained' if in_long_step else 'burst'} (MEASURED_PEAKS.json)",
-                "note": f"algorithmic fp32-equivalent FLOPs; the kernel issues {split}x that in bf16 MMAs (split-bf16)"}
+                "note": "algorithmic fp32-equivalent FLOPs summed over the kernel's launches / summed live CUDA-event "
+                        f"durations; the kernel issues 3-6x that in bf16 MMAs (split-bf16). These GEMMs are latency "
+                        "bound (M = 240 tokens), see profiles/r1_ncu_linear_tc.md"}
     else:
-        roof = {"kernel": top, "bound": "hbm", "achieved": r["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": r["frac_hbm"], "traffic": None, "peak_source": f"{peaks['source']} (MEASURED_PEAKS.json)"}
+        ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9
+        roof = {**common, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "peak_source": f"{peaks['source']} (MEASURED_PEAKS.json)"}
     return roof, table
