@@ -226,6 +226,63 @@ __device__ __forceinline__ void row_load16(const float *p, bool vec, int n_valid
   }
 }
 
+// 32 lanes x 4 columns of f32
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+
+// FFN forward epilogue (EPI_FFN1): x = acc + b1;  out = dropout(gelu(x));  aux_out = gelu'(x) * mask.
+// Four columns per step in a rolled loop: erf / exp are shared between gelu and its derivative and
+// one Philox block covers the four dropout decisions.  Requires N % 4 == 0 and 16 B aligned rows.
+template <int BN>
+__device__ __noinline__ void epilogue_ffn1(const GemmArgs &g, uint32_t tmem_d, int nt, int m0, int warp, int lane) {
+  const int q = warp & 3, h = warp >> 2;
+  const int grow = m0 + q * 32 + lane;
+  const bool row_ok = grow < g.M;
+  // 16 columns per step (N % 16 == 0 is required by the launcher for this epilogue): all loads of a
+  // step are issued together and the 16 independent erf/exp chains hide each other's latency
+#pragma unroll 1
+  for (int c0 = h * (BN / 2); c0 < (h + 1) * (BN / 2); c0 += 16) {
+    const int n0 = nt * BN + c0;
+    if (n0 >= g.N) break;
+    uint32_t r[16];
+    tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+    float b[16];
+    if (g.bias != nullptr) row_load16(g.bias + n0, true, 16, b);
+    else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) b[j] = 0.f;
+    }
+    tmem_ld_wait();
+    if (!row_ok) continue;
+    const long long off = (long long)grow * g.ldaux + n0;
+    float hh[16], gp[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 16; j4 += 4) {
+      float m[4];
+      g.drop.mask4((uint64_t)(off + j4), g.epi_site, m);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = __uint_as_float(r[j4 + j]) + b[j4 + j];
+        const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+        const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+        hh[j4 + j] = x * cdf * m[j];
+        gp[j4 + j] = (cdf + x * pdf) * m[j];
+      }
+    }
+    float *o = g.out + (long long)grow * g.ldo + n0;
+    float *ao = g.aux_out + off;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      *reinterpret_cast<float4 *>(o + j) = make_float4(hh[j], hh[j + 1], hh[j + 2], hh[j + 3]);
+      *reinterpret_cast<float4 *>(ao + j) = make_float4(gp[j], gp[j + 1], gp[j + 2], gp[j + 3]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // The GEMM.  256 threads: every thread loads/splits operands; thread 0 drives TMA and
 // the tensor core; all 8 warps run the epilogue (warp w owns TMEM lanes
@@ -347,6 +404,13 @@ linear_tc_kernel(GemmArgs g) {
     fence_after_sync();
   }
 
+  if (FFN && g.epi == EPI_FFN1) {
+    epilogue_ffn1<BN>(g, tmem_d, nt, m0, warp, lane);
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, BN);
+    return;
+  }
   // ---- epilogue: 16 columns per step; every global operand of the step is loaded up front
   // (vectorised) so nothing inside the element loops waits on memory or branches per element
   const int q = warp & 3, h = warp >> 2;
@@ -395,27 +459,6 @@ linear_tc_kernel(GemmArgs g) {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         if (j < nv) v[j] = gelu_grad_masked(v[j], av[j], &g.drop, g.epi_site, off0 + j);
-    } else if (FFN && g.epi == EPI_FFN1) {
-      float gp[16];
-      const long long off0 = (long long)grow * g.ldaux + n0;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float2 t = ffn1_pair(v[j], &g.drop, g.epi_site, off0 + j);
-        v[j] = t.x;
-        gp[j] = t.y;
-      }
-      if (row_ok) {
-        float *ao = g.aux_out + off0;
-        if (full && aux_vec) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4 *>(ao + j) = make_float4(gp[j], gp[j + 1], gp[j + 2], gp[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nv) ao[j] = gp[j];
-        }
-      }
     }
     if (use_res) {
 #pragma unroll
@@ -537,7 +580,11 @@ MSR3D_API int msr3d_gemm_tc_f32(const msr3d_gemm_desc *d, msr3d_stream_t stream)
   MSR3D_REQUIRE(d->a_xform >= 0 && d->a_xform <= 2 && d->b_xform >= 0 && d->b_xform <= 2, "gemm_tc: bad xform");
   MSR3D_REQUIRE(d->epilogue >= 0 && d->epilogue <= 3, "gemm_tc: bad epilogue %d", d->epilogue);
   MSR3D_REQUIRE(d->epilogue == 0 || d->epilogue == 2 || d->aux, "gemm_tc: epilogue %d needs aux", d->epilogue);
-  MSR3D_REQUIRE(d->epilogue != 2 || d->aux_out, "gemm_tc: EPI_FFN1 needs aux_out");
+  MSR3D_REQUIRE(d->epilogue != 2 || (d->aux_out && d->N % 16 == 0 && d->ld_out % 4 == 0 && d->ld_aux % 4 == 0 &&
+                                      d->accumulate == 0 && d->act == 0 && !d->residual &&
+                                      ((uintptr_t)d->out % 16 == 0) && ((uintptr_t)d->aux_out % 16 == 0) &&
+                                      ((uintptr_t)d->bias % 16 == 0)),
+                "gemm_tc: EPI_FFN1 needs aux_out, N %% 16 == 0, ld %% 4 == 0, 16 B aligned pointers, plain store");
   MSR3D_REQUIRE(d->ksplit <= 1 || (d->accumulate == 2 && d->act == 0 && d->epilogue == 0),
                 "gemm_tc: split-K needs atomic accumulation (accumulate=2), act=0, plain epilogue");
   MSR3D_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, "gemm_tc: bad dropout p");

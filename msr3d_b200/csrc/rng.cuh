@@ -6,9 +6,11 @@
 
 namespace msr3d {
 
-__host__ __device__ __forceinline__ uint32_t philox_first_word(uint64_t seed, uint64_t offset,
-                                                               uint32_t site) {
-  uint32_t c0 = (uint32_t)offset, c1 = (uint32_t)(offset >> 32), c2 = site, c3 = 0x6d737233u;
+// Philox-4x32-10: four 32-bit words per (key, counter).  Element `offset` uses word (offset & 3) of
+// block (offset >> 2), so vectorised callers pay one evaluation per four consecutive elements.
+struct Philox4 { uint32_t w[4]; };
+__host__ __device__ __forceinline__ Philox4 philox4(uint64_t seed, uint64_t block, uint32_t site) {
+  uint32_t c0 = (uint32_t)block, c1 = (uint32_t)(block >> 32), c2 = site, c3 = 0x6d737233u;
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -18,7 +20,14 @@ __host__ __device__ __forceinline__ uint32_t philox_first_word(uint64_t seed, ui
     c0 = n0; c1 = n1; c2 = n2; c3 = n3;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  return c0;
+  Philox4 r;
+  r.w[0] = c0; r.w[1] = c1; r.w[2] = c2; r.w[3] = c3;
+  return r;
+}
+__host__ __device__ __forceinline__ uint32_t philox_word(uint64_t seed, uint64_t offset, uint32_t site) {
+  const Philox4 p = philox4(seed, offset >> 2, site);
+  const uint32_t i = (uint32_t)offset & 3u;
+  return i == 0 ? p.w[0] : (i == 1 ? p.w[1] : (i == 2 ? p.w[2] : p.w[3]));
 }
 
 struct Dropout {
@@ -32,11 +41,18 @@ struct Dropout {
   }
   __host__ __device__ __forceinline__ float apply(float v, uint64_t offset, uint32_t site) const {
     if (threshold == 0u) return v;
-    return philox_first_word(seed, offset, site) < threshold ? 0.f : v * scale;
+    return philox_word(seed, offset, site) < threshold ? 0.f : v * scale;
   }
   __host__ __device__ __forceinline__ float mask(uint64_t offset, uint32_t site) const {
     if (threshold == 0u) return 1.f;
-    return philox_first_word(seed, offset, site) < threshold ? 0.f : scale;
+    return philox_word(seed, offset, site) < threshold ? 0.f : scale;
+  }
+  // masks of the four elements offset4 .. offset4+3 (offset4 % 4 == 0)
+  __host__ __device__ __forceinline__ void mask4(uint64_t offset4, uint32_t site, float (&m)[4]) const {
+    if (threshold == 0u) { m[0] = m[1] = m[2] = m[3] = 1.f; return; }
+    const Philox4 p = philox4(seed, offset4 >> 2, site);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = p.w[i] < threshold ? 0.f : scale;
   }
 };
 
