@@ -33,6 +33,8 @@ def furthest_point_sampling(points: torch.Tensor, nsamples: int) -> torch.Tensor
     _check(points, torch.float32, "points")
     B, N, _ = points.shape
     out = torch.empty(B, nsamples, dtype=torch.int32, device=points.device)
+    if out.numel() == 0:
+        return out
     with torch.cuda.device(points.device):
         _C.call("msr3d_furthest_point_sampling_f32", points.data_ptr(), out.data_ptr(),
                 B, N, int(nsamples), _stream())
@@ -44,6 +46,8 @@ def gather_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     B, C, N = points.shape
     M = idx.shape[1]
     out = torch.empty(B, C, M, dtype=torch.float32, device=points.device)
+    if out.numel() == 0:
+        return out
     with torch.cuda.device(points.device):
         _C.call("msr3d_gather_points_f32", points.data_ptr(), idx.data_ptr(), out.data_ptr(),
                 B, C, N, M, _stream())
@@ -53,7 +57,9 @@ def gather_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 def gather_points_grad(grad_out: torch.Tensor, idx: torch.Tensor, n: int) -> torch.Tensor:
     _check(grad_out, torch.float32, "grad_out"); _check(idx, torch.int32, "idx")
     B, C, M = grad_out.shape
-    out = torch.empty(B, C, int(n), dtype=torch.float32, device=grad_out.device)
+    out = torch.zeros(B, C, int(n), dtype=torch.float32, device=grad_out.device)
+    if grad_out.numel() == 0 or out.numel() == 0:
+        return out
     with torch.cuda.device(grad_out.device):
         _C.call("msr3d_gather_points_grad_f32", grad_out.data_ptr(), idx.data_ptr(),
                 out.data_ptr(), B, C, int(n), M, _stream())
@@ -65,6 +71,8 @@ def ball_query(new_xyz: torch.Tensor, xyz: torch.Tensor, radius: float, nsample:
     B, N, _ = xyz.shape
     M = new_xyz.shape[1]
     idx = torch.empty(B, M, int(nsample), dtype=torch.int32, device=xyz.device)
+    if idx.numel() == 0:
+        return idx
     with torch.cuda.device(xyz.device):
         _C.call("msr3d_ball_query_f32", new_xyz.data_ptr(), xyz.data_ptr(), idx.data_ptr(),
                 B, N, M, float(radius), int(nsample), _stream())
@@ -76,6 +84,8 @@ def group_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     B, C, N = points.shape
     _, P, S = idx.shape
     out = torch.empty(B, C, P, S, dtype=torch.float32, device=points.device)
+    if out.numel() == 0:
+        return out
     with torch.cuda.device(points.device):
         _C.call("msr3d_group_points_f32", points.data_ptr(), idx.data_ptr(), out.data_ptr(),
                 B, C, N, P, S, _stream())
@@ -85,7 +95,9 @@ def group_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 def group_points_grad(grad_out: torch.Tensor, idx: torch.Tensor, n: int) -> torch.Tensor:
     _check(grad_out, torch.float32, "grad_out"); _check(idx, torch.int32, "idx")
     B, C, P, S = grad_out.shape
-    out = torch.empty(B, C, int(n), dtype=torch.float32, device=grad_out.device)
+    out = torch.zeros(B, C, int(n), dtype=torch.float32, device=grad_out.device)
+    if grad_out.numel() == 0 or out.numel() == 0:
+        return out
     with torch.cuda.device(grad_out.device):
         _C.call("msr3d_group_points_grad_f32", grad_out.data_ptr(), idx.data_ptr(),
                 out.data_ptr(), B, C, int(n), P, S, _stream())

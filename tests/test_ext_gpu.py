@@ -162,3 +162,41 @@ def test_scene_distribution_full_size(ext, ref):
                                   eo.ball_query(new_xyz, xyz, 0.2, 32).numpy())
     if ref is not None:
         np.testing.assert_array_equal(got.cpu().numpy(), ref.furthest_point_sampling(xyz.cuda(), 32).cpu().numpy())
+
+
+def test_empty_and_degenerate_inputs(ext):
+    """B = 0, m = 0, nsample = 0: no launch, correctly shaped outputs, no error."""
+    z = torch.zeros(0, 64, 3, device="cuda")
+    assert tuple(ext.furthest_point_sampling(z, 4).shape) == (0, 4)
+    x = torch.randn(2, 64, 3, device="cuda")
+    assert tuple(ext.furthest_point_sampling(x, 0).shape) == (2, 0)
+    assert tuple(ext.ball_query(x[:, :0].contiguous(), x, 0.2, 8).shape) == (2, 0, 8)
+    assert tuple(ext.ball_query(x[:, :4].contiguous(), x, 0.2, 0).shape) == (2, 4, 0)
+    f = torch.randn(2, 5, 64, device="cuda")
+    assert tuple(ext.group_points(f, torch.zeros(2, 0, 3, dtype=torch.int32, device="cuda")).shape) == (2, 5, 0, 3)
+    # m > N: FPS keeps picking (duplicates allowed), same as the reference kernel
+    small = torch.randn(1, 5, 3)
+    np.testing.assert_array_equal(ext.furthest_point_sampling(small.cuda(), 9).cpu().numpy(),
+                                  eo.furthest_point_sampling(small, 9).numpy())
+
+
+def test_autograd_through_layerwise_modules_matches_oracle():
+    """Unfrozen encoder path: gradients flow through group_points_grad / gather (atomic scatter)."""
+    from msr3d_b200.encoder import PointnetSAModule
+    torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False      # the layer-wise path uses torch's conv: keep it fp32 here
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sa = PointnetSAModule(npoint=8, radius=0.5, nsample=16, mlp=[4, 16, 32], bn=False).cuda()
+    xyz = (torch.randn(2, 64, 3) * 0.3)
+    feats = torch.randn(2, 4, 64, requires_grad=True)
+    f_gpu = feats.detach().cuda().requires_grad_(True)
+    new_xyz, out = sa(xyz.cuda(), f_gpu)
+    out.sum().backward()
+    # oracle: same weights through the functional restatement + autograd
+    from oracle import modules_oracle as mo
+    sd = {"m." + k: v.detach().cpu() for k, v in sa.state_dict().items()}
+    nx, o = mo.sa_module(sd, "m", xyz, feats, 8, 0.5, 16)
+    o.sum().backward()
+    assert torch.equal(new_xyz.cpu(), nx)
+    torch.testing.assert_close(out.detach().cpu(), o.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(f_gpu.grad.cpu(), feats.grad, rtol=1e-4, atol=1e-5)
