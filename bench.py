@@ -41,6 +41,9 @@ def parse():
                     help="tensor-core operand split of the transformer GEMMs: 6 = three-way bf16 (fp32-grade, default), "
                          "3 = two-way, 1 = single bf16 pass; the frozen encoder uses the two-way split unless 1")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="run the frozen encoder and the transformer step of a batch back to back instead of "
+                         "overlapping the encoder of batch i+1 with the step of batch i")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -174,7 +177,8 @@ def main():
     sd = synthetic.make_state_dict(load_spec(), 0)          # identical replicas on every rank
     model.load_state_dict(sd, strict=True)
     model = model.to(dev).train()
-    trainer = HotPathTrainer(model, B, O, P, world_size=world, split=args.split, use_graph=not args.no_graph)
+    trainer = HotPathTrainer(model, B, O, P, world_size=world, split=args.split, use_graph=not args.no_graph,
+                             pipeline=not args.no_pipeline)
     # four distinct pinned host batches per rank, cycled (seed = cfg_id*1000 + rank)
     host = [synthetic.make_batch(B, O, P, seed=2000 + rank + 17 * i).pin() for i in range(4)]
     devb = [h.to(dev) for h in host]
@@ -247,6 +251,9 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.config, "batch_per_gpu": B, "objects": O, "points": P,
                        "l2": "flushed (256 MB memset) between timed iterations", "parallelism": f"dp{world}",
+                       "schedule": "sequential" if args.no_pipeline else
+                       "pipelined: frozen encoder of batch i+1 overlaps the transformer step of batch i "
+                       "(one encoder pass + one update per step)",
                        "timing": "sum of per-step CUDA-event intervals, max over ranks"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches_per_step * args.steps),

@@ -126,6 +126,7 @@ class FusedPrompter:
         self._keep = []          # ctypes descriptors must outlive the program
         self.graph = None
         self.side_stream = torch.cuda.Stream(device=dev)
+        self.enc_stream = torch.cuda.Stream(device=dev)
         self.use_side = True
         self._side_pending = False
 
@@ -204,8 +205,15 @@ class FusedPrompter:
         w["du"] = [f(M, F) for _ in range(nl)]
         w["dqkvc"] = [f(M, QKVC) for _ in range(nl)]
         w["dx"] = [f(M, H) for _ in range(nl)]
+        # pipelined mode: the frozen encoder of the NEXT batch overlaps the transformer step of the current one
+        w["emb_next"] = None   # allocated in prepare() once the embedding width is known
+        w["obj_locs_n"], w["anchor_locs_n"], w["anchor_ori_n"] = f(B, L, 6), f(B, 3), f(B, 4)
+        w["obj_masks_n"] = torch.ones(B, L, dtype=torch.bool, device=self.dev)
+        w["upstream_n"] = f(M, H)
         self._shape = (B, L, O_pts)
         self.graph = None
+        self.graph_pipelined = None
+        self._primed = False
 
     def _gemm(self, prog, A, sa, Bm, sb, M, N, K, out, ldo, bias=0, residual=0, ldr=0, aux=0, ldaux=0,
               act=0, accumulate=0, epilogue=0, ksplit=1, a_xform=0, b_xform=0, a_site=0, b_site=0,
@@ -395,6 +403,7 @@ class FusedPrompter:
         if self._shape != (B, L, n_points):
             self._build(B, L, n_points)
             self.ws["emb"] = self._buf(B * L, self.emb_dim)
+            self.ws["emb_next"] = self._buf(B * L, self.emb_dim)
         self.emb_ptr = self.ws["emb"].data_ptr()
         self._keep = []
         self.pre_prog, self.fwd_prog, self.bwd_prog = self._programs(training)
@@ -412,12 +421,88 @@ class FusedPrompter:
         if upstream is not None:
             w["upstream"].copy_(upstream.reshape(w["upstream"].shape), non_blocking=non_blocking)
 
-    def _encode(self):
+    def _encode(self, out_key="emb"):
         w = self.ws
         enc = self.model.obj_encoder
         B, L, Pn, _ = w["obj_fts"].shape
         enc.freeze_bn(enc.pcd_net)
-        enc.pcd_net.forward_fused(w["obj_fts"].view(B * L, Pn, 6), self.enc_split, out=w["emb"])
+        enc.pcd_net.forward_fused(w["obj_fts"].view(B * L, Pn, 6), self.enc_split, out=w[out_key])
+
+    # ------------------------------------------------------------------ pipelined mode
+    # The encoder is frozen, so the embedding of batch i+1 does not depend on the update made with
+    # batch i: it is computed on its own stream while the transformer forward/backward/optimiser of
+    # batch i runs (what a prefetching data loader does for the host side).  Call order per step:
+    #   stage_points(batch_{i+1}) -> pipelined step (consumes batch_i) -> stage_scene(batch_{i+1})
+    # Results are identical to the sequential order; only the wall-clock placement changes.
+    def stage_points(self, batch, non_blocking=True):
+        self.ws["obj_fts"].copy_(batch.obj_fts, non_blocking=non_blocking)
+
+    def stage_scene(self, batch, upstream, non_blocking=True):
+        w = self.ws
+        w["obj_locs_n"].copy_(batch.obj_locs, non_blocking=non_blocking)
+        w["obj_masks_n"].copy_(batch.obj_masks, non_blocking=non_blocking)
+        w["anchor_locs_n"].copy_(batch.anchor_locs, non_blocking=non_blocking)
+        w["anchor_ori_n"].copy_(batch.anchor_orientation, non_blocking=non_blocking)
+        w["upstream_n"].copy_(upstream.reshape(w["upstream_n"].shape), non_blocking=non_blocking)
+
+    def prime(self, batch, upstream):
+        """Fill the pipeline: encode `batch` now; its transformer step happens in the next call."""
+        self.stage_points(batch)
+        self._encode("emb_next")
+        self.stage_scene(batch, upstream)
+        self._primed = True
+
+    def _pipelined_body(self, with_encoder=True):
+        w = self.ws
+        main = torch.cuda.current_stream()
+        for k in ("obj_locs", "obj_masks", "anchor_locs", "anchor_ori", "upstream"):
+            w[k].copy_(w[k + "_n"])
+        w["emb"].copy_(w["emb_next"])
+        if with_encoder:                       # fork: encoder of the incoming batch
+            self.enc_stream.wait_stream(main)
+            with torch.cuda.stream(self.enc_stream):
+                self._encode("emb_next")
+        self.flat_g.zero_()
+        torch.logical_not(w["obj_masks"], out=w["key_pad"].view(torch.bool))
+        self._run(self.pre_prog)
+        self._run(self.fwd_prog)
+        self.backward()
+        if self.world_size == 1:
+            self.optimizer_step()
+        if with_encoder:
+            main.wait_stream(self.enc_stream)  # join
+
+    def train_step_pipelined(self, flush=False):
+        """Transformer step on the staged batch (+ encoder of the batch in `obj_fts` unless flush)."""
+        assert self._primed, "call prime() first"
+        if self.graph_pipelined is not None and not flush:
+            self.graph_pipelined.replay()
+        else:
+            self._pipelined_body(with_encoder=not flush)
+        if self.world_size > 1:
+            from . import dist as _dist
+            _dist.allreduce_sum_(self.flat_g[:self.n_opt])
+            self.optimizer_step()
+        B, L = self.ws["obj_locs"].shape[:2]
+        return self.ws["tokens"].view(B, L, H)
+
+    def capture_pipelined(self):
+        """CUDA graph of one pipelined step.  Warm-up replays leave parameters untouched."""
+        assert self._primed
+        saved = (self.flat_p.clone(), self.m.clone(), self.v.clone(), self.opt_state.clone(), self.seed_counter.clone())
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._pipelined_body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            self._pipelined_body()
+        self.graph_pipelined = g
+        for dst, src in zip((self.flat_p, self.m, self.v, self.opt_state, self.seed_counter), saved):
+            dst.copy_(src)
+        torch.cuda.synchronize()
 
     def forward(self):
         """Encoder + transformer forward on the static buffers; returns tokens (B, L, 256) view."""

@@ -23,26 +23,48 @@ from .fused import FusedPrompter
 
 
 class HotPathTrainer:
+    """pipeline=True (default): the frozen encoder of batch i+1 runs concurrently with the transformer
+    forward/backward/optimiser of batch i (one call = one encoder pass + one update, identical results,
+    the update for a batch lands one call later; `flush()` drains the last one)."""
+
     def __init__(self, model: torch.nn.Module, B: int, O: int, P: int, lr: float = 3e-5,
                  weight_decay: float = 0.05, betas=(0.9, 0.999), grad_norm: float = 5.0,
-                 world_size: int = 1, split: int = 6, use_graph: bool = True):
+                 world_size: int = 1, split: int = 6, use_graph: bool = True, pipeline: bool = True):
         self.engine = FusedPrompter(model, lr=lr, weight_decay=weight_decay, betas=betas,
                                     grad_norm=grad_norm, world_size=world_size, split=split)
         self.engine.prepare(B, O, P, training=model.training)
         self.use_graph = use_graph
+        self.pipeline = pipeline
         self.n_trainable = self.engine.n_trainable
 
     def warmup(self, batch: synthetic.SceneBatch, upstream: torch.Tensor):
-        """First eager step (lazy kernel attribute setup), then graph capture."""
-        self.engine.load_inputs(batch, upstream)
-        self.engine.train_step_eager()
+        """First eager step (lazy kernel attribute setup), then graph capture (and pipeline priming)."""
+        e = self.engine
+        e.load_inputs(batch, upstream)
+        e.train_step_eager()
         torch.cuda.synchronize()
-        if self.use_graph:
-            self.engine.capture()
+        if self.pipeline:
+            e.prime(batch, upstream)
+            if self.use_graph:
+                e.capture_pipelined()
+        elif self.use_graph:
+            e.capture()
 
     def step(self, batch: synthetic.SceneBatch, upstream: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """One micro-step on `batch` (device or pinned-host tensors; copied into the engine's static
-        input buffers).  Returns the surrogate loss <obj_tokens, upstream> as a device scalar."""
-        self.engine.load_inputs(batch, upstream)
-        self.engine.train_step()
+        """One micro-step fed with `batch` (device or pinned-host tensors).  Returns the surrogate loss
+        <obj_tokens, upstream> (device scalar) of the batch whose update was applied in this call."""
+        e = self.engine
+        if not self.pipeline:
+            e.load_inputs(batch, upstream)
+            e.train_step()
+            return e.loss()
+        e.stage_points(batch)               # H2D of the point clouds: needed by the overlapped encoder
+        e.train_step_pipelined()            # update with the previously staged batch
+        loss = e.loss()
+        e.stage_scene(batch, upstream)      # small per-scene inputs of `batch`, consumed by the next call
+        return loss
+
+    def flush(self) -> torch.Tensor:
+        """Apply the update of the last staged batch (pipeline mode)."""
+        self.engine.train_step_pipelined(flush=True)
         return self.engine.loss()
