@@ -49,6 +49,11 @@ const char *msr3d_last_error(void);
 int msr3d_abi_version(void);
 /* Number of kernel launches issued through this library by the calling process. */
 unsigned long long msr3d_launch_count(void);
+/* Programmatic dependent launch (default on; env MSR3D_PDL=0 disables): kernels are launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization and wait with griddepcontrol.wait before their
+ * first global access, so consecutive small kernels overlap launch latency and set-up code. */
+void msr3d_set_pdl(int enabled);
+int msr3d_get_pdl(void);
 
 /* ------------------------------------------------------------------ group A
  * The nine pointnet2._ext operators.  Layouts and semantics are exactly the

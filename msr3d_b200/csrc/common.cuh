@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <utility>
 
 #include "../../include/msr3d_b200.h"
 
@@ -38,6 +39,35 @@ inline int check_launch(const char *what) {
   } while (0)
 
 constexpr int kNumSMs = 148;  // B200
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------
+// The step is a chain of ~60 small dependent kernels; with the ProgrammaticStreamSerialization
+// launch attribute the next kernel's CTAs are scheduled (and run their set-up code) while the
+// current kernel is still executing, and block in pdl_wait() until it has completed and flushed.
+// Every kernel of this library calls pdl_wait() before its first global access, so the
+// dependency is never weaker than stream order.  Toggle: msr3d_set_pdl() / env MSR3D_PDL=0.
+extern int g_pdl;
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_launch_dependents(); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);  // errors surface in check_launch()
+}
+#endif
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -1,11 +1,16 @@
 // Error reporting, ABI version and launch accounting for libmsr3d_b200.so.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace msr3d {
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+int g_pdl = [] {
+  const char *e = getenv("MSR3D_PDL");
+  return (e != nullptr && e[0] == '0') ? 0 : 1;
+}();
 
 int set_error(int code, const char *fmt, ...) {
   va_list ap;
@@ -21,3 +26,6 @@ MSR3D_API int msr3d_abi_version(void) { return 1; }
 MSR3D_API unsigned long long msr3d_launch_count(void) {
   return msr3d::g_launches.load(std::memory_order_relaxed);
 }
+/* Enable (1, default) / disable (0) programmatic dependent launch for subsequent launches. */
+MSR3D_API void msr3d_set_pdl(int enabled) { msr3d::g_pdl = enabled ? 1 : 0; }
+MSR3D_API int msr3d_get_pdl(void) { return msr3d::g_pdl; }

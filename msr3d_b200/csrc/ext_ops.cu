@@ -46,6 +46,7 @@ template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS)
 fps_kernel(const float *__restrict__ xyz, int ld, int32_t *__restrict__ idx,
            float *__restrict__ new_xyz, int N, int m, int log2bs, int nper) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   extern __shared__ float s_xyz[];  // N*3 floats, then m int32 picks
   int32_t *s_pick = reinterpret_cast<int32_t *>(s_xyz + (size_t)N * 3);
   constexpr int NW = THREADS / 32;
@@ -159,7 +160,7 @@ int launch_fps(const float *xyz, int ld, int32_t *idx, float *new_xyz, int B, in
     if (smem > 48 * 1024)                                                                 \
       MSR3D_CUDA(cudaFuncSetAttribute(fps_kernel<T, P>,                                   \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    fps_kernel<T, P><<<B, T, smem, stream>>>(xyz, ld, idx, new_xyz, N, m, log2bs, nper);  \
+    launch_pdl(fps_kernel<T, P>, dim3(B), dim3(T), smem, stream, xyz, ld, idx, new_xyz, N, m, log2bs, nper);  \
   } while (0)
   if (N <= 32) FPS_LAUNCH(32, 1);
   else if (N <= 64) FPS_LAUNCH(32, 2);
@@ -185,6 +186,7 @@ constexpr int kBqWarps = 4;
 __global__ void __launch_bounds__(kBqWarps * 32)
 ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int ld,
                   int32_t *__restrict__ idx, int N, int M, float radius2, int nsample) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * kBqWarps + warp;
   const int b = blockIdx.y;
@@ -224,6 +226,7 @@ ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
 __global__ void __launch_bounds__(256)
 index_gather_kernel(const float *__restrict__ points, const int32_t *__restrict__ idx,
                     float *__restrict__ out, int C, int N, int Q, size_t total) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     const size_t bc = i / Q;
@@ -235,6 +238,7 @@ index_gather_kernel(const float *__restrict__ points, const int32_t *__restrict_
 __global__ void __launch_bounds__(256)
 index_scatter_add_kernel(const float *__restrict__ grad_out, const int32_t *__restrict__ idx,
                          float *__restrict__ grad_points, int C, int N, int Q, size_t total) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     const size_t bc = i / Q;
@@ -261,6 +265,7 @@ static int flat_grid(size_t total) {
 __global__ void __launch_bounds__(128)
 three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ known,
                 float *__restrict__ dist2, int32_t *__restrict__ idx, int n, int m) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -294,6 +299,7 @@ __global__ void __launch_bounds__(256)
 three_interpolate_kernel(const float *__restrict__ points, const int32_t *__restrict__ idx,
                          const float *__restrict__ weight, float *__restrict__ out, int c,
                          int m, int n, size_t total) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     const size_t bl = i / n;
@@ -314,6 +320,7 @@ three_interpolate_grad_kernel(const float *__restrict__ grad_out,
                               const float *__restrict__ weight,
                               float *__restrict__ grad_points, int c, int n, int m,
                               size_t total) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     const size_t bl = i / n;
@@ -346,7 +353,7 @@ MSR3D_API int msr3d_gather_points_f32(const float *points, const int32_t *idx, f
   MSR3D_REQUIRE(B >= 0 && C >= 0 && N >= 1 && M >= 0, "gather_points: bad sizes");
   const size_t total = (size_t)B * C * M;
   if (total == 0) return MSR3D_OK;
-  index_gather_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(points, idx, out, C,
+  launch_pdl(index_gather_kernel, dim3(flat_grid(total)), dim3(256), 0, (cudaStream_t)stream, points, idx, out, C,
                                                                            N, M, total);
   return check_launch("gather_points");
 }
@@ -361,7 +368,7 @@ MSR3D_API int msr3d_gather_points_grad_f32(const float *grad_out, const int32_t 
                              (cudaStream_t)stream));
   const size_t total = (size_t)B * C * M;
   if (total == 0) return MSR3D_OK;
-  index_scatter_add_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(index_scatter_add_kernel, dim3(flat_grid(total)), dim3(256), 0, (cudaStream_t)stream, 
       grad_out, idx, grad_points, C, N, M, total);
   return check_launch("gather_points_grad");
 }
@@ -375,7 +382,7 @@ MSR3D_API int msr3d_ball_query_f32(const float *new_xyz, const float *xyz, int32
   if (B == 0 || M == 0 || nsample == 0) return MSR3D_OK;
   const float radius2 = radius * radius;  // ball_query_gpu.cu:22, f32 product
   dim3 grid(ceil_div(M, kBqWarps), B);
-  ball_query_kernel<<<grid, kBqWarps * 32, 0, (cudaStream_t)stream>>>(new_xyz, xyz, 3, idx, N, M,
+  launch_pdl(ball_query_kernel, dim3(grid), dim3(kBqWarps * 32), 0, (cudaStream_t)stream, new_xyz, xyz, 3, idx, N, M,
                                                                       radius2, nsample);
   return check_launch("ball_query");
 }
@@ -390,7 +397,7 @@ int launch_ball_query(const float *new_xyz, const float *xyz, int ld, int32_t *i
   if (B == 0 || M == 0 || nsample == 0) return MSR3D_OK;
   const float radius2 = radius * radius;
   dim3 grid(ceil_div(M, kBqWarps), B);
-  ball_query_kernel<<<grid, kBqWarps * 32, 0, stream>>>(new_xyz, xyz, ld, idx, N, M, radius2, nsample);
+  launch_pdl(ball_query_kernel, dim3(grid), dim3(kBqWarps * 32), 0, stream, new_xyz, xyz, ld, idx, N, M, radius2, nsample);
   return check_launch("ball_query");
 }
 }  // namespace msr3d
@@ -403,7 +410,7 @@ MSR3D_API int msr3d_group_points_f32(const float *points, const int32_t *idx, fl
                 "group_points: bad sizes");
   const size_t total = (size_t)B * C * npoint * nsample;
   if (total == 0) return MSR3D_OK;
-  index_gather_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(index_gather_kernel, dim3(flat_grid(total)), dim3(256), 0, (cudaStream_t)stream, 
       points, idx, out, C, N, npoint * nsample, total);
   return check_launch("group_points");
 }
@@ -419,7 +426,7 @@ MSR3D_API int msr3d_group_points_grad_f32(const float *grad_out, const int32_t *
                              (cudaStream_t)stream));
   const size_t total = (size_t)B * C * npoint * nsample;
   if (total == 0) return MSR3D_OK;
-  index_scatter_add_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(index_scatter_add_kernel, dim3(flat_grid(total)), dim3(256), 0, (cudaStream_t)stream, 
       grad_out, idx, grad_points, C, N, npoint * nsample, total);
   return check_launch("group_points_grad");
 }
@@ -430,7 +437,7 @@ MSR3D_API int msr3d_three_nn_f32(const float *unknown, const float *known, float
   MSR3D_REQUIRE(B >= 0 && n >= 0 && m >= 0 && B <= 65535, "three_nn: bad sizes");
   if (B == 0 || n == 0) return MSR3D_OK;
   dim3 grid(ceil_div(n, 128), B);
-  three_nn_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(unknown, known, dist2, idx, n, m);
+  launch_pdl(three_nn_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, unknown, known, dist2, idx, n, m);
   return check_launch("three_nn");
 }
 
@@ -441,7 +448,7 @@ MSR3D_API int msr3d_three_interpolate_f32(const float *points, const int32_t *id
   MSR3D_REQUIRE(B >= 0 && c >= 0 && m >= 1 && n >= 0, "three_interpolate: bad sizes");
   const size_t total = (size_t)B * c * n;
   if (total == 0) return MSR3D_OK;
-  three_interpolate_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(three_interpolate_kernel, dim3(flat_grid(total)), dim3(256), 0, (cudaStream_t)stream, 
       points, idx, weight, out, c, m, n, total);
   return check_launch("three_interpolate");
 }
@@ -456,7 +463,7 @@ MSR3D_API int msr3d_three_interpolate_grad_f32(const float *grad_out, const int3
                              (cudaStream_t)stream));
   const size_t total = (size_t)B * c * n;
   if (total == 0) return MSR3D_OK;
-  three_interpolate_grad_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(three_interpolate_grad_kernel, dim3(flat_grid(total)), dim3(256), 0, (cudaStream_t)stream, 
       grad_out, idx, weight, grad_points, c, n, m, total);
   return check_launch("three_interpolate_grad");
 }

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256)
 pack_weight_kernel(const float *__restrict__ W, int N, int K, long long sn, long long sk,
                    const float *__restrict__ row_scale, const int *__restrict__ col_perm,
                    int BN, int BK, int Np, int Kp, uint8_t *__restrict__ out) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   const int chunks_per_row = Kp / 8;
   const long long total = (long long)Np * chunks_per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -293,7 +294,6 @@ __device__ __noinline__ void epilogue_ffn1(const GemmArgs &g, uint32_t tmem_d, i
 template <int BN, bool FFN>
 __global__ void __launch_bounds__(256, 1)
 linear_tc_kernel(GemmArgs g) {
-  g.drop.resolve();
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr uint32_t kATile = kTileM * kChunkK * 2;  // one of h / m / l
   constexpr uint32_t kBTile = BN * kChunkK * 2;
@@ -314,14 +314,10 @@ linear_tc_kernel(GemmArgs g) {
   const int kc_begin = blockIdx.z * per;
   const int kc_end = min(nkc_total, kc_begin + per);
   const int nkc = kc_end - kc_begin;
-  if (nkc <= 0) return;  // uniform per CTA: nothing allocated yet
+  if (nkc <= 0) { pdl_sync(); return; }  // uniform per CTA: nothing allocated yet
 
-  // first operand chunk goes in flight before any set-up work
-  OperandRegs<kTileM> ra;
-  OperandRegs<BN> rb;
-  op_load<kTileM>(ra, g.A, g.sam, g.sak, m0, g.M, kc_begin * kChunkK, g.K, tid);
-  if (g.b_mode == 1) op_load<BN>(rb, g.Bf, g.sbn, g.sbk, nt * BN, g.N, kc_begin * kChunkK, g.K, tid);
-
+  // set-up that touches no global memory runs before the PDL wait, i.e. while the producer kernel
+  // is still executing: barrier init and TMEM allocation
   if (tid == 0) {
     mbar_init(&b_full[0], 1);
     mbar_init(&b_full[1], 1);
@@ -330,6 +326,13 @@ linear_tc_kernel(GemmArgs g) {
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&s_tmem, BN);
+  pdl_sync();
+  g.drop.resolve();
+  // first operand chunk in flight before the set-up barrier
+  OperandRegs<kTileM> ra;
+  OperandRegs<BN> rb;
+  op_load<kTileM>(ra, g.A, g.sam, g.sak, m0, g.M, kc_begin * kChunkK, g.K, tid);
+  if (g.b_mode == 1) op_load<BN>(rb, g.Bf, g.sbn, g.sbk, nt * BN, g.N, kc_begin * kChunkK, g.K, tid);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -521,8 +524,8 @@ static int launch_gemm(GemmArgs &g, int ksplit, cudaStream_t stream) {
   if (ksplit > nkc) ksplit = nkc;
   dim3 grid(ceil_div(g.M, kTileM), ceil_div(g.N, BN), ksplit);
   const bool ffn = g.a_xform != XF_NONE || g.b_xform != XF_NONE || g.epi == EPI_GELU_GRAD || g.epi == EPI_FFN1;
-  if (ffn) linear_tc_kernel<BN, true><<<grid, 256, smem, stream>>>(g);
-  else linear_tc_kernel<BN, false><<<grid, 256, smem, stream>>>(g);
+  if (ffn) launch_pdl(linear_tc_kernel<BN, true>, dim3(grid), dim3(256), smem, stream, g);
+  else launch_pdl(linear_tc_kernel<BN, false>, dim3(grid), dim3(256), smem, stream, g);
   return check_launch("linear_tc");
 }
 
@@ -547,7 +550,7 @@ MSR3D_API int msr3d_pack_weight_f32(const float *W, int N, int K, long long stri
   const long long total = (long long)Np * (Kp / 8);
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-  pack_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, N, K, stride_n, stride_k, row_scale,
+  launch_pdl(pack_weight_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, W, N, K, stride_n, stride_k, row_scale,
                                                             col_perm, BN, BK, Np, Kp,
                                                             (uint8_t *)packed);
   return check_launch("pack_weight");

@@ -17,6 +17,7 @@ struct OptState {   // device-resident, 8 floats
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float *__restrict__ g, long long n, float grad_scale, OptState *st,
              unsigned int *ticket, unsigned long long *seed_counter) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
              float *__restrict__ v, long long n, long long n_decay, float grad_scale,
              OptState *st) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   const float norm = sqrtf(st->sumsq);
   const float clip = st->max_norm > 0.f ? fminf(1.f, st->max_norm / (norm + 1e-6f)) : 1.f;
   const float gs = grad_scale * clip;
@@ -69,7 +71,10 @@ adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restri
   }
 }
 
-__global__ void reset_sumsq_kernel(OptState *st) { st->sumsq = 0.f; }
+__global__ void reset_sumsq_kernel(OptState *st) {
+  pdl_sync();
+  st->sumsq = 0.f;
+}
 
 }  // namespace msr3d
 
@@ -88,12 +93,12 @@ MSR3D_API int msr3d_adamw_clip_step_f32(float *params, const float *grads, float
   OptState *st = reinterpret_cast<OptState *>(state);
   int grid = (int)((n + 255) / 256);
   if (grid > kNumSMs * 4) grid = kNumSMs * 4;
-  reset_sumsq_kernel<<<1, 1, 0, s>>>(st);
+  launch_pdl(reset_sumsq_kernel, dim3(1), dim3(1), 0, s, st);
   int rc = check_launch("reset_sumsq");
   if (rc) return rc;
-  sumsq_kernel<<<grid, 256, 0, s>>>(grads, n, grad_scale, st, ticket, seed_counter);
+  launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, s, grads, n, grad_scale, st, ticket, seed_counter);
   rc = check_launch("sumsq");
   if (rc) return rc;
-  adamw_kernel<<<grid, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, n_decay, grad_scale, st);
+  launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq, n, n_decay, grad_scale, st);
   return check_launch("adamw");
 }

@@ -120,6 +120,7 @@ __device__ __forceinline__ void epilogue_to_operand(uint32_t tmem_d, const float
 template <int K0P, int C1, int C2, int C3, bool RESIDENT>
 __global__ void __launch_bounds__(256, RESIDENT ? 2 : 1)
 sa_mlp_kernel(const SaParams p) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   using L = SaLayout<K0P, C1, C2, C3, RESIDENT>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *s_a = smem;
@@ -304,7 +305,7 @@ static int launch_sa_mlp(const SaParams &p, cudaStream_t stream) {
   }
   const int per_sm = RESIDENT ? 2 : 1;
   int grid = p.n_tiles < kNumSMs * per_sm ? p.n_tiles : kNumSMs * per_sm;
-  kern<<<grid, 256, L::kSmem, stream>>>(p);
+  launch_pdl(kern, dim3(grid), dim3(256), L::kSmem, stream, p);
   return check_launch("sa_mlp_kernel");
 }
 
@@ -330,6 +331,7 @@ namespace msr3d {
 __global__ void __launch_bounds__(256)
 scatter_xyz_cols_kernel(const float *__restrict__ src, float *__restrict__ dst, long long ld_dst,
                         int col0, int rows) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rows * 3) dst[(long long)(i / 3) * ld_dst + col0 + i % 3] = src[i];
 }
@@ -340,7 +342,7 @@ MSR3D_API int msr3d_scatter_xyz_cols_f32(const float *xyz, float *dst, long long
                                          int rows, msr3d_stream_t stream) {
   MSR3D_REQUIRE(xyz && dst && rows >= 0 && col0 >= 0 && ld_dst >= col0 + 3, "scatter_xyz_cols: bad args");
   if (rows == 0) return MSR3D_OK;
-  scatter_xyz_cols_kernel<<<ceil_div(rows * 3, 256), 256, 0, (cudaStream_t)stream>>>(xyz, dst, ld_dst,
+  launch_pdl(scatter_xyz_cols_kernel, dim3(ceil_div(rows * 3, 256)), dim3(256), 0, (cudaStream_t)stream, xyz, dst, ld_dst,
                                                                                     col0, rows);
   return check_launch("scatter_xyz_cols");
 }

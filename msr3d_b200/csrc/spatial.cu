@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(kMaxL)
 geometry_kernel(const float *__restrict__ loc, const float *__restrict__ anchor,
                 const float *__restrict__ quat, int L, int dist_norm, int use_agent_frame,
                 float *__restrict__ pw, float *__restrict__ ff, float *__restrict__ sz) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   __shared__ float cx[kMaxL], cy[kMaxL], cz[kMaxL];
   __shared__ float s_red[kMaxL / 32];
   const int b = blockIdx.x, l = threadIdx.x;
@@ -195,6 +196,7 @@ attn_tail_fwd_kernel(const float *__restrict__ o, const float *__restrict__ x, i
                      float *__restrict__ xhat_a, float *__restrict__ rstd_a,
                      float *__restrict__ xhat_1, float *__restrict__ rstd_1,
                      float *__restrict__ y2) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   drop.resolve();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
@@ -227,6 +229,7 @@ attn_tail_bwd_kernel(const float *__restrict__ dy2, int M, LnParams lna, LnParam
                      float *__restrict__ do_, float *__restrict__ dgamma_a,
                      float *__restrict__ dbeta_a, float *__restrict__ dgamma_1,
                      float *__restrict__ dbeta_1, float *__restrict__ dbias_o) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   drop.resolve();
   __shared__ float s_acc[5 * kD];
   ColAcc acc{s_acc};
@@ -279,6 +282,7 @@ ffn_tail_fwd_kernel(const float *__restrict__ f, const float *__restrict__ y2, i
                     Dropout drop, unsigned site_2, const float *__restrict__ add,
                     float *__restrict__ xhat_2, float *__restrict__ rstd_2, float *__restrict__ y3,
                     float *__restrict__ x_next) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   drop.resolve();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
@@ -307,6 +311,7 @@ ffn_tail_bwd_kernel(const float *__restrict__ dy3, int M, LnParams ln2, Dropout 
                     const float *__restrict__ xhat_2, const float *__restrict__ rstd_2,
                     float *__restrict__ dy2, float *__restrict__ df, float *__restrict__ dgamma_2,
                     float *__restrict__ dbeta_2, float *__restrict__ dbias_2) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   drop.resolve();
   __shared__ float s_acc[3 * kD];
   ColAcc acc{s_acc};
@@ -347,6 +352,7 @@ qpos_fwd_kernel(const float *__restrict__ h1, const float *__restrict__ sz, int 
                 const float *__restrict__ extra_a, const float *__restrict__ extra_b,
                 float *__restrict__ xhat_l, float *__restrict__ rstd_l, float *__restrict__ xhat_s,
                 float *__restrict__ rstd_s, float *__restrict__ qpos, float *__restrict__ qpos0) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -385,6 +391,7 @@ qpos_bwd_kernel(const float *__restrict__ dq, const float *__restrict__ dq1,
                 float *__restrict__ dh1, float *__restrict__ dgamma_l, float *__restrict__ dbeta_l,
                 float *__restrict__ dgamma_s, float *__restrict__ dbeta_s, float *__restrict__ dWs,
                 float *__restrict__ dbs, float *__restrict__ dbl) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   __shared__ float s_acc[8 * kD];
   ColAcc acc{s_acc};
   acc.zero(8, threadIdx.x);
@@ -451,6 +458,7 @@ qpos_bwd_kernel(const float *__restrict__ dq, const float *__restrict__ dq1,
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float *__restrict__ src, long long ld, int M, int N, float *__restrict__ d0,
               float *__restrict__ d1, float *__restrict__ d2, int rows_per_cta) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int m0 = blockIdx.y * rows_per_cta;
@@ -481,6 +489,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32)
 attn_fwd_kernel(const float *__restrict__ qkvc, int ldq, const float *__restrict__ pw,
                 const unsigned char *__restrict__ key_pad, int L, int H, float *__restrict__ P,
                 float *__restrict__ LOC, float *__restrict__ ctx, int ldc) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   extern __shared__ float sm[];
   const int LT = ((L + 31) / 32) * 32;
   float *kT = sm;                 // [32][LT]
@@ -572,6 +581,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32)
 attn_bwd_kernel(const float *__restrict__ dctx, int ldc, const float *__restrict__ qkvc, int ldq,
                 const float *__restrict__ pw, const float *__restrict__ P,
                 const float *__restrict__ LOC, int L, int H, float *__restrict__ dqkvc) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   extern __shared__ float sm[];
   const int LT = ((L + 31) / 32) * 32;
   const int LP = LT + 1;
@@ -676,6 +686,7 @@ attn_bwd_kernel(const float *__restrict__ dctx, int ldc, const float *__restrict
 }
 
 __global__ void dropout_mask_kernel(Dropout drop, unsigned site, long long n, float *out) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   drop.resolve();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
@@ -698,7 +709,7 @@ MSR3D_API int msr3d_spatial_geometry_f32(const float *loc, const float *anchor, 
   MSR3D_REQUIRE(!use_agent_frame || (anchor && quat), "geometry: agent frame needs anchor + quaternion");
   MSR3D_REQUIRE(B >= 0 && L >= 1 && L <= kMaxL, "geometry: L=%d must be in [1,%d]", L, kMaxL);
   if (B == 0) return MSR3D_OK;
-  geometry_kernel<<<B, kMaxL, 0, (cudaStream_t)stream>>>(loc, anchor, quat, L, dist_norm,
+  launch_pdl(geometry_kernel, dim3(B), dim3(kMaxL), 0, (cudaStream_t)stream, loc, anchor, quat, L, dist_norm,
                                                         use_agent_frame, pw, ff, sz);
   return check_launch("geometry");
 }
@@ -711,7 +722,7 @@ MSR3D_API int msr3d_attn_tail_fwd_f32(const float *o, const float *x, int M, con
   MSR3D_REQUIRE(o && x && gamma_a && beta_a && gamma_1 && beta_1 && xhat_a && rstd_a && xhat_1 && rstd_1 && y2,
                 "attn_tail_fwd: null pointer");
   if (M <= 0) return MSR3D_OK;
-  attn_tail_fwd_kernel<<<ln_grid(M), kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+  launch_pdl(attn_tail_fwd_kernel, dim3(ln_grid(M)), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, 
       o, x, M, LnParams{gamma_a, beta_a}, LnParams{gamma_1, beta_1}, mk(seed, p, seed_ptr), site_fc, site_1,
       xhat_a, rstd_a, xhat_1, rstd_1, y2);
   return check_launch("attn_tail_fwd");
@@ -728,7 +739,7 @@ MSR3D_API int msr3d_attn_tail_bwd_f32(const float *dy2, int M, const float *gamm
   MSR3D_REQUIRE(dy2 && gamma_a && gamma_1 && xhat_a && rstd_a && xhat_1 && rstd_1 && dx && do_,
                 "attn_tail_bwd: null pointer");
   if (M <= 0) return MSR3D_OK;
-  attn_tail_bwd_kernel<<<ln_grid(M), kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+  launch_pdl(attn_tail_bwd_kernel, dim3(ln_grid(M)), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, 
       dy2, M, LnParams{gamma_a, nullptr}, LnParams{gamma_1, nullptr}, mk(seed, p, seed_ptr), site_fc, site_1,
       xhat_a, rstd_a, xhat_1, rstd_1, dx, do_, dgamma_a, dbeta_a, dgamma_1, dbeta_1, dbias_o);
   return check_launch("attn_tail_bwd");
@@ -741,7 +752,7 @@ MSR3D_API int msr3d_ffn_tail_fwd_f32(const float *f, const float *y2, int M, con
                                      float *y3, float *x_next, msr3d_stream_t stream) {
   MSR3D_REQUIRE(f && y2 && gamma_2 && beta_2 && xhat_2 && rstd_2, "ffn_tail_fwd: null pointer");
   if (M <= 0) return MSR3D_OK;
-  ffn_tail_fwd_kernel<<<ln_grid(M), kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+  launch_pdl(ffn_tail_fwd_kernel, dim3(ln_grid(M)), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, 
       f, y2, M, LnParams{gamma_2, beta_2}, mk(seed, p, seed_ptr), site_2, add, xhat_2, rstd_2, y3, x_next);
   return check_launch("ffn_tail_fwd");
 }
@@ -753,7 +764,7 @@ MSR3D_API int msr3d_ffn_tail_bwd_f32(const float *dy3, int M, const float *gamma
                                      msr3d_stream_t stream) {
   MSR3D_REQUIRE(dy3 && gamma_2 && xhat_2 && rstd_2 && dy2 && df, "ffn_tail_bwd: null pointer");
   if (M <= 0) return MSR3D_OK;
-  ffn_tail_bwd_kernel<<<ln_grid(M), kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+  launch_pdl(ffn_tail_bwd_kernel, dim3(ln_grid(M)), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, 
       dy3, M, LnParams{gamma_2, nullptr}, mk(seed, p, seed_ptr), site_2, xhat_2, rstd_2, dy2, df, dgamma_2,
       dbeta_2, dbias_2);
   return check_launch("ffn_tail_bwd");
@@ -767,7 +778,7 @@ MSR3D_API int msr3d_qpos_fwd_f32(const float *h1, const float *sz, int M, const 
   MSR3D_REQUIRE(h1 && sz && Ws && bs && gamma_l && beta_l && gamma_s && beta_s && xhat_l && rstd_l &&
                     xhat_s && rstd_s && qpos && qpos0, "qpos_fwd: null pointer");
   if (M <= 0) return MSR3D_OK;
-  qpos_fwd_kernel<<<ln_grid(M), kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+  launch_pdl(qpos_fwd_kernel, dim3(ln_grid(M)), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, 
       h1, sz, M, Ws, bs, LnParams{gamma_l, beta_l}, LnParams{gamma_s, beta_s}, extra_a, extra_b,
       xhat_l, rstd_l, xhat_s, rstd_s, qpos, qpos0);
   return check_launch("qpos_fwd");
@@ -782,7 +793,7 @@ MSR3D_API int msr3d_qpos_bwd_f32(const float *dq, const float *dq1, const float 
   MSR3D_REQUIRE(dq && sz && gamma_l && gamma_s && xhat_l && rstd_l && xhat_s && rstd_s && dh1,
                 "qpos_bwd: null pointer");
   if (M <= 0) return MSR3D_OK;
-  qpos_bwd_kernel<<<ln_grid(M), kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+  launch_pdl(qpos_bwd_kernel, dim3(ln_grid(M)), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, 
       dq, dq1, dq2, sz, M, LnParams{gamma_l, nullptr}, LnParams{gamma_s, nullptr}, xhat_l, rstd_l, xhat_s,
       rstd_s, dh1, dgamma_l, dbeta_l, dgamma_s, dbeta_s, dWs, dbs, dbl);
   return check_launch("qpos_bwd");
@@ -794,7 +805,7 @@ MSR3D_API int msr3d_colsum_add_f32(const float *src, long long ld, int M, int N,
   if (M == 0 || N == 0) return MSR3D_OK;
   const int rows = 32;
   dim3 grid(ceil_div(N, 256), ceil_div(M, rows));
-  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld, M, N, dst0, dst1, dst2, rows);
+  launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, src, ld, M, N, dst0, dst1, dst2, rows);
   return check_launch("colsum");
 }
 
@@ -808,7 +819,7 @@ MSR3D_API int msr3d_attn_fwd_f32(const float *qkvc, int ldq, const float *pw,
   const int LT = ((L + 31) / 32) * 32;
   const size_t smem = ((size_t)kDh * LT + (size_t)L * kDh) * sizeof(float);
   const int zr = L > 2 * kAttnWarps ? 2 : 1;
-  attn_fwd_kernel<<<dim3(H, B, zr), kAttnWarps * 32, smem, (cudaStream_t)stream>>>(
+  launch_pdl(attn_fwd_kernel, dim3(dim3(H, B, zr)), dim3(kAttnWarps * 32), smem, (cudaStream_t)stream, 
       qkvc, ldq, pw, key_pad, L, H, P, LOC, ctx, ldc);
   return check_launch("attn_fwd");
 }
@@ -829,7 +840,7 @@ MSR3D_API int msr3d_attn_bwd_f32(const float *dctx, int ldc, const float *qkvc, 
                                     (int)bytes(kMaxL)));
     configured = true;
   }
-  attn_bwd_kernel<<<dim3(H, B), kAttnWarps * 32, bytes(L), (cudaStream_t)stream>>>(
+  launch_pdl(attn_bwd_kernel, dim3(dim3(H, B)), dim3(kAttnWarps * 32), bytes(L), (cudaStream_t)stream, 
       dctx, ldc, qkvc, ldq, pw, P, LOC, L, H, dqkvc);
   return check_launch("attn_bwd");
 }
@@ -841,6 +852,6 @@ MSR3D_API int msr3d_dropout_mask_f32(unsigned long long seed, const unsigned lon
                                      msr3d_stream_t stream) {
   MSR3D_REQUIRE(out && n >= 0 && p >= 0.f && p < 1.f, "dropout_mask: bad args");
   if (n == 0) return MSR3D_OK;
-  dropout_mask_kernel<<<kNumSMs * 2, 256, 0, (cudaStream_t)stream>>>(mk(seed, p, seed_ptr), site, n, out);
+  launch_pdl(dropout_mask_kernel, dim3(kNumSMs * 2), dim3(256), 0, (cudaStream_t)stream, mk(seed, p, seed_ptr), site, n, out);
   return check_launch("dropout_mask");
 }
