@@ -175,31 +175,47 @@ sa_mlp_kernel(const SaParams p) {
       const float *x = p.xyz + ((size_t)cloud * p.Nsrc + nb) * p.ld_xyz;
       const float *c = p.new_xyz + ((size_t)cloud * p.npoint + centre) * 3;
       const bool vec_ok = (p.ld_feat & 3) == 0 && (reinterpret_cast<uintptr_t>(p.feat) & 15) == 0;
-#pragma unroll 1
-      for (int ch = half; ch < K0P / 8; ch += 2) {
-        float v[8];
-        const int k0 = ch * 8;
-        if (vec_ok && k0 + 8 <= p.nfeat) {
-          const float4 a = *reinterpret_cast<const float4 *>(f + k0);
-          const float4 b = *reinterpret_cast<const float4 *>(f + k0 + 4);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-          v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
+      // chunks ch = half, half+2, ... in batches of three: the six 16 B loads of a batch are issued
+      // before any conversion, so a tile pays 3 L2 round trips here instead of 9
+      constexpr int kChunks = K0P / 8;
+      constexpr int kIters = (kChunks + 1) / 2;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int k = k0 + j;
-            float val = 0.f;
-            if (k < p.nfeat) val = f[k];
-            else if (k < p.nfeat + 3) val = __fsub_rn(x[k - p.nfeat], c[k - p.nfeat]);  // pointnet2_utils.py:347
-            v[j] = val;
+      for (int it0 = 0; it0 < kIters; it0 += 3) {
+        float v[3][8];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int ch = half + 2 * (it0 + u);
+          const int k0 = ch * 8;
+          if (it0 + u < kIters && ch < kChunks) {
+            if (vec_ok && k0 + 8 <= p.nfeat) {
+              const float4 a = *reinterpret_cast<const float4 *>(f + k0);
+              const float4 b = *reinterpret_cast<const float4 *>(f + k0 + 4);
+              v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
+              v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int k = k0 + j;
+                float val = 0.f;
+                if (k < p.nfeat) val = f[k];
+                else if (k < p.nfeat + 3) val = __fsub_rn(x[k - p.nfeat], c[k - p.nfeat]);  // pointnet2_utils.py:347
+                v[u][j] = val;
+              }
+            }
           }
         }
-        uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) split_pack2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-        const uint32_t off = chunk_offset(128, row, ch);
-        *reinterpret_cast<uint4 *>(s_a + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4 *>(s_a + 128u * K0P * 2u + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        for (int u = 0; u < 3; ++u) {
+          const int ch = half + 2 * (it0 + u);
+          if (it0 + u < kIters && ch < kChunks) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split_pack2(v[u][2 * j], v[u][2 * j + 1], hi[j], lo[j]);
+            const uint32_t off = chunk_offset(128, row, ch);
+            *reinterpret_cast<uint4 *>(s_a + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(s_a + 128u * K0P * 2u + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
       }
     }
     fence_async_smem();
