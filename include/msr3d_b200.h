@@ -54,6 +54,10 @@ unsigned long long msr3d_launch_count(void);
  * first global access, so consecutive small kernels overlap launch latency and set-up code. */
 void msr3d_set_pdl(int enabled);
 int msr3d_get_pdl(void);
+/* Tuning hook for tools/gemm_sweep.py: overrides one launch heuristic (0 = GEMM N-tile 64/128,
+ * 1 = GEMM split-K factor, 2/3 = warps per CTA of the attention forward/backward kernels,
+ * 4 = row blocks per (head, scene) of the attention forward); value 0 restores the heuristic. */
+int msr3d_set_tunable(int id, int value);
 
 /* ------------------------------------------------------------------ group A
  * The nine pointnet2._ext operators.  Layouts and semantics are exactly the
@@ -119,13 +123,13 @@ int msr3d_linear_tc_f32(const float *A, long long stride_am, long long stride_ak
                         const void *packed_w, const float *bias, float *out, long long ldo, int N,
                         int act, int pool, int split, int accumulate, msr3d_stream_t stream);
 /* General tensor-core GEMM with fp32 (strided) operands on both sides:
- *   out[M,N] (+)= epilogue( act( xa(A)[M,K] * xb(B)[N,K]^T + bias ) ) + residual
+ *   out[M,N] (+)= epilogue( act( A[M,K] * B[N,K]^T + bias ) ) + residual
  * Used by the spatial transformer's forward and backward (weights and their transposes are
  * read in place through strides; nothing is pre-packed).  Element (m,k) of A at
  * A[m*stride_am + k*stride_ak]; element (n,k) of B at B[n*stride_bn + k*stride_bk].
- *   a_xform / b_xform: 0 none, 1 GELU, 2 GELU then dropout(site, memory offset as counter)
- *   epilogue: 0 plain; 1 x *= gelu'(aux[m,n]) * dropout_mask(epi_site);
- *             2 (FFN forward) out = dropout(gelu(x)), aux_out = gelu'(x) * mask;  3 x *= aux[m,n]
+ *   a_xform / b_xform: must be 0 (operand transforms are retired: MSR3D_ERR_UNSUPPORTED otherwise)
+ *   epilogue: 0 plain; 1 retired;
+ *             2 (FFN forward) out = dropout(gelu(x)), aux_out = gelu'(x) * mask(epi_site);  3 x *= aux[m,n]
  *   accumulate: 0 store, 1 out += (single CTA per element), 2 atomicAdd (required for ksplit > 1)
  *   ksplit: number of CTAs along K (split-K)
  *   split: 1 = one bf16 MMA per K slice, 3 = two-way split operands (hh+hm+mh, ~2^-17),
@@ -136,7 +140,7 @@ typedef struct msr3d_gemm_desc {
   const float *bias;       /* [N] or NULL */
   const float *residual;   /* [M, ld_residual] or NULL */
   long long ld_residual;
-  const float *aux;        /* [M, ld_aux] for epilogues 1 and 3 */
+  const float *aux;        /* [M, ld_aux] for epilogue 3 */
   long long ld_aux;
   float *aux_out;          /* [M, ld_aux] second output of epilogue 2 */
   float *out; long long ld_out;

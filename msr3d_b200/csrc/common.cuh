@@ -47,6 +47,11 @@ constexpr int kNumSMs = 148;  // B200
 // Every kernel of this library calls pdl_wait() before its first global access, so the
 // dependency is never weaker than stream order.  Toggle: msr3d_set_pdl() / env MSR3D_PDL=0.
 extern int g_pdl;
+// Tuning knobs (msr3d_set_tunable): 0 = library heuristics.  Used by tools/gemm_sweep.py to pick the
+// heuristics' constants on the hardware; the product never changes them.
+enum { TUNE_GEMM_BN = 0, TUNE_GEMM_KSPLIT = 1, TUNE_ATTN_FWD_WARPS = 2, TUNE_ATTN_BWD_WARPS = 3,
+       TUNE_ATTN_FWD_ZSPLIT = 4, TUNE_ATTN_BWD_CLUSTER = 5, TUNE_COUNT = 8 };
+extern int g_tune[TUNE_COUNT];
 #if defined(__CUDACC__)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -66,6 +71,26 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);  // errors surface in check_launch()
+}
+// same, with a thread-block cluster shape (grid must be a multiple of it)
+template <typename... KArgs, typename... Args>
+inline void launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                               dim3 cluster, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = cluster.x;
+  attr[1].val.clusterDim.y = cluster.y;
+  attr[1].val.clusterDim.z = cluster.z;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 #endif
 

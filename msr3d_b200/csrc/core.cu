@@ -12,6 +12,8 @@ int g_pdl = [] {
   return (e != nullptr && e[0] == '0') ? 0 : 1;
 }();
 
+int g_tune[TUNE_COUNT] = {0};
+
 int set_error(int code, const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -29,3 +31,9 @@ MSR3D_API unsigned long long msr3d_launch_count(void) {
 /* Enable (1, default) / disable (0) programmatic dependent launch for subsequent launches. */
 MSR3D_API void msr3d_set_pdl(int enabled) { msr3d::g_pdl = enabled ? 1 : 0; }
 MSR3D_API int msr3d_get_pdl(void) { return msr3d::g_pdl; }
+/* Tuning hook (tools/gemm_sweep.py): id = TUNE_* in csrc/common.cuh, value 0 = library heuristic. */
+MSR3D_API int msr3d_set_tunable(int id, int value) {
+  if (id < 0 || id >= msr3d::TUNE_COUNT) return msr3d::set_error(MSR3D_ERR_INVALID_ARG, "set_tunable: bad id %d", id);
+  msr3d::g_tune[id] = value;
+  return MSR3D_OK;
+}

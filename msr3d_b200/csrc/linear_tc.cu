@@ -80,24 +80,22 @@ pack_weight_kernel(const float *__restrict__ W, int N, int K, long long sn, long
 // in instruction-fetch stalls (ncu: stall_no_instructions).  Everything that is not on the
 // critical path is therefore kept out of line (__noinline__) or in rolled loops.
 
-// Operand element transforms applied while loading fp32 operands (before the bf16 split).
-enum { XF_NONE = 0, XF_GELU = 1, XF_GELU_DROPOUT = 2 };
 // Epilogue modes.
-//   EPI_GELU_GRAD: x *= gelu'(aux) * dropout_mask            (generic FFN backward, recomputes from u)
+//   (1 is retired: gelu'(u) is no longer recomputed in the backward, see EPI_FFN1)
 //   EPI_FFN1     : out = dropout(gelu(x)), aux_out = gelu'(x) * dropout_mask   (FFN forward: both the
 //                  hidden activation and its local derivative are materialised once, 2 MB each)
 //   EPI_MUL_AUX  : x *= aux                                   (FFN backward using the stored derivative)
-enum { EPI_PLAIN = 0, EPI_GELU_GRAD = 1, EPI_FFN1 = 2, EPI_MUL_AUX = 3 };
+enum { EPI_PLAIN = 0, EPI_FFN1 = 2, EPI_MUL_AUX = 3 };
 
 struct GemmArgs {
-  const float *A; long long sam, sak; int a_xform; unsigned a_site;
+  const float *A; long long sam, sak;
   const uint8_t *PW;                                   // packed B (b_mode 0)
-  const float *Bf; long long sbn, sbk; int b_xform; unsigned b_site;  // fp32 B (b_mode 1)
+  const float *Bf; long long sbn, sbk;                 // fp32 B (b_mode 1)
   int b_mode;
   int M, N, K, Kp;
   const float *bias;                                   // [N] nullable
   const float *res; long long ldr;                     // residual [M,N] added after act, nullable
-  const float *aux; long long ldaux; unsigned epi_site;  // EPI_GELU_GRAD: pre-activation u[M,N]; EPI_MUL_AUX: factor
+  const float *aux; long long ldaux; unsigned epi_site;  // EPI_MUL_AUX: factor [M,N]; epi_site: dropout site of EPI_FFN1
   float *aux_out;                                        // EPI_FFN1: second output [M, ldaux]
   float *out; long long ldo;
   int act, pool, split, accumulate, epi;               // accumulate: 0 store, 1 +=, 2 atomicAdd
@@ -112,29 +110,20 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.f);
   return act_slow(v, act);
 }
-__device__ __noinline__ float xform_slow(float v, int mode, const Dropout *d, unsigned site, long long off) {
-  v = gelu_f(v);
-  if (mode == XF_GELU_DROPOUT) v = d->apply(v, (uint64_t)off, site);
-  return v;
-}
-__device__ __noinline__ float gelu_grad_masked(float x, float u, const Dropout *d, unsigned site, long long off) {
-  return x * gelu_grad_f(u) * d->mask((uint64_t)off, site);
-}
 // (dropout(gelu(x)), gelu'(x) * mask)
-__device__ __noinline__ float2 ffn1_pair(float x, const Dropout *d, unsigned site, long long off) {
-  const float m = d->mask((uint64_t)off, site);
-  return make_float2(gelu_f(x) * m, gelu_grad_f(x) * m);
-}
-
-// An (R x 64) fp32 operand chunk in registers: thread t holds row t % R, and the threads sharing a
-// row split the eight 8-wide k groups.  Lanes map to consecutive rows: conflict-free 16 B shared
-// stores, and for transposed operands (k stride != 1, row stride 1) fully coalesced global loads.
-// Loading (op_load) and converting (op_store) are separate so that chunk i+1 is in flight while
-// chunk i is converted, fenced and multiplied: these GEMMs are latency bound, not bandwidth bound.
+// An (R x 64) fp32 operand chunk in registers, 512 producer threads, R/64 groups of 8 consecutive k per thread.
+// Two thread -> element mappings, chosen per operand from its strides (lanes must walk along the
+// unit-stride dimension or every warp load touches 32 different 128 B lines — measured: 2.2 us per
+// chunk, LSU bound, with the row mapping on K-contiguous operands):
+//   k-major operand (k stride 1: activations, weights W[N,K]):  k group = tid % 8, rows tid/8 + 64 c
+//       -> a warp reads 4 rows x 256 contiguous bytes per pair of 16 B loads;
+//   transposed operand (row stride 1: W^T in data gradients, X^T / dY^T in weight gradients):
+//       row = tid % R, k groups (tid / R) * R/64 + c  -> 32 consecutive rows per scalar load.
+// Loading (op_load) and converting (op_store) are separate so that chunks are in flight while
+// earlier ones are converted, fenced and multiplied.
 template <int R>
 struct OperandRegs {
-  static constexpr int kThreadsPerRow = 256 / R;       // R = 128 -> 2
-  static constexpr int kPer = 8 / kThreadsPerRow;      // 8-wide k groups per thread
+  static constexpr int kPer = R / 64;
   float v[kPer][8];
 };
 
@@ -142,53 +131,49 @@ template <int R>
 __device__ __forceinline__ void op_load(OperandRegs<R> &o, const float *__restrict__ base, long long sr,
                                         long long sk, int r0, int rmax, int k0, int K, int tid) {
   constexpr int kPer = OperandRegs<R>::kPer;
-  const int row = tid % R, part = tid / R;
-  const bool row_ok = (r0 + row) < rmax;
-  const float *rp = base + (long long)(r0 + row) * sr;
-  const bool vec_ok = (sk == 1) && ((sr & 3) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+  if (sk == 1) {
+    const bool vec_ok = ((sr & 3) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+    const int kk = k0 + (tid & 7) * 8;
 #pragma unroll
-  for (int c = 0; c < kPer; ++c) {
-    const int kk = k0 + (part * kPer + c) * 8;
-    if (row_ok && vec_ok && kk + 8 <= K) {
-      const float4 a = *reinterpret_cast<const float4 *>(rp + kk);
-      const float4 b = *reinterpret_cast<const float4 *>(rp + kk + 4);
-      o.v[c][0] = a.x; o.v[c][1] = a.y; o.v[c][2] = a.z; o.v[c][3] = a.w;
-      o.v[c][4] = b.x; o.v[c][5] = b.y; o.v[c][6] = b.z; o.v[c][7] = b.w;
-    } else {
+    for (int c = 0; c < kPer; ++c) {
+      const int row = (tid >> 3) + 64 * c;
+      const bool row_ok = (r0 + row) < rmax;
+      const float *rp = base + (long long)(r0 + row) * sr + kk;
+      if (row_ok && vec_ok && kk + 8 <= K) {
+        const float4 a = *reinterpret_cast<const float4 *>(rp);
+        const float4 b = *reinterpret_cast<const float4 *>(rp + 4);
+        o.v[c][0] = a.x; o.v[c][1] = a.y; o.v[c][2] = a.z; o.v[c][3] = a.w;
+        o.v[c][4] = b.x; o.v[c][5] = b.y; o.v[c][6] = b.z; o.v[c][7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[c][j] = (row_ok && kk + j < K) ? rp[j] : 0.f;
+      }
+    }
+  } else {
+    const int row = tid % R, part = tid / R;
+    const bool row_ok = (r0 + row) < rmax;
+    const float *rp = base + (long long)(r0 + row) * sr;
+#pragma unroll
+    for (int c = 0; c < kPer; ++c) {
+      const int kk = k0 + (part * kPer + c) * 8;
 #pragma unroll
       for (int j = 0; j < 8; ++j) o.v[c][j] = (row_ok && kk + j < K) ? rp[(long long)(kk + j) * sk] : 0.f;
     }
   }
 }
 
-// FFN variant only: GELU (+ dropout) on the loaded hidden activations.  Unrolled (the values must stay
-// in registers) around an out-of-line scalar function.
-template <int R>
-__device__ __forceinline__ void op_xform(OperandRegs<R> &o, long long sr, long long sk, int r0, int rmax,
-                                         int k0, int K, int xmode, const Dropout *drop, unsigned site, int tid) {
-  constexpr int kPer = OperandRegs<R>::kPer;
-  const int row = tid % R, part = tid / R;
-  if ((r0 + row) >= rmax) return;
-#pragma unroll
-  for (int c = 0; c < kPer; ++c)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int kk = k0 + (part * kPer + c) * 8 + j;
-      if (kk < K)
-        o.v[c][j] = xform_slow(o.v[c][j], xmode, drop, site, (long long)(r0 + row) * sr + (long long)kk * sk);
-    }
-}
-
-// split to bf16 and store in the canonical layout: tiles [h | m | l] `tile_bytes` apart
+// split to bf16 and store in the canonical layout with padded K stride: tiles [h | m | l] are
+// `tile_bytes` apart; `kmajor` = the mapping op_load used (sk == 1)
 template <int R>
 __device__ __forceinline__ void op_store(const OperandRegs<R> &o, uint8_t *tiles, uint32_t tile_bytes,
-                                         bool three_way, int tid) {
+                                         bool three_way, bool kmajor, int tid) {
   constexpr int kPer = OperandRegs<R>::kPer;
-  const int row = tid % R, part = tid / R;
+  constexpr uint32_t kLbo = lbo_padded(R);
 #pragma unroll
   for (int c = 0; c < kPer; ++c) {
     uint32_t h[4], m[4], l[4];
-    const uint32_t off = chunk_offset(R, row, part * kPer + c);
+    const uint32_t off = kmajor ? (uint32_t)(tid & 7) * kLbo + (uint32_t)((tid >> 3) + 64 * c) * 16u
+                                : (uint32_t)((tid / R) * kPer + c) * kLbo + (uint32_t)(tid % R) * 16u;
     if (three_way) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) split_pack2_3way(o.v[c][2 * j], o.v[c][2 * j + 1], h[j], m[j], l[j]);
@@ -227,6 +212,11 @@ __device__ __forceinline__ void row_load16(const float *p, bool vec, int n_valid
   }
 }
 
+// four consecutive floats added to global memory with one reduction (REDG.ADD.F32x4), 16 B aligned
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // 32 lanes x 4 columns of f32
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
@@ -246,7 +236,7 @@ __device__ __noinline__ void epilogue_ffn1(const GemmArgs &g, uint32_t tmem_d, i
   // 16 columns per step (N % 16 == 0 is required by the launcher for this epilogue): all loads of a
   // step are issued together and the 16 independent erf/exp chains hide each other's latency
 #pragma unroll 1
-  for (int c0 = h * (BN / 2); c0 < (h + 1) * (BN / 2); c0 += 16) {
+  for (int c0 = h * (BN / 4); c0 < (h + 1) * (BN / 4); c0 += 16) {
     const int n0 = nt * BN + c0;
     if (n0 >= g.N) break;
     uint32_t r[16];
@@ -284,146 +274,19 @@ __device__ __noinline__ void epilogue_ffn1(const GemmArgs &g, uint32_t tmem_d, i
   }
 }
 
-// ---------------------------------------------------------------------------
-// The GEMM.  256 threads: every thread loads/splits operands; thread 0 drives TMA and
-// the tensor core; all 8 warps run the epilogue (warp w owns TMEM lanes
-// 32*(w%4).., column half w/4).  gridDim = (M tiles, N tiles, K splits).
-// ---------------------------------------------------------------------------
-// FFN = true adds the operand transforms (GELU / dropout on load) and the gelu'(u) epilogue: only the
-// three FFN GEMMs need them, everything else runs the smaller FFN = false instance.
-template <int BN, bool FFN>
-__global__ void __launch_bounds__(256, 1)
-linear_tc_kernel(GemmArgs g) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr uint32_t kATile = kTileM * kChunkK * 2;  // one of h / m / l
-  constexpr uint32_t kBTile = BN * kChunkK * 2;
-  constexpr uint32_t kBBlock = 2 * kBTile;           // h + m (packed image)
-  // stage = A tiles [h | m | l] then B tiles [h | m | l]; the third tiles only exist for split 6
-  constexpr uint32_t kAOff = 0, kBOff = 3 * kATile;
-  constexpr uint32_t kStage = 3 * kATile + 3 * kBTile;
-  __shared__ __align__(8) uint64_t b_full[2];
-  __shared__ __align__(8) uint64_t mma_done[2];
-  __shared__ uint32_t s_tmem;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int m0 = blockIdx.x * kTileM;
-  const int nt = blockIdx.y;
-  const int nkc_total = g.Kp / kChunkK;
-  // K split: contiguous chunk ranges per blockIdx.z
-  const int per = (nkc_total + gridDim.z - 1) / gridDim.z;
-  const int kc_begin = blockIdx.z * per;
-  const int kc_end = min(nkc_total, kc_begin + per);
-  const int nkc = kc_end - kc_begin;
-  if (nkc <= 0) { pdl_sync(); return; }  // uniform per CTA: nothing allocated yet
-
-  // set-up that touches no global memory runs before the PDL wait, i.e. while the producer kernel
-  // is still executing: barrier init and TMEM allocation
-  if (tid == 0) {
-    mbar_init(&b_full[0], 1);
-    mbar_init(&b_full[1], 1);
-    mbar_init(&mma_done[0], 1);
-    mbar_init(&mma_done[1], 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc(&s_tmem, BN);
-  pdl_sync();
-  g.drop.resolve();
-  // first operand chunk in flight before the set-up barrier
-  OperandRegs<kTileM> ra;
-  OperandRegs<BN> rb;
-  op_load<kTileM>(ra, g.A, g.sam, g.sak, m0, g.M, kc_begin * kChunkK, g.K, tid);
-  if (g.b_mode == 1) op_load<BN>(rb, g.Bf, g.sbn, g.sbk, nt * BN, g.N, kc_begin * kChunkK, g.K, tid);
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem_d = s_tmem;
-  const uint32_t idesc = make_idesc_bf16(kTileM, BN);
-  const bool three_way = g.split == 6;
-
-#pragma unroll 1
-  for (int i = 0; i < nkc; ++i) {
-    const int kc = kc_begin + i;
-    const int s = i & 1;
-    uint8_t *st = smem + (size_t)s * kStage;
-    if (i >= 2) mbar_wait(&mma_done[s], ((i >> 1) - 1) & 1);  // stage free again
-    if (g.b_mode == 0) {
-      if (tid == 0) {
-        mbar_expect_tx(&b_full[s], kBBlock);
-        bulk_g2s(st + kBOff, g.PW + ((size_t)nt * nkc_total + kc) * kBBlock, kBBlock, &b_full[s]);
-      }
-    } else {
-      if (FFN && g.b_xform != XF_NONE)
-        op_xform<BN>(rb, g.sbn, g.sbk, nt * BN, g.N, kc * kChunkK, g.K, g.b_xform, &g.drop, g.b_site, tid);
-      op_store<BN>(rb, st + kBOff, kBTile, three_way, tid);
-    }
-    if (FFN && g.a_xform != XF_NONE)
-      op_xform<kTileM>(ra, g.sam, g.sak, m0, g.M, kc * kChunkK, g.K, g.a_xform, &g.drop, g.a_site, tid);
-    op_store<kTileM>(ra, st + kAOff, kATile, three_way, tid);
-    if (i + 1 < nkc) {  // next chunk in flight while this one is fenced, synchronised and multiplied
-      op_load<kTileM>(ra, g.A, g.sam, g.sak, m0, g.M, (kc + 1) * kChunkK, g.K, tid);
-      if (g.b_mode == 1) op_load<BN>(rb, g.Bf, g.sbn, g.sbk, nt * BN, g.N, (kc + 1) * kChunkK, g.K, tid);
-    }
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      if (g.b_mode == 0) mbar_wait(&b_full[s], (i >> 1) & 1);
-      fence_after_sync();
-      // descriptors of K-slice 0 of every tile; a K slice (two 16 B chunks) advances the 16 B-unit
-      // address field by 2*rows, so the issue loop is pure adds (one thread issues: keep it short)
-      const uint32_t a_h = smem_u32(st) + kAOff, b_h = smem_u32(st) + kBOff;
-      uint64_t da[3], db[3];
-#pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        da[t] = kslice_desc(a_h + t * kATile, kTileM, 0);
-        db[t] = kslice_desc(b_h + t * kBTile, BN, 0);
-      }
-      constexpr uint64_t kStepA = 2 * kTileM, kStepB = 2 * BN;
-      if (g.split == 6) {
-#pragma unroll
-        for (int ks = 0; ks < kChunkK / 16; ++ks) {   // smallest products first
-          mma_bf16(tmem_d, da[1] + ks * kStepA, db[1] + ks * kStepB, idesc, (i | ks) ? 1u : 0u);
-          mma_bf16(tmem_d, da[0] + ks * kStepA, db[2] + ks * kStepB, idesc, 1u);
-          mma_bf16(tmem_d, da[2] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
-          mma_bf16(tmem_d, da[0] + ks * kStepA, db[1] + ks * kStepB, idesc, 1u);
-          mma_bf16(tmem_d, da[1] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
-          mma_bf16(tmem_d, da[0] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
-        }
-      } else {
-#pragma unroll
-        for (int ks = 0; ks < kChunkK / 16; ++ks) {
-          mma_bf16(tmem_d, da[0] + ks * kStepA, db[0] + ks * kStepB, idesc, (i | ks) ? 1u : 0u);
-          if (g.split == 3) {
-            mma_bf16(tmem_d, da[0] + ks * kStepA, db[1] + ks * kStepB, idesc, 1u);
-            mma_bf16(tmem_d, da[1] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
-          }
-        }
-      }
-      mma_commit(&mma_done[s]);
-    }
-  }
-  {  // the last commit covers every MMA issued before it
-    const int last = nkc - 1;
-    mbar_wait(&mma_done[last & 1], (last >> 1) & 1);
-    fence_after_sync();
-  }
-
-  if (FFN && g.epi == EPI_FFN1) {
-    epilogue_ffn1<BN>(g, tmem_d, nt, m0, warp, lane);
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, BN);
-    return;
-  }
+// Plain epilogue: tcgen05.ld -> bias -> act -> (* aux) -> (+ residual) -> (row-group max) -> store / += / red.add.
+template <int BN>
+__device__ __noinline__ void epilogue_plain(const GemmArgs &g, uint32_t tmem_d, int nt, int m0, int warp, int lane) {
   // ---- epilogue: 16 columns per step; every global operand of the step is loaded up front
   // (vectorised) so nothing inside the element loops waits on memory or branches per element
   const int q = warp & 3, h = warp >> 2;
   const int grow = m0 + q * 32 + lane;  // global row of this thread's TMEM lane
-  constexpr int kColsPerHalf = BN / 2;
+  constexpr int kColsPerHalf = BN / 4;   // 16 warps: 4 lane quarters x 4 column quarters
   const bool first_split = blockIdx.z == 0;
   const bool row_ok = grow < g.M;
   const bool use_bias = g.bias != nullptr && first_split;
   const bool use_res = g.res != nullptr && first_split && row_ok;
-  const bool use_aux = ((FFN && g.epi == EPI_GELU_GRAD) || g.epi == EPI_MUL_AUX) && row_ok;
+  const bool use_aux = g.epi == EPI_MUL_AUX && row_ok;
   const bool bias_vec = (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0;
   const bool res_vec = ((g.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.res) & 15) == 0);
   const bool aux_vec = ((g.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.aux) & 15) == 0) &&
@@ -457,11 +320,6 @@ linear_tc_kernel(GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] *= av[j];
       }
-    } else if (FFN && use_aux) {
-      const long long off0 = (long long)grow * g.ldaux + n0;
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j < nv) v[j] = gelu_grad_masked(v[j], av[j], &g.drop, g.epi_site, off0 + j);
     }
     if (use_res) {
 #pragma unroll
@@ -485,6 +343,9 @@ linear_tc_kernel(GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
           *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else if (g.accumulate == 2 && full && out_vec) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
       } else if (g.accumulate == 2) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -502,15 +363,170 @@ linear_tc_kernel(GemmArgs g) {
       }
     }
   }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, BN);
 }
 
-static int launch_gemm(GemmArgs &g, int ksplit, cudaStream_t stream) {
-  constexpr int BN = 128;
-  g.Kp = ceil_div(g.K, kChunkK) * kChunkK;
-  const size_t smem = 2 * (3 * (size_t)kTileM * kChunkK * 2 + 3 * (size_t)BN * kChunkK * 2) + 1024;
+// ---------------------------------------------------------------------------
+// The GEMM.  544 threads, warp specialised:
+//   warps 0-15 producers: load fp32 operand chunks (one chunk ahead, in registers), split them to
+//              bf16 and store them into a 2-stage shared-memory ring; thread 0 also starts the TMA
+//              copy of the packed weights (b_mode 0).  A stage is handed over with one mbarrier
+//              arrival per warp (`full`), and taken back when tcgen05.commit arrives on `mma_done`.
+//              Afterwards the same 16 warps run the epilogue (warp w owns TMEM lanes 32*(w%4)..,
+//              column quarter w/4).
+//   warp 16    one elected thread waits for `full` and issues the MMAs.  With the issue inside the
+//              producers' loop (thread 0, then a block barrier) every chunk cost ~2 us: seven warps
+//              sat at the barrier while warp 0 issued 24 MMAs and then caught up on its conversion
+//              work (ncu: the samples pile up right behind BAR.SYNC).
+// gridDim = (M tiles, N tiles, K splits).
+// ---------------------------------------------------------------------------
+// FFN = true adds the FFN-forward epilogue (EPI_FFN1); everything else runs the smaller instance.
+constexpr int kProducerWarps = 16;
+constexpr int kGemmThreads = (kProducerWarps + 1) * 32;
+
+template <int BN, bool FFN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+linear_tc_kernel(GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // register-written tiles have the padded K stride (umma.cuh); the TMA-loaded packed-weight image is dense
+  constexpr uint32_t kATile = tile_bytes_padded(kTileM, kChunkK);  // one of h / m / l
+  constexpr uint32_t kBTile = tile_bytes_padded(BN, kChunkK);
+  constexpr uint32_t kBTileDense = BN * kChunkK * 2;
+  constexpr uint32_t kBBlock = 2 * kBTileDense;      // h + m (packed image)
+  // stage = A tiles [h | m | l] then B tiles [h | m | l]; the third tiles only exist for split 6
+  constexpr uint32_t kAOff = 0, kBOff = 3 * kATile;
+  constexpr uint32_t kStage = 3 * kATile + 3 * kBTile;
+  __shared__ __align__(8) uint64_t full[2];      // producers -> issuer (one arrival per producer warp)
+  __shared__ __align__(8) uint64_t b_full[2];    // TMA bytes of the packed weights
+  __shared__ __align__(8) uint64_t mma_done[2];  // tensor core -> producers / epilogue
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m0 = blockIdx.x * kTileM;
+  const int nt = blockIdx.y;
+  const int nkc_total = g.Kp / kChunkK;
+  // K split: contiguous chunk ranges per blockIdx.z
+  const int per = (nkc_total + gridDim.z - 1) / gridDim.z;
+  const int kc_begin = blockIdx.z * per;
+  const int kc_end = min(nkc_total, kc_begin + per);
+  const int nkc = kc_end - kc_begin;
+  if (nkc <= 0) { pdl_sync(); return; }  // uniform per CTA: nothing allocated yet
+
+  // set-up that touches no global memory runs before the PDL wait, i.e. while the producer kernel
+  // is still executing: barrier init and TMEM allocation
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full[s], kProducerWarps);
+      mbar_init(&b_full[s], 1);
+      mbar_init(&mma_done[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kProducerWarps) tmem_alloc(&s_tmem, BN);
+  pdl_sync();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_d = s_tmem;
+  const uint32_t b_lbo = g.b_mode == 0 ? (uint32_t)BN * 16u : lbo_padded(BN);
+  const uint32_t b_tile = g.b_mode == 0 ? kBTileDense : kBTile;
+
+  if (warp == kProducerWarps) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, BN);
+      // a K=16 slice is two k columns: the start-address field (16 B units) advances by 2 * LBO / 16
+      constexpr uint64_t kStepA = 2 * (lbo_padded(kTileM) >> 4);
+      const uint64_t kStepB = 2 * (b_lbo >> 4);
+#pragma unroll 1
+      for (int i = 0; i < nkc; ++i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait(&full[s], ph);
+        if (g.b_mode == 0) mbar_wait(&b_full[s], ph);
+        fence_after_sync();
+        const uint32_t a_h = smem_u32(smem + (size_t)s * kStage) + kAOff;
+        const uint32_t b_h = smem_u32(smem + (size_t)s * kStage) + kBOff;
+        uint64_t da[3], db[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          da[t] = make_desc(a_h + t * kATile, lbo_padded(kTileM), 128u);
+          db[t] = make_desc(b_h + t * b_tile, b_lbo, 128u);
+        }
+        if (g.split == 6) {
+#pragma unroll
+          for (int ks = 0; ks < kChunkK / 16; ++ks) {   // smallest products first
+            mma_bf16(tmem_d, da[1] + ks * kStepA, db[1] + ks * kStepB, idesc, (i | ks) ? 1u : 0u);
+            mma_bf16(tmem_d, da[0] + ks * kStepA, db[2] + ks * kStepB, idesc, 1u);
+            mma_bf16(tmem_d, da[2] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
+            mma_bf16(tmem_d, da[0] + ks * kStepA, db[1] + ks * kStepB, idesc, 1u);
+            mma_bf16(tmem_d, da[1] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
+            mma_bf16(tmem_d, da[0] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < kChunkK / 16; ++ks) {
+            mma_bf16(tmem_d, da[0] + ks * kStepA, db[0] + ks * kStepB, idesc, (i | ks) ? 1u : 0u);
+            if (g.split == 3) {
+              mma_bf16(tmem_d, da[0] + ks * kStepA, db[1] + ks * kStepB, idesc, 1u);
+              mma_bf16(tmem_d, da[1] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
+            }
+          }
+        }
+        mma_commit(&mma_done[s]);   // frees the stage; the last one also releases the epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ producers, then epilogue
+    g.drop.resolve();
+    // One chunk is prefetched into registers while the previous one is converted; the 16 producer
+    // warps hide the rest of the latency (with 8 warps the SM issued 0.27 instructions per cycle per
+    // scheduler: the conversion is ~500 dependent-ish instructions per warp per chunk).
+    OperandRegs<kTileM> ra;
+    OperandRegs<BN> rb;
+    auto load_chunk = [&](int kc) {
+      op_load<kTileM>(ra, g.A, g.sam, g.sak, m0, g.M, kc * kChunkK, g.K, tid);
+      if (g.b_mode == 1) op_load<BN>(rb, g.Bf, g.sbn, g.sbk, nt * BN, g.N, kc * kChunkK, g.K, tid);
+    };
+    load_chunk(kc_begin);
+    const bool three_way = g.split == 6;
+    const bool a_kmajor = g.sak == 1, b_kmajor = g.sbk == 1;
+#pragma unroll 1
+    for (int i = 0; i < nkc; ++i) {
+      const int kc = kc_begin + i;
+      const int s = i & 1;
+      uint8_t *st = smem + (size_t)s * kStage;
+      if (i >= 2) mbar_wait(&mma_done[s], ((i >> 1) - 1) & 1);  // stage free again
+      if (g.b_mode == 0) {
+        if (tid == 0) {
+          mbar_expect_tx(&b_full[s], kBBlock);
+          bulk_g2s(st + kBOff, g.PW + ((size_t)nt * nkc_total + kc) * kBBlock, kBBlock, &b_full[s]);
+        }
+      } else {
+        op_store<BN>(rb, st + kBOff, kBTile, three_way, b_kmajor, tid);
+      }
+      op_store<kTileM>(ra, st + kAOff, kATile, three_way, a_kmajor, tid);
+      if (i + 1 < nkc) load_chunk(kc + 1);
+      fence_async_smem();      // my generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+    {  // the last commit covers every MMA issued before it
+      const int last = nkc - 1;
+      mbar_wait(&mma_done[last & 1], (last >> 1) & 1);
+      fence_after_sync();
+    }
+    if (FFN && g.epi == EPI_FFN1) epilogue_ffn1<BN>(g, tmem_d, nt, m0, warp, lane);
+    else epilogue_plain<BN>(g, tmem_d, nt, m0, warp, lane);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == kProducerWarps) tmem_dealloc(tmem_d, BN);
+}
+
+template <int BN>
+static int launch_gemm_bn(GemmArgs &g, int ksplit, cudaStream_t stream) {
+  const size_t smem = 2 * (3 * (size_t)tile_bytes_padded(kTileM, kChunkK) + 3 * (size_t)tile_bytes_padded(BN, kChunkK)) + 1024;
   static bool configured = false;
   if (!configured) {
     MSR3D_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -519,14 +535,30 @@ static int launch_gemm(GemmArgs &g, int ksplit, cudaStream_t stream) {
                                     (int)smem));
     configured = true;
   }
+  dim3 grid(ceil_div(g.M, kTileM), ceil_div(g.N, BN), ksplit);
+  const bool ffn = g.epi == EPI_FFN1;
+  if (ffn) launch_pdl(linear_tc_kernel<BN, true>, dim3(grid), dim3(kGemmThreads), smem, stream, g);
+  else launch_pdl(linear_tc_kernel<BN, false>, dim3(grid), dim3(kGemmThreads), smem, stream, g);
+  return check_launch("linear_tc");
+}
+
+// Tile selection.  Packed weights (frozen encoder) are 128-row images.  The transformer GEMMs have
+// M = B*L ~ 240 tokens: with 128-wide N tiles most of them fill 4-32 of the 148 SMs, so the N tile
+// drops to 64 while that still leaves SMs idle (half the MMA and half the B-operand work per CTA).
+static int launch_gemm(GemmArgs &g, int ksplit, cudaStream_t stream) {
+  g.Kp = ceil_div(g.K, kChunkK) * kChunkK;
   const int nkc = g.Kp / kChunkK;
+  if (g_tune[TUNE_GEMM_KSPLIT] > 0 && g.accumulate == 2 && g.act == ACT_NONE && g.epi == EPI_PLAIN)
+    ksplit = g_tune[TUNE_GEMM_KSPLIT];
   if (ksplit < 1) ksplit = 1;
   if (ksplit > nkc) ksplit = nkc;
-  dim3 grid(ceil_div(g.M, kTileM), ceil_div(g.N, BN), ksplit);
-  const bool ffn = g.a_xform != XF_NONE || g.b_xform != XF_NONE || g.epi == EPI_GELU_GRAD || g.epi == EPI_FFN1;
-  if (ffn) launch_pdl(linear_tc_kernel<BN, true>, dim3(grid), dim3(256), smem, stream, g);
-  else launch_pdl(linear_tc_kernel<BN, false>, dim3(grid), dim3(256), smem, stream, g);
-  return check_launch("linear_tc");
+  int bn = 128;
+  if (g.b_mode == 1) {
+    const int ctas128 = ceil_div(g.M, kTileM) * ceil_div(g.N, 128) * ksplit;
+    if (2 * ctas128 <= kNumSMs) bn = 64;
+    if (g_tune[TUNE_GEMM_BN] == 64 || g_tune[TUNE_GEMM_BN] == 128) bn = g_tune[TUNE_GEMM_BN];
+  }
+  return bn == 64 ? launch_gemm_bn<64>(g, ksplit, stream) : launch_gemm_bn<128>(g, ksplit, stream);
 }
 
 }  // namespace msr3d
@@ -580,7 +612,8 @@ MSR3D_API int msr3d_gemm_tc_f32(const msr3d_gemm_desc *d, msr3d_stream_t stream)
   MSR3D_REQUIRE(d->A && d->B && d->out, "gemm_tc: null pointer");
   MSR3D_REQUIRE(d->M >= 0 && d->K > 0 && d->N > 0, "gemm_tc: bad sizes M=%d K=%d N=%d", d->M, d->K, d->N);
   MSR3D_REQUIRE(d->act >= 0 && d->act <= 2 && (d->split == 1 || d->split == 3 || d->split == 6), "gemm_tc: bad act/split");
-  MSR3D_REQUIRE(d->a_xform >= 0 && d->a_xform <= 2 && d->b_xform >= 0 && d->b_xform <= 2, "gemm_tc: bad xform");
+  if (d->a_xform != 0 || d->b_xform != 0 || d->epilogue == 1)
+    return set_error(MSR3D_ERR_UNSUPPORTED, "gemm_tc: operand transforms and epilogue 1 are retired (use epilogue 2 + 3)");
   MSR3D_REQUIRE(d->epilogue >= 0 && d->epilogue <= 3, "gemm_tc: bad epilogue %d", d->epilogue);
   MSR3D_REQUIRE(d->epilogue == 0 || d->epilogue == 2 || d->aux, "gemm_tc: epilogue %d needs aux", d->epilogue);
   MSR3D_REQUIRE(d->epilogue != 2 || (d->aux_out && d->N % 16 == 0 && d->ld_out % 4 == 0 && d->ld_aux % 4 == 0 &&
@@ -593,8 +626,8 @@ MSR3D_API int msr3d_gemm_tc_f32(const msr3d_gemm_desc *d, msr3d_stream_t stream)
   MSR3D_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, "gemm_tc: bad dropout p");
   if (d->M == 0) return MSR3D_OK;
   GemmArgs g{};
-  g.A = d->A; g.sam = d->stride_am; g.sak = d->stride_ak; g.a_xform = d->a_xform; g.a_site = d->a_site;
-  g.Bf = d->B; g.sbn = d->stride_bn; g.sbk = d->stride_bk; g.b_xform = d->b_xform; g.b_site = d->b_site;
+  g.A = d->A; g.sam = d->stride_am; g.sak = d->stride_ak;
+  g.Bf = d->B; g.sbn = d->stride_bn; g.sbk = d->stride_bk;
   g.b_mode = 1;
   g.M = d->M; g.N = d->N; g.K = d->K; g.bias = d->bias; g.res = d->residual; g.ldr = d->ld_residual;
   g.aux = d->aux; g.ldaux = d->ld_aux; g.epi_site = d->epi_site; g.out = d->out; g.ldo = d->ld_out;

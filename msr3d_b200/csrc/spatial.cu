@@ -7,6 +7,8 @@
 #include "common.cuh"
 #include "rng.cuh"
 
+#include <cooperative_groups.h>
+
 namespace msr3d {
 
 constexpr int kD = 256;        // hidden size of the spatial encoder (configs/msr3d.yaml:181)
@@ -482,10 +484,10 @@ colsum_kernel(const float *__restrict__ src, long long ld, int M, int N, float *
 // Saves P and loc (B,H,L,L) for the backward pass.
 // ---------------------------------------------------------------------------
 constexpr int kDh = 32;
-constexpr int kAttnWarps = 8;
+constexpr int kAttnMaxWarps = 16;    // launch bound; the warp count itself is a launch-time choice
 constexpr int kKeysPerLane = kMaxL / 32;  // 4
 
-__global__ void __launch_bounds__(kAttnWarps * 32)
+__global__ void __launch_bounds__(kAttnMaxWarps * 32)
 attn_fwd_kernel(const float *__restrict__ qkvc, int ldq, const float *__restrict__ pw,
                 const unsigned char *__restrict__ key_pad, int L, int H, float *__restrict__ P,
                 float *__restrict__ LOC, float *__restrict__ ctx, int ldc) {
@@ -506,7 +508,8 @@ attn_fwd_kernel(const float *__restrict__ qkvc, int ldq, const float *__restrict
   __syncthreads();
   const float scale = rsqrtf((float)kDh);
   const int nj = LT / 32;
-  for (int l = blockIdx.z * kAttnWarps + warp; l < L; l += gridDim.z * kAttnWarps) {
+  const int nwarps = blockDim.x >> 5;
+  for (int l = blockIdx.z * nwarps + warp; l < L; l += gridDim.z * nwarps) {
     const float *r = qkvc + ((size_t)b * L + l) * ldq;
     const float qd = r[h * kDh + lane];
     const float swl = lane < 6 ? r[3 * D + h * 6 + lane] : 0.f;
@@ -575,24 +578,35 @@ attn_fwd_kernel(const float *__restrict__ qkvc, int ldq, const float *__restrict
 
 // Backward of the attention core.  In: dctx (M,256), P, LOC, qkvc, pw.  Out: dqkvc (M,816),
 // every column written exactly once (the cond gradient goes to columns 768..815).
-// One CTA per (head, scene).  Phase 1: warp per query row (keys over lanes) -> dlogits into shared
-// memory, dq and d(cond).  Phase 2: warp per key row (dims over lanes) -> dk, dv.
-__global__ void __launch_bounds__(kAttnWarps * 32)
+// One thread-block CLUSTER per (head, scene); the CTAs of the cluster split the rows.
+//   Phase 1: warp per query row (keys over lanes) -> dlogits and P rows into this CTA's shared
+//            memory, dq and d(cond) to global.
+//   Phase 2: warp per key row (dims over lanes) -> dk, dv.  These contract over EVERY query row, so
+//            the dlogits / P rows of the other CTAs are read through distributed shared memory
+//            (no atomics, no zero-fill, deterministic).
+// With 32 (head, scene) pairs a one-CTA-per-pair kernel filled 32 SMs and walked 8 rows per warp in
+// each phase (40 us); a cluster of 4 x 16 warps does one row per warp per phase.
+__global__ void __launch_bounds__(kAttnMaxWarps * 32)
 attn_bwd_kernel(const float *__restrict__ dctx, int ldc, const float *__restrict__ qkvc, int ldq,
                 const float *__restrict__ pw, const float *__restrict__ P,
                 const float *__restrict__ LOC, int L, int H, float *__restrict__ dqkvc) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int nz = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   extern __shared__ float sm[];
   const int LT = ((L + 31) / 32) * 32;
   const int LP = LT + 1;
+  const int rpc = (L + nz - 1) / nz;   // rows per CTA (query rows in phase 1, key rows in phase 2)
   float *qs = sm;                 // [L][32]
   float *ks = qs + L * kDh;       // [L][32]
   float *gs = ks + L * kDh;       // dctx [L][32]
   float *vT = gs + L * kDh;       // [32][LT]
-  float *dS = vT + kDh * LT;      // [L][LP]
-  float *Ps = dS + L * LP;        // [L][LP]
+  float *dS = vT + kDh * LT;      // [rpc][LP]   rows rank*rpc ..
+  float *Ps = dS + rpc * LP;      // [rpc][LP]
   const int h = blockIdx.x, b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
   const int D = H * kDh;
   for (int i = threadIdx.x; i < L * kDh; i += blockDim.x) {
     const int t = i / kDh, d = i % kDh;
@@ -605,7 +619,9 @@ attn_bwd_kernel(const float *__restrict__ dctx, int ldc, const float *__restrict
   __syncthreads();
   const float scale = rsqrtf((float)kDh);
   const int nj = LT / 32;
-  for (int l = warp; l < L; l += kAttnWarps) {
+  const int row0 = rank * rpc, row1 = min(L, row0 + rpc);
+  for (int l = row0 + warp; l < row1; l += nwarps) {
+    const int ll = l - row0;
     const float *r = qkvc + ((size_t)b * L + l) * ldq;
     const float swl = lane < 6 ? r[3 * D + h * 6 + lane] : 0.f;
     float sw[6];
@@ -640,8 +656,8 @@ attn_bwd_kernel(const float *__restrict__ dctx, int ldc, const float *__restrict
       const float dl = p[j] * (dp[j] - rowdot);   // d logits
       dp[j] = dl;
       if (j < nj && t < L) {
-        dS[l * LP + t] = dl;
-        Ps[l * LP + t] = p[j];
+        dS[ll * LP + t] = dl;
+        Ps[ll * LP + t] = p[j];
         const float lc = Lr[t];
         const float *g = pwr + t * 5;
         // log(clamp(sigmoid(z), 1e-6)): d/dz = (loc >= 1e-6) * (1 - loc); 1 - sigmoid(z) is evaluated as
@@ -672,17 +688,23 @@ attn_bwd_kernel(const float *__restrict__ dctx, int ldc, const float *__restrict
     }
     o[h * kDh + lane] = dq * scale;
   }
-  __syncthreads();
-  for (int t = warp; t < L; t += kAttnWarps) {  // lane = dim
+  cluster.sync();   // every CTA's dS / Ps rows are complete and visible cluster-wide
+  for (int t = row0 + warp; t < row1; t += nwarps) {  // lane = dim
     float dk = 0.f, dv = 0.f;
-    for (int i = 0; i < L; ++i) {
-      dk += dS[i * LP + t] * qs[i * kDh + lane];
-      dv += Ps[i * LP + t] * gs[i * kDh + lane];
+    for (int r = 0; r < nz; ++r) {
+      const float *dS_r = cluster.map_shared_rank(dS, r);
+      const float *Ps_r = cluster.map_shared_rank(Ps, r);
+      const int i0 = r * rpc, cnt = min(L, i0 + rpc) - i0;
+      for (int il = 0; il < cnt; ++il) {
+        dk += dS_r[il * LP + t] * qs[(i0 + il) * kDh + lane];
+        dv += Ps_r[il * LP + t] * gs[(i0 + il) * kDh + lane];
+      }
     }
     float *o = dqkvc + ((size_t)b * L + t) * ldq;
     o[D + h * kDh + lane] = dk * scale;
     o[2 * D + h * kDh + lane] = dv;
   }
+  cluster.sync();   // nobody exits while a peer may still be reading its shared memory
 }
 
 __global__ void dropout_mask_kernel(Dropout drop, unsigned site, long long n, float *out) {
@@ -818,8 +840,12 @@ MSR3D_API int msr3d_attn_fwd_f32(const float *qkvc, int ldq, const float *pw,
   if (B == 0) return MSR3D_OK;
   const int LT = ((L + 31) / 32) * 32;
   const size_t smem = ((size_t)kDh * LT + (size_t)L * kDh) * sizeof(float);
-  const int zr = L > 2 * kAttnWarps ? 2 : 1;
-  launch_pdl(attn_fwd_kernel, dim3(dim3(H, B, zr)), dim3(kAttnWarps * 32), smem, (cudaStream_t)stream, 
+  // few (head, scene) pairs and L ~ 60 rows: one warp per query row, rows spread over `zr` CTAs
+  int warps = g_tune[TUNE_ATTN_FWD_WARPS] > 0 ? g_tune[TUNE_ATTN_FWD_WARPS] : 16;
+  warps = max(1, min(kAttnMaxWarps, warps));
+  int zr = g_tune[TUNE_ATTN_FWD_ZSPLIT] > 0 ? g_tune[TUNE_ATTN_FWD_ZSPLIT] : ceil_div(L, warps);
+  zr = max(1, min(zr, 8));
+  launch_pdl(attn_fwd_kernel, dim3(dim3(H, B, zr)), dim3(warps * 32), smem, (cudaStream_t)stream, 
       qkvc, ldq, pw, key_pad, L, H, P, LOC, ctx, ldc);
   return check_launch("attn_fwd");
 }
@@ -830,18 +856,24 @@ MSR3D_API int msr3d_attn_bwd_f32(const float *dctx, int ldc, const float *qkvc, 
   MSR3D_REQUIRE(dctx && qkvc && pw && P && LOC && dqkvc, "attn_bwd: null pointer");
   MSR3D_REQUIRE(L >= 1 && L <= kMaxL && H >= 1, "attn_bwd: bad sizes");
   if (B == 0) return MSR3D_OK;
-  auto bytes = [](int l) {
+  // cluster of `nz` CTAs per (head, scene): rows per CTA = ceil(L / nz); `warps` rows in flight per CTA
+  int nz = g_tune[TUNE_ATTN_BWD_CLUSTER] > 0 ? g_tune[TUNE_ATTN_BWD_CLUSTER] : 4;
+  nz = max(1, min(nz, 8));
+  int warps = g_tune[TUNE_ATTN_BWD_WARPS] > 0 ? g_tune[TUNE_ATTN_BWD_WARPS] : 16;
+  warps = max(1, min(kAttnMaxWarps, warps));
+  auto bytes = [](int l, int z) {
     const int lt = ((l + 31) / 32) * 32;
-    return ((size_t)3 * l * kDh + (size_t)kDh * lt + (size_t)2 * l * (lt + 1)) * sizeof(float);
+    const int rpc = (l + z - 1) / z;
+    return ((size_t)3 * l * kDh + (size_t)kDh * lt + (size_t)2 * rpc * (lt + 1)) * sizeof(float);
   };
   static bool configured = false;
   if (!configured) {
     MSR3D_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)bytes(kMaxL)));
+                                    (int)bytes(kMaxL, 1)));
     configured = true;
   }
-  launch_pdl(attn_bwd_kernel, dim3(dim3(H, B)), dim3(kAttnWarps * 32), bytes(L), (cudaStream_t)stream, 
-      dctx, ldc, qkvc, ldq, pw, P, LOC, L, H, dqkvc);
+  launch_pdl_cluster(attn_bwd_kernel, dim3(H, B, nz), dim3(warps * 32), bytes(L, nz), (cudaStream_t)stream,
+                     dim3(1, 1, nz), dctx, ldc, qkvc, ldq, pw, P, LOC, L, H, dqkvc);
   return check_launch("attn_bwd");
 }
 

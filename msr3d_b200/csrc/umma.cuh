@@ -22,6 +22,15 @@ __host__ __device__ constexpr uint32_t chunk_offset(int rows, int r, int kchunk)
   return (uint32_t)kchunk * rows * 16 + (uint32_t)r * 16;
 }
 
+// Tiles that are written from registers (fp32 operands split on the fly) use a PADDED K stride:
+// K-adjacent core matrices are rows*16 + 16 bytes apart.  With the dense stride every 16 B chunk of
+// one row group lands in the same four banks whatever its k index, so a warp whose lanes walk along
+// k (the coalesced way to read K-contiguous global rows) would store with 8-way bank conflicts; one
+// extra 16 B per k column spreads the eight k chunks of a 64-wide block over all 32 banks.  The
+// tensor core does not care: LBO is a descriptor field.
+__host__ __device__ constexpr uint32_t lbo_padded(int rows) { return (uint32_t)rows * 16u + 16u; }
+__host__ __device__ constexpr uint32_t tile_bytes_padded(int rows, int k) { return lbo_padded(rows) * (uint32_t)(k / 8); }
+
 // 64-bit shared-memory matrix descriptor (tcgen05): bits [0,14) start>>4,
 // [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1, [61,64) swizzle = 0 (none).
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes,
@@ -58,6 +67,9 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;

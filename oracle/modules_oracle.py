@@ -307,3 +307,27 @@ def ose3d_situation(sd: SD, data: dict, *, n_head: int = 8, num_layers: int = 3,
             trace[f"layer{i}.out"] = x
             trace[f"layer{i}.attn"] = att
     return x, ~mask
+
+
+# --------------------------------------------------------------------------
+# Scene-token splice into the LLM input (the step right after the prompter)
+# --------------------------------------------------------------------------
+def scene_splice(W: torch.Tensor, b: torch.Tensor, inputs_embeds: torch.Tensor,
+                 attention_mask: torch.Tensor, input_ids: torch.Tensor, obj_tokens: torch.Tensor,
+                 obj_masks: torch.Tensor, scene_sp_token: int = 31495):
+    """MSR3D.build_embeds, scene branch (model/msr3d/msr3d.py:277-287).
+
+    scene_embeds = llm_proj(obj_tokens) cast to the embedding dtype (:277-279); written over the
+    rows of `inputs_embeds` whose id is the scene placeholder, in the row-major order of
+    `torch.where` (:280,282); the attention mask becomes bool and takes `obj_masks` at the same
+    positions (:283-287).  Returns new tensors (the reference writes in place into the embedding
+    lookup's output); differentiable w.r.t. W, b, obj_tokens.
+    Pinned by tests/golden/splice.npz (tests/golden/gen_golden_splice.py runs the reference method).
+    """
+    scene = F.linear(obj_tokens, W, b).to(inputs_embeds.dtype)
+    idx = torch.where(input_ids == scene_sp_token)
+    out = inputs_embeds.clone()
+    out[idx] = scene.reshape(-1, scene.shape[-1])
+    am = attention_mask.to(obj_masks.dtype).clone()
+    am[idx] = obj_masks.reshape(-1)
+    return out, am

@@ -99,3 +99,21 @@ def test_spatial_mha_all_fusions(golden_dir, fusion):
     out, att = mo.spatial_mha(sd, "a", x, pw, mask, 4, fusion)
     np.testing.assert_allclose(out.numpy(), fx[f"{fusion}_out"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(att.numpy(), fx[f"{fusion}_attn"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", ["f32", "f16", "bf16"])
+def test_scene_splice_matches_reference(golden_dir, case):
+    """oracle.scene_splice vs the unmodified reference MSR3D.build_embeds (msr3d.py:277-287)."""
+    fx = _load(golden_dir, "splice")
+    get = lambda k: torch.from_numpy(fx[f"{case}:{k}"])  # noqa: E731
+    dtype = getattr(torch, str(fx[f"{case}:dtype"]))
+    W, b, tok = get("W").requires_grad_(True), get("b").requires_grad_(True), get("tokens").requires_grad_(True)
+    out, am = mo.scene_splice(W, b, get("emb_rows").to(dtype), get("attention_mask"), get("ids"), tok,
+                              get("masks"))
+    assert out.dtype == dtype and am.dtype == torch.bool
+    np.testing.assert_array_equal(out.detach().float().numpy(), fx[f"{case}:out"])   # same ops, same order: exact
+    np.testing.assert_array_equal(am.numpy().astype(np.int64), fx[f"{case}:am_out"])
+    (out.float() * get("G")).sum().backward()
+    for name, t in (("dW", W), ("db", b), ("dtokens", tok)):
+        ref = fx[f"{case}:{name}"]
+        assert np.abs(t.grad.numpy() - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-6), name
