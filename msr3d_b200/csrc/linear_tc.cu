@@ -119,73 +119,96 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 //       -> a warp reads 4 rows x 256 contiguous bytes per pair of 16 B loads;
 //   transposed operand (row stride 1: W^T in data gradients, X^T / dY^T in weight gradients):
 //       row = tid % R, k groups (tid / R) * R/64 + c  -> 32 consecutive rows per scalar load.
-// Loading (op_load) and converting (op_store) are separate so that chunks are in flight while
-// earlier ones are converted, fenced and multiplied.
+// Loading and converting (OperandLoader::load / ::store) are separate so that a chunk is in flight
+// while the previous one is converted, fenced and multiplied.
 template <int R>
 struct OperandRegs {
   static constexpr int kPer = R / 64;
   float v[kPer][8];
 };
 
+// Per-thread addressing of one operand, computed once per kernel: everything inside the chunk loop is
+// pointer + chunk offset, and the bounds checks collapse to one CTA-uniform "chunk fully inside K" test.
 template <int R>
-__device__ __forceinline__ void op_load(OperandRegs<R> &o, const float *__restrict__ base, long long sr,
-                                        long long sk, int r0, int rmax, int k0, int K, int tid) {
-  constexpr int kPer = OperandRegs<R>::kPer;
-  if (sk == 1) {
-    const bool vec_ok = ((sr & 3) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
-    const int kk = k0 + (tid & 7) * 8;
+struct OperandLoader {
+  static constexpr int kPer = R / 64;
+  const float *p[kPer];     // element (row_c, k group_c, k = 0 of the chunk) of this thread
+  uint32_t soff[kPer];      // byte offset of its 16 B chunk inside a shared-memory tile
+  int kofs[kPer];           // first k of the group inside a chunk
+  bool ok[kPer];            // row inside the matrix
+  long long sk;
+  bool kmajor, vec;
+
+  __device__ __forceinline__ void init(const float *base, long long sr, long long sk_, int r0, int rmax, int tid) {
+    sk = sk_;
+    kmajor = sk_ == 1;
+    vec = kmajor && ((sr & 3) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+    constexpr uint32_t kLbo = lbo_padded(R);
 #pragma unroll
     for (int c = 0; c < kPer; ++c) {
-      const int row = (tid >> 3) + 64 * c;
-      const bool row_ok = (r0 + row) < rmax;
-      const float *rp = base + (long long)(r0 + row) * sr + kk;
-      if (row_ok && vec_ok && kk + 8 <= K) {
-        const float4 a = *reinterpret_cast<const float4 *>(rp);
-        const float4 b = *reinterpret_cast<const float4 *>(rp + 4);
-        o.v[c][0] = a.x; o.v[c][1] = a.y; o.v[c][2] = a.z; o.v[c][3] = a.w;
-        o.v[c][4] = b.x; o.v[c][5] = b.y; o.v[c][6] = b.z; o.v[c][7] = b.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o.v[c][j] = (row_ok && kk + j < K) ? rp[j] : 0.f;
-      }
-    }
-  } else {
-    const int row = tid % R, part = tid / R;
-    const bool row_ok = (r0 + row) < rmax;
-    const float *rp = base + (long long)(r0 + row) * sr;
-#pragma unroll
-    for (int c = 0; c < kPer; ++c) {
-      const int kk = k0 + (part * kPer + c) * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o.v[c][j] = (row_ok && kk + j < K) ? rp[(long long)(kk + j) * sk] : 0.f;
+      const int row = kmajor ? (tid >> 3) + 64 * c : tid % R;
+      const int kg = kmajor ? (tid & 7) : (tid / R) * kPer + c;
+      ok[c] = (r0 + row) < rmax;
+      kofs[c] = kg * 8;
+      p[c] = base + (long long)(r0 + row) * sr + (long long)(kg * 8) * sk_;
+      soff[c] = (uint32_t)kg * kLbo + (uint32_t)row * 16u;
     }
   }
-}
 
-// split to bf16 and store in the canonical layout with padded K stride: tiles [h | m | l] are
-// `tile_bytes` apart; `kmajor` = the mapping op_load used (sk == 1)
-template <int R>
-__device__ __forceinline__ void op_store(const OperandRegs<R> &o, uint8_t *tiles, uint32_t tile_bytes,
-                                         bool three_way, bool kmajor, int tid) {
-  constexpr int kPer = OperandRegs<R>::kPer;
-  constexpr uint32_t kLbo = lbo_padded(R);
+  // chunk starting at k0; `inside` = k0 + 64 <= K (uniform)
+  __device__ __forceinline__ void load(OperandRegs<R> &o, int k0, int K) const {
+    const bool inside = k0 + kChunkK <= K;
+    if (kmajor) {
 #pragma unroll
-  for (int c = 0; c < kPer; ++c) {
-    uint32_t h[4], m[4], l[4];
-    const uint32_t off = kmajor ? (uint32_t)(tid & 7) * kLbo + (uint32_t)((tid >> 3) + 64 * c) * 16u
-                                : (uint32_t)((tid / R) * kPer + c) * kLbo + (uint32_t)(tid % R) * 16u;
-    if (three_way) {
+      for (int c = 0; c < kPer; ++c) {
+        const float *q = p[c] + k0;
+        if (ok[c] && vec && inside) {
+          const float4 a = *reinterpret_cast<const float4 *>(q);
+          const float4 b = *reinterpret_cast<const float4 *>(q + 4);
+          o.v[c][0] = a.x; o.v[c][1] = a.y; o.v[c][2] = a.z; o.v[c][3] = a.w;
+          o.v[c][4] = b.x; o.v[c][5] = b.y; o.v[c][6] = b.z; o.v[c][7] = b.w;
+        } else {
+          const int kk = k0 + kofs[c];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) split_pack2_3way(o.v[c][2 * j], o.v[c][2 * j + 1], h[j], m[j], l[j]);
-      *reinterpret_cast<uint4 *>(tiles + 2 * tile_bytes + off) = make_uint4(l[0], l[1], l[2], l[3]);
+          for (int j = 0; j < 8; ++j) o.v[c][j] = (ok[c] && kk + j < K) ? q[j] : 0.f;
+        }
+      }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) split_pack2(o.v[c][2 * j], o.v[c][2 * j + 1], h[j], m[j]);
+      for (int c = 0; c < kPer; ++c) {
+        const float *q = p[c] + (long long)k0 * sk;
+        if (ok[c] && inside) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o.v[c][j] = q[(long long)j * sk];
+        } else {
+          const int kk = k0 + kofs[c];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o.v[c][j] = (ok[c] && kk + j < K) ? q[(long long)j * sk] : 0.f;
+        }
+      }
     }
-    *reinterpret_cast<uint4 *>(tiles + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4 *>(tiles + tile_bytes + off) = make_uint4(m[0], m[1], m[2], m[3]);
   }
-}
+
+  // split to bf16 and store in the canonical layout with padded K stride: tiles [h | m | l] are
+  // `tile_bytes` apart
+  __device__ __forceinline__ void store(const OperandRegs<R> &o, uint8_t *tiles, uint32_t tile_bytes,
+                                        bool three_way) const {
+#pragma unroll
+    for (int c = 0; c < kPer; ++c) {
+      uint32_t h[4], m[4], l[4];
+      if (three_way) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_pack2_3way(o.v[c][2 * j], o.v[c][2 * j + 1], h[j], m[j], l[j]);
+        *reinterpret_cast<uint4 *>(tiles + 2 * tile_bytes + soff[c]) = make_uint4(l[0], l[1], l[2], l[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_pack2(o.v[c][2 * j], o.v[c][2 * j + 1], h[j], m[j]);
+      }
+      *reinterpret_cast<uint4 *>(tiles + soff[c]) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4 *>(tiles + tile_bytes + soff[c]) = make_uint4(m[0], m[1], m[2], m[3]);
+    }
+  }
+};
 
 // 32 lanes x 16 columns of f32
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -229,24 +252,31 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
 // Four columns per step in a rolled loop: erf / exp are shared between gelu and its derivative and
 // one Philox block covers the four dropout decisions.  Requires N % 4 == 0 and 16 B aligned rows.
 template <int BN>
-__device__ __noinline__ void epilogue_ffn1(const GemmArgs &g, uint32_t tmem_d, int nt, int m0, int warp, int lane) {
+__device__ __noinline__ void epilogue_ffn1(const GemmArgs &g, uint32_t tmem_d, int nt, int m0, int warp, int lane,
+                                           uint64_t *done_bar, uint32_t done_parity) {
   const int q = warp & 3, h = warp >> 2;
   const int grow = m0 + q * 32 + lane;
   const bool row_ok = grow < g.M;
+  bool waited = false;
   // 16 columns per step (N % 16 == 0 is required by the launcher for this epilogue): all loads of a
   // step are issued together and the 16 independent erf/exp chains hide each other's latency
 #pragma unroll 1
   for (int c0 = h * (BN / 4); c0 < (h + 1) * (BN / 4); c0 += 16) {
     const int n0 = nt * BN + c0;
     if (n0 >= g.N) break;
-    uint32_t r[16];
-    tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
     float b[16];
     if (g.bias != nullptr) row_load16(g.bias + n0, true, 16, b);
     else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) b[j] = 0.f;
     }
+    if (!waited) {   // accumulator complete (the bias row of the first step is already in flight)
+      mbar_wait(done_bar, done_parity);
+      fence_after_sync();
+      waited = true;
+    }
+    uint32_t r[16];
+    tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
     tmem_ld_wait();
     if (!row_ok) continue;
     const long long off = (long long)grow * g.ldaux + n0;
@@ -276,7 +306,9 @@ __device__ __noinline__ void epilogue_ffn1(const GemmArgs &g, uint32_t tmem_d, i
 
 // Plain epilogue: tcgen05.ld -> bias -> act -> (* aux) -> (+ residual) -> (row-group max) -> store / += / red.add.
 template <int BN>
-__device__ __noinline__ void epilogue_plain(const GemmArgs &g, uint32_t tmem_d, int nt, int m0, int warp, int lane) {
+__device__ __noinline__ void epilogue_plain(const GemmArgs &g, uint32_t tmem_d, int nt, int m0, int warp, int lane,
+                                            uint64_t *done_bar, uint32_t done_parity) {
+  bool waited = false;
   // ---- epilogue: 16 columns per step; every global operand of the step is loaded up front
   // (vectorised) so nothing inside the element loops waits on memory or branches per element
   const int q = warp & 3, h = warp >> 2;
@@ -298,12 +330,17 @@ __device__ __noinline__ void epilogue_plain(const GemmArgs &g, uint32_t tmem_d, 
     if (n0 >= g.N) break;  // warp-uniform
     const int nv = min(16, g.N - n0);
     const bool full = nv == 16;
-    uint32_t r[16];
-    tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
     float bv[16], rv[16], av[16];
     if (use_bias) row_load16(g.bias + n0, full && bias_vec, nv, bv);
     if (use_res) row_load16(g.res + (long long)grow * g.ldr + n0, full && res_vec, nv, rv);
     if (use_aux) row_load16(g.aux + (long long)grow * g.ldaux + n0, full && aux_vec, nv, av);
+    if (!waited) {   // accumulator complete (the global operands of the first step are already in flight)
+      mbar_wait(done_bar, done_parity);
+      fence_after_sync();
+      waited = true;
+    }
+    uint32_t r[16];
+    tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
     tmem_ld_wait();
     float v[16];
 #pragma unroll
@@ -424,6 +461,20 @@ linear_tc_kernel(GemmArgs g) {
   }
   if (warp == kProducerWarps) tmem_alloc(&s_tmem, BN);
   pdl_sync();
+  // producers: first operand chunk in flight before the set-up barrier
+  OperandRegs<kTileM> ra;
+  OperandRegs<BN> rb;
+  OperandLoader<kTileM> la;
+  OperandLoader<BN> lb;
+  if (warp < kProducerWarps) {
+    if (FFN) g.drop.resolve();
+    la.init(g.A, g.sam, g.sak, m0, g.M, tid);
+    la.load(ra, kc_begin * kChunkK, g.K);
+    if (g.b_mode == 1) {
+      lb.init(g.Bf, g.sbn, g.sbk, nt * BN, g.N, tid);
+      lb.load(rb, kc_begin * kChunkK, g.K);
+    }
+  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -478,19 +529,10 @@ linear_tc_kernel(GemmArgs g) {
     }
   } else {
     // ------------------------------------------------------------------ producers, then epilogue
-    g.drop.resolve();
     // One chunk is prefetched into registers while the previous one is converted; the 16 producer
     // warps hide the rest of the latency (with 8 warps the SM issued 0.27 instructions per cycle per
     // scheduler: the conversion is ~500 dependent-ish instructions per warp per chunk).
-    OperandRegs<kTileM> ra;
-    OperandRegs<BN> rb;
-    auto load_chunk = [&](int kc) {
-      op_load<kTileM>(ra, g.A, g.sam, g.sak, m0, g.M, kc * kChunkK, g.K, tid);
-      if (g.b_mode == 1) op_load<BN>(rb, g.Bf, g.sbn, g.sbk, nt * BN, g.N, kc * kChunkK, g.K, tid);
-    };
-    load_chunk(kc_begin);
     const bool three_way = g.split == 6;
-    const bool a_kmajor = g.sak == 1, b_kmajor = g.sbk == 1;
 #pragma unroll 1
     for (int i = 0; i < nkc; ++i) {
       const int kc = kc_begin + i;
@@ -503,21 +545,24 @@ linear_tc_kernel(GemmArgs g) {
           bulk_g2s(st + kBOff, g.PW + ((size_t)nt * nkc_total + kc) * kBBlock, kBBlock, &b_full[s]);
         }
       } else {
-        op_store<BN>(rb, st + kBOff, kBTile, three_way, b_kmajor, tid);
+        lb.store(rb, st + kBOff, kBTile, three_way);
       }
-      op_store<kTileM>(ra, st + kAOff, kATile, three_way, a_kmajor, tid);
-      if (i + 1 < nkc) load_chunk(kc + 1);
+      la.store(ra, st + kAOff, kATile, three_way);
+      if (i + 1 < nkc) {
+        la.load(ra, (kc + 1) * kChunkK, g.K);
+        if (g.b_mode == 1) lb.load(rb, (kc + 1) * kChunkK, g.K);
+      }
       fence_async_smem();      // my generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
     }
-    {  // the last commit covers every MMA issued before it
-      const int last = nkc - 1;
-      mbar_wait(&mma_done[last & 1], (last >> 1) & 1);
-      fence_after_sync();
-    }
-    if (FFN && g.epi == EPI_FFN1) epilogue_ffn1<BN>(g, tmem_d, nt, m0, warp, lane);
-    else epilogue_plain<BN>(g, tmem_d, nt, m0, warp, lane);
+    // the last commit covers every MMA issued before it; the epilogues wait for it AFTER issuing the
+    // global loads of their first column step (bias / residual / aux rows)
+    const int last = nkc - 1;
+    uint64_t *done_bar = &mma_done[last & 1];
+    const uint32_t done_parity = (last >> 1) & 1;
+    if (FFN && g.epi == EPI_FFN1) epilogue_ffn1<BN>(g, tmem_d, nt, m0, warp, lane, done_bar, done_parity);
+    else epilogue_plain<BN>(g, tmem_d, nt, m0, warp, lane, done_bar, done_parity);
   }
   fence_before_sync();
   __syncthreads();

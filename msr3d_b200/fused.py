@@ -182,24 +182,41 @@ class FusedPrompter:
             w[k] = f(M, H)
         for k in ("rstd_l", "rstd_s"):
             w[k] = f(M)
-        w["x_in"] = [f(M, H) for _ in range(nl)]
-        w["qkvc"] = [f(M, QKVC) for _ in range(nl)]
+        # split-K GEMM outputs (accumulated with red.add): carved out of two arenas that are zeroed with
+        # one memset each per step (forward: x_in[0], qkvc, o, f of every layer; backward: dctx)
+        n_f = M * H + nl * (M * QKVC + 2 * M * H)
+        w["arena_f"] = f(n_f)
+        w["arena_b"] = f(nl * M * H)
+        cur = [0]
+
+        def carve(arena, *shape):
+            n = 1
+            for d in shape:
+                n *= d
+            t = arena[cur[0]:cur[0] + n].view(*shape)
+            cur[0] += n
+            return t
+        w["x_in"] = [carve(w["arena_f"], M, H)] + [f(M, H) for _ in range(nl - 1)]
+        w["qkvc"] = [carve(w["arena_f"], M, QKVC) for _ in range(nl)]
+        w["o"] = [carve(w["arena_f"], M, H) for _ in range(nl)]
+        w["f"] = [carve(w["arena_f"], M, H) for _ in range(nl)]
+        assert cur[0] == n_f
+        cur[0] = 0
+        w["dctx"] = [carve(w["arena_b"], M, H) for _ in range(nl)]
         w["P"] = [f(B, NHEAD, L, L) for _ in range(nl)]
         w["LOC"] = [f(B, NHEAD, L, L) for _ in range(nl)]
         w["ctx"] = [f(M, H) for _ in range(nl)]
-        w["o"] = f(M, H)
         for k in ("xhat_a", "xhat_1", "xhat_2", "y2"):
             w[k] = [f(M, H) for _ in range(nl)]
         for k in ("rstd_a", "rstd_1", "rstd_2"):
             w[k] = [f(M) for _ in range(nl)]
         w["h"] = [f(M, F) for _ in range(nl)]     # dropout(gelu(u))
         w["gp"] = [f(M, F) for _ in range(nl)]    # gelu'(u) * dropout mask
-        w["f"] = f(M, H)
         w["tokens"] = f(M, H)
         # backward
         # per-layer copies of everything a weight-gradient GEMM reads: those GEMMs run on a side
         # stream, off the critical path, while the main stream moves on to the next layer
-        w["dy2"], w["dctx"], w["dh1"] = f(M, H), f(M, H), f(M, H)
+        w["dy2"], w["dh1"] = f(M, H), f(M, H)
         w["df"] = [f(M, H) for _ in range(nl)]
         w["do"] = [f(M, H) for _ in range(nl)]
         w["du"] = [f(M, F) for _ in range(nl)]
@@ -252,6 +269,9 @@ class FusedPrompter:
         bwd: List = []
         # ---------------- forward.  geometry -> loc_fc -> qpos depend only on the inputs: side stream,
         # concurrent with the PointNet++ encoder on the main stream
+        # split-K factors: tools/gemm_sweep.py (one 64-wide K chunk per CTA wherever the epilogue is linear)
+        ks_h = max(1, -(-H // 64))
+        pre_prog.append(("memset", None, (w["arena_f"],), None, False))
         self._call(pre_prog, "msr3d_spatial_geometry_f32", ptr(w["obj_locs"]), ptr(w["anchor_locs"]), ptr(w["anchor_ori"]),
                    B, L, self.dist_norm, 1, ptr(w["pw"]), ptr(w["ff"]), ptr(w["sz"]), tag="geometry", side=True)
         self._gemm(pre_prog, ptr(w["ff"]), (64, 1), P("loc_embedding_encoder.0.weight"), (63, 1), M, H, 63, ptr(w["h1"]), H,
@@ -265,19 +285,20 @@ class FusedPrompter:
         fwd.append(("join", None, (), None, False))
         E = self.emb_dim
         self._gemm(fwd, self.emb_ptr, (E, 1), P("obj_linear_projection.weight"), (E, 1), M, H, E, ptr(w["x_in"][0]), H,
-                   bias=P("obj_linear_projection.bias"), residual=ptr(w["qpos0"]), ldr=H, tag="obj_proj")
+                   bias=P("obj_linear_projection.bias"), residual=ptr(w["qpos0"]), ldr=H, accumulate=2,
+                   ksplit=max(1, -(-E // 64)), tag="obj_proj")
         for i in range(nl):
             pre = f"spatial_encoder.{i}."
             sa = pre + "self_attn."
             s0 = i * 8
             x_in = ptr(w["x_in"][i])
             self._gemm(fwd, x_in, (H, 1), P(sa + "w_qs.weight"), (H, 1), M, QKVC, H, ptr(w["qkvc"][i]), QKVC,
-                       bias=P(sa + "w_qs.bias"), tag="qkvc")
+                       bias=P(sa + "w_qs.bias"), accumulate=2, ksplit=ks_h, tag="qkvc")
             self._call(fwd, "msr3d_attn_fwd_f32", ptr(w["qkvc"][i]), QKVC, ptr(w["pw"]), ptr(w["key_pad"]), B, L, NHEAD,
                        ptr(w["P"][i]), ptr(w["LOC"][i]), ptr(w["ctx"][i]), H, tag="attn_core")
-            self._gemm(fwd, ptr(w["ctx"][i]), (H, 1), P(sa + "fc.weight"), (H, 1), M, H, H, ptr(w["o"]), H,
-                       bias=P(sa + "fc.bias"), tag="out_proj")
-            self._call(fwd, "msr3d_attn_tail_fwd_f32", ptr(w["o"]), x_in, M, P(sa + "layer_norm.weight"),
+            self._gemm(fwd, ptr(w["ctx"][i]), (H, 1), P(sa + "fc.weight"), (H, 1), M, H, H, ptr(w["o"][i]), H,
+                       bias=P(sa + "fc.bias"), accumulate=2, ksplit=ks_h, tag="out_proj")
+            self._call(fwd, "msr3d_attn_tail_fwd_f32", ptr(w["o"][i]), x_in, M, P(sa + "layer_norm.weight"),
                        P(sa + "layer_norm.bias"), P(pre + "norm1.weight"), P(pre + "norm1.bias"), seed, sptr, p,
                        s0 + 0, s0 + 1, ptr(w["xhat_a"][i]), ptr(w["rstd_a"][i]), ptr(w["xhat_1"][i]),
                        ptr(w["rstd_1"][i]), ptr(w["y2"][i]), tag="attn_tail")
@@ -285,17 +306,17 @@ class FusedPrompter:
             self._gemm(fwd, ptr(w["y2"][i]), (H, 1), P(pre + "linear1.weight"), (H, 1), M, F, H, ptr(w["h"][i]), F,
                        bias=P(pre + "linear1.bias"), epilogue=2, aux_out=ptr(w["gp"][i]), ldaux=F,
                        epi_site=s0 + 2, tag="ffn1")
-            fwd.append(("memset", None, (w["f"],), None, False))
-            self._gemm(fwd, ptr(w["h"][i]), (F, 1), P(pre + "linear2.weight"), (F, 1), M, H, F, ptr(w["f"]), H,
-                       bias=P(pre + "linear2.bias"), accumulate=2, ksplit=8, tag="ffn2")
+            self._gemm(fwd, ptr(w["h"][i]), (F, 1), P(pre + "linear2.weight"), (F, 1), M, H, F, ptr(w["f"][i]), H,
+                       bias=P(pre + "linear2.bias"), accumulate=2, ksplit=16, tag="ffn2")
             last = i == nl - 1
             add = 0 if (last or not self.same_all) else ptr(w["qpos"])
-            self._call(fwd, "msr3d_ffn_tail_fwd_f32", ptr(w["f"]), ptr(w["y2"][i]), M, P(pre + "norm2.weight"),
+            self._call(fwd, "msr3d_ffn_tail_fwd_f32", ptr(w["f"][i]), ptr(w["y2"][i]), M, P(pre + "norm2.weight"),
                        P(pre + "norm2.bias"), seed, sptr, p, s0 + 3, add or None, ptr(w["xhat_2"][i]),
                        ptr(w["rstd_2"][i]), ptr(w["tokens"]) if last else None,
                        None if last else ptr(w["x_in"][i + 1]), tag="ffn_tail")
         # ---------------- backward (gradients accumulate into the flat buffer)
         dy3 = ptr(w["upstream"])
+        bwd.append(("memset", None, (w["arena_b"],), None, False))
         for i in reversed(range(nl)):
             pre = f"spatial_encoder.{i}."
             sa = pre + "self_attn."
@@ -307,18 +328,18 @@ class FusedPrompter:
                        G(pre + "norm2.bias"), G(pre + "linear2.bias"), tag="ffn_tail_bwd")
             # dW2 (H x F) += df^T . h                                   [side stream]
             self._gemm(bwd, df, (1, H), ptr(w["h"][i]), (1, F), H, F, M, G(pre + "linear2.weight"), F,
-                       accumulate=1, tag="dW2", wgrad=True, side=True)
+                       accumulate=2, ksplit=2, tag="dW2", wgrad=True, side=True)
             # du = (df . W2) * gelu'(u) * mask
             self._gemm(bwd, df, (H, 1), P(pre + "linear2.weight"), (1, F), M, F, H, du, F,
                        epilogue=3, aux=ptr(w["gp"][i]), ldaux=F, tag="du")
             # dW1 (F x H) += du^T . y2 ; db1                            [side stream]
             self._gemm(bwd, du, (1, F), ptr(w["y2"][i]), (1, H), F, H, M, G(pre + "linear1.weight"), H,
-                       accumulate=1, tag="dW1", wgrad=True, side=True)
+                       accumulate=2, ksplit=2, tag="dW1", wgrad=True, side=True)
             self._call(bwd, "msr3d_colsum_add_f32", du, F, M, F, G(pre + "linear1.bias"), None, None, tag="db1",
                        side=True)
             # dy2 += du . W1
             self._gemm(bwd, du, (F, 1), P(pre + "linear1.weight"), (1, H), M, H, F, ptr(w["dy2"]), H,
-                       accumulate=2, ksplit=8, tag="dy2")
+                       accumulate=2, ksplit=16, tag="dy2")
             self._call(bwd, "msr3d_attn_tail_bwd_f32", ptr(w["dy2"]), M, P(sa + "layer_norm.weight"),
                        P(pre + "norm1.weight"), seed, sptr, p, s0 + 0, s0 + 1, ptr(w["xhat_a"][i]),
                        ptr(w["rstd_a"][i]), ptr(w["xhat_1"][i]), ptr(w["rstd_1"][i]), dx, do_,
@@ -326,17 +347,18 @@ class FusedPrompter:
                        G(pre + "norm1.bias"), G(sa + "fc.bias"), tag="attn_tail_bwd")
             # dWo (H x H) += do^T . ctx [side] ;  dctx = do . Wo
             self._gemm(bwd, do_, (1, H), ptr(w["ctx"][i]), (1, H), H, H, M, G(sa + "fc.weight"), H,
-                       accumulate=1, tag="dWo", wgrad=True, side=True)
-            self._gemm(bwd, do_, (H, 1), P(sa + "fc.weight"), (1, H), M, H, H, ptr(w["dctx"]), H, tag="dctx")
-            self._call(bwd, "msr3d_attn_bwd_f32", ptr(w["dctx"]), H, ptr(w["qkvc"][i]), QKVC, ptr(w["pw"]),
+                       accumulate=2, ksplit=4, tag="dWo", wgrad=True, side=True)
+            self._gemm(bwd, do_, (H, 1), P(sa + "fc.weight"), (1, H), M, H, H, ptr(w["dctx"][i]), H,
+                       accumulate=2, ksplit=ks_h, tag="dctx")
+            self._call(bwd, "msr3d_attn_bwd_f32", ptr(w["dctx"][i]), H, ptr(w["qkvc"][i]), QKVC, ptr(w["pw"]),
                        ptr(w["P"][i]), ptr(w["LOC"][i]), B, L, NHEAD, dqkvc, tag="attn_core_bwd")
             # dWqkvc (816 x H) += dqkvc^T . x_in ; bias [side] ; dx += dqkvc . Wqkvc
             self._gemm(bwd, dqkvc, (1, QKVC), ptr(w["x_in"][i]), (1, H), QKVC, H, M, G(sa + "w_qs.weight"), H,
-                       accumulate=1, tag="dWqkvc", wgrad=True, side=True)
+                       accumulate=2, ksplit=4, tag="dWqkvc", wgrad=True, side=True)
             self._call(bwd, "msr3d_colsum_add_f32", dqkvc, QKVC, M, QKVC, G(sa + "w_qs.bias"), None, None,
                        tag="dbqkvc", side=True)
             self._gemm(bwd, dqkvc, (QKVC, 1), P(sa + "w_qs.weight"), (1, H), M, H, QKVC, dx, H,
-                       accumulate=2, ksplit=4, tag="dx")
+                       accumulate=2, ksplit=max(1, -(-QKVC // 64)), tag="dx")
             dy3 = dx
         dx0 = ptr(w["dx"][0])
         # x_in0 = emb Wp^T + bp + orientation_feat + type_emb[0] + qpos
@@ -344,7 +366,7 @@ class FusedPrompter:
                    G("object_orientation_feat"), G("object_type_embedding.weight"), tag="dbias_proj", side=True)
         E = self.emb_dim
         self._gemm(bwd, dx0, (1, H), self.emb_ptr, (1, E), H, E, M, G("obj_linear_projection.weight"), E,
-                   accumulate=1, tag="dWproj", wgrad=True, side=True)
+                   accumulate=2, ksplit=4, tag="dWproj", wgrad=True, side=True)
         dq = [ptr(w["dx"][i]) for i in range(nl)] if self.same_all else [dx0]
         dq += [None] * (3 - len(dq))
         assert len(dq) == 3, "fused qpos backward sums at most three layers"
