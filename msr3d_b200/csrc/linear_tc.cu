@@ -649,7 +649,11 @@ MSR3D_API int msr3d_linear_tc_f32(const float *A, long long stride_am, long long
   g.A = A; g.sam = stride_am; g.sak = stride_ak; g.PW = (const uint8_t *)packed_w; g.b_mode = 0;
   g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo; g.act = act; g.pool = pool;
   g.split = split; g.accumulate = accumulate ? 1 : 0; g.drop = make_dropout(0, 0.f);
-  return launch_gemm(g, 1, (cudaStream_t)stream);
+  // NOTE: no split-K here although the encoder's final fc (240 x 768 x 768) runs on 12 CTAs: split-K
+  // accumulates with red.add, and the frozen encoder is required to be run-to-run bit-identical
+  // (tests/test_prompter_gpu.py); measured cost of keeping it deterministic: ~10 us per step.
+  const int ksplit = 1;
+  return launch_gemm(g, ksplit, (cudaStream_t)stream);
 }
 
 MSR3D_API int msr3d_gemm_tc_f32(const msr3d_gemm_desc *d, msr3d_stream_t stream) {

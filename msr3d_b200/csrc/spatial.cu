@@ -30,51 +30,65 @@ __device__ __forceinline__ float warp_max(float v) {
 // Geometry: pairwise relative locations (calc_pairwise_locs, 'center', spatial_dim 5,
 // modules/utils.py:88-137) and Fourier features of agent-frame centres
 // (transform_to_agent_coor :60-82 + generate_fourier_features, ose3d_situation.py:31-59).
-// One CTA per scene, one thread per object.
+// grid (scene, row block): every CTA recomputes the scene's maximum pairwise distance (L*L/256
+// evaluations per thread — cheaper than a second launch), then one thread per (row, key) pair of
+// its row block writes the 5 pairwise features and one thread per (row, feature) the Fourier block.
+// The first version used one CTA per scene and one thread per row (50 us for 4 scenes, a serial
+// loop over the keys and 30 serial sincosf per thread).
 //   loc   (B, L, 6)   centre xyz + size whl
 //   anchor(B, 3), quat (B, 4) (x,y,z,w); use_agent_frame = 0 -> features of the raw centres
 //   pw    (B, L, L, 5), ff (B*L, 64) [p'(3) | sin(pi p'_d f_j) d-major (30) | cos (30) | 0], sz (B*L, 3)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMaxL)
+constexpr int kGeoThreads = 256;
+constexpr int kGeoRows = 8;    // rows of the pairwise matrix per CTA
+
+__global__ void __launch_bounds__(kGeoThreads)
 geometry_kernel(const float *__restrict__ loc, const float *__restrict__ anchor,
                 const float *__restrict__ quat, int L, int dist_norm, int use_agent_frame,
                 float *__restrict__ pw, float *__restrict__ ff, float *__restrict__ sz) {
   pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   __shared__ float cx[kMaxL], cy[kMaxL], cz[kMaxL];
-  __shared__ float s_red[kMaxL / 32];
-  const int b = blockIdx.x, l = threadIdx.x;
+  __shared__ float s_red[kGeoThreads / 32];
+  const int b = blockIdx.x, tid = threadIdx.x;
   const float eps = 1e-10f;
-  if (l < L) {
+  for (int l = tid; l < L; l += kGeoThreads) {
     const float *p = loc + ((size_t)b * L + l) * 6;
     cx[l] = p[0]; cy[l] = p[1]; cz[l] = p[2];
   }
   __syncthreads();
-  float mymax = 0.f;
-  if (l < L) {
-    for (int t = 0; t < L; ++t) {
+  float gmax = 1.f;
+  if (dist_norm) {
+    float mymax = 0.f;
+    for (int i = tid; i < L * L; i += kGeoThreads) {
+      const int l = i / L, t = i - l * L;
       const float dx = cx[l] - cx[t], dy = cy[l] - cy[t], dz = cz[l] - cz[t];
       mymax = fmaxf(mymax, sqrtf((dx * dx + dy * dy) + dz * dz + eps));
     }
+    mymax = warp_max(mymax);
+    if ((tid & 31) == 0) s_red[tid >> 5] = mymax;
+    __syncthreads();
+    gmax = 0.f;
+#pragma unroll
+    for (int w = 0; w < kGeoThreads / 32; ++w) gmax = fmaxf(gmax, s_red[w]);
   }
-  mymax = warp_max(mymax);
-  if ((l & 31) == 0) s_red[l >> 5] = mymax;
-  __syncthreads();
-  float gmax = 0.f;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) gmax = fmaxf(gmax, s_red[w]);
-  if (l < L) {
-    const float inv = dist_norm ? 1.f / gmax : 1.f;
-    for (int t = 0; t < L; ++t) {
-      const float dx = cx[l] - cx[t], dy = cy[l] - cy[t], dz = cz[l] - cz[t];
-      const float d = sqrtf((dx * dx + dy * dy) + dz * dz + eps);
-      const float d2 = sqrtf(dx * dx + dy * dy + eps);
-      float *o = pw + (((size_t)b * L + l) * L + t) * 5;
-      o[0] = dist_norm ? d / gmax : d;
-      o[1] = dz / d;
-      o[2] = d2 / d;
-      o[3] = dy / d2;
-      o[4] = dx / d2;
-      (void)inv;
-    }
+  const int l0 = blockIdx.y * kGeoRows;
+  const int nrows = min(kGeoRows, L - l0);
+  for (int i = tid; i < nrows * L; i += kGeoThreads) {
+    const int l = l0 + i / L, t = i % L;
+    const float dx = cx[l] - cx[t], dy = cy[l] - cy[t], dz = cz[l] - cz[t];
+    const float d = sqrtf((dx * dx + dy * dy) + dz * dz + eps);
+    const float d2 = sqrtf(dx * dx + dy * dy + eps);
+    float *o = pw + (((size_t)b * L + l) * L + t) * 5;
+    o[0] = dist_norm ? d / gmax : d;
+    o[1] = dz / d;
+    o[2] = d2 / d;
+    o[3] = dy / d2;
+    o[4] = dx / d2;
+  }
+  // Fourier block: one thread per (row, slot) with slot = 0..31: slots 0..29 -> (sin, cos) pair e,
+  // slot 30 -> the three raw coordinates + zero pad, slot 31 -> the size triple
+  for (int i = tid; i < nrows * 32; i += kGeoThreads) {
+    const int l = l0 + (i >> 5), e = i & 31;
     // agent frame: p' = (p - anchor) R, R from the conjugate quaternion
     float px = cx[l], py = cy[l], pz = cz[l];
     if (use_agent_frame) {
@@ -92,12 +106,9 @@ geometry_kernel(const float *__restrict__ loc, const float *__restrict__ anchor,
       pz = (ux * r02 + uy * r12) + uz * r22;
     }
     float *f = ff + ((size_t)b * L + l) * 64;
-    f[0] = px; f[1] = py; f[2] = pz;
-    const float kPi = 3.14159265358979323846f;
-    // rolled on purpose: sincosf's slow-path range reduction is large, and this kernel runs once
-#pragma unroll 1
-    for (int e = 0; e < 30; ++e) {
+    if (e < 30) {
       const int d = e / 10, j = e % 10;
+      const float kPi = 3.14159265358979323846f;
       // torch.linspace(1, 15, 10): start + j*step below the midpoint, end - (9-j)*step above
       const float step = 14.f / 9.f;
       const float fr = j < 5 ? 1.f + j * step : 15.f - (9 - j) * step;
@@ -106,11 +117,14 @@ geometry_kernel(const float *__restrict__ loc, const float *__restrict__ anchor,
       sincosf(arg, &sn, &cs);
       f[3 + e] = sn;
       f[33 + e] = cs;
+    } else if (e == 30) {
+      f[0] = px; f[1] = py; f[2] = pz;
+      f[63] = 0.f;
+    } else {
+      const float *p = loc + ((size_t)b * L + l) * 6;
+      float *sp = sz + ((size_t)b * L + l) * 3;
+      sp[0] = p[3]; sp[1] = p[4]; sp[2] = p[5];
     }
-    f[63] = 0.f;
-    const float *p = loc + ((size_t)b * L + l) * 6;
-    float *s = sz + ((size_t)b * L + l) * 3;
-    s[0] = p[3]; s[1] = p[4]; s[2] = p[5];
   }
 }
 
@@ -731,7 +745,7 @@ MSR3D_API int msr3d_spatial_geometry_f32(const float *loc, const float *anchor, 
   MSR3D_REQUIRE(!use_agent_frame || (anchor && quat), "geometry: agent frame needs anchor + quaternion");
   MSR3D_REQUIRE(B >= 0 && L >= 1 && L <= kMaxL, "geometry: L=%d must be in [1,%d]", L, kMaxL);
   if (B == 0) return MSR3D_OK;
-  launch_pdl(geometry_kernel, dim3(B), dim3(kMaxL), 0, (cudaStream_t)stream, loc, anchor, quat, L, dist_norm,
+  launch_pdl(geometry_kernel, dim3(B, ceil_div(L, kGeoRows)), dim3(kGeoThreads), 0, (cudaStream_t)stream, loc, anchor, quat, L, dist_norm,
                                                         use_agent_frame, pw, ff, sz);
   return check_launch("geometry");
 }

@@ -126,9 +126,11 @@ class FusedPrompter:
         self._keep = []          # ctypes descriptors must outlive the program
         self.graph = None
         self.side_stream = torch.cuda.Stream(device=dev)
+        self.side_stream2 = torch.cuda.Stream(device=dev)
+        self.hi_stream = torch.cuda.Stream(device=dev, priority=-1)
         self.enc_stream = torch.cuda.Stream(device=dev)
         self.use_side = True
-        self._side_pending = False
+        self._side_pending = [False, False]
 
     # ------------------------------------------------------------------ parameters
     def _rehome(self):
@@ -334,9 +336,9 @@ class FusedPrompter:
                        epilogue=3, aux=ptr(w["gp"][i]), ldaux=F, tag="du")
             # dW1 (F x H) += du^T . y2 ; db1                            [side stream]
             self._gemm(bwd, du, (1, F), ptr(w["y2"][i]), (1, H), F, H, M, G(pre + "linear1.weight"), H,
-                       accumulate=2, ksplit=2, tag="dW1", wgrad=True, side=True)
+                       accumulate=2, ksplit=2, tag="dW1", wgrad=True, side=2)
             self._call(bwd, "msr3d_colsum_add_f32", du, F, M, F, G(pre + "linear1.bias"), None, None, tag="db1",
-                       side=True)
+                       side=2)
             # dy2 += du . W1
             self._gemm(bwd, du, (F, 1), P(pre + "linear1.weight"), (1, H), M, H, F, ptr(w["dy2"]), H,
                        accumulate=2, ksplit=16, tag="dy2")
@@ -354,9 +356,9 @@ class FusedPrompter:
                        ptr(w["P"][i]), ptr(w["LOC"][i]), B, L, NHEAD, dqkvc, tag="attn_core_bwd")
             # dWqkvc (816 x H) += dqkvc^T . x_in ; bias [side] ; dx += dqkvc . Wqkvc
             self._gemm(bwd, dqkvc, (1, QKVC), ptr(w["x_in"][i]), (1, H), QKVC, H, M, G(sa + "w_qs.weight"), H,
-                       accumulate=2, ksplit=4, tag="dWqkvc", wgrad=True, side=True)
+                       accumulate=2, ksplit=4, tag="dWqkvc", wgrad=True, side=2)
             self._call(bwd, "msr3d_colsum_add_f32", dqkvc, QKVC, M, QKVC, G(sa + "w_qs.bias"), None, None,
-                       tag="dbqkvc", side=True)
+                       tag="dbqkvc", side=2)
             self._gemm(bwd, dqkvc, (QKVC, 1), P(sa + "w_qs.weight"), (1, H), M, H, QKVC, dx, H,
                        accumulate=2, ksplit=max(1, -(-QKVC // 64)), tag="dx")
             dy3 = dx
@@ -382,25 +384,27 @@ class FusedPrompter:
         return pre_prog, fwd, bwd
 
     def _run(self, prog):
-        """Issue a launch list.  Entries flagged `side` go to the side stream after it has caught up
-        with the main stream (fork); a "join" entry (and the end of the list) makes the main stream
-        wait for the side stream.  Under CUDA-graph capture this becomes parallel graph branches."""
+        """Issue a launch list.  Entries flagged `side` (1 or 2) go to that side stream after it has
+        caught up with the main stream (fork); a "join" entry (and the end of the list) makes the main
+        stream wait for the side streams.  Under CUDA-graph capture this becomes parallel graph branches."""
         main = torch.cuda.current_stream()
-        side = self.side_stream
+        sides = (self.side_stream, self.side_stream2)
         timer = ops.TIMER
-        forked = False
         for name, fn, args, tag, on_side in prog:
             if name == "join":
-                if forked or self._side_pending:
-                    main.wait_stream(side)
-                    forked = self._side_pending = False
+                for k, side in enumerate(sides):
+                    if self._side_pending[k]:
+                        main.wait_stream(side)
+                        self._side_pending[k] = False
                 continue
             if fn is None:                  # memset of a workspace tensor
                 args[0].zero_()
                 continue
             if on_side and self.use_side:
+                k = int(on_side) - 1
+                side = sides[k]
                 side.wait_stream(main)
-                forked = self._side_pending = True
+                self._side_pending[k] = True
                 if timer is not None and tag:
                     with torch.cuda.stream(side), timer.range(tag):
                         rc = fn(*args, side.cuda_stream)
@@ -519,7 +523,10 @@ class FusedPrompter:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        # captured on a HIGH-priority stream: the transformer chain is latency bound (small grids, one
+        # after the other) while the overlapped encoder is throughput work on the default-priority
+        # stream — the block scheduler should hand freed SMs to the chain first
+        with torch.cuda.graph(g, stream=self.hi_stream, capture_error_mode="thread_local"):
             self._pipelined_body()
         self.graph_pipelined = g
         for dst, src in zip((self.flat_p, self.m, self.v, self.opt_state, self.seed_counter), saved):
