@@ -151,8 +151,33 @@ typedef struct msr3d_gemm_desc {
   float dropout_p;
   unsigned long long seed;
   const unsigned long long *seed_ptr; /* optional device counter added to seed (graph replays) */
+  /* ABI 2: scattered / typed output (plain store only).  row_map[m] = output row of GEMM row m
+   * (negative: row dropped), NULL = identity; out_dtype 0 f32, 1 f16, 2 bf16 (`out` then points
+   * to that type and ld_out counts its elements). */
+  const int32_t *row_map;
+  int out_dtype;
 } msr3d_gemm_desc;
 int msr3d_gemm_tc_f32(const msr3d_gemm_desc *desc, msr3d_stream_t stream);
+/* ------------------------------------------------------------------ group E
+ * Scene-token splice into the LLM input (the step right after the path):
+ * MSR3D.build_embeds, model/msr3d/msr3d.py:277-287 —
+ *     scene_embeds = llm_proj(obj_tokens).to(inputs_embeds.dtype)
+ *     inputs_embeds[where(input_ids == scene_sp_token)] = scene_embeds.reshape(-1, D)
+ *     attention_mask (-> bool) [same positions] = obj_masks
+ * The projection is msr3d_gemm_tc_f32 with row_map / out_dtype (rows land directly in the LLM input,
+ * fp16 / bf16 conversion in the epilogue); the two entry points below are the index side and the
+ * gather that starts the backward. */
+/* rows[k] = flat position b*T + t of the k-th placeholder in row-major order (torch.where order),
+ * k < max_rows; entries past the number found are -1; *count = number found (may exceed max_rows).
+ * mask_out (B*T bytes, bool) = (attention_mask != 0) with obj_masks[k] written at rows[k];
+ * attention_mask (int64) and obj_masks (bool bytes) may be NULL (mask_out untouched). */
+int msr3d_scene_rows_i64(const int64_t *input_ids, int B, int T, long long sp_token,
+                         const int64_t *attention_mask, const uint8_t *obj_masks, int32_t *rows,
+                         int max_rows, int32_t *count, uint8_t *mask_out, msr3d_stream_t stream);
+/* dY[m, 0:D] = float(d_embeds[rows[m], 0:D]) (zeros where rows[m] < 0): the slice of the LLM's input
+ * gradient that belongs to the scene tokens.  dtype 0 f32, 1 f16, 2 bf16; ld in elements. */
+int msr3d_splice_gather_grad(const void *d_embeds, int dtype, long long ld, const int32_t *rows, int M,
+                             int D, float *dY, msr3d_stream_t stream);
 /* FPS + centre gather + ball query of one SA level (pointnet2_modules.py:54-58,
  * pointnet2_utils.py:331).  xyz: (B,N,ld) records whose first 3 floats are the
  * coordinates.  Outputs fps_idx (B,m) i32, new_xyz (B,m,3), ball_idx (B,m,nsample) i32. */

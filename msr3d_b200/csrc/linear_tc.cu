@@ -98,6 +98,8 @@ struct GemmArgs {
   const float *aux; long long ldaux; unsigned epi_site;  // EPI_MUL_AUX: factor [M,N]; epi_site: dropout site of EPI_FFN1
   float *aux_out;                                        // EPI_FFN1: second output [M, ldaux]
   float *out; long long ldo;
+  const int32_t *row_map;                              // nullable: output row of GEMM row m (< 0: dropped)
+  int out_dtype;                                       // 0 f32, 1 f16, 2 bf16 (typed stores: plain store only)
   int act, pool, split, accumulate, epi;               // accumulate: 0 store, 1 +=, 2 atomicAdd
   Dropout drop;
 };
@@ -240,6 +242,42 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// 16 consecutive columns of one output row stored as f32 / f16 / bf16 (`dtype` 0 / 1 / 2); `o` is a
+// byte pointer to column 0 of the step.  16 B stores when the address allows.
+__device__ __forceinline__ void store16_typed(uint8_t *o, int dtype, int nv, const float (&v)[16]) {
+  if (dtype == 0) {
+    float *f = reinterpret_cast<float *>(o);
+    if (nv == 16 && (reinterpret_cast<uintptr_t>(f) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(f + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nv) f[j] = v[j];
+    }
+    return;
+  }
+  uint32_t w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (dtype == 1) {
+      const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      w[j] = *reinterpret_cast<const uint32_t *>(&h);
+    } else {
+      w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    }
+  }
+  if (nv == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+    *reinterpret_cast<uint4 *>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4 *>(o + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+  } else {
+    uint16_t *h = reinterpret_cast<uint16_t *>(o);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < nv) h[j] = (uint16_t)((j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu));
+  }
+}
+
 // 32 lanes x 4 columns of f32
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
@@ -373,6 +411,13 @@ __device__ __noinline__ void epilogue_plain(const GemmArgs &g, uint32_t tmem_d, 
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           if (j < nv) o[j] = v[j];
+      }
+    } else if (row_ok && (g.row_map != nullptr || g.out_dtype != 0)) {
+      // scattered / typed store (scene-token splice: rows of the LLM input, fp16 or bf16)
+      const long long orow = g.row_map != nullptr ? (long long)g.row_map[grow] : (long long)grow;
+      if (orow >= 0) {
+        const int esz = g.out_dtype == 0 ? 4 : 2;
+        store16_typed(reinterpret_cast<uint8_t *>(g.out) + (orow * g.ldo + n0) * esz, g.out_dtype, nv, v);
       }
     } else if (row_ok) {
       float *o = g.out + (long long)grow * g.ldo + n0;
@@ -673,6 +718,9 @@ MSR3D_API int msr3d_gemm_tc_f32(const msr3d_gemm_desc *d, msr3d_stream_t stream)
   MSR3D_REQUIRE(d->ksplit <= 1 || (d->accumulate == 2 && d->act == 0 && d->epilogue == 0),
                 "gemm_tc: split-K needs atomic accumulation (accumulate=2), act=0, plain epilogue");
   MSR3D_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, "gemm_tc: bad dropout p");
+  MSR3D_REQUIRE(d->out_dtype >= 0 && d->out_dtype <= 2, "gemm_tc: bad out_dtype %d", d->out_dtype);
+  MSR3D_REQUIRE((d->row_map == nullptr && d->out_dtype == 0) || (d->accumulate == 0 && d->ksplit <= 1 && d->epilogue != 2),
+                "gemm_tc: row_map / typed output need a plain store (no accumulate, no split-K, not epilogue 2)");
   if (d->M == 0) return MSR3D_OK;
   GemmArgs g{};
   g.A = d->A; g.sam = d->stride_am; g.sak = d->stride_ak;
@@ -681,6 +729,7 @@ MSR3D_API int msr3d_gemm_tc_f32(const msr3d_gemm_desc *d, msr3d_stream_t stream)
   g.M = d->M; g.N = d->N; g.K = d->K; g.bias = d->bias; g.res = d->residual; g.ldr = d->ld_residual;
   g.aux = d->aux; g.ldaux = d->ld_aux; g.epi_site = d->epi_site; g.out = d->out; g.ldo = d->ld_out;
   g.aux_out = d->aux_out;
+  g.row_map = d->row_map; g.out_dtype = d->out_dtype;
   g.act = d->act; g.pool = 0; g.split = d->split; g.accumulate = d->accumulate; g.epi = d->epilogue;
   g.drop = make_dropout(d->seed, d->dropout_p, d->seed_ptr);
   return launch_gemm(g, d->ksplit, (cudaStream_t)stream);

@@ -39,7 +39,8 @@ class GemmDesc(ctypes.Structure):
                 ("act", c_int), ("split", c_int), ("accumulate", c_int), ("epilogue", c_int), ("ksplit", c_int),
                 ("a_xform", c_int), ("b_xform", c_int),
                 ("a_site", c_uint), ("b_site", c_uint), ("epi_site", c_uint),
-                ("dropout_p", c_float), ("seed", c_ull), ("seed_ptr", c_vp)]
+                ("dropout_p", c_float), ("seed", c_ull), ("seed_ptr", c_vp),
+                ("row_map", c_vp), ("out_dtype", c_int)]
 
 
 _C.register_protos({
