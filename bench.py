@@ -152,6 +152,62 @@ def cpu_baseline(args):
             "sample": f"{n} full steps of {args.config} (B={B}) after 1 warm-up; oracle port: torch CPU fp32 + C/OpenMP pointnet2 ops"}
 
 
+def bench_splice(dev, B, L, flush, cores):
+    """SURVEY.md §8f-1 (the step after the path): llm_proj + fp16 scatter into the LLM input and its
+    backward, at config-2 shapes (T = 204 prompt positions, D = 4096).  Per-call CUDA-event times with
+    L2 flushed, and the oracle (torch CPU) timed beside it."""
+    from msr3d_b200 import splice
+    from oracle import modules_oracle as mo
+    T, D = 204, 4096
+    g = torch.Generator().manual_seed(7)
+    ids = torch.randint(0, 30000, (B, T), generator=g)
+    ids[:, 100:100 + L] = splice.SCENE_SP_TOKEN
+    am = torch.ones(B, T, dtype=torch.long)
+    tok = torch.randn(B, L, 256, generator=g)
+    masks = torch.ones(B, L, dtype=torch.bool)
+    W = torch.randn(D, 256, generator=g) * 0.02
+    bias = torch.zeros(D)
+    emb = (torch.randn(B, T, D, generator=g) * 0.02).half()
+    G = torch.randn(B, T, D, generator=g).half()
+    d = lambda t: t.to(dev)  # noqa: E731
+    ids_d, am_d, masks_d, G_d = d(ids), d(am), d(masks), d(G)
+    Wd, bd, tokd = (d(t).requires_grad_(True) for t in (W, bias, tok))
+    res = {}
+    for mode in ("fwd", "fwd+bwd"):
+        ts = []
+        for i in range(13):
+            e = d(emb)
+            for t in (Wd, bd, tokd):
+                t.grad = None
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out, _ = splice.splice_scene_tokens(e, am_d, ids_d, tokd, masks_d, Wd, bd, check=False)
+            if mode != "fwd":
+                out.backward(G_d)
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(a.elapsed_time(b) * 1e3)
+        res[mode + "_us"] = round(statistics.median(ts), 1)
+    # algorithmic bytes of the forward: tokens + weight + bias read, B*L rows of D halves written
+    fwd_bytes = B * L * 256 * 4 + D * 256 * 4 + D * 4 + B * L * D * 2
+    res["fwd_algorithmic_bytes"] = fwd_bytes
+    res["fwd_gbs"] = round(fwd_bytes / (res["fwd_us"] * 1e-6) / 1e9, 1)
+    res["note"] = ("eager launches through the autograd op (3 kernels forward, 4 backward), host launch gaps "
+                   "included; the GEMM in a graph chain is ~10 us (tools/gemm_sweep.py)")
+    torch.set_num_threads(cores)
+    Wc, bc, tc = (t.clone().requires_grad_(True) for t in (W, bias, tok))
+    t0 = time.perf_counter()
+    n = 5
+    for _ in range(n):
+        o, _ = mo.scene_splice(Wc, bc, emb.clone(), am, ids, tc, masks)
+        o.backward(G)
+    res["cpu_oracle_fwd+bwd_us"] = round((time.perf_counter() - t0) / n * 1e6, 1)
+    res["workload"] = f"B={B} T={T} L={L} D={D} fp16 embeddings"
+    return res
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -266,6 +322,8 @@ def main():
                            for k, v in table.items()}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
+        if world == 1:
+            line["next_rows"] = {"scene_splice (SURVEY 8f-1)": bench_splice(dev, B, O, flush, os.cpu_count() or 1)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -156,6 +156,7 @@ typedef struct msr3d_gemm_desc {
    * to that type and ld_out counts its elements). */
   const int32_t *row_map;
   int out_dtype;
+  int tile_n;   /* N tile: 0 = library heuristic, 64 or 128 (few large CTAs keep SMs free for a concurrent chain) */
 } msr3d_gemm_desc;
 int msr3d_gemm_tc_f32(const msr3d_gemm_desc *desc, msr3d_stream_t stream);
 /* ------------------------------------------------------------------ group E

@@ -100,6 +100,7 @@ struct GemmArgs {
   float *out; long long ldo;
   const int32_t *row_map;                              // nullable: output row of GEMM row m (< 0: dropped)
   int out_dtype;                                       // 0 f32, 1 f16, 2 bf16 (typed stores: plain store only)
+  int tile_n;                                          // 0 auto, 64, 128
   int act, pool, split, accumulate, epi;               // accumulate: 0 store, 1 +=, 2 atomicAdd
   Dropout drop;
 };
@@ -646,6 +647,7 @@ static int launch_gemm(GemmArgs &g, int ksplit, cudaStream_t stream) {
   if (g.b_mode == 1) {
     const int ctas128 = ceil_div(g.M, kTileM) * ceil_div(g.N, 128) * ksplit;
     if (2 * ctas128 <= kNumSMs) bn = 64;
+    if (g.tile_n == 64 || g.tile_n == 128) bn = g.tile_n;
     if (g_tune[TUNE_GEMM_BN] == 64 || g_tune[TUNE_GEMM_BN] == 128) bn = g_tune[TUNE_GEMM_BN];
   }
   return bn == 64 ? launch_gemm_bn<64>(g, ksplit, stream) : launch_gemm_bn<128>(g, ksplit, stream);
@@ -719,6 +721,7 @@ MSR3D_API int msr3d_gemm_tc_f32(const msr3d_gemm_desc *d, msr3d_stream_t stream)
                 "gemm_tc: split-K needs atomic accumulation (accumulate=2), act=0, plain epilogue");
   MSR3D_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, "gemm_tc: bad dropout p");
   MSR3D_REQUIRE(d->out_dtype >= 0 && d->out_dtype <= 2, "gemm_tc: bad out_dtype %d", d->out_dtype);
+  MSR3D_REQUIRE(d->tile_n == 0 || d->tile_n == 64 || d->tile_n == 128, "gemm_tc: tile_n must be 0, 64 or 128");
   MSR3D_REQUIRE((d->row_map == nullptr && d->out_dtype == 0) || (d->accumulate == 0 && d->ksplit <= 1 && d->epilogue != 2),
                 "gemm_tc: row_map / typed output need a plain store (no accumulate, no split-K, not epilogue 2)");
   if (d->M == 0) return MSR3D_OK;
@@ -729,7 +732,7 @@ MSR3D_API int msr3d_gemm_tc_f32(const msr3d_gemm_desc *d, msr3d_stream_t stream)
   g.M = d->M; g.N = d->N; g.K = d->K; g.bias = d->bias; g.res = d->residual; g.ldr = d->ld_residual;
   g.aux = d->aux; g.ldaux = d->ld_aux; g.epi_site = d->epi_site; g.out = d->out; g.ldo = d->ld_out;
   g.aux_out = d->aux_out;
-  g.row_map = d->row_map; g.out_dtype = d->out_dtype;
+  g.row_map = d->row_map; g.out_dtype = d->out_dtype; g.tile_n = d->tile_n;
   g.act = d->act; g.pool = 0; g.split = d->split; g.accumulate = d->accumulate; g.epi = d->epilogue;
   g.drop = make_dropout(d->seed, d->dropout_p, d->seed_ptr);
   return launch_gemm(g, d->ksplit, (cudaStream_t)stream);

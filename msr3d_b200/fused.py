@@ -40,7 +40,7 @@ class GemmDesc(ctypes.Structure):
                 ("a_xform", c_int), ("b_xform", c_int),
                 ("a_site", c_uint), ("b_site", c_uint), ("epi_site", c_uint),
                 ("dropout_p", c_float), ("seed", c_ull), ("seed_ptr", c_vp),
-                ("row_map", c_vp), ("out_dtype", c_int)]
+                ("row_map", c_vp), ("out_dtype", c_int), ("tile_n", c_int)]
 
 
 _C.register_protos({
@@ -131,6 +131,7 @@ class FusedPrompter:
         self.hi_stream = torch.cuda.Stream(device=dev, priority=-1)
         self.enc_stream = torch.cuda.Stream(device=dev)
         self.use_side = True
+        self.wgrad_small = True
         self._side_pending = [False, False]
 
     # ------------------------------------------------------------------ parameters
@@ -237,7 +238,7 @@ class FusedPrompter:
 
     def _gemm(self, prog, A, sa, Bm, sb, M, N, K, out, ldo, bias=0, residual=0, ldr=0, aux=0, ldaux=0,
               act=0, accumulate=0, epilogue=0, ksplit=1, a_xform=0, b_xform=0, a_site=0, b_site=0,
-              epi_site=0, tag=None, wgrad=False, aux_out=0, side=False):
+              epi_site=0, tag=None, wgrad=False, aux_out=0, side=False, tile_n=0):
         d = GemmDesc()
         d.A, d.stride_am, d.stride_ak = A, sa[0], sa[1]
         d.B, d.stride_bn, d.stride_bk = Bm, sb[0], sb[1]
@@ -245,6 +246,11 @@ class FusedPrompter:
         d.aux_out = aux_out or None
         d.out, d.ld_out, d.M, d.N, d.K = out, ldo, M, N, K
         d.act, d.accumulate, d.epilogue, d.ksplit = act, accumulate, epilogue, ksplit
+        d.tile_n = tile_n
+        if wgrad and side and self.wgrad_small:
+            # weight gradients run beside the critical chain: few large CTAs, no split-K, so that the
+            # chain's 100+-CTA GEMMs still find free SMs (each CTA of this kernel owns a whole SM)
+            d.tile_n, d.ksplit = 128, 1
         # weight gradients contract over tokens and cancel heavily: three-way split (fp32-grade)
         d.split = self.grad_split if wgrad else self.split
         d.a_xform, d.b_xform, d.a_site, d.b_site, d.epi_site = a_xform, b_xform, a_site, b_site, epi_site

@@ -113,6 +113,8 @@ def main():
         ("dW2     256x2048x240 (A^T,B^T)", H, F, M, dict(transposed_a=True, transposed_b=True, bias=False), [1, 2, 4]),
         ("dWqkvc  816x256x240 (A^T,B^T)", Q, H, M, dict(transposed_a=True, transposed_b=True, bias=False), [1, 2, 4]),
         ("obj_proj 240x256x768", M, H, 768, dict(), [1, 3, 6, 12]),
+        ("loc_fc  240x256x63", M, H, 63, dict(), [1]),
+        ("splice  240x4096x256", M, 4096, H, dict(), [1]),
     ]
     for split in (6,):
         for tag, m, n, k, kw, kss in shapes:

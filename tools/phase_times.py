@@ -58,8 +58,11 @@ phases = {
     "inputs+loss": lambda: (eng.load_inputs(batch, up), eng.loss()),
 }
 res = {}
-for use_side in (True, False):
-    eng.use_side = use_side
+for use_side, small in ((True, True), (True, False), (False, True)):
+    eng.use_side, eng.wgrad_small = use_side, small
+    eng._key = None
+    eng.prepare(B, O, P, training=True)          # rebuild the launch lists with the new policy
     for k, fn in phases.items():
-        res[f"{k}{'' if use_side else ' (no side stream)'}"] = round(timeit(graph_of(fn)), 1)
+        label = k + ("" if use_side else " (no side stream)") + ("" if small else " (wgrad split-K/64-wide)")
+        res[label] = round(timeit(graph_of(fn)), 1)
 print(json.dumps(res, indent=1))
