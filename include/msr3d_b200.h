@@ -121,7 +121,7 @@ int msr3d_pack_weight_f32(const float *W, int N, int K, long long stride_n, long
  * calls of pytorch_utils.py:157-188 and modules/layers/pointnet.py:53,63.    */
 int msr3d_linear_tc_f32(const float *A, long long stride_am, long long stride_ak, int M, int K,
                         const void *packed_w, const float *bias, float *out, long long ldo, int N,
-                        int act, int pool, int split, int accumulate, msr3d_stream_t stream);
+                        int act, int pool, int split, int accumulate, int tile_n, msr3d_stream_t stream);
 /* General tensor-core GEMM with fp32 (strided) operands on both sides:
  *   out[M,N] (+)= epilogue( act( A[M,K] * B[N,K]^T + bias ) ) + residual
  * Used by the spatial transformer's forward and backward (weights and their transposes are
@@ -269,6 +269,9 @@ int msr3d_adamw_clip_step_f32(float *params, const float *grads, float *exp_avg,
                               long long n, long long n_decay, float grad_scale, float *state,
                               unsigned int *ticket, unsigned long long *seed_counter,
                               msr3d_stream_t stream);
+/* out[0] = <a, b> over n floats (one CTA, fixed summation order): the scalar the training loop reads
+ * back (trainer/leo_trainer.py:196-201 logs the loss every step). */
+int msr3d_dot_f32(const float *a, const float *b, long long n, float *out, msr3d_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,17 @@ int g_pdl = [] {
 }();
 
 int g_tune[TUNE_COUNT] = {0};
+static int g_tune_env = [] {   // MSR3D_TUNE="id=value,id=value" (A/B experiments from the shell)
+  const char *e = getenv("MSR3D_TUNE");
+  while (e != nullptr && *e) {
+    int id = 0, v = 0, n = 0;
+    if (sscanf(e, "%d=%d%n", &id, &v, &n) == 2 && id >= 0 && id < TUNE_COUNT) g_tune[id] = v;
+    else break;
+    e += n;
+    if (*e == ',') ++e;
+  }
+  return 0;
+}();
 
 int set_error(int code, const char *fmt, ...) {
   va_list ap;

@@ -477,7 +477,8 @@ linear_tc_kernel(GemmArgs g) {
   constexpr uint32_t kBBlock = 2 * kBTileDense;      // h + m (packed image)
   // stage = A tiles [h | m | l] then B tiles [h | m | l]; the third tiles only exist for split 6
   constexpr uint32_t kAOff = 0, kBOff = 3 * kATile;
-  constexpr uint32_t kStage = 3 * kATile + 3 * kBTile;
+  // packed weights occupy two dense tiles, fp32 B operands up to three padded ones
+  const uint32_t kStage = 3 * kATile + (g.b_mode == 0 ? 2 * kBTileDense : 3 * kBTile);
   __shared__ __align__(8) uint64_t full[2];      // producers -> issuer (one arrival per producer warp)
   __shared__ __align__(8) uint64_t b_full[2];    // TMA bytes of the packed weights
   __shared__ __align__(8) uint64_t mma_done[2];  // tensor core -> producers / epilogue
@@ -505,7 +506,8 @@ linear_tc_kernel(GemmArgs g) {
     }
     fence_mbar_init();
   }
-  if (warp == kProducerWarps) tmem_alloc(&s_tmem, BN);
+  constexpr uint32_t kTmemCols = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);   // power of two >= BN
+  if (warp == kProducerWarps) tmem_alloc(&s_tmem, kTmemCols);
   pdl_sync();
   // producers: first operand chunk in flight before the set-up barrier
   OperandRegs<kTileM> ra;
@@ -612,18 +614,23 @@ linear_tc_kernel(GemmArgs g) {
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == kProducerWarps) tmem_dealloc(tmem_d, BN);
+  if (warp == kProducerWarps) tmem_dealloc(tmem_d, kTmemCols);
 }
 
 template <int BN>
 static int launch_gemm_bn(GemmArgs &g, int ksplit, cudaStream_t stream) {
-  const size_t smem = 2 * (3 * (size_t)tile_bytes_padded(kTileM, kChunkK) + 3 * (size_t)tile_bytes_padded(BN, kChunkK)) + 1024;
+  const size_t b_stage = g.b_mode == 0 ? 2 * (size_t)BN * kChunkK * 2 : 3 * (size_t)tile_bytes_padded(BN, kChunkK);
+  const size_t smem = 2 * (3 * (size_t)tile_bytes_padded(kTileM, kChunkK) + b_stage) + 1024;
+  constexpr size_t smem_max_all = 2 * (3 * (size_t)tile_bytes_padded(kTileM, kChunkK) + 3 * (size_t)tile_bytes_padded(BN, kChunkK)) + 1024;
+  constexpr size_t kDynLimit = 227 * 1024 - 2048;   // 227 KB per CTA minus this kernel's static shared memory
+  constexpr size_t smem_max = smem_max_all < kDynLimit ? smem_max_all : kDynLimit;   // BN = 192: packed B only
+  MSR3D_REQUIRE(smem <= smem_max, "linear_tc: tile %d needs %zu B of shared memory", BN, smem);
   static bool configured = false;
   if (!configured) {
     MSR3D_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
+                                    (int)smem_max));
     MSR3D_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
+                                    (int)smem_max));
     configured = true;
   }
   dim3 grid(ceil_div(g.M, kTileM), ceil_div(g.N, BN), ksplit);
@@ -644,6 +651,8 @@ static int launch_gemm(GemmArgs &g, int ksplit, cudaStream_t stream) {
   if (ksplit < 1) ksplit = 1;
   if (ksplit > nkc) ksplit = nkc;
   int bn = 128;
+  if (g.b_mode == 0 && g.tile_n == 192) return launch_gemm_bn<192>(g, ksplit, stream);   // image packed with BN = 192
+  if (g.b_mode == 0 && g.tile_n == 64) return launch_gemm_bn<64>(g, ksplit, stream);     // image packed with BN = 64
   if (g.b_mode == 1) {
     const int ctas128 = ceil_div(g.M, kTileM) * ceil_div(g.N, 128) * ksplit;
     if (2 * ctas128 <= kNumSMs) bn = 64;
@@ -683,7 +692,7 @@ MSR3D_API int msr3d_pack_weight_f32(const float *W, int N, int K, long long stri
 MSR3D_API int msr3d_linear_tc_f32(const float *A, long long stride_am, long long stride_ak, int M,
                                   int K, const void *packed_w, const float *bias, float *out,
                                   long long ldo, int N, int act, int pool, int split,
-                                  int accumulate, msr3d_stream_t stream) {
+                                  int accumulate, int tile_n, msr3d_stream_t stream) {
   MSR3D_REQUIRE(A && packed_w && out, "linear_tc: null pointer");
   MSR3D_REQUIRE(M >= 0 && K > 0 && N > 0, "linear_tc: bad sizes M=%d K=%d N=%d", M, K, N);
   MSR3D_REQUIRE(act >= 0 && act <= 2, "linear_tc: bad act %d", act);
@@ -696,6 +705,7 @@ MSR3D_API int msr3d_linear_tc_f32(const float *A, long long stride_am, long long
   g.A = A; g.sam = stride_am; g.sak = stride_ak; g.PW = (const uint8_t *)packed_w; g.b_mode = 0;
   g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo; g.act = act; g.pool = pool;
   g.split = split; g.accumulate = accumulate ? 1 : 0; g.drop = make_dropout(0, 0.f);
+  g.tile_n = tile_n;
   // NOTE: no split-K here although the encoder's final fc (240 x 768 x 768) runs on 12 CTAs: split-K
   // accumulates with red.add, and the frozen encoder is required to be run-to-run bit-identical
   // (tests/test_prompter_gpu.py); measured cost of keeping it deterministic: ~10 us per step.

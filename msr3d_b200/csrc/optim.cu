@@ -71,6 +71,26 @@ adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restri
   }
 }
 
+// out = <a, b>: the surrogate loss <obj_tokens, upstream> read back by the training loop.  One CTA,
+// fixed summation order (deterministic); n is a few 10^4.
+__global__ void __launch_bounds__(1024)
+dot_kernel(const float *__restrict__ a, const float *__restrict__ b, long long n, float *__restrict__ out) {
+  pdl_sync();
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 1024) s += a[i] * b[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float w[32];
+  if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = w[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) *out = t;
+  }
+}
+
 __global__ void reset_sumsq_kernel(OptState *st) {
   pdl_sync();
   st->sumsq = 0.f;
@@ -101,4 +121,11 @@ MSR3D_API int msr3d_adamw_clip_step_f32(float *params, const float *grads, float
   if (rc) return rc;
   launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq, n, n_decay, grad_scale, st);
   return check_launch("adamw");
+}
+
+/* out[0] = sum_i a[i] * b[i] (device scalar), deterministic. */
+MSR3D_API int msr3d_dot_f32(const float *a, const float *b, long long n, float *out, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(a && b && out && n >= 0, "dot: bad args");
+  launch_pdl(dot_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, a, b, n, out);
+  return check_launch("dot");
 }

@@ -28,7 +28,7 @@ using namespace umma;
 
 // ext_ops.cu
 int launch_fps(const float *xyz, int ld, int32_t *idx, float *new_xyz, int B, int N, int m,
-               cudaStream_t stream);
+               cudaStream_t stream, int32_t *ball_idx, float radius, int nsample);
 int launch_ball_query(const float *new_xyz, const float *xyz, int ld, int32_t *idx, int B, int N,
                       int M, float radius, int nsample, cudaStream_t stream);
 
@@ -320,7 +320,9 @@ static int launch_sa_mlp(const SaParams &p, cudaStream_t stream) {
     configured = true;
   }
   const int per_sm = RESIDENT ? 2 : 1;
-  int grid = p.n_tiles < kNumSMs * per_sm ? p.n_tiles : kNumSMs * per_sm;
+  int sms = kNumSMs;
+  if (g_tune[TUNE_SA_SM_LIMIT] > 0 && g_tune[TUNE_SA_SM_LIMIT] < kNumSMs) sms = g_tune[TUNE_SA_SM_LIMIT];  // A/B: leave SMs to a concurrent chain
+  int grid = p.n_tiles < sms * per_sm ? p.n_tiles : sms * per_sm;
   launch_pdl(kern, dim3(grid), dim3(256), L::kSmem, stream, p);
   return check_launch("sa_mlp_kernel");
 }
@@ -337,9 +339,17 @@ MSR3D_API int msr3d_sa_group_f32(const float *xyz, int ld, int B, int N, int m, 
                                  int nsample, int32_t *fps_idx, float *new_xyz, int32_t *ball_idx,
                                  msr3d_stream_t stream) {
   MSR3D_REQUIRE(xyz && fps_idx && new_xyz && ball_idx, "sa_group: null pointer");
-  int rc = launch_fps(xyz, ld, fps_idx, new_xyz, B, N, m, (cudaStream_t)stream);
-  if (rc != MSR3D_OK) return rc;
-  return launch_ball_query(new_xyz, xyz, ld, ball_idx, B, N, m, radius, nsample, (cudaStream_t)stream);
+  MSR3D_REQUIRE(nsample >= 0, "sa_group: bad nsample %d", nsample);
+  // Two launches by default.  Fusing the ball query into the FPS kernel (the cloud is already in its shared
+  // memory) saves a launch and a re-read, but the FPS CTAs then walk 32 centres with 8 warps while the
+  // rest of the GPU idles: measured +38 us per pipelined step (A/B with MSR3D_TUNE=6=1).
+  if (!g_tune[TUNE_SA_GROUP_FUSED]) {
+    int rc = launch_fps(xyz, ld, fps_idx, new_xyz, B, N, m, (cudaStream_t)stream, nullptr, 0.f, 0);
+    if (rc != MSR3D_OK) return rc;
+    return launch_ball_query(new_xyz, xyz, ld, ball_idx, B, N, m, radius, nsample, (cudaStream_t)stream);
+  }
+  // one launch: FPS, centre gather and ball query share the cloud staged in shared memory
+  return launch_fps(xyz, ld, fps_idx, new_xyz, B, N, m, (cudaStream_t)stream, ball_idx, radius, nsample);
 }
 
 namespace msr3d {

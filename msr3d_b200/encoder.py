@@ -257,11 +257,11 @@ def _first_layer_perm(nfeat: int, kp: int, device) -> torch.Tensor:
     return perm.to(device)
 
 
-def fold_sa_level(sd, prefix: str, nfeat: int, fused: bool):
+def fold_sa_level(sd, prefix: str, nfeat: int, fused: bool, bn_last: int = 128, bn_first: int = 128):
     """Packs the three conv+BN layers under `prefix` (…mlps.0) for the tensor cores.
 
     fused=True : tiles for sa_mlp_fused (BN = min(C,128), BK = whole padded K of the layer)
-    fused=False: tiles for linear_tc    (BN = 128, BK = 64)
+    fused=False: tiles for linear_tc    (BN = 128, BK = 64; `bn_last` = N tile of the last layer)
     Returns ([PackedWeight]*3, [bias]*3)."""
     weights, biases = [], []
     i = 0
@@ -275,6 +275,10 @@ def fold_sa_level(sd, prefix: str, nfeat: int, fused: bool):
             bn_, bk = min(n, 128), -(-k // 16) * 16
         else:
             bn_, bk = 128, 64
+            if bn_last != 128 and f"{prefix}.layer{i + 1}.conv.weight" not in sd and n % bn_last == 0:
+                bn_ = bn_last
+            if i == 0 and bn_first != 128:
+                bn_ = bn_first
         perm = None
         if i == 0:
             kp = -(-k // bk) * bk
@@ -349,7 +353,15 @@ class PointNetPP(nn.Module):
             packed["sa1"] = fold_sa_level(sd, "encoder.0.mlps.0", 3, fused=True)
             packed["sa2"] = fold_sa_level(sd, "encoder.1.mlps.0", self._widths(0)[-1], fused=True)
             packed["sa3"] = fold_sa_level(sd, "encoder.2.mlps.0", self._widths(1)[-1], fused=False)
-            packed["fc"] = (ops.pack_weight(sd["fc.weight"]), sd["fc.bias"].float().contiguous())
+            # last SA3 layer a second time with 192-wide N tiles: 3840 x 768 is 180 tiles of 128 x 128
+            # (1.2 waves on 148 SMs) but 120 tiles of 128 x 192 (one wave) — chosen per call from M
+            packed["sa3_w192"] = fold_sa_level(sd, "encoder.2.mlps.0", self._widths(1)[-1], fused=False,
+                                               bn_last=192)[0][2]
+            packed["fc"] = (ops.pack_weight(sd["fc.weight"], BN=64 if ops.ENC_SMALL_TILES else 128),
+                            sd["fc.bias"].float().contiguous())
+            if ops.ENC_SMALL_TILES:
+                packed["sa3"][0][0] = fold_sa_level(sd, "encoder.2.mlps.0", self._widths(1)[-1], fused=False,
+                                                    bn_first=64)[0][0]
             self._packed, self._pack_key = packed, key
         return self._packed
 
@@ -388,7 +400,12 @@ class PointNetPP(nn.Module):
                            out=self._workspace("h1", (Bc * np2, w3[1]), dev), tag="sa3_l1")
         h2 = ops.linear_tc(h1, pk["sa3"][0][1], pk["sa3"][1][1], act="relu", split=split,
                            out=self._workspace("h2", (Bc * np2, w3[2]), dev), tag="sa3_l2")
-        g = ops.linear_tc(h2, pk["sa3"][0][2], pk["sa3"][1][2], act="relu", pool=np2, split=split,
+        w_l3 = pk["sa3"][0][2]
+        mt = -(-(Bc * np2) // 128)
+        if (ops.SA3_WIDE_TILES and mt * -(-w3[3] // 128) > ops.NUM_SMS and pk["sa3_w192"].BN == 192
+                and mt * (w3[3] // 192) <= ops.NUM_SMS):
+            w_l3 = pk["sa3_w192"]
+        g = ops.linear_tc(h2, w_l3, pk["sa3"][1][2], act="relu", pool=np2, split=split,
                           out=self._workspace("g", (Bc, w3[3]), dev), tag="sa3_l3")
         out = ops.linear_tc(g, pk["fc"][0], pk["fc"][1], split=split, tag="fc", out=out)
         if trace is not None:

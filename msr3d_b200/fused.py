@@ -61,6 +61,7 @@ _C.register_protos({
     "msr3d_colsum_add_f32": [c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "msr3d_dropout_mask_f32": [c_ull, c_vp, c_float, c_uint, c_ll, c_vp, c_vp],
     "msr3d_adamw_clip_step_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp],
+    "msr3d_dot_f32": [c_vp, c_vp, c_ll, c_vp, c_vp],
 })
 
 H = 256          # hidden size the fused kernels are built for
@@ -121,6 +122,7 @@ class FusedPrompter:
         self.opt_state = torch.tensor([0.0, 0.0, lr, betas[0], betas[1], eps, weight_decay,
                                        grad_norm if grad_norm else 0.0], dtype=torch.float32, device=dev)
         self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.loss_buf = torch.zeros(1, dtype=torch.float32, device=dev)
         self.seed_counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self.seed = 0x5EED
         self._shape = None
@@ -386,7 +388,7 @@ class FusedPrompter:
                    G("size_embedding_encoder.0.weight"), G("size_embedding_encoder.0.bias"),
                    G("loc_embedding_encoder.0.bias"), tag="qpos_bwd")
         self._gemm(bwd, ptr(w["dh1"]), (1, H), ptr(w["ff"]), (1, 64), H, 63, M, G("loc_embedding_encoder.0.weight"), 63,
-                   accumulate=1, tag="dWloc", wgrad=True)
+                   accumulate=2, ksplit=4, tag="dWloc", wgrad=True)
         bwd.append(("join", None, (), None, False))
         return pre_prog, fwd, bwd
 
@@ -620,8 +622,12 @@ class FusedPrompter:
         return self.ws["tokens"].view(B, L, H)
 
     def loss(self):
-        """Surrogate scalar <tokens, upstream> (what bench.py reads back)."""
-        return (self.ws["tokens"] * self.ws["upstream"]).sum()
+        """Surrogate scalar <tokens, upstream> (what bench.py reads back): one deterministic single-CTA
+        kernel instead of torch's mul + two-pass reduction (20 us cold)."""
+        t = self.ws["tokens"]
+        _C.call("msr3d_dot_f32", t.data_ptr(), self.ws["upstream"].data_ptr(), t.numel(), self.loss_buf.data_ptr(),
+                torch.cuda.current_stream().cuda_stream)
+        return self.loss_buf[0]
 
 
 def gemm_tc(A: torch.Tensor, Bm: torch.Tensor, bias: Optional[torch.Tensor] = None, split: int = 3,

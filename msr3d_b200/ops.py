@@ -12,6 +12,14 @@ from . import _C
 ACT = {"none": 0, None: 0, "relu": 1, "gelu": 2}
 #: 3 = split-bf16 (fp32-grade), 1 = single bf16 pass.  Module default; tests flip it.
 DEFAULT_SPLIT = 3
+NUM_SMS = 148   # B200
+#: 192-wide N tiles for the last SA3 layer when 128-wide ones spill into a second wave: 10 us faster for
+#: the encoder alone, 5 us SLOWER per pipelined step (120 CTAs that each own an SM for the whole kernel
+#: starve the concurrent transformer chain) -> off unless MSR3D_SA3_WIDE=1
+#: N tile of the packed weights of GEMMs that run on few CTAs (final fc: M = 240 rows; first SA3 layer):
+#: 64 doubles their CTA count.  A/B: MSR3D_ENC_BN64=0/1
+ENC_SMALL_TILES = __import__("os").environ.get("MSR3D_ENC_BN64", "0") == "1"
+SA3_WIDE_TILES = __import__("os").environ.get("MSR3D_SA3_WIDE", "0") == "1"
 #: roofline.KernelTimer or None; when set, launches are bracketed by CUDA events on the current stream
 TIMER = None
 
@@ -74,7 +82,7 @@ def linear_tc(A: torch.Tensor, W: PackedWeight, bias: Optional[torch.Tensor] = N
               tag: Optional[str] = None) -> torch.Tensor:
     """out[M,N] = act(A[M,K] @ W^T + bias) on the tensor cores; A may be any 2-D view."""
     assert A.is_cuda and A.dtype == torch.float32 and A.dim() == 2
-    assert W.BN == 128 and W.BK == 64
+    assert W.BN in (64, 128, 192) and W.BK == 64
     M, K = A.shape
     assert K == W.K, (K, W.K)
     rows = M // pool if pool > 1 else M
@@ -84,7 +92,7 @@ def linear_tc(A: torch.Tensor, W: PackedWeight, bias: Optional[torch.Tensor] = N
     with torch.cuda.device(A.device), _range(tag):
         _C.call("msr3d_linear_tc_f32", A.data_ptr(), A.stride(0), A.stride(1), M, K,
                 W.data.data_ptr(), _ptr(bias), out.data_ptr(), out.stride(0), W.N, ACT[act],
-                int(pool), int(split or DEFAULT_SPLIT), int(accumulate), _stream())
+                int(pool), int(split or DEFAULT_SPLIT), int(accumulate), int(W.BN), _stream())
     return out
 
 
