@@ -26,13 +26,17 @@ namespace msr3d {
 //   equal maxima the winner is the thread with the smallest BIT-REVERSED id,
 //   then the smallest k inside that thread.  rank(k) encodes exactly that
 //   order; arg-max of (value, -rank) reproduces the reference pick for pick.
-__device__ __forceinline__ uint32_t fps_rank(int k, int log2bs, int nper) {
+// Only the ORDER of ranks matters, so the rank is (bit-reversed thread id) * 16 + (k / bs): k / bs < 16
+// for every supported size (N <= 8192 with bs = 512, and N < 2 * bs below that), and unranking is a
+// shift and a mask instead of an integer division in every thread every round.
+constexpr int kFpsRankShift = 4;
+__device__ __forceinline__ uint32_t fps_rank(int k, int log2bs) {
   const uint32_t t = (uint32_t)k & ((1u << log2bs) - 1u);
   const uint32_t rev = log2bs ? (__brev(t) >> (32 - log2bs)) : 0u;
-  return rev * (uint32_t)nper + ((uint32_t)k >> log2bs);
+  return (rev << kFpsRankShift) | ((uint32_t)k >> log2bs);
 }
-__device__ __forceinline__ int fps_unrank(uint32_t r, int log2bs, int nper) {
-  const uint32_t rev = r / (uint32_t)nper, i = r % (uint32_t)nper;
+__device__ __forceinline__ int fps_unrank(uint32_t r, int log2bs) {
+  const uint32_t rev = r >> kFpsRankShift, i = r & ((1u << kFpsRankShift) - 1u);
   const uint32_t t = log2bs ? (__brev(rev) >> (32 - log2bs)) : 0u;
   return (int)(t + (i << log2bs));
 }
@@ -85,7 +89,7 @@ fps_kernel(const float *__restrict__ xyz, int ld, int32_t *__restrict__ idx,
       // `mag <= 1e-3` is a double comparison in the reference (DSETP.GTU).
       if (!((double)mag <= 1e-3)) {
         valid |= 1u << i;
-        rk[i] = fps_rank(k, log2bs, nper);
+        rk[i] = fps_rank(k, log2bs);
       }
     }
   }
@@ -115,18 +119,14 @@ fps_kernel(const float *__restrict__ xyz, int ld, int32_t *__restrict__ idx,
     if (NW > 1) {
       if (lane == 0) s_part[j & 1][warp] = make_uint2(wkey, wrank);
       __syncthreads();
-      uint32_t gkey = 0, grank = 0xffffffffu;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        const uint2 p = s_part[j & 1][w];
-        if (p.x > gkey || (p.x == gkey && p.y < grank)) {
-          gkey = p.x;
-          grank = p.y;
-        }
-      }
-      old = gkey ? fps_unrank(grank, log2bs, nper) : 0;
+      // cross-warp merge: lane w holds warp w's partial, two more REDUX (every warp redundantly, so no
+      // second barrier); the serial NW-way compare chain in every thread was a third of the round
+      const uint2 p = lane < NW ? s_part[j & 1][lane] : make_uint2(0u, 0xffffffffu);
+      const uint32_t gkey = __reduce_max_sync(0xffffffffu, p.x);
+      const uint32_t grank = __reduce_min_sync(0xffffffffu, p.x == gkey ? p.y : 0xffffffffu);
+      old = gkey ? fps_unrank(grank, log2bs) : 0;
     } else {
-      old = wkey ? fps_unrank(wrank, log2bs, nper) : 0;
+      old = wkey ? fps_unrank(wrank, log2bs) : 0;
     }
     if (tid == 0) s_pick[j] = old;
   }
@@ -185,6 +185,7 @@ int launch_fps(const float *xyz, int ld, int32_t *idx, float *new_xyz, int B, in
   if (log2bs > 9) log2bs = 9;
   const int bs = 1 << log2bs;
   const int nper = ceil_div(N, bs);
+  MSR3D_REQUIRE(nper <= (1 << kFpsRankShift), "fps: N=%d needs %d points per reference thread (max 16)", N, nper);
   const size_t smem = (size_t)N * 3 * sizeof(float) + (size_t)m * sizeof(int32_t);
   const float radius2 = radius * radius;   // f32 product, as ball_query.cpp / ball_query_gpu.cu:22
   if (nsample <= 0) ball_idx = nullptr;
