@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--no-pipeline", action="store_true",
                     help="run the frozen encoder and the transformer step of a batch back to back instead of "
                          "overlapping the encoder of batch i+1 with the step of batch i")
+    ap.add_argument("--no-prefetch", action="store_true",
+                    help="copy the point clouds on the compute stream in front of the step instead of prefetching "
+                         "them on a copy stream during the previous step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -234,7 +237,7 @@ def main():
     model.load_state_dict(sd, strict=True)
     model = model.to(dev).train()
     trainer = HotPathTrainer(model, B, O, P, world_size=world, split=args.split, use_graph=not args.no_graph,
-                             pipeline=not args.no_pipeline)
+                             pipeline=False if args.no_pipeline else (True if args.no_prefetch else "prefetch"))
     # four distinct pinned host batches per rank, cycled (seed = cfg_id*1000 + rank)
     host = [synthetic.make_batch(B, O, P, seed=2000 + rank + 17 * i).pin() for i in range(4)]
     devb = [h.to(dev) for h in host]
@@ -254,8 +257,7 @@ def main():
             flush.zero_()                                    # L2 flush between timed iterations
             ev[i][0].record()
             if from_host:
-                loss = trainer.step(host[i % 4], up)     # H2D from pinned memory into the static buffers
-                loss_host.copy_(loss, non_blocking=True)
+                trainer.step(host[i % 4], up, loss_out=loss_host)   # H2D from pinned memory, loss read back
             else:
                 trainer.step(devb[i % 4], up)
             ev[i][1].record()
@@ -308,8 +310,10 @@ def main():
             "config": {"workload": args.config, "batch_per_gpu": B, "objects": O, "points": P,
                        "l2": "flushed (256 MB memset) between timed iterations", "parallelism": f"dp{world}",
                        "schedule": "sequential" if args.no_pipeline else
-                       "pipelined: frozen encoder of batch i+1 overlaps the transformer step of batch i "
-                       "(one encoder pass + one update per step)",
+                       ("pipelined: frozen encoder of batch i+1 overlaps the transformer step of batch i "
+                        "(one encoder pass + one update per step)" +
+                        ("" if args.no_prefetch else "; point clouds of batch i+2 prefetched (H2D on a copy stream) "
+                         "during the same step")),
                        "timing": "sum of per-step CUDA-event intervals, max over ranks"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches_per_step * args.steps),

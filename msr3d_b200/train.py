@@ -23,9 +23,11 @@ from .fused import FusedPrompter
 
 
 class HotPathTrainer:
-    """pipeline=True (default): the frozen encoder of batch i+1 runs concurrently with the transformer
+    """pipeline=True: the frozen encoder of batch i+1 runs concurrently with the transformer
     forward/backward/optimiser of batch i (one call = one encoder pass + one update, identical results,
-    the update for a batch lands one call later; `flush()` drains the last one)."""
+    the update for a batch lands one call later; `flush()` drains the last one).
+    pipeline="prefetch": additionally the point clouds of the batch handed to `step` are copied to the
+    device on a copy stream while the current step runs (update lands two calls later)."""
 
     def __init__(self, model: torch.nn.Module, B: int, O: int, P: int, lr: float = 3e-5,
                  weight_decay: float = 0.05, betas=(0.9, 0.999), grad_norm: float = 5.0,
@@ -35,6 +37,7 @@ class HotPathTrainer:
         self.engine.prepare(B, O, P, training=model.training)
         self.use_graph = use_graph
         self.pipeline = pipeline
+        self._calls = 0
         self.n_trainable = self.engine.n_trainable
 
     def warmup(self, batch: synthetic.SceneBatch, upstream: torch.Tensor):
@@ -43,20 +46,47 @@ class HotPathTrainer:
         e.load_inputs(batch, upstream)
         e.train_step_eager()
         torch.cuda.synchronize()
-        if self.pipeline:
+        if self.pipeline == "prefetch":
+            e.prime2(batch, upstream, batch, upstream)
+            if self.use_graph:
+                e.capture_prefetch()
+            self._calls = 2
+        elif self.pipeline:
             e.prime(batch, upstream)
             if self.use_graph:
                 e.capture_pipelined()
         elif self.use_graph:
             e.capture()
 
-    def step(self, batch: synthetic.SceneBatch, upstream: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def step(self, batch: synthetic.SceneBatch, upstream: Optional[torch.Tensor] = None,
+             loss_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One micro-step fed with `batch` (device or pinned-host tensors).  Returns the surrogate loss
-        <obj_tokens, upstream> (device scalar) of the batch whose update was applied in this call."""
+        <obj_tokens, upstream> (device scalar) of the batch whose update was applied in this call;
+        `loss_out` (pinned host scalar) additionally receives it through an asynchronous D2H copy."""
+        loss = self._step(batch, upstream)
+        if loss_out is not None:
+            if self.pipeline == "prefetch":
+                ev = torch.cuda.Event()
+                ev.record()
+                cs = self.engine.copy_stream
+                cs.wait_event(ev)
+                with torch.cuda.stream(cs):
+                    loss_out.copy_(loss, non_blocking=True)
+            else:
+                loss_out.copy_(loss, non_blocking=True)
+        return loss
+
+    def _step(self, batch, upstream):
         e = self.engine
         if not self.pipeline:
             e.load_inputs(batch, upstream)
             e.train_step()
+            return e.loss()
+        if self.pipeline == "prefetch":
+            i = self._calls
+            e.prefetch(batch, upstream, i % 2)              # async H2D, consumed by the NEXT call's step
+            e.train_step_prefetch((i - 1) % 2)              # encode batch i-1, update with batch i-2
+            self._calls += 1
             return e.loss()
         e.stage_points(batch)               # H2D of the point clouds: needed by the overlapped encoder
         e.train_step_pipelined()            # update with the previously staged batch
@@ -64,7 +94,16 @@ class HotPathTrainer:
         e.stage_scene(batch, upstream)      # small per-scene inputs of `batch`, consumed by the next call
         return loss
 
-    def flush(self) -> torch.Tensor:
-        """Apply the update of the last staged batch (pipeline mode)."""
-        self.engine.train_step_pipelined(flush=True)
-        return self.engine.loss()
+    def flush(self):
+        """Apply the updates still in the pipeline.  Returns the loss of the last one (pipeline=True) or
+        the list of the last two (pipeline="prefetch")."""
+        e = self.engine
+        if self.pipeline == "prefetch":
+            i = self._calls
+            e.train_step_prefetch((i - 1) % 2, flush=1)     # encode the last batch, update with the one before
+            l1 = e.loss().clone()
+            e.train_step_prefetch(i % 2, flush=2)           # update with the last batch
+            self._calls += 2
+            return [l1, e.loss()]
+        e.train_step_pipelined(flush=True)
+        return e.loss()

@@ -198,12 +198,23 @@ def test_pipelined_schedule_equals_sequential(sd_spec):
     batches = [synthetic.make_batch(B, O, P, seed=seed + i).to("cuda") for i in range(4)]
     ups = [torch.randn(B, O, 256, generator=torch.Generator().manual_seed(i)).cuda() for i in range(4)]
     res = {}
-    for mode in ("sequential", "pipelined", "pipelined_graph"):
+    for mode in ("sequential", "pipelined", "pipelined_graph", "prefetch", "prefetch_graph"):
         model = helpers.build_prompter(seed, device="cuda")     # eval mode: no dropout
-        tr = HotPathTrainer(model, B, O, P, lr=1e-4, use_graph=mode.endswith("graph"), pipeline=mode != "sequential")
+        pipe = False if mode == "sequential" else ("prefetch" if mode.startswith("prefetch") else True)
+        tr = HotPathTrainer(model, B, O, P, lr=1e-4, use_graph=mode.endswith("graph"), pipeline=pipe)
         if mode == "sequential":
             for b, u in zip(batches, ups):
                 tr.step(b, u)
+        elif pipe == "prefetch":
+            # points arrive from pinned host memory on the copy stream; updates land two calls later
+            host = [b.to("cpu").pin() for b in batches]
+            tr.engine.prime2(host[0], ups[0], host[1], ups[1])
+            if tr.use_graph:
+                tr.engine.capture_prefetch()
+            tr._calls = 2
+            losses = [tr.step(b, u) for b, u in zip(host[2:], ups[2:])]
+            losses += tr.flush()
+            assert len(losses) == 4
         else:
             tr.engine.prime(batches[0], ups[0])
             if tr.use_graph:
@@ -212,8 +223,10 @@ def test_pipelined_schedule_equals_sequential(sd_spec):
             losses.append(tr.flush())
         torch.cuda.synchronize()
         res[mode] = (tr.engine.flat_p.clone(), float(tr.engine.opt_state[1]))
-    assert res["sequential"][1] == res["pipelined"][1] == res["pipelined_graph"][1] == 4.0
+    assert all(r[1] == 4.0 for r in res.values())
     # same updates in the same order; only atomics ordering (split-K, column sums) differs between runs,
     # and Adam's first steps turn tiny gradient differences into +-lr flips of near-zero entries
     assert helpers.rel_err(res["pipelined"][0], res["sequential"][0]) < 5e-4
     assert helpers.rel_err(res["pipelined_graph"][0], res["sequential"][0]) < 5e-4
+    assert helpers.rel_err(res["prefetch"][0], res["sequential"][0]) < 5e-4
+    assert helpers.rel_err(res["prefetch_graph"][0], res["sequential"][0]) < 5e-4
