@@ -129,18 +129,35 @@ geometry_kernel(const float *__restrict__ loc, const float *__restrict__ anchor,
 }
 
 // ---------------------------------------------------------------------------
-// LayerNorm helpers: one warp per row of kD = 256 values (8 per lane, lane-strided).
+// LayerNorm helpers: one warp per row of kD = 256 values; lane l owns the 8 CONSECUTIVE columns
+// 8l .. 8l+7 (two 16 B accesses per row and, above all, two Philox blocks per dropout site instead
+// of eight: the mask of element `offset` is word offset & 3 of Philox block offset >> 2, rng.cuh —
+// with the lane-strided mapping every element paid its own ten-round Philox evaluation, which made
+// the tail kernels 9-10 us of pure integer arithmetic).
 // ---------------------------------------------------------------------------
 struct Row8 { float v[8]; };
+__device__ __forceinline__ int col8(int lane, int i) { return lane * 8 + i; }
 __device__ __forceinline__ Row8 row_load(const float *p, int lane) {
   Row8 r;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) r.v[i] = p[lane + 32 * i];
+  const float4 a = *reinterpret_cast<const float4 *>(p + lane * 8);
+  const float4 b = *reinterpret_cast<const float4 *>(p + lane * 8 + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
   return r;
 }
 __device__ __forceinline__ void row_store(float *p, int lane, const Row8 &r) {
+  *reinterpret_cast<float4 *>(p + lane * 8) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  *reinterpret_cast<float4 *>(p + lane * 8 + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+// dropout masks of this lane's 8 columns of the row starting at element offset `base` (base % 8 == 0)
+__device__ __forceinline__ Row8 drop_mask8(const Dropout &d, size_t base, int lane, unsigned site) {
+  Row8 m;
+  float a[4], b[4];
+  d.mask4((uint64_t)base + lane * 8, site, a);
+  d.mask4((uint64_t)base + lane * 8 + 4, site, b);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) p[lane + 32 * i] = r.v[i];
+  for (int i = 0; i < 4; ++i) { m.v[i] = a[i]; m.v[4 + i] = b[i]; }
+  return m;
 }
 // y = gamma * xhat + beta; returns xhat in `x`, rstd via out param
 __device__ __forceinline__ Row8 ln_forward(Row8 &x, const float *gamma, const float *beta, int lane,
@@ -157,7 +174,7 @@ __device__ __forceinline__ Row8 ln_forward(Row8 &x, const float *gamma, const fl
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     x.v[i] *= rstd;
-    y.v[i] = x.v[i] * gamma[lane + 32 * i] + beta[lane + 32 * i];
+    y.v[i] = x.v[i] * gamma[col8(lane, i)] + beta[col8(lane, i)];
   }
   return y;
 }
@@ -168,7 +185,7 @@ __device__ __forceinline__ Row8 ln_backward(const Row8 &dy, const Row8 &xhat, co
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    g.v[i] = dy.v[i] * gamma[lane + 32 * i];
+    g.v[i] = dy.v[i] * gamma[col8(lane, i)];
     s1 += g.v[i];
     s2 += g.v[i] * xhat.v[i];
   }
@@ -188,13 +205,16 @@ struct ColAcc {
   __device__ void zero(int n_acc, int tid) {
     for (int i = tid; i < n_acc * kD; i += kLnWarps * 32) s[i] = 0.f;
   }
+  // column c = 8 * lane + i lives at slot i * 32 + lane: lanes hit distinct banks
+  __device__ static int slot(int c) { return (c & 7) * 32 + (c >> 3); }
   __device__ void add(int which, int lane, const Row8 &r) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&s[which * kD + lane + 32 * i], r.v[i]);
+    for (int i = 0; i < 8; ++i) atomicAdd(&s[which * kD + i * 32 + lane], r.v[i]);
   }
+  __device__ float get(int which, int c) const { return s[which * kD + slot(c)]; }
   __device__ void flush(int which, float *dst, int tid) {
     if (dst == nullptr) return;
-    for (int i = tid; i < kD; i += kLnWarps * 32) atomicAdd(dst + i, s[which * kD + i]);
+    for (int c = tid; c < kD; c += kLnWarps * 32) atomicAdd(dst + c, get(which, c));
   }
 };
 
@@ -213,21 +233,21 @@ attn_tail_fwd_kernel(const float *__restrict__ o, const float *__restrict__ x, i
                      float *__restrict__ xhat_1, float *__restrict__ rstd_1,
                      float *__restrict__ y2) {
   pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
-  drop.resolve();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   if (row >= M) return;
   const size_t base = (size_t)row * kD;
-  Row8 xo = row_load(o + base, lane), xr = row_load(x + base, lane), v;
+  Row8 xo = row_load(o + base, lane), xr = row_load(x + base, lane), v;   // rows in flight ...
+  drop.resolve();                                                         // ... with the seed counter
+  const Row8 mfc = drop_mask8(drop, base, lane, site_fc), m1 = drop_mask8(drop, base, lane, site_1);
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    v.v[i] = drop.apply(xo.v[i], base + lane + 32 * i, site_fc) + xr.v[i];
+  for (int i = 0; i < 8; ++i) v.v[i] = xo.v[i] * mfc.v[i] + xr.v[i];
   float ra, r1;
   Row8 y1 = ln_forward(v, lna.gamma, lna.beta, lane, ra);
   row_store(xhat_a + base, lane, v);
   Row8 w;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) w.v[i] = xr.v[i] + drop.apply(y1.v[i], base + lane + 32 * i, site_1);
+  for (int i = 0; i < 8; ++i) w.v[i] = xr.v[i] + y1.v[i] * m1.v[i];
   Row8 out = ln_forward(w, ln1.gamma, ln1.beta, lane, r1);
   row_store(xhat_1 + base, lane, w);
   row_store(y2 + base, lane, out);
@@ -257,6 +277,7 @@ attn_tail_bwd_kernel(const float *__restrict__ dy2, int M, LnParams lna, LnParam
     const size_t base = (size_t)row * kD;
     const Row8 g2 = row_load(dy2 + base, lane);
     const Row8 h1 = row_load(xhat_1 + base, lane), ha = row_load(xhat_a + base, lane);
+    const Row8 m1 = drop_mask8(drop, base, lane, site_1), mfc = drop_mask8(drop, base, lane, site_fc);
     Row8 t;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t.v[i] = g2.v[i] * h1.v[i];
@@ -265,7 +286,7 @@ attn_tail_bwd_kernel(const float *__restrict__ dy2, int M, LnParams lna, LnParam
     const Row8 dw = ln_backward(g2, h1, ln1.gamma, lane, rstd_1[row]);
     Row8 dy1;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dy1.v[i] = dw.v[i] * drop.mask(base + lane + 32 * i, site_1);
+    for (int i = 0; i < 8; ++i) dy1.v[i] = dw.v[i] * m1.v[i];
 #pragma unroll
     for (int i = 0; i < 8; ++i) t.v[i] = dy1.v[i] * ha.v[i];
     acc.add(0, lane, t);    // dgamma_a
@@ -275,7 +296,7 @@ attn_tail_bwd_kernel(const float *__restrict__ dy2, int M, LnParams lna, LnParam
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       dxr.v[i] = dw.v[i] + dv.v[i];
-      dor.v[i] = dv.v[i] * drop.mask(base + lane + 32 * i, site_fc);
+      dor.v[i] = dv.v[i] * mfc.v[i];
     }
     acc.add(4, lane, dor);  // bias gradient of the out projection
     row_store(dx + base, lane, dxr);
@@ -299,14 +320,15 @@ ffn_tail_fwd_kernel(const float *__restrict__ f, const float *__restrict__ y2, i
                     float *__restrict__ xhat_2, float *__restrict__ rstd_2, float *__restrict__ y3,
                     float *__restrict__ x_next) {
   pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
-  drop.resolve();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   if (row >= M) return;
   const size_t base = (size_t)row * kD;
   Row8 xf = row_load(f + base, lane), xr = row_load(y2 + base, lane), w;
+  drop.resolve();
+  const Row8 m2 = drop_mask8(drop, base, lane, site_2);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) w.v[i] = xr.v[i] + drop.apply(xf.v[i], base + lane + 32 * i, site_2);
+  for (int i = 0; i < 8; ++i) w.v[i] = xr.v[i] + xf.v[i] * m2.v[i];
   float r2;
   Row8 out = ln_forward(w, ln2.gamma, ln2.beta, lane, r2);
   row_store(xhat_2 + base, lane, w);
@@ -338,6 +360,7 @@ ffn_tail_bwd_kernel(const float *__restrict__ dy3, int M, LnParams ln2, Dropout 
   if (row < M) {
     const size_t base = (size_t)row * kD;
     const Row8 g = row_load(dy3 + base, lane), h = row_load(xhat_2 + base, lane);
+    const Row8 m2 = drop_mask8(drop, base, lane, site_2);
     Row8 t;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t.v[i] = g.v[i] * h.v[i];
@@ -346,7 +369,7 @@ ffn_tail_bwd_kernel(const float *__restrict__ dy3, int M, LnParams ln2, Dropout 
     const Row8 dw = ln_backward(g, h, ln2.gamma, lane, rstd_2[row]);
     Row8 dfr;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dfr.v[i] = dw.v[i] * drop.mask(base + lane + 32 * i, site_2);
+    for (int i = 0; i < 8; ++i) dfr.v[i] = dw.v[i] * m2.v[i];
     acc.add(2, lane, dfr);
     row_store(dy2 + base, lane, dw);
     row_store(df + base, lane, dfr);
@@ -377,7 +400,7 @@ qpos_fwd_kernel(const float *__restrict__ h1, const float *__restrict__ sz, int 
   const float s0 = sz[row * 3 + 0], s1 = sz[row * 3 + 1], s2 = sz[row * 3 + 2];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int c = lane + 32 * i;
+    const int c = col8(lane, i);
     b.v[i] = (Ws[c * 3 + 0] * s0 + Ws[c * 3 + 1] * s1) + Ws[c * 3 + 2] * s2 + bs[c];
   }
   float rl, rs;
@@ -388,7 +411,7 @@ qpos_fwd_kernel(const float *__restrict__ h1, const float *__restrict__ sz, int 
   Row8 q, q0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int c = lane + 32 * i;
+    const int c = col8(lane, i);
     q.v[i] = ya.v[i] + yb.v[i];
     q0.v[i] = q.v[i] + (extra_a ? extra_a[c] : 0.f) + (extra_b ? extra_b[c] : 0.f);
   }
@@ -461,9 +484,9 @@ qpos_bwd_kernel(const float *__restrict__ dq, const float *__restrict__ dq1,
   acc.flush(4, dbs, threadIdx.x);
   if (dWs != nullptr)
     for (int c = threadIdx.x; c < kD; c += kLnWarps * 32) {
-      atomicAdd(dWs + c * 3 + 0, s_acc[5 * kD + c]);
-      atomicAdd(dWs + c * 3 + 1, s_acc[6 * kD + c]);
-      atomicAdd(dWs + c * 3 + 2, s_acc[7 * kD + c]);
+      atomicAdd(dWs + c * 3 + 0, acc.get(5, c));
+      atomicAdd(dWs + c * 3 + 1, acc.get(6, c));
+      atomicAdd(dWs + c * 3 + 2, acc.get(7, c));
     }
 }
 
