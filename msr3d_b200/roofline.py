@@ -81,8 +81,12 @@ _GEMM_TAGS = ("sa3_l1", "sa3_l2", "sa3_l3", "fc", "loc_fc", "obj_proj", "qkvc", 
               "du", "dW1", "dy2", "dWo", "dctx", "dWqkvc", "dx", "dWproj", "dWloc")
 KERNEL_OF_TAG = {t: "linear_tc_kernel" for t in _GEMM_TAGS}
 KERNEL_OF_TAG.update({"sa1_mlp": "sa_mlp_kernel<16,64,64,128>", "sa2_mlp": "sa_mlp_kernel<144,128,128,256>"})
-#: dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/r1_ncu_sa_mlp.md)
-TRAFFIC_NCU = {"sa_mlp_kernel<16,64,64,128>": 5.93e6, "sa_mlp_kernel<144,128,128,256>": 4.47e6}
+#: dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures (cold cache:
+#: ncu flushes L2 between replays).  sa_mlp: profiles/r1_ncu_sa_mlp.md.  linear_tc: mean over 26
+#: consecutive launches of the transformer step, profiles/r1_ncu_linear_tc_raw.csv (0.8 - 4.4 MB per
+#: launch = the fp32 weight matrix + the activations + the zero-filled split-K output lines).
+TRAFFIC_NCU = {"sa_mlp_kernel<16,64,64,128>": 5.93e6, "sa_mlp_kernel<144,128,128,256>": 4.47e6,
+               "linear_tc_kernel": 2.73e6}
 
 
 def summarize(timer: KernelTimer, B: int, O: int, P: int, split: int, in_long_step: bool = True, steps: int = 1):
@@ -128,8 +132,10 @@ def summarize(timer: KernelTimer, B: int, O: int, P: int, split: int, in_long_st
         roof = {**common, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                 "peak_source": f"{peaks['source']} bf16 {'sustained' if in_long_step else 'burst'} (MEASURED_PEAKS.json)",
                 "note": "algorithmic fp32-equivalent FLOPs summed over the kernel's launches / summed live CUDA-event "
-                        f"durations; the kernel issues 3-6x that in bf16 MMAs (split-bf16). These GEMMs are latency "
-                        "bound (M = 240 tokens), see profiles/r1_ncu_linear_tc.md"}
+                        "durations (each bracketed launch carries ~7 us of event overhead); the kernel issues 3-6x "
+                        "that in bf16 MMAs (split-bf16). These GEMMs are latency bound (M = 240 tokens: 5.5 us fixed "
+                        "+ ~1.2 us per 64-wide K chunk in a graph chain), see profiles/r1_ncu_linear_tc.md and "
+                        "profiles/r1_gemm_sweep.md"}
     else:
         ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9
         roof = {**common, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",

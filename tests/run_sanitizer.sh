@@ -15,6 +15,15 @@ eng = FusedPrompter(model); eng.prepare(1, 8, 256, training=True)
 b = synthetic.make_batch(1, 8, 256, seed=3).to("cuda")
 eng.load_inputs(b, torch.randn(1, 8, 256, device="cuda"))
 eng.train_step_eager(); torch.cuda.synchronize(); print("step ok", float(eng.loss()))
+# scene-token splice: index scan, scattered fp16 epilogue, backward gather + GEMMs
+from msr3d_b200 import splice
+ids = torch.randint(0, 30000, (1, 40), device="cuda"); ids[0, 5:13] = splice.SCENE_SP_TOKEN
+W = torch.randn(96, 256, device="cuda", requires_grad=True); bias = torch.zeros(96, device="cuda", requires_grad=True)
+tok = torch.randn(1, 8, 256, device="cuda", requires_grad=True)
+out, am = splice.splice_scene_tokens(torch.zeros(1, 40, 96, device="cuda", dtype=torch.float16),
+                                     torch.ones(1, 40, dtype=torch.long, device="cuda"), ids, tok,
+                                     torch.ones(1, 8, dtype=torch.bool, device="cuda"), W, bias)
+out.float().sum().backward(); torch.cuda.synchronize(); print("splice ok", float(W.grad.abs().sum()))
 '
 for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 20 python -c "$SCRIPT" > gpurun_out/sanitizer_$tool.log 2>&1
