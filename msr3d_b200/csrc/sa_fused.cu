@@ -158,6 +158,13 @@ sa_mlp_kernel(const SaParams p) {
 
   const int tiles_per_cloud = p.npoint / 4;
   const int row = tid & 127, half = tid >> 7;
+  // neighbour index of this thread's row in tile t (the first link of the gather's dependent chain:
+  // index -> feature row -> operand image); the one of the NEXT tile is fetched a whole tile ahead
+  auto ball_of = [&](int t) -> int {
+    const int cl = t / tiles_per_cloud, c0 = (t % tiles_per_cloud) * 4;
+    return p.ball[((size_t)cl * p.npoint + c0 + (row >> 5)) * 32 + (row & 31)];
+  };
+  int nb_next = (int)blockIdx.x < p.n_tiles ? ball_of(blockIdx.x) : 0;
   for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
     const int cloud = t / tiles_per_cloud;
     const int centre0 = (t % tiles_per_cloud) * 4;
@@ -170,20 +177,24 @@ sa_mlp_kernel(const SaParams p) {
     // ---------------- gather: build the layer-1 operand image (K order: feats | dxyz | 0)
     {
       const int centre = centre0 + (row >> 5);
-      const int nb = p.ball[((size_t)cloud * p.npoint + centre) * 32 + (row & 31)];
+      const int nb = nb_next;
+      if (t + (int)gridDim.x < p.n_tiles) nb_next = ball_of(t + gridDim.x);
       const float *f = p.feat + ((size_t)cloud * p.Nsrc + nb) * p.ld_feat;
       const float *x = p.xyz + ((size_t)cloud * p.Nsrc + nb) * p.ld_xyz;
       const float *c = p.new_xyz + ((size_t)cloud * p.npoint + centre) * 3;
       const bool vec_ok = (p.ld_feat & 3) == 0 && (reinterpret_cast<uintptr_t>(p.feat) & 15) == 0;
-      // chunks ch = half, half+2, ... in batches of three: the six 16 B loads of a batch are issued
-      // before any conversion, so a tile pays 3 L2 round trips here instead of 9
+      // chunks ch = half, half+2, ...: every 16 B load of a batch is issued before any conversion.  The
+      // streaming variant (one CTA per SM, 255 registers available) takes the whole row in ONE batch
+      // (nine chunks = 72 registers, one L2 round trip per tile instead of three); the resident
+      // variant has a single batch anyway.
       constexpr int kChunks = K0P / 8;
       constexpr int kIters = (kChunks + 1) / 2;
+      constexpr int kBatch = RESIDENT ? 3 : (kIters < 9 ? kIters : 9);
 #pragma unroll
-      for (int it0 = 0; it0 < kIters; it0 += 3) {
-        float v[3][8];
+      for (int it0 = 0; it0 < kIters; it0 += kBatch) {
+        float v[kBatch][8];
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
+        for (int u = 0; u < kBatch; ++u) {
           const int ch = half + 2 * (it0 + u);
           const int k0 = ch * 8;
           if (it0 + u < kIters && ch < kChunks) {
@@ -205,7 +216,7 @@ sa_mlp_kernel(const SaParams p) {
           }
         }
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
+        for (int u = 0; u < kBatch; ++u) {
           const int ch = half + 2 * (it0 + u);
           if (it0 + u < kIters && ch < kChunks) {
             uint32_t hi[4], lo[4];
