@@ -159,6 +159,8 @@ typedef struct msr3d_gemm_desc {
   int tile_n;   /* N tile: 0 = library heuristic, 64 or 128 (few large CTAs keep SMs free for a concurrent chain) */
 } msr3d_gemm_desc;
 int msr3d_gemm_tc_f32(const msr3d_gemm_desc *desc, msr3d_stream_t stream);
+/* sizeof(msr3d_gemm_desc) in the loaded library (a binding's struct mirror must agree). */
+int msr3d_sizeof_gemm_desc(void);
 /* ------------------------------------------------------------------ group E
  * Scene-token splice into the LLM input (the step right after the path):
  * MSR3D.build_embeds, model/msr3d/msr3d.py:277-287 —

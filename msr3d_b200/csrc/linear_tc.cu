@@ -713,6 +713,9 @@ MSR3D_API int msr3d_linear_tc_f32(const float *A, long long stride_am, long long
   return launch_gemm(g, ksplit, (cudaStream_t)stream);
 }
 
+/* sizeof(msr3d_gemm_desc) as this library was compiled: bindings check it against their own mirror. */
+MSR3D_API int msr3d_sizeof_gemm_desc(void) { return (int)sizeof(msr3d_gemm_desc); }
+
 MSR3D_API int msr3d_gemm_tc_f32(const msr3d_gemm_desc *d, msr3d_stream_t stream) {
   MSR3D_REQUIRE(d != nullptr, "gemm_tc: null descriptor");
   MSR3D_REQUIRE(d->A && d->B && d->out, "gemm_tc: null pointer");

@@ -85,17 +85,3 @@ def test_splice_placeholder_count_mismatch_raises():
         splice.splice_scene_tokens(emb, torch.ones(2, 16, dtype=torch.long, device="cuda"), ids,
                                    torch.zeros(2, 2, 256, device="cuda"), torch.ones(2, 2, dtype=torch.bool, device="cuda"),
                                    torch.zeros(64, 256, device="cuda"), None)
-
-
-def test_splice_rejects_cpu_tensors():
-    from msr3d_b200 import splice
-    with pytest.raises(RuntimeError, match="CUDA"):
-        splice.splice_scene_tokens(torch.zeros(1, 4, 8), torch.ones(1, 4, dtype=torch.long),
-                                   torch.zeros(1, 4, dtype=torch.long), torch.zeros(1, 1, 256),
-                                   torch.ones(1, 1, dtype=torch.bool), torch.zeros(8, 256), None)
-
-
-def test_scene_splice_module_state_dict_keys():
-    from msr3d_b200.splice import SceneSplice
-    m = SceneSplice(256, 512)
-    assert set(m.state_dict()) == {"llm_proj.weight", "llm_proj.bias"}   # model/msr3d/msr3d.py:84-87
