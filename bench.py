@@ -229,6 +229,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"     # NCCL prints its version banner on STDOUT: keep stdout = the JSON line
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     ops.DEFAULT_SPLIT = 3 if args.split == 6 else args.split
     B, O, P = synthetic.CONFIGS[args.config]

@@ -264,12 +264,14 @@ int msr3d_colsum_add_f32(const float *src, long long ld, int M, int N, float *ds
 
 /* ------------------------------------------------------------------ group D
  * Global-norm clip + AdamW on one flat buffer (trainer/leo_trainer.py:192-195,
- * optim/build.py:7-17).  state: 8 device floats {sumsq, step, lr, beta1, beta2, eps,
- * weight_decay, max_norm}; ticket: one zeroed device uint32; seed_counter (nullable): device
- * uint64 incremented once per step (the dropout seed offset).  Elements [0, n_decay) decay. */
+ * optim/build.py:7-17).  state: MSR3D_OPT_STATE_FLOATS device floats {sumsq, step, lr, beta1, beta2,
+ * eps, weight_decay, max_norm, then scratch for the deterministic norm reduction}; ticket: one zeroed device uint32; seed_counter (nullable): device
+ * uint64 incremented once per step (the dropout seed offset).  Elements [decay_begin, decay_end)
+ * decay (the flat layout is [late biases | late weights | early weights | early biases], msr3d_b200/dist.py). */
+#define MSR3D_OPT_STATE_FLOATS (8 + 4 * 148)
 int msr3d_adamw_clip_step_f32(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
-                              long long n, long long n_decay, float grad_scale, float *state,
-                              unsigned int *ticket, unsigned long long *seed_counter,
+                              long long n, long long decay_begin, long long decay_end, float grad_scale,
+                              float *state, unsigned int *ticket, unsigned long long *seed_counter,
                               msr3d_stream_t stream);
 /* out[0] = <a, b> over n floats (one CTA, fixed summation order): the scalar the training loop reads
  * back (trainer/leo_trainer.py:196-201 logs the loss every step). */

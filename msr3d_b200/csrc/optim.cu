@@ -8,10 +8,12 @@
 
 namespace msr3d {
 
-struct OptState {   // device-resident, 8 floats
-  float sumsq;      // written by sumsq_kernel (zeroed by adamw_kernel for the next step)
+constexpr int kSumsqBlocks = kNumSMs * 4;
+struct OptState {   // device-resident: 8 floats + one partial sum per block of sumsq_kernel
+  float sumsq;      // written by sumsq_kernel's last block
   float step;       // incremented once per step by sumsq_kernel's last block
   float lr, beta1, beta2, eps, weight_decay, max_norm;
+  float partial[kSumsqBlocks];
 };
 
 __global__ void __launch_bounds__(256)
@@ -29,12 +31,32 @@ sumsq_kernel(const float *__restrict__ g, long long n, float grad_scale, OptStat
   __shared__ float w[8];
   if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = s;
   __syncthreads();
+  // Deterministic: block partials are stored, and the last block to finish adds them up in a fixed
+  // order.  (An atomicAdd per block made the norm — hence the clip factor, hence the update — depend on
+  // the arrival order: data-parallel replicas that hold the same reduced gradient drifted apart in the
+  // last bits, tools/check_ddp_equiv.py.)
+  __shared__ bool s_last;
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += w[i];
-    atomicAdd(&st->sumsq, t);
+    st->partial[blockIdx.x] = t;
     __threadfence();
-    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {  // last block: advance the step counter
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    float t = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) t += ((volatile float *)st->partial)[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int i = 0; i < 8; ++i) tot += w[i];
+      st->sumsq = tot;
       st->step += 1.f;
       if (seed_counter != nullptr) *seed_counter += 1ull;  // next step draws fresh dropout masks
       *ticket = 0u;
@@ -44,10 +66,10 @@ sumsq_kernel(const float *__restrict__ g, long long n, float grad_scale, OptStat
 
 // p -= lr * ( m_hat / (sqrt(v_hat) + eps) + wd * p ), grads first scaled by grad_scale (1/world)
 // and by the global-norm clip coefficient min(1, max_norm / (norm + 1e-6)).
-// Elements [0, n_decay) get weight decay, the rest (biases, LayerNorm) do not.
+// Elements [decay_begin, decay_end) get weight decay, the rest (biases, LayerNorm) do not.
 __global__ void __launch_bounds__(256)
 adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
-             float *__restrict__ v, long long n, long long n_decay, float grad_scale,
+             float *__restrict__ v, long long n, long long decay_begin, long long decay_end, float grad_scale,
              OptState *st) {
   pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   const float norm = sqrtf(st->sumsq);
@@ -61,7 +83,7 @@ adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restri
        i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gs;
     float pi = p[i];
-    if (i < n_decay) pi *= 1.f - lr * wd;  // decoupled weight decay (torch AdamW order)
+    if (i >= decay_begin && i < decay_end) pi *= 1.f - lr * wd;  // decoupled weight decay (torch AdamW order)
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
@@ -91,35 +113,29 @@ dot_kernel(const float *__restrict__ a, const float *__restrict__ b, long long n
   }
 }
 
-__global__ void reset_sumsq_kernel(OptState *st) {
-  pdl_sync();
-  st->sumsq = 0.f;
-}
-
 }  // namespace msr3d
 
 using namespace msr3d;
 
-/* state: 8 floats on the device {sumsq, step, lr, beta1, beta2, eps, weight_decay, max_norm};
+/* state: MSR3D_OPT_STATE_FLOATS floats on the device {sumsq, step, lr, beta1, beta2, eps, weight_decay, max_norm,
+ * then one scratch float per block of the norm reduction};
  * ticket: one zero-initialised uint32 on the device. */
 MSR3D_API int msr3d_adamw_clip_step_f32(float *params, const float *grads, float *exp_avg,
-                                        float *exp_avg_sq, long long n, long long n_decay,
-                                        float grad_scale, float *state, unsigned int *ticket,
+                                        float *exp_avg_sq, long long n, long long decay_begin,
+                                        long long decay_end, float grad_scale, float *state, unsigned int *ticket,
                                         unsigned long long *seed_counter, msr3d_stream_t stream) {
   MSR3D_REQUIRE(params && grads && exp_avg && exp_avg_sq && state && ticket, "adamw: null pointer");
-  MSR3D_REQUIRE(n >= 0 && n_decay >= 0 && n_decay <= n, "adamw: bad sizes");
+  MSR3D_REQUIRE(n >= 0 && decay_begin >= 0 && decay_begin <= decay_end && decay_end <= n, "adamw: bad sizes");
   if (n == 0) return MSR3D_OK;
   cudaStream_t s = (cudaStream_t)stream;
   OptState *st = reinterpret_cast<OptState *>(state);
   int grid = (int)((n + 255) / 256);
-  if (grid > kNumSMs * 4) grid = kNumSMs * 4;
-  launch_pdl(reset_sumsq_kernel, dim3(1), dim3(1), 0, s, st);
-  int rc = check_launch("reset_sumsq");
-  if (rc) return rc;
+  if (grid > kSumsqBlocks) grid = kSumsqBlocks;
+  int rc;
   launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, s, grads, n, grad_scale, st, ticket, seed_counter);
   rc = check_launch("sumsq");
   if (rc) return rc;
-  launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq, n, n_decay, grad_scale, st);
+  launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq, n, decay_begin, decay_end, grad_scale, st);
   return check_launch("adamw");
 }
 

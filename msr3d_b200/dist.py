@@ -43,6 +43,37 @@ def flat_order(names: Sequence[str], num_layers: int) -> Tuple[List[str], List[s
     return order_w, order_b, order_u
 
 
+def is_late(name: str) -> bool:
+    """Parameters whose gradient is complete only at the very end of the backward pass: layer 0 of the
+    spatial encoder and everything in front of it (projection, location / size encoders, embeddings)."""
+    return (not name.startswith("spatial_encoder.")) or name.startswith("spatial_encoder.0.")
+
+
+def flat_layout(names: Sequence[str], numel: Dict[str, int], num_layers: int) -> dict:
+    """Layout of the flat parameter / gradient buffers:
+
+        [ late biases | late weights | early weights | early biases | never-used ]
+
+    so that (a) weight decay applies to ONE range, (b) the gradients that the backward pass finishes
+    first (layers >= 1: "early") are ONE contiguous bucket whose all-reduce can run under the backward
+    of layer 0, and the rest ("late") is one more, (c) the QKV+cond projections of a layer stay adjacent.
+    Returns order, offs, total and the element boundaries decay=(d0,d1), late=(0,e0), early=(e0,n_opt)."""
+    w, b, u = flat_order(names, num_layers)
+    b_late, b_early = [n for n in b if is_late(n)], [n for n in b if not is_late(n)]
+    w_late, w_early = [n for n in w if is_late(n)], [n for n in w if not is_late(n)]
+    order = b_late + w_late + w_early + b_early + u
+    offs, total = flat_offsets(order, numel)
+
+    def start(group, default):
+        return offs[group[0]] if group else default
+    n_opt = start(u, total)
+    e1 = start(b_early, n_opt)           # end of the decayed range
+    e0 = start(w_early, e1)              # start of the early bucket
+    d0 = start(w_late, e0)
+    return {"order": order, "offs": offs, "total": total, "decay": (d0, e1), "late": (0, e0), "early": (e0, n_opt),
+            "n_opt": n_opt}
+
+
 def flat_offsets(order: Sequence[str], numel: Dict[str, int], align: int = 4) -> Tuple[Dict[str, int], int]:
     """Element offsets of each tensor (starts aligned to 16 B) and the total length."""
     offs, off = {}, 0

@@ -60,7 +60,7 @@ _C.register_protos({
                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_colsum_add_f32": [c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "msr3d_dropout_mask_f32": [c_ull, c_vp, c_float, c_uint, c_ll, c_vp, c_vp],
-    "msr3d_adamw_clip_step_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp],
+    "msr3d_adamw_clip_step_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp],
     "msr3d_dot_f32": [c_vp, c_vp, c_ll, c_vp, c_vp],
 })
 
@@ -119,8 +119,11 @@ class FusedPrompter:
         self.m = torch.zeros_like(self.flat_p[:self.n_opt])
         self.v = torch.zeros_like(self.flat_p[:self.n_opt])
         # {sumsq, step, lr, beta1, beta2, eps, weight_decay, max_norm}
-        self.opt_state = torch.tensor([0.0, 0.0, lr, betas[0], betas[1], eps, weight_decay,
-                                       grad_norm if grad_norm else 0.0], dtype=torch.float32, device=dev)
+        # {sumsq, step, lr, beta1, beta2, eps, weight_decay, max_norm} + scratch of the norm reduction
+        # (MSR3D_OPT_STATE_FLOATS in include/msr3d_b200.h)
+        self.opt_state = torch.zeros(8 + 4 * 148, dtype=torch.float32, device=dev)
+        self.opt_state[:8] = torch.tensor([0.0, 0.0, lr, betas[0], betas[1], eps, weight_decay,
+                                           grad_norm if grad_norm else 0.0])
         self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         self.loss_buf = torch.zeros(2, dtype=torch.float32, device=dev)   # double-buffered (async read-back)
         self._loss_i = 0
@@ -138,6 +141,10 @@ class FusedPrompter:
         self.enc_stream = torch.cuda.Stream(device=dev)
         self.use_side = True
         self.wgrad_small = True
+        # data parallel: all-reduce the gradients of layers >= 1 under the backward of layer 0 (two buckets)
+        # instead of one collective after the backward.  A/B: MSR3D_DDP_BUCKETS=0/1
+        import os as _os
+        self.ddp_buckets = _os.environ.get("MSR3D_DDP_BUCKETS", "1") == "1"
         self._side_pending = [False, False]
 
     # ------------------------------------------------------------------ parameters
@@ -145,11 +152,12 @@ class FusedPrompter:
         from . import dist as _dist
         named = [(n, p) for n, p in self.model.named_parameters() if p.requires_grad]
         by_name = dict(named)
-        order_w, order_b, order_u = _dist.flat_order([n for n, _ in named], self.nl)
-        self.order = order_w + order_b + order_u
-        offs, total = _dist.flat_offsets(self.order, {n: p.numel() for n, p in named})
-        self.n_decay = offs[order_b[0]] if order_b else total
-        self.n_opt = offs[order_u[0]] if order_u else total
+        lay = _dist.flat_layout([n for n, _ in named], {n: p.numel() for n, p in named}, self.nl)
+        self.order, offs, total = lay["order"], lay["offs"], lay["total"]
+        self.decay_range = lay["decay"]          # [d0, d1): weights (decayed)
+        self.bucket_early = lay["early"]         # gradients of layers >= 1: complete before layer 0's backward
+        self.bucket_late = lay["late"]
+        self.n_opt = lay["n_opt"]
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=self.dev)
         self.flat_g = torch.zeros(total, dtype=torch.float32, device=self.dev)
         self.offs = offs
@@ -342,6 +350,10 @@ class FusedPrompter:
         dy3 = ptr(w["upstream"])
         bwd.append(("memset", None, (w["arena_b"],), None, False))
         for i in reversed(range(nl)):
+            if i == 0:
+                # everything below contributes to the LATE gradient bucket only (dist.flat_layout): the
+                # gradients of layers >= 1 are final once the side streams have been joined here
+                self.bwd_split = len(bwd)
             pre = f"spatial_encoder.{i}."
             sa = pre + "self_attn."
             s0 = i * 8
@@ -500,9 +512,15 @@ class FusedPrompter:
         self.stage_scene(batch, upstream)
         self._primed = True
 
-    def _pipelined_body(self, with_encoder=True, slot=0, depth2=False):
+    def _pipelined_body(self, with_encoder=True, slot=0, depth2=False, part=0):
+        """part 0: the whole step.  Parts 1 / 2 (data-parallel runs): everything up to the point where the
+        early gradient bucket is final / the rest of the backward — the all-reduce of the early bucket is
+        issued between them and overlaps part 2."""
         w = self.ws
         main = torch.cuda.current_stream()
+        if part == 2:
+            self._run(self.bwd_prog[self.bwd_split:])
+            return
         for k in ("obj_locs", "obj_masks", "anchor_locs", "anchor_ori", "upstream"):
             w[k].copy_(w[k + "_n"])
             if depth2:
@@ -516,9 +534,12 @@ class FusedPrompter:
         torch.logical_not(w["obj_masks"], out=w["key_pad"].view(torch.bool))
         self._run(self.pre_prog)
         self._run(self.fwd_prog)
-        self.backward()
-        if self.world_size == 1:
-            self.optimizer_step()
+        if part == 1:
+            self._run(self.bwd_prog[:self.bwd_split] + [("join", None, (), None, False)])
+        else:
+            self.backward()
+            if self.world_size == 1:
+                self.optimizer_step()
         if with_encoder:
             main.wait_stream(self.enc_stream)  # join
 
@@ -595,14 +616,36 @@ class FusedPrompter:
         main = torch.cuda.current_stream()
         if flush != 2:
             main.wait_event(self._copied[slot])
-        if self.graph_prefetch[slot] is not None and not flush:
-            self.graph_prefetch[slot].replay()
+        graphed = self.graph_prefetch[slot] is not None and not flush
+        if self.world_size == 1 or not self.ddp_buckets:
+            if graphed:
+                self.graph_prefetch[slot].replay()
+            else:
+                self._pipelined_body(with_encoder=flush != 2, slot=slot, depth2=True)
+            self._slot_free[slot].record(main)
+            if self.world_size > 1:
+                from . import dist as _dist
+                _dist.allreduce_sum_(self.flat_g[:self.n_opt])
+                self.optimizer_step()
         else:
-            self._pipelined_body(with_encoder=flush != 2, slot=slot, depth2=True)
-        self._slot_free[slot].record(main)
-        if self.world_size > 1:
-            from . import dist as _dist
-            _dist.allreduce_sum_(self.flat_g[:self.n_opt])
+            # two gradient buckets: layers >= 1 are reduced while layer 0 (and the input encoders) are
+            # still in their backward pass; the optimiser waits for both collectives on the device
+            import torch.distributed as dist
+            (e0, e1), (l0, l1) = self.bucket_early, self.bucket_late
+            if graphed:
+                self.graph_prefetch[slot].replay()
+            else:
+                self._pipelined_body(with_encoder=flush != 2, slot=slot, depth2=True, part=1)
+            self._slot_free[slot].record(main)
+            w_early = dist.all_reduce(self.flat_g[e0:e1], async_op=True) if e1 > e0 else None
+            if graphed:
+                self.graph_prefetch_tail.replay()
+            else:
+                self._pipelined_body(part=2)
+            w_late = dist.all_reduce(self.flat_g[l0:l1], async_op=True)
+            if w_early is not None:
+                w_early.wait()
+            w_late.wait()
             self.optimizer_step()
         B, L = self.ws["obj_locs"].shape[:2]
         return self.ws["tokens"].view(B, L, H)
@@ -625,8 +668,13 @@ class FusedPrompter:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self.hi_stream, capture_error_mode="thread_local"):
-                self._pipelined_body(slot=slot, depth2=True)
+                self._pipelined_body(slot=slot, depth2=True, part=1 if (self.world_size > 1 and self.ddp_buckets) else 0)
             self.graph_prefetch[slot] = g
+        if self.world_size > 1 and self.ddp_buckets:      # the rest of the backward (same for both slots)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.hi_stream, capture_error_mode="thread_local"):
+                self._pipelined_body(part=2)
+            self.graph_prefetch_tail = g
         for dst, src in zip((self.flat_p, self.m, self.v, self.opt_state, self.seed_counter, w["emb"], w["emb_next"]), saved):
             dst.copy_(src)
         for k in keys:
@@ -648,9 +696,9 @@ class FusedPrompter:
         self._run(self.bwd_prog)
 
     def optimizer_step(self):
-        n, nd = self.n_opt, self.n_decay
+        n, (d0, d1) = self.n_opt, self.decay_range
         _C.call("msr3d_adamw_clip_step_f32", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(),
-                self.v.data_ptr(), n, nd, 1.0 / self.world_size, self.opt_state.data_ptr(),
+                self.v.data_ptr(), n, d0, d1, 1.0 / self.world_size, self.opt_state.data_ptr(),
                 self.ticket.data_ptr(), self.seed_counter.data_ptr(), torch.cuda.current_stream().cuda_stream)
 
     def set_lr(self, lr: float):

@@ -95,3 +95,27 @@ def test_flat_layout_groups_attention_projections(sd_spec):
     # QKV+cond weights are one contiguous (816 x 256) block
     assert offs[w[3]] + numel[w[3]] - offs[w[0]] == 816 * 256
     assert sorted(w + b + u) == sorted(names)
+
+
+def test_flat_layout_buckets_and_decay_range(sd_spec):
+    """[late biases | late weights | early weights | early biases | never-used]: one decayed range, the
+    gradients of layers >= 1 in one contiguous bucket (reduced under the backward of layer 0)."""
+    names = [k for k, _, _ in sd_spec if not k.startswith("obj_encoder.") and k != "anchor_size"
+             and "running" not in k and "num_batches" not in k]
+    numel = {k: int(torch.tensor(s).prod()) for k, s, _ in sd_spec}
+    lay = mdist.flat_layout(names, numel, 3)
+    offs, (d0, d1), (l0, l1), (e0, e1) = lay["offs"], lay["decay"], lay["late"], lay["early"]
+    assert sorted(lay["order"]) == sorted(names)
+    assert l0 == 0 and l1 == e0 and e1 == lay["n_opt"] and 0 < d0 < e0 < d1 < e1 < lay["total"]
+    for n in names:
+        if n.startswith(mdist.UNUSED_IN_SHIPPED_MODE):
+            assert offs[n] >= lay["n_opt"], n
+            continue
+        decayed = d0 <= offs[n] < d1
+        assert decayed == ("bias" not in n), n                        # optim/utils.py:1-18
+        early = e0 <= offs[n] < e1
+        assert early == (n.startswith("spatial_encoder.") and not n.startswith("spatial_encoder.0.")), n
+    # QKV+cond weights of every layer are still one contiguous (816 x 256) block
+    for i in range(3):
+        pre = f"spatial_encoder.{i}.self_attn."
+        assert offs[pre + "lang_cond_fc.weight"] + numel[pre + "lang_cond_fc.weight"] - offs[pre + "w_qs.weight"] == 816 * 256

@@ -145,7 +145,10 @@ def test_fused_adamw_matches_torch(sd_spec):
     batch = synthetic.make_batch(B, O, P, seed=seed).to("cuda")
     up = torch.randn(B, O, 256, generator=torch.Generator().manual_seed(1)).cuda()
     ref_p = eng.flat_p[:eng.n_opt].clone()
-    decay, nodecay = ref_p[:eng.n_decay].clone().requires_grad_(True), ref_p[eng.n_decay:].clone().requires_grad_(True)
+    d0, d1 = eng.decay_range                                   # [late biases | WEIGHTS | early biases]
+    is_decayed = torch.zeros(eng.n_opt, dtype=torch.bool, device="cuda")
+    is_decayed[d0:d1] = True
+    decay, nodecay = ref_p[is_decayed].clone().requires_grad_(True), ref_p[~is_decayed].clone().requires_grad_(True)
     opt = torch.optim.AdamW([{"params": [decay], "weight_decay": 0.05}, {"params": [nodecay], "weight_decay": 0.0}],
                             lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
     for step in range(3):
@@ -154,12 +157,13 @@ def test_fused_adamw_matches_torch(sd_spec):
         eng.forward(); eng.backward()
         g = eng.flat_g[:eng.n_opt].clone()
         coef = torch.clamp(0.5 / (g.norm() + 1e-6), max=1.0)
-        decay.grad, nodecay.grad = (g[:eng.n_decay] * coef), (g[eng.n_decay:] * coef)
+        decay.grad, nodecay.grad = (g[is_decayed] * coef), (g[~is_decayed] * coef)
         opt.step()
         eng.optimizer_step()
         torch.cuda.synchronize()
         got = eng.flat_p[:eng.n_opt]
-        want = torch.cat([decay.detach(), nodecay.detach()])
+        want = torch.empty_like(got)
+        want[is_decayed], want[~is_decayed] = decay.detach(), nodecay.detach()
         assert float((got - want).abs().max()) < 2e-6, step
     assert float(eng.opt_state[1]) == 3.0                     # device-side step counter
     unused = eng.flat_p[eng.n_opt:]

@@ -1,0 +1,52 @@
+"""Run under torchrun on >= 2 GPUs: the bucketed, overlapped gradient exchange of the prefetch schedule gives the
+same parameter trajectory as the sequential schedule with one all-reduce after the backward.
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_ddp_equiv.py"""
+import datetime
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from msr3d_b200 import synthetic  # noqa: E402
+from msr3d_b200.train import HotPathTrainer  # noqa: E402
+from tests import helpers  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+B, O, P, seed = 2, 12, 512, 21
+batches = [synthetic.make_batch(B, O, P, seed=seed + 10 * rank + i).to(dev) for i in range(4)]   # different data per rank
+ups = [torch.randn(B, O, 256, generator=torch.Generator().manual_seed(i)).to(dev) for i in range(4)]
+res = {}
+for mode in ("sequential", "prefetch_graph", "prefetch_eager"):
+    model = helpers.build_prompter(seed, device=dev)          # eval mode: no dropout
+    pipe = False if mode == "sequential" else "prefetch"
+    tr = HotPathTrainer(model, B, O, P, lr=1e-4, world_size=world, use_graph=mode != "prefetch_eager", pipeline=pipe)
+    if mode == "sequential":
+        for b, u in zip(batches, ups):
+            tr.step(b, u)
+    else:
+        tr.engine.prime2(batches[0], ups[0], batches[1], ups[1])
+        if tr.use_graph:
+            tr.engine.capture_prefetch()
+        tr._calls = 2
+        for b, u in zip(batches[2:], ups[2:]):
+            tr.step(b, u)
+        tr.flush()
+    torch.cuda.synchronize()
+    res[mode] = tr.engine.flat_p.clone()
+    # replicas stay identical
+    ref = res[mode].clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(ref, res[mode]), f"{mode}: replicas diverged on rank {rank}"
+for mode in ("prefetch_graph", "prefetch_eager"):
+    e = helpers.rel_err(res[mode], res["sequential"])
+    if rank == 0:
+        print(f"{mode} vs sequential: rel err {e:.2e}")
+    assert e < 5e-4, (mode, e)
+if rank == 0:
+    print("ddp equivalence ok")
+dist.destroy_process_group()
