@@ -21,10 +21,24 @@ sumsq_kernel(const float *__restrict__ g, long long n, float grad_scale, OptStat
              unsigned int *ticket, unsigned long long *seed_counter) {
   pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   float s = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const float v = g[i] * grad_scale;
-    s += v * v;
+  const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {   // 16 B loads; the tail (n % 4) goes to the scalar loop below
+    const float4 *g4 = reinterpret_cast<const float4 *>(g);
+    const long long n4 = n >> 2;
+    for (long long i = tid0; i < n4; i += nthr) {
+      const float4 q = g4[i];
+      const float a = q.x * grad_scale, b = q.y * grad_scale, c = q.z * grad_scale, d = q.w * grad_scale;
+      s += (a * a + b * b) + (c * c + d * d);
+    }
+    for (long long i = (n4 << 2) + tid0; i < n; i += nthr) {
+      const float v = g[i] * grad_scale;
+      s += v * v;
+    }
+  } else {
+    for (long long i = tid0; i < n; i += nthr) {
+      const float v = g[i] * grad_scale;
+      s += v * v;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -99,7 +113,17 @@ __global__ void __launch_bounds__(1024)
 dot_kernel(const float *__restrict__ a, const float *__restrict__ b, long long n, float *__restrict__ out) {
   pdl_sync();
   float s = 0.f;
-  for (long long i = threadIdx.x; i < n; i += 1024) s += a[i] * b[i];
+  if (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) {
+    const float4 *a4 = reinterpret_cast<const float4 *>(a), *b4 = reinterpret_cast<const float4 *>(b);
+    const long long n4 = n >> 2;
+    for (long long i = threadIdx.x; i < n4; i += 1024) {
+      const float4 x = a4[i], y = b4[i];
+      s += (x.x * y.x + x.y * y.y) + (x.z * y.z + x.w * y.w);
+    }
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += 1024) s += a[i] * b[i];
+  } else {
+    for (long long i = threadIdx.x; i < n; i += 1024) s += a[i] * b[i];
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   __shared__ float w[32];
