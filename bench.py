@@ -227,10 +227,13 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 (NCCL prints its
+    # version banner there when the first communicator is created) are sent to stderr until the line is printed
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import datetime
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"     # NCCL prints its version banner on STDOUT: keep stdout = the JSON line
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     ops.DEFAULT_SPLIT = 3 if args.split == 6 else args.split
     B, O, P = synthetic.CONFIGS[args.config]
@@ -330,7 +333,9 @@ def main():
             line["cpu_baseline"] = cpu_baseline(args)
         if world == 1:
             line["next_rows"] = {"scene_splice (SURVEY 8f-1)": bench_splice(dev, B, O, flush, os.cpu_count() or 1)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
