@@ -23,7 +23,9 @@
  *   - the caller owns every buffer (the reference allocates with torch::zeros);
  *     entry points that need zero-initialised outputs do the memset themselves;
  *   - errors come back as status codes (cuda_utils.h:30-39 calls exit(-1));
- *   - furthest_point_sampling needs no `temp` scratch (kept in registers).
+ *   - furthest_point_sampling needs no `temp` scratch (kept in registers);
+ *   - gather_points_grad / group_points_grad are deterministic (atomic-free segmented reductions; the
+ *     reference kernels use atomicAdd) whenever one cloud's index table fits in shared memory.
  */
 #ifndef MSR3D_B200_H
 #define MSR3D_B200_H

@@ -334,6 +334,103 @@ index_scatter_add_kernel(const float *__restrict__ grad_out, const int32_t *__re
   }
 }
 
+// Deterministic, atomic-free form of the two scatter-add gradients:
+//   grad_points[b, c, n] = sum over { q : idx[b, q] == n } of grad_out[b, c, q],  q ascending.
+// A CTA owns one cloud (and a slice of the channels).  It inverts idx[b, :] into a CSR in shared memory
+// with a STABLE counting sort — counts by shared-memory atomics, an exclusive block scan, then one
+// warp walks q in order, 32 at a time, and ranks equal keys inside a chunk with __match_any_sync — and
+// then every (channel, point) pair adds up its segment in a fixed order.  No global atomics, no
+// zero-fill (every output element is written), run-to-run bit-identical; the reference kernels
+// (group_points_gpu.cu:43-75, sampling_gpu.cu:34-57) and the fallback above use atomicAdd.
+constexpr int kSegThreads = 256;
+__global__ void __launch_bounds__(kSegThreads)
+index_segment_sum_kernel(const float *__restrict__ grad_out, const int32_t *__restrict__ idx,
+                         float *__restrict__ grad_points, int C, int N, int Q, int c_per_cta) {
+  pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
+  extern __shared__ int seg_sm[];
+  int *start = seg_sm;            // [N + 1] exclusive prefix of the bin sizes
+  int *cursor = start + N + 1;    // [N]     counts, then fill cursors
+  int *entry = cursor + N;        // [Q]     q values grouped by bin, ascending inside a bin
+  __shared__ int s_warp[kSegThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const int32_t *ib = idx + (size_t)b * Q;
+  for (int n = tid; n < N; n += kSegThreads) cursor[n] = 0;
+  __syncthreads();
+  for (int q = tid; q < Q; q += kSegThreads) atomicAdd(&cursor[ib[q]], 1);
+  __syncthreads();
+  // exclusive scan over N bins: a contiguous slab per thread, then a block scan of the slab totals
+  const int per = (N + kSegThreads - 1) / kSegThreads;
+  const int n0 = min(N, tid * per), n1 = min(N, n0 + per);
+  int tot = 0;
+  for (int n = n0; n < n1; ++n) tot += cursor[n];
+  int incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < warp; ++w) base += s_warp[w];
+  int run = base + incl - tot;
+  for (int n = n0; n < n1; ++n) {
+    start[n] = run;
+    run += cursor[n];
+    cursor[n] = 0;
+  }
+  if (tid == kSegThreads - 1) start[N] = run;
+  __syncthreads();
+  if (warp == 0) {   // stable fill: chunks of 32 consecutive q, equal keys ranked by lane
+    for (int q0 = 0; q0 < Q; q0 += 32) {
+      const int q = q0 + lane;
+      const bool ok = q < Q;
+      const int key = ok ? ib[q] : -1 - lane;                  // distinct dummies for the tail
+      const unsigned m = __match_any_sync(0xffffffffu, key);
+      const int rank = __popc(m & ((1u << lane) - 1u));
+      const int leader = __ffs(m) - 1;
+      int pos = 0;
+      if (ok && lane == leader) {
+        pos = cursor[key];
+        cursor[key] = pos + __popc(m);
+      }
+      pos = __shfl_sync(0xffffffffu, pos, leader);
+      if (ok) entry[start[key] + pos + rank] = q;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  const int c0 = blockIdx.y * c_per_cta, c1 = min(C, c0 + c_per_cta);
+  for (int i = tid; i < (c1 - c0) * N; i += kSegThreads) {
+    const int c = c0 + i / N, n = i % N;
+    const float *g = grad_out + ((size_t)b * C + c) * Q;
+    float acc = 0.f;
+    for (int e = start[n]; e < start[n + 1]; ++e) acc += g[entry[e]];
+    grad_points[((size_t)b * C + c) * N + n] = acc;
+  }
+}
+
+// shared launcher of the two gradients; returns -1 when the CSR does not fit (caller falls back to atomics)
+static int launch_segment_sum(const float *grad_out, const int32_t *idx, float *grad_points, int B, int C, int N, int Q,
+                              cudaStream_t stream) {
+  const size_t smem = ((size_t)2 * N + 1 + Q) * sizeof(int);
+  if (smem > 96 * 1024 || B > 65535 * 32) return -1;
+  static bool configured = false;
+  if (!configured) {
+    MSR3D_CUDA(cudaFuncSetAttribute(index_segment_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  // enough CTAs to fill the GPU: split the channels when there are few clouds
+  int csplit = B >= 2 * kNumSMs ? 1 : ceil_div(2 * kNumSMs, B);
+  if (csplit > C) csplit = C;
+  if (csplit > 65535) csplit = 65535;
+  const int c_per_cta = ceil_div(C, csplit);
+  launch_pdl(index_segment_sum_kernel, dim3(B, ceil_div(C, c_per_cta)), dim3(kSegThreads), smem, stream, grad_out, idx,
+             grad_points, C, N, Q, c_per_cta);
+  return check_launch("index_segment_sum");
+}
+
 static int flat_grid(size_t total) {
   size_t g = (total + 255) / 256;
   const size_t cap = (size_t)kNumSMs * 16;
@@ -450,6 +547,10 @@ MSR3D_API int msr3d_gather_points_grad_f32(const float *grad_out, const int32_t 
   MSR3D_REQUIRE(grad_out && idx && grad_points, "gather_points_grad: null pointer");
   MSR3D_REQUIRE(B >= 0 && C >= 0 && N >= 1 && M >= 0, "gather_points_grad: bad sizes");
   if ((size_t)B * C * N == 0) return MSR3D_OK;
+  if (M > 0 && !g_tune[TUNE_GRAD_ATOMICS]) {   // deterministic segmented reduce when the CSR fits in shared memory
+    const int rc = launch_segment_sum(grad_out, idx, grad_points, B, C, N, M, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
+  }
   MSR3D_CUDA(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)B * C * N,
                              (cudaStream_t)stream));
   const size_t total = (size_t)B * C * M;
@@ -520,6 +621,10 @@ MSR3D_API int msr3d_group_points_grad_f32(const float *grad_out, const int32_t *
   MSR3D_REQUIRE(B >= 0 && C >= 0 && N >= 1 && npoint >= 0 && nsample >= 0,
                 "group_points_grad: bad sizes");
   if ((size_t)B * C * N == 0) return MSR3D_OK;
+  if ((size_t)npoint * nsample > 0 && !g_tune[TUNE_GRAD_ATOMICS]) {
+    const int rc = launch_segment_sum(grad_out, idx, grad_points, B, C, N, npoint * nsample, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
+  }
   MSR3D_CUDA(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)B * C * N,
                              (cudaStream_t)stream));
   const size_t total = (size_t)B * C * npoint * nsample;

@@ -111,6 +111,30 @@ def test_gather_group_and_grads(ext, ref):
         assert torch.equal(ext.gather_points(pts.cuda(), idx2.cuda()), ref.gather_points(pts.cuda(), idx2.cuda()))
 
 
+@pytest.mark.parametrize("B,C,N,P,S", [(240, 3, 1024, 32, 32), (6, 131, 32, 16, 32), (2, 7, 33, 5, 3), (1, 1, 1, 9, 4)])
+def test_scatter_grads_are_deterministic_segmented_reductions(ext, B, C, N, P, S):
+    """group_points_grad / gather_points_grad are atomic-free (stable counting sort into a shared-memory CSR,
+    fixed summation order): bit-identical run to run, exact against a float64 reference rounded once where the
+    segments are short, and correct under heavy collisions (every index equal — the padded-ball case)."""
+    g = torch.Generator().manual_seed(B * 31 + N)
+    idx3 = torch.randint(0, N, (B, P, S), generator=g, dtype=torch.int32)
+    idx3[0] = idx3[0, 0, 0]                                   # one cloud where all P*S samples hit the same point
+    idx2 = torch.randint(0, N, (B, P), generator=g, dtype=torch.int32)
+    go3 = torch.randn(B, C, P, S, generator=g)
+    go2 = torch.randn(B, C, P, generator=g)
+    a = ext.group_points_grad(go3.cuda(), idx3.cuda(), N)
+    b = ext.group_points_grad(go3.cuda(), idx3.cuda(), N)
+    assert torch.equal(a, b)
+    want = torch.zeros(B, C, N, dtype=torch.float64)
+    want.scatter_add_(2, idx3.view(B, 1, P * S).expand(-1, C, -1).long(), go3.view(B, C, P * S).double())
+    torch.testing.assert_close(a.cpu().double(), want, rtol=1e-5, atol=1e-5)
+    c = ext.gather_points_grad(go2.cuda(), idx2.cuda(), N)
+    assert torch.equal(c, ext.gather_points_grad(go2.cuda(), idx2.cuda(), N))
+    want2 = torch.zeros(B, C, N, dtype=torch.float64)
+    want2.scatter_add_(2, idx2.view(B, 1, P).expand(-1, C, -1).long(), go2.double())
+    torch.testing.assert_close(c.cpu().double(), want2, rtol=1e-5, atol=1e-5)
+
+
 def test_three_nn_and_interpolate(ext, ref):
     g = torch.Generator().manual_seed(13)
     B, n, m, c = 2, 150, 40, 6
