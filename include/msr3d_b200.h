@@ -183,6 +183,18 @@ int msr3d_scene_rows_i64(const int64_t *input_ids, int B, int T, long long sp_to
  * gradient that belongs to the scene tokens.  dtype 0 f32, 1 f16, 2 bf16; ld in elements. */
 int msr3d_splice_gather_grad(const void *d_embeds, int dtype, long long ld, const int32_t *rows, int M,
                              int D, float *dY, msr3d_stream_t stream);
+/* ------------------------------------------------------------------ group F
+ * Per-object point-cloud preprocessing on the device (the CPU work in front of the path):
+ * MSR3DDataset.preprocess_pcd, data/datasets/msr3d.py:181-215, + the padding of dataset_wrapper.py:151-158.
+ * points (total, 6) = xyz + rgb of all objects back to back; offsets (n_obj + 1) int32; sample_idx (n_obj, P)
+ * indices INSIDE each object (np.random.choice stays on the host); rot = 9 floats, row-major 3x3
+ * (build_rotate_mat) or NULL.  Per object: xyz = xyz @ rot^T; obj_locs = [mean, max - min] over ALL its points;
+ * the P sampled points are centred on their own mean and divided by their largest norm (1 if < 1e-6).
+ * Slots n_obj .. o_max-1 are padding: points of ones, zero location, mask 0.
+ * Outputs obj_fts (o_max, P, 6), obj_locs (o_max, 6), obj_masks (o_max) bytes. */
+int msr3d_preprocess_objects_f32(const float *points, const int32_t *offsets, const int32_t *sample_idx,
+                                 const float *rot, int n_obj, int o_max, int P, float *obj_fts,
+                                 float *obj_locs, uint8_t *obj_masks, msr3d_stream_t stream);
 /* FPS + centre gather + ball query of one SA level (pointnet2_modules.py:54-58,
  * pointnet2_utils.py:331).  xyz: (B,N,ld) records whose first 3 floats are the
  * coordinates.  Outputs fps_idx (B,m) i32, new_xyz (B,m,3), ball_idx (B,m,nsample) i32. */

@@ -117,3 +117,19 @@ def test_scene_splice_matches_reference(golden_dir, case):
     for name, t in (("dW", W), ("db", b), ("dtokens", tok)):
         ref = fx[f"{case}:{name}"]
         assert np.abs(t.grad.numpy() - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-6), name
+
+
+@pytest.mark.parametrize("case", ["train", "val"])
+def test_preprocess_objects_matches_reference(golden_dir, case):
+    """oracle.preprocess_objects vs the unmodified reference preprocess_pcd + padding (msr3d.py:181-215)."""
+    from oracle import data_oracle
+    fx = _load(golden_dir, "preprocess")
+    g = lambda k: fx[f"{case}:{k}"]  # noqa: E731
+    rot = g("rot") if bool(g("has_rot")) else None
+    fts, locs, masks = data_oracle.preprocess_objects(g("points"), g("offsets"), g("sample_idx"), rot,
+                                                      g("obj_fts").shape[0])
+    np.testing.assert_array_equal(fts, g("obj_fts"))          # same numpy operations in the same order: exact
+    np.testing.assert_array_equal(locs, g("obj_locs"))
+    np.testing.assert_array_equal(masks, g("obj_masks"))
+    # the degenerate object (all points equal) is left unscaled, the padding rows are ones / zeros / False
+    assert np.all(fts[~masks] == 1.0) and np.all(locs[~masks] == 0.0)

@@ -49,3 +49,11 @@ def test_oracle_splice_edge_cases():
     assert torch.allclose(out[0, 4], want[0, 0]) and torch.allclose(out[1, 0], want[1, 0])
     assert bool(m[0, 4]) is True and bool(m[1, 0]) is False
     assert torch.equal(out[0, :4], emb[0, :4]) and torch.equal(out[1, 1:], emb[1, 1:])
+
+
+def test_data_preprocess_rejects_cpu_tensors_and_packs_objects():
+    from msr3d_b200 import data
+    pts, offs = data.pack_objects([torch.zeros(5, 6), torch.ones(3, 6)])
+    assert pts.shape == (8, 6) and offs.tolist() == [0, 5, 8] and offs.dtype == torch.int32
+    with pytest.raises(RuntimeError, match="CUDA"):
+        data.preprocess_objects(pts, offs, torch.zeros(2, 4, dtype=torch.int32), None, 2)
