@@ -3,6 +3,9 @@ spatial-attention transformer) behind the reference's module / extension API.
 
     from msr3d_b200 import OSE3DSituation, PcdObjEncoder      # drop-in nn.Modules
     import msr3d_b200.compat as compat; compat.install_ext()   # serve `pointnet2._ext`
+    from msr3d_b200.splice import splice_scene_tokens           # llm_proj + scatter into the LLM input (msr3d.py:277-287)
+    from msr3d_b200.data import preprocess_objects              # per-object preprocessing on the device (msr3d.py:181-215)
+    from msr3d_b200.train import HotPathTrainer                 # fused, graph-replayed, pipelined training step
 
 The compute runs in hand-written sm_100a kernels (msr3d_b200/csrc) reached through the C ABI
 of include/msr3d_b200.h; importing this package never loads the oracle and never falls back to

@@ -1,7 +1,7 @@
 """Fused execution engine for the trainable half of the MSR3D prompter.
 
 `FusedPrompter` takes a (drop-in) `OSE3DSituation` and runs its forward, backward and optimiser
-step as a fixed program of ~85 launches of this repo's kernels (tensor-core GEMMs from
+step as a fixed program of ~95 launches of this repo's kernels (tensor-core GEMMs from
 csrc/linear_tc.cu, everything else from csrc/spatial.cu, csrc/optim.cu, and the fused PointNet++
 encoder), optionally replayed as ONE CUDA graph per step.  It replaces what the reference does
 with ~500 ATen launches plus a host sync per layer.
