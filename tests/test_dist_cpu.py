@@ -97,6 +97,39 @@ def test_flat_layout_groups_attention_projections(sd_spec):
     assert sorted(w + b + u) == sorted(names)
 
 
+def _bucket_worker(rank, world, port, e0, n_opt, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(100 + rank)
+        flat = torch.randn(n_opt + 16, generator=g)
+        whole = flat.clone()
+        mdist.allreduce_sum_(whole[:n_opt])                     # one collective after the backward
+        w1 = dist.all_reduce(flat[e0:n_opt], async_op=True)      # early bucket, issued under layer 0's backward
+        w2 = dist.all_reduce(flat[0:e0], async_op=True)          # late bucket
+        w1.wait(); w2.wait()
+        out[rank] = (torch.equal(whole, flat), flat.clone())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_bucket_exchange_equals_single_allreduce(sd_spec):
+    """The bucketed gradient exchange of the prefetch schedule (fused.py::train_step_prefetch) covers exactly
+    [0, n_opt) and leaves the never-used tail alone."""
+    names = [k for k, _, _ in sd_spec if not k.startswith("obj_encoder.") and k != "anchor_size"
+             and "running" not in k and "num_batches" not in k]
+    numel = {k: int(torch.tensor(s).prod()) for k, s, _ in sd_spec}
+    lay = mdist.flat_layout(names, numel, 3)
+    assert lay["late"] == (0, lay["early"][0]) and lay["early"][1] == lay["n_opt"]
+    # scaled-down copy of the two ranges (the real buffer is 4.2 M floats)
+    e0, n_opt = 1000, 3000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_bucket_worker, args=(2, _free_port(), e0, n_opt, out), nprocs=2, join=True)
+    assert out[0][0] and out[1][0]
+    assert torch.equal(out[0][1][:n_opt], out[1][1][:n_opt]) and not torch.equal(out[0][1][n_opt:], out[1][1][n_opt:])
+
+
 def test_flat_layout_buckets_and_decay_range(sd_spec):
     """[late biases | late weights | early weights | early biases | never-used]: one decayed range, the
     gradients of layers >= 1 in one contiguous bucket (reduced under the backward of layer 0)."""
