@@ -375,7 +375,7 @@ class PointNetPP(nn.Module):
     @torch.no_grad()
     def forward_fused(self, pc, split: Optional[int] = None, trace: Optional[dict] = None,
                       out: Optional[torch.Tensor] = None):
-        """pc: (B', P, 6) contiguous CUDA f32 -> (B', C_out).  10 kernel launches."""
+        """pc: (B', P, 6) contiguous CUDA f32 -> (B', C_out).  11 kernel launches."""
         pk = self._packed_weights()
         Bc, P, _ = pc.shape
         dev = pc.device
