@@ -24,6 +24,14 @@ out, am = splice.splice_scene_tokens(torch.zeros(1, 40, 96, device="cuda", dtype
                                      torch.ones(1, 40, dtype=torch.long, device="cuda"), ids, tok,
                                      torch.ones(1, 8, dtype=torch.bool, device="cuda"), W, bias)
 out.float().sum().backward(); torch.cuda.synchronize(); print("splice ok", float(W.grad.abs().sum()))
+# deterministic scatter gradients (shared-memory CSR) and device-side object preprocessing
+from msr3d_b200 import ext, data
+idx3 = torch.randint(0, 33, (2, 5, 3), device="cuda", dtype=torch.int32)
+g = ext.group_points_grad(torch.randn(2, 7, 5, 3, device="cuda"), idx3, 33)
+pts = torch.randn(300, 6, device="cuda")
+fts, locs, masks = data.preprocess_objects(pts, torch.tensor([0, 100, 300], dtype=torch.int32),
+                                           torch.randint(0, 100, (2, 64), dtype=torch.int32), torch.eye(3), 4)
+torch.cuda.synchronize(); print("next rows ok", float(g.abs().sum()), float(fts.abs().sum()))
 '
 for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 20 python -c "$SCRIPT" > gpurun_out/sanitizer_$tool.log 2>&1
