@@ -13,14 +13,28 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def measured_peaks():
-    """MEASURED_PEAKS.json (driver-written) or the profiling guide's stated fallback."""
+    """MEASURED_PEAKS.json (driver-written) or the profiling guide's stated fallback.  Any surprise in the
+    file (missing keys, other spellings, unreadable) falls back instead of failing the bench."""
+    fallback = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
+    try:
         with open(path) as fh:
             p = json.load(fh)
-        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
-                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+        def pick(*names):
+            for n in names:
+                v = p.get(n)
+                if isinstance(v, (int, float)) and v > 0:
+                    return float(v)
+            return None
+        hbm = pick("hbm_gbs", "hbm_gb_s", "hbm_GBps", "hbm_bandwidth_gbs")
+        tf = pick("bf16_tflops", "bf16_tf_s", "bf16_dense_tflops")
+        if hbm is None or tf is None:
+            return fallback
+        return {"hbm_gbs": hbm, "bf16_tflops": tf,
+                "bf16_tflops_sustained": pick("bf16_tflops_sustained", "bf16_sustained_tflops") or tf, "source": "measured"}
+    except (OSError, ValueError, AttributeError):
+        return fallback
 
 
 class KernelTimer:
