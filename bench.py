@@ -329,10 +329,18 @@ def main():
         line["roofline"] = roof
         line["kernels"] = {k: {kk: (round(vv, 5) if isinstance(vv, float) else vv) for kk, vv in v.items()}
                            for k, v in table.items()}
+        # the two side measurements must never cost the bench line itself
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args)
+            try:
+                line["cpu_baseline"] = cpu_baseline(args)
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                        "sample": f"failed: {type(e).__name__}: {e}"}
         if world == 1:
-            line["next_rows"] = {"scene_splice (SURVEY 8f-1)": bench_splice(dev, B, O, flush, os.cpu_count() or 1)}
+            try:
+                line["next_rows"] = {"scene_splice (SURVEY 8f-1)": bench_splice(dev, B, O, flush, os.cpu_count() or 1)}
+            except Exception as e:  # noqa: BLE001
+                line["next_rows"] = {"error": f"{type(e).__name__}: {e}"}
         sys.stdout.flush()
         os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
