@@ -45,4 +45,4 @@ class CpuHotPath:
             for g in grads:
                 g.mul_(scale)
         self.opt.step()
-        return float(loss)
+        return float(loss.detach())
