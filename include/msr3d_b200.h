@@ -163,6 +163,32 @@ typedef struct msr3d_gemm_desc {
 int msr3d_gemm_tc_f32(const msr3d_gemm_desc *desc, msr3d_stream_t stream);
 /* sizeof(msr3d_gemm_desc) in the loaded library (a binding's struct mirror must agree). */
 int msr3d_sizeof_gemm_desc(void);
+/* Same contraction, TMA-fed: both operands are fetched by tensor-map TMA (cp.async.bulk.tensor) straight
+ * from the row-major fp32 tensors and multiplied with tcgen05.mma kind::tf32 as big/small pairs ("3xTF32":
+ * As*Bb + Ab*Bs + Ab*Bb, fp32-grade, ~2^-22 per product).  Each operand must have one unit stride
+ * (stride_ak == 1: stored [m][k]; stride_am == 1: stored [k][m] — transposes need no copy), a 16 B aligned
+ * base and a row pitch that is a multiple of 4 floats.  Subset of the descriptor: act 0; epilogue 0, 2, 3;
+ * accumulate 0 or 2; no row_map / typed output; `split` is ignored.  b_static != 0 promises that no kernel
+ * of the current step writes B (weights): its tiles are then requested before the programmatic-dependent-
+ * launch wait.  msr3d_gemm_tf32x3_supported returns 1 when a descriptor qualifies (callers fall back to
+ * msr3d_gemm_tc_f32 otherwise, e.g. the K = 63 Fourier projection).
+ * Replaces the cuBLAS calls behind nn.Linear in modules/layers/transformers.py:200-252,314-329. */
+int msr3d_gemm_tf32x3_supported(const msr3d_gemm_desc *desc);
+int msr3d_gemm_tf32x3_f32(const msr3d_gemm_desc *desc, int b_static, msr3d_stream_t stream);
+/* Fused feed-forward pair of one encoder layer (transformers.py:326-327), d_model = 256, one CTA per
+ * (128-token tile, `slice`-wide slice of the F hidden units; slice = 32 or 64, F % slice == 0):
+ *   forward :  h = dropout(gelu(y2 W1^T + b1));  f_accum += h W2^T (+ b2, added once)
+ *              also stores h and gp = gelu'(u) * mask (M x F each) for the backward pass
+ *   backward:  du = (df W2) * gp;  dy2_accum += du W1;  also stores du (M x F)
+ * The hidden tile stays in shared memory between the two tensor-core GEMMs (3xTF32, TMA-fed, see above);
+ * the per-slice partial sums of the second GEMM are reduced with red.global.add, so f_accum must be zeroed
+ * (dy2_accum: pre-filled with the residual-path gradient) by the caller.  W1 (F x 256), W2 (256 x F)
+ * row-major and 16 B aligned; dropout mask = Philox(seed (+ *seed_ptr), site, m * F + f). */
+int msr3d_ffn_pair_fwd_f32(const float *y2, const float *W1, const float *b1, const float *W2, const float *b2,
+                           int M, int F, unsigned long long seed, const unsigned long long *seed_ptr, float p,
+                           unsigned site, float *h, float *gp, float *f_accum, int slice, msr3d_stream_t stream);
+int msr3d_ffn_pair_bwd_f32(const float *df, const float *W1, const float *W2, const float *gp, int M, int F,
+                           float *du, float *dy2_accum, int slice, msr3d_stream_t stream);
 /* ------------------------------------------------------------------ group E
  * Scene-token splice into the LLM input (the step right after the path):
  * MSR3D.build_embeds, model/msr3d/msr3d.py:277-287 —
@@ -280,13 +306,16 @@ int msr3d_colsum_add_f32(const float *src, long long ld, int M, int N, float *ds
  * Global-norm clip + AdamW on one flat buffer (trainer/leo_trainer.py:192-195,
  * optim/build.py:7-17).  state: MSR3D_OPT_STATE_FLOATS device floats {sumsq, step, lr, beta1, beta2,
  * eps, weight_decay, max_norm, then scratch for the deterministic norm reduction}; ticket: one zeroed device uint32; seed_counter (nullable): device
- * uint64 incremented once per step (the dropout seed offset).  Elements [decay_begin, decay_end)
+ * uint64 incremented once per step (the dropout seed offset); extra_sumsq (nullable, ABI 3): one device float
+ * added to the squared gradient norm before the clip coefficient is formed — the squared norm (after the same
+ * grad_scale) of the trainable parameters the caller optimises elsewhere (llm_proj, LoRA ...), because the
+ * reference clips over ALL model parameters at once (accelerator.clip_grad_norm_(self.model.parameters())).  Elements [decay_begin, decay_end)
  * decay (the flat layout is [late biases | late weights | early weights | early biases], msr3d_b200/dist.py). */
 #define MSR3D_OPT_STATE_FLOATS (8 + 4 * 148)
 int msr3d_adamw_clip_step_f32(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
                               long long n, long long decay_begin, long long decay_end, float grad_scale,
                               float *state, unsigned int *ticket, unsigned long long *seed_counter,
-                              msr3d_stream_t stream);
+                              const float *extra_sumsq, msr3d_stream_t stream);
 /* out[0] = <a, b> over n floats (one CTA, fixed summation order): the scalar the training loop reads
  * back (trainer/leo_trainer.py:196-201 logs the loss every step). */
 int msr3d_dot_f32(const float *a, const float *b, long long n, float *out, msr3d_stream_t stream);

@@ -18,7 +18,7 @@ struct OptState {   // device-resident: 8 floats + one partial sum per block of 
 
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float *__restrict__ g, long long n, float grad_scale, OptState *st,
-             unsigned int *ticket, unsigned long long *seed_counter) {
+             unsigned int *ticket, unsigned long long *seed_counter, const float *__restrict__ extra_sumsq) {
   pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   float s = 0.f;
   const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
@@ -70,6 +70,10 @@ sumsq_kernel(const float *__restrict__ g, long long n, float grad_scale, OptStat
     if (threadIdx.x == 0) {
       float tot = 0.f;
       for (int i = 0; i < 8; ++i) tot += w[i];
+      // the reference clips by the norm over ALL trainable parameters of the model
+      // (accelerator.clip_grad_norm_(self.model.parameters(), ...), trainer/leo_trainer.py:192-193): the caller
+      // hands in the squared norm of whatever it optimises itself (llm_proj, LoRA, ...)
+      if (extra_sumsq != nullptr) tot += *extra_sumsq;
       st->sumsq = tot;
       st->step += 1.f;
       if (seed_counter != nullptr) *seed_counter += 1ull;  // next step draws fresh dropout masks
@@ -147,7 +151,8 @@ using namespace msr3d;
 MSR3D_API int msr3d_adamw_clip_step_f32(float *params, const float *grads, float *exp_avg,
                                         float *exp_avg_sq, long long n, long long decay_begin,
                                         long long decay_end, float grad_scale, float *state, unsigned int *ticket,
-                                        unsigned long long *seed_counter, msr3d_stream_t stream) {
+                                        unsigned long long *seed_counter, const float *extra_sumsq,
+                                        msr3d_stream_t stream) {
   MSR3D_REQUIRE(params && grads && exp_avg && exp_avg_sq && state && ticket, "adamw: null pointer");
   MSR3D_REQUIRE(n >= 0 && decay_begin >= 0 && decay_begin <= decay_end && decay_end <= n, "adamw: bad sizes");
   if (n == 0) return MSR3D_OK;
@@ -156,7 +161,7 @@ MSR3D_API int msr3d_adamw_clip_step_f32(float *params, const float *grads, float
   int grid = (int)((n + 255) / 256);
   if (grid > kSumsqBlocks) grid = kSumsqBlocks;
   int rc;
-  launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, s, grads, n, grad_scale, st, ticket, seed_counter);
+  launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, s, grads, n, grad_scale, st, ticket, seed_counter, extra_sumsq);
   rc = check_launch("sumsq");
   if (rc) return rc;
   launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq, n, decay_begin, decay_end, grad_scale, st);

@@ -18,9 +18,10 @@ UNUSED_IN_SHIPPED_MODE = ("anchor_feat", "orientation_encoder.", "loc_layers.")
 
 
 def flat_order(names: Sequence[str], num_layers: int) -> Tuple[List[str], List[str], List[str]]:
-    """Order of the trainable parameters in the flat buffers: (decayed weights, non-decayed biases,
-    never-used).  The four input projections of each attention block are adjacent so QKV+cond is a
-    single GEMM; the no-decay rule is the reference's (optim/utils.py:1-18: names containing 'bias')."""
+    """Order of the trainable parameters in the flat buffers: (weights, biases, never-used).  The four
+    input projections of each attention block are adjacent so QKV+cond is a single GEMM.  Weights and
+    biases are kept in separate ranges so that the OPT-IN no-decay rule (names containing 'bias',
+    optim/utils.py:1-18 — a helper the reference imports but never calls) is one range too."""
     names = list(names)
     order_w, order_b, order_u, taken = [], [], [], set()
     for i in range(num_layers):
@@ -49,7 +50,7 @@ def is_late(name: str) -> bool:
     return (not name.startswith("spatial_encoder.")) or name.startswith("spatial_encoder.0.")
 
 
-def flat_layout(names: Sequence[str], numel: Dict[str, int], num_layers: int) -> dict:
+def flat_layout(names: Sequence[str], numel: Dict[str, int], num_layers: int, no_decay_bias: bool = False) -> dict:
     """Layout of the flat parameter / gradient buffers:
 
         [ late biases | late weights | early weights | early biases | never-used ]
@@ -57,7 +58,12 @@ def flat_layout(names: Sequence[str], numel: Dict[str, int], num_layers: int) ->
     so that (a) weight decay applies to ONE range, (b) the gradients that the backward pass finishes
     first (layers >= 1: "early") are ONE contiguous bucket whose all-reduce can run under the backward
     of layer 0, and the rest ("late") is one more, (c) the QKV+cond projections of a layer stay adjacent.
-    Returns order, offs, total and the element boundaries decay=(d0,d1), late=(0,e0), early=(e0,n_opt)."""
+    Returns order, offs, total and the element boundaries decay=(d0,d1), late=(0,e0), early=(e0,n_opt).
+
+    decay: the reference optimises ONE uniform parameter list (MSR3D.get_opt_params,
+    model/msr3d/msr3d.py:165-172 -> AdamW(weight_decay=0.05), optim/build.py:7-17), i.e. biases and
+    LayerNorm parameters decay too: decay = (0, n_opt).  no_decay_bias=True restricts it to the weight
+    range (what optim/utils.py:no_decay_param_group would do if the reference called it)."""
     w, b, u = flat_order(names, num_layers)
     b_late, b_early = [n for n in b if is_late(n)], [n for n in b if not is_late(n)]
     w_late, w_early = [n for n in w if is_late(n)], [n for n in w if not is_late(n)]
@@ -70,8 +76,9 @@ def flat_layout(names: Sequence[str], numel: Dict[str, int], num_layers: int) ->
     e1 = start(b_early, n_opt)           # end of the decayed range
     e0 = start(w_early, e1)              # start of the early bucket
     d0 = start(w_late, e0)
-    return {"order": order, "offs": offs, "total": total, "decay": (d0, e1), "late": (0, e0), "early": (e0, n_opt),
-            "n_opt": n_opt}
+    decay = (d0, e1) if no_decay_bias else (0, n_opt)
+    return {"order": order, "offs": offs, "total": total, "decay": decay, "weights": (d0, e1), "late": (0, e0),
+            "early": (e0, n_opt), "n_opt": n_opt}
 
 
 def flat_offsets(order: Sequence[str], numel: Dict[str, int], align: int = 4) -> Tuple[Dict[str, int], int]:

@@ -7,7 +7,7 @@ encoder), optionally replayed as ONE CUDA graph per step.  It replaces what the 
 with ~500 ATen launches plus a host sync per layer.
 
 Parameters are re-homed into one flat fp32 buffer (each `p.data` becomes a view) laid out as
-[ weights (decayed) | biases (not decayed) | parameters the shipped mode never touches ] with the
+[ weights | biases | parameters the shipped mode never touches ] with the
 four input projections of every attention block (w_qs, w_ks, w_vs, lang_cond_fc) adjacent, so
 that QKV+cond is a single (816 x 256) GEMM, its weight gradient another one, and the gradient
 all-reduce and AdamW are single flat operations.  State-dict keys and shapes are unchanged.
@@ -45,6 +45,11 @@ class GemmDesc(ctypes.Structure):
 
 _C.register_protos({
     "msr3d_gemm_tc_f32": [ctypes.POINTER(GemmDesc), c_vp],
+    "msr3d_gemm_tf32x3_supported": [ctypes.POINTER(GemmDesc)],
+    "msr3d_gemm_tf32x3_f32": [ctypes.POINTER(GemmDesc), c_int, c_vp],
+    "msr3d_ffn_pair_fwd_f32": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_ull, c_vp, c_float, c_uint,
+                               c_vp, c_vp, c_vp, c_int, c_vp],
+    "msr3d_ffn_pair_bwd_f32": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp],
     "msr3d_spatial_geometry_f32": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "msr3d_qpos_fwd_f32": [c_vp, c_vp, c_int] + [c_vp] * 14 + [c_vp],
     "msr3d_qpos_bwd_f32": [c_vp, c_vp, c_vp, c_vp, c_int] + [c_vp] * 14 + [c_vp],
@@ -60,7 +65,7 @@ _C.register_protos({
                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_colsum_add_f32": [c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "msr3d_dropout_mask_f32": [c_ull, c_vp, c_float, c_uint, c_ll, c_vp, c_vp],
-    "msr3d_adamw_clip_step_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp],
+    "msr3d_adamw_clip_step_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_dot_f32": [c_vp, c_vp, c_ll, c_vp, c_vp],
 })
 
@@ -97,12 +102,23 @@ def supported(model) -> Optional[str]:
 class FusedPrompter:
     def __init__(self, model, lr=3e-5, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
                  grad_norm: Optional[float] = 5.0, world_size: int = 1, split: int = 3,
-                 grad_split: int = 6):
+                 grad_split: int = 6, gemm_impl: Optional[str] = None, no_decay_bias: bool = False):
         # NOTE: weight-gradient GEMMs and bias reductions are issued on a side stream (see _run)
         why = supported(model)
         if why is not None:
             raise NotImplementedError(f"fused prompter: unsupported configuration ({why})")
         self.model = model
+        # weight decay: the reference decays every optimised parameter (one uniform AdamW group,
+        # model/msr3d/msr3d.py:165-172); no_decay_bias=True exempts names containing "bias" (opt-in)
+        self.no_decay_bias = bool(no_decay_bias)
+        # transformer GEMMs: "tf32x3" = TMA-fed tcgen05 kind::tf32 big/small pairs (csrc/gemm3x.cu, default),
+        # "bf16" = round-1 register-path split-bf16 kernel (csrc/linear_tc.cu; `split` / `grad_split` apply)
+        import os as _os0
+        self.gemm_impl = gemm_impl or _os0.environ.get("MSR3D_GEMM_IMPL", "tf32x3")
+        assert self.gemm_impl in ("tf32x3", "bf16")
+        # fused FFN pair kernels (FFN1 + GELU + dropout + FFN2 / du + dy2): on with the TMA-fed GEMMs
+        self.ffn_pair = self.gemm_impl == "tf32x3" and _os0.environ.get("MSR3D_FFN_PAIR", "1") == "1"
+        self.ffn_slice = int(_os0.environ.get("MSR3D_FFN_SLICE", "64"))
         self.split = split                    # transformer GEMMs (forward + data gradients)
         self.enc_split = 3 if split == 6 else split   # frozen encoder: two-way split is ample (1.5e-5)
         self.grad_split = grad_split if split >= 3 else split
@@ -146,15 +162,17 @@ class FusedPrompter:
         import os as _os
         self.ddp_buckets = _os.environ.get("MSR3D_DDP_BUCKETS", "1") == "1"
         self._side_pending = [False, False]
+        self.extra_sumsq: Optional[torch.Tensor] = None   # see optimizer_step()
 
     # ------------------------------------------------------------------ parameters
     def _rehome(self):
         from . import dist as _dist
         named = [(n, p) for n, p in self.model.named_parameters() if p.requires_grad]
         by_name = dict(named)
-        lay = _dist.flat_layout([n for n, _ in named], {n: p.numel() for n, p in named}, self.nl)
+        lay = _dist.flat_layout([n for n, _ in named], {n: p.numel() for n, p in named}, self.nl,
+                                no_decay_bias=self.no_decay_bias)
         self.order, offs, total = lay["order"], lay["offs"], lay["total"]
-        self.decay_range = lay["decay"]          # [d0, d1): weights (decayed)
+        self.decay_range = lay["decay"]          # [d0, d1): decayed elements (everything optimised by default)
         self.bucket_early = lay["early"]         # gradients of layers >= 1: complete before layer 0's backward
         self.bucket_late = lay["late"]
         self.n_opt = lay["n_opt"]
@@ -281,8 +299,16 @@ class FusedPrompter:
         d.seed = self.seed
         d.seed_ptr = self.seed_counter.data_ptr()
         self._keep.append(d)
-        fn = _C.lib().msr3d_gemm_tc_f32
         ref = ctypes.byref(d)
+        if self.gemm_impl == "tf32x3" and _C.lib().msr3d_gemm_tf32x3_supported(ref):
+            # TMA-fed 3xTF32 kernel (csrc/gemm3x.cu); the weights of the forward / data-gradient GEMMs are
+            # "static" operands (written by the optimiser of the previous step only)
+            if wgrad and side and self.wgrad_small:
+                d.tile_n = 128
+            fn = _C.lib().msr3d_gemm_tf32x3_f32
+            prog.append(("msr3d_gemm_tf32x3_f32", fn, (ref, 0 if wgrad else 1), tag, side))
+            return
+        fn = _C.lib().msr3d_gemm_tc_f32
         prog.append(("msr3d_gemm_tc_f32", fn, (ref,), tag, side))
 
     def _call(self, prog, name, *args, tag=None, side=False):
@@ -334,12 +360,19 @@ class FusedPrompter:
                        P(sa + "layer_norm.bias"), P(pre + "norm1.weight"), P(pre + "norm1.bias"), seed, sptr, p,
                        s0 + 0, s0 + 1, ptr(w["xhat_a"][i]), ptr(w["rstd_a"][i]), ptr(w["xhat_1"][i]),
                        ptr(w["rstd_1"][i]), ptr(w["y2"][i]), tag="attn_tail")
-            # FFN: the first GEMM's epilogue materialises h = dropout(gelu(u)) and gelu'(u)*mask once
-            self._gemm(fwd, ptr(w["y2"][i]), (H, 1), P(pre + "linear1.weight"), (H, 1), M, F, H, ptr(w["h"][i]), F,
-                       bias=P(pre + "linear1.bias"), epilogue=2, aux_out=ptr(w["gp"][i]), ldaux=F,
-                       epi_site=s0 + 2, tag="ffn1")
-            self._gemm(fwd, ptr(w["h"][i]), (F, 1), P(pre + "linear2.weight"), (F, 1), M, H, F, ptr(w["f"][i]), H,
-                       bias=P(pre + "linear2.bias"), accumulate=2, ksplit=16, tag="ffn2")
+            # FFN: h = dropout(gelu(u)) and gelu'(u)*mask are materialised once (the backward reads both)
+            if self.ffn_pair:
+                # both GEMMs in one kernel, the hidden tile stays in shared memory (csrc/gemm3x.cu)
+                self._call(fwd, "msr3d_ffn_pair_fwd_f32", ptr(w["y2"][i]), P(pre + "linear1.weight"),
+                           P(pre + "linear1.bias"), P(pre + "linear2.weight"), P(pre + "linear2.bias"), M, F,
+                           seed, sptr, p, s0 + 2, ptr(w["h"][i]), ptr(w["gp"][i]), ptr(w["f"][i]),
+                           self.ffn_slice, tag="ffn_pair")
+            else:
+                self._gemm(fwd, ptr(w["y2"][i]), (H, 1), P(pre + "linear1.weight"), (H, 1), M, F, H, ptr(w["h"][i]), F,
+                           bias=P(pre + "linear1.bias"), epilogue=2, aux_out=ptr(w["gp"][i]), ldaux=F,
+                           epi_site=s0 + 2, tag="ffn1")
+                self._gemm(fwd, ptr(w["h"][i]), (F, 1), P(pre + "linear2.weight"), (F, 1), M, H, F, ptr(w["f"][i]), H,
+                           bias=P(pre + "linear2.bias"), accumulate=2, ksplit=16, tag="ffn2")
             last = i == nl - 1
             add = 0 if (last or not self.same_all) else ptr(w["qpos"])
             self._call(fwd, "msr3d_ffn_tail_fwd_f32", ptr(w["f"][i]), ptr(w["y2"][i]), M, P(pre + "norm2.weight"),
@@ -365,17 +398,23 @@ class FusedPrompter:
             # dW2 (H x F) += df^T . h                                   [side stream]
             self._gemm(bwd, df, (1, H), ptr(w["h"][i]), (1, F), H, F, M, G(pre + "linear2.weight"), F,
                        accumulate=2, ksplit=2, tag="dW2", wgrad=True, side=True)
-            # du = (df . W2) * gelu'(u) * mask
-            self._gemm(bwd, df, (H, 1), P(pre + "linear2.weight"), (1, F), M, F, H, du, F,
-                       epilogue=3, aux=ptr(w["gp"][i]), ldaux=F, tag="du")
+            if self.ffn_pair:
+                # du = (df . W2) * gelu'(u) * mask and dy2 += du . W1 in one kernel
+                self._call(bwd, "msr3d_ffn_pair_bwd_f32", df, P(pre + "linear1.weight"), P(pre + "linear2.weight"),
+                           ptr(w["gp"][i]), M, F, du, ptr(w["dy2"]), self.ffn_slice, tag="ffn_pair_bwd")
+            else:
+                # du = (df . W2) * gelu'(u) * mask
+                self._gemm(bwd, df, (H, 1), P(pre + "linear2.weight"), (1, F), M, F, H, du, F,
+                           epilogue=3, aux=ptr(w["gp"][i]), ldaux=F, tag="du")
             # dW1 (F x H) += du^T . y2 ; db1                            [side stream]
             self._gemm(bwd, du, (1, F), ptr(w["y2"][i]), (1, H), F, H, M, G(pre + "linear1.weight"), H,
                        accumulate=2, ksplit=2, tag="dW1", wgrad=True, side=2)
             self._call(bwd, "msr3d_colsum_add_f32", du, F, M, F, G(pre + "linear1.bias"), None, None, tag="db1",
                        side=2)
-            # dy2 += du . W1
-            self._gemm(bwd, du, (F, 1), P(pre + "linear1.weight"), (1, H), M, H, F, ptr(w["dy2"]), H,
-                       accumulate=2, ksplit=16, tag="dy2")
+            if not self.ffn_pair:
+                # dy2 += du . W1
+                self._gemm(bwd, du, (F, 1), P(pre + "linear1.weight"), (1, H), M, H, F, ptr(w["dy2"]), H,
+                           accumulate=2, ksplit=16, tag="dy2")
             self._call(bwd, "msr3d_attn_tail_bwd_f32", ptr(w["dy2"]), M, P(sa + "layer_norm.weight"),
                        P(pre + "norm1.weight"), seed, sptr, p, s0 + 0, s0 + 1, ptr(w["xhat_a"][i]),
                        ptr(w["rstd_a"][i]), ptr(w["xhat_1"][i]), ptr(w["rstd_1"][i]), dx, do_,
@@ -696,10 +735,22 @@ class FusedPrompter:
         self._run(self.bwd_prog)
 
     def optimizer_step(self):
+        """Global-norm clip + AdamW over the flat buffer.  `self.extra_sumsq` (a 1-element CUDA tensor, optional)
+        is added to the squared gradient norm: set it to the squared norm of the trainable parameters that live
+        outside this engine (llm_proj, LoRA, ...) to reproduce the reference's clip over ALL model parameters
+        (trainer/leo_trainer.py:192-193); the caller then scales its own gradients by `clip_coef()`."""
         n, (d0, d1) = self.n_opt, self.decay_range
+        ex = self.extra_sumsq.data_ptr() if self.extra_sumsq is not None else None
         _C.call("msr3d_adamw_clip_step_f32", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(),
                 self.v.data_ptr(), n, d0, d1, 1.0 / self.world_size, self.opt_state.data_ptr(),
-                self.ticket.data_ptr(), self.seed_counter.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                self.ticket.data_ptr(), self.seed_counter.data_ptr(), ex, torch.cuda.current_stream().cuda_stream)
+
+    def clip_coef(self) -> torch.Tensor:
+        """min(1, max_norm / (||g|| + 1e-6)) of the last optimizer_step (device scalar), for parameters the
+        caller updates itself with the same global norm."""
+        norm = self.opt_state[0].sqrt()
+        mx = self.opt_state[7]
+        return torch.where(mx > 0, torch.clamp(mx / (norm + 1e-6), max=1.0), torch.ones_like(norm))
 
     def set_lr(self, lr: float):
         self.opt_state[2] = lr
@@ -773,9 +824,11 @@ class FusedPrompter:
 
 def gemm_tc(A: torch.Tensor, Bm: torch.Tensor, bias: Optional[torch.Tensor] = None, split: int = 3,
             out: Optional[torch.Tensor] = None, accumulate: int = 0, ksplit: int = 1,
-            residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+            residual: Optional[torch.Tensor] = None, impl: str = "bf16", tile_n: int = 0,
+            aux: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = A[M,K] @ Bm[N,K]^T (+ bias + residual) on the tensor cores; A and Bm are any 2-D
-    fp32 CUDA views (strides are passed through, nothing is packed or copied)."""
+    fp32 CUDA views (strides are passed through, nothing is packed or copied).
+    impl "bf16": register-path split-bf16 kernel (linear_tc.cu); "tf32x3": TMA-fed 3xTF32 kernel (gemm3x.cu)."""
     M, K = A.shape
     N = Bm.shape[0]
     assert Bm.shape[1] == K
@@ -788,7 +841,12 @@ def gemm_tc(A: torch.Tensor, Bm: torch.Tensor, bias: Optional[torch.Tensor] = No
     if residual is not None:
         d.residual, d.ld_residual = residual.data_ptr(), residual.stride(0)
     d.out, d.ld_out, d.M, d.N, d.K = out.data_ptr(), out.stride(0), M, N, K
-    d.split, d.accumulate, d.ksplit = split, accumulate, ksplit
+    d.split, d.accumulate, d.ksplit, d.tile_n = split, accumulate, ksplit, tile_n
+    if aux is not None:
+        d.aux, d.ld_aux, d.epilogue = aux.data_ptr(), aux.stride(0), 3
     with torch.cuda.device(A.device):
-        _C.call("msr3d_gemm_tc_f32", ctypes.byref(d), torch.cuda.current_stream().cuda_stream)
+        if impl == "tf32x3":
+            _C.call("msr3d_gemm_tf32x3_f32", ctypes.byref(d), 0, torch.cuda.current_stream().cuda_stream)
+        else:
+            _C.call("msr3d_gemm_tc_f32", ctypes.byref(d), torch.cuda.current_stream().cuda_stream)
     return out

@@ -15,7 +15,7 @@ FROZEN_PREFIXES = ("obj_encoder.",)
 
 class CpuHotPath:
     def __init__(self, sd: dict, situation_type="as_transform_for_objects", lr=3e-5, weight_decay=0.05,
-                 betas=(0.9, 0.999), grad_norm=5.0):
+                 betas=(0.9, 0.999), grad_norm=5.0, no_decay_bias=False):
         self.sd = {}
         for k, v in sd.items():
             frozen = k.startswith(FROZEN_PREFIXES) or k == "anchor_size" or not v.is_floating_point()
@@ -23,11 +23,13 @@ class CpuHotPath:
         self.situation_type = situation_type
         self.grad_norm = grad_norm
         named = [(k, v) for k, v in self.sd.items() if v.requires_grad]
-        nd = ("bias", "LayerNorm.bias", "LayerNorm.weight")  # optim/utils.py:1-18
-        self.opt = torch.optim.AdamW(
-            [{"params": [v for k, v in named if not any(s in k for s in nd)], "weight_decay": weight_decay},
-             {"params": [v for k, v in named if any(s in k for s in nd)], "weight_decay": 0.0}],
-            lr=lr, betas=betas)
+        if no_decay_bias:   # optim/utils.py:1-18 (dead code in the reference: imported, never called)
+            nd = ("bias", "LayerNorm.bias", "LayerNorm.weight")
+            groups = [{"params": [v for k, v in named if not any(s in k for s in nd)], "weight_decay": weight_decay},
+                      {"params": [v for k, v in named if any(s in k for s in nd)], "weight_decay": 0.0}]
+        else:               # MSR3D.get_opt_params (model/msr3d/msr3d.py:165-172): one uniform list
+            groups = [{"params": [v for _, v in named], "weight_decay": weight_decay}]
+        self.opt = torch.optim.AdamW(groups, lr=lr, betas=betas)
         self.trainable = [v for _, v in named]
 
     def forward(self, data: dict):

@@ -137,6 +137,10 @@ def test_flat_layout_buckets_and_decay_range(sd_spec):
              and "running" not in k and "num_batches" not in k]
     numel = {k: int(torch.tensor(s).prod()) for k, s, _ in sd_spec}
     lay = mdist.flat_layout(names, numel, 3)
+    # the reference decays every optimised parameter (one uniform AdamW group, model/msr3d/msr3d.py:165-172)
+    assert lay["decay"] == (0, lay["n_opt"])
+    lay = mdist.flat_layout(names, numel, 3, no_decay_bias=True)      # opt-in rule of optim/utils.py:1-18
+    assert lay["decay"] == lay["weights"]
     offs, (d0, d1), (l0, l1), (e0, e1) = lay["offs"], lay["decay"], lay["late"], lay["early"]
     assert sorted(lay["order"]) == sorted(names)
     assert l0 == 0 and l1 == e0 and e1 == lay["n_opt"] and 0 < d0 < e0 < d1 < e1 < lay["total"]

@@ -139,15 +139,20 @@ def test_fused_dropout_masks_forward_backward(sd_spec):
     assert e < TOL
 
 
-def test_fused_adamw_matches_torch(sd_spec):
+@pytest.mark.parametrize("no_decay_bias", [False, True])
+def test_fused_adamw_matches_torch(sd_spec, no_decay_bias):
+    """no_decay_bias=False (default): every optimised parameter decays, as the reference's uniform AdamW group
+    does (model/msr3d/msr3d.py:165-172); True: the opt-in bias/LayerNorm exemption."""
     seed, B, O, P = 9, 1, 8, 256
-    model, eng = _engine(seed, B, O, P, training=False, lr=1e-3, grad_norm=0.5)
+    model, eng = _engine(seed, B, O, P, training=False, lr=1e-3, grad_norm=0.5, no_decay_bias=no_decay_bias)
+    assert eng.decay_range == ((0, eng.n_opt) if not no_decay_bias else eng.decay_range)
     batch = synthetic.make_batch(B, O, P, seed=seed).to("cuda")
     up = torch.randn(B, O, 256, generator=torch.Generator().manual_seed(1)).cuda()
     ref_p = eng.flat_p[:eng.n_opt].clone()
     d0, d1 = eng.decay_range                                   # [late biases | WEIGHTS | early biases]
     is_decayed = torch.zeros(eng.n_opt, dtype=torch.bool, device="cuda")
     is_decayed[d0:d1] = True
+    assert bool(is_decayed.all()) == (not no_decay_bias)
     decay, nodecay = ref_p[is_decayed].clone().requires_grad_(True), ref_p[~is_decayed].clone().requires_grad_(True)
     opt = torch.optim.AdamW([{"params": [decay], "weight_decay": 0.05}, {"params": [nodecay], "weight_decay": 0.0}],
                             lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
