@@ -173,6 +173,9 @@ int msr3d_sizeof_gemm_desc(void);
  * launch wait.  msr3d_gemm_tf32x3_supported returns 1 when a descriptor qualifies (callers fall back to
  * msr3d_gemm_tc_f32 otherwise, e.g. the K = 63 Fourier projection).
  * Replaces the cuBLAS calls behind nn.Linear in modules/layers/transformers.py:200-252,314-329. */
+/* Development hook: device buffer of 16 int64 SM-clock slots per CTA that the TMA-fed kernels fill at their
+ * phase boundaries (tools/trace_kernels.py); NULL (default) turns tracing off. */
+int msr3d_set_trace_buffer(long long *buf);
 int msr3d_gemm_tf32x3_supported(const msr3d_gemm_desc *desc);
 int msr3d_gemm_tf32x3_f32(const msr3d_gemm_desc *desc, int b_static, msr3d_stream_t stream);
 /* Fused feed-forward pair of one encoder layer (transformers.py:326-327), d_model = 256, one CTA per

@@ -1,0 +1,108 @@
+"""The fused kernels behind the drop-in module call.
+
+`OSE3DSituation.forward` (prompter.py; reference model/ose3d_situation.py:288-454) is what
+`MSR3D.forward` calls and what `trainer/leo_trainer.py:189-195` differentiates with `loss.backward()`.
+When the configuration is one the fused engine covers (`fused.supported`), that call runs the engine's
+forward program (frozen PointNet++ on the tensor cores, TMA-fed 3xTF32 GEMMs, attention / LayerNorm /
+FFN-pair kernels) inside a `torch.autograd.Function`; its backward runs the engine's hand-written backward
+program from the incoming `grad_output` and hands autograd one gradient per trainable parameter — so DDP
+hooks, gradient accumulation, `clip_grad_norm_` and any torch optimiser see exactly what they would see
+from the reference module tree, while no cuBLAS / ATen kernel is launched on the way.
+
+Parameters stay `nn.Parameter`s; their storage is re-homed once into the engine's flat buffer (values and
+state-dict keys unchanged) because the kernels read the four input projections of an attention block as
+one (816 x 256) matrix.  Gradients are NOT aliased to the engine's buffer in this mode: each backward
+returns fresh tensors and autograd accumulates them into `p.grad` as usual.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+_KEYS = ("obj_fts", "obj_locs", "obj_masks", "anchor_locs", "anchor_orientation")
+
+
+def eligible(module, data_dict) -> Optional[str]:
+    """None if this call can run on the fused engine, else the reason it cannot."""
+    from . import fused
+    if os.environ.get("MSR3D_MODULE_FUSED", "1") != "1" or not getattr(module, "fused_kernels", True):
+        return "disabled"
+    if any(k not in data_dict for k in _KEYS):
+        return "inputs missing"
+    why = fused.supported(module)
+    if why is not None:
+        return why
+    fts = data_dict["obj_fts"]
+    if not fts.is_cuda or fts.dim() != 4 or fts.shape[-1] != 6 or fts.dtype != torch.float32:
+        return "obj_fts must be a (B, O, P, 6) fp32 CUDA tensor"
+    if fts.shape[1] > 128:
+        return "more than 128 objects per scene"
+    p0 = next(module.parameters())
+    if not p0.is_cuda or p0.dtype != torch.float32:
+        return "parameters must be fp32 CUDA tensors"
+    return None
+
+
+def _engine(module):
+    from .fused import FusedPrompter
+    eng = getattr(module, "_fused_engine", None)
+    if eng is None or eng.dev != next(module.parameters()).device:
+        eng = FusedPrompter(module, alias_grads=False)
+        object.__setattr__(module, "_fused_engine", eng)      # not a submodule / buffer: never in state_dict
+    return eng
+
+
+class _FusedPrompterFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, engine, obj_fts, obj_locs, obj_masks, anchor_locs, anchor_ori, *params):
+        B, L, P = obj_fts.shape[:3]
+        engine.prepare(B, L, P, training=module.training)
+        if module.training:
+            engine.seed_counter.add_(1)            # fresh dropout masks per call (the engine's own optimiser is not used)
+        w = engine.ws
+        w["obj_fts"].copy_(obj_fts)
+        w["obj_locs"].copy_(obj_locs)
+        w["obj_masks"].copy_(obj_masks)
+        w["anchor_locs"].copy_(anchor_locs)
+        w["anchor_ori"].copy_(anchor_ori)
+        tokens = engine.forward()
+        ctx.engine = engine
+        ctx.n_params = len(params)
+        ctx.key = engine._key
+        ctx.call_id = engine._module_calls = getattr(engine, "_module_calls", 0) + 1
+        return tokens.clone()
+
+    @staticmethod
+    def backward(ctx, grad_tokens):
+        e = ctx.engine
+        if ctx.call_id != e._module_calls or ctx.key != e._key:
+            raise RuntimeError("msr3d_b200: the fused prompter keeps ONE set of saved activations; call backward() "
+                               "before the next forward of the same module (or set module.fused_kernels = False)")
+        e.ws["upstream"].copy_(grad_tokens.reshape(e.ws["upstream"].shape))
+        # engine-API engines alias p.grad to flat_g: keep what autograd has accumulated there so far
+        saved = e.flat_g[:e.n_opt].clone() if e.alias_grads else None
+        e.flat_g.zero_()
+        e.backward()
+        flat = e.flat_g[:e.n_opt].clone()          # fresh storage: autograd may keep / steal what we return
+        if saved is not None:
+            e.flat_g[:e.n_opt].copy_(saved)
+        grads = []
+        for n in e.autograd_names:
+            off = e.offs.get(n)
+            p = e.by_name[n]
+            if off is None or off >= e.n_opt:
+                grads.append(None)                 # parameters the shipped mode never touches
+            else:
+                grads.append(flat[off:off + p.numel()].view_as(p))
+        return (None,) * 7 + tuple(grads)
+
+
+def fused_forward(module, data_dict) -> torch.Tensor:
+    """obj_tokens (B, O, 256) of `module(data_dict)` through the fused engine, differentiable w.r.t. the
+    module's trainable parameters."""
+    eng = _engine(module)
+    params = [eng.by_name[n] for n in eng.autograd_names]
+    return _FusedPrompterFn.apply(module, eng, data_dict["obj_fts"], data_dict["obj_locs"], data_dict["obj_masks"],
+                                  data_dict["anchor_locs"], data_dict["anchor_orientation"], *params)

@@ -72,6 +72,18 @@ constexpr int kFirstConvWarp = 4;
 
 enum { EPI3_PLAIN = 0, EPI3_FFN1 = 2, EPI3_MUL_AUX = 3 };
 
+// Optional per-CTA timeline (tools/trace_kernels.py): slot s of CTA c = SM clock at a phase boundary.
+// g_trace is a device pointer set by msr3d_set_trace_buffer (nullptr = off, the default).
+constexpr int kTraceSlots = 16;
+__device__ long long *g_trace = nullptr;
+__device__ __forceinline__ void trace_mark(int slot) {
+  long long *t = g_trace;
+  if (t != nullptr) {
+    const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    t[(size_t)cta * kTraceSlots + slot] = clock64();
+  }
+}
+
 struct alignas(64) Gemm3xParams {
   CUtensorMap map_a, map_b;
   int a_mn, b_mn;                 // operand orientation (1 = MN-major, i.e. stored [k][mn])
@@ -145,6 +157,7 @@ __device__ __noinline__ void epilogue3x(const Gemm3xParams &g, uint32_t tmem_d, 
       mbar_wait(acc_bar, 0);
       fence_after_sync();
       waited = true;
+      if (cw == 0 && lane == 0) trace_mark(6);
     }
     uint32_t r[16];
     tmem_ld16_3x(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
@@ -244,6 +257,7 @@ gemm3x_kernel(const __grid_constant__ Gemm3xParams g) {
   if (nkc <= 0) { pdl_sync(); return; }   // uniform per CTA, nothing allocated yet
 
   if (tid == 0) {
+    trace_mark(0);
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
@@ -260,10 +274,11 @@ gemm3x_kernel(const __grid_constant__ Gemm3xParams g) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_d = s_tmem;
+  if (tid == 0) trace_mark(1);
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (one elected lane)
+    if (tma::elect_one()) {
       auto load_a = [&](int i) {
         const int s = i % S;
         uint8_t *dst = smem + (size_t)s * C::kStageBytes;
@@ -290,6 +305,7 @@ gemm3x_kernel(const __grid_constant__ Gemm3xParams g) {
         if (g.b_static) load_b(i);            // weights: in flight while the previous kernel drains
       }
       pdl_wait();
+      trace_mark(2);
       for (int i = 0; i < pre; ++i) {
         if (!g.b_static) load_b(i);
         load_a(i);
@@ -304,8 +320,8 @@ gemm3x_kernel(const __grid_constant__ Gemm3xParams g) {
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp waits, one lane issues)
+    {
       const uint32_t idesc = tma::make_idesc_tf32(kTileM3, BN, g.a_mn != 0, g.b_mn != 0);
       const uint64_t step_a = tma::kstep_units(g.a_mn != 0), step_b = tma::kstep_units(g.b_mn != 0);
 #pragma unroll 1
@@ -313,17 +329,23 @@ gemm3x_kernel(const __grid_constant__ Gemm3xParams g) {
         const int s = i % S;
         mbar_wait(&conv_done[s], (i / S) & 1);
         fence_after_sync();
-        const uint32_t base = smem_u32(smem + (size_t)s * C::kStageBytes);
-        const uint64_t a_big = g.a_mn ? tma::desc_mnmajor(base) : tma::desc_kmajor(base);
-        const uint64_t b_big = g.b_mn ? tma::desc_mnmajor(base + C::kABytes) : tma::desc_kmajor(base + C::kABytes);
-        constexpr uint64_t small = C::kBigBytes >> 4;
+        if (tma::elect_one()) {
+          const uint32_t base = smem_u32(smem + (size_t)s * C::kStageBytes);
+          const uint64_t a_big = g.a_mn ? tma::desc_mnmajor(base) : tma::desc_kmajor(base);
+          const uint64_t b_big = g.b_mn ? tma::desc_mnmajor(base + C::kABytes) : tma::desc_kmajor(base + C::kABytes);
+          constexpr uint64_t small = C::kBigBytes >> 4;
 #pragma unroll
-        for (int ks = 0; ks < kChunk3 / 8; ++ks)
-          tma::mma_3x(tmem_d, a_big + ks * step_a, a_big + small + ks * step_a, b_big + ks * step_b,
-                      b_big + small + ks * step_b, idesc, (i | ks) ? 1u : 0u);
-        mma_commit(&mma_done[s]);
+          for (int ks = 0; ks < kChunk3 / 8; ++ks)
+            tma::mma_3x(tmem_d, a_big + ks * step_a, a_big + small + ks * step_a, b_big + ks * step_b,
+                        b_big + small + ks * step_b, idesc, (i | ks) ? 1u : 0u);
+          mma_commit(&mma_done[s]);
+          if (i == nkc - 1) {
+            trace_mark(5);
+            mma_commit(&acc_full);
+          }
+        }
+        __syncwarp();
       }
-      mma_commit(&acc_full);
     }
   } else if (warp >= kFirstConvWarp) {
     // ------------------------------------------------------------------ converters, then epilogue
@@ -335,6 +357,7 @@ gemm3x_kernel(const __grid_constant__ Gemm3xParams g) {
       const int s = i % S;
       uint4 *tile = reinterpret_cast<uint4 *>(smem + (size_t)s * C::kStageBytes);
       mbar_wait(&full[s], (i / S) & 1);
+      if (i == 0 && ct == 0) trace_mark(3);
       float4 v[C::kPer];
 #pragma unroll
       for (int j = 0; j < C::kPer; ++j) v[j] = *reinterpret_cast<const float4 *>(tile + ct + j * (kConvWarps * 32));
@@ -352,7 +375,9 @@ gemm3x_kernel(const __grid_constant__ Gemm3xParams g) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&conv_done[s]);
     }
+    if (ct == 0) trace_mark(4);
     epilogue3x<BN>(g, tmem_d, m0, n0, cw, lane, &acc_full);
+    if (ct == 0) trace_mark(11);
   } else {
     pdl_sync();
   }
@@ -401,6 +426,13 @@ static const char *gemm3x_why_not(const msr3d_gemm_desc *d) {
 }  // namespace msr3d
 
 using namespace msr3d;
+
+/* Development hook (tools/trace_kernels.py): device buffer of 16 int64 SM-clock slots per CTA that the gemm3x / ffn_pair
+ * kernels fill at their phase boundaries; NULL (default) disables tracing. */
+MSR3D_API int msr3d_set_trace_buffer(long long *buf) {
+  MSR3D_CUDA(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
+  return MSR3D_OK;
+}
 
 /* 1 if msr3d_gemm_tf32x3_f32 accepts this descriptor, else 0 (msr3d_last_error() says why). */
 MSR3D_API int msr3d_gemm_tf32x3_supported(const msr3d_gemm_desc *d) {
@@ -520,6 +552,7 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
   const int f0 = blockIdx.y * FS;
 
   if (tid == 0) {
+    trace_mark(0);
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
@@ -541,10 +574,11 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem1 = s_tmem, tmem2 = s_tmem + C::kAcc2Col;
+  if (tid == 0) trace_mark(1);
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (one elected lane)
+    if (tma::elect_one()) {
       auto load_b1 = [&](int i) {
         const int s = i % S;
         uint8_t *dst = ring + (size_t)s * C::kStage1 + C::kABytes;
@@ -564,6 +598,7 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
         load_b1(i);                              // weights: requested while the previous kernel drains
       }
       pdl_wait();
+      trace_mark(2);
       for (int i = 0; i < S; ++i) load_a(i);
       pdl_launch_dependents();
       for (int i = S; i < kNkc1; ++i) {
@@ -588,8 +623,8 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp waits, one lane issues)
+    {
       const uint32_t idesc1 = tma::make_idesc_tf32(kTileM3, FS, false, BWD);
       const uint64_t step_b1 = tma::kstep_units(BWD);
 #pragma unroll 1
@@ -597,36 +632,45 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
         const int s = i % S;
         mbar_wait(&conv_done[s], (i / S) & 1);
         fence_after_sync();
-        const uint32_t base = smem_u32(ring + (size_t)s * C::kStage1);
-        const uint64_t a_big = tma::desc_kmajor(base);
-        const uint64_t b_big = BWD ? tma::desc_mnmajor(base + C::kABytes) : tma::desc_kmajor(base + C::kABytes);
-        constexpr uint64_t small = C::kBig1 >> 4;
+        if (tma::elect_one()) {
+          const uint32_t base = smem_u32(ring + (size_t)s * C::kStage1);
+          const uint64_t a_big = tma::desc_kmajor(base);
+          const uint64_t b_big = BWD ? tma::desc_mnmajor(base + C::kABytes) : tma::desc_kmajor(base + C::kABytes);
+          constexpr uint64_t small = C::kBig1 >> 4;
 #pragma unroll
-        for (int ks = 0; ks < kChunk3 / 8; ++ks)
-          tma::mma_3x(tmem1, a_big + ks * 2, a_big + small + ks * 2, b_big + ks * step_b1, b_big + small + ks * step_b1,
-                      idesc1, (i | ks) ? 1u : 0u);
-        mma_commit(&mma_done[s]);
+          for (int ks = 0; ks < kChunk3 / 8; ++ks)
+            tma::mma_3x(tmem1, a_big + ks * 2, a_big + small + ks * 2, b_big + ks * step_b1, b_big + small + ks * step_b1,
+                        idesc1, (i | ks) ? 1u : 0u);
+          mma_commit(&mma_done[s]);
+          if (i == kNkc1 - 1) {
+            trace_mark(5);
+            mma_commit(&acc1_full);
+          }
+        }
+        __syncwarp();
       }
-      mma_commit(&acc1_full);
       // GEMM 2: A = h images written by epilogue 1, B = the converted B2 slice
       mbar_wait(&h_ready, 0);
       mbar_wait(&b2_conv, 0);
       fence_after_sync();
-      const uint32_t idesc2 = tma::make_idesc_tf32(kTileM3, kHid, false, BWD);
-      const uint64_t step_b2 = tma::kstep_units(BWD);
+      if (tma::elect_one()) {
+        const uint32_t idesc2 = tma::make_idesc_tf32(kTileM3, kHid, false, BWD);
+        const uint64_t step_b2 = tma::kstep_units(BWD);
 #pragma unroll
-      for (int c = 0; c < C::kNch2; ++c) {
-        const uint64_t a_big = tma::desc_kmajor(smem_u32(hbuf + (size_t)c * C::kHTile));
-        const uint64_t a_small = tma::desc_kmajor(smem_u32(hbuf + (size_t)(C::kNch2 + c) * C::kHTile));
-        const uint32_t bb = smem_u32(ring + (size_t)c * C::kB2Chunk);
-        const uint64_t b_big = BWD ? tma::desc_mnmajor(bb) : tma::desc_kmajor(bb);
-        constexpr uint64_t b_small_off = C::kB2Big >> 4;
+        for (int c = 0; c < C::kNch2; ++c) {
+          const uint64_t a_big = tma::desc_kmajor(smem_u32(hbuf + (size_t)c * C::kHTile));
+          const uint64_t a_small = tma::desc_kmajor(smem_u32(hbuf + (size_t)(C::kNch2 + c) * C::kHTile));
+          const uint32_t bb = smem_u32(ring + (size_t)c * C::kB2Chunk);
+          const uint64_t b_big = BWD ? tma::desc_mnmajor(bb) : tma::desc_kmajor(bb);
+          constexpr uint64_t b_small_off = C::kB2Big >> 4;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          tma::mma_3x(tmem2, a_big + ks * 2, a_small + ks * 2, b_big + ks * step_b2, b_big + b_small_off + ks * step_b2,
-                      idesc2, (c | ks) ? 1u : 0u);
+          for (int ks = 0; ks < 4; ++ks)
+            tma::mma_3x(tmem2, a_big + ks * 2, a_small + ks * 2, b_big + ks * step_b2, b_big + b_small_off + ks * step_b2,
+                        idesc2, (c | ks) ? 1u : 0u);
+        }
+        mma_commit(&acc2_full);
       }
-      mma_commit(&acc2_full);
+      __syncwarp();
     }
   } else if (warp >= kFirstConvWarp) {
     // ------------------------------------------------------------------ converters / epilogues
@@ -638,6 +682,7 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
       const int s = i % S;
       uint4 *tile = reinterpret_cast<uint4 *>(ring + (size_t)s * C::kStage1);
       mbar_wait(&full[s], (i / S) & 1);
+      if (i == 0 && ct == 0) trace_mark(3);
       float4 v[C::kPer];
 #pragma unroll
       for (int j = 0; j < C::kPer; ++j) v[j] = *reinterpret_cast<const float4 *>(tile + ct + j * (kConvWarps * 32));
@@ -655,6 +700,7 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&conv_done[s]);
     }
+    if (ct == 0) trace_mark(4);
     // ---- epilogue 1: hidden tile -> global (for the backward) and -> shared-memory operand images
     const int q = cw & 3, half = cw >> 2;
     const int r = q * 32 + lane;            // row of the tile = TMEM lane
@@ -675,6 +721,7 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
           mbar_wait(&acc1_full, 0);
           fence_after_sync();
           waited = true;
+          if (ct == 0) trace_mark(6);
         }
         uint32_t acc[16];
         tmem_ld16_3x(tmem1 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
@@ -731,10 +778,12 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
     fence_before_sync();    // order this warp's tcgen05.ld of acc1 before the issuer's next MMAs
     __syncwarp();
     if (lane == 0) mbar_arrive(&h_ready);
+    if (ct == 0) trace_mark(7);
     // ---- B2 slice: big / small split in place
     {
       uint4 *tile = reinterpret_cast<uint4 *>(ring);
       mbar_wait(&b2_full, 0);
+      if (ct == 0) trace_mark(8);
 #pragma unroll 2
       for (int j = 0; j < C::kB2Per; ++j) {
         const float4 v = *reinterpret_cast<const float4 *>(tile + ct + j * (kConvWarps * 32));
@@ -749,6 +798,7 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&b2_conv);
+      if (ct == 0) trace_mark(9);
     }
     // ---- epilogue 2: partial [128 x 256] -> red.add
     {
@@ -762,6 +812,7 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
           mbar_wait(&acc2_full, 0);
           fence_after_sync();
           waited = true;
+          if (ct == 0) trace_mark(10);
         }
         uint32_t acc[16];
         tmem_ld16_3x(tmem2 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
@@ -773,6 +824,7 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
           red_add4(o + j, __uint_as_float(acc[j]) + (add_bias ? bv[j] : 0.f), __uint_as_float(acc[j + 1]) + (add_bias ? bv[j + 1] : 0.f),
                    __uint_as_float(acc[j + 2]) + (add_bias ? bv[j + 2] : 0.f), __uint_as_float(acc[j + 3]) + (add_bias ? bv[j + 3] : 0.f));
       }
+      if (ct == 0) trace_mark(11);
     }
   } else {
     pdl_sync();

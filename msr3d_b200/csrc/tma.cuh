@@ -108,15 +108,34 @@ __device__ __forceinline__ void mma_3x(uint32_t tmem_d, uint64_t a_big, uint64_t
   mma_tf32(tmem_d, a_big, b_big, idesc, 1u);
 }
 
+// one lane of a converged warp (CUTLASS's elect_one_sync): code under `if (elect_one())` compiles to straight
+// uniform-datapath instructions (UTCHMMA, UTMALDG back to back); under `if (lane == 0)` the compiler wraps every
+// such instruction in an ELECT / BRA.U.ANY serialisation loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- device: big / small split
 __device__ __forceinline__ uint32_t rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
 }
+// big = x rounded to tf32 (nearest, ties away: add half an ulp of the 13 dropped bits, mask), small = x - big
+// exactly; the tensor core ignores the low 13 bits of `small` (error 2^-21 |x|, the same order as the dropped
+// small*small term).  Integer ALU + one FADD: cvt.rna.tf32.f32 runs at 16 lanes/clk/SM and made the split the
+// bottleneck of the whole pipeline (0.58 us per 24 KB stage, tools/trace_kernels.py).
 __device__ __forceinline__ void split_tf32(float x, uint32_t &big, uint32_t &small) {
-  big = rna_tf32(x);
-  small = rna_tf32(x - __uint_as_float(big));
+  big = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  small = __float_as_uint(x - __uint_as_float(big));
 }
 // in place: tile[i] = big(x_i), tile[i + small_off] = small(x_i) for the float4s idx, idx + stride, ... < n_f4
 __device__ __forceinline__ void split_region(uint8_t *tile, uint32_t small_off, int n_f4, int idx, int stride) {

@@ -91,7 +91,10 @@ def supported(model) -> Optional[str]:
         (bool(c.use_orientation), "use_orientation off"),
         (c.vision.name == "PcdObjEncoder", "vision backbone is not PcdObjEncoder"),
         (c.loc_fourier_dim == 63, "loc_fourier_dim != 63"),
-        (se.dim_feedforward % 4 == 0, "dim_feedforward % 4"),
+        (se.dim_feedforward % 64 == 0, "dim_feedforward % 64"),
+        # the engine runs the encoder without autograd: an unfrozen encoder must use the module tree
+        (hasattr(model, "obj_encoder") and all(not p.requires_grad for p in model.obj_encoder.parameters()),
+         "object encoder is not frozen"),
     ]
     for ok, why in checks:
         if not ok:
@@ -102,7 +105,8 @@ def supported(model) -> Optional[str]:
 class FusedPrompter:
     def __init__(self, model, lr=3e-5, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
                  grad_norm: Optional[float] = 5.0, world_size: int = 1, split: int = 3,
-                 grad_split: int = 6, gemm_impl: Optional[str] = None, no_decay_bias: bool = False):
+                 grad_split: int = 6, gemm_impl: Optional[str] = None, no_decay_bias: bool = False,
+                 alias_grads: bool = True):
         # NOTE: weight-gradient GEMMs and bias reductions are issued on a side stream (see _run)
         why = supported(model)
         if why is not None:
@@ -111,6 +115,10 @@ class FusedPrompter:
         # weight decay: the reference decays every optimised parameter (one uniform AdamW group,
         # model/msr3d/msr3d.py:165-172); no_decay_bias=True exempts names containing "bias" (opt-in)
         self.no_decay_bias = bool(no_decay_bias)
+        # alias_grads: p.grad of every trainable parameter is a view of the flat gradient buffer (engine API:
+        # the fused optimiser and the all-reduce work on it).  False = module / autograd mode (autograd.py):
+        # p.grad belongs to autograd, the flat buffer is scratch of one backward.
+        self.alias_grads = bool(alias_grads)
         # transformer GEMMs: "tf32x3" = TMA-fed tcgen05 kind::tf32 big/small pairs (csrc/gemm3x.cu, default),
         # "bf16" = round-1 register-path split-bf16 kernel (csrc/linear_tc.cu; `split` / `grad_split` apply)
         import os as _os0
@@ -163,6 +171,9 @@ class FusedPrompter:
         self.ddp_buckets = _os.environ.get("MSR3D_DDP_BUCKETS", "1") == "1"
         self._side_pending = [False, False]
         self.extra_sumsq: Optional[torch.Tensor] = None   # see optimizer_step()
+        # one engine per model: the drop-in module call (autograd.py) reuses this one instead of re-homing
+        # the parameters a second time
+        object.__setattr__(model, "_fused_engine", self)
 
     # ------------------------------------------------------------------ parameters
     def _rehome(self):
@@ -184,7 +195,10 @@ class FusedPrompter:
             view = self.flat_p[offs[n]:offs[n] + p.numel()].view_as(p)
             view.copy_(p.data)
             p.data = view
-            p.grad = self.flat_g[offs[n]:offs[n] + p.numel()].view_as(p)
+            if self.alias_grads:
+                p.grad = self.flat_g[offs[n]:offs[n] + p.numel()].view_as(p)
+        self.by_name = by_name
+        self.autograd_names = [n for n, _ in named]
         self.n_trainable = sum(p.numel() for _, p in named)
         if self.world_size > 1:
             _dist.broadcast_(self.flat_p)     # identical replicas, as DDP's constructor guarantees

@@ -128,6 +128,9 @@ class OSE3DSituation(BaseModel):
     def device(self):
         return next(self.parameters()).device
 
+    def obj_encoder_is_native(self) -> bool:
+        return hasattr(self, "obj_encoder") and hasattr(self.obj_encoder, "encode")
+
     # ------------------------------------------------------------------ encoder
     def forward_gtpcd(self, data_dict):
         enc = self.obj_encoder
@@ -170,6 +173,15 @@ class OSE3DSituation(BaseModel):
             data_dict["single_obj_token"] = self.forward_gtpcd(data_dict)
             data_dict["obj_fts"] = keep
             return data_dict
+        if self.obj_encoder_is_native() and data_dict["obj_fts"].is_cuda:
+            # the reference's call path (MSR3D.forward -> loss.backward(), trainer/leo_trainer.py:189-195) on the
+            # hand-written kernels: forward and backward of the fused engine behind a torch.autograd.Function
+            from . import autograd as _ag
+            if _ag.eligible(self, data_dict) is None:
+                data_dict["obj_tokens"] = _ag.fused_forward(self, data_dict)
+                data_dict["oatt"] = None
+                data_dict["obj_masks"] = data_dict["obj_masks"].clone()
+                return data_dict
         feat = self.forward_gtpcd(data_dict)
         mask = ~data_dict["obj_masks"]          # True = padded
         B, N, H = feat.shape

@@ -93,7 +93,28 @@ def _chk(t: torch.Tensor, dtype, name: str) -> None:
         raise RuntimeError("oracle works on CPU tensors only")
 
 
+_ref_mod = None
+
+
+def ref_cuda():
+    """The reference's own CUDA extension compiled for sm_100 into oracle/_ref (oracle/build_ref.py): serves
+    CUDA tensors when the oracle port runs on the GPU (bench.py's `gpu_baseline`: reference kernels + stock
+    torch ops on the same B200)."""
+    global _ref_mod
+    if _ref_mod is None:
+        import importlib.util
+        path = os.path.join(_HERE, "_ref", "pointnet2_ref_ext.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not found (python oracle/build_ref.py builds it where /root/reference exists)")
+        spec = importlib.util.spec_from_file_location("pointnet2_ref_ext", path)
+        _ref_mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_ref_mod)
+    return _ref_mod
+
+
 def furthest_point_sampling(points: torch.Tensor, nsamples: int) -> torch.Tensor:
+    if points.is_cuda:
+        return ref_cuda().furthest_point_sampling(points, int(nsamples))
     _chk(points, torch.float32, "points")
     b, n, _ = points.shape
     out = torch.zeros(b, nsamples, dtype=torch.int32)
@@ -120,6 +141,8 @@ def gather_points_grad(grad_out: torch.Tensor, idx: torch.Tensor, n: int) -> tor
 
 
 def ball_query(new_xyz: torch.Tensor, xyz: torch.Tensor, radius: float, nsample: int) -> torch.Tensor:
+    if new_xyz.is_cuda:
+        return ref_cuda().ball_query(new_xyz, xyz, float(radius), int(nsample))
     _chk(new_xyz, torch.float32, "new_xyz"); _chk(xyz, torch.float32, "xyz")
     b, n, _ = xyz.shape
     m = new_xyz.shape[1]

@@ -281,7 +281,7 @@ def ose3d_situation(sd: SD, data: dict, *, n_head: int = 8, num_layers: int = 3,
                          sd["orientation_encoder.weight"], sd["orientation_encoder.bias"])
         a_loc = torch.cat([data["anchor_locs"].unsqueeze(1), sd["anchor_size"].expand(B, -1, -1)], -1)
         feat = torch.cat([a_feat, feat], 1)
-        mask = torch.cat([torch.zeros(B, 1, dtype=torch.bool), mask], 1)
+        mask = torch.cat([torch.zeros(B, 1, dtype=torch.bool, device=mask.device), mask], 1)
         ori_feat = torch.cat([a_ori, ori_feat], 1)
         loc = torch.cat([a_loc, loc], 1)
         type_emb = torch.cat([type_w[1].view(1, 1, H).expand(B, 1, -1), type_emb], 1)

@@ -15,10 +15,13 @@ FROZEN_PREFIXES = ("obj_encoder.",)
 
 class CpuHotPath:
     def __init__(self, sd: dict, situation_type="as_transform_for_objects", lr=3e-5, weight_decay=0.05,
-                 betas=(0.9, 0.999), grad_norm=5.0, no_decay_bias=False):
+                 betas=(0.9, 0.999), grad_norm=5.0, no_decay_bias=False, device="cpu"):
+        """device="cuda": the same restatement as stock eager torch ops on the GPU with the reference's own
+        CUDA kernels (oracle/_ref) behind FPS / ball query — the GPU baseline of BASELINE.md §4."""
         self.sd = {}
         for k, v in sd.items():
             frozen = k.startswith(FROZEN_PREFIXES) or k == "anchor_size" or not v.is_floating_point()
+            v = v.to(device)
             self.sd[k] = v.clone() if frozen else v.clone().requires_grad_(True)
         self.situation_type = situation_type
         self.grad_norm = grad_norm
@@ -35,7 +38,7 @@ class CpuHotPath:
     def forward(self, data: dict):
         return mo.ose3d_situation(self.sd, data, situation_type=self.situation_type)
 
-    def step(self, data: dict, upstream: torch.Tensor) -> float:
+    def step(self, data: dict, upstream: torch.Tensor, sync: bool = True):
         self.opt.zero_grad(set_to_none=True)
         tokens, _ = self.forward(data)
         loss = (tokens * upstream).sum()
@@ -47,4 +50,4 @@ class CpuHotPath:
             for g in grads:
                 g.mul_(scale)
         self.opt.step()
-        return float(loss.detach())
+        return float(loss.detach()) if sync else loss.detach()

@@ -10,43 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-class AttrDict(dict):
-    def __getattr__(self, k):
-        try:
-            return self[k]
-        except KeyError as e:
-            raise AttributeError(k) from e
-
-    def __setattr__(self, k, v):
-        self[k] = v
-
-
-def to_attr(o):
-    if isinstance(o, dict):
-        return AttrDict({k: to_attr(v) for k, v in o.items()})
-    if isinstance(o, (list, tuple)):
-        return [to_attr(v) for v in o]
-    return o
-
-
-def prompter_cfg(situation_type="as_transform_for_objects", fusion="cond", **spatial_over):
-    """configs/msr3d.yaml:174-217 as a plain attribute dict (what hydra hands the reference)."""
-    se = {"dim_loc": 6, "num_attention_heads": 8, "dim_feedforward": 2048, "dropout": 0.1,
-          "activation": "gelu", "spatial_multihead": True, "spatial_dim": 5, "spatial_dist_norm": True,
-          "spatial_attn_fusion": fusion, "num_layers": 3, "obj_loc_encoding": "same_all",
-          "pairwise_rel_type": "center"}
-    se.update(spatial_over)
-    return to_attr({"model": {
-        "name": "OSE3DSituation", "situation_type": situation_type, "scene_token_len": 60,
-        "loc_fourier_dim": 63, "hidden_size": 256, "label_size": 300, "vision_backbone_name": "gtpcd",
-        "use_spatial_attn": True, "use_anchor": True, "use_orientation": True, "fourier_size": 84,
-        "attn_flat": {"use_attn_flat": False, "mcan_flat_mlp_size": 512, "mcan_flat_glimpses": 1,
-                      "mcan_flat_out_size": 1024},
-        "vision": {"name": "PcdObjEncoder", "args": {
-            "sa_n_points": [32, 16, None], "sa_n_samples": [32, 32, None], "sa_radii": [0.2, 0.4, None],
-            "sa_mlps": [[3, 64, 64, 128], [128, 128, 128, 256], [256, 256, 512, 768]],
-            "dropout": 0.1, "freeze": True, "path": None}},
-        "spatial_encoder": se}})
+from msr3d_b200.configs import AttrDict, to_attr, prompter_cfg, build_prompter  # noqa: E402,F401  (moved into the package)
 
 
 def load_spec():
@@ -56,15 +20,6 @@ def load_spec():
 
 def golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
-
-
-def build_prompter(seed, situation_type="as_transform_for_objects", device="cpu"):
-    import msr3d_b200
-    model = msr3d_b200.build_model(prompter_cfg(situation_type))
-    sd = synthetic.make_state_dict(load_spec(), seed)
-    # other situation modes own a subset of the shipped model's keys; values are keyed by name
-    model.load_state_dict({k: sd[k] for k in model.state_dict()}, strict=True)
-    return model.to(device).eval()
 
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:

@@ -6,7 +6,7 @@ import torch
 import msr3d_b200
 from msr3d_b200 import synthetic
 from msr3d_b200.fused import FusedPrompter
-from tests import helpers
+from msr3d_b200 import configs as helpers
 
 B, O, P = synthetic.CONFIGS["cfg2_60x1024"]
 model = helpers.build_prompter(0, device="cuda").train()
