@@ -72,20 +72,9 @@ constexpr int kFirstConvWarp = 4;
 
 enum { EPI3_PLAIN = 0, EPI3_FFN1 = 2, EPI3_MUL_AUX = 3 };
 
-// Optional per-CTA timeline (tools/trace_kernels.py): slot s of CTA c = SM clock at a phase boundary.
-// g_trace is a device pointer set by msr3d_set_trace_buffer (nullptr = off, the default).
-constexpr int kTraceSlots = 16;
-__device__ long long *g_trace = nullptr;
-__device__ __forceinline__ void trace_mark(int slot) {
-  long long *t = g_trace;
-  if (t != nullptr) {
-    const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    t[(size_t)cta * kTraceSlots + slot] = clock64();
-  }
-}
-
 struct alignas(64) Gemm3xParams {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_out;
+  int tma_out;                    // output goes through shared memory + TMA store / reduce-add (map_out valid)
   int a_mn, b_mn;                 // operand orientation (1 = MN-major, i.e. stored [k][mn])
   int b_static;                   // B is not written by any kernel of the current step (weights)
   int M, N, K;
@@ -124,7 +113,88 @@ __device__ __forceinline__ void red_add4(float *p, float a, float b, float c, fl
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// Epilogue of one 128 x BN accumulator: 8 warps = 4 lane quarters x 2 column halves, 16 columns per step.
+// Epilogue through shared memory: TMEM -> registers (bias, * aux, + residual) -> swizzled [128 x 32] boxes in the
+// (now idle) operand ring -> ONE TMA store / reduce-add per box.  A thread owns a TMEM lane = an output ROW, so
+// direct global stores touch 32 different 128 B lines per warp instruction (half a sector each): the round-1
+// style epilogue below cost 1.2 us per 128 x 64 tile and 4.2 us per 128 x 256 tile of red.add
+// (tools/trace_kernels.py); the bulk tensor copy writes full lines and clips the M / N tails in hardware.
+template <int BN>
+__device__ __forceinline__ void epilogue3x_tma(const Gemm3xParams &g, uint32_t tmem_d, uint8_t *stage, int m0, int n_base,
+                                               int cw, int lane, uint64_t *acc_bar) {
+  const int q = cw & 3, half = cw >> 2;
+  const int r = q * 32 + lane;
+  const int grow = m0 + r;
+  const bool row_ok = grow < g.M;
+  const bool first_split = blockIdx.z == 0;
+  const bool use_bias = g.bias != nullptr && first_split;
+  const bool use_res = g.res != nullptr && first_split && row_ok;
+  const bool use_aux = g.epi == EPI3_MUL_AUX && row_ok;
+  const bool res_vec = ((g.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.res) & 15) == 0);
+  const bool aux_vec = ((g.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.aux) & 15) == 0);
+  const bool bias_vec = (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0;
+  constexpr int kSteps = BN / 32;          // 16-column steps per warp
+  constexpr int kGroup = 2;                // steps whose global operands are in flight together
+  bool waited = false;
+#pragma unroll
+  for (int st0 = 0; st0 < kSteps; st0 += kGroup) {
+    // the global operands of a group of steps are requested together — those of the first group before the
+    // wait for the accumulator
+    float bv[kGroup][16], rv[kGroup][16], av[kGroup][16];
+#pragma unroll
+    for (int u = 0; u < kGroup; ++u) {
+      const int n0 = n_base + half * (BN / 2) + (st0 + u) * 16;
+      const int nv = min(16, g.N - n0);
+      if (nv <= 0) continue;
+      const bool full = nv == 16;
+      if (use_bias) load16(g.bias + n0, full && bias_vec, nv, bv[u]);
+      if (use_res) load16(g.res + (long long)grow * g.ldr + n0, full && res_vec, nv, rv[u]);
+      if (use_aux) load16(g.aux + (long long)grow * g.ldaux + n0, full && aux_vec, nv, av[u]);
+    }
+    if (!waited) {
+      mbar_wait(acc_bar, 0);
+      fence_after_sync();
+      waited = true;
+      if (cw == 0 && lane == 0) trace_mark(6);
+    }
+#pragma unroll
+    for (int u = 0; u < kGroup; ++u) {
+      const int c0 = half * (BN / 2) + (st0 + u) * 16;
+      uint32_t acc[16];
+      tmem_ld16_3x(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+      tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[j] = __uint_as_float(acc[j]);
+        if (use_bias) v[j] += bv[u][j];
+        if (use_aux) v[j] *= av[u][j];
+        if (use_res) v[j] += rv[u][j];
+      }
+      uint8_t *box = stage + (size_t)(c0 >> 5) * (kTileM3 * tma::kRowBytes);
+      const int ch0 = (c0 & 31) >> 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4 *>(box + tma::sw128_offset(r, ch0 + j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  }
+  fence_async_smem();                                   // generic-proxy tile -> visible to the TMA engine
+  tma::named_barrier(1, kConvWarps * 32);
+  if (cw == 0 && tma::elect_one()) {
+#pragma unroll
+    for (int b = 0; b < BN / 32; ++b) {
+      if (n_base + 32 * b >= g.N) break;
+      const uint8_t *box = stage + (size_t)b * (kTileM3 * tma::kRowBytes);
+      if (g.accumulate == 2) tma::reduce_add_2d(&g.map_out, box, n_base + 32 * b, m0);
+      else tma::store_2d(&g.map_out, box, n_base + 32 * b, m0);
+    }
+    tma::store_commit();
+    tma::store_wait_read();
+  }
+  __syncwarp();
+}
+
+// Direct epilogue (fallback: unaligned outputs, the dual-output FFN1 epilogue): 8 warps = 4 lane quarters x 2 column
+// halves, 16 columns per step, row-per-thread global accesses.
 template <int BN>
 __device__ __noinline__ void epilogue3x(const Gemm3xParams &g, uint32_t tmem_d, int m0, int n_base, int cw, int lane,
                                         uint64_t *acc_bar) {
@@ -171,16 +241,16 @@ __device__ __noinline__ void epilogue3x(const Gemm3xParams &g, uint32_t tmem_d, 
       const long long off = (long long)grow * g.ldaux + n0;
       float hh[16], gp[16];
 #pragma unroll
-      for (int j4 = 0; j4 < 16; j4 += 4) {
-        float m[4];
-        drop.mask4((uint64_t)(off + j4), g.epi_site, m);
+      for (int j8 = 0; j8 < 16; j8 += 8) {
+        float m[8];
+        drop.mask8((uint64_t)(off + j8), g.epi_site, m);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float x = v[j4 + j];
-          const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
-          const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-          hh[j4 + j] = x * cdf * m[j];
-          gp[j4 + j] = (cdf + x * pdf) * m[j];
+        for (int j = 0; j < 8; ++j) {
+          const float x = v[j8 + j];
+          float cdf, pdf;
+          gelu_cdf_pdf(x, cdf, pdf);
+          hh[j8 + j] = x * cdf * m[j];
+          gp[j8 + j] = fmaf(x, pdf, cdf) * m[j];
         }
       }
       float *o = g.out + (long long)grow * g.ldo + n0;
@@ -268,6 +338,7 @@ gemm3x_kernel(const __grid_constant__ Gemm3xParams g) {
     fence_mbar_init();
     tma::prefetch_map(&g.map_a);
     tma::prefetch_map(&g.map_b);
+    if (g.tma_out) tma::prefetch_map(&g.map_out);
   }
   if (warp == 2) tmem_alloc(&s_tmem, C::kTmemCols);
   fence_before_sync();
@@ -376,7 +447,9 @@ gemm3x_kernel(const __grid_constant__ Gemm3xParams g) {
       if (lane == 0) mbar_arrive(&conv_done[s]);
     }
     if (ct == 0) trace_mark(4);
-    epilogue3x<BN>(g, tmem_d, m0, n0, cw, lane, &acc_full);
+    // the ring is idle once the accumulator is complete: stage 0 doubles as the output staging tile
+    if (g.tma_out) epilogue3x_tma<BN>(g, tmem_d, smem, m0, n0, cw, lane, &acc_full);
+    else epilogue3x<BN>(g, tmem_d, m0, n0, cw, lane, &acc_full);
     if (ct == 0) trace_mark(11);
   } else {
     pdl_sync();
@@ -429,9 +502,10 @@ using namespace msr3d;
 
 /* Development hook (tools/trace_kernels.py): device buffer of 16 int64 SM-clock slots per CTA that the gemm3x / ffn_pair
  * kernels fill at their phase boundaries; NULL (default) disables tracing. */
+namespace msr3d { int set_trace_spatial(long long *buf); }
 MSR3D_API int msr3d_set_trace_buffer(long long *buf) {
   MSR3D_CUDA(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
-  return MSR3D_OK;
+  return set_trace_spatial(buf);
 }
 
 /* 1 if msr3d_gemm_tf32x3_f32 accepts this descriptor, else 0 (msr3d_last_error() says why). */
@@ -466,6 +540,12 @@ MSR3D_API int msr3d_gemm_tf32x3_f32(const msr3d_gemm_desc *d, int b_static, msr3
   g.bias = d->bias; g.res = d->residual; g.ldr = d->ld_residual;
   g.aux = d->aux; g.ldaux = d->ld_aux; g.aux_out = d->aux_out;
   g.out = d->out; g.ldo = d->ld_out;
+  g.tma_out = (d->epilogue != EPI3_FFN1 && (d->ld_out & 3) == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 &&
+               d->ld_out >= d->N && g_tune[TUNE_GEMM3X_DIRECT_EPI] == 0) ? 1 : 0;
+  if (g.tma_out) {
+    rc = tma::make_map_f32(&g.map_out, d->out, d->M, d->N, d->ld_out, kTileM3, false);
+    if (rc != MSR3D_OK) return rc;
+  }
   g.accumulate = d->accumulate; g.epi = d->epilogue; g.epi_site = d->epi_site;
   g.drop = make_dropout(d->seed, d->dropout_p, d->seed_ptr);
   const int nkc = ceil_div(d->K, kChunk3);
@@ -488,22 +568,25 @@ using namespace umma;
 //            du is also stored (weight gradients of linear1 contract it over the tokens).
 // The 128 x FS hidden tile never leaves the SM between the two GEMMs: epilogue 1 writes it as the big /
 // small tf32 images of the second GEMM's A operand (swizzled K-major tiles) while TMA fetches the B2
-// slice into the shared memory the first GEMM's ring just released.  Partial sums of the second GEMM
-// (one per F slice) are reduced with red.global.add.v4 into a zeroed (forward) / pre-filled (backward,
-// the residual path gradient) output.  Replaces two GEMM launches and a 2 MB round trip of the hidden
-// activation per layer and direction.
+// slice into the shared memory the first GEMM's ring just released.  ALL global traffic is bulk tensor
+// copies: operands and the stored gelu'*mask tile arrive by TMA load; h / gelu'*mask / du leave as TMA
+// stores of swizzled staging tiles; the per-slice partial sums of the second GEMM are reduced into the
+// zeroed (forward) / pre-filled (backward: residual-path gradient) output with TMA reduce-add
+// (cp.reduce.async.bulk.tensor, SASS UTMAREDG).  A thread owns a TMEM lane = a ROW of the tile, so direct
+// global accesses from the epilogues touch 32 different lines per warp instruction: in the first version of
+// this kernel the two epilogues were 11 of its 23 us (tools/trace_kernels.py).
+// Replaces two GEMM launches and a 2 MB round trip of the hidden activation per layer and direction.
 // =====================================================================================================
 constexpr int kHid = 256;   // d_model of the spatial encoder (configs/msr3d.yaml:181)
 
 struct alignas(64) FfnPairParams {
   CUtensorMap map_a, map_b1, map_b2;
+  CUtensorMap map_h;       // [M, F] forward: h (store); backward: du (store)
+  CUtensorMap map_gp;      // [M, F] forward: gelu'(u) * mask (store); backward: the same tensor (load)
+  CUtensorMap map_out2;    // [M, 256] reduce-add
   int M, F;
   const float *bias1;      // forward: linear1.bias [F]
   const float *bias2;      // forward: linear2.bias [256], added by the slice-0 CTAs
-  const float *gp_in;      // backward: gelu'(u) * mask [M, F]
-  float *h_out;            // forward: h [M, F]; backward: du [M, F]
-  float *gp_out;           // forward: gelu'(u) * mask [M, F]
-  float *out2;             // [M, 256], red.add
   unsigned site;
   Dropout drop;
 };
@@ -511,18 +594,23 @@ struct alignas(64) FfnPairParams {
 template <int FS>
 struct FfnPairCfg {
   static constexpr int kNch2 = FS / 32;                                        // K chunks of GEMM 2
-  static constexpr uint32_t kABytes = kTileM3 * tma::kRowBytes;                // 16 KB
+  static constexpr uint32_t kBox = kTileM3 * tma::kRowBytes;                   // 16 KB: one 128 x 32 fp32 box
+  static constexpr uint32_t kABytes = kBox;
   static constexpr uint32_t kB1Bytes = FS * tma::kRowBytes;
   static constexpr uint32_t kBig1 = kABytes + kB1Bytes;
   static constexpr uint32_t kStage1 = 2 * kBig1;
-  static constexpr uint32_t kHTile = kTileM3 * tma::kRowBytes;                 // one 128 x 32 image of h
+  static constexpr uint32_t kHTile = kBox;                                     // one 128 x 32 image of h
   static constexpr uint32_t kHBytes = 2 * kNch2 * kHTile;                      // [big chunks | small chunks]
   static constexpr uint32_t kB2Chunk = kHid * tma::kRowBytes;                  // 32 KB: 256 x 32
   static constexpr uint32_t kB2Big = kNch2 * kB2Chunk;
   static constexpr uint32_t kB2Bytes = 2 * kB2Big;
   static constexpr int kStages = 3;
   static constexpr uint32_t kRing = kStages * kStage1;
-  static constexpr uint32_t kUnion = kRing > kB2Bytes ? kRing : kB2Bytes;      // ring of GEMM 1, then B2
+  static constexpr uint32_t kOut2 = (kHid / 32) * kBox;                        // 128 KB: staging of the second accumulator
+  static constexpr uint32_t kU0 = kRing > kB2Bytes ? kRing : kB2Bytes;
+  static constexpr uint32_t kUnion = kU0 > kOut2 ? kU0 : kOut2;                // GEMM-1 ring, then B2, then output staging
+  static constexpr uint32_t kStageH = kB2Big;                                  // h / gelu' staging = the B2-small region
+  static_assert(2 * kNch2 * kBox <= kB2Big, "hidden-tile staging must fit in the B2-small region");
   static constexpr size_t kSmem = (size_t)kHBytes + kUnion + 1024;
   static constexpr int kF4 = kBig1 / 16;
   static constexpr int kPer = kF4 / (kConvWarps * 32);
@@ -541,10 +629,10 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
   constexpr int kNkc1 = kHid / kChunk3;   // 8 chunks of GEMM 1
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t *hbuf = smem;                    // A operand of GEMM 2
-  uint8_t *ring = smem + C::kHBytes;       // stages of GEMM 1, later the B2 slice
+  uint8_t *hbuf = smem;                    // A operand of GEMM 2: [big chunks | small chunks]
+  uint8_t *ring = smem + C::kHBytes;       // stages of GEMM 1, later the B2 slice, later the output staging
   __shared__ __align__(8) uint64_t full[S], conv_done[S], mma_done[S];
-  __shared__ __align__(8) uint64_t acc1_full, h_ready, b2_full, b2_conv, acc2_full;
+  __shared__ __align__(8) uint64_t acc1_full, h_ready, b2_full, b2_conv, acc2_full, gp_full;
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -564,10 +652,14 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
     mbar_init(&b2_full, 1);
     mbar_init(&b2_conv, kConvWarps);
     mbar_init(&acc2_full, 1);
+    mbar_init(&gp_full, 1);
     fence_mbar_init();
     tma::prefetch_map(&g.map_a);
     tma::prefetch_map(&g.map_b1);
     tma::prefetch_map(&g.map_b2);
+    tma::prefetch_map(&g.map_h);
+    tma::prefetch_map(&g.map_gp);
+    tma::prefetch_map(&g.map_out2);
   }
   if (warp == 2) tmem_alloc(&s_tmem, C::kTmemCols);
   fence_before_sync();
@@ -596,6 +688,15 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
       for (int i = 0; i < S; ++i) {
         mbar_expect_tx(&full[i], C::kBig1);
         load_b1(i);                              // weights: requested while the previous kernel drains
+      }
+      if (BWD) {
+        // gelu'(u) * mask of this tile (written by the forward pass of this step, long complete): lands in the
+        // "small" half of the hidden-tile buffer; every epilogue thread reads its own elements before it
+        // overwrites them with the small image of du
+        mbar_expect_tx(&gp_full, C::kNch2 * C::kBox);
+#pragma unroll
+        for (int c = 0; c < C::kNch2; ++c)
+          tma::load_2d(hbuf + (size_t)(C::kNch2 + c) * C::kHTile, &g.map_gp, f0 + 32 * c, m0, &gp_full);
       }
       pdl_wait();
       trace_mark(2);
@@ -701,66 +802,66 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
       if (lane == 0) mbar_arrive(&conv_done[s]);
     }
     if (ct == 0) trace_mark(4);
-    // ---- epilogue 1: hidden tile -> global (for the backward) and -> shared-memory operand images
+    // ---- epilogue 1: hidden tile -> operand images of GEMM 2 + exact fp32 staging tiles for the TMA stores
     const int q = cw & 3, half = cw >> 2;
     const int r = q * 32 + lane;            // row of the tile = TMEM lane
-    const int grow = m0 + r;
-    const bool row_ok = grow < g.M;
+    uint8_t *stage_h = ring + C::kStageH;                                   // kNch2 boxes: h (forward) / du (backward)
+    uint8_t *stage_gp = stage_h + (size_t)C::kNch2 * C::kBox;               // kNch2 boxes: gelu'(u) * mask (forward)
     Dropout drop = g.drop;
     if (!BWD) drop.resolve();
     {
-      bool waited = false;
-#pragma unroll 1
-      for (int c0 = half * (FS / 2); c0 < (half + 1) * (FS / 2); c0 += 16) {
-        const int n0 = f0 + c0;
-        const long long off = (long long)grow * g.F + n0;
-        float bv[16];
-        if (!BWD) load16(g.bias1 + n0, true, 16, bv);
-        else if (row_ok) load16(g.gp_in + off, true, 16, bv);
-        if (!waited) {
-          mbar_wait(&acc1_full, 0);
-          fence_after_sync();
-          waited = true;
-          if (ct == 0) trace_mark(6);
+      constexpr int kSteps1 = FS / 32;      // 16-column steps of this warp
+      float bvs[kSteps1][16];
+      if (!BWD) {
+#pragma unroll
+        for (int st = 0; st < kSteps1; ++st) load16(g.bias1 + f0 + half * (FS / 2) + st * 16, true, 16, bvs[st]);
+      } else {
+        mbar_wait(&gp_full, 0);
+#pragma unroll
+        for (int st = 0; st < kSteps1; ++st) {
+          const int c0 = half * (FS / 2) + st * 16;
+          const uint8_t *src = hbuf + (size_t)(C::kNch2 + (c0 >> 5)) * C::kHTile;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 t = *reinterpret_cast<const float4 *>(src + tma::sw128_offset(r, ((c0 & 31) >> 2) + j));
+            bvs[st][4 * j] = t.x; bvs[st][4 * j + 1] = t.y; bvs[st][4 * j + 2] = t.z; bvs[st][4 * j + 3] = t.w;
+          }
         }
+      }
+      mbar_wait(&acc1_full, 0);
+      fence_after_sync();
+      if (ct == 0) trace_mark(6);
+#pragma unroll
+      for (int st = 0; st < kSteps1; ++st) {
+        const int c0 = half * (FS / 2) + st * 16;
+        const float (&bv)[16] = bvs[st];
         uint32_t acc[16];
         tmem_ld16_3x(tmem1 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
         tmem_ld_wait();
-        float hv[16];
+        float hv[16], gp[16];
         if (!BWD) {
-          float gp[16];
+          const long long off = (long long)(m0 + r) * g.F + f0 + c0;        // element offset = dropout counter
 #pragma unroll
-          for (int j4 = 0; j4 < 16; j4 += 4) {
-            float m[4];
-            drop.mask4((uint64_t)(off + j4), g.site, m);
+          for (int j8 = 0; j8 < 16; j8 += 8) {
+            float m[8];
+            drop.mask8((uint64_t)(off + j8), g.site, m);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float x = __uint_as_float(acc[j4 + j]) + bv[j4 + j];
-              const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
-              const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-              hv[j4 + j] = row_ok ? x * cdf * m[j] : 0.f;
-              gp[j4 + j] = (cdf + x * pdf) * m[j];
-            }
-          }
-          if (row_ok) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              *reinterpret_cast<float4 *>(g.h_out + off + j) = make_float4(hv[j], hv[j + 1], hv[j + 2], hv[j + 3]);
-              *reinterpret_cast<float4 *>(g.gp_out + off + j) = make_float4(gp[j], gp[j + 1], gp[j + 2], gp[j + 3]);
+            for (int j = 0; j < 8; ++j) {
+              const float x = __uint_as_float(acc[j8 + j]) + bv[j8 + j];
+              float cdf, pdf;
+              gelu_cdf_pdf(x, cdf, pdf);
+              hv[j8 + j] = x * cdf * m[j];
+              gp[j8 + j] = fmaf(x, pdf, cdf) * m[j];
             }
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) hv[j] = row_ok ? __uint_as_float(acc[j]) * bv[j] : 0.f;
-          if (row_ok) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<float4 *>(g.h_out + off + j) = make_float4(hv[j], hv[j + 1], hv[j + 2], hv[j + 3]);
-          }
+          for (int j = 0; j < 16; ++j) hv[j] = __uint_as_float(acc[j]) * bv[j];
         }
-        // operand images: columns c0 .. c0+15 of the slice = K chunk c0 / 32, 16 B chunks (c0 % 32) / 4 ..
+        // columns c0 .. c0+15 of the slice = K chunk c0 / 32, 16 B chunks (c0 % 32) / 4 .. +3 of row r
         const int kc = c0 >> 5, ch0 = (c0 & 31) >> 2;
         uint8_t *big = hbuf + (size_t)kc * C::kHTile, *small = hbuf + (size_t)(C::kNch2 + kc) * C::kHTile;
+        uint8_t *sh = stage_h + (size_t)kc * C::kBox, *sg = stage_gp + (size_t)kc * C::kBox;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint4 b, sm;
@@ -771,6 +872,8 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
           const uint32_t o = tma::sw128_offset(r, ch0 + j);
           *reinterpret_cast<uint4 *>(big + o) = b;
           *reinterpret_cast<uint4 *>(small + o) = sm;
+          *reinterpret_cast<float4 *>(sh + o) = make_float4(hv[4 * j], hv[4 * j + 1], hv[4 * j + 2], hv[4 * j + 3]);
+          if (!BWD) *reinterpret_cast<float4 *>(sg + o) = make_float4(gp[4 * j], gp[4 * j + 1], gp[4 * j + 2], gp[4 * j + 3]);
         }
       }
     }
@@ -779,12 +882,25 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
     __syncwarp();
     if (lane == 0) mbar_arrive(&h_ready);
     if (ct == 0) trace_mark(7);
+    // ---- hidden tile (and gelu'*mask) -> global: TMA stores of the staging boxes.  The staging area is the
+    // B2-small region, so the stores must have READ it before the B2 split below writes there.
+    tma::named_barrier(1, kConvWarps * 32);
+    if (cw == 0 && tma::elect_one()) {
+#pragma unroll
+      for (int c = 0; c < C::kNch2; ++c) {
+        tma::store_2d(&g.map_h, stage_h + (size_t)c * C::kBox, f0 + 32 * c, m0);
+        if (!BWD) tma::store_2d(&g.map_gp, stage_gp + (size_t)c * C::kBox, f0 + 32 * c, m0);
+      }
+      tma::store_commit();
+      tma::store_wait_read();
+    }
+    tma::named_barrier(1, kConvWarps * 32);
     // ---- B2 slice: big / small split in place
     {
       uint4 *tile = reinterpret_cast<uint4 *>(ring);
       mbar_wait(&b2_full, 0);
       if (ct == 0) trace_mark(8);
-#pragma unroll 2
+#pragma unroll 4
       for (int j = 0; j < C::kB2Per; ++j) {
         const float4 v = *reinterpret_cast<const float4 *>(tile + ct + j * (kConvWarps * 32));
         uint4 b, sm;
@@ -800,30 +916,38 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
       if (lane == 0) mbar_arrive(&b2_conv);
       if (ct == 0) trace_mark(9);
     }
-    // ---- epilogue 2: partial [128 x 256] -> red.add
+    // ---- epilogue 2: partial [128 x 256] -> staging boxes (the ring is idle once GEMM 2 is complete) -> TMA reduce-add
     {
       const bool add_bias = !BWD && g.bias2 != nullptr && blockIdx.y == 0;
-      bool waited = false;
-#pragma unroll 1
+      mbar_wait(&acc2_full, 0);
+      fence_after_sync();
+      if (ct == 0) trace_mark(10);
+#pragma unroll 2
       for (int c0 = half * (kHid / 2); c0 < (half + 1) * (kHid / 2); c0 += 16) {
         float bv[16];
         if (add_bias) load16(g.bias2 + c0, true, 16, bv);
-        if (!waited) {
-          mbar_wait(&acc2_full, 0);
-          fence_after_sync();
-          waited = true;
-          if (ct == 0) trace_mark(10);
-        }
         uint32_t acc[16];
         tmem_ld16_3x(tmem2 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
         tmem_ld_wait();
-        if (!row_ok) continue;
-        float *o = g.out2 + (long long)grow * kHid + c0;
+        uint8_t *box = ring + (size_t)(c0 >> 5) * C::kBox;
+        const int ch0 = (c0 & 31) >> 2;
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          red_add4(o + j, __uint_as_float(acc[j]) + (add_bias ? bv[j] : 0.f), __uint_as_float(acc[j + 1]) + (add_bias ? bv[j + 1] : 0.f),
-                   __uint_as_float(acc[j + 2]) + (add_bias ? bv[j + 2] : 0.f), __uint_as_float(acc[j + 3]) + (add_bias ? bv[j + 3] : 0.f));
+        for (int j = 0; j < 4; ++j) {
+          float4 t = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
+                                 __uint_as_float(acc[4 * j + 3]));
+          if (add_bias) { t.x += bv[4 * j]; t.y += bv[4 * j + 1]; t.z += bv[4 * j + 2]; t.w += bv[4 * j + 3]; }
+          *reinterpret_cast<float4 *>(box + tma::sw128_offset(r, ch0 + j)) = t;
+        }
       }
+      fence_async_smem();
+      tma::named_barrier(1, kConvWarps * 32);
+      if (cw == 0 && tma::elect_one()) {
+#pragma unroll
+        for (int b = 0; b < kHid / 32; ++b) tma::reduce_add_2d(&g.map_out2, ring + (size_t)b * C::kBox, 32 * b, m0);
+        tma::store_commit();
+        tma::store_wait_read();
+      }
+      __syncwarp();
       if (ct == 0) trace_mark(11);
     }
   } else {
@@ -849,8 +973,8 @@ static int launch_ffn_pair(const FfnPairParams &g, cudaStream_t stream) {
 }  // namespace msr3d
 
 static int ffn_pair_common(FfnPairParams &g, const float *A, const float *W1, const float *W2, int M, int F, bool bwd,
-                           int fs) {
-  MSR3D_REQUIRE(A && W1 && W2, "ffn_pair: null pointer");
+                           int fs, const float *h_or_du, const float *gp, const float *out2) {
+  MSR3D_REQUIRE(A && W1 && W2 && h_or_du && gp && out2, "ffn_pair: null pointer");
   MSR3D_REQUIRE(M > 0 && F > 0 && (fs == 32 || fs == 64) && F % fs == 0, "ffn_pair: bad sizes M=%d F=%d slice=%d", M, F, fs);
   g.M = M; g.F = F;
   int rc = tma::make_map_f32(&g.map_a, A, M, kHid, kHid, kTileM3, false);
@@ -866,32 +990,36 @@ static int ffn_pair_common(FfnPairParams &g, const float *A, const float *W1, co
     if (rc != MSR3D_OK) return rc;
     rc = tma::make_map_f32(&g.map_b2, W1, F, kHid, kHid, tma::kBoxKRows, true);
   }
-  return rc;
+  if (rc != MSR3D_OK) return rc;
+  rc = tma::make_map_f32(&g.map_h, h_or_du, M, F, F, kTileM3, false);
+  if (rc != MSR3D_OK) return rc;
+  rc = tma::make_map_f32(&g.map_gp, gp, M, F, F, kTileM3, false);
+  if (rc != MSR3D_OK) return rc;
+  return tma::make_map_f32(&g.map_out2, out2, M, kHid, kHid, kTileM3, false);
 }
 
 /* see include/msr3d_b200.h */
 MSR3D_API int msr3d_ffn_pair_fwd_f32(const float *y2, const float *W1, const float *b1, const float *W2, const float *b2,
                                      int M, int F, unsigned long long seed, const unsigned long long *seed_ptr, float p,
                                      unsigned site, float *h, float *gp, float *f_accum, int slice, msr3d_stream_t stream) {
-  MSR3D_REQUIRE(b1 && h && gp && f_accum, "ffn_pair_fwd: null pointer");
+  MSR3D_REQUIRE(b1 && (reinterpret_cast<uintptr_t>(b1) & 15) == 0 && (!b2 || (reinterpret_cast<uintptr_t>(b2) & 15) == 0),
+                "ffn_pair_fwd: biases must be 16 B aligned");
   MSR3D_REQUIRE(p >= 0.f && p < 1.f, "ffn_pair_fwd: bad dropout p");
   FfnPairParams g{};
   const int fs = slice == 32 ? 32 : 64;
-  const int rc = ffn_pair_common(g, y2, W1, W2, M, F, false, fs);
+  const int rc = ffn_pair_common(g, y2, W1, W2, M, F, false, fs, h, gp, f_accum);
   if (rc != MSR3D_OK) return rc;
-  g.bias1 = b1; g.bias2 = b2; g.h_out = h; g.gp_out = gp; g.out2 = f_accum; g.site = site;
+  g.bias1 = b1; g.bias2 = b2; g.site = site;
   g.drop = make_dropout(seed, p, seed_ptr);
   return fs == 32 ? launch_ffn_pair<32, false>(g, (cudaStream_t)stream) : launch_ffn_pair<64, false>(g, (cudaStream_t)stream);
 }
 
 MSR3D_API int msr3d_ffn_pair_bwd_f32(const float *df, const float *W1, const float *W2, const float *gp, int M, int F,
                                      float *du, float *dy2_accum, int slice, msr3d_stream_t stream) {
-  MSR3D_REQUIRE(gp && du && dy2_accum, "ffn_pair_bwd: null pointer");
   FfnPairParams g{};
   const int fs = slice == 32 ? 32 : 64;
-  const int rc = ffn_pair_common(g, df, W1, W2, M, F, true, fs);
+  const int rc = ffn_pair_common(g, df, W1, W2, M, F, true, fs, du, gp, dy2_accum);
   if (rc != MSR3D_OK) return rc;
-  g.gp_in = gp; g.h_out = du; g.out2 = dy2_accum;
   g.drop = make_dropout(0, 0.f);
   return fs == 32 ? launch_ffn_pair<32, true>(g, (cudaStream_t)stream) : launch_ffn_pair<64, true>(g, (cudaStream_t)stream);
 }

@@ -532,7 +532,9 @@ linear_tc_kernel(GemmArgs g) {
 
   if (warp == kProducerWarps) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // the whole warp waits, ONE ELECTED LANE issues: under `if (lane == 0)` the compiler wraps every tcgen05.mma
+    // in an ELECT / BRA.U.ANY serialisation loop (228 of them in the round-1 build of this file)
+    {
       const uint32_t idesc = make_idesc_bf16(kTileM, BN);
       // a K=16 slice is two k columns: the start-address field (16 B units) advances by 2 * LBO / 16
       constexpr uint64_t kStepA = 2 * (lbo_padded(kTileM) >> 4);
@@ -544,35 +546,38 @@ linear_tc_kernel(GemmArgs g) {
         mbar_wait(&full[s], ph);
         if (g.b_mode == 0) mbar_wait(&b_full[s], ph);
         fence_after_sync();
-        const uint32_t a_h = smem_u32(smem + (size_t)s * kStage) + kAOff;
-        const uint32_t b_h = smem_u32(smem + (size_t)s * kStage) + kBOff;
-        uint64_t da[3], db[3];
+        if (elect_one()) {
+          const uint32_t a_h = smem_u32(smem + (size_t)s * kStage) + kAOff;
+          const uint32_t b_h = smem_u32(smem + (size_t)s * kStage) + kBOff;
+          uint64_t da[3], db[3];
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
-          da[t] = make_desc(a_h + t * kATile, lbo_padded(kTileM), 128u);
-          db[t] = make_desc(b_h + t * b_tile, b_lbo, 128u);
-        }
-        if (g.split == 6) {
-#pragma unroll
-          for (int ks = 0; ks < kChunkK / 16; ++ks) {   // smallest products first
-            mma_bf16(tmem_d, da[1] + ks * kStepA, db[1] + ks * kStepB, idesc, (i | ks) ? 1u : 0u);
-            mma_bf16(tmem_d, da[0] + ks * kStepA, db[2] + ks * kStepB, idesc, 1u);
-            mma_bf16(tmem_d, da[2] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
-            mma_bf16(tmem_d, da[0] + ks * kStepA, db[1] + ks * kStepB, idesc, 1u);
-            mma_bf16(tmem_d, da[1] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
-            mma_bf16(tmem_d, da[0] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
+          for (int t = 0; t < 3; ++t) {
+            da[t] = make_desc(a_h + t * kATile, lbo_padded(kTileM), 128u);
+            db[t] = make_desc(b_h + t * b_tile, b_lbo, 128u);
           }
-        } else {
+          if (g.split == 6) {
 #pragma unroll
-          for (int ks = 0; ks < kChunkK / 16; ++ks) {
-            mma_bf16(tmem_d, da[0] + ks * kStepA, db[0] + ks * kStepB, idesc, (i | ks) ? 1u : 0u);
-            if (g.split == 3) {
+            for (int ks = 0; ks < kChunkK / 16; ++ks) {   // smallest products first
+              mma_bf16(tmem_d, da[1] + ks * kStepA, db[1] + ks * kStepB, idesc, (i | ks) ? 1u : 0u);
+              mma_bf16(tmem_d, da[0] + ks * kStepA, db[2] + ks * kStepB, idesc, 1u);
+              mma_bf16(tmem_d, da[2] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
               mma_bf16(tmem_d, da[0] + ks * kStepA, db[1] + ks * kStepB, idesc, 1u);
               mma_bf16(tmem_d, da[1] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
+              mma_bf16(tmem_d, da[0] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < kChunkK / 16; ++ks) {
+              mma_bf16(tmem_d, da[0] + ks * kStepA, db[0] + ks * kStepB, idesc, (i | ks) ? 1u : 0u);
+              if (g.split == 3) {
+                mma_bf16(tmem_d, da[0] + ks * kStepA, db[1] + ks * kStepB, idesc, 1u);
+                mma_bf16(tmem_d, da[1] + ks * kStepA, db[0] + ks * kStepB, idesc, 1u);
+              }
             }
           }
+          mma_commit(&mma_done[s]);   // frees the stage; the last one also releases the epilogue
         }
-        mma_commit(&mma_done[s]);   // frees the stage; the last one also releases the epilogue
+        __syncwarp();
       }
     }
   } else {
@@ -588,7 +593,7 @@ linear_tc_kernel(GemmArgs g) {
       uint8_t *st = smem + (size_t)s * kStage;
       if (i >= 2) mbar_wait(&mma_done[s], ((i >> 1) - 1) & 1);  // stage free again
       if (g.b_mode == 0) {
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
           mbar_expect_tx(&b_full[s], kBBlock);
           bulk_g2s(st + kBOff, g.PW + ((size_t)nt * nkc_total + kc) * kBBlock, kBBlock, &b_full[s]);
         }

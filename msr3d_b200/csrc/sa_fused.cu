@@ -149,7 +149,10 @@ sa_mlp_kernel(const SaParams p) {
   const uint32_t a_addr = smem_u32(s_a), w_addr = smem_u32(s_w);
 
   uint32_t mma_uses = 0, w_uses0 = 0, w_uses1 = 0;
-  if (RESIDENT && tid == 0) {
+  // Everything that drives the uniform datapath (TMA bulk copies, tcgen05.mma / commit) is issued by ONE ELECTED
+  // LANE OF WARP 0 inside a warp-uniform branch: under `if (tid == 0)` the compiler wraps every such instruction
+  // in an ELECT / BRA.U.ANY serialisation loop (53 of them in the round-1 build of this file).
+  if (RESIDENT && warp == 0 && elect_one()) {
     mbar_expect_tx(&bar_w[0], L::kW1 + L::kW2 + L::kW3);
     bulk_g2s(s_w, p.w[0], L::kW1, &bar_w[0]);
     bulk_g2s(s_w + L::kW1, p.w[1], L::kW2, &bar_w[0]);
@@ -168,7 +171,7 @@ sa_mlp_kernel(const SaParams p) {
   for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
     const int cloud = t / tiles_per_cloud;
     const int centre0 = (t % tiles_per_cloud) * 4;
-    if (!RESIDENT && tid == 0) {  // all MMAs of the previous tile are complete: both buffers are free
+    if (!RESIDENT && warp == 0 && elect_one()) {  // all MMAs of the previous tile are complete: both buffers are free
       mbar_expect_tx(&bar_w[0], L::kW1);
       bulk_g2s(s_w, p.w[0], L::kW1, &bar_w[0]);
       mbar_expect_tx(&bar_w[1], L::kW2);
@@ -233,17 +236,20 @@ sa_mlp_kernel(const SaParams p) {
     __syncthreads();
 
     // ---------------- layer 1
-    if (tid == 0) {
+    if (warp == 0) {
       if (RESIDENT) { if (t == (int)blockIdx.x) mbar_wait(&bar_w[0], 0); }
       else mbar_wait(&bar_w[0], w_uses0 & 1);
       fence_after_sync();
-      issue_layer(a_addr, K0P, w_addr, C1, d1, p.split);
-      mma_commit(&bar_mma);
+      if (elect_one()) {
+        issue_layer(a_addr, K0P, w_addr, C1, d1, p.split);
+        mma_commit(&bar_mma);
+      }
+      __syncwarp();
     }
     if (!RESIDENT) ++w_uses0;
     mbar_wait(&bar_mma, mma_uses & 1); ++mma_uses;
     fence_after_sync();
-    if (!RESIDENT && tid == 0) {  // buffer 0 is free: prefetch first half of layer 3
+    if (!RESIDENT && warp == 0 && elect_one()) {  // buffer 0 is free: prefetch first half of layer 3
       mbar_expect_tx(&bar_w[0], L::kW3Block);
       bulk_g2s(s_w, p.w[2], L::kW3Block, &bar_w[0]);
     }
@@ -253,16 +259,19 @@ sa_mlp_kernel(const SaParams p) {
     __syncthreads();
 
     // ---------------- layer 2
-    if (tid == 0) {
+    if (warp == 0) {
       if (!RESIDENT) mbar_wait(&bar_w[1], w_uses1 & 1);
       fence_after_sync();
-      issue_layer(a_addr, C1, RESIDENT ? w_addr + L::kW1 : w_addr + L::kBuf0, C2, d2, p.split);
-      mma_commit(&bar_mma);
+      if (elect_one()) {
+        issue_layer(a_addr, C1, RESIDENT ? w_addr + L::kW1 : w_addr + L::kBuf0, C2, d2, p.split);
+        mma_commit(&bar_mma);
+      }
+      __syncwarp();
     }
     if (!RESIDENT) ++w_uses1;
     mbar_wait(&bar_mma, mma_uses & 1); ++mma_uses;
     fence_after_sync();
-    if (!RESIDENT && tid == 0) {  // buffer 1 is free: second half of layer 3
+    if (!RESIDENT && warp == 0 && elect_one()) {  // buffer 1 is free: second half of layer 3
       mbar_expect_tx(&bar_w[1], L::kW3Block);
       bulk_g2s(s_w + L::kBuf0, p.w[2] + L::kW3Block, L::kW3Block, &bar_w[1]);
     }
@@ -272,21 +281,28 @@ sa_mlp_kernel(const SaParams p) {
     __syncthreads();
 
     // ---------------- layer 3
-    if (tid == 0) {
+    if (warp == 0) {
       fence_after_sync();
       if (RESIDENT) {
-        constexpr int NB = L::kNB3, BNN = C3 / NB;
-        for (int nb = 0; nb < NB; ++nb)
-          issue_layer(a_addr, C2, w_addr + L::kW1 + L::kW2 + nb * L::kW3Block, BNN, d3 + nb * BNN, p.split);
+        if (elect_one()) {
+          constexpr int NB = L::kNB3, BNN = C3 / NB;
+          for (int nb = 0; nb < NB; ++nb)
+            issue_layer(a_addr, C2, w_addr + L::kW1 + L::kW2 + nb * L::kW3Block, BNN, d3 + nb * BNN, p.split);
+          mma_commit(&bar_mma);
+        }
       } else {
         mbar_wait(&bar_w[0], w_uses0 & 1);
         fence_after_sync();
-        issue_layer(a_addr, C2, w_addr, 128, d3, p.split);
+        if (elect_one()) issue_layer(a_addr, C2, w_addr, 128, d3, p.split);
+        __syncwarp();
         mbar_wait(&bar_w[1], w_uses1 & 1);
         fence_after_sync();
-        issue_layer(a_addr, C2, w_addr + L::kBuf0, 128, d3 + 128, p.split);
+        if (elect_one()) {
+          issue_layer(a_addr, C2, w_addr + L::kBuf0, 128, d3 + 128, p.split);
+          mma_commit(&bar_mma);
+        }
       }
-      mma_commit(&bar_mma);
+      __syncwarp();
     }
     if (!RESIDENT) { ++w_uses0; ++w_uses1; }
     mbar_wait(&bar_mma, mma_uses & 1); ++mma_uses;

@@ -152,11 +152,7 @@ __device__ __forceinline__ void row_store(float *p, int lane, const Row8 &r) {
 // dropout masks of this lane's 8 columns of the row starting at element offset `base` (base % 8 == 0)
 __device__ __forceinline__ Row8 drop_mask8(const Dropout &d, size_t base, int lane, unsigned site) {
   Row8 m;
-  float a[4], b[4];
-  d.mask4((uint64_t)base + lane * 8, site, a);
-  d.mask4((uint64_t)base + lane * 8 + 4, site, b);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { m.v[i] = a[i]; m.v[4 + i] = b[i]; }
+  d.mask8((uint64_t)base + lane * 8, site, m.v);   // one Philox block per eight decisions
   return m;
 }
 // y = gamma * xhat + beta; returns xhat in `x`, rstd via out param
@@ -521,6 +517,7 @@ colsum_kernel(const float *__restrict__ src, long long ld, int M, int N, float *
 // Saves P and loc (B,H,L,L) for the backward pass.
 // ---------------------------------------------------------------------------
 constexpr int kDh = 32;
+constexpr size_t kOnePerSmBytes = 116 * 1024;   // more than half of the 227 KB an SM can give its CTAs
 constexpr int kAttnMaxWarps = 16;    // launch bound; the warp count itself is a launch-time choice
 constexpr int kKeysPerLane = kMaxL / 32;  // 4
 
@@ -528,7 +525,9 @@ __global__ void __launch_bounds__(kAttnMaxWarps * 32)
 attn_fwd_kernel(const float *__restrict__ qkvc, int ldq, const float *__restrict__ pw,
                 const unsigned char *__restrict__ key_pad, int L, int H, float *__restrict__ P,
                 float *__restrict__ LOC, float *__restrict__ ctx, int ldc) {
+  if (threadIdx.x == 0) trace_mark(12);
   pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
+  if (threadIdx.x == 0) trace_mark(13);
   extern __shared__ float sm[];
   const int LT = ((L + 31) / 32) * 32;
   float *kT = sm;                 // [32][LT]
@@ -543,6 +542,7 @@ attn_fwd_kernel(const float *__restrict__ qkvc, int ldq, const float *__restrict
     vs[i] = r[2 * D + h * kDh + d];
   }
   __syncthreads();
+  if (threadIdx.x == 0) trace_mark(14);
   const float scale = rsqrtf((float)kDh);
   const int nj = LT / 32;
   const int nwarps = blockDim.x >> 5;
@@ -585,6 +585,7 @@ attn_fwd_kernel(const float *__restrict__ qkvc, int ldq, const float *__restrict
       }
     }
     mx = warp_max(mx);
+    if (threadIdx.x == 0) trace_mark(15);
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < kKeysPerLane; ++j) {
@@ -610,6 +611,7 @@ attn_fwd_kernel(const float *__restrict__ qkvc, int ldq, const float *__restrict
       }
     }
     ctx[((size_t)b * L + l) * ldc + h * kDh + lane] = acc;
+    if (threadIdx.x == 0) trace_mark(8);
   }
 }
 
@@ -754,6 +756,13 @@ __global__ void dropout_mask_kernel(Dropout drop, unsigned site, long long n, fl
 
 }  // namespace msr3d
 
+namespace msr3d {
+int set_trace_spatial(long long *buf) {
+  MSR3D_CUDA(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
+  return MSR3D_OK;
+}
+}  // namespace msr3d
+
 using namespace msr3d;
 
 static inline Dropout mk(unsigned long long seed, float p, const unsigned long long *sp) {
@@ -876,7 +885,17 @@ MSR3D_API int msr3d_attn_fwd_f32(const float *qkvc, int ldq, const float *pw,
                 "attn_fwd: bad sizes L=%d H=%d", L, H);
   if (B == 0) return MSR3D_OK;
   const int LT = ((L + 31) / 32) * 32;
-  const size_t smem = ((size_t)kDh * LT + (size_t)L * kDh) * sizeof(float);
+  size_t smem = ((size_t)kDh * LT + (size_t)L * kDh) * sizeof(float);
+  // ONE CTA PER SM: with programmatic dependent launch the CTAs of this kernel are placed while the GEMM in front
+  // of it still owns most SMs (register file: they cannot co-reside), so the block scheduler packs them two per
+  // SM onto the few free SMs and the kernel runs at half speed there — 14.6 us instead of 8.1 us in the forward
+  // chain (tools/chain_profile.py).  Asking for more than half of the shared memory forces one CTA per SM.
+  static bool configured = false;
+  if (!configured) {
+    MSR3D_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOnePerSmBytes));
+    configured = true;
+  }
+  if (g_tune[TUNE_ATTN_PACK] == 0 && smem < kOnePerSmBytes) smem = kOnePerSmBytes;
   // few (head, scene) pairs and L ~ 60 rows: one warp per query row, rows spread over `zr` CTAs
   int warps = g_tune[TUNE_ATTN_FWD_WARPS] > 0 ? g_tune[TUNE_ATTN_FWD_WARPS] : 16;
   warps = max(1, min(kAttnMaxWarps, warps));
@@ -905,11 +924,13 @@ MSR3D_API int msr3d_attn_bwd_f32(const float *dctx, int ldc, const float *qkvc, 
   };
   static bool configured = false;
   if (!configured) {
-    MSR3D_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)bytes(kMaxL, 1)));
+    const size_t mx = bytes(kMaxL, 1) > kOnePerSmBytes ? bytes(kMaxL, 1) : kOnePerSmBytes;
+    MSR3D_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
     configured = true;
   }
-  launch_pdl_cluster(attn_bwd_kernel, dim3(H, B, nz), dim3(warps * 32), bytes(L, nz), (cudaStream_t)stream,
+  size_t smem_bwd = bytes(L, nz);
+  if (g_tune[TUNE_ATTN_PACK] == 0 && smem_bwd < kOnePerSmBytes) smem_bwd = kOnePerSmBytes;   // one CTA per SM, see attn_fwd
+  launch_pdl_cluster(attn_bwd_kernel, dim3(H, B, nz), dim3(warps * 32), smem_bwd, (cudaStream_t)stream,
                      dim3(1, 1, nz), dctx, ldc, qkvc, ldq, pw, P, LOC, L, H, dqkvc);
   return check_launch("attn_bwd");
 }

@@ -51,6 +51,28 @@ __device__ __forceinline__ void load_2d(void *smem_dst, const CUtensorMap *map, 
       "l"(reinterpret_cast<uint64_t>(map)), "r"(umma::smem_u32(bar)), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+// shared -> global tile store / reduce-add (SASS UTMASTG / UTMAREDG): box at (c_inner, c_outer); rows and columns
+// outside the tensor are clipped by the hardware.  Bulk-group completion: commit, then wait_read before the
+// shared-memory source is reused or the CTA exits.
+__device__ __forceinline__ void store_2d(const CUtensorMap *map, const void *smem_src, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(umma::smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+__device__ __forceinline__ void reduce_add_2d(const CUtensorMap *map, const void *smem_src, int c_inner, int c_outer) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(umma::smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+__device__ __forceinline__ void store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// named barrier among `nthreads` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __device__ __forceinline__ void prefetch_map(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -108,20 +130,7 @@ __device__ __forceinline__ void mma_3x(uint32_t tmem_d, uint64_t a_big, uint64_t
   mma_tf32(tmem_d, a_big, b_big, idesc, 1u);
 }
 
-// one lane of a converged warp (CUTLASS's elect_one_sync): code under `if (elect_one())` compiles to straight
-// uniform-datapath instructions (UTCHMMA, UTMALDG back to back); under `if (lane == 0)` the compiler wraps every
-// such instruction in an ELECT / BRA.U.ANY serialisation loop
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
+using umma::elect_one;
 
 // ---------------------------------------------------------------- device: big / small split
 __device__ __forceinline__ uint32_t rna_tf32(float x) {

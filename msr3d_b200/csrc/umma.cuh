@@ -100,6 +100,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   }
 }
 
+// one lane of a converged warp (CUTLASS's elect_one_sync): code under `if (elect_one())` compiles to straight
+// uniform-datapath instructions (UTCHMMA, UTMALDG back to back); under `if (lane == 0)` the compiler wraps every
+// such instruction in an ELECT / BRA.U.ANY serialisation loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- TMA bulk copy (UBLKCP)
 // 1-D global -> shared bulk copy completing on an mbarrier (size multiple of 16 B).
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes,

@@ -126,7 +126,7 @@ class FusedPrompter:
         assert self.gemm_impl in ("tf32x3", "bf16")
         # fused FFN pair kernels (FFN1 + GELU + dropout + FFN2 / du + dy2): on with the TMA-fed GEMMs
         self.ffn_pair = self.gemm_impl == "tf32x3" and _os0.environ.get("MSR3D_FFN_PAIR", "1") == "1"
-        self.ffn_slice = int(_os0.environ.get("MSR3D_FFN_SLICE", "64"))
+        self.ffn_slice = int(_os0.environ.get("MSR3D_FFN_SLICE", "32"))
         self.split = split                    # transformer GEMMs (forward + data gradients)
         self.enc_split = 3 if split == 6 else split   # frozen encoder: two-way split is ample (1.5e-5)
         self.grad_split = grad_split if split >= 3 else split

@@ -81,11 +81,11 @@ def test_gemm3x_epilogues():
     res = torch.randn(240, 512, generator=g).cuda()
     want = (A.double() @ W.double().t()) * aux.double() + res.double()
     got = gemm_tc(A, W, impl="tf32x3", aux=aux, residual=res, tile_n=64)
-    assert _rel(got, want) < 2e-6
+    assert _rel(got, want) < 5e-6
     # red.add accumulation on top of existing contents
     base = torch.ones(240, 512, device="cuda")
     got = gemm_tc(A, W, impl="tf32x3", out=base.clone(), accumulate=2, ksplit=4, tile_n=128)
-    assert _rel(got, A.double() @ W.double().t() + 1) < 2e-6
+    assert _rel(got, A.double() @ W.double().t() + 1) < 5e-6
 
 
 def _dropout_mask(seed, p, site, n):
