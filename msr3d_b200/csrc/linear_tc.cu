@@ -28,6 +28,11 @@ namespace msr3d {
 
 using namespace umma;
 
+// linear_tma.cu
+int linear_tma_try(const float *A, long long stride_am, long long stride_ak, int M, int K, const void *packed_w,
+                   const float *bias, float *out, long long ldo, int N, int act, int pool, int split, int accumulate,
+                   int tile_n, cudaStream_t stream);
+
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;  // K elements per pipeline stage
 
@@ -706,6 +711,13 @@ MSR3D_API int msr3d_linear_tc_f32(const float *A, long long stride_am, long long
                 "linear_tc: pool=%d must be a power of two <= 32 dividing M", pool);
   MSR3D_REQUIRE(!(accumulate && (pool > 1 || act != 0)), "linear_tc: accumulate needs act=0, pool<=1");
   if (M == 0) return MSR3D_OK;
+  // TMA-fed activation operand (linear_tma.cu) whenever A is K-contiguous and aligned; the register-path kernel
+  // below serves strided / unaligned views, split 1 and accumulation
+  {
+    const int rc = linear_tma_try(A, stride_am, stride_ak, M, K, packed_w, bias, out, ldo, N, act, pool, split, accumulate,
+                                  tile_n, (cudaStream_t)stream);
+    if (rc != MSR3D_ERR_UNSUPPORTED) return rc;
+  }
   GemmArgs g{};
   g.A = A; g.sam = stride_am; g.sak = stride_ak; g.PW = (const uint8_t *)packed_w; g.b_mode = 0;
   g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo; g.act = act; g.pool = pool;

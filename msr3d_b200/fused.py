@@ -106,7 +106,7 @@ class FusedPrompter:
     def __init__(self, model, lr=3e-5, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
                  grad_norm: Optional[float] = 5.0, world_size: int = 1, split: int = 3,
                  grad_split: int = 6, gemm_impl: Optional[str] = None, no_decay_bias: bool = False,
-                 alias_grads: bool = True):
+                 alias_grads: bool = True, chain_sms: Optional[int] = None):
         # NOTE: weight-gradient GEMMs and bias reductions are issued on a side stream (see _run)
         why = supported(model)
         if why is not None:
@@ -156,13 +156,28 @@ class FusedPrompter:
         self._shape = None
         self._keep = []          # ctypes descriptors must outlive the program
         self.graph = None
-        self.side_stream = torch.cuda.Stream(device=dev)
-        self.side_stream2 = torch.cuda.Stream(device=dev)
-        self.hi_stream = torch.cuda.Stream(device=dev, priority=-1)
+        # SM partition (msr3d_b200/partition.py): the transformer chain of batch i and the frozen encoder of batch
+        # i+1 run on disjoint sets of SMs; chain_sms = 0 keeps everything on one set (round-1 behaviour)
+        chain_sms = int(_os0.environ.get("MSR3D_CHAIN_SMS", "0")) if chain_sms is None else int(chain_sms)
+        self.partition = None
+        if chain_sms > 0:
+            from . import partition as _part
+            self.partition = _part.make(dev, chain_sms)
+        if self.partition is not None:
+            part = self.partition
+            self.side_stream, self.side_stream2 = part.stream(0), part.stream(0)
+            self.hi_stream = part.stream(0, priority=-1)
+            self.enc_stream_part = part.stream(1)
+            _C.lib().msr3d_set_tunable(7, part.counts[1])      # persistent SA kernels: one CTA per encoder SM
+        else:
+            self.side_stream = torch.cuda.Stream(device=dev)
+            self.side_stream2 = torch.cuda.Stream(device=dev)
+            self.hi_stream = torch.cuda.Stream(device=dev, priority=-1)
+            self.enc_stream_part = None
         self.copy_stream = torch.cuda.Stream(device=dev)
         self._copied = [torch.cuda.Event(), torch.cuda.Event()]      # H2D of slot s complete
         self._slot_free = [torch.cuda.Event(), torch.cuda.Event()]   # encoder that read slot s complete
-        self.enc_stream = torch.cuda.Stream(device=dev)
+        self.enc_stream = self.enc_stream_part if self.enc_stream_part is not None else torch.cuda.Stream(device=dev)
         self.use_side = True
         self.wgrad_small = True
         # data parallel: all-reduce the gradients of layers >= 1 under the backward of layer 0 (two buckets)
@@ -314,6 +329,13 @@ class FusedPrompter:
         d.seed_ptr = self.seed_counter.data_ptr()
         self._keep.append(d)
         ref = ctypes.byref(d)
+        if self.partition is not None and not (wgrad and side) and d.ksplit > 1:
+            # the chain owns `counts[0]` SMs: a GEMM wider than that would run in two waves
+            bn = d.tile_n if d.tile_n in (64, 128) else 64
+            tiles = -(-M // 128) * -(-N // bn)
+            while d.ksplit > 1 and tiles * d.ksplit > self.partition.counts[0]:
+                d.ksplit -= 1
+            d.tile_n = bn
         if self.gemm_impl == "tf32x3" and _C.lib().msr3d_gemm_tf32x3_supported(ref):
             # TMA-fed 3xTF32 kernel (csrc/gemm3x.cu); the weights of the forward / data-gradient GEMMs are
             # "static" operands (written by the optimiser of the previous step only)
