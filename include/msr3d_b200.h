@@ -277,6 +277,25 @@ int msr3d_attn_fwd_f32(const float *qkvc, int ldq, const float *pw, const unsign
 int msr3d_attn_bwd_f32(const float *dctx, int ldc, const float *qkvc, int ldq, const float *pw,
                        const float *P, const float *LOC, int B, int L, int H, float *dqkvc,
                        msr3d_stream_t stream);
+/* big = x rounded to tf32 (low 13 mantissa bits zero), small = x - big: the two operand images of the "3xTF32"
+ * tensor-core products.  Run once per step over the flat parameter buffer so that no GEMM CTA splits a weight
+ * tile again.  n % 4 == 0, 16 B aligned buffers. */
+int msr3d_split_tf32_f32(const float *src, float *big, float *small, long long n, msr3d_stream_t stream);
+/* The attention block of one encoder layer in ONE launch (cluster of 8 CTAs per scene, CTA = head):
+ * qkvc = x Wqkvc^T + b; P, LOC, ctx as msr3d_attn_fwd_f32; o = ctx Wo^T + bo;
+ * y2 = LN_1(x + drop_1(LN_a(drop_fc(o) + x)))   — transformers.py:205-251, 324-325.
+ * Weights are passed as the big / small images written by msr3d_split_tf32_f32 (Wqkvc = [w_qs; w_ks; w_vs;
+ * lang_cond_fc] (816, 256), Wo (256, 256)).  Outputs: everything the backward pass reads (qkvc (B*L, 816),
+ * P / LOC (B, 8, L, L), ctx, xhat_a, xhat_1, y2 (B*L, 256), rstd_a, rstd_1 (B*L)).  Requires
+ * msr3d_attn_block_supported(L, heads, hidden) (L <= 64, 8 heads, hidden 256). */
+int msr3d_attn_block_supported(int L, int H, int hidden);
+int msr3d_attn_block_fwd_f32(const float *x, const float *wqkvc_big, const float *wqkvc_small, const float *bqkvc,
+                             const float *wo_big, const float *wo_small, const float *bo, const float *pw,
+                             const unsigned char *key_pad, int B, int L, const float *gamma_a, const float *beta_a,
+                             const float *gamma_1, const float *beta_1, unsigned long long seed,
+                             const unsigned long long *seed_ptr, float p, unsigned site_fc, unsigned site_1,
+                             float *qkvc, float *P, float *LOC, float *ctx, float *xhat_a, float *rstd_a,
+                             float *xhat_1, float *rstd_1, float *y2, msr3d_stream_t stream);
 /* y2 = LN_1(x + drop_1(LN_a(drop_fc(o) + x)))  — transformers.py:250-251 then :324-325. */
 int msr3d_attn_tail_fwd_f32(const float *o, const float *x, int M, const float *gamma_a,
                             const float *beta_a, const float *gamma_1, const float *beta_1,

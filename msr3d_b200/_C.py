@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmsr3d_b200.so")
+LIB_PATH = os.environ.get("MSR3D_LIB") or os.path.join(_HERE, "libmsr3d_b200.so")   # MSR3D_LIB: development builds (make trace)
 
 c_int = ctypes.c_int
 c_float = ctypes.c_float

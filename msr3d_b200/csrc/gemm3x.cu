@@ -502,9 +502,11 @@ using namespace msr3d;
 
 /* Development hook (tools/trace_kernels.py): device buffer of 16 int64 SM-clock slots per CTA that the gemm3x / ffn_pair
  * kernels fill at their phase boundaries; NULL (default) disables tracing. */
-namespace msr3d { int set_trace_spatial(long long *buf); }
+namespace msr3d { int set_trace_spatial(long long *buf); int set_trace_attn_block(long long *buf); }
 MSR3D_API int msr3d_set_trace_buffer(long long *buf) {
   MSR3D_CUDA(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
+  const int rc = set_trace_attn_block(buf);
+  if (rc != MSR3D_OK) return rc;
   return set_trace_spatial(buf);
 }
 

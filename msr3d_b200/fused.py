@@ -67,6 +67,10 @@ _C.register_protos({
     "msr3d_dropout_mask_f32": [c_ull, c_vp, c_float, c_uint, c_ll, c_vp, c_vp],
     "msr3d_adamw_clip_step_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_dot_f32": [c_vp, c_vp, c_ll, c_vp, c_vp],
+    "msr3d_split_tf32_f32": [c_vp, c_vp, c_vp, c_ll, c_vp],
+    "msr3d_attn_block_supported": [c_int, c_int, c_int],
+    "msr3d_attn_block_fwd_f32": [c_vp] * 9 + [c_int, c_int] + [c_vp] * 4 + [c_ull, c_vp, c_float, c_uint, c_uint]
+                                + [c_vp] * 9 + [c_vp],
 })
 
 H = 256          # hidden size the fused kernels are built for
@@ -127,6 +131,9 @@ class FusedPrompter:
         # fused FFN pair kernels (FFN1 + GELU + dropout + FFN2 / du + dy2): on with the TMA-fed GEMMs
         self.ffn_pair = self.gemm_impl == "tf32x3" and _os0.environ.get("MSR3D_FFN_PAIR", "1") == "1"
         self.ffn_slice = int(_os0.environ.get("MSR3D_FFN_SLICE", "32"))
+        # attention block of a layer (QKV+cond GEMM, attention core, out-projection, LayerNorm tail) as ONE cluster
+        # kernel (csrc/attn_block.cu); needs the pre-split weight images (flat_big / flat_small)
+        self.attn_block = self.gemm_impl == "tf32x3" and _os0.environ.get("MSR3D_ATTN_BLOCK", "1") == "1"
         self.split = split                    # transformer GEMMs (forward + data gradients)
         self.enc_split = 3 if split == 6 else split   # frozen encoder: two-way split is ample (1.5e-5)
         self.grad_split = grad_split if split >= 3 else split
@@ -202,8 +209,13 @@ class FusedPrompter:
         self.bucket_early = lay["early"]         # gradients of layers >= 1: complete before layer 0's backward
         self.bucket_late = lay["late"]
         self.n_opt = lay["n_opt"]
-        self.flat_p = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        total4 = (total + 3) // 4 * 4
+        self.flat_p = torch.zeros(total4, dtype=torch.float32, device=self.dev)[:total]
         self.flat_g = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        # tf32 big / small operand images of the whole parameter buffer, refreshed once per step (_programs)
+        self.flat_big = torch.zeros(total4, dtype=torch.float32, device=self.dev)
+        self.flat_small = torch.zeros(total4, dtype=torch.float32, device=self.dev)
+        self.n_split = total4
         self.offs = offs
         for n in self.order:
             p = by_name[n]
@@ -223,6 +235,12 @@ class FusedPrompter:
 
     def G(self, name):
         return self.flat_g.data_ptr() + 4 * self.offs[name]
+
+    def PB(self, name):  # big / small tf32 images of a parameter (msr3d_split_tf32_f32)
+        return self.flat_big.data_ptr() + 4 * self.offs[name]
+
+    def PS(self, name):
+        return self.flat_small.data_ptr() + 4 * self.offs[name]
 
     # ------------------------------------------------------------------ workspaces + program
     def _buf(self, *shape, dtype=torch.float32, zero=False):
@@ -376,6 +394,12 @@ class FusedPrompter:
                    P("object_orientation_feat"), P("object_type_embedding.weight"),
                    ptr(w["xhat_l"]), ptr(w["rstd_l"]), ptr(w["xhat_s"]), ptr(w["rstd_s"]), ptr(w["qpos"]), ptr(w["qpos0"]),
                    tag="qpos", side=True)
+        use_ab = self.attn_block and bool(_C.lib().msr3d_attn_block_supported(L, NHEAD, H))
+        self.attn_block_active = use_ab
+        if use_ab:
+            # operand images of the weights: once per step, beside the input encoders
+            self._call(pre_prog, "msr3d_split_tf32_f32", self.flat_p.data_ptr(), self.flat_big.data_ptr(),
+                       self.flat_small.data_ptr(), self.n_split, tag="split_w", side=2)
         fwd.append(("join", None, (), None, False))
         E = self.emb_dim
         self._gemm(fwd, self.emb_ptr, (E, 1), P("obj_linear_projection.weight"), (E, 1), M, H, E, ptr(w["x_in"][0]), H,
@@ -386,16 +410,25 @@ class FusedPrompter:
             sa = pre + "self_attn."
             s0 = i * 8
             x_in = ptr(w["x_in"][i])
-            self._gemm(fwd, x_in, (H, 1), P(sa + "w_qs.weight"), (H, 1), M, QKVC, H, ptr(w["qkvc"][i]), QKVC,
-                       bias=P(sa + "w_qs.bias"), accumulate=2, ksplit=ks_h, tag="qkvc")
-            self._call(fwd, "msr3d_attn_fwd_f32", ptr(w["qkvc"][i]), QKVC, ptr(w["pw"]), ptr(w["key_pad"]), B, L, NHEAD,
-                       ptr(w["P"][i]), ptr(w["LOC"][i]), ptr(w["ctx"][i]), H, tag="attn_core")
-            self._gemm(fwd, ptr(w["ctx"][i]), (H, 1), P(sa + "fc.weight"), (H, 1), M, H, H, ptr(w["o"][i]), H,
-                       bias=P(sa + "fc.bias"), accumulate=2, ksplit=ks_h, tag="out_proj")
-            self._call(fwd, "msr3d_attn_tail_fwd_f32", ptr(w["o"][i]), x_in, M, P(sa + "layer_norm.weight"),
-                       P(sa + "layer_norm.bias"), P(pre + "norm1.weight"), P(pre + "norm1.bias"), seed, sptr, p,
-                       s0 + 0, s0 + 1, ptr(w["xhat_a"][i]), ptr(w["rstd_a"][i]), ptr(w["xhat_1"][i]),
-                       ptr(w["rstd_1"][i]), ptr(w["y2"][i]), tag="attn_tail")
+            if use_ab:
+                self._call(fwd, "msr3d_attn_block_fwd_f32", x_in, self.PB(sa + "w_qs.weight"), self.PS(sa + "w_qs.weight"),
+                           P(sa + "w_qs.bias"), self.PB(sa + "fc.weight"), self.PS(sa + "fc.weight"), P(sa + "fc.bias"),
+                           ptr(w["pw"]), ptr(w["key_pad"]), B, L, P(sa + "layer_norm.weight"), P(sa + "layer_norm.bias"),
+                           P(pre + "norm1.weight"), P(pre + "norm1.bias"), seed, sptr, p, s0 + 0, s0 + 1,
+                           ptr(w["qkvc"][i]), ptr(w["P"][i]), ptr(w["LOC"][i]), ptr(w["ctx"][i]),
+                           ptr(w["xhat_a"][i]), ptr(w["rstd_a"][i]), ptr(w["xhat_1"][i]), ptr(w["rstd_1"][i]),
+                           ptr(w["y2"][i]), tag="attn_block")
+            else:
+                self._gemm(fwd, x_in, (H, 1), P(sa + "w_qs.weight"), (H, 1), M, QKVC, H, ptr(w["qkvc"][i]), QKVC,
+                           bias=P(sa + "w_qs.bias"), accumulate=2, ksplit=ks_h, tag="qkvc")
+                self._call(fwd, "msr3d_attn_fwd_f32", ptr(w["qkvc"][i]), QKVC, ptr(w["pw"]), ptr(w["key_pad"]), B, L, NHEAD,
+                           ptr(w["P"][i]), ptr(w["LOC"][i]), ptr(w["ctx"][i]), H, tag="attn_core")
+                self._gemm(fwd, ptr(w["ctx"][i]), (H, 1), P(sa + "fc.weight"), (H, 1), M, H, H, ptr(w["o"][i]), H,
+                           bias=P(sa + "fc.bias"), accumulate=2, ksplit=ks_h, tag="out_proj")
+                self._call(fwd, "msr3d_attn_tail_fwd_f32", ptr(w["o"][i]), x_in, M, P(sa + "layer_norm.weight"),
+                           P(sa + "layer_norm.bias"), P(pre + "norm1.weight"), P(pre + "norm1.bias"), seed, sptr, p,
+                           s0 + 0, s0 + 1, ptr(w["xhat_a"][i]), ptr(w["rstd_a"][i]), ptr(w["xhat_1"][i]),
+                           ptr(w["rstd_1"][i]), ptr(w["y2"][i]), tag="attn_tail")
             # FFN: h = dropout(gelu(u)) and gelu'(u)*mask are materialised once (the backward reads both)
             if self.ffn_pair:
                 # both GEMMs in one kernel, the hidden tile stays in shared memory (csrc/gemm3x.cu)
