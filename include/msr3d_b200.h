@@ -262,6 +262,12 @@ int msr3d_qpos_fwd_f32(const float *h1, const float *sz, int M, const float *Ws,
                        const float *beta_s, const float *extra_a, const float *extra_b, float *xhat_l,
                        float *rstd_l, float *xhat_s, float *rstd_s, float *qpos, float *qpos0,
                        msr3d_stream_t stream);
+/* Same; qpos0 is additionally ADDED (red.add) into x0_accum (M, 256), the zero-filled layer-0 input that the
+ * object-projection GEMM reduces its split-K partial sums into (the two kernels run side by side). */
+int msr3d_qpos_fwd_acc_f32(const float *h1, const float *sz, int M, const float *Ws, const float *bs,
+                           const float *gamma_l, const float *beta_l, const float *gamma_s, const float *beta_s,
+                           const float *extra_a, const float *extra_b, float *xhat_l, float *rstd_l, float *xhat_s,
+                           float *rstd_s, float *qpos, float *qpos0, float *x0_accum, msr3d_stream_t stream);
 /* dq, dq1, dq2: per-layer gradients wrt qpos, summed on load (dq1/dq2 nullable). */
 int msr3d_qpos_bwd_f32(const float *dq, const float *dq1, const float *dq2, const float *sz, int M,
                        const float *gamma_l,
@@ -338,6 +344,28 @@ int msr3d_adamw_clip_step_f32(float *params, const float *grads, float *exp_avg,
                               long long n, long long decay_begin, long long decay_end, float grad_scale,
                               float *state, unsigned int *ticket, unsigned long long *seed_counter,
                               const float *extra_sumsq, msr3d_stream_t stream);
+int msr3d_adamw_clip_step_zg_f32(float *params, float *grads, float *exp_avg, float *exp_avg_sq, long long n,
+                                 long long decay_begin, long long decay_end, float grad_scale, float *state,
+                                 unsigned int *ticket, unsigned long long *seed_counter, const float *extra_sumsq,
+                                 int zero_grads, msr3d_stream_t stream);
+/* Input staging of a pipelined step in one launch (csrc/stage.cu): rotate k: a[i] <- b[i]; b[i] <- c[i] (c nullable)
+ * over rot_n[k] floats; copy k: dst[i] <- src[i]; masks (bytes): the same rotation and key_pad[i] <- !a[i]. */
+#define MSR3D_STAGE_MAX 8
+typedef struct msr3d_stage_desc {
+  float *rot_a[MSR3D_STAGE_MAX];
+  float *rot_b[MSR3D_STAGE_MAX];
+  const float *rot_c[MSR3D_STAGE_MAX];
+  long long rot_n[MSR3D_STAGE_MAX];
+  float *cp_dst[MSR3D_STAGE_MAX];
+  const float *cp_src[MSR3D_STAGE_MAX];
+  long long cp_n[MSR3D_STAGE_MAX];
+  unsigned char *mask_a, *mask_b;
+  const unsigned char *mask_c;
+  unsigned char *key_pad;
+  long long n_mask;
+  int n_rotate, n_copy;
+} msr3d_stage_desc;
+int msr3d_stage_step(const msr3d_stage_desc *d, msr3d_stream_t stream);
 /* out[0] = <a, b> over n floats (one CTA, fixed summation order): the scalar the training loop reads
  * back (trainer/leo_trainer.py:196-201 logs the loss every step). */
 int msr3d_dot_f32(const float *a, const float *b, long long n, float *out, msr3d_stream_t stream);

@@ -86,9 +86,9 @@ sumsq_kernel(const float *__restrict__ g, long long n, float grad_scale, OptStat
 // and by the global-norm clip coefficient min(1, max_norm / (norm + 1e-6)).
 // Elements [decay_begin, decay_end) get weight decay, the rest (biases, LayerNorm) do not.
 __global__ void __launch_bounds__(256)
-adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+adamw_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
              float *__restrict__ v, long long n, long long decay_begin, long long decay_end, float grad_scale,
-             OptState *st) {
+             OptState *st, int zero_grads) {
   pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   const float norm = sqrtf(st->sumsq);
   const float clip = st->max_norm > 0.f ? fminf(1.f, st->max_norm / (norm + 1e-6f)) : 1.f;
@@ -100,6 +100,7 @@ adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restri
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gs;
+    if (zero_grads) g[i] = 0.f;   // the next step accumulates into a clean buffer: no separate 17 MB memset in front of it
     float pi = p[i];
     if (i >= decay_begin && i < decay_end) pi *= 1.f - lr * wd;  // decoupled weight decay (torch AdamW order)
     const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -148,11 +149,9 @@ using namespace msr3d;
 /* state: MSR3D_OPT_STATE_FLOATS floats on the device {sumsq, step, lr, beta1, beta2, eps, weight_decay, max_norm,
  * then one scratch float per block of the norm reduction};
  * ticket: one zero-initialised uint32 on the device. */
-MSR3D_API int msr3d_adamw_clip_step_f32(float *params, const float *grads, float *exp_avg,
-                                        float *exp_avg_sq, long long n, long long decay_begin,
-                                        long long decay_end, float grad_scale, float *state, unsigned int *ticket,
-                                        unsigned long long *seed_counter, const float *extra_sumsq,
-                                        msr3d_stream_t stream) {
+static int adamw_impl(float *params, float *grads, float *exp_avg, float *exp_avg_sq, long long n, long long decay_begin,
+                      long long decay_end, float grad_scale, float *state, unsigned int *ticket,
+                      unsigned long long *seed_counter, const float *extra_sumsq, int zero_grads, msr3d_stream_t stream) {
   MSR3D_REQUIRE(params && grads && exp_avg && exp_avg_sq && state && ticket, "adamw: null pointer");
   MSR3D_REQUIRE(n >= 0 && decay_begin >= 0 && decay_begin <= decay_end && decay_end <= n, "adamw: bad sizes");
   if (n == 0) return MSR3D_OK;
@@ -164,8 +163,27 @@ MSR3D_API int msr3d_adamw_clip_step_f32(float *params, const float *grads, float
   launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, s, grads, n, grad_scale, st, ticket, seed_counter, extra_sumsq);
   rc = check_launch("sumsq");
   if (rc) return rc;
-  launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq, n, decay_begin, decay_end, grad_scale, st);
+  launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq, n, decay_begin, decay_end, grad_scale, st,
+             zero_grads);
   return check_launch("adamw");
+}
+
+MSR3D_API int msr3d_adamw_clip_step_f32(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, long long n,
+                                        long long decay_begin, long long decay_end, float grad_scale, float *state,
+                                        unsigned int *ticket, unsigned long long *seed_counter, const float *extra_sumsq,
+                                        msr3d_stream_t stream) {
+  return adamw_impl(params, const_cast<float *>(grads), exp_avg, exp_avg_sq, n, decay_begin, decay_end, grad_scale, state, ticket,
+                    seed_counter, extra_sumsq, 0, stream);
+}
+
+/* Same, and the gradient buffer is zeroed as it is consumed (zero_grads != 0): the next step's backward accumulates
+ * into it without a memset in front of the step. */
+MSR3D_API int msr3d_adamw_clip_step_zg_f32(float *params, float *grads, float *exp_avg, float *exp_avg_sq, long long n,
+                                           long long decay_begin, long long decay_end, float grad_scale, float *state,
+                                           unsigned int *ticket, unsigned long long *seed_counter,
+                                           const float *extra_sumsq, int zero_grads, msr3d_stream_t stream) {
+  return adamw_impl(params, grads, exp_avg, exp_avg_sq, n, decay_begin, decay_end, grad_scale, state, ticket, seed_counter,
+                    extra_sumsq, zero_grads, stream);
 }
 
 /* out[0] = sum_i a[i] * b[i] (device scalar), deterministic. */

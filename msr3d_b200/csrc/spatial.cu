@@ -287,7 +287,8 @@ qpos_fwd_kernel(const float *__restrict__ h1, const float *__restrict__ sz, int 
                 const float *__restrict__ Ws, const float *__restrict__ bs, LnParams lnl, LnParams lns,
                 const float *__restrict__ extra_a, const float *__restrict__ extra_b,
                 float *__restrict__ xhat_l, float *__restrict__ rstd_l, float *__restrict__ xhat_s,
-                float *__restrict__ rstd_s, float *__restrict__ qpos, float *__restrict__ qpos0) {
+                float *__restrict__ rstd_s, float *__restrict__ qpos, float *__restrict__ qpos0,
+                float *__restrict__ x0_accum) {
   pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
@@ -314,6 +315,13 @@ qpos_fwd_kernel(const float *__restrict__ h1, const float *__restrict__ sz, int 
   }
   row_store(qpos + base, lane, q);
   row_store(qpos0 + base, lane, q0);
+  if (x0_accum != nullptr) {
+    // layer-0 input = projected object embedding (split-K partial sums reduced with red.add into a zeroed buffer by the
+    // projection GEMM, which runs beside this kernel) + qpos0: one more term of the same reduction
+    float *d = x0_accum + base + lane * 8;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(q0.v[0]), "f"(q0.v[1]), "f"(q0.v[2]), "f"(q0.v[3]) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4), "f"(q0.v[4]), "f"(q0.v[5]), "f"(q0.v[6]), "f"(q0.v[7]) : "memory");
+  }
   if (lane == 0) { rstd_l[row] = rl; rstd_s[row] = rs; }
 }
 
@@ -739,18 +747,38 @@ MSR3D_API int msr3d_ffn_tail_bwd_f32(const float *dy3, int M, const float *gamma
   return check_launch("ffn_tail_bwd");
 }
 
-MSR3D_API int msr3d_qpos_fwd_f32(const float *h1, const float *sz, int M, const float *Ws,
+static int qpos_fwd_impl(const float *h1, const float *sz, int M, const float *Ws,
                                  const float *bs, const float *gamma_l, const float *beta_l,
                                  const float *gamma_s, const float *beta_s, const float *extra_a,
                                  const float *extra_b, float *xhat_l, float *rstd_l, float *xhat_s,
-                                 float *rstd_s, float *qpos, float *qpos0, msr3d_stream_t stream) {
+                                 float *rstd_s, float *qpos, float *qpos0, float *x0_accum, msr3d_stream_t stream) {
   MSR3D_REQUIRE(h1 && sz && Ws && bs && gamma_l && beta_l && gamma_s && beta_s && xhat_l && rstd_l &&
                     xhat_s && rstd_s && qpos && qpos0, "qpos_fwd: null pointer");
   if (M <= 0) return MSR3D_OK;
   launch_pdl(qpos_fwd_kernel, dim3(ln_grid(M)), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, 
       h1, sz, M, Ws, bs, LnParams{gamma_l, beta_l}, LnParams{gamma_s, beta_s}, extra_a, extra_b,
-      xhat_l, rstd_l, xhat_s, rstd_s, qpos, qpos0);
+      xhat_l, rstd_l, xhat_s, rstd_s, qpos, qpos0, x0_accum);
   return check_launch("qpos_fwd");
+}
+
+MSR3D_API int msr3d_qpos_fwd_f32(const float *h1, const float *sz, int M, const float *Ws, const float *bs,
+                                 const float *gamma_l, const float *beta_l, const float *gamma_s, const float *beta_s,
+                                 const float *extra_a, const float *extra_b, float *xhat_l, float *rstd_l, float *xhat_s,
+                                 float *rstd_s, float *qpos, float *qpos0, msr3d_stream_t stream) {
+  return qpos_fwd_impl(h1, sz, M, Ws, bs, gamma_l, beta_l, gamma_s, beta_s, extra_a, extra_b, xhat_l, rstd_l, xhat_s, rstd_s,
+                       qpos, qpos0, nullptr, stream);
+}
+
+/* Same; additionally qpos0 is ADDED (red.add) into x0_accum (M, 256): the layer-0 input is assembled by this kernel and
+ * the object-projection GEMM running side by side, both reducing into one zero-filled buffer. */
+MSR3D_API int msr3d_qpos_fwd_acc_f32(const float *h1, const float *sz, int M, const float *Ws, const float *bs,
+                                     const float *gamma_l, const float *beta_l, const float *gamma_s, const float *beta_s,
+                                     const float *extra_a, const float *extra_b, float *xhat_l, float *rstd_l,
+                                     float *xhat_s, float *rstd_s, float *qpos, float *qpos0, float *x0_accum,
+                                     msr3d_stream_t stream) {
+  MSR3D_REQUIRE(x0_accum != nullptr && (reinterpret_cast<uintptr_t>(x0_accum) & 15) == 0, "qpos_fwd_acc: x0_accum must be 16 B aligned");
+  return qpos_fwd_impl(h1, sz, M, Ws, bs, gamma_l, beta_l, gamma_s, beta_s, extra_a, extra_b, xhat_l, rstd_l, xhat_s, rstd_s,
+                       qpos, qpos0, x0_accum, stream);
 }
 
 MSR3D_API int msr3d_qpos_bwd_f32(const float *dq, const float *dq1, const float *dq2,

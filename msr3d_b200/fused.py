@@ -43,6 +43,17 @@ class GemmDesc(ctypes.Structure):
                 ("row_map", c_vp), ("out_dtype", c_int), ("tile_n", c_int)]
 
 
+STAGE_MAX = 8
+
+
+class StageDesc(ctypes.Structure):
+    """Mirror of `msr3d_stage_desc` (include/msr3d_b200.h)."""
+    _fields_ = [("rot_a", c_vp * STAGE_MAX), ("rot_b", c_vp * STAGE_MAX), ("rot_c", c_vp * STAGE_MAX), ("rot_n", c_ll * STAGE_MAX),
+                ("cp_dst", c_vp * STAGE_MAX), ("cp_src", c_vp * STAGE_MAX), ("cp_n", c_ll * STAGE_MAX),
+                ("mask_a", c_vp), ("mask_b", c_vp), ("mask_c", c_vp), ("key_pad", c_vp), ("n_mask", c_ll),
+                ("n_rotate", c_int), ("n_copy", c_int)]
+
+
 _C.register_protos({
     "msr3d_gemm_tc_f32": [ctypes.POINTER(GemmDesc), c_vp],
     "msr3d_gemm_tf32x3_supported": [ctypes.POINTER(GemmDesc)],
@@ -67,6 +78,9 @@ _C.register_protos({
     "msr3d_dropout_mask_f32": [c_ull, c_vp, c_float, c_uint, c_ll, c_vp, c_vp],
     "msr3d_adamw_clip_step_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_dot_f32": [c_vp, c_vp, c_ll, c_vp, c_vp],
+    "msr3d_adamw_clip_step_zg_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
+    "msr3d_qpos_fwd_acc_f32": [c_vp, c_vp, c_int] + [c_vp] * 15 + [c_vp],
+    "msr3d_stage_step": [ctypes.POINTER(StageDesc), c_vp],
     "msr3d_split_tf32_f32": [c_vp, c_vp, c_vp, c_ll, c_vp],
     "msr3d_attn_block_supported": [c_int, c_int, c_int],
     "msr3d_attn_block_fwd_f32": [c_vp] * 9 + [c_int, c_int] + [c_vp] * 4 + [c_ull, c_vp, c_float, c_uint, c_uint]
@@ -260,6 +274,9 @@ class FusedPrompter:
         w["anchor_ori"] = f(B, 4)
         w["upstream"] = f(M, H)
         w["pw"], w["ff"], w["sz"] = f(B, L, L, 5), f(M, 64), f(M, 3)
+        # prefetch schedule: the geometry of the batch being encoded is computed beside the encoder (it depends on
+        # the inputs only) and handed to the next step
+        w["pw_n"], w["ff_n"], w["sz_n"] = f(B, L, L, 5), f(M, 64), f(M, 3)
         w["h1"], w["qpos"], w["qpos0"] = f(M, H), f(M, H), f(M, H)
         for k in ("xhat_l", "xhat_s"):
             w[k] = f(M, H)
@@ -384,27 +401,37 @@ class FusedPrompter:
         # split-K factors: tools/gemm_sweep.py (one 64-wide K chunk per CTA wherever the epilogue is linear)
         ks_h = max(1, -(-H // 64))
         pre_prog.append(("memset", None, (w["arena_f"],), None, False))
-        self._call(pre_prog, "msr3d_spatial_geometry_f32", ptr(w["obj_locs"]), ptr(w["anchor_locs"]), ptr(w["anchor_ori"]),
+        geo: List = []
+        self._call(geo, "msr3d_spatial_geometry_f32", ptr(w["obj_locs"]), ptr(w["anchor_locs"]), ptr(w["anchor_ori"]),
                    B, L, self.dist_norm, 1, ptr(w["pw"]), ptr(w["ff"]), ptr(w["sz"]), tag="geometry", side=True)
+        # prefetch schedule: geometry of the batch in point-cloud slot s, from its freshly copied inputs, for the NEXT step
+        self.geo_prog = []
+        for q in ("_q0", "_q1"):
+            gq: List = []
+            self._call(gq, "msr3d_spatial_geometry_f32", ptr(w["obj_locs" + q]), ptr(w["anchor_locs" + q]), ptr(w["anchor_ori" + q]),
+                       B, L, self.dist_norm, 1, ptr(w["pw_n"]), ptr(w["ff_n"]), ptr(w["sz_n"]), tag="geometry")
+            self.geo_prog.append(gq)
         self._gemm(pre_prog, ptr(w["ff"]), (64, 1), P("loc_embedding_encoder.0.weight"), (63, 1), M, H, 63, ptr(w["h1"]), H,
                    bias=P("loc_embedding_encoder.0.bias"), tag="loc_fc", side=True)
-        self._call(pre_prog, "msr3d_qpos_fwd_f32", ptr(w["h1"]), ptr(w["sz"]), M, P("size_embedding_encoder.0.weight"),
+        # qpos0 is reduced into the (zero-filled) layer-0 input together with the split-K partial sums of the projection
+        self._call(pre_prog, "msr3d_qpos_fwd_acc_f32", ptr(w["h1"]), ptr(w["sz"]), M, P("size_embedding_encoder.0.weight"),
                    P("size_embedding_encoder.0.bias"), P("loc_embedding_encoder.1.weight"), P("loc_embedding_encoder.1.bias"),
                    P("size_embedding_encoder.1.weight"), P("size_embedding_encoder.1.bias"),
                    P("object_orientation_feat"), P("object_type_embedding.weight"),
                    ptr(w["xhat_l"]), ptr(w["rstd_l"]), ptr(w["xhat_s"]), ptr(w["rstd_s"]), ptr(w["qpos"]), ptr(w["qpos0"]),
-                   tag="qpos", side=True)
+                   ptr(w["x_in"][0]), tag="qpos", side=True)
+        pre_prog[1:1] = geo                              # geometry first on the side stream
         use_ab = self.attn_block and bool(_C.lib().msr3d_attn_block_supported(L, NHEAD, H))
         self.attn_block_active = use_ab
         if use_ab:
             # operand images of the weights: once per step, beside the input encoders
             self._call(pre_prog, "msr3d_split_tf32_f32", self.flat_p.data_ptr(), self.flat_big.data_ptr(),
                        self.flat_small.data_ptr(), self.n_split, tag="split_w", side=2)
-        fwd.append(("join", None, (), None, False))
         E = self.emb_dim
+        # the projection runs beside the query-position kernels (side stream); both reduce into x_in[0]
         self._gemm(fwd, self.emb_ptr, (E, 1), P("obj_linear_projection.weight"), (E, 1), M, H, E, ptr(w["x_in"][0]), H,
-                   bias=P("obj_linear_projection.bias"), residual=ptr(w["qpos0"]), ldr=H, accumulate=2,
-                   ksplit=max(1, -(-E // 64)), tag="obj_proj")
+                   bias=P("obj_linear_projection.bias"), accumulate=2, ksplit=max(1, -(-E // 64)), tag="obj_proj")
+        fwd.append(("join", None, (), None, False))
         for i in range(nl):
             pre = f"spatial_encoder.{i}."
             sa = pre + "self_attn."
@@ -523,6 +550,9 @@ class FusedPrompter:
         self._gemm(bwd, ptr(w["dh1"]), (1, H), ptr(w["ff"]), (1, 64), H, 63, M, G("loc_embedding_encoder.0.weight"), 63,
                    accumulate=2, ksplit=4, tag="dWloc", wgrad=True)
         bwd.append(("join", None, (), None, False))
+        # prefetch schedule: the geometry was computed beside the encoder of the previous step
+        # and the gradient buffer is cleared beside the input encoders (first written by the backward pass)
+        self.pre_prog_nogeo = [e for e in pre_prog if e[3] != "geometry"] + [("memset", None, (self.flat_g,), None, 2)]
         return pre_prog, fwd, bwd
 
     def _run(self, prog):
@@ -540,7 +570,14 @@ class FusedPrompter:
                         self._side_pending[k] = False
                 continue
             if fn is None:                  # memset of a workspace tensor
-                args[0].zero_()
+                if on_side and self.use_side:
+                    k = int(on_side) - 1
+                    sides[k].wait_stream(main)
+                    self._side_pending[k] = True
+                    with torch.cuda.stream(sides[k]):
+                        args[0].zero_()
+                else:
+                    args[0].zero_()
                 continue
             if on_side and self.use_side:
                 k = int(on_side) - 1
@@ -629,18 +666,28 @@ class FusedPrompter:
         if part == 2:
             self._run(self.bwd_prog[self.bwd_split:])
             return
-        for k in ("obj_locs", "obj_masks", "anchor_locs", "anchor_ori", "upstream"):
-            w[k].copy_(w[k + "_n"])
-            if depth2:
-                w[k + "_n"].copy_(w[k + ("_q1" if slot else "_q0")])
-        w["emb"].copy_(w["emb_next"])
-        if with_encoder:                       # fork: encoder of the incoming batch
-            self.enc_stream.wait_stream(main)
-            with torch.cuda.stream(self.enc_stream):
-                self._encode("emb_next", "obj_fts_b" if slot else "obj_fts")
-        self.flat_g.zero_()
-        torch.logical_not(w["obj_masks"], out=w["key_pad"].view(torch.bool))
-        self._run(self.pre_prog)
+        if depth2:
+            # ONE launch moves every staged input one generation on (csrc/stage.cu)
+            rc = _C.lib().msr3d_stage_step(ctypes.byref(self._stage_desc(slot)), main.cuda_stream)
+            if rc != 0:
+                raise _C.Msr3dError(f"stage_step failed ({rc}): {_C.lib().msr3d_last_error().decode()}")
+            if with_encoder:                   # fork: geometry + encoder of the incoming batch
+                self.enc_stream.wait_stream(main)
+                with torch.cuda.stream(self.enc_stream):
+                    self._run(self.geo_prog[slot])
+                    self._encode("emb_next", "obj_fts_b" if slot else "obj_fts")
+            self._run(self.pre_prog_nogeo)
+        else:
+            for k in ("obj_locs", "obj_masks", "anchor_locs", "anchor_ori", "upstream"):
+                w[k].copy_(w[k + "_n"])
+            w["emb"].copy_(w["emb_next"])
+            if with_encoder:                       # fork: encoder of the incoming batch
+                self.enc_stream.wait_stream(main)
+                with torch.cuda.stream(self.enc_stream):
+                    self._encode("emb_next", "obj_fts_b" if slot else "obj_fts")
+            self.flat_g.zero_()
+            torch.logical_not(w["obj_masks"], out=w["key_pad"].view(torch.bool))
+            self._run(self.pre_prog)
         self._run(self.fwd_prog)
         if part == 1:
             self._run(self.bwd_prog[:self.bwd_split] + [("join", None, (), None, False)])
@@ -650,6 +697,27 @@ class FusedPrompter:
                 self.optimizer_step()
         if with_encoder:
             main.wait_stream(self.enc_stream)  # join
+
+    def _stage_desc(self, slot):
+        """Descriptor of the staging launch of a prefetch-schedule step that encodes the batch in `slot` (kept alive
+        in self._stage_keep: a captured graph holds no reference to host memory, but eager launches read it)."""
+        cache = self.__dict__.setdefault("_stage_keep", {})
+        if slot in cache and cache[slot][0] is self.ws:
+            return cache[slot][1]
+        w, q = self.ws, "_q1" if slot else "_q0"
+        d = StageDesc()
+        rot = [k for k in ("obj_locs", "anchor_locs", "anchor_ori", "upstream")]
+        for i, k in enumerate(rot):
+            d.rot_a[i], d.rot_b[i], d.rot_c[i], d.rot_n[i] = w[k].data_ptr(), w[k + "_n"].data_ptr(), w[k + q].data_ptr(), w[k].numel()
+        d.n_rotate = len(rot)
+        cps = [("emb", "emb_next"), ("pw", "pw_n"), ("ff", "ff_n"), ("sz", "sz_n")]
+        for i, (a, b) in enumerate(cps):
+            d.cp_dst[i], d.cp_src[i], d.cp_n[i] = w[a].data_ptr(), w[b].data_ptr(), w[a].numel()
+        d.n_copy = len(cps)
+        d.mask_a, d.mask_b, d.mask_c = w["obj_masks"].data_ptr(), w["obj_masks_n"].data_ptr(), w["obj_masks" + q].data_ptr()
+        d.key_pad, d.n_mask = w["key_pad"].data_ptr(), w["obj_masks"].numel()
+        cache[slot] = (self.ws, d)
+        return d
 
     def train_step_pipelined(self, flush=False):
         """Transformer step on the staged batch (+ encoder of the batch in `obj_fts` unless flush)."""
@@ -711,6 +779,7 @@ class FusedPrompter:
         self.prefetch(batch0, up0, 0)
         main.wait_event(self._copied[0])
         self._encode("emb_next", "obj_fts")
+        self._run(self.geo_prog[0])
         for k in ("obj_locs", "obj_masks", "anchor_locs", "anchor_ori", "upstream"):
             self.ws[k + "_n"].copy_(self.ws[k + "_q0"])
         self._slot_free[0].record()
@@ -764,6 +833,7 @@ class FusedPrompter:
         w = self.ws
         keys = [k + lv for k in ("obj_locs", "obj_masks", "anchor_locs", "anchor_ori", "upstream")
                 for lv in ("", "_n", "_q0", "_q1")]
+        keys += ["pw", "ff", "sz", "pw_n", "ff_n", "sz_n"]
         saved = [t.clone() for t in (self.flat_p, self.m, self.v, self.opt_state, self.seed_counter, w["emb"], w["emb_next"])]
         saved_in = {k: w[k].clone() for k in keys}
         torch.cuda.synchronize()
@@ -803,16 +873,17 @@ class FusedPrompter:
         """Backward from ws['upstream']; accumulates into the flat gradient buffer."""
         self._run(self.bwd_prog)
 
-    def optimizer_step(self):
+    def optimizer_step(self, zero_grads: bool = False):
         """Global-norm clip + AdamW over the flat buffer.  `self.extra_sumsq` (a 1-element CUDA tensor, optional)
         is added to the squared gradient norm: set it to the squared norm of the trainable parameters that live
         outside this engine (llm_proj, LoRA, ...) to reproduce the reference's clip over ALL model parameters
         (trainer/leo_trainer.py:192-193); the caller then scales its own gradients by `clip_coef()`."""
         n, (d0, d1) = self.n_opt, self.decay_range
         ex = self.extra_sumsq.data_ptr() if self.extra_sumsq is not None else None
-        _C.call("msr3d_adamw_clip_step_f32", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(),
+        _C.call("msr3d_adamw_clip_step_zg_f32", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(),
                 self.v.data_ptr(), n, d0, d1, 1.0 / self.world_size, self.opt_state.data_ptr(),
-                self.ticket.data_ptr(), self.seed_counter.data_ptr(), ex, torch.cuda.current_stream().cuda_stream)
+                self.ticket.data_ptr(), self.seed_counter.data_ptr(), ex, 1 if zero_grads else 0,
+                torch.cuda.current_stream().cuda_stream)
 
     def clip_coef(self) -> torch.Tensor:
         """min(1, max_norm / (||g|| + 1e-6)) of the last optimizer_step (device scalar), for parameters the
