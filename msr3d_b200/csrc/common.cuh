@@ -50,7 +50,7 @@ extern int g_pdl;
 // Tuning knobs (msr3d_set_tunable): 0 = library heuristics.  Used by tools/gemm_sweep.py to pick the
 // heuristics' constants on the hardware; the product never changes them.
 enum { TUNE_GEMM_BN = 0, TUNE_GEMM_KSPLIT = 1, TUNE_ATTN_FWD_WARPS = 2, TUNE_ATTN_BWD_WARPS = 3,
-       TUNE_ATTN_FWD_ZSPLIT = 4, TUNE_ATTN_BWD_CLUSTER = 5, TUNE_SA_GROUP_FUSED = 6, TUNE_SA_SM_LIMIT = 7, TUNE_GRAD_ATOMICS = 8, TUNE_GEMM3X_DIRECT_EPI = 9, TUNE_ATTN_PACK = 10, TUNE_LINEAR_TMA_OFF = 11, TUNE_COUNT = 12 };
+       TUNE_ATTN_FWD_ZSPLIT = 4, TUNE_ATTN_BWD_CLUSTER = 5, TUNE_SA_GROUP_FUSED = 6, TUNE_SA_SM_LIMIT = 7, TUNE_GRAD_ATOMICS = 8, TUNE_GEMM3X_DIRECT_EPI = 9, TUNE_ATTN_PACK = 10, TUNE_LINEAR_TMA_OFF = 11, TUNE_SA_OVERSUB = 12, TUNE_COUNT = 14 };
 extern int g_tune[TUNE_COUNT];
 #if defined(__CUDACC__)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
