@@ -192,6 +192,14 @@ int msr3d_ffn_pair_fwd_f32(const float *y2, const float *W1, const float *b1, co
                            unsigned site, float *h, float *gp, float *f_accum, int slice, msr3d_stream_t stream);
 int msr3d_ffn_pair_bwd_f32(const float *df, const float *W1, const float *W2, const float *gp, int M, int F,
                            float *du, float *dy2_accum, int slice, msr3d_stream_t stream);
+/* Pre-split variants of the pair: activations and weights as big / small tf32 images (no conversion in the kernel). */
+int msr3d_ffn_pair_fwd_ps_f32(const float *y2_big, const float *y2_small, const float *W1_big, const float *W1_small,
+                              const float *b1, const float *W2_big, const float *W2_small, const float *b2, int M, int F,
+                              unsigned long long seed, const unsigned long long *seed_ptr, float p, unsigned site,
+                              float *h, float *gp, float *f_accum, int slice, msr3d_stream_t stream);
+int msr3d_ffn_pair_bwd_ps_f32(const float *df_big, const float *df_small, const float *W1_big, const float *W1_small,
+                              const float *W2_big, const float *W2_small, const float *gp, int M, int F, float *du,
+                              float *dy2_accum, int slice, msr3d_stream_t stream);
 /* ------------------------------------------------------------------ group E
  * Scene-token splice into the LLM input (the step right after the path):
  * MSR3D.build_embeds, model/msr3d/msr3d.py:277-287 —
@@ -302,6 +310,15 @@ int msr3d_attn_block_fwd_f32(const float *x, const float *wqkvc_big, const float
                              const unsigned long long *seed_ptr, float p, unsigned site_fc, unsigned site_1,
                              float *qkvc, float *P, float *LOC, float *ctx, float *xhat_a, float *rstd_a,
                              float *xhat_1, float *rstd_1, float *y2, msr3d_stream_t stream);
+/* Same; additionally y2's big / small tf32 images (B*L, 256 each) for msr3d_ffn_pair_fwd_ps_f32. */
+int msr3d_attn_block_fwd_ps_f32(const float *x, const float *wqkvc_big, const float *wqkvc_small, const float *bqkvc,
+                                const float *wo_big, const float *wo_small, const float *bo, const float *pw,
+                                const unsigned char *key_pad, int B, int L, const float *gamma_a, const float *beta_a,
+                                const float *gamma_1, const float *beta_1, unsigned long long seed,
+                                const unsigned long long *seed_ptr, float p, unsigned site_fc, unsigned site_1,
+                                float *qkvc, float *P, float *LOC, float *ctx, float *xhat_a, float *rstd_a,
+                                float *xhat_1, float *rstd_1, float *y2, float *y2_big, float *y2_small,
+                                msr3d_stream_t stream);
 /* y2 = LN_1(x + drop_1(LN_a(drop_fc(o) + x)))  — transformers.py:250-251 then :324-325. */
 int msr3d_attn_tail_fwd_f32(const float *o, const float *x, int M, const float *gamma_a,
                             const float *beta_a, const float *gamma_1, const float *beta_1,
@@ -323,6 +340,11 @@ int msr3d_ffn_tail_bwd_f32(const float *dy3, int M, const float *gamma_2, unsign
                            const unsigned long long *seed_ptr, float p, unsigned site_2, const float *xhat_2, const float *rstd_2,
                            float *dy2, float *df, float *dgamma_2, float *dbeta_2, float *dbias_2,
                            msr3d_stream_t stream);
+/* Same; additionally df's big / small tf32 images (M, 256 each) for msr3d_ffn_pair_bwd_ps_f32. */
+int msr3d_ffn_tail_bwd_ps_f32(const float *dy3, int M, const float *gamma_2, unsigned long long seed,
+                              const unsigned long long *seed_ptr, float p, unsigned site_2, const float *xhat_2,
+                              const float *rstd_2, float *dy2, float *df, float *dgamma_2, float *dbeta_2, float *dbias_2,
+                              float *df_big, float *df_small, msr3d_stream_t stream);
 /* Test hook: the multiplicative dropout mask (0 or 1/(1-p)) applied at `site` to offsets [0,n). */
 int msr3d_dropout_mask_f32(unsigned long long seed, const unsigned long long *seed_ptr, float p,
                            unsigned site, long long n, float *out, msr3d_stream_t stream);

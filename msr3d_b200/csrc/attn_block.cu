@@ -102,6 +102,7 @@ struct alignas(64) AttnBlockFwdParams {
   unsigned site_fc, site_1;
   float *qkvc, *P, *LOC, *ctx;           // saved for the backward pass
   float *xhat_a, *rstd_a, *xhat_1, *rstd_1, *y2;
+  float *y2_big, *y2_small;              // nullable: operand images of y2 for the pre-split FFN pair
   int B, L;
 };
 
@@ -658,6 +659,18 @@ attn_block_fwd_kernel(const __grid_constant__ AttnBlockFwdParams g) {
       Row8 out = ln_forward(w, s_g1, s_b1, lane, r1);
       row_store(g.xhat_1 + base, lane, w);
       row_store(g.y2 + base, lane, out);
+      if (g.y2_big != nullptr) {
+        Row8 bg, sm;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint32_t ub, us;
+          tma::split_tf32(out.v[i], ub, us);
+          bg.v[i] = __uint_as_float(ub);
+          sm.v[i] = __uint_as_float(us);
+        }
+        row_store(g.y2_big + base, lane, bg);
+        row_store(g.y2_small + base, lane, sm);
+      }
       if (lane == 0) { g.rstd_a[row] = ra; g.rstd_1[row] = r1; }
     }
   }
@@ -717,13 +730,14 @@ MSR3D_API int msr3d_attn_block_supported(int L, int H, int hidden) {
   return (L >= 1 && L <= kAbRT && H == kAbHeads && hidden == kD) ? 1 : 0;
 }
 
-MSR3D_API int msr3d_attn_block_fwd_f32(const float *x, const float *wqkvc_big, const float *wqkvc_small, const float *bqkvc,
+static int attn_block_fwd_impl(const float *x, const float *wqkvc_big, const float *wqkvc_small, const float *bqkvc,
                                        const float *wo_big, const float *wo_small, const float *bo, const float *pw,
                                        const unsigned char *key_pad, int B, int L, const float *gamma_a, const float *beta_a,
                                        const float *gamma_1, const float *beta_1, unsigned long long seed,
                                        const unsigned long long *seed_ptr, float p, unsigned site_fc, unsigned site_1,
                                        float *qkvc, float *P, float *LOC, float *ctx, float *xhat_a, float *rstd_a,
-                                       float *xhat_1, float *rstd_1, float *y2, msr3d_stream_t stream) {
+                                       float *xhat_1, float *rstd_1, float *y2, float *y2_big, float *y2_small,
+                                       msr3d_stream_t stream) {
   MSR3D_REQUIRE(x && wqkvc_big && wqkvc_small && bqkvc && wo_big && wo_small && bo && pw && gamma_a && beta_a && gamma_1 &&
                     beta_1 && qkvc && P && LOC && ctx && xhat_a && rstd_a && xhat_1 && rstd_1 && y2,
                 "attn_block_fwd: null pointer");
@@ -749,6 +763,7 @@ MSR3D_API int msr3d_attn_block_fwd_f32(const float *x, const float *wqkvc_big, c
   g.site_fc = site_fc; g.site_1 = site_1;
   g.qkvc = qkvc; g.P = P; g.LOC = LOC; g.ctx = ctx;
   g.xhat_a = xhat_a; g.rstd_a = rstd_a; g.xhat_1 = xhat_1; g.rstd_1 = rstd_1; g.y2 = y2;
+  g.y2_big = y2_big; g.y2_small = y2_small;
   g.B = B; g.L = L;
   static bool configured = false;
   if (!configured) {
@@ -758,4 +773,30 @@ MSR3D_API int msr3d_attn_block_fwd_f32(const float *x, const float *wqkvc_big, c
   launch_pdl_cluster(attn_block_fwd_kernel, dim3(kAbHeads, B), dim3(kAbThreads), kAbSmem, (cudaStream_t)stream,
                      dim3(kAbHeads, 1, 1), g);
   return check_launch("attn_block_fwd");
+}
+
+MSR3D_API int msr3d_attn_block_fwd_f32(const float *x, const float *wqkvc_big, const float *wqkvc_small, const float *bqkvc,
+                                       const float *wo_big, const float *wo_small, const float *bo, const float *pw,
+                                       const unsigned char *key_pad, int B, int L, const float *gamma_a, const float *beta_a,
+                                       const float *gamma_1, const float *beta_1, unsigned long long seed,
+                                       const unsigned long long *seed_ptr, float p, unsigned site_fc, unsigned site_1,
+                                       float *qkvc, float *P, float *LOC, float *ctx, float *xhat_a, float *rstd_a,
+                                       float *xhat_1, float *rstd_1, float *y2, msr3d_stream_t stream) {
+  return attn_block_fwd_impl(x, wqkvc_big, wqkvc_small, bqkvc, wo_big, wo_small, bo, pw, key_pad, B, L, gamma_a, beta_a, gamma_1,
+                             beta_1, seed, seed_ptr, p, site_fc, site_1, qkvc, P, LOC, ctx, xhat_a, rstd_a, xhat_1, rstd_1, y2,
+                             nullptr, nullptr, stream);
+}
+
+MSR3D_API int msr3d_attn_block_fwd_ps_f32(const float *x, const float *wqkvc_big, const float *wqkvc_small, const float *bqkvc,
+                                          const float *wo_big, const float *wo_small, const float *bo, const float *pw,
+                                          const unsigned char *key_pad, int B, int L, const float *gamma_a,
+                                          const float *beta_a, const float *gamma_1, const float *beta_1,
+                                          unsigned long long seed, const unsigned long long *seed_ptr, float p,
+                                          unsigned site_fc, unsigned site_1, float *qkvc, float *P, float *LOC, float *ctx,
+                                          float *xhat_a, float *rstd_a, float *xhat_1, float *rstd_1, float *y2,
+                                          float *y2_big, float *y2_small, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(y2_big && y2_small, "attn_block_fwd_ps: null image pointer");
+  return attn_block_fwd_impl(x, wqkvc_big, wqkvc_small, bqkvc, wo_big, wo_small, bo, pw, key_pad, B, L, gamma_a, beta_a, gamma_1,
+                             beta_1, seed, seed_ptr, p, site_fc, site_1, qkvc, P, LOC, ctx, xhat_a, rstd_a, xhat_1, rstd_1, y2,
+                             y2_big, y2_small, stream);
 }

@@ -583,6 +583,7 @@ constexpr int kHid = 256;   // d_model of the spatial encoder (configs/msr3d.yam
 
 struct alignas(64) FfnPairParams {
   CUtensorMap map_a, map_b1, map_b2;
+  CUtensorMap map_a_s, map_b1_s, map_b2_s;   // pre-split variant: the small images (map_a / b1 / b2 = the big ones)
   CUtensorMap map_h;       // [M, F] forward: h (store); backward: du (store)
   CUtensorMap map_gp;      // [M, F] forward: gelu'(u) * mask (store); backward: the same tensor (load)
   CUtensorMap map_out2;    // [M, 256] reduce-add
@@ -623,7 +624,10 @@ struct FfnPairCfg {
   static constexpr uint32_t kAcc2Col = 64;
 };
 
-template <int FS, bool BWD>
+// PS = operands arrive PRE-SPLIT (big / small tf32 images written once by their producers: the LayerNorm tails for the
+// activations, msr3d_split_tf32_f32 for the weights): no conversion pass at all — round 2's trace showed the in-kernel
+// split of the 128 x 256 activation tile, redone by every CTA of an M tile, as 5 of the kernel's 14 us.
+template <int FS, bool BWD, bool PS>
 __global__ void __launch_bounds__(kThreads3, 1)
 ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
   using C = FfnPairCfg<FS>;
@@ -634,7 +638,7 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
   uint8_t *hbuf = smem;                    // A operand of GEMM 2: [big chunks | small chunks]
   uint8_t *ring = smem + C::kHBytes;       // stages of GEMM 1, later the B2 slice, later the output staging
   __shared__ __align__(8) uint64_t full[S], conv_done[S], mma_done[S];
-  __shared__ __align__(8) uint64_t acc1_full, h_ready, b2_full, b2_conv, acc2_full, gp_full;
+  __shared__ __align__(8) uint64_t acc1_full, h_ready, b2_full, b2_conv, acc2_full, gp_full, b2s_full;
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -655,10 +659,16 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
     mbar_init(&b2_conv, kConvWarps);
     mbar_init(&acc2_full, 1);
     mbar_init(&gp_full, 1);
+    mbar_init(&b2s_full, 1);
     fence_mbar_init();
     tma::prefetch_map(&g.map_a);
     tma::prefetch_map(&g.map_b1);
     tma::prefetch_map(&g.map_b2);
+    if (PS) {
+      tma::prefetch_map(&g.map_a_s);
+      tma::prefetch_map(&g.map_b1_s);
+      tma::prefetch_map(&g.map_b2_s);
+    }
     tma::prefetch_map(&g.map_h);
     tma::prefetch_map(&g.map_gp);
     tma::prefetch_map(&g.map_out2);
@@ -675,20 +685,26 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
     if (tma::elect_one()) {
       auto load_b1 = [&](int i) {
         const int s = i % S;
-        uint8_t *dst = ring + (size_t)s * C::kStage1 + C::kABytes;
         const int k0 = i * kChunk3;
-        if (!BWD) tma::load_2d(dst, &g.map_b1, k0, f0, &full[s]);                    // W1[f0 + r][k0 ..]
-        else {
 #pragma unroll
-          for (int b = 0; b < FS / 32; ++b) tma::load_2d(dst + b * tma::kMnBoxBytes, &g.map_b1, f0 + 32 * b, k0, &full[s]);   // W2[k0 + r][f ..]
+        for (int img = 0; img < (PS ? 2 : 1); ++img) {
+          uint8_t *dst = ring + (size_t)s * C::kStage1 + C::kABytes + (size_t)img * C::kBig1;
+          const CUtensorMap *mp = img ? &g.map_b1_s : &g.map_b1;
+          if (!BWD) tma::load_2d(dst, mp, k0, f0, &full[s]);                    // W1[f0 + r][k0 ..]
+          else {
+#pragma unroll
+            for (int b = 0; b < FS / 32; ++b) tma::load_2d(dst + b * tma::kMnBoxBytes, mp, f0 + 32 * b, k0, &full[s]);   // W2[k0 + r][f ..]
+          }
         }
       };
       auto load_a = [&](int i) {
         const int s = i % S;
         tma::load_2d(ring + (size_t)s * C::kStage1, &g.map_a, i * kChunk3, m0, &full[s]);
+        if (PS) tma::load_2d(ring + (size_t)s * C::kStage1 + C::kBig1, &g.map_a_s, i * kChunk3, m0, &full[s]);
       };
+      constexpr uint32_t kTx1 = PS ? C::kStage1 : C::kBig1;
       for (int i = 0; i < S; ++i) {
-        mbar_expect_tx(&full[i], C::kBig1);
+        mbar_expect_tx(&full[i], kTx1);
         load_b1(i);                              // weights: requested while the previous kernel drains
       }
       if (BWD) {
@@ -707,7 +723,7 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
       for (int i = S; i < kNkc1; ++i) {
         const int s = i % S;
         mbar_wait(&mma_done[s], ((i / S) - 1) & 1);
-        mbar_expect_tx(&full[s], C::kBig1);
+        mbar_expect_tx(&full[s], kTx1);
         load_b1(i);
         load_a(i);
       }
@@ -733,7 +749,8 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
 #pragma unroll 1
       for (int i = 0; i < kNkc1; ++i) {
         const int s = i % S;
-        mbar_wait(&conv_done[s], (i / S) & 1);
+        if (PS) mbar_wait(&full[s], (i / S) & 1);       // both images arrive by TMA
+        else mbar_wait(&conv_done[s], (i / S) & 1);
         fence_after_sync();
         if (tma::elect_one()) {
           const uint32_t base = smem_u32(ring + (size_t)s * C::kStage1);
@@ -754,24 +771,58 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
       }
       // GEMM 2: A = h images written by epilogue 1, B = the converted B2 slice
       mbar_wait(&h_ready, 0);
-      mbar_wait(&b2_conv, 0);
+      if (PS) mbar_wait(&b2_full, 0);       // big image of the B2 slice (requested when GEMM 1 released the ring)
+      else mbar_wait(&b2_conv, 0);
       fence_after_sync();
-      if (tma::elect_one()) {
-        const uint32_t idesc2 = tma::make_idesc_tf32(kTileM3, kHid, false, BWD);
-        const uint64_t step_b2 = tma::kstep_units(BWD);
+      const uint32_t idesc2 = tma::make_idesc_tf32(kTileM3, kHid, false, BWD);
+      const uint64_t step_b2 = tma::kstep_units(BWD);
+      constexpr uint64_t b_small_off = C::kB2Big >> 4;
+      if (!PS) {
+        if (tma::elect_one()) {
 #pragma unroll
-        for (int c = 0; c < C::kNch2; ++c) {
-          const uint64_t a_big = tma::desc_kmajor(smem_u32(hbuf + (size_t)c * C::kHTile));
-          const uint64_t a_small = tma::desc_kmajor(smem_u32(hbuf + (size_t)(C::kNch2 + c) * C::kHTile));
-          const uint32_t bb = smem_u32(ring + (size_t)c * C::kB2Chunk);
-          const uint64_t b_big = BWD ? tma::desc_mnmajor(bb) : tma::desc_kmajor(bb);
-          constexpr uint64_t b_small_off = C::kB2Big >> 4;
+          for (int c = 0; c < C::kNch2; ++c) {
+            const uint64_t a_big = tma::desc_kmajor(smem_u32(hbuf + (size_t)c * C::kHTile));
+            const uint64_t a_small = tma::desc_kmajor(smem_u32(hbuf + (size_t)(C::kNch2 + c) * C::kHTile));
+            const uint32_t bb = smem_u32(ring + (size_t)c * C::kB2Chunk);
+            const uint64_t b_big = BWD ? tma::desc_mnmajor(bb) : tma::desc_kmajor(bb);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            tma::mma_3x(tmem2, a_big + ks * 2, a_small + ks * 2, b_big + ks * step_b2, b_big + b_small_off + ks * step_b2,
-                        idesc2, (c | ks) ? 1u : 0u);
+            for (int ks = 0; ks < 4; ++ks)
+              tma::mma_3x(tmem2, a_big + ks * 2, a_small + ks * 2, b_big + ks * step_b2, b_big + b_small_off + ks * step_b2,
+                          idesc2, (c | ks) ? 1u : 0u);
+          }
+          mma_commit(&acc2_full);
         }
-        mma_commit(&acc2_full);
+      } else {
+        // the small image of B2 lands in the region the h / gelu' staging tiles occupy until their TMA stores have read
+        // them: the two products that need only the big image go first, big x small follows when it has arrived
+        if (tma::elect_one()) {
+#pragma unroll
+          for (int c = 0; c < C::kNch2; ++c) {
+            const uint64_t a_big = tma::desc_kmajor(smem_u32(hbuf + (size_t)c * C::kHTile));
+            const uint64_t a_small = tma::desc_kmajor(smem_u32(hbuf + (size_t)(C::kNch2 + c) * C::kHTile));
+            const uint32_t bb = smem_u32(ring + (size_t)c * C::kB2Chunk);
+            const uint64_t b_big = BWD ? tma::desc_mnmajor(bb) : tma::desc_kmajor(bb);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              tma::mma_tf32(tmem2, a_small + ks * 2, b_big + ks * step_b2, idesc2, (c | ks) ? 1u : 0u);
+              tma::mma_tf32(tmem2, a_big + ks * 2, b_big + ks * step_b2, idesc2, 1u);
+            }
+          }
+        }
+        __syncwarp();
+        mbar_wait(&b2s_full, 0);
+        fence_after_sync();
+        if (tma::elect_one()) {
+#pragma unroll
+          for (int c = 0; c < C::kNch2; ++c) {
+            const uint64_t a_big = tma::desc_kmajor(smem_u32(hbuf + (size_t)c * C::kHTile));
+            const uint32_t bb = smem_u32(ring + (size_t)c * C::kB2Chunk);
+            const uint64_t b_big = BWD ? tma::desc_mnmajor(bb) : tma::desc_kmajor(bb);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) tma::mma_tf32(tmem2, a_big + ks * 2, b_big + b_small_off + ks * step_b2, idesc2, 1u);
+          }
+          mma_commit(&acc2_full);
+        }
       }
       __syncwarp();
     }
@@ -781,7 +832,7 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
     const int cw = warp - kFirstConvWarp;
     const int ct = cw * 32 + lane;
 #pragma unroll 1
-    for (int i = 0; i < kNkc1; ++i) {
+    for (int i = 0; i < (PS ? 0 : kNkc1); ++i) {
       const int s = i % S;
       uint4 *tile = reinterpret_cast<uint4 *>(ring + (size_t)s * C::kStage1);
       mbar_wait(&full[s], (i / S) & 1);
@@ -895,10 +946,24 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
       }
       tma::store_commit();
       tma::store_wait_read();
+      if (PS) {
+        // the staging tiles have been read: the small image of the B2 slice may land there now
+        mbar_expect_tx(&b2s_full, C::kB2Big);
+#pragma unroll
+        for (int c = 0; c < C::kNch2; ++c) {
+          uint8_t *dst = ring + C::kB2Big + (size_t)c * C::kB2Chunk;
+          const int k0 = f0 + c * 32;
+          if (!BWD) tma::load_2d(dst, &g.map_b2_s, k0, 0, &b2s_full);
+          else {
+#pragma unroll
+            for (int b = 0; b < kHid / 32; ++b) tma::load_2d(dst + b * tma::kMnBoxBytes, &g.map_b2_s, 32 * b, k0, &b2s_full);
+          }
+        }
+      }
     }
     tma::named_barrier(1, kConvWarps * 32);
     // ---- B2 slice: big / small split in place
-    {
+    if (!PS) {
       uint4 *tile = reinterpret_cast<uint4 *>(ring);
       mbar_wait(&b2_full, 0);
       if (ct == 0) trace_mark(8);
@@ -960,19 +1025,34 @@ ffn_pair_kernel(const __grid_constant__ FfnPairParams g) {
   if (warp == 2) tmem_dealloc(s_tmem, C::kTmemCols);
 }
 
-template <int FS, bool BWD>
+template <int FS, bool BWD, bool PS = false>
 static int launch_ffn_pair(const FfnPairParams &g, cudaStream_t stream) {
   using C = FfnPairCfg<FS>;
   static bool configured = false;
   if (!configured) {
-    MSR3D_CUDA(cudaFuncSetAttribute(ffn_pair_kernel<FS, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+    MSR3D_CUDA(cudaFuncSetAttribute(ffn_pair_kernel<FS, BWD, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
     configured = true;
   }
-  launch_pdl(ffn_pair_kernel<FS, BWD>, dim3(ceil_div(g.M, kTileM3), g.F / FS), dim3(kThreads3), C::kSmem, stream, g);
+  launch_pdl(ffn_pair_kernel<FS, BWD, PS>, dim3(ceil_div(g.M, kTileM3), g.F / FS), dim3(kThreads3), C::kSmem, stream, g);
   return check_launch("ffn_pair");
 }
 
 }  // namespace msr3d
+
+// small images of the pre-split variant (same shapes and boxes as the big ones)
+static int ffn_pair_small_maps(FfnPairParams &g, const float *A_s, const float *W1_s, const float *W2_s, int M, int F, bool bwd, int fs) {
+  MSR3D_REQUIRE(A_s && W1_s && W2_s, "ffn_pair: null small image");
+  int rc = tma::make_map_f32(&g.map_a_s, A_s, M, kHid, kHid, kTileM3, false);
+  if (rc != MSR3D_OK) return rc;
+  if (!bwd) {
+    rc = tma::make_map_f32(&g.map_b1_s, W1_s, F, kHid, kHid, fs, false);
+    if (rc != MSR3D_OK) return rc;
+    return tma::make_map_f32(&g.map_b2_s, W2_s, kHid, F, F, kHid, false);
+  }
+  rc = tma::make_map_f32(&g.map_b1_s, W2_s, kHid, F, F, tma::kBoxKRows, true);
+  if (rc != MSR3D_OK) return rc;
+  return tma::make_map_f32(&g.map_b2_s, W1_s, F, kHid, kHid, tma::kBoxKRows, true);
+}
 
 static int ffn_pair_common(FfnPairParams &g, const float *A, const float *W1, const float *W2, int M, int F, bool bwd,
                            int fs, const float *h_or_du, const float *gp, const float *out2) {
@@ -1024,4 +1104,37 @@ MSR3D_API int msr3d_ffn_pair_bwd_f32(const float *df, const float *W1, const flo
   if (rc != MSR3D_OK) return rc;
   g.drop = make_dropout(0, 0.f);
   return fs == 32 ? launch_ffn_pair<32, true>(g, (cudaStream_t)stream) : launch_ffn_pair<64, true>(g, (cudaStream_t)stream);
+}
+
+/* Pre-split variants: every operand is given as its big / small tf32 images (msr3d_split_tf32_f32 for the weights, the
+ * LayerNorm-tail kernels for the activations); no conversion pass inside the kernel. */
+MSR3D_API int msr3d_ffn_pair_fwd_ps_f32(const float *y2_big, const float *y2_small, const float *W1_big, const float *W1_small,
+                                        const float *b1, const float *W2_big, const float *W2_small, const float *b2, int M,
+                                        int F, unsigned long long seed, const unsigned long long *seed_ptr, float p,
+                                        unsigned site, float *h, float *gp, float *f_accum, int slice, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(b1 && (reinterpret_cast<uintptr_t>(b1) & 15) == 0 && (!b2 || (reinterpret_cast<uintptr_t>(b2) & 15) == 0),
+                "ffn_pair_fwd: biases must be 16 B aligned");
+  MSR3D_REQUIRE(p >= 0.f && p < 1.f, "ffn_pair_fwd: bad dropout p");
+  FfnPairParams g{};
+  const int fs = slice == 32 ? 32 : 64;
+  int rc = ffn_pair_common(g, y2_big, W1_big, W2_big, M, F, false, fs, h, gp, f_accum);
+  if (rc != MSR3D_OK) return rc;
+  rc = ffn_pair_small_maps(g, y2_small, W1_small, W2_small, M, F, false, fs);
+  if (rc != MSR3D_OK) return rc;
+  g.bias1 = b1; g.bias2 = b2; g.site = site;
+  g.drop = make_dropout(seed, p, seed_ptr);
+  return fs == 32 ? launch_ffn_pair<32, false, true>(g, (cudaStream_t)stream) : launch_ffn_pair<64, false, true>(g, (cudaStream_t)stream);
+}
+
+MSR3D_API int msr3d_ffn_pair_bwd_ps_f32(const float *df_big, const float *df_small, const float *W1_big, const float *W1_small,
+                                        const float *W2_big, const float *W2_small, const float *gp, int M, int F, float *du,
+                                        float *dy2_accum, int slice, msr3d_stream_t stream) {
+  FfnPairParams g{};
+  const int fs = slice == 32 ? 32 : 64;
+  int rc = ffn_pair_common(g, df_big, W1_big, W2_big, M, F, true, fs, du, gp, dy2_accum);
+  if (rc != MSR3D_OK) return rc;
+  rc = ffn_pair_small_maps(g, df_small, W1_small, W2_small, M, F, true, fs);
+  if (rc != MSR3D_OK) return rc;
+  g.drop = make_dropout(0, 0.f);
+  return fs == 32 ? launch_ffn_pair<32, true, true>(g, (cudaStream_t)stream) : launch_ffn_pair<64, true, true>(g, (cudaStream_t)stream);
 }

@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 ffn_tail_bwd_kernel(const float *__restrict__ dy3, int M, LnParams ln2, Dropout drop, unsigned site_2,
                     const float *__restrict__ xhat_2, const float *__restrict__ rstd_2,
                     float *__restrict__ dy2, float *__restrict__ df, float *__restrict__ dgamma_2,
-                    float *__restrict__ dbeta_2, float *__restrict__ dbias_2) {
+                    float *__restrict__ dbeta_2, float *__restrict__ dbias_2, float *__restrict__ df_big,
+                    float *__restrict__ df_small) {
   pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   drop.resolve();
   __shared__ float s_acc[3 * kD];
@@ -270,6 +271,17 @@ ffn_tail_bwd_kernel(const float *__restrict__ dy3, int M, LnParams ln2, Dropout 
     acc.add(2, lane, dfr);
     row_store(dy2 + base, lane, dw);
     row_store(df + base, lane, dfr);
+    if (df_big != nullptr) {     // operand images of df for the pre-split FFN pair (big = tf32-rounded, small = rest)
+      Row8 bg, sm;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t ub = (__float_as_uint(dfr.v[i]) + 0x1000u) & 0xffffe000u;
+        bg.v[i] = __uint_as_float(ub);
+        sm.v[i] = dfr.v[i] - bg.v[i];
+      }
+      row_store(df_big + base, lane, bg);
+      row_store(df_small + base, lane, sm);
+    }
   }
   __syncthreads();
   acc.flush(0, dgamma_2, threadIdx.x);
@@ -734,17 +746,27 @@ MSR3D_API int msr3d_ffn_tail_fwd_f32(const float *f, const float *y2, int M, con
   return check_launch("ffn_tail_fwd");
 }
 
+MSR3D_API int msr3d_ffn_tail_bwd_ps_f32(const float *dy3, int M, const float *gamma_2,
+                                        unsigned long long seed, const unsigned long long *seed_ptr, float p,
+                                        unsigned site_2, const float *xhat_2, const float *rstd_2, float *dy2, float *df,
+                                        float *dgamma_2, float *dbeta_2, float *dbias_2, float *df_big, float *df_small,
+                                        msr3d_stream_t stream) {
+  MSR3D_REQUIRE(dy3 && gamma_2 && xhat_2 && rstd_2 && dy2 && df, "ffn_tail_bwd: null pointer");
+  MSR3D_REQUIRE((df_big == nullptr) == (df_small == nullptr), "ffn_tail_bwd: both images or none");
+  if (M <= 0) return MSR3D_OK;
+  launch_pdl(ffn_tail_bwd_kernel, dim3(ln_grid(M)), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, 
+      dy3, M, LnParams{gamma_2, nullptr}, mk(seed, p, seed_ptr), site_2, xhat_2, rstd_2, dy2, df, dgamma_2,
+      dbeta_2, dbias_2, df_big, df_small);
+  return check_launch("ffn_tail_bwd");
+}
+
 MSR3D_API int msr3d_ffn_tail_bwd_f32(const float *dy3, int M, const float *gamma_2,
                                      unsigned long long seed, const unsigned long long *seed_ptr, float p,
                                      unsigned site_2, const float *xhat_2, const float *rstd_2, float *dy2, float *df,
                                      float *dgamma_2, float *dbeta_2, float *dbias_2,
                                      msr3d_stream_t stream) {
-  MSR3D_REQUIRE(dy3 && gamma_2 && xhat_2 && rstd_2 && dy2 && df, "ffn_tail_bwd: null pointer");
-  if (M <= 0) return MSR3D_OK;
-  launch_pdl(ffn_tail_bwd_kernel, dim3(ln_grid(M)), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, 
-      dy3, M, LnParams{gamma_2, nullptr}, mk(seed, p, seed_ptr), site_2, xhat_2, rstd_2, dy2, df, dgamma_2,
-      dbeta_2, dbias_2);
-  return check_launch("ffn_tail_bwd");
+  return msr3d_ffn_tail_bwd_ps_f32(dy3, M, gamma_2, seed, seed_ptr, p, site_2, xhat_2, rstd_2, dy2, df, dgamma_2, dbeta_2, dbias_2,
+                                   nullptr, nullptr, stream);
 }
 
 static int qpos_fwd_impl(const float *h1, const float *sz, int M, const float *Ws,

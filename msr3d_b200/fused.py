@@ -82,6 +82,12 @@ _C.register_protos({
     "msr3d_qpos_fwd_acc_f32": [c_vp, c_vp, c_int] + [c_vp] * 15 + [c_vp],
     "msr3d_stage_step": [ctypes.POINTER(StageDesc), c_vp],
     "msr3d_split_tf32_f32": [c_vp, c_vp, c_vp, c_ll, c_vp],
+    "msr3d_ffn_pair_fwd_ps_f32": [c_vp] * 8 + [c_int, c_int, c_ull, c_vp, c_float, c_uint, c_vp, c_vp, c_vp, c_int, c_vp],
+    "msr3d_ffn_pair_bwd_ps_f32": [c_vp] * 7 + [c_int, c_int, c_vp, c_vp, c_int, c_vp],
+    "msr3d_attn_block_fwd_ps_f32": [c_vp] * 9 + [c_int, c_int] + [c_vp] * 4 + [c_ull, c_vp, c_float, c_uint, c_uint]
+                                   + [c_vp] * 11 + [c_vp],
+    "msr3d_ffn_tail_bwd_ps_f32": [c_vp, c_int, c_vp, c_ull, c_vp, c_float, c_uint, c_vp, c_vp,
+                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_attn_block_supported": [c_int, c_int, c_int],
     "msr3d_attn_block_fwd_f32": [c_vp] * 9 + [c_int, c_int] + [c_vp] * 4 + [c_ull, c_vp, c_float, c_uint, c_uint]
                                 + [c_vp] * 9 + [c_vp],
@@ -148,6 +154,9 @@ class FusedPrompter:
         # attention block of a layer (QKV+cond GEMM, attention core, out-projection, LayerNorm tail) as ONE cluster
         # kernel (csrc/attn_block.cu); needs the pre-split weight images (flat_big / flat_small)
         self.attn_block = self.gemm_impl == "tf32x3" and _os0.environ.get("MSR3D_ATTN_BLOCK", "1") == "1"
+        # FFN pair fed with PRE-SPLIT operands (activation images written by the LayerNorm tails, weight images by the
+        # once-per-step split): needs the attention block (producer of the y2 images)
+        self.ffn_presplit = self.ffn_pair and self.attn_block and _os0.environ.get("MSR3D_FFN_PRESPLIT", "1") == "1"
         self.split = split                    # transformer GEMMs (forward + data gradients)
         self.enc_split = 3 if split == 6 else split   # frozen encoder: two-way split is ample (1.5e-5)
         self.grad_split = grad_split if split >= 3 else split
@@ -313,6 +322,8 @@ class FusedPrompter:
         w["h"] = [f(M, F) for _ in range(nl)]     # dropout(gelu(u))
         w["gp"] = [f(M, F) for _ in range(nl)]    # gelu'(u) * dropout mask
         w["tokens"] = f(M, H)
+        # operand images (big / small tf32) of y2 and df for the pre-split FFN pair: live inside one layer only
+        w["y2_big"], w["y2_small"], w["df_big"], w["df_small"] = f(M, H), f(M, H), f(M, H), f(M, H)
         # backward
         # per-layer copies of everything a weight-gradient GEMM reads: those GEMMs run on a side
         # stream, off the critical path, while the main stream moves on to the next layer
@@ -437,7 +448,16 @@ class FusedPrompter:
             sa = pre + "self_attn."
             s0 = i * 8
             x_in = ptr(w["x_in"][i])
-            if use_ab:
+            use_ps = use_ab and self.ffn_presplit
+            if use_ab and use_ps:
+                self._call(fwd, "msr3d_attn_block_fwd_ps_f32", x_in, self.PB(sa + "w_qs.weight"), self.PS(sa + "w_qs.weight"),
+                           P(sa + "w_qs.bias"), self.PB(sa + "fc.weight"), self.PS(sa + "fc.weight"), P(sa + "fc.bias"),
+                           ptr(w["pw"]), ptr(w["key_pad"]), B, L, P(sa + "layer_norm.weight"), P(sa + "layer_norm.bias"),
+                           P(pre + "norm1.weight"), P(pre + "norm1.bias"), seed, sptr, p, s0 + 0, s0 + 1,
+                           ptr(w["qkvc"][i]), ptr(w["P"][i]), ptr(w["LOC"][i]), ptr(w["ctx"][i]),
+                           ptr(w["xhat_a"][i]), ptr(w["rstd_a"][i]), ptr(w["xhat_1"][i]), ptr(w["rstd_1"][i]),
+                           ptr(w["y2"][i]), ptr(w["y2_big"]), ptr(w["y2_small"]), tag="attn_block")
+            elif use_ab:
                 self._call(fwd, "msr3d_attn_block_fwd_f32", x_in, self.PB(sa + "w_qs.weight"), self.PS(sa + "w_qs.weight"),
                            P(sa + "w_qs.bias"), self.PB(sa + "fc.weight"), self.PS(sa + "fc.weight"), P(sa + "fc.bias"),
                            ptr(w["pw"]), ptr(w["key_pad"]), B, L, P(sa + "layer_norm.weight"), P(sa + "layer_norm.bias"),
@@ -457,7 +477,13 @@ class FusedPrompter:
                            s0 + 0, s0 + 1, ptr(w["xhat_a"][i]), ptr(w["rstd_a"][i]), ptr(w["xhat_1"][i]),
                            ptr(w["rstd_1"][i]), ptr(w["y2"][i]), tag="attn_tail")
             # FFN: h = dropout(gelu(u)) and gelu'(u)*mask are materialised once (the backward reads both)
-            if self.ffn_pair:
+            if self.ffn_pair and use_ps:
+                self._call(fwd, "msr3d_ffn_pair_fwd_ps_f32", ptr(w["y2_big"]), ptr(w["y2_small"]),
+                           self.PB(pre + "linear1.weight"), self.PS(pre + "linear1.weight"), P(pre + "linear1.bias"),
+                           self.PB(pre + "linear2.weight"), self.PS(pre + "linear2.weight"), P(pre + "linear2.bias"), M, F,
+                           seed, sptr, p, s0 + 2, ptr(w["h"][i]), ptr(w["gp"][i]), ptr(w["f"][i]),
+                           self.ffn_slice, tag="ffn_pair")
+            elif self.ffn_pair:
                 # both GEMMs in one kernel, the hidden tile stays in shared memory (csrc/gemm3x.cu)
                 self._call(fwd, "msr3d_ffn_pair_fwd_f32", ptr(w["y2"][i]), P(pre + "linear1.weight"),
                            P(pre + "linear1.bias"), P(pre + "linear2.weight"), P(pre + "linear2.bias"), M, F,
@@ -488,13 +514,25 @@ class FusedPrompter:
             s0 = i * 8
             dx = ptr(w["dx"][i])
             df, du, do_, dqkvc = ptr(w["df"][i]), ptr(w["du"][i]), ptr(w["do"][i]), ptr(w["dqkvc"][i])
-            self._call(bwd, "msr3d_ffn_tail_bwd_f32", dy3, M, P(pre + "norm2.weight"), seed, sptr, p, s0 + 3,
-                       ptr(w["xhat_2"][i]), ptr(w["rstd_2"][i]), ptr(w["dy2"]), df, G(pre + "norm2.weight"),
-                       G(pre + "norm2.bias"), G(pre + "linear2.bias"), tag="ffn_tail_bwd")
+            ps_b = self.ffn_pair and self.attn_block_active and self.ffn_presplit
+            if ps_b:
+                self._call(bwd, "msr3d_ffn_tail_bwd_ps_f32", dy3, M, P(pre + "norm2.weight"), seed, sptr, p, s0 + 3,
+                           ptr(w["xhat_2"][i]), ptr(w["rstd_2"][i]), ptr(w["dy2"]), df, G(pre + "norm2.weight"),
+                           G(pre + "norm2.bias"), G(pre + "linear2.bias"), ptr(w["df_big"]), ptr(w["df_small"]),
+                           tag="ffn_tail_bwd")
+            else:
+                self._call(bwd, "msr3d_ffn_tail_bwd_f32", dy3, M, P(pre + "norm2.weight"), seed, sptr, p, s0 + 3,
+                           ptr(w["xhat_2"][i]), ptr(w["rstd_2"][i]), ptr(w["dy2"]), df, G(pre + "norm2.weight"),
+                           G(pre + "norm2.bias"), G(pre + "linear2.bias"), tag="ffn_tail_bwd")
             # dW2 (H x F) += df^T . h                                   [side stream]
             self._gemm(bwd, df, (1, H), ptr(w["h"][i]), (1, F), H, F, M, G(pre + "linear2.weight"), F,
                        accumulate=2, ksplit=2, tag="dW2", wgrad=True, side=True)
-            if self.ffn_pair:
+            if ps_b:
+                self._call(bwd, "msr3d_ffn_pair_bwd_ps_f32", ptr(w["df_big"]), ptr(w["df_small"]),
+                           self.PB(pre + "linear1.weight"), self.PS(pre + "linear1.weight"),
+                           self.PB(pre + "linear2.weight"), self.PS(pre + "linear2.weight"),
+                           ptr(w["gp"][i]), M, F, du, ptr(w["dy2"]), self.ffn_slice, tag="ffn_pair_bwd")
+            elif self.ffn_pair:
                 # du = (df . W2) * gelu'(u) * mask and dy2 += du . W1 in one kernel
                 self._call(bwd, "msr3d_ffn_pair_bwd_f32", df, P(pre + "linear1.weight"), P(pre + "linear2.weight"),
                            ptr(w["gp"][i]), M, F, du, ptr(w["dy2"]), self.ffn_slice, tag="ffn_pair_bwd")
