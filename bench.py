@@ -26,6 +26,11 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+L2_TEXT = "flushed (256 MB memset) between timed iterations"
+TIMING_TEXT = "sum of per-step CUDA-event intervals, max over ranks"
+SCHEDULE_TEXT = {True: "sequential",
+                 False: "pipelined: frozen encoder of batch i+1 overlaps the transformer step of batch i (one encoder pass + "
+                        "one update per step); point clouds of batch i+2 prefetched (H2D on a copy stream) during the same step"}
 METRIC = "MSR3D hot-path train-step samples/sec (60 obj x 1024 pt, bs=4/GPU; prompter fwd+bwd+allreduce+AdamW, frozen LLM excluded)"
 UNIT = "samples/s"
 
@@ -48,17 +53,29 @@ def parse():
                     help="copy the point clouds on the compute stream in front of the step instead of prefetching "
                          "them on a copy stream during the previous step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fast", action="store_true",
+                    help="headline numbers only: skip the side measurements (CPU / GPU baselines, secondary configs, "
+                         "LLM context line, scene-token splice)")
+    ap.add_argument("--chain-sms", type=int, default=int(os.environ.get("MSR3D_CHAIN_SMS", "88")),
+                    help="SMs of the partition that runs the transformer chain (the frozen encoder of the next batch "
+                         "gets the rest); 0 = no partition")
     return ap.parse_args()
 
 
 def load_spec():
-    with open(os.path.join(ROOT, "tests", "golden", "state_dict_spec.json")) as fh:
-        return [tuple(x) for x in json.load(fh)]
+    from msr3d_b200 import configs
+    return configs.load_spec()
 
 
 def prompter_cfg():
-    from tests.helpers import prompter_cfg as cfg
-    return cfg()
+    from msr3d_b200 import configs
+    return configs.prompter_cfg()
+
+
+def config_dict(name, B, O, P, world, schedule, l2, timing):
+    """The `config` object: identical keys in both arms (the driver compares them)."""
+    return {"workload": name, "batch_per_gpu": B, "objects": O, "points": P, "l2": l2, "parallelism": f"dp{world}",
+            "schedule": schedule, "timing": timing}
 
 
 class ClockSampler(threading.Thread):
@@ -114,8 +131,8 @@ def run_reference(args, rank, world):
     hot = train_oracle.CpuHotPath(sd)
     batch = synthetic.make_batch(B, O, P, seed=2000)
     up = torch.randn(B, O, 256, generator=torch.Generator().manual_seed(1))
-    steps = max(1, min(args.steps, 10))
-    warm = max(1, min(args.warmup, 3))
+    steps = max(1, args.steps)
+    warm = max(1, args.warmup)
     for _ in range(warm):
         hot.step(batch.as_dict(), up)
     t0 = time.perf_counter()
@@ -128,8 +145,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.config, "batch_per_gpu": B, "objects": O, "points": P,
-                   "note": "CPU arm runs on rank 0 only"},
+        "config": config_dict(args.config, B, O, P, world, SCHEDULE_TEXT[False], L2_TEXT, TIMING_TEXT),
+        "note": "CPU arm: ONE process on rank 0 stepping B=%d samples per step on all %d host cores (whatever --gpus says): "
+                "compare with the N=1 line of the GPU arm only" % (B, cores),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -242,7 +260,8 @@ def main():
     model.load_state_dict(sd, strict=True)
     model = model.to(dev).train()
     trainer = HotPathTrainer(model, B, O, P, world_size=world, split=args.split, use_graph=not args.no_graph,
-                             pipeline=False if args.no_pipeline else (True if args.no_prefetch else "prefetch"))
+                             pipeline=False if args.no_pipeline else (True if args.no_prefetch else "prefetch"),
+                             chain_sms=0 if args.no_pipeline else args.chain_sms)
     # four distinct pinned host batches per rank, cycled (seed = cfg_id*1000 + rank)
     host = [synthetic.make_batch(B, O, P, seed=2000 + rank + 17 * i).pin() for i in range(4)]
     devb = [h.to(dev) for h in host]
@@ -256,15 +275,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n_steps, from_host):
+    def timed(tr, n_steps, from_host, hostb, devbb, upp):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
         for i in range(n_steps):
             flush.zero_()                                    # L2 flush between timed iterations
             ev[i][0].record()
             if from_host:
-                trainer.step(host[i % 4], up, loss_out=loss_host)   # H2D from pinned memory, loss read back
+                tr.step(hostb[i % 4], upp, loss_out=loss_host)   # H2D from pinned memory, loss read back
             else:
-                trainer.step(devb[i % 4], up)
+                tr.step(devbb[i % 4], upp)
             ev[i][1].record()
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in ev]
@@ -272,32 +291,32 @@ def main():
     trainer.warmup(devb[0], up)
     for i in range(max(args.warmup, 3)):
         trainer.step(devb[i % 4], up)
-    timed(3, True)
+    timed(trainer, 3, True, host, devb, up)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     from msr3d_b200 import roofline
     barrier()
-    ms = timed(args.steps, False)
+    ms = timed(trainer, args.steps, False, host, devb, up)
     barrier()
     launches_per_step = trainer.engine.launches_per_step
-    ms_e2e = timed(args.steps, True)
+    ms_e2e = timed(trainer, args.steps, True, host, devb, up)
     barrier()
     sampler.stop_flag = True
     sampler.join()
 
-    # per-kernel durations (every rank: the step contains a collective): the same step launched eagerly
-    # with CUDA events around every kernel (a graph replay cannot be instrumented from the host).  A
-    # spin kernel keeps the stream busy while the host enqueues the whole step, so the events bracket
-    # back-to-back kernels and not host launch gaps; L2 is flushed before each step.
-    ops.TIMER = ktimer = roofline.KernelTimer()
-    for i in range(min(args.steps, 20)):
-        trainer.engine.load_inputs(devb[i % 4], up)
-        flush.zero_()
-        torch.cuda._sleep(40_000_000)                         # ~20 ms of GPU spin
-        trainer.engine.train_step_eager()
-        torch.cuda.synchronize()
-    ops.TIMER = None
+    # per-kernel durations: CUPTI intervals over replays of the whole step as one sequential CUDA graph captured with
+    # programmatic dependent launch OFF (msr3d_b200/roofline.py explains why); L2 flushed before each replay
+    eng = trainer.engine
+    trainer.flush()
+    lib = _C.lib()
+    lib.msr3d_set_pdl(0)
+    eng.load_inputs(devb[0], up)
+    eng.graph = None
+    eng.capture()
+    times = roofline.cupti_kernel_times(eng.graph.replay, 5, before_each=flush.zero_)
+    lib.msr3d_set_pdl(1)
+    eng.graph = None
     barrier()
 
     tot = torch.tensor([sum(ms), sum(ms_e2e)], device=dev, dtype=torch.float64)
@@ -307,45 +326,159 @@ def main():
     if rank == 0:
         value = B * world * args.steps / t_dev
         e2e = B * world * args.steps / t_e2e
+        ms_step = t_dev / args.steps * 1e3
+        part = getattr(eng, "partition", None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (split-bf16 tensor-core MMAs, f32 accumulate in TMEM)" if args.split != 1 else "bf16",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (split-bf16 / 3xTF32 tensor-core products, f32 accumulate in TMEM)" if args.split != 1 else "bf16",
             "data": "synthetic",
-            "config": {"workload": args.config, "batch_per_gpu": B, "objects": O, "points": P,
-                       "l2": "flushed (256 MB memset) between timed iterations", "parallelism": f"dp{world}",
-                       "schedule": "sequential" if args.no_pipeline else
-                       ("pipelined: frozen encoder of batch i+1 overlaps the transformer step of batch i "
-                        "(one encoder pass + one update per step)" +
-                        ("" if args.no_prefetch else "; point clouds of batch i+2 prefetched (H2D on a copy stream) "
-                         "during the same step")),
-                       "timing": "sum of per-step CUDA-event intervals, max over ranks"},
+            "config": config_dict(args.config, B, O, P, world, SCHEDULE_TEXT[bool(args.no_pipeline)], L2_TEXT, TIMING_TEXT),
+            "sm_partition": ({"chain_sms": part.counts[0], "encoder_sms": part.counts[1]} if part is not None else None),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": sampler.result(),
         }
-        roof, table = roofline.summarize(ktimer, B, O, P, 3 if args.split == 6 else args.split,
-                                         steps=min(args.steps, 20))
+        roof, table, step_roof = roofline.summarize_cupti(times, B, O, P, ms_step, n_opt=eng.n_opt)
         line["roofline"] = roof
+        line["step_roofline"] = step_roof
         line["kernels"] = {k: {kk: (round(vv, 5) if isinstance(vv, float) else vv) for kk, vv in v.items()}
-                           for k, v in table.items()}
-        # the two side measurements must never cost the bench line itself
-        if world == 1 and not args.no_cpu_baseline:
+                           for k, v in sorted(table.items(), key=lambda kv: -kv[1]["us_per_step"])}
+        side = world == 1 and not args.fast
+        # side measurements must never cost the bench line itself
+        if side and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(args)
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                         "sample": f"failed: {type(e).__name__}: {e}"}
-        if world == 1:
-            try:
-                line["next_rows"] = {"scene_splice (SURVEY 8f-1)": bench_splice(dev, B, O, flush, os.cpu_count() or 1)}
-            except Exception as e:  # noqa: BLE001
-                line["next_rows"] = {"error": f"{type(e).__name__}: {e}"}
+        if side:
+            for key, fn in (("gpu_baseline", lambda: gpu_baseline(args, dev, flush)),
+                            ("secondary", lambda: secondary_configs(args, dev, world, flush)),
+                            ("llm_context", lambda: llm_context(dev, B, O, ms_step)),
+                            ("next_rows", lambda: {"scene_splice (SURVEY 8f-1)": bench_splice(dev, B, O, flush, os.cpu_count() or 1)})):
+                try:
+                    line[key] = fn()
+                except Exception as e:  # noqa: BLE001
+                    line[key] = {"error": f"{type(e).__name__}: {e}"}
+            if isinstance(line.get("gpu_baseline"), dict) and line["gpu_baseline"].get("value"):
+                line["gpu_baseline"]["ratio_value_over_gpu_baseline"] = round(value / line["gpu_baseline"]["value"], 2)
         sys.stdout.flush()
         os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def gpu_baseline(args, dev, flush):
+    """BASELINE.md §4 bar (i): the reference's own pointnet2 kernels recompiled for sm_100 (oracle/_ref) + stock eager
+    torch ops, same step definition, on this GPU.  Test infrastructure timed beside the product, like cpu_baseline."""
+    from msr3d_b200 import synthetic
+    from oracle import train_oracle
+    B, O, P = synthetic.CONFIGS[args.config]
+    hot = train_oracle.CpuHotPath(synthetic.make_state_dict(load_spec(), 0), device="cuda")
+    batch = synthetic.make_batch(B, O, P, seed=2000).to(dev)
+    data = batch.as_dict()
+    up = torch.randn(B, O, 256, generator=torch.Generator().manual_seed(1)).to(dev)
+    for _ in range(3):
+        hot.step(data, up, sync=False)
+    torch.cuda.synchronize()
+    n = 10
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        hot.step(data, up, sync=False)
+        b.record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in ev)
+    med = ms[len(ms) // 2]
+    return {"value": B / (med * 1e-3), "unit": UNIT, "ms_per_step": med, "kind": "reference pointnet2 .cu for sm_100 + eager torch ops (fp32, TF32 off)",
+            "sample": f"median of {n} eager steps of {args.config} (B={B}) after 3 warm-ups, inputs resident, L2 flushed, host launch gaps included"}
+
+
+def secondary_configs(args, dev, world, flush):
+    """Throughput of the other BASELINE.json configurations that fit one GPU (parity cases in tests/test_configs_gpu.py):
+    config 4 shapes (80 objects x 2048 points, bs 2: the attention block falls back to the four-launch path, L > 64) and
+    config 5 shapes (bs 8, 60 x 1024).  Extra keys; the headline stays config 2."""
+    import msr3d_b200
+    from msr3d_b200 import synthetic
+    from msr3d_b200.train import HotPathTrainer
+    out = {}
+    for name in ("cfg4_80x2048", "cfg5_msnn_60x1024"):
+        B, O, P = synthetic.CONFIGS[name]
+        model = msr3d_b200.build_model(prompter_cfg())
+        model.load_state_dict(synthetic.make_state_dict(load_spec(), 0), strict=True)
+        model = model.to(dev).train()
+        tr = HotPathTrainer(model, B, O, P, world_size=1, split=args.split, pipeline="prefetch", chain_sms=args.chain_sms)
+        devb = [synthetic.make_batch(B, O, P, seed=3000 + 17 * i).to(dev) for i in range(4)]
+        up = torch.randn(B, O, 256, generator=torch.Generator().manual_seed(1)).to(dev)
+        tr.warmup(devb[0], up)
+        for i in range(5):
+            tr.step(devb[i % 4], up)
+        n = 20
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for i, (a, b) in enumerate(ev):
+            flush.zero_()
+            a.record()
+            tr.step(devb[i % 4], up)
+            b.record()
+        torch.cuda.synchronize()
+        t = sum(a.elapsed_time(b) for a, b in ev) / n
+        from msr3d_b200 import roofline
+        work = roofline.function_work(B, O, P, n_opt=tr.engine.n_opt)
+        flops = sum(w["flops"] for _, w in work if "flops" in w)
+        peaks = roofline.measured_peaks()
+        out[name] = {"value": B / (t * 1e-3), "unit": UNIT, "ms_per_step": t, "batch_per_gpu": B, "objects": O, "points": P,
+                     "attn_block_kernel": bool(getattr(tr.engine, "attn_block_active", False)),
+                     "step_frac_tensor": flops / (t * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]}
+        del tr, model
+        torch.cuda.empty_cache()
+    return out
+
+
+def llm_context(dev, B, L, hot_ms):
+    """SURVEY.md §8(d) context: the frozen LLM around the path — HF Llama, Vicuna-7B geometry (32 layers, hidden 4096,
+    32 heads, FFN 11008), random fp16 weights, forward + backward to the inputs_embeds of one micro-batch (B prompts of
+    128 text tokens + L scene tokens).  Library code outside the path: timed only to put the hot path's share of a
+    training micro-step on record."""
+    import time as _t
+    from transformers import LlamaConfig, LlamaForCausalLM
+    T = 128 + L
+    cfg = LlamaConfig(vocab_size=32000, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                      num_attention_heads=32, num_key_value_heads=32, max_position_embeddings=2048)
+    t0 = _t.perf_counter()
+    with torch.device(dev):
+        llm = LlamaForCausalLM(cfg).to(torch.float16)
+    for p_ in llm.parameters():
+        p_.requires_grad_(False)
+    llm.gradient_checkpointing_enable()
+    llm.train()
+    emb = (torch.randn(B, T, 4096, device=dev) * 0.02).half().requires_grad_(True)
+    labels = torch.randint(0, 32000, (B, T), device=dev)
+
+    def step():
+        emb.grad = None
+        out = llm(inputs_embeds=emb, labels=labels, use_cache=False)
+        out.loss.backward()
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    n = 3
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    llm_ms = a.elapsed_time(b) / n
+    del llm
+    torch.cuda.empty_cache()
+    return {"llm": "HF LlamaForCausalLM, Vicuna-7B geometry, random fp16 weights, frozen, gradient checkpointing, eager",
+            "tokens_per_prompt": T, "batch": B, "llm_fwd_bwd_ms": llm_ms, "hot_path_ms": hot_ms,
+            "train_microstep_samples_per_s": B / ((llm_ms + hot_ms) * 1e-3),
+            "hot_path_share_of_microstep": hot_ms / (llm_ms + hot_ms), "setup_s": round(_t.perf_counter() - t0, 1)}
 
 
 if __name__ == "__main__":

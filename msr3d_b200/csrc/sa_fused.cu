@@ -351,7 +351,7 @@ static int launch_sa_mlp(const SaParams &p, cudaStream_t stream) {
   if (g_tune[TUNE_SA_SM_LIMIT] > 0 && g_tune[TUNE_SA_SM_LIMIT] < kNumSMs) sms = g_tune[TUNE_SA_SM_LIMIT];  // A/B: leave SMs to a concurrent chain
   // oversubscription (A/B): k x as many CTAs as fit at once, each walking 1/k of the tiles — a CTA then lives a few
   // microseconds and a concurrent high-priority chain gets the SM at the next retirement instead of after the whole level
-  const int over = g_tune[TUNE_SA_OVERSUB] > 1 ? g_tune[TUNE_SA_OVERSUB] : 1;
+  const int over = g_tune[TUNE_SA_OVERSUB] > 0 ? g_tune[TUNE_SA_OVERSUB] : 2;   // 2: measured best (profiles/r2_ab_experiments.md)
   int grid = p.n_tiles < sms * per_sm * over ? p.n_tiles : sms * per_sm * over;
   launch_pdl(kern, dim3(grid), dim3(256), L::kSmem, stream, p);
   return check_launch("sa_mlp_kernel");

@@ -150,7 +150,7 @@ class FusedPrompter:
         assert self.gemm_impl in ("tf32x3", "bf16")
         # fused FFN pair kernels (FFN1 + GELU + dropout + FFN2 / du + dy2): on with the TMA-fed GEMMs
         self.ffn_pair = self.gemm_impl == "tf32x3" and _os0.environ.get("MSR3D_FFN_PAIR", "1") == "1"
-        self.ffn_slice = int(_os0.environ.get("MSR3D_FFN_SLICE", "32"))
+        self.ffn_slice = int(_os0.environ.get("MSR3D_FFN_SLICE", "64"))
         # attention block of a layer (QKV+cond GEMM, attention core, out-projection, LayerNorm tail) as ONE cluster
         # kernel (csrc/attn_block.cu); needs the pre-split weight images (flat_big / flat_small)
         self.attn_block = self.gemm_impl == "tf32x3" and _os0.environ.get("MSR3D_ATTN_BLOCK", "1") == "1"
@@ -209,7 +209,7 @@ class FusedPrompter:
         self._slot_free = [torch.cuda.Event(), torch.cuda.Event()]   # encoder that read slot s complete
         self.enc_stream = self.enc_stream_part if self.enc_stream_part is not None else torch.cuda.Stream(device=dev)
         self.use_side = True
-        self.wgrad_small = True
+        self.wgrad_small = _os0.environ.get("MSR3D_WGRAD_SMALL", "1") == "1"
         # data parallel: all-reduce the gradients of layers >= 1 under the backward of layer 0 (two buckets)
         # instead of one collective after the backward.  A/B: MSR3D_DDP_BUCKETS=0/1
         import os as _os

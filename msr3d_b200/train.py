@@ -31,9 +31,10 @@ class HotPathTrainer:
 
     def __init__(self, model: torch.nn.Module, B: int, O: int, P: int, lr: float = 3e-5,
                  weight_decay: float = 0.05, betas=(0.9, 0.999), grad_norm: float = 5.0,
-                 world_size: int = 1, split: int = 6, use_graph: bool = True, pipeline: bool = True):
+                 world_size: int = 1, split: int = 6, use_graph: bool = True, pipeline: bool = True,
+                 chain_sms: Optional[int] = None):
         self.engine = FusedPrompter(model, lr=lr, weight_decay=weight_decay, betas=betas,
-                                    grad_norm=grad_norm, world_size=world_size, split=split)
+                                    grad_norm=grad_norm, world_size=world_size, split=split, chain_sms=chain_sms)
         self.engine.prepare(B, O, P, training=model.training)
         self.use_graph = use_graph
         self.pipeline = pipeline
@@ -44,7 +45,12 @@ class HotPathTrainer:
         """First eager step (lazy kernel attribute setup), then graph capture (and pipeline priming)."""
         e = self.engine
         e.load_inputs(batch, upstream)
+        # the eager step only warms the launch paths up: parameters, optimiser state and the dropout counter are put back
+        # (the warm-up batch is not trained on twice)
+        saved = [t.clone() for t in (e.flat_p, e.m, e.v, e.opt_state, e.seed_counter)]
         e.train_step_eager()
+        for dst, src in zip((e.flat_p, e.m, e.v, e.opt_state, e.seed_counter), saved):
+            dst.copy_(src)
         torch.cuda.synchronize()
         if self.pipeline == "prefetch":
             e.prime2(batch, upstream, batch, upstream)
@@ -58,7 +64,7 @@ class HotPathTrainer:
         elif self.use_graph:
             e.capture()
 
-    def step(self, batch: synthetic.SceneBatch, upstream: Optional[torch.Tensor] = None,
+    def step(self, batch: synthetic.SceneBatch, upstream: torch.Tensor,
              loss_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One micro-step fed with `batch` (device or pinned-host tensors).  Returns the surrogate loss
         <obj_tokens, upstream> (device scalar) of the batch whose update was applied in this call;

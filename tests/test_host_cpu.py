@@ -89,3 +89,70 @@ def test_compat_aliases_resolve():
                  "modules.vision.pcd_pointnet_encoder", "modules.layers.pointnet", "modules.layers.transformers"):
         import sys
         sys.modules.pop(name, None)
+
+
+def test_install_modules_patches_instead_of_shadowing():
+    """install_modules() must not replace whole reference modules by 4-name stubs.  A module that is already
+    importable keeps everything it defines; only the hot-path classes are swapped."""
+    import sys
+    import types
+    fake = types.ModuleType("modules.layers.transformers")
+    fake.GPT2Model = object()                         # what model/msr3d/msr3d.py:27 imports next to the hot-path classes
+    fake.TransformerSpatialEncoderLayer = "reference class"
+    pkgs = {}
+    for pkg in ("modules", "modules.layers"):
+        if pkg not in sys.modules:
+            pkgs[pkg] = types.ModuleType(pkg)
+            pkgs[pkg].__path__ = []
+            sys.modules[pkg] = pkgs[pkg]
+    sys.modules["modules.layers.transformers"] = fake
+    try:
+        compat.install_modules()
+        m = sys.modules["modules.layers.transformers"]
+        assert m is fake and m.GPT2Model is fake.GPT2Model
+        assert m.TransformerSpatialEncoderLayer is msr3d_b200.spatial.TransformerSpatialEncoderLayer
+        stub = sys.modules["model.ose3d_situation"]
+        if getattr(stub, "__msr3d_stub__", False):   # no reference tree here: missing names explain themselves
+            with pytest.raises(AttributeError, match="stand-in"):
+                stub.SomethingElse
+    finally:
+        for name in ("pointnet2", "pointnet2._ext", "modules.build", "model.build", "model.ose3d_situation", "model",
+                     "modules.vision.pcd_pointnet_encoder", "modules.vision", "modules.layers.pointnet",
+                     "modules.layers.transformers", "modules.layers", "modules"):
+            sys.modules.pop(name, None)
+
+
+@pytest.mark.skipif(not __import__("oracle.refshim", fromlist=["x"]).available(), reason="needs /root/reference")
+def test_reference_pointnet2_utils_binds_to_ext():
+    """SURVEY 8b import side-effects: the reference's OWN pointnet2_utils.py / pointnet2_modules.py, imported where
+    they lie, bind to msr3d_b200.ext (`import pointnet2._ext as _ext`, pointnet2_utils.py:22-30) and their autograd
+    Functions reach our operators, which refuse CPU tensors exactly like the reference extension.  Own process: the
+    shim's sys.modules arrangement is global."""
+    import subprocess
+    import sys
+    code = """
+import torch, msr3d_b200
+from msr3d_b200 import compat
+from oracle import refshim
+compat.install_ext()
+refshim.install(ext_module=msr3d_b200.ext)
+import importlib
+u = importlib.import_module("modules.third_party.pointnet2.pointnet2_utils")
+m = importlib.import_module("modules.third_party.pointnet2.pointnet2_modules")
+assert u._ext is msr3d_b200.ext
+for name in ("furthest_point_sampling", "gather_points", "gather_points_grad", "ball_query", "group_points",
+             "group_points_grad", "three_nn", "three_interpolate", "three_interpolate_grad"):
+    assert hasattr(u._ext, name), name
+for fn, args in ((u.furthest_point_sample, (torch.zeros(1, 8, 3), 4)),
+                 (u.ball_query, (0.2, 4, torch.zeros(1, 8, 3), torch.zeros(1, 2, 3)))):
+    try:
+        fn(*args)
+    except RuntimeError as e:
+        assert "CPU not supported" in str(e), e
+    else:
+        raise SystemExit("CPU tensors were accepted")
+sa = m.PointnetSAModule(npoint=4, radius=0.2, nsample=4, mlp=[3, 8], use_xyz=True)   # builds on the reference's own classes
+print("ok")
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=helpers.ROOT, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

@@ -1,14 +1,8 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r2_t12.log
-cat gpurun_out/r2_t12.log
-run() { r=$(env "$@" timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['ms_per_step'],4), round(d['value']), round(d['e2e']['value']))"); echo "$*: $r"; }
-{
-run MSR3D_FFN_PRESPLIT=0 MSR3D_TUNE=12=2 MSR3D_FFN_SLICE=64
-run MSR3D_FFN_PRESPLIT=1 MSR3D_TUNE=12=2 MSR3D_FFN_SLICE=64
-run MSR3D_FFN_PRESPLIT=1 MSR3D_TUNE=12=2 MSR3D_FFN_SLICE=32
-run MSR3D_FFN_PRESPLIT=1 MSR3D_CHAIN_SMS=88 MSR3D_FFN_SLICE=64 MSR3D_TUNE=12=2
-run MSR3D_FFN_PRESPLIT=1 MSR3D_CHAIN_SMS=80 MSR3D_FFN_SLICE=64 MSR3D_TUNE=12=2
-} > gpurun_out/r2_sweep9.log 2>&1
-cat gpurun_out/r2_sweep9.log
-timeout 300 python tools/chain_profile.py fwd 2>&1 | cut -c1-100 | tail -14 > gpurun_out/r2_chain6.log
-cat gpurun_out/r2_chain6.log
+timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches.csv python tools/step_launches.py > gpurun_out/r2_launches.log 2>&1
+wc -l gpurun_out/r2_launches.csv
+timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"sa_mlp_kernel|gemm3x_kernel|attn_block|ffn_pair|linear_tma|attn_bwd" -c 40 -o /tmp/r2_prof -f python tools/step_launches.py > gpurun_out/r2_ncu.log 2>&1
+tail -3 gpurun_out/r2_ncu.log
+ncu -i /tmp/r2_prof.ncu-rep --page raw --csv > gpurun_out/r2_ncu_raw.csv 2>/dev/null
+ncu -i /tmp/r2_prof.ncu-rep --page details --csv --kernel-name regex:"attn_block" 2>/dev/null | head -400 > gpurun_out/r2_ncu_attn_block_details.csv
+wc -c gpurun_out/r2_ncu_raw.csv
