@@ -368,7 +368,13 @@ def main():
         os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL collectives were captured in CUDA graphs: tearing the communicator down can block (seen with
+        # tools/check_ddp_equiv.py); all ranks are in sync and the line is out, so leave directly
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def gpu_baseline(args, dev, flush):

@@ -214,6 +214,11 @@ class FusedPrompter:
         # instead of one collective after the backward.  A/B: MSR3D_DDP_BUCKETS=0/1
         import os as _os
         self.ddp_buckets = _os.environ.get("MSR3D_DDP_BUCKETS", "1") == "1"
+        # data parallel, prefetch schedule: the NCCL all-reduces and the optimiser are CAPTURED in the step's CUDA graph
+        # (one replay per step; round 1 cut the step into two graphs with the collectives and AdamW launched from the
+        # host in between: +64 us per step already at 2 GPUs).  MSR3D_DDP_IN_GRAPH=0 restores that.
+        self.ddp_in_graph = _os.environ.get("MSR3D_DDP_IN_GRAPH", "1") == "1"
+        self.comm_stream = torch.cuda.Stream(device=dev) if world_size > 1 else None
         self._side_pending = [False, False]
         self.extra_sumsq: Optional[torch.Tensor] = None   # see optimizer_step()
         # one engine per model: the drop-in module call (autograd.py) reuses this one instead of re-homing
@@ -729,6 +734,24 @@ class FusedPrompter:
         self._run(self.fwd_prog)
         if part == 1:
             self._run(self.bwd_prog[:self.bwd_split] + [("join", None, (), None, False)])
+        elif part == 3:
+            # whole data-parallel step in one stream-ordered program (capturable): gradients of layers >= 1 are
+            # all-reduced on the communication stream under the backward of layer 0 and the input encoders, the rest
+            # right after it; clip + AdamW follow on the device
+            import torch.distributed as dist
+            (e0, e1), (l0, l1) = self.bucket_early, self.bucket_late
+            if self.ddp_buckets and e1 > e0:
+                self._run(self.bwd_prog[:self.bwd_split] + [("join", None, (), None, False)])
+                self.comm_stream.wait_stream(main)
+                with torch.cuda.stream(self.comm_stream):
+                    dist.all_reduce(self.flat_g[e0:e1])
+                self._run(self.bwd_prog[self.bwd_split:])
+                dist.all_reduce(self.flat_g[l0:l1])
+                main.wait_stream(self.comm_stream)
+            else:
+                self.backward()
+                dist.all_reduce(self.flat_g[:self.n_opt])
+            self.optimizer_step()
         else:
             self.backward()
             if self.world_size == 1:
@@ -832,7 +855,13 @@ class FusedPrompter:
         if flush != 2:
             main.wait_event(self._copied[slot])
         graphed = self.graph_prefetch[slot] is not None and not flush
-        if self.world_size == 1 or not self.ddp_buckets:
+        if self.world_size > 1 and self.ddp_in_graph:
+            if graphed:
+                self.graph_prefetch[slot].replay()
+            else:
+                self._pipelined_body(with_encoder=flush != 2, slot=slot, depth2=True, part=3)
+            self._slot_free[slot].record(main)
+        elif self.world_size == 1 or not self.ddp_buckets:
             if graphed:
                 self.graph_prefetch[slot].replay()
             else:
@@ -879,14 +908,16 @@ class FusedPrompter:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                self._pipelined_body(slot=slot, depth2=True)
+                self._pipelined_body(slot=slot, depth2=True, part=3 if (self.world_size > 1 and self.ddp_in_graph) else 0)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            in_graph = self.world_size > 1 and self.ddp_in_graph
             with torch.cuda.graph(g, stream=self.hi_stream, capture_error_mode="thread_local"):
-                self._pipelined_body(slot=slot, depth2=True, part=1 if (self.world_size > 1 and self.ddp_buckets) else 0)
+                self._pipelined_body(slot=slot, depth2=True,
+                                     part=3 if in_graph else (1 if (self.world_size > 1 and self.ddp_buckets) else 0))
             self.graph_prefetch[slot] = g
-        if self.world_size > 1 and self.ddp_buckets:      # the rest of the backward (same for both slots)
+        if self.world_size > 1 and self.ddp_buckets and not self.ddp_in_graph:      # the rest of the backward (same for both slots)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self.hi_stream, capture_error_mode="thread_local"):
                 self._pipelined_body(part=2)

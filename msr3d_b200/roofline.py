@@ -201,7 +201,7 @@ def _short(name: str) -> str:
     name = re.sub(r"^void\s+", "", name)
     name = re.sub(r"\(.*$", "", name)
     name = name.replace("msr3d::", "").replace(" ", "")
-    return name
+    return name.replace("false", "0").replace("true", "1")        # ncu prints bool template arguments as 0 / 1
 
 
 def function_work(B: int, O: int, P: int, nl: int = 3, n_opt: int = 4224144, F: int = 2048):
@@ -219,8 +219,8 @@ def function_work(B: int, O: int, P: int, nl: int = 3, n_opt: int = 4224144, F: 
         (r"^linear_t(ma|c)_kernel", {"flops": w["sa3_l1"]["flops"] + w["sa3_l2"]["flops"] + w["sa3_l3"]["flops"] + w["fc"]["flops"] + 2 * 2.0 * M * 63 * 256,
                                      "what": "SA3 (GroupAll MLP 259-256-512-768) + fc 768-768 + loc_fc / dWloc"}),
         (r"^gemm3x_kernel", {"flops": gemm3x, "what": "object projection, data / weight gradients of the transformer (3xTF32)"}),
-        (r"^ffn_pair_kernel<\d+,false", {"flops": nl * (w["ffn1"]["flops"] + w["ffn2"]["flops"]), "what": "FFN1 + GELU + dropout + FFN2 (forward)"}),
-        (r"^ffn_pair_kernel<\d+,true", {"flops": nl * (w["du"]["flops"] + w["dy2"]["flops"]), "what": "du + dy2 (backward of the FFN pair)"}),
+        (r"^ffn_pair_kernel<\d+,0", {"flops": nl * (w["ffn1"]["flops"] + w["ffn2"]["flops"]), "what": "FFN1 + GELU + dropout + FFN2 (forward)"}),
+        (r"^ffn_pair_kernel<\d+,1", {"flops": nl * (w["du"]["flops"] + w["dy2"]["flops"]), "what": "du + dy2 (backward of the FFN pair)"}),
         (r"^attn_block_fwd_kernel", {"flops": nl * (w["qkvc"]["flops"] + w["out_proj"]["flops"] + attn_mm), "what": "QKV+cond, attention, out-projection, LayerNorm tail"}),
         (r"^adamw_kernel", {"bytes": 28.0 * n_opt, "what": "clip + AdamW: 16 B read + 12 B written per parameter"}),
         (r"^sumsq_kernel", {"bytes": 4.0 * n_opt, "what": "gradient norm"}),

@@ -22,6 +22,7 @@ batches = [synthetic.make_batch(B, O, P, seed=seed + 10 * rank + i).to(dev) for 
 ups = [torch.randn(B, O, 256, generator=torch.Generator().manual_seed(i)).to(dev) for i in range(4)]
 res = {}
 for mode in ("sequential", "prefetch_graph", "prefetch_eager"):
+    print(f"[rank {rank}] {mode}", file=sys.stderr, flush=True)
     model = helpers.build_prompter(seed, device=dev)          # eval mode: no dropout
     pipe = False if mode == "sequential" else "prefetch"
     tr = HotPathTrainer(model, B, O, P, lr=1e-4, world_size=world, use_graph=mode != "prefetch_eager", pipeline=pipe)
@@ -37,6 +38,7 @@ for mode in ("sequential", "prefetch_graph", "prefetch_eager"):
             tr.step(b, u)
         tr.flush()
     torch.cuda.synchronize()
+    print(f"[rank {rank}] {mode} stepped", file=sys.stderr, flush=True)
     res[mode] = tr.engine.flat_p.clone()
     # replicas stay identical
     ref = res[mode].clone()
@@ -48,5 +50,11 @@ for mode in ("prefetch_graph", "prefetch_eager"):
         print(f"{mode} vs sequential: rel err {e:.2e}")
     assert e < 5e-4, (mode, e)
 if rank == 0:
-    print("ddp equivalence ok")
-dist.destroy_process_group()
+    print("ddp equivalence ok", flush=True)
+# communicators whose collectives were captured in CUDA graphs: destroy_process_group() was seen to block forever here
+# (NCCL 2.28 / torch 2.11); every rank is done and in sync, so leave without the teardown
+torch.cuda.synchronize()
+dist.barrier()
+sys.stdout.flush()
+sys.stderr.flush()
+os._exit(0)
