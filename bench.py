@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--fast", action="store_true",
                     help="headline numbers only: skip the side measurements (CPU / GPU baselines, secondary configs, "
                          "LLM context line, scene-token splice)")
-    ap.add_argument("--chain-sms", type=int, default=int(os.environ.get("MSR3D_CHAIN_SMS", "88")),
+    ap.add_argument("--chain-sms", type=int, default=int(os.environ.get("MSR3D_CHAIN_SMS", "80")),
                     help="SMs of the partition that runs the transformer chain (the frozen encoder of the next batch "
                          "gets the rest); 0 = no partition")
     return ap.parse_args()

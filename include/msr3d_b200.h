@@ -370,6 +370,12 @@ int msr3d_adamw_clip_step_zg_f32(float *params, float *grads, float *exp_avg, fl
                                  long long decay_begin, long long decay_end, float grad_scale, float *state,
                                  unsigned int *ticket, unsigned long long *seed_counter, const float *extra_sumsq,
                                  int zero_grads, msr3d_stream_t stream);
+/* msr3d_adamw_clip_step_f32 that also writes the tf32 big / small operand images (msr3d_split_tf32_f32) of every
+ * updated parameter: the next step's 3xTF32 kernels find their weight operands split. */
+int msr3d_adamw_clip_step_split_f32(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, long long n,
+                                    long long decay_begin, long long decay_end, float grad_scale, float *state,
+                                    unsigned int *ticket, unsigned long long *seed_counter, const float *extra_sumsq,
+                                    float *big, float *small, msr3d_stream_t stream);
 /* Input staging of a pipelined step in one launch (csrc/stage.cu): rotate k: a[i] <- b[i]; b[i] <- c[i] (c nullable)
  * over rot_n[k] floats; copy k: dst[i] <- src[i]; masks (bytes): the same rotation and key_pad[i] <- !a[i]. */
 #define MSR3D_STAGE_MAX 8

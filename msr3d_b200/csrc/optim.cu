@@ -88,7 +88,7 @@ sumsq_kernel(const float *__restrict__ g, long long n, float grad_scale, OptStat
 __global__ void __launch_bounds__(256)
 adamw_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
              float *__restrict__ v, long long n, long long decay_begin, long long decay_end, float grad_scale,
-             OptState *st, int zero_grads) {
+             OptState *st, int zero_grads, float *__restrict__ big, float *__restrict__ small) {
   pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
   const float norm = sqrtf(st->sumsq);
   const float clip = st->max_norm > 0.f ? fminf(1.f, st->max_norm / (norm + 1e-6f)) : 1.f;
@@ -108,7 +108,15 @@ adamw_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
-    p[i] = pi - step_size * (mi / denom);
+    const float pn = pi - step_size * (mi / denom);
+    p[i] = pn;
+    if (big != nullptr) {
+      // tf32 operand images of the updated parameter for the next step's 3xTF32 GEMMs (tma.cuh: big = x rounded to
+      // tf32, small = x - big): written here so that no separate pass over the parameters sits in front of the step
+      const float b = __uint_as_float((__float_as_uint(pn) + 0x1000u) & 0xffffe000u);
+      big[i] = b;
+      small[i] = pn - b;
+    }
   }
 }
 
@@ -151,7 +159,8 @@ using namespace msr3d;
  * ticket: one zero-initialised uint32 on the device. */
 static int adamw_impl(float *params, float *grads, float *exp_avg, float *exp_avg_sq, long long n, long long decay_begin,
                       long long decay_end, float grad_scale, float *state, unsigned int *ticket,
-                      unsigned long long *seed_counter, const float *extra_sumsq, int zero_grads, msr3d_stream_t stream) {
+                      unsigned long long *seed_counter, const float *extra_sumsq, int zero_grads, float *big, float *small,
+                      msr3d_stream_t stream) {
   MSR3D_REQUIRE(params && grads && exp_avg && exp_avg_sq && state && ticket, "adamw: null pointer");
   MSR3D_REQUIRE(n >= 0 && decay_begin >= 0 && decay_begin <= decay_end && decay_end <= n, "adamw: bad sizes");
   if (n == 0) return MSR3D_OK;
@@ -164,7 +173,7 @@ static int adamw_impl(float *params, float *grads, float *exp_avg, float *exp_av
   rc = check_launch("sumsq");
   if (rc) return rc;
   launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq, n, decay_begin, decay_end, grad_scale, st,
-             zero_grads);
+             zero_grads, big, small);
   return check_launch("adamw");
 }
 
@@ -173,7 +182,7 @@ MSR3D_API int msr3d_adamw_clip_step_f32(float *params, const float *grads, float
                                         unsigned int *ticket, unsigned long long *seed_counter, const float *extra_sumsq,
                                         msr3d_stream_t stream) {
   return adamw_impl(params, const_cast<float *>(grads), exp_avg, exp_avg_sq, n, decay_begin, decay_end, grad_scale, state, ticket,
-                    seed_counter, extra_sumsq, 0, stream);
+                    seed_counter, extra_sumsq, 0, nullptr, nullptr, stream);
 }
 
 /* Same, and the gradient buffer is zeroed as it is consumed (zero_grads != 0): the next step's backward accumulates
@@ -183,7 +192,18 @@ MSR3D_API int msr3d_adamw_clip_step_zg_f32(float *params, float *grads, float *e
                                            unsigned int *ticket, unsigned long long *seed_counter,
                                            const float *extra_sumsq, int zero_grads, msr3d_stream_t stream) {
   return adamw_impl(params, grads, exp_avg, exp_avg_sq, n, decay_begin, decay_end, grad_scale, state, ticket, seed_counter,
-                    extra_sumsq, zero_grads, stream);
+                    extra_sumsq, zero_grads, nullptr, nullptr, stream);
+}
+
+/* Same as msr3d_adamw_clip_step_f32; additionally writes the tf32 big / small operand images of every updated parameter
+ * (what msr3d_split_tf32_f32 would produce) into big[0..n) / small[0..n). */
+MSR3D_API int msr3d_adamw_clip_step_split_f32(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, long long n,
+                                              long long decay_begin, long long decay_end, float grad_scale, float *state,
+                                              unsigned int *ticket, unsigned long long *seed_counter,
+                                              const float *extra_sumsq, float *big, float *small, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(big && small, "adamw_split: null image pointer");
+  return adamw_impl(params, const_cast<float *>(grads), exp_avg, exp_avg_sq, n, decay_begin, decay_end, grad_scale, state, ticket,
+                    seed_counter, extra_sumsq, 0, big, small, stream);
 }
 
 /* out[0] = sum_i a[i] * b[i] (device scalar), deterministic. */

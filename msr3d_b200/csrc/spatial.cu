@@ -846,7 +846,7 @@ MSR3D_API int msr3d_attn_fwd_f32(const float *qkvc, int ldq, const float *pw,
     MSR3D_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOnePerSmBytes));
     configured = true;
   }
-  if (g_tune[TUNE_ATTN_PACK] == 0 && smem < kOnePerSmBytes) smem = kOnePerSmBytes;
+  if (g_tune[TUNE_ATTN_PACK] == 2 && smem < kOnePerSmBytes) smem = kOnePerSmBytes;   // A/B knob; default: pack (r2 sweep, SM partition)
   // few (head, scene) pairs and L ~ 60 rows: one warp per query row, rows spread over `zr` CTAs
   int warps = g_tune[TUNE_ATTN_FWD_WARPS] > 0 ? g_tune[TUNE_ATTN_FWD_WARPS] : 16;
   warps = max(1, min(kAttnMaxWarps, warps));
@@ -880,7 +880,7 @@ MSR3D_API int msr3d_attn_bwd_f32(const float *dctx, int ldc, const float *qkvc, 
     configured = true;
   }
   size_t smem_bwd = bytes(L, nz);
-  if (g_tune[TUNE_ATTN_PACK] == 0 && smem_bwd < kOnePerSmBytes) smem_bwd = kOnePerSmBytes;   // one CTA per SM, see attn_fwd
+  if (g_tune[TUNE_ATTN_PACK] == 2 && smem_bwd < kOnePerSmBytes) smem_bwd = kOnePerSmBytes;   // one CTA per SM, see attn_fwd
   launch_pdl_cluster(attn_bwd_kernel, dim3(H, B, nz), dim3(warps * 32), smem_bwd, (cudaStream_t)stream,
                      dim3(1, 1, nz), dctx, ldc, qkvc, ldq, pw, P, LOC, L, H, dqkvc);
   return check_launch("attn_bwd");

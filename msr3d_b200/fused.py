@@ -79,6 +79,7 @@ _C.register_protos({
     "msr3d_adamw_clip_step_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_dot_f32": [c_vp, c_vp, c_ll, c_vp, c_vp],
     "msr3d_adamw_clip_step_zg_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp, c_int, c_vp],
+    "msr3d_adamw_clip_step_split_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_qpos_fwd_acc_f32": [c_vp, c_vp, c_int] + [c_vp] * 15 + [c_vp],
     "msr3d_stage_step": [ctypes.POINTER(StageDesc), c_vp],
     "msr3d_split_tf32_f32": [c_vp, c_vp, c_vp, c_ll, c_vp],
@@ -595,7 +596,9 @@ class FusedPrompter:
         bwd.append(("join", None, (), None, False))
         # prefetch schedule: the geometry was computed beside the encoder of the previous step
         # and the gradient buffer is cleared beside the input encoders (first written by the backward pass)
-        self.pre_prog_nogeo = [e for e in pre_prog if e[3] != "geometry"] + [("memset", None, (self.flat_g,), None, 2)]
+        # ... and the weight images were written by the optimiser of the previous step (refresh_split() after any other
+        # change of the parameters)
+        self.pre_prog_nogeo = [e for e in pre_prog if e[3] not in ("geometry", "split_w")] + [("memset", None, (self.flat_g,), None, 2)]
         return pre_prog, fwd, bwd
 
     def _run(self, prog):
@@ -751,11 +754,11 @@ class FusedPrompter:
             else:
                 self.backward()
                 dist.all_reduce(self.flat_g[:self.n_opt])
-            self.optimizer_step()
+            self.optimizer_step(split=depth2 and self.attn_block_active)
         else:
             self.backward()
             if self.world_size == 1:
-                self.optimizer_step()
+                self.optimizer_step(split=depth2 and self.attn_block_active)
         if with_encoder:
             main.wait_stream(self.enc_stream)  # join
 
@@ -841,6 +844,8 @@ class FusedPrompter:
         main.wait_event(self._copied[0])
         self._encode("emb_next", "obj_fts")
         self._run(self.geo_prog[0])
+        if self.attn_block_active:
+            self.refresh_split()
         for k in ("obj_locs", "obj_masks", "anchor_locs", "anchor_ori", "upstream"):
             self.ws[k + "_n"].copy_(self.ws[k + "_q0"])
         self._slot_free[0].record()
@@ -870,7 +875,7 @@ class FusedPrompter:
             if self.world_size > 1:
                 from . import dist as _dist
                 _dist.allreduce_sum_(self.flat_g[:self.n_opt])
-                self.optimizer_step()
+                self.optimizer_step(split=self.attn_block_active)
         else:
             # two gradient buckets: layers >= 1 are reduced while layer 0 (and the input encoders) are
             # still in their backward pass; the optimiser waits for both collectives on the device
@@ -890,7 +895,7 @@ class FusedPrompter:
             if w_early is not None:
                 w_early.wait()
             w_late.wait()
-            self.optimizer_step()
+            self.optimizer_step(split=self.attn_block_active)
         B, L = self.ws["obj_locs"].shape[:2]
         return self.ws["tokens"].view(B, L, H)
 
@@ -926,6 +931,8 @@ class FusedPrompter:
             dst.copy_(src)
         for k in keys:
             w[k].copy_(saved_in[k])
+        if self.attn_block_active:
+            self.refresh_split()
         torch.cuda.synchronize()
 
     def forward(self):
@@ -942,13 +949,24 @@ class FusedPrompter:
         """Backward from ws['upstream']; accumulates into the flat gradient buffer."""
         self._run(self.bwd_prog)
 
-    def optimizer_step(self, zero_grads: bool = False):
+    def refresh_split(self):
+        """tf32 big / small images of the parameters (after anything but optimizer_step(split=True) changed them)."""
+        _C.call("msr3d_split_tf32_f32", self.flat_p.data_ptr(), self.flat_big.data_ptr(), self.flat_small.data_ptr(),
+                self.n_split, torch.cuda.current_stream().cuda_stream)
+
+    def optimizer_step(self, zero_grads: bool = False, split: bool = False):
         """Global-norm clip + AdamW over the flat buffer.  `self.extra_sumsq` (a 1-element CUDA tensor, optional)
         is added to the squared gradient norm: set it to the squared norm of the trainable parameters that live
         outside this engine (llm_proj, LoRA, ...) to reproduce the reference's clip over ALL model parameters
         (trainer/leo_trainer.py:192-193); the caller then scales its own gradients by `clip_coef()`."""
         n, (d0, d1) = self.n_opt, self.decay_range
         ex = self.extra_sumsq.data_ptr() if self.extra_sumsq is not None else None
+        if split:
+            _C.call("msr3d_adamw_clip_step_split_f32", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(),
+                    self.v.data_ptr(), n, d0, d1, 1.0 / self.world_size, self.opt_state.data_ptr(),
+                    self.ticket.data_ptr(), self.seed_counter.data_ptr(), ex, self.flat_big.data_ptr(),
+                    self.flat_small.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            return
         _C.call("msr3d_adamw_clip_step_zg_f32", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(),
                 self.v.data_ptr(), n, d0, d1, 1.0 / self.world_size, self.opt_state.data_ptr(),
                 self.ticket.data_ptr(), self.seed_counter.data_ptr(), ex, 1 if zero_grads else 0,

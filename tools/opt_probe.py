@@ -32,6 +32,7 @@ for cold in (True, False):
     for zg in (False, True):
         eng.flat_g.normal_()
         print(f"optimizer_step zero_grads={zg} cold={cold}: {t(lambda: eng.optimizer_step(zero_grads=zg), cold=cold):.1f} us")
+    print(f"optimizer_step split=True cold={cold}: {t(lambda: eng.optimizer_step(split=True), cold=cold):.1f} us")
     import ctypes
     from msr3d_b200 import _C
     d = eng._stage_desc(0)
