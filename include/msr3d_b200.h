@@ -124,6 +124,15 @@ int msr3d_pack_weight_f32(const float *W, int N, int K, long long stride_n, long
 int msr3d_linear_tc_f32(const float *A, long long stride_am, long long stride_ak, int M, int K,
                         const void *packed_w, const float *bias, float *out, long long ldo, int N,
                         int act, int pool, int split, int accumulate, int tile_n, msr3d_stream_t stream);
+/* Same contraction (out = act(A W^T + b), optional max over `pool` consecutive rows; packed weights with 128-wide
+ * blocks, split-bf16 hh + hl + lh) for CHAINS of dense layers: the activation operand may be given PRE-SPLIT as two
+ * bf16 tensors (A_hi, A_lo: (M, K), row pitch lda elements; A = NULL) and the result may be written as bf16 hi / lo
+ * (out_hi, out_lo: (M, N), row pitch ldo elements; out = NULL) for the next layer — the fp32 -> bf16 split is then
+ * done once, by the producer's epilogue, instead of by every CTA that reads the tile (SA3 of the frozen encoder:
+ * pointnet2_modules.py:34-75 GroupAll MLP 259 -> 256 -> 512 -> 768). */
+int msr3d_linear_bf16x3_f32(const float *A, const void *A_hi, const void *A_lo, long long lda, int M, int K,
+                            const void *packed_w, const float *bias, float *out, void *out_hi, void *out_lo,
+                            long long ldo, int N, int act, int pool, msr3d_stream_t stream);
 /* General tensor-core GEMM with fp32 (strided) operands on both sides:
  *   out[M,N] (+)= epilogue( act( A[M,K] * B[N,K]^T + bias ) ) + residual
  * Used by the spatial transformer's forward and backward (weights and their transposes are

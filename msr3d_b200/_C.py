@@ -50,6 +50,7 @@ _PROTOS = {
     "msr3d_three_interpolate_grad_f32": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
     # group B
     "msr3d_pack_weight_f32": [_P, c_int, c_int, c_ll, c_ll, _P, _P, c_int, c_int, _P, _P],
+    "msr3d_linear_bf16x3_f32": [_P, _P, _P, c_ll, c_int, c_int, _P, _P, _P, _P, _P, c_ll, c_int, c_int, c_int, _P],
     "msr3d_linear_tc_f32": [_P, c_ll, c_ll, c_int, c_int, _P, _P, _P, c_ll, c_int, c_int, c_int,
                             c_int, c_int, c_int, _P],
     "msr3d_sa_group_f32": [_P, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P],

@@ -36,6 +36,8 @@ constexpr uint32_t kLtBox = kLtM * tma::kRowBytes;     // 16 KB: one [128 x 32 f
 
 struct alignas(64) LinTmaParams {
   CUtensorMap map_a, map_out;
+  CUtensorMap map_a_hi, map_a_lo;        // PS: the activation operand arrives as bf16 hi / lo tensors [M, K]
+  uint16_t *out_hi, *out_lo;             // OS: the result leaves as bf16 hi / lo tensors [M, ldo] (next layer's operand)
   const uint8_t *PW;
   const float *bias;
   float *out;
@@ -77,7 +79,11 @@ __device__ __forceinline__ float lt_act(float v, int act) {
   return v;
 }
 
-template <int BN>
+// PS (pre-split): A is given as two bf16 tensors (hi, lo) written by the previous layer's epilogue — the TMA boxes
+//     {64 bf16, 128 rows} land exactly as the swizzled operand images, no conversion pass (r2 timeline: the in-place
+//     fp32 -> bf16 hi/lo conversion made SA3's 512 -> 768 layer 75 us on the encoder's SM partition, 3 us of it MMAs);
+// OS (output split): the epilogue writes bf16 hi / lo instead of fp32 (for a PS consumer).
+template <int BN, bool PS, bool OS>
 __global__ void __launch_bounds__(kLtThreads, 1)
 linear_tma_kernel(const __grid_constant__ LinTmaParams g) {
   using C = LinTmaCfg<BN>;
@@ -102,7 +108,12 @@ linear_tma_kernel(const __grid_constant__ LinTmaParams g) {
     }
     mbar_init(&acc_full, 1);
     fence_mbar_init();
-    tma::prefetch_map(&g.map_a);
+    if (PS) {
+      tma::prefetch_map(&g.map_a_hi);
+      tma::prefetch_map(&g.map_a_lo);
+    } else {
+      tma::prefetch_map(&g.map_a);
+    }
     if (g.tma_out) tma::prefetch_map(&g.map_out);
   }
   if (warp == 2) tmem_alloc(&s_tmem, C::kTmemCols);
@@ -121,8 +132,13 @@ linear_tma_kernel(const __grid_constant__ LinTmaParams g) {
       auto load_a = [&](int i) {
         const int s = i % S;
         uint8_t *dst = smem + (size_t)s * C::kStage;
-        tma::load_2d(dst, &g.map_a, i * kLtChunk, m0, &full[s]);
-        tma::load_2d(dst + kLtBox, &g.map_a, i * kLtChunk + 32, m0, &full[s]);
+        if (PS) {
+          tma::load_2d(dst, &g.map_a_hi, i * kLtChunk, m0, &full[s]);
+          tma::load_2d(dst + kLtBox, &g.map_a_lo, i * kLtChunk, m0, &full[s]);
+        } else {
+          tma::load_2d(dst, &g.map_a, i * kLtChunk, m0, &full[s]);
+          tma::load_2d(dst + kLtBox, &g.map_a, i * kLtChunk + 32, m0, &full[s]);
+        }
       };
       const int pre = min(S, nkc);
       for (int i = 0; i < pre; ++i) {
@@ -146,7 +162,8 @@ linear_tma_kernel(const __grid_constant__ LinTmaParams g) {
 #pragma unroll 1
     for (int i = 0; i < nkc; ++i) {
       const int s = i % S;
-      mbar_wait(&conv_done[s], (i / S) & 1);
+      if (PS) mbar_wait(&full[s], (i / S) & 1);
+      else mbar_wait(&conv_done[s], (i / S) & 1);
       fence_after_sync();
       if (elect_one()) {
         const uint32_t base = smem_u32(smem + (size_t)s * C::kStage);
@@ -173,7 +190,7 @@ linear_tma_kernel(const __grid_constant__ LinTmaParams g) {
     // this thread converts row `cr`, k half `cb` of every chunk: eight 16 B fp32 chunks in, four bf16 hi + four lo out
     const int cr = ct & 127, cb = ct >> 7;
 #pragma unroll 1
-    for (int i = 0; i < nkc; ++i) {
+    for (int i = 0; i < (PS ? 0 : nkc); ++i) {
       const int s = i % S;
       uint8_t *tile = smem + (size_t)s * C::kStage;
       mbar_wait(&full[s], (i / S) & 1);
@@ -204,7 +221,33 @@ linear_tma_kernel(const __grid_constant__ LinTmaParams g) {
     mbar_wait(&acc_full, 0);
     fence_after_sync();
     constexpr int kColsPerHalf = BN / 2;
-    if (g.pool <= 1 && g.tma_out) {
+    if (OS) {
+      // bf16 hi / lo rows of the next layer's operand: 16 columns = 32 B of each image per step
+      const bool row_ok = grow < g.M;
+#pragma unroll 1
+      for (int c0 = half * kColsPerHalf; c0 < (half + 1) * kColsPerHalf; c0 += 16) {
+        const int n0 = n_base + c0;
+        if (n0 >= g.N) break;
+        uint32_t acc[16];
+        lt_tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+        tmem_ld_wait();
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = lt_act(__uint_as_float(acc[2 * j]) + (g.bias != nullptr ? g.bias[n0 + 2 * j] : 0.f), g.act);
+          const float b = lt_act(__uint_as_float(acc[2 * j + 1]) + (g.bias != nullptr ? g.bias[n0 + 2 * j + 1] : 0.f), g.act);
+          split_pack2(a, b, hi[j], lo[j]);
+        }
+        if (row_ok) {
+          uint4 *ph = reinterpret_cast<uint4 *>(g.out_hi + (size_t)grow * g.ldo + n0);
+          uint4 *pl = reinterpret_cast<uint4 *>(g.out_lo + (size_t)grow * g.ldo + n0);
+          ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        }
+      }
+    } else if (g.pool <= 1 && g.tma_out) {
 #pragma unroll 1
       for (int c0 = half * kColsPerHalf; c0 < (half + 1) * kColsPerHalf; c0 += 16) {
         const int n0 = n_base + c0;
@@ -278,16 +321,33 @@ linear_tma_kernel(const __grid_constant__ LinTmaParams g) {
   if (warp == 2) tmem_dealloc(tmem_d, C::kTmemCols);
 }
 
-template <int BN>
+template <int BN, bool PS = false, bool OS = false>
 static int launch_linear_tma(const LinTmaParams &g, cudaStream_t stream) {
   using C = LinTmaCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    MSR3D_CUDA(cudaFuncSetAttribute(linear_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+    MSR3D_CUDA(cudaFuncSetAttribute(linear_tma_kernel<BN, PS, OS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
     configured = true;
   }
-  launch_pdl(linear_tma_kernel<BN>, dim3(ceil_div(g.M, kLtM), ceil_div(g.N, BN)), dim3(kLtThreads), C::kSmem, stream, g);
+  launch_pdl(linear_tma_kernel<BN, PS, OS>, dim3(ceil_div(g.M, kLtM), ceil_div(g.N, BN)), dim3(kLtThreads), C::kSmem, stream, g);
   return check_launch("linear_tma");
+}
+
+// 2-D bf16 row-major tensor [rows][cols], row pitch `ld` elements; box = 64 columns (128 B) x 128 rows, 128 B swizzle
+static int make_map_bf16(CUtensorMap *map, const void *base, long long rows, long long cols, long long ld) {
+  tma::EncodeTiledFn fn = tma::encode_fn();
+  if (fn == nullptr) return set_error(MSR3D_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  MSR3D_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld & 7) == 0 && ld >= cols && rows > 0 && cols > 0,
+                "bf16 tensor map: base must be 16 B aligned and the row pitch a multiple of 8 elements");
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)kLtM};
+  const cuuint32_t estride[2] = {1u, 1u};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(MSR3D_ERR_CUDA, "cuTensorMapEncodeTiled (bf16) failed (%d)", (int)r);
+  return MSR3D_OK;
 }
 
 // Returns MSR3D_ERR_UNSUPPORTED (without touching the error string of a caller that falls back) when the
@@ -318,3 +378,40 @@ int linear_tma_try(const float *A, long long stride_am, long long stride_ak, int
 }
 
 }  // namespace msr3d
+
+using namespace msr3d;
+
+/* see include/msr3d_b200.h */
+MSR3D_API int msr3d_linear_bf16x3_f32(const float *A, const void *A_hi, const void *A_lo, long long lda, int M, int K,
+                                      const void *packed_w, const float *bias, float *out, void *out_hi, void *out_lo,
+                                      long long ldo, int N, int act, int pool, msr3d_stream_t stream) {
+  const bool ps = A_hi != nullptr, os = out_hi != nullptr;
+  MSR3D_REQUIRE(packed_w && M >= 0 && K > 0 && N > 0, "linear_bf16x3: bad arguments");
+  MSR3D_REQUIRE(ps ? (A_lo != nullptr) : (A != nullptr), "linear_bf16x3: activation operand missing");
+  MSR3D_REQUIRE(os ? (out_lo != nullptr && pool <= 1 && (ldo & 7) == 0 && (N & 15) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 15) == 0)
+                   : (out != nullptr),
+                "linear_bf16x3: output (hi / lo outputs need pool <= 1, N %% 16 == 0, ldo %% 8 == 0, 16 B alignment)");
+  MSR3D_REQUIRE(pool <= 1 || (pool <= 32 && (pool & (pool - 1)) == 0 && M % pool == 0), "linear_bf16x3: pool=%d", pool);
+  if (M == 0) return MSR3D_OK;
+  if (!ps && !os)
+    return linear_tma_try(A, lda, 1, M, K, packed_w, bias, out, ldo, N, act, pool, 3, 0, 128, (cudaStream_t)stream);
+  LinTmaParams g{};
+  g.PW = static_cast<const uint8_t *>(packed_w);
+  g.bias = bias; g.out = out; g.ldo = ldo;
+  g.out_hi = static_cast<uint16_t *>(out_hi); g.out_lo = static_cast<uint16_t *>(out_lo);
+  g.M = M; g.N = N; g.K = K; g.nkc = ceil_div(K, kLtChunk);
+  g.act = act; g.pool = pool; g.tma_out = 0;
+  int rc;
+  if (ps) {
+    if ((rc = make_map_bf16(&g.map_a_hi, A_hi, M, K, lda)) != MSR3D_OK) return rc;
+    if ((rc = make_map_bf16(&g.map_a_lo, A_lo, M, K, lda)) != MSR3D_OK) return rc;
+  } else {
+    MSR3D_REQUIRE((lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && lda >= K, "linear_bf16x3: A alignment");
+    if ((rc = tma::make_map_f32(&g.map_a, A, M, K, lda, kLtM, false)) != MSR3D_OK) return rc;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ps && os) return launch_linear_tma<128, true, true>(g, st);
+  if (ps) return launch_linear_tma<128, true, false>(g, st);
+  return launch_linear_tma<128, false, true>(g, st);
+}

@@ -372,6 +372,13 @@ class PointNetPP(nn.Module):
             self._ws[name] = t
         return t
 
+    def _workspace16(self, name, shape, device):
+        t = self._ws.get(name)
+        if t is None or t.shape != torch.Size(shape) or t.device != device:
+            t = torch.empty(shape, dtype=torch.bfloat16, device=device)
+            self._ws[name] = t
+        return t
+
     @torch.no_grad()
     def forward_fused(self, pc, split: Optional[int] = None, trace: Optional[dict] = None,
                       out: Optional[torch.Tensor] = None):
@@ -396,17 +403,30 @@ class PointNetPP(nn.Module):
                 torch.cuda.current_stream().cuda_stream)
         # level 3 (GroupAll): three GEMMs, max over the np2 points of a cloud in the last epilogue
         a = x3.view(Bc * np2, ld3)[:, :k3]
-        h1 = ops.linear_tc(a, pk["sa3"][0][0], pk["sa3"][1][0], act="relu", split=split,
-                           out=self._workspace("h1", (Bc * np2, w3[1]), dev), tag="sa3_l1")
-        h2 = ops.linear_tc(h1, pk["sa3"][0][1], pk["sa3"][1][1], act="relu", split=split,
-                           out=self._workspace("h2", (Bc * np2, w3[2]), dev), tag="sa3_l2")
-        w_l3 = pk["sa3"][0][2]
-        mt = -(-(Bc * np2) // 128)
-        if (ops.SA3_WIDE_TILES and mt * -(-w3[3] // 128) > ops.NUM_SMS and pk["sa3_w192"].BN == 192
-                and mt * (w3[3] // 192) <= ops.NUM_SMS):
-            w_l3 = pk["sa3_w192"]
-        g = ops.linear_tc(h2, w_l3, pk["sa3"][1][2], act="relu", pool=np2, split=split,
-                          out=self._workspace("g", (Bc, w3[3]), dev), tag="sa3_l3")
+        chain = (ops.SA3_CHAIN and (split or ops.DEFAULT_SPLIT) == 3 and all(w.BN == 128 for w in pk["sa3"][0])
+                 and w3[1] % 16 == 0 and w3[2] % 16 == 0)
+        if chain:
+            # the two inner activations leave their producer as bf16 hi / lo images: the consumer's TMA boxes land as
+            # operand tiles, no CTA converts anything (csrc/linear_tma.cu)
+            M3 = Bc * np2
+            h1s = (self._workspace16("h1_hi", (M3, w3[1]), dev), self._workspace16("h1_lo", (M3, w3[1]), dev))
+            h2s = (self._workspace16("h2_hi", (M3, w3[2]), dev), self._workspace16("h2_lo", (M3, w3[2]), dev))
+            ops.linear_chain(a, pk["sa3"][0][0], pk["sa3"][1][0], act="relu", out_split=h1s, tag="sa3_l1")
+            ops.linear_chain(h1s, pk["sa3"][0][1], pk["sa3"][1][1], act="relu", out_split=h2s, tag="sa3_l2")
+            g = ops.linear_chain(h2s, pk["sa3"][0][2], pk["sa3"][1][2], act="relu", pool=np2,
+                                 out=self._workspace("g", (Bc, w3[3]), dev), tag="sa3_l3")
+        else:
+            h1 = ops.linear_tc(a, pk["sa3"][0][0], pk["sa3"][1][0], act="relu", split=split,
+                               out=self._workspace("h1", (Bc * np2, w3[1]), dev), tag="sa3_l1")
+            h2 = ops.linear_tc(h1, pk["sa3"][0][1], pk["sa3"][1][1], act="relu", split=split,
+                               out=self._workspace("h2", (Bc * np2, w3[2]), dev), tag="sa3_l2")
+            w_l3 = pk["sa3"][0][2]
+            mt = -(-(Bc * np2) // 128)
+            if (ops.SA3_WIDE_TILES and mt * -(-w3[3] // 128) > ops.NUM_SMS and pk["sa3_w192"].BN == 192
+                    and mt * (w3[3] // 192) <= ops.NUM_SMS):
+                w_l3 = pk["sa3_w192"]
+            g = ops.linear_tc(h2, w_l3, pk["sa3"][1][2], act="relu", pool=np2, split=split,
+                              out=self._workspace("g", (Bc, w3[3]), dev), tag="sa3_l3")
         out = ops.linear_tc(g, pk["fc"][0], pk["fc"][1], split=split, tag="fc", out=out)
         if trace is not None:
             trace.update(fps1=fps1, ball1=ball1, xyz1=xyz1, f1=f1, fps2=fps2, ball2=ball2, xyz2=xyz2,

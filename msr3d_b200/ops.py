@@ -20,6 +20,7 @@ NUM_SMS = 148   # B200
 #: 64 doubles their CTA count.  A/B: MSR3D_ENC_BN64=0/1
 ENC_SMALL_TILES = __import__("os").environ.get("MSR3D_ENC_BN64", "0") == "1"
 SA3_WIDE_TILES = __import__("os").environ.get("MSR3D_SA3_WIDE", "0") == "1"
+SA3_CHAIN = __import__("os").environ.get("MSR3D_SA3_CHAIN", "1") == "1"     # SA3 layers hand their outputs on pre-split (bf16 hi / lo)
 #: roofline.KernelTimer or None; when set, launches are bracketed by CUDA events on the current stream
 TIMER = None
 
@@ -94,6 +95,39 @@ def linear_tc(A: torch.Tensor, W: PackedWeight, bias: Optional[torch.Tensor] = N
                 W.data.data_ptr(), _ptr(bias), out.data_ptr(), out.stride(0), W.N, ACT[act],
                 int(pool), int(split or DEFAULT_SPLIT), int(accumulate), int(W.BN), _stream())
     return out
+
+
+def linear_chain(A, W: PackedWeight, bias: Optional[torch.Tensor], act: str = "none", pool: int = 1,
+                 out: Optional[torch.Tensor] = None, out_split=None, tag: Optional[str] = None):
+    """One dense layer of a chain (csrc/linear_tma.cu, split-bf16 hh + hl + lh): `A` is an fp32 (M, K) tensor or a
+    (hi, lo) pair of bf16 (M, K) tensors written by the previous layer; the result goes to `out` (fp32, optionally
+    max-pooled over `pool` rows) or, with out_split=(hi, lo) bf16 (M, N) tensors, leaves PRE-SPLIT for the next layer."""
+    assert W.BN == 128 and W.BK == 64
+    if isinstance(A, tuple):
+        a_hi, a_lo = A
+        assert a_hi.dtype == torch.bfloat16 and a_lo.dtype == torch.bfloat16 and a_hi.stride(1) == 1 and a_hi.shape == a_lo.shape
+        M, K = a_hi.shape
+        a_args = (None, a_hi.data_ptr(), a_lo.data_ptr(), a_hi.stride(0))
+        dev = a_hi.device
+    else:
+        assert A.is_cuda and A.dtype == torch.float32 and A.dim() == 2 and A.stride(1) == 1
+        M, K = A.shape
+        a_args = (A.data_ptr(), None, None, A.stride(0))
+        dev = A.device
+    assert K == W.K, (K, W.K)
+    if out_split is not None:
+        o_hi, o_lo = out_split
+        assert o_hi.dtype == torch.bfloat16 and o_hi.shape == (M, W.N) and o_lo.shape == (M, W.N) and o_hi.stride(0) == o_lo.stride(0)
+        o_args = (None, o_hi.data_ptr(), o_lo.data_ptr(), o_hi.stride(0))
+    else:
+        rows = M // pool if pool > 1 else M
+        if out is None:
+            out = torch.empty(rows, W.N, dtype=torch.float32, device=dev)
+        o_args = (out.data_ptr(), None, None, out.stride(0))
+    with torch.cuda.device(dev), _range(tag):
+        _C.call("msr3d_linear_bf16x3_f32", a_args[0], a_args[1], a_args[2], a_args[3], M, K, W.data.data_ptr(), _ptr(bias),
+                o_args[0], o_args[1], o_args[2], o_args[3], W.N, ACT[act], int(pool), _stream())
+    return out_split if out_split is not None else out
 
 
 def sa_group(xyz_records: torch.Tensor, npoint: int, radius: float, nsample: int, tag: Optional[str] = None):

@@ -66,6 +66,28 @@ def _check_grads(model, want, tol=TOL):
     return worst
 
 
+def _check_grads_own_scale(model, want, tol):
+    """every gradient relative to ITS OWN magnitude (the check above floors the scale at 1e-3 of the largest
+    gradient in the model, which leaves LayerNorm biases and lang_cond_fc effectively unchecked).  Parameters whose
+    gradient is analytically zero (w_ks.bias: softmax is shift-invariant in the keys) are compared absolutely."""
+    gmax = max(float(w.abs().max()) for w in want.values() if w is not None)
+    worst = ("", 0.0)
+    for n, p in model.named_parameters():
+        w = want.get(n)
+        if not p.requires_grad or w is None:
+            continue
+        g = p.grad.detach().cpu()
+        own = float(w.abs().max())
+        if own < 1e-6 * gmax:                       # analytically zero
+            assert float(g.abs().max()) < 1e-5 * gmax, n
+            continue
+        err = float((g - w).abs().max()) / own
+        if err > worst[1]:
+            worst = (n, err)
+    assert worst[1] < tol, worst
+    return worst
+
+
 @pytest.mark.parametrize("split", [6, 3])
 @pytest.mark.parametrize("B,O,P,seed", [(1, 8, 256, 1001), (2, 12, 1024, 2002), (4, 60, 1024, 31)])
 def test_fused_forward_backward_match_oracle(sd_spec, B, O, P, seed, split):
@@ -88,6 +110,9 @@ def test_fused_forward_backward_match_oracle(sd_spec, B, O, P, seed, split):
     # reaches ~1e-3 on the ill-conditioned softmax-logit / lang_cond gradients
     worst = _check_grads(model, want, tol=3e-4 if split == 6 else 5e-3)
     print(f"fused split={split} B={B} O={O} P={P}: tokens rel err {e:.2e}; worst grad {worst[0]} {worst[1]:.2e}")
+    if split == 6:
+        own = _check_grads_own_scale(model, want, tol=2e-3)
+        print(f"   per-tensor (own scale): worst {own[0]} {own[1]:.2e}")
     assert e < (1e-4 if split == 6 else TOL)
     # (2) end to end: oracle encoder (fp32 CPU) + oracle transformer.  The 1.5e-5 difference of the
     # encoder outputs is amplified ~30x by the conditioning of d(q,k,cond) in layer 0.
