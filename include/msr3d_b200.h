@@ -385,6 +385,35 @@ int msr3d_adamw_clip_step_split_f32(float *params, const float *grads, float *ex
                                     long long decay_begin, long long decay_end, float grad_scale, float *state,
                                     unsigned int *ticket, unsigned long long *seed_counter, const float *extra_sumsq,
                                     float *big, float *small, msr3d_stream_t stream);
+/* Clip + AdamW when the squared gradient norm is already in state[0] (msr3d_grad_norm_finalize_f32): the update
+ * kernel alone; big / small (nullable) as in msr3d_adamw_clip_step_split_f32. */
+int msr3d_adamw_apply_f32(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, long long n,
+                          long long decay_begin, long long decay_end, float grad_scale, float *state, float *big,
+                          float *small, msr3d_stream_t stream);
+/* Data-parallel gradient exchange over NVLink peer memory (csrc/allreduce.cu; replaces the NCCL all-reduce behind DDP,
+ * trainer/leo_trainer.py:50-52,135).  buf[q] / flags[q] / partials[q]: rank q's copy of three SYMMETRIC allocations as
+ * mapped into this process (torch.distributed._symmetric_memory): the flat gradient buffer, 2 * MSR3D_AR_MAX_BLOCKS *
+ * MSR3D_AR_MAX_WORLD * 2 zero-initialised uint32 flags, 2 * MSR3D_AR_MAX_WORLD * MSR3D_AR_MAX_BLOCKS floats.  epoch:
+ * local zero-initialised uint32[2 * MSR3D_AR_MAX_BLOCKS].  channel 0 / 1: two buckets may be in flight at once.
+ * msr3d_allreduce_sum_f32 sums elements [begin, end) of the gradient buffer over the ranks IN PLACE on every rank
+ * (fixed summation order: bit-identical replicas) and leaves the squared norm of each rank's slice in `partials`;
+ * every rank must launch it with the same range, channel and nblocks.  msr3d_grad_norm_finalize_f32 adds the partials
+ * of both channels (nblocks1 = 0: one bucket) * grad_scale^2 (+ *extra_sumsq) into state[0], increments state[1]
+ * (step) and *seed_counter: what the norm pass of msr3d_adamw_clip_step_f32 does. */
+#define MSR3D_AR_MAX_WORLD 8
+#define MSR3D_AR_MAX_BLOCKS 64
+typedef struct msr3d_allreduce_desc {
+  float *buf[MSR3D_AR_MAX_WORLD];
+  unsigned *flags[MSR3D_AR_MAX_WORLD];
+  float *partials[MSR3D_AR_MAX_WORLD];
+  unsigned *epoch;
+  int rank, world, channel;
+} msr3d_allreduce_desc;
+int msr3d_allreduce_sum_f32(const msr3d_allreduce_desc *d, long long begin, long long end, int nblocks,
+                            msr3d_stream_t stream);
+int msr3d_grad_norm_finalize_f32(const float *partials, int world, int nblocks0, int nblocks1, float grad_scale,
+                                 const float *extra_sumsq, float *state, unsigned long long *seed_counter,
+                                 msr3d_stream_t stream);
 /* Input staging of a pipelined step in one launch (csrc/stage.cu): rotate k: a[i] <- b[i]; b[i] <- c[i] (c nullable)
  * over rot_n[k] floats; copy k: dst[i] <- src[i]; masks (bytes): the same rotation and key_pad[i] <- !a[i]. */
 #define MSR3D_STAGE_MAX 8

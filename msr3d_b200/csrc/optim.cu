@@ -206,6 +206,20 @@ MSR3D_API int msr3d_adamw_clip_step_split_f32(float *params, const float *grads,
                     seed_counter, extra_sumsq, 0, big, small, stream);
 }
 
+MSR3D_API int msr3d_adamw_apply_f32(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, long long n,
+                                    long long decay_begin, long long decay_end, float grad_scale, float *state, float *big,
+                                    float *small, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(params && grads && exp_avg && exp_avg_sq && state, "adamw_apply: null pointer");
+  MSR3D_REQUIRE(n >= 0 && decay_begin >= 0 && decay_begin <= decay_end && decay_end <= n, "adamw_apply: bad sizes");
+  MSR3D_REQUIRE((big == nullptr) == (small == nullptr), "adamw_apply: both images or none");
+  if (n == 0) return MSR3D_OK;
+  int grid = (int)((n + 255) / 256);
+  if (grid > kSumsqBlocks) grid = kSumsqBlocks;
+  launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, params, const_cast<float *>(grads), exp_avg, exp_avg_sq, n,
+             decay_begin, decay_end, grad_scale, reinterpret_cast<OptState *>(state), 0, big, small);
+  return check_launch("adamw");
+}
+
 /* out[0] = sum_i a[i] * b[i] (device scalar), deterministic. */
 MSR3D_API int msr3d_dot_f32(const float *a, const float *b, long long n, float *out, msr3d_stream_t stream) {
   MSR3D_REQUIRE(a && b && out && n >= 0, "dot: bad args");

@@ -54,6 +54,15 @@ class StageDesc(ctypes.Structure):
                 ("n_rotate", c_int), ("n_copy", c_int)]
 
 
+AR_MAX_WORLD, AR_MAX_BLOCKS = 8, 64
+
+
+class AllreduceDesc(ctypes.Structure):
+    """Mirror of `msr3d_allreduce_desc` (include/msr3d_b200.h)."""
+    _fields_ = [("buf", c_vp * AR_MAX_WORLD), ("flags", c_vp * AR_MAX_WORLD), ("partials", c_vp * AR_MAX_WORLD),
+                ("epoch", c_vp), ("rank", c_int), ("world", c_int), ("channel", c_int)]
+
+
 _C.register_protos({
     "msr3d_gemm_tc_f32": [ctypes.POINTER(GemmDesc), c_vp],
     "msr3d_gemm_tf32x3_supported": [ctypes.POINTER(GemmDesc)],
@@ -82,6 +91,9 @@ _C.register_protos({
     "msr3d_adamw_clip_step_split_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_qpos_fwd_acc_f32": [c_vp, c_vp, c_int] + [c_vp] * 15 + [c_vp],
     "msr3d_stage_step": [ctypes.POINTER(StageDesc), c_vp],
+    "msr3d_adamw_apply_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp],
+    "msr3d_allreduce_sum_f32": [ctypes.POINTER(AllreduceDesc), c_ll, c_ll, c_int, c_vp],
+    "msr3d_grad_norm_finalize_f32": [c_vp, c_int, c_int, c_int, c_float, c_vp, c_vp, c_vp, c_vp],
     "msr3d_split_tf32_f32": [c_vp, c_vp, c_vp, c_ll, c_vp],
     "msr3d_ffn_pair_fwd_ps_f32": [c_vp] * 8 + [c_int, c_int, c_ull, c_vp, c_float, c_uint, c_vp, c_vp, c_vp, c_int, c_vp],
     "msr3d_ffn_pair_bwd_ps_f32": [c_vp] * 7 + [c_int, c_int, c_vp, c_vp, c_int, c_vp],
@@ -240,7 +252,11 @@ class FusedPrompter:
         self.n_opt = lay["n_opt"]
         total4 = (total + 3) // 4 * 4
         self.flat_p = torch.zeros(total4, dtype=torch.float32, device=self.dev)[:total]
-        self.flat_g = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.p2p = None
+        if self.world_size > 1:
+            self.p2p = self._symmetric_gradients(total4)
+        self.flat_g = (self.p2p["grad"][:total] if self.p2p is not None
+                       else torch.zeros(total, dtype=torch.float32, device=self.dev))
         # tf32 big / small operand images of the whole parameter buffer, refreshed once per step (_programs)
         self.flat_big = torch.zeros(total4, dtype=torch.float32, device=self.dev)
         self.flat_small = torch.zeros(total4, dtype=torch.float32, device=self.dev)
@@ -258,6 +274,66 @@ class FusedPrompter:
         self.n_trainable = sum(p.numel() for _, p in named)
         if self.world_size > 1:
             _dist.broadcast_(self.flat_p)     # identical replicas, as DDP's constructor guarantees
+
+    def _symmetric_gradients(self, n):
+        """Data parallel: the flat gradient buffer (and the flags / norm partials of csrc/allreduce.cu) in SYMMETRIC
+        memory, so that the all-reduce is this library's own NVLink peer-memory kernel instead of ncclAllReduce.
+        None (NCCL stays the exchange) when MSR3D_P2P_ALLREDUCE=0 or symmetric memory is not available."""
+        import os
+        import warnings
+        if os.environ.get("MSR3D_P2P_ALLREDUCE", "1") != "1" or self.world_size > AR_MAX_WORLD:
+            return None
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            group = dist.group.WORLD
+            enable = getattr(symm_mem, "enable_symm_mem_for_group", None)
+            if enable is not None:
+                try:
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        enable(group.group_name)
+                except Exception:  # noqa: BLE001
+                    pass
+            out = {}
+            for key, numel, dtype in (("grad", n, torch.float32), ("flags", 2 * AR_MAX_BLOCKS * AR_MAX_WORLD * 2, torch.int32),
+                                      ("partials", 2 * AR_MAX_WORLD * AR_MAX_BLOCKS, torch.float32)):
+                t = symm_mem.empty(numel, dtype=dtype, device=self.dev)
+                t.zero_()
+                hdl = symm_mem.rendezvous(t, group)
+                out[key], out[key + "_ptrs"], out[key + "_hdl"] = t, [int(x) for x in hdl.buffer_ptrs], hdl
+            out["epoch"] = torch.zeros(2 * AR_MAX_BLOCKS, dtype=torch.int32, device=self.dev)
+            out["rank"] = dist.get_rank()
+            torch.cuda.synchronize()
+            dist.barrier()                      # every rank's flags are zero before anybody launches
+            descs = []
+            for ch in (0, 1):
+                d = AllreduceDesc()
+                for q in range(self.world_size):
+                    d.buf[q], d.flags[q], d.partials[q] = out["grad_ptrs"][q], out["flags_ptrs"][q], out["partials_ptrs"][q]
+                d.epoch, d.rank, d.world, d.channel = out["epoch"].data_ptr(), out["rank"], self.world_size, ch
+                descs.append(d)
+            out["desc"] = descs
+            return out
+        except Exception as e:  # noqa: BLE001
+            warnings.warn(f"msr3d_b200: symmetric memory unavailable ({type(e).__name__}: {e}); gradients are exchanged with NCCL")
+            return None
+
+    def _allreduce_p2p(self, channel, begin, end, nblocks, stream):
+        rc = _C.lib().msr3d_allreduce_sum_f32(ctypes.byref(self.p2p["desc"][channel]), begin, end, nblocks, stream.cuda_stream)
+        if rc != 0:
+            raise _C.Msr3dError(f"allreduce_sum failed ({rc}): {_C.lib().msr3d_last_error().decode()}")
+
+    def _optimizer_after_p2p(self, nb0, nb1, split):
+        """Clip + AdamW on gradients reduced by _allreduce_p2p: the norm partials came with the data."""
+        st = torch.cuda.current_stream().cuda_stream
+        ex = self.extra_sumsq.data_ptr() if self.extra_sumsq is not None else None
+        _C.call("msr3d_grad_norm_finalize_f32", self.p2p["partials"].data_ptr(), self.world_size, nb0, nb1,
+                1.0 / self.world_size, ex, self.opt_state.data_ptr(), self.seed_counter.data_ptr(), st)
+        n, (d0, d1) = self.n_opt, self.decay_range
+        _C.call("msr3d_adamw_apply_f32", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                n, d0, d1, 1.0 / self.world_size, self.opt_state.data_ptr(),
+                self.flat_big.data_ptr() if split else None, self.flat_small.data_ptr() if split else None, st)
 
     def P(self, name):  # device pointer of a parameter / its gradient
         return self.flat_p.data_ptr() + 4 * self.offs[name]
@@ -743,18 +819,35 @@ class FusedPrompter:
             # right after it; clip + AdamW follow on the device
             import torch.distributed as dist
             (e0, e1), (l0, l1) = self.bucket_early, self.bucket_late
-            if self.ddp_buckets and e1 > e0:
-                self._run(self.bwd_prog[:self.bwd_split] + [("join", None, (), None, False)])
-                self.comm_stream.wait_stream(main)
-                with torch.cuda.stream(self.comm_stream):
-                    dist.all_reduce(self.flat_g[e0:e1])
-                self._run(self.bwd_prog[self.bwd_split:])
-                dist.all_reduce(self.flat_g[l0:l1])
-                main.wait_stream(self.comm_stream)
+            split_w = depth2 and self.attn_block_active
+            if self.p2p is not None:
+                # this library's own exchange over NVLink peer memory (csrc/allreduce.cu), norm partials fused in
+                nb0, nb1 = 32, 48
+                if self.ddp_buckets and e1 > e0:
+                    self._run(self.bwd_prog[:self.bwd_split] + [("join", None, (), None, False)])
+                    self.comm_stream.wait_stream(main)
+                    self._allreduce_p2p(0, e0, e1, nb0, self.comm_stream)
+                    self._run(self.bwd_prog[self.bwd_split:])
+                    self._allreduce_p2p(1, l0, l1, nb1, main)
+                    main.wait_stream(self.comm_stream)
+                    self._optimizer_after_p2p(nb0, nb1, split_w)
+                else:
+                    self.backward()
+                    self._allreduce_p2p(0, 0, self.n_opt, AR_MAX_BLOCKS, main)
+                    self._optimizer_after_p2p(AR_MAX_BLOCKS, 0, split_w)
             else:
-                self.backward()
-                dist.all_reduce(self.flat_g[:self.n_opt])
-            self.optimizer_step(split=depth2 and self.attn_block_active)
+                if self.ddp_buckets and e1 > e0:
+                    self._run(self.bwd_prog[:self.bwd_split] + [("join", None, (), None, False)])
+                    self.comm_stream.wait_stream(main)
+                    with torch.cuda.stream(self.comm_stream):
+                        dist.all_reduce(self.flat_g[e0:e1])
+                    self._run(self.bwd_prog[self.bwd_split:])
+                    dist.all_reduce(self.flat_g[l0:l1])
+                    main.wait_stream(self.comm_stream)
+                else:
+                    self.backward()
+                    dist.all_reduce(self.flat_g[:self.n_opt])
+                self.optimizer_step(split=split_w)
         else:
             self.backward()
             if self.world_size == 1:

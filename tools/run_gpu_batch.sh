@@ -1,11 +1,11 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -12 > gpurun_out/r2_t14.log
-cat gpurun_out/r2_t14.log
-run() { r=$(env "$@" timeout 300 python bench.py --steps 40 --warmup 5 --fast 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['ms_per_step'],4), round(d['value']), round(d['e2e']['value'])); print({k:round(v['us_per_step'],1) for k,v in d['kernels'].items() if 'linear_t' in k})"); echo "$*: $r"; }
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29631 tools/check_ddp_equiv.py > gpurun_out/r2_ddp_eq2.log 2>&1
+echo "rc=$?"; grep -v "^\[rank\|^$\|\*\*\*\|OMP_NUM" gpurun_out/r2_ddp_eq2.log | tail -8
+run2() { r=$(env "$@" timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29577 bench.py --gpus 2 --steps 40 --warmup 5 --fast 2>gpurun_out/r2_ddp_err.log | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['ms_per_step'],4), round(d['value']), round(d['e2e']['value']))"); echo "$*: $r"; }
 {
-run MSR3D_SA3_CHAIN=0
-run MSR3D_SA3_CHAIN=1
-run MSR3D_SA3_CHAIN=1 MSR3D_CHAIN_SMS=88
-run MSR3D_SA3_CHAIN=1 MSR3D_CHAIN_SMS=96
-} > gpurun_out/r2_sweep13.log 2>&1
-cat gpurun_out/r2_sweep13.log
+run2 MSR3D_P2P_ALLREDUCE=1
+run2 MSR3D_P2P_ALLREDUCE=0
+} > gpurun_out/r2_ddp_sweep2.log 2>&1
+cat gpurun_out/r2_ddp_sweep2.log; grep -i "warn\|error" gpurun_out/r2_ddp_err.log | head -5
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29641 tools/step_timeline.py 2>/dev/null | cut -c1-120 > gpurun_out/r2_step_tl_n2b.log
+grep -n "allreduce\|nccl\|finalize\|adamw\|sumsq\|qpos_bwd\|total" gpurun_out/r2_step_tl_n2b.log | cut -c1-120
