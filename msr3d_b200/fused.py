@@ -319,6 +319,15 @@ class FusedPrompter:
             warnings.warn(f"msr3d_b200: symmetric memory unavailable ({type(e).__name__}: {e}); gradients are exchanged with NCCL")
             return None
 
+    def _comm_waits_for_gradients(self, main):
+        """The early bucket is final once the main chain AND the weight-gradient side streams have got this far: the
+        COMMUNICATION stream waits for them — the main chain does not (joining it here kept layer 0's backward waiting
+        for the weight-gradient GEMMs of layers >= 1: +45 us per step at every N > 1)."""
+        self.comm_stream.wait_stream(main)
+        for k, side in enumerate((self.side_stream, self.side_stream2)):
+            if self._side_pending[k]:
+                self.comm_stream.wait_stream(side)
+
     def _allreduce_p2p(self, channel, begin, end, nblocks, stream):
         rc = _C.lib().msr3d_allreduce_sum_f32(ctypes.byref(self.p2p["desc"][channel]), begin, end, nblocks, stream.cuda_stream)
         if rc != 0:
@@ -824,8 +833,8 @@ class FusedPrompter:
                 # this library's own exchange over NVLink peer memory (csrc/allreduce.cu), norm partials fused in
                 nb0, nb1 = 32, 48
                 if self.ddp_buckets and e1 > e0:
-                    self._run(self.bwd_prog[:self.bwd_split] + [("join", None, (), None, False)])
-                    self.comm_stream.wait_stream(main)
+                    self._run(self.bwd_prog[:self.bwd_split])
+                    self._comm_waits_for_gradients(main)
                     self._allreduce_p2p(0, e0, e1, nb0, self.comm_stream)
                     self._run(self.bwd_prog[self.bwd_split:])
                     self._allreduce_p2p(1, l0, l1, nb1, main)
@@ -837,8 +846,8 @@ class FusedPrompter:
                     self._optimizer_after_p2p(AR_MAX_BLOCKS, 0, split_w)
             else:
                 if self.ddp_buckets and e1 > e0:
-                    self._run(self.bwd_prog[:self.bwd_split] + [("join", None, (), None, False)])
-                    self.comm_stream.wait_stream(main)
+                    self._run(self.bwd_prog[:self.bwd_split])
+                    self._comm_waits_for_gradients(main)
                     with torch.cuda.stream(self.comm_stream):
                         dist.all_reduce(self.flat_g[e0:e1])
                     self._run(self.bwd_prog[self.bwd_split:])
