@@ -15,6 +15,15 @@ eng = FusedPrompter(model); eng.prepare(1, 8, 256, training=True)
 b = synthetic.make_batch(1, 8, 256, seed=3).to("cuda")
 eng.load_inputs(b, torch.randn(1, 8, 256, device="cuda"))
 eng.train_step_eager(); torch.cuda.synchronize(); print("step ok", float(eng.loss()))
+# prefetch schedule, eager (staging launch, geometry beside the encoder, AdamW writing the tf32 weight images)
+from msr3d_b200.train import HotPathTrainer
+m2 = helpers.build_prompter(4, device="cuda"); m2.train()
+tr = HotPathTrainer(m2, 1, 8, 256, use_graph=False, pipeline="prefetch", chain_sms=0)
+up = torch.randn(1, 8, 256, device="cuda")
+tr.warmup(b, up)
+for _ in range(3):
+    tr.step(b, up)
+tr.flush(); torch.cuda.synchronize(); print("prefetch steps ok", float(tr.engine.loss()))
 # scene-token splice: index scan, scattered fp16 epilogue, backward gather + GEMMs
 from msr3d_b200 import splice
 ids = torch.randint(0, 30000, (1, 40), device="cuda"); ids[0, 5:13] = splice.SCENE_SP_TOKEN
