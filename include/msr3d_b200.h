@@ -300,6 +300,10 @@ int msr3d_attn_fwd_f32(const float *qkvc, int ldq, const float *pw, const unsign
 int msr3d_attn_bwd_f32(const float *dctx, int ldc, const float *qkvc, int ldq, const float *pw,
                        const float *P, const float *LOC, int B, int L, int H, float *dqkvc,
                        msr3d_stream_t stream);
+/* Same contract as msr3d_attn_bwd_f32 on the tensor cores (csrc/attn_block.cu: dP, dq, dk, dv as tcgen05 kind::tf32
+ * 3xTF32 products, one CTA per (head, scene)); requires L <= 64, 8 heads, ldq = 816. */
+int msr3d_attn_bwd_tc_f32(const float *dctx, int ldc, const float *qkvc, int ldq, const float *pw, const float *P,
+                          const float *LOC, int B, int L, int H, float *dqkvc, msr3d_stream_t stream);
 /* big = x rounded to tf32 (low 13 mantissa bits zero), small = x - big: the two operand images of the "3xTF32"
  * tensor-core products.  Run once per step over the flat parameter buffer so that no GEMM CTA splits a weight
  * tile again.  n % 4 == 0, 16 B aligned buffers. */

@@ -685,6 +685,268 @@ attn_block_fwd_kernel(const __grid_constant__ AttnBlockFwdParams g) {
   AB_TRACE(tid == 128, 12);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of the attention core on the tensor cores (replaces attn_bwd_kernel for L <= 64; same inputs / outputs:
+// transformers.py:205-248 differentiated).  One CTA per (head, scene):
+//     dP = dctx v^T            dl = P o (dP - rowsum(dP o P))        (softmax backward, thread = query row)
+//     dq = dl k / sqrt(dh)     dk = dl^T q / sqrt(dh)     dv = P^T dctx
+//     d cond[l] = sum_t gz[l,t] [1, pairwise(l,t)],   gz = [loc >= 1e-6] dl sigmoid(-z)        (pair warps, keys over lanes)
+// The CUDA-core kernel needed a cluster of four 16-warp CTAs per (head, scene) — 128 CTAs competing with the
+// weight-gradient GEMMs for the chain's SMs, 20 us alone and 35 us beside them; the four contractions are 84 small MMAs.
+// Operand tiles are written by the row warps straight from global memory (natural and transposed, big / small images).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kBbGn = 0, kBbVn = 16 * 1024;                    // dctx [l][d] (A of dP), v [t][d] (B of dP); later dl [l][t]
+constexpr uint32_t kBbDs = 0;                                       // dl [l][t]: big chunks 0,1 | small chunks 0,1 (A of dq)
+constexpr uint32_t kBbDst = 32 * 1024;                              // dl^T [t][l] (A of dk)
+constexpr uint32_t kBbPt = 64 * 1024;                               // P^T  [t][l] (A of dv)
+constexpr uint32_t kBbQt = 96 * 1024, kBbKt = 112 * 1024, kBbGt = 128 * 1024;   // q^T, k^T, dctx^T [d][64]: B tiles, N = 32
+constexpr uint32_t kBbDl = 144 * 1024;                              // dl as plain fp32 [64][kAbZp] for the pair warps
+constexpr uint32_t kBbCs = kBbDl + 17 * 1024, kBbRed = kBbCs + 2 * 1024;
+constexpr size_t kBbSmem = (size_t)kBbRed + 1024 + 1024;
+constexpr uint32_t kBbTmemCols = 256;
+
+struct alignas(16) AttnCoreBwdParams {
+  const float *dctx;      // [B*L, ldc]
+  const float *qkvc;      // [B*L, 816]
+  const float *pw, *P, *LOC;
+  float *dqkvc;           // [B*L, 816]
+  int ldc, B, L;
+};
+
+// image pair of a 64-row operand tile whose rows are this thread's COLUMN index: element (row j0 + j, k = r), 32 rows
+__device__ __forceinline__ void put_col32(uint32_t big, uint32_t small, int j0, int r, const float (&v)[32]) {
+  const uint32_t cb = (uint32_t)(r >> 5) * 0;   // chunk offset is applied by the caller
+  (void)cb;
+  const int kk = r & 31;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    uint32_t bg, sm;
+    tma::split_tf32(v[j], bg, sm);
+    const uint32_t o = tma::sw128_offset(j0 + j, kk >> 2) + ((uint32_t)(kk & 3) << 2);
+    sts32u(big + o, bg);
+    sts32u(small + o, sm);
+  }
+}
+
+__global__ void __launch_bounds__(kAbThreads, 1)
+attn_core_bwd_tc_kernel(const __grid_constant__ AttnCoreBwdParams g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sb = smem_u32(smem);
+  __shared__ __align__(8) uint64_t in_ready, accp_full, ds_ready, acco_full;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = blockIdx.x, b = blockIdx.y, L = g.L;
+  const int row0 = b * L;
+  if (tid == 0) {
+    mbar_init(&in_ready, 4);
+    mbar_init(&accp_full, 1);
+    mbar_init(&ds_ready, 4);
+    mbar_init(&acco_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&s_tmem, kBbTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t t_dp = s_tmem, t_dq = s_tmem + 64, t_dk = s_tmem + 96, t_dv = s_tmem + 128;
+  pdl_sync();
+  const bool row_warp = warp >= 4 && (warp & 3) < 2;
+  const int qd = warp & 3, half = (warp - 4) >> 2;
+  const int r = qd * 32 + lane;
+  const float scale = rsqrtf((float)kAbDh);
+
+  if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    mbar_wait(&in_ready, 0);
+    fence_after_sync();
+    if (elect_one()) {
+      const uint32_t idesc = tma::make_idesc_tf32(128, 64, false, false);
+      const uint64_t ab = tma::desc_kmajor(sb + kBbGn), as = tma::desc_kmajor(sb + kBbGn + 8192);
+      const uint64_t bb = tma::desc_kmajor(sb + kBbVn), bs = tma::desc_kmajor(sb + kBbVn + 8192);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) tma::mma_3x(t_dp, ab + ks * 2, as + ks * 2, bb + ks * 2, bs + ks * 2, idesc, ks ? 1u : 0u);
+      mma_commit(&accp_full);
+    }
+    __syncwarp();
+    mbar_wait(&ds_ready, 0);
+    fence_after_sync();
+    if (elect_one()) {
+      const uint32_t idesc = tma::make_idesc_tf32(128, kAbDh, false, false);
+      // A tiles: [big chunk 0 | big chunk 1 | small chunk 0 | small chunk 1], 8 KB each; B tiles: the same with 4 KB chunks
+      const uint32_t a_of[3] = {kBbDs, kBbDst, kBbPt}, b_of[3] = {kBbKt, kBbQt, kBbGt};
+      const uint32_t acc[3] = {t_dq, t_dk, t_dv};
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint64_t ab = tma::desc_kmajor(sb + a_of[m] + c * 8192), as = tma::desc_kmajor(sb + a_of[m] + 16384 + c * 8192);
+          const uint64_t bb = tma::desc_kmajor(sb + b_of[m] + c * 4096), bs = tma::desc_kmajor(sb + b_of[m] + 8192 + c * 4096);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) tma::mma_3x(acc[m], ab + ks * 2, as + ks * 2, bb + ks * 2, bs + ks * 2, idesc, (c | ks) ? 1u : 0u);
+        }
+      }
+      mma_commit(&acco_full);
+    }
+    __syncwarp();
+  } else if (row_warp) {
+    // ------------------------------------------------------------------ row warps: thread = row r (query or key)
+    const bool row_ok = r < L;
+    const float *qrow = g.qkvc + (size_t)(row0 + r) * kAbQkvc;
+    const int nk = max(0, min(32, L - half * 32));
+    // P row of this thread's half (needed after dP): requested first
+    float pr[32];
+    {
+      const float *prow = g.P + (((size_t)b * kAbHeads + h) * L + r) * L + half * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pr[j] = (row_ok && j < nk) ? prow[j] : 0.f;
+    }
+    {
+      // operand tiles of the four contractions: half 0 -> q^T, k^T;  half 1 -> v, dctx, dctx^T, cond
+      float a[32], c[32];
+      const float *p0 = half == 0 ? qrow + h * kAbDh : qrow + 2 * kD + h * kAbDh;                       // q | v
+      const float *p1 = half == 0 ? qrow + kD + h * kAbDh : g.dctx + (size_t)(row0 + r) * g.ldc + h * kAbDh;   // k | dctx
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 u = row_ok ? *reinterpret_cast<const float4 *>(p0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 w = row_ok ? *reinterpret_cast<const float4 *>(p1 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        a[j] = u.x; a[j + 1] = u.y; a[j + 2] = u.z; a[j + 3] = u.w;
+        c[j] = w.x; c[j + 1] = w.y; c[j + 2] = w.z; c[j + 3] = w.w;
+      }
+      const uint32_t ch = (uint32_t)(r >> 5) * 4096;
+      if (half == 0) {
+        put_col32(sb + kBbQt + ch, sb + kBbQt + 8192 + ch, 0, r, a);
+        put_col32(sb + kBbKt + ch, sb + kBbKt + 8192 + ch, 0, r, c);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          put4(sb + kBbVn, sb + kBbVn + 8192, r, j, a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+          put4(sb + kBbGn, sb + kBbGn + 8192, r, j, c[4 * j], c[4 * j + 1], c[4 * j + 2], c[4 * j + 3]);
+        }
+        put_col32(sb + kBbGt + ch, sb + kBbGt + 8192 + ch, 0, r, c);
+#pragma unroll
+        for (int j = 0; j < kAbCond; ++j) sts32(sb + kBbCs + (uint32_t)(r * 8 + j) * 4u, row_ok ? qrow[3 * kD + h * kAbCond + j] : 0.f);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&in_ready);
+    }
+    {
+      // ---- softmax backward on this thread's row: dl = P o (dP - sum_t dP P)
+      mbar_wait(&accp_full, 0);
+      fence_after_sync();
+      uint32_t acc[32];
+      tmem_ld32(t_dp + ((uint32_t)(qd * 32) << 16) + (uint32_t)(half * 32), acc);
+      tmem_ld_wait();
+      float part = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) part += __uint_as_float(acc[j]) * pr[j];
+      sts32(sb + kBbRed + (uint32_t)(half * 64 + r) * 4u, part);
+      tma::named_barrier(2, kAbRowThreads);
+      const float rowdot = lds32(sb + kBbRed + (uint32_t)r * 4u) + lds32(sb + kBbRed + (uint32_t)(64 + r) * 4u);
+      float dl[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dl[j] = pr[j] * (__uint_as_float(acc[j]) - rowdot);    // 0 where P = 0 (padded / out of range)
+      // dl [l][t]: A of dq (aliases the dP operands: every row warp is past accp_full, i.e. the dP MMAs are complete)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        put4(sb + kBbDs + half * 8192, sb + kBbDs + 16384 + half * 8192, r, j, dl[4 * j], dl[4 * j + 1], dl[4 * j + 2], dl[4 * j + 3]);
+      // dl^T and P^T [t][l]: A of dk / dv; rows t = half * 32 + j, column l = r (chunk r / 32)
+      const uint32_t chk = (uint32_t)(r >> 5) * 8192;
+      put_col32(sb + kBbDst + chk, sb + kBbDst + 16384 + chk, half * 32, r, dl);
+      put_col32(sb + kBbPt + chk, sb + kBbPt + 16384 + chk, half * 32, r, pr);
+      // plain copy for the pair warps
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sts32(sb + kBbDl + (uint32_t)(r * kAbZp + half * 32 + j) * 4u, dl[j]);
+      fence_before_sync();
+      fence_async_smem();
+      tma::named_barrier(5, kAbRowThreads + 7 * 32);      // dl table complete: the pair warps may start
+      if (lane == 0) mbar_arrive(&ds_ready);
+    }
+    {
+      // ---- dq (row = query), dk, dv (row = key): 16 dims per thread
+      mbar_wait(&acco_full, 0);
+      fence_after_sync();
+      uint32_t aq[16], ak[16], av[16];
+      ab_tmem_ld16(t_dq + ((uint32_t)(qd * 32) << 16) + (uint32_t)(half * 16), aq);
+      ab_tmem_ld16(t_dk + ((uint32_t)(qd * 32) << 16) + (uint32_t)(half * 16), ak);
+      ab_tmem_ld16(t_dv + ((uint32_t)(qd * 32) << 16) + (uint32_t)(half * 16), av);
+      tmem_ld_wait();
+      if (row_ok) {
+        float *o = g.dqkvc + (size_t)(row0 + r) * kAbQkvc + h * kAbDh + half * 16;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          *reinterpret_cast<float4 *>(o + j) = make_float4(__uint_as_float(aq[j]) * scale, __uint_as_float(aq[j + 1]) * scale,
+                                                           __uint_as_float(aq[j + 2]) * scale, __uint_as_float(aq[j + 3]) * scale);
+          *reinterpret_cast<float4 *>(o + kD + j) = make_float4(__uint_as_float(ak[j]) * scale, __uint_as_float(ak[j + 1]) * scale,
+                                                                __uint_as_float(ak[j + 2]) * scale, __uint_as_float(ak[j + 3]) * scale);
+          *reinterpret_cast<float4 *>(o + 2 * kD + j) = make_float4(__uint_as_float(av[j]), __uint_as_float(av[j + 1]),
+                                                                    __uint_as_float(av[j + 2]), __uint_as_float(av[j + 3]));
+        }
+      }
+      fence_before_sync();
+    }
+  } else {
+    // ------------------------------------------------------------------ pair warps (0, 2, 3, 6, 7, 10, 11): d cond
+    const int pwi = warp == 0 ? 0 : (warp < 4 ? warp - 1 : (warp < 8 ? warp - 3 : warp - 5));     // 0..6
+    const int t0 = lane, t1 = lane + 32;
+    const bool ok0 = t0 < L, ok1 = t1 < L;
+    const float *pws = g.pw + (size_t)b * L * L * 5;
+    const float *locs = g.LOC + ((size_t)b * kAbHeads + h) * L * L;
+    float ga[5], gb[5], la = 0.f, lb = 0.f;
+    auto load_row = [&](int l) {
+      const float *pr5 = pws + (size_t)l * L * 5;
+#pragma unroll
+      for (int d = 0; d < 5; ++d) {
+        ga[d] = ok0 ? pr5[t0 * 5 + d] : 0.f;
+        gb[d] = ok1 ? pr5[t1 * 5 + d] : 0.f;
+      }
+      la = ok0 ? locs[(size_t)l * L + t0] : 0.f;
+      lb = ok1 ? locs[(size_t)l * L + t1] : 0.f;
+    };
+    if (pwi < L) load_row(pwi);
+    tma::named_barrier(5, kAbRowThreads + 7 * 32);
+#pragma unroll 1
+    for (int l = pwi; l < L; l += 7) {
+      float fa[5], fb[5];
+#pragma unroll
+      for (int d = 0; d < 5; ++d) { fa[d] = ga[d]; fb[d] = gb[d]; }
+      const float lca = la, lcb = lb;
+      if (l + 7 < L) load_row(l + 7);
+      const float4 sw = lds128(sb + kBbCs + (uint32_t)l * 32u);
+      const float sw4 = lds32(sb + kBbCs + (uint32_t)l * 32u + 16u), sw5 = lds32(sb + kBbCs + (uint32_t)l * 32u + 20u);
+      const float dla = lds32(sb + kBbDl + (uint32_t)(l * kAbZp + t0) * 4u), dlb = lds32(sb + kBbDl + (uint32_t)(l * kAbZp + t1) * 4u);
+      float za = sw.x, zb = sw.x;
+      za = fmaf(sw.y, fa[0], za); zb = fmaf(sw.y, fb[0], zb);
+      za = fmaf(sw.z, fa[1], za); zb = fmaf(sw.z, fb[1], zb);
+      za = fmaf(sw.w, fa[2], za); zb = fmaf(sw.w, fb[2], zb);
+      za = fmaf(sw4, fa[3], za);  zb = fmaf(sw4, fb[3], zb);
+      za = fmaf(sw5, fa[4], za);  zb = fmaf(sw5, fb[4], zb);
+      // d/dz log(clamp(sigmoid(z), 1e-6)) = [loc >= 1e-6] sigmoid(-z)
+      const float gza = (ok0 && lca >= 1e-6f) ? dla / (1.f + __expf(za)) : 0.f;
+      const float gzb = (ok1 && lcb >= 1e-6f) ? dlb / (1.f + __expf(zb)) : 0.f;
+      float acc6[6];
+      acc6[0] = gza + gzb;
+#pragma unroll
+      for (int d = 0; d < 5; ++d) acc6[1 + d] = gza * fa[d] + gzb * fb[d];
+#pragma unroll
+      for (int d = 0; d < 6; ++d) acc6[d] = warp_sum(acc6[d]);
+      if (lane < kAbCond) {
+        float v = acc6[0];
+#pragma unroll
+        for (int d = 1; d < 6; ++d) v = lane == d ? acc6[d] : v;
+        g.dqkvc[(size_t)(row0 + l) * kAbQkvc + 3 * kD + h * kAbCond + lane] = v;
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    fence_after_sync();
+    tmem_dealloc(s_tmem, kBbTmemCols);
+  }
+}
+
 // big = x rounded to tf32, small = x - big: the operand images of the 3xTF32 products (tma.cuh), written once
 // per step for the whole flat parameter buffer so that no GEMM CTA has to split a weight tile again.
 __global__ void __launch_bounds__(256)
@@ -799,4 +1061,23 @@ MSR3D_API int msr3d_attn_block_fwd_ps_f32(const float *x, const float *wqkvc_big
   return attn_block_fwd_impl(x, wqkvc_big, wqkvc_small, bqkvc, wo_big, wo_small, bo, pw, key_pad, B, L, gamma_a, beta_a, gamma_1,
                              beta_1, seed, seed_ptr, p, site_fc, site_1, qkvc, P, LOC, ctx, xhat_a, rstd_a, xhat_1, rstd_1, y2,
                              y2_big, y2_small, stream);
+}
+
+MSR3D_API int msr3d_attn_bwd_tc_f32(const float *dctx, int ldc, const float *qkvc, int ldq, const float *pw, const float *P,
+                                    const float *LOC, int B, int L, int H, float *dqkvc, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(dctx && qkvc && pw && P && LOC && dqkvc, "attn_bwd_tc: null pointer");
+  MSR3D_REQUIRE(L >= 1 && L <= kAbRT && H == kAbHeads && ldq == kAbQkvc && (ldc & 3) == 0, "attn_bwd_tc: needs L <= 64, 8 heads, ldq = 816");
+  MSR3D_REQUIRE(((reinterpret_cast<uintptr_t>(dctx) | reinterpret_cast<uintptr_t>(qkvc) | reinterpret_cast<uintptr_t>(dqkvc)) & 15) == 0,
+                "attn_bwd_tc: 16 B alignment");
+  if (B <= 0) return MSR3D_OK;
+  AttnCoreBwdParams g{};
+  g.dctx = dctx; g.qkvc = qkvc; g.pw = pw; g.P = P; g.LOC = LOC; g.dqkvc = dqkvc;
+  g.ldc = ldc; g.B = B; g.L = L;
+  static bool configured = false;
+  if (!configured) {
+    MSR3D_CUDA(cudaFuncSetAttribute(attn_core_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBbSmem));
+    configured = true;
+  }
+  launch_pdl(attn_core_bwd_tc_kernel, dim3(kAbHeads, B), dim3(kAbThreads), kBbSmem, (cudaStream_t)stream, g);
+  return check_launch("attn_bwd_tc");
 }

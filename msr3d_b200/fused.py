@@ -75,6 +75,7 @@ _C.register_protos({
     "msr3d_qpos_bwd_f32": [c_vp, c_vp, c_vp, c_vp, c_int] + [c_vp] * 14 + [c_vp],
     "msr3d_attn_fwd_f32": [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp],
     "msr3d_attn_bwd_f32": [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp],
+    "msr3d_attn_bwd_tc_f32": [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp],
     "msr3d_attn_tail_fwd_f32": [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_ull, c_vp, c_float, c_uint, c_uint,
                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_attn_tail_bwd_f32": [c_vp, c_int, c_vp, c_vp, c_ull, c_vp, c_float, c_uint, c_uint,
@@ -105,6 +106,11 @@ _C.register_protos({
     "msr3d_attn_block_fwd_f32": [c_vp] * 9 + [c_int, c_int] + [c_vp] * 4 + [c_ull, c_vp, c_float, c_uint, c_uint]
                                 + [c_vp] * 9 + [c_vp],
 })
+
+def _os_env(name, default):
+    import os
+    return os.environ.get(name, default)
+
 
 H = 256          # hidden size the fused kernels are built for
 NHEAD = 8
@@ -650,8 +656,11 @@ class FusedPrompter:
                        accumulate=2, ksplit=4, tag="dWo", wgrad=True, side=True)
             self._gemm(bwd, do_, (H, 1), P(sa + "fc.weight"), (1, H), M, H, H, ptr(w["dctx"][i]), H,
                        accumulate=2, ksplit=ks_h, tag="dctx")
-            self._call(bwd, "msr3d_attn_bwd_f32", ptr(w["dctx"][i]), H, ptr(w["qkvc"][i]), QKVC, ptr(w["pw"]),
-                       ptr(w["P"][i]), ptr(w["LOC"][i]), B, L, NHEAD, dqkvc, tag="attn_core_bwd")
+            # attention backward: tensor-core kernel (one CTA per head and scene, csrc/attn_block.cu) when L <= 64
+            bwd_tc = self.attn_block_active and _os_env("MSR3D_ATTN_BWD_TC", "1") == "1"
+            self._call(bwd, "msr3d_attn_bwd_tc_f32" if bwd_tc else "msr3d_attn_bwd_f32", ptr(w["dctx"][i]), H,
+                       ptr(w["qkvc"][i]), QKVC, ptr(w["pw"]), ptr(w["P"][i]), ptr(w["LOC"][i]), B, L, NHEAD, dqkvc,
+                       tag="attn_core_bwd")
             # dWqkvc (816 x H) += dqkvc^T . x_in ; bias [side] ; dx += dqkvc . Wqkvc
             self._gemm(bwd, dqkvc, (1, QKVC), ptr(w["x_in"][i]), (1, H), QKVC, H, M, G(sa + "w_qs.weight"), H,
                        accumulate=2, ksplit=4, tag="dWqkvc", wgrad=True, side=2)

@@ -84,3 +84,34 @@ def test_attn_block_deterministic():
     torch.cuda.synchronize()
     for k in SAVED:
         assert torch.equal(a[k], eng.ws[k][0]), k
+
+
+@pytest.mark.parametrize("B,O,P,seed", [(1, 8, 256, 21), (4, 60, 256, 22), (2, 64, 256, 23), (3, 33, 256, 24)])
+def test_attention_backward_on_tensor_cores_equals_cuda_core_kernel(B, O, P, seed):
+    """msr3d_attn_bwd_tc_f32 against msr3d_attn_bwd_f32 on the tensors of a real backward pass (same contract)."""
+    from msr3d_b200 import _C
+    batch = synthetic.make_batch(B, O, P, seed=seed)
+    if B > 1:
+        batch.obj_masks[-1, O - max(1, O // 5):] = False
+    up = torch.randn(B, O, 256, generator=torch.Generator().manual_seed(seed + 1))
+    model, eng = _engine(seed, B, O, P, True, True)
+    eng.load_inputs(batch.to("cuda"), up.cuda())
+    eng.flat_g.zero_()
+    eng.forward()
+    eng.backward()
+    torch.cuda.synchronize()
+    w = eng.ws
+    st = torch.cuda.current_stream().cuda_stream
+    for i in range(eng.nl):
+        outs = []
+        for fn in ("msr3d_attn_bwd_f32", "msr3d_attn_bwd_tc_f32"):
+            o = torch.full_like(w["dqkvc"][i], float("nan"))
+            _C.call(fn, w["dctx"][i].data_ptr(), 256, w["qkvc"][i].data_ptr(), 816, w["pw"].data_ptr(), w["P"][i].data_ptr(),
+                    w["LOC"][i].data_ptr(), B, O, 8, o.data_ptr(), st)
+            torch.cuda.synchronize()
+            outs.append(o)
+        ref, got = outs
+        assert torch.isfinite(got).all(), i                      # every column written
+        for name, sl in (("dq", slice(0, 256)), ("dk", slice(256, 512)), ("dv", slice(512, 768)), ("dcond", slice(768, 816))):
+            e = helpers.rel_err(got[:, sl], ref[:, sl])
+            assert e < 2e-4, (i, name, e)
