@@ -412,12 +412,22 @@ def secondary_configs(args, dev, world, flush):
     from msr3d_b200 import synthetic
     from msr3d_b200.train import HotPathTrainer
     out = {}
-    for name in ("cfg4_80x2048", "cfg5_msnn_60x1024"):
-        B, O, P = synthetic.CONFIGS[name]
+    for name in ("cfg4_80x2048", "cfg5_msnn_60x1024", "cfg2_60x1024+all_trainable_13.67M"):
+        B, O, P = synthetic.CONFIGS[name.split("+")[0]]
         model = msr3d_b200.build_model(prompter_cfg())
         model.load_state_dict(synthetic.make_state_dict(load_spec(), 0), strict=True)
         model = model.to(dev).train()
-        tr = HotPathTrainer(model, B, O, P, world_size=1, split=args.split, pipeline="prefetch", chain_sms=args.chain_sms)
+        extra = None
+        if "+" in name:
+            # SURVEY.md 8e / BASELINE config 3: the reference's single gradient exchange + clip + AdamW covers the prompter AND
+            # llm_proj (1 052 672), llm_proj_img (4 198 400), clip_proj (4 198 400): attached to the engine's flat buffers
+            # (their forward / backward belong to the LLM side: zero gradients here, the exchange / optimiser cost is real)
+            g = torch.Generator().manual_seed(11)
+            shapes = {"llm_proj.weight": (4096, 256), "llm_proj.bias": (4096,), "llm_proj_img.weight": (4096, 1024),
+                      "llm_proj_img.bias": (4096,), "clip_proj.weight": (4096, 1024), "clip_proj.bias": (4096,)}
+            extra = {k: torch.nn.Parameter((torch.randn(*v, generator=g) * 0.02).to(dev)) for k, v in shapes.items()}
+        tr = HotPathTrainer(model, B, O, P, world_size=1, split=args.split, pipeline="prefetch", chain_sms=args.chain_sms,
+                            extra_params=extra)
         devb = [synthetic.make_batch(B, O, P, seed=3000 + 17 * i).to(dev) for i in range(4)]
         up = torch.randn(B, O, 256, generator=torch.Generator().manual_seed(1)).to(dev)
         tr.warmup(devb[0], up)
@@ -437,6 +447,7 @@ def secondary_configs(args, dev, world, flush):
         flops = sum(w["flops"] for _, w in work if "flops" in w)
         peaks = roofline.measured_peaks()
         out[name] = {"value": B / (t * 1e-3), "unit": UNIT, "ms_per_step": t, "batch_per_gpu": B, "objects": O, "points": P,
+                     "optimised_parameters": int(tr.engine.n_opt),
                      "attn_block_kernel": bool(getattr(tr.engine, "attn_block_active", False)),
                      "step_frac_tensor": flops / (t * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]}
         del tr, model

@@ -47,6 +47,8 @@ def flat_order(names: Sequence[str], num_layers: int) -> Tuple[List[str], List[s
 def is_late(name: str) -> bool:
     """Parameters whose gradient is complete only at the very end of the backward pass: layer 0 of the
     spatial encoder and everything in front of it (projection, location / size encoders, embeddings)."""
+    if name.startswith("ext."):     # parameters of the caller attached to the flat buffer (llm_proj, ...): their
+        return False                # gradients come out of the LLM's backward, before the prompter's begins
     return (not name.startswith("spatial_encoder.")) or name.startswith("spatial_encoder.0.")
 
 

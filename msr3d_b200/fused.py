@@ -149,7 +149,8 @@ class FusedPrompter:
     def __init__(self, model, lr=3e-5, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
                  grad_norm: Optional[float] = 5.0, world_size: int = 1, split: int = 3,
                  grad_split: int = 6, gemm_impl: Optional[str] = None, no_decay_bias: bool = False,
-                 alias_grads: bool = True, chain_sms: Optional[int] = None):
+                 alias_grads: bool = True, chain_sms: Optional[int] = None,
+                 extra_params: Optional[Dict[str, torch.nn.Parameter]] = None):
         # NOTE: weight-gradient GEMMs and bias reductions are issued on a side stream (see _run)
         why = supported(model)
         if why is not None:
@@ -162,6 +163,13 @@ class FusedPrompter:
         # the fused optimiser and the all-reduce work on it).  False = module / autograd mode (autograd.py):
         # p.grad belongs to autograd, the flat buffer is scratch of one backward.
         self.alias_grads = bool(alias_grads)
+        # extra_params: trainable parameters of the CALLER (llm_proj, llm_proj_img, clip_proj: model/msr3d/msr3d.py:84-130)
+        # re-homed into the same flat buffers, so that the reference's ONE gradient exchange, ONE global-norm clip and
+        # ONE AdamW over all trainable parameters (13.67 M elements) are this engine's single flat
+        # operations.  Their forward / backward stay the caller's (torch autograd accumulates into p.grad, which is a
+        # view of the flat gradient buffer); they sit in the early bucket (final before the prompter's backward).
+        self.extra_params = dict(extra_params or {})
+        assert alias_grads or not self.extra_params, "extra_params need alias_grads=True"
         # transformer GEMMs: "tf32x3" = TMA-fed tcgen05 kind::tf32 big/small pairs (csrc/gemm3x.cu, default),
         # "bf16" = round-1 register-path split-bf16 kernel (csrc/linear_tc.cu; `split` / `grad_split` apply)
         import os as _os0
@@ -248,6 +256,8 @@ class FusedPrompter:
     def _rehome(self):
         from . import dist as _dist
         named = [(n, p) for n, p in self.model.named_parameters() if p.requires_grad]
+        n_model = len(named)
+        named += [("ext." + k, p) for k, p in self.extra_params.items() if p.requires_grad]
         by_name = dict(named)
         lay = _dist.flat_layout([n for n, _ in named], {n: p.numel() for n, p in named}, self.nl,
                                 no_decay_bias=self.no_decay_bias)
@@ -276,7 +286,7 @@ class FusedPrompter:
             if self.alias_grads:
                 p.grad = self.flat_g[offs[n]:offs[n] + p.numel()].view_as(p)
         self.by_name = by_name
-        self.autograd_names = [n for n, _ in named]
+        self.autograd_names = [n for n, _ in named[:n_model]]
         self.n_trainable = sum(p.numel() for _, p in named)
         if self.world_size > 1:
             _dist.broadcast_(self.flat_p)     # identical replicas, as DDP's constructor guarantees

@@ -156,3 +156,21 @@ def test_flat_layout_buckets_and_decay_range(sd_spec):
     for i in range(3):
         pre = f"spatial_encoder.{i}.self_attn."
         assert offs[pre + "lang_cond_fc.weight"] + numel[pre + "lang_cond_fc.weight"] - offs[pre + "w_qs.weight"] == 816 * 256
+
+
+def test_flat_layout_with_attached_caller_parameters(sd_spec):
+    """llm_proj / llm_proj_img / clip_proj join the prompter in ONE flat buffer (13.67 M elements): they land in
+    the early bucket (their gradients exist before the prompter's backward starts) and inside the decayed range."""
+    names = [n for n, shape, _ in sd_spec if not n.startswith("obj_encoder.") and n != "anchor_size"]
+    numel = {n: int(__import__("math").prod(shape)) for n, shape, _ in sd_spec}
+    extra = {"ext.llm_proj.weight": 4096 * 256, "ext.llm_proj.bias": 4096, "ext.llm_proj_img.weight": 4096 * 1024,
+             "ext.llm_proj_img.bias": 4096, "ext.clip_proj.weight": 4096 * 1024, "ext.clip_proj.bias": 4096}
+    numel.update(extra)
+    lay = mdist.flat_layout(names + list(extra), numel, 3)
+    (e0, e1), (l0, l1) = lay["early"], lay["late"]
+    for n in extra:
+        assert e0 <= lay["offs"][n] < e1, n
+        assert lay["decay"][0] <= lay["offs"][n] < lay["decay"][1]
+    # 4 224 144 trainable prompter parameters, 24 320 of them never used in the shipped mode (outside n_opt), + 9 449 472
+    assert lay["total"] == 13_673_616 and lay["n_opt"] == 13_673_616 - 24_320
+    assert l1 == e0 and l0 == 0

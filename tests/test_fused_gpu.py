@@ -264,3 +264,35 @@ def test_pipelined_schedule_equals_sequential(sd_spec):
     assert helpers.rel_err(res["pipelined_graph"][0], res["sequential"][0]) < 5e-4
     assert helpers.rel_err(res["prefetch"][0], res["sequential"][0]) < 5e-4
     assert helpers.rel_err(res["prefetch_graph"][0], res["sequential"][0]) < 5e-4
+
+
+def test_attached_caller_parameters_share_exchange_clip_and_adamw():
+    """parameters of the caller (llm_proj ...) re-homed into the engine's flat buffers get the SAME global-norm
+    clip coefficient and the same AdamW as the prompter's (the reference clips over all model parameters and uses one
+    optimiser, trainer/leo_trainer.py:192-195): checked against torch.optim.AdamW fed the clipped gradient."""
+    from msr3d_b200.fused import FusedPrompter
+    seed, B, O, P = 9, 2, 12, 256
+    model = helpers.build_prompter(seed, device="cuda")
+    ext = torch.nn.Parameter(torch.randn(64, 256, device="cuda") * 0.05)
+    ref = torch.nn.Parameter(ext.detach().clone())
+    eng = FusedPrompter(model, lr=1e-3, weight_decay=0.05, grad_norm=5.0, extra_params={"llm_proj.weight": ext})
+    assert ext.data_ptr() == eng.P("ext.llm_proj.weight") and ext.grad.data_ptr() == eng.G("ext.llm_proj.weight")
+    e0, e1 = eng.bucket_early
+    assert e0 <= eng.offs["ext.llm_proj.weight"] < e1
+    eng.prepare(B, O, P, training=False)
+    batch = synthetic.make_batch(B, O, P, seed=seed)
+    up = torch.randn(B, O, 256, generator=torch.Generator().manual_seed(3)) * 50.0     # large: the clip is active
+    eng.load_inputs(batch.to("cuda"), up.cuda())
+    eng.flat_g.zero_()
+    eng.forward()
+    eng.backward()
+    gext = torch.randn_like(ext)
+    ext.grad.add_(gext)                       # what the caller's autograd would accumulate
+    total = float(eng.flat_g[:eng.n_opt].double().norm())
+    eng.optimizer_step()
+    coef = float(eng.clip_coef())
+    assert coef < 1.0 and abs(coef - 5.0 / (total + 1e-6)) < 1e-4 * coef
+    opt = torch.optim.AdamW([ref], lr=1e-3, weight_decay=0.05)
+    ref.grad = gext * coef
+    opt.step()
+    assert helpers.rel_err(ext.detach(), ref.detach()) < 2e-6
