@@ -393,7 +393,19 @@ int msr3d_adamw_clip_step_split_f32(float *params, const float *grads, float *ex
  * kernel alone; big / small (nullable) as in msr3d_adamw_clip_step_split_f32. */
 int msr3d_adamw_apply_f32(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, long long n,
                           long long decay_begin, long long decay_end, float grad_scale, float *state, float *big,
-                          float *small, msr3d_stream_t stream);
+                          float *small, const int *gate, msr3d_stream_t stream);
+/* Gradient accumulation inside a replayable step (configs/msr3d.yaml:33 gradient_accumulation_steps,
+ * trainer/leo_trainer.py:66,211): state = int32 {micro, k, clear_now, sync_now} on the device.  msr3d_accum_tick with
+ * phase 0 (start of a micro-step) sets clear_now = (micro == 0) and sync_now = (micro == k - 1); with phase 1 (end)
+ * it advances micro modulo k and increments *seed_counter (fresh dropout masks per micro-step).  Kernels that take
+ * `gate` (nullable: always run) return at once when *gate == 0: the gradient clear is gated by &state[2]; the
+ * exchange, the norm and the update by &state[3]. */
+int msr3d_accum_tick(int *state, unsigned long long *seed_counter, int phase, msr3d_stream_t stream);
+int msr3d_zero_gated_f32(float *p, long long n, const int *gate, msr3d_stream_t stream);
+int msr3d_adamw_clip_step_gated_f32(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, long long n,
+                                    long long decay_begin, long long decay_end, float grad_scale, float *state,
+                                    unsigned int *ticket, const float *extra_sumsq, float *big, float *small,
+                                    const int *gate, msr3d_stream_t stream);
 /* Data-parallel gradient exchange over NVLink peer memory (csrc/allreduce.cu; replaces the NCCL all-reduce behind DDP,
  * trainer/leo_trainer.py:50-52,135).  buf[q] / flags[q] / partials[q]: rank q's copy of three SYMMETRIC allocations as
  * mapped into this process (torch.distributed._symmetric_memory): the flat gradient buffer, 2 * MSR3D_AR_MAX_BLOCKS *
@@ -411,13 +423,14 @@ typedef struct msr3d_allreduce_desc {
   unsigned *flags[MSR3D_AR_MAX_WORLD];
   float *partials[MSR3D_AR_MAX_WORLD];
   unsigned *epoch;
+  const int *gate;          /* nullable; *gate == 0: the launch does nothing (gradient accumulation) */
   int rank, world, channel;
 } msr3d_allreduce_desc;
 int msr3d_allreduce_sum_f32(const msr3d_allreduce_desc *d, long long begin, long long end, int nblocks,
                             msr3d_stream_t stream);
 int msr3d_grad_norm_finalize_f32(const float *partials, int world, int nblocks0, int nblocks1, float grad_scale,
                                  const float *extra_sumsq, float *state, unsigned long long *seed_counter,
-                                 msr3d_stream_t stream);
+                                 const int *gate, msr3d_stream_t stream);
 /* Input staging of a pipelined step in one launch (csrc/stage.cu): rotate k: a[i] <- b[i]; b[i] <- c[i] (c nullable)
  * over rot_n[k] floats; copy k: dst[i] <- src[i]; masks (bytes): the same rotation and key_pad[i] <- !a[i]. */
 #define MSR3D_STAGE_MAX 8

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(kArThreads)
 allreduce_p2p_kernel(const __grid_constant__ ArParams p) {
   pdl_sync();
   const msr3d_allreduce_desc &d = p.d;
+  if (d.gate != nullptr && *d.gate == 0) return;   // gradient accumulation: every rank skips the same micro-steps
   const int W = d.world, r = d.rank, b = blockIdx.x, nb = gridDim.x, tid = threadIdx.x;
   __shared__ unsigned s_epoch;
   __shared__ float s_red[kArThreads / 32];
@@ -133,8 +134,10 @@ struct OptStateHead { float sumsq, step; };
 // what sumsq_kernel's last block does on the single-GPU path).  grad_scale: the 1/world factor of the mean.
 __global__ void __launch_bounds__(256)
 grad_norm_finalize_kernel(const float *__restrict__ partials, int world, int nb0, int nb1, float grad_scale,
-                          const float *__restrict__ extra_sumsq, float *state, unsigned long long *seed_counter) {
+                          const float *__restrict__ extra_sumsq, float *state, unsigned long long *seed_counter,
+                          const int *__restrict__ gate) {
   pdl_sync();
+  if (gate != nullptr && *gate == 0) return;
   __shared__ float w[8];
   float t = 0.f;
   const int nbs[2] = {nb0, nb1};
@@ -183,10 +186,10 @@ MSR3D_API int msr3d_allreduce_sum_f32(const msr3d_allreduce_desc *d, long long b
 
 MSR3D_API int msr3d_grad_norm_finalize_f32(const float *partials, int world, int nblocks0, int nblocks1, float grad_scale,
                                            const float *extra_sumsq, float *state, unsigned long long *seed_counter,
-                                           msr3d_stream_t stream) {
+                                           const int *gate, msr3d_stream_t stream) {
   MSR3D_REQUIRE(partials && state && world >= 1 && world <= kArMaxWorld && nblocks0 >= 0 && nblocks0 <= kArMaxBlocks &&
                     nblocks1 >= 0 && nblocks1 <= kArMaxBlocks, "grad_norm_finalize: bad arguments");
   launch_pdl(grad_norm_finalize_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, partials, world, nblocks0, nblocks1, grad_scale,
-             extra_sumsq, state, seed_counter);
+             extra_sumsq, state, seed_counter, gate);
   return check_launch("grad_norm_finalize");
 }

@@ -18,8 +18,10 @@ struct OptState {   // device-resident: 8 floats + one partial sum per block of 
 
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float *__restrict__ g, long long n, float grad_scale, OptState *st,
-             unsigned int *ticket, unsigned long long *seed_counter, const float *__restrict__ extra_sumsq) {
+             unsigned int *ticket, unsigned long long *seed_counter, const float *__restrict__ extra_sumsq,
+             const int *__restrict__ gate) {
   pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
+  if (gate != nullptr && *gate == 0) return;   // gradient accumulation: not a synchronisation step (uniform over the grid)
   float s = 0.f;
   const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
   if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {   // 16 B loads; the tail (n % 4) goes to the scalar loop below
@@ -88,8 +90,9 @@ sumsq_kernel(const float *__restrict__ g, long long n, float grad_scale, OptStat
 __global__ void __launch_bounds__(256)
 adamw_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
              float *__restrict__ v, long long n, long long decay_begin, long long decay_end, float grad_scale,
-             OptState *st, int zero_grads, float *__restrict__ big, float *__restrict__ small) {
+             OptState *st, int zero_grads, float *__restrict__ big, float *__restrict__ small, const int *__restrict__ gate) {
   pdl_sync();  // PDL: wait for the producer grid, then let the consumer grid start scheduling
+  if (gate != nullptr && *gate == 0) return;
   const float norm = sqrtf(st->sumsq);
   const float clip = st->max_norm > 0.f ? fminf(1.f, st->max_norm / (norm + 1e-6f)) : 1.f;
   const float gs = grad_scale * clip;
@@ -160,7 +163,7 @@ using namespace msr3d;
 static int adamw_impl(float *params, float *grads, float *exp_avg, float *exp_avg_sq, long long n, long long decay_begin,
                       long long decay_end, float grad_scale, float *state, unsigned int *ticket,
                       unsigned long long *seed_counter, const float *extra_sumsq, int zero_grads, float *big, float *small,
-                      msr3d_stream_t stream) {
+                      msr3d_stream_t stream, const int *gate = nullptr) {
   MSR3D_REQUIRE(params && grads && exp_avg && exp_avg_sq && state && ticket, "adamw: null pointer");
   MSR3D_REQUIRE(n >= 0 && decay_begin >= 0 && decay_begin <= decay_end && decay_end <= n, "adamw: bad sizes");
   if (n == 0) return MSR3D_OK;
@@ -169,11 +172,11 @@ static int adamw_impl(float *params, float *grads, float *exp_avg, float *exp_av
   int grid = (int)((n + 255) / 256);
   if (grid > kSumsqBlocks) grid = kSumsqBlocks;
   int rc;
-  launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, s, grads, n, grad_scale, st, ticket, seed_counter, extra_sumsq);
+  launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, s, grads, n, grad_scale, st, ticket, seed_counter, extra_sumsq, gate);
   rc = check_launch("sumsq");
   if (rc) return rc;
   launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, s, params, grads, exp_avg, exp_avg_sq, n, decay_begin, decay_end, grad_scale, st,
-             zero_grads, big, small);
+             zero_grads, big, small, gate);
   return check_launch("adamw");
 }
 
@@ -208,7 +211,7 @@ MSR3D_API int msr3d_adamw_clip_step_split_f32(float *params, const float *grads,
 
 MSR3D_API int msr3d_adamw_apply_f32(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, long long n,
                                     long long decay_begin, long long decay_end, float grad_scale, float *state, float *big,
-                                    float *small, msr3d_stream_t stream) {
+                                    float *small, const int *gate, msr3d_stream_t stream) {
   MSR3D_REQUIRE(params && grads && exp_avg && exp_avg_sq && state, "adamw_apply: null pointer");
   MSR3D_REQUIRE(n >= 0 && decay_begin >= 0 && decay_begin <= decay_end && decay_end <= n, "adamw_apply: bad sizes");
   MSR3D_REQUIRE((big == nullptr) == (small == nullptr), "adamw_apply: both images or none");
@@ -216,9 +219,58 @@ MSR3D_API int msr3d_adamw_apply_f32(float *params, const float *grads, float *ex
   int grid = (int)((n + 255) / 256);
   if (grid > kSumsqBlocks) grid = kSumsqBlocks;
   launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, params, const_cast<float *>(grads), exp_avg, exp_avg_sq, n,
-             decay_begin, decay_end, grad_scale, reinterpret_cast<OptState *>(state), 0, big, small);
+             decay_begin, decay_end, grad_scale, reinterpret_cast<OptState *>(state), 0, big, small, gate);
   return check_launch("adamw");
 }
+
+namespace msr3d {
+// ---- gradient accumulation (configs/msr3d.yaml:33 gradient_accumulation_steps, trainer/leo_trainer.py:66,211) inside a
+// replayable step: a device-side counter decides whether this micro-step clears / exchanges / applies, so ONE CUDA graph
+// serves every micro-step.  state = {micro, k, clear_next, sync_now}.
+__global__ void accum_tick_kernel(int *st, unsigned long long *seed_counter, int phase) {
+  pdl_sync();
+  if (threadIdx.x == 0) {
+    const int k = st[1] > 0 ? st[1] : 1;
+    if (phase == 0) {               // start of a micro-step: what this one does
+      st[2] = st[0] == 0 ? 1 : 0;       // first of the window: gradients are cleared
+      st[3] = st[0] == k - 1 ? 1 : 0;   // last of the window: exchange + clip + AdamW run
+    } else {                        // end of a micro-step
+      st[0] = (st[0] + 1) % k;
+      if (seed_counter != nullptr) *seed_counter += 1ull;   // fresh dropout masks every micro-step
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+zero_gated_kernel(float4 *__restrict__ p, long long n4, const int *__restrict__ gate) {
+  pdl_sync();
+  if (gate != nullptr && *gate == 0) return;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+}  // namespace msr3d
+using namespace msr3d;
+
+MSR3D_API int msr3d_accum_tick(int *state, unsigned long long *seed_counter, int phase, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(state != nullptr && (phase == 0 || phase == 1), "accum_tick: bad arguments");
+  launch_pdl(accum_tick_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, state, seed_counter, phase);
+  return check_launch("accum_tick");
+}
+MSR3D_API int msr3d_zero_gated_f32(float *p, long long n, const int *gate, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(p != nullptr && n >= 0 && (n & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0, "zero_gated: alignment");
+  if (n == 0) return MSR3D_OK;
+  launch_pdl(zero_gated_kernel, dim3(kNumSMs * 2), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<float4 *>(p), n >> 2, gate);
+  return check_launch("zero_gated");
+}
+/* msr3d_adamw_clip_step_split_f32 gated by *gate (gradient accumulation; big / small nullable). */
+MSR3D_API int msr3d_adamw_clip_step_gated_f32(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, long long n,
+                                              long long decay_begin, long long decay_end, float grad_scale, float *state,
+                                              unsigned int *ticket, const float *extra_sumsq, float *big, float *small,
+                                              const int *gate, msr3d_stream_t stream) {
+  return adamw_impl(params, const_cast<float *>(grads), exp_avg, exp_avg_sq, n, decay_begin, decay_end, grad_scale, state, ticket,
+                    nullptr, extra_sumsq, 0, big, small, stream, gate);
+}
+
 
 /* out[0] = sum_i a[i] * b[i] (device scalar), deterministic. */
 MSR3D_API int msr3d_dot_f32(const float *a, const float *b, long long n, float *out, msr3d_stream_t stream) {

@@ -60,7 +60,7 @@ AR_MAX_WORLD, AR_MAX_BLOCKS = 8, 64
 class AllreduceDesc(ctypes.Structure):
     """Mirror of `msr3d_allreduce_desc` (include/msr3d_b200.h)."""
     _fields_ = [("buf", c_vp * AR_MAX_WORLD), ("flags", c_vp * AR_MAX_WORLD), ("partials", c_vp * AR_MAX_WORLD),
-                ("epoch", c_vp), ("rank", c_int), ("world", c_int), ("channel", c_int)]
+                ("epoch", c_vp), ("gate", c_vp), ("rank", c_int), ("world", c_int), ("channel", c_int)]
 
 
 _C.register_protos({
@@ -92,9 +92,12 @@ _C.register_protos({
     "msr3d_adamw_clip_step_split_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_qpos_fwd_acc_f32": [c_vp, c_vp, c_int] + [c_vp] * 15 + [c_vp],
     "msr3d_stage_step": [ctypes.POINTER(StageDesc), c_vp],
-    "msr3d_adamw_apply_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp],
+    "msr3d_adamw_apply_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "msr3d_accum_tick": [c_vp, c_vp, c_int, c_vp],
+    "msr3d_zero_gated_f32": [c_vp, c_ll, c_vp, c_vp],
+    "msr3d_adamw_clip_step_gated_f32": [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_allreduce_sum_f32": [ctypes.POINTER(AllreduceDesc), c_ll, c_ll, c_int, c_vp],
-    "msr3d_grad_norm_finalize_f32": [c_vp, c_int, c_int, c_int, c_float, c_vp, c_vp, c_vp, c_vp],
+    "msr3d_grad_norm_finalize_f32": [c_vp, c_int, c_int, c_int, c_float, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_split_tf32_f32": [c_vp, c_vp, c_vp, c_ll, c_vp],
     "msr3d_ffn_pair_fwd_ps_f32": [c_vp] * 8 + [c_int, c_int, c_ull, c_vp, c_float, c_uint, c_vp, c_vp, c_vp, c_int, c_vp],
     "msr3d_ffn_pair_bwd_ps_f32": [c_vp] * 7 + [c_int, c_int, c_vp, c_vp, c_int, c_vp],
@@ -150,7 +153,7 @@ class FusedPrompter:
                  grad_norm: Optional[float] = 5.0, world_size: int = 1, split: int = 3,
                  grad_split: int = 6, gemm_impl: Optional[str] = None, no_decay_bias: bool = False,
                  alias_grads: bool = True, chain_sms: Optional[int] = None,
-                 extra_params: Optional[Dict[str, torch.nn.Parameter]] = None):
+                 extra_params: Optional[Dict[str, torch.nn.Parameter]] = None, accum_steps: int = 1):
         # NOTE: weight-gradient GEMMs and bias reductions are issued on a side stream (see _run)
         why = supported(model)
         if why is not None:
@@ -168,6 +171,13 @@ class FusedPrompter:
         # ONE AdamW over all trainable parameters (13.67 M elements) are this engine's single flat
         # operations.  Their forward / backward stay the caller's (torch autograd accumulates into p.grad, which is a
         # view of the flat gradient buffer); they sit in the early bucket (final before the prompter's backward).
+        # accum_steps = k > 1: gradient accumulation over k micro-steps (configs/msr3d.yaml:33 gradient_accumulation_steps:
+        # 5; trainer/leo_trainer.py:66,211) in the prefetch schedule — gradients are cleared at the first micro-step of a
+        # window, exchanged / clipped / applied (scaled by 1 / (world * k), the mean over micro-batches as
+        # accelerator.backward produces it) at the last; a device-side counter gates those kernels, so the SAME CUDA
+        # graph replays for every micro-step.
+        self.accum_steps = int(accum_steps)
+        assert self.accum_steps >= 1
         self.extra_params = dict(extra_params or {})
         assert alias_grads or not self.extra_params, "extra_params need alias_grads=True"
         # transformer GEMMs: "tf32x3" = TMA-fed tcgen05 kind::tf32 big/small pairs (csrc/gemm3x.cu, default),
@@ -206,6 +216,13 @@ class FusedPrompter:
         self.opt_state[:8] = torch.tensor([0.0, 0.0, lr, betas[0], betas[1], eps, weight_decay,
                                            grad_norm if grad_norm else 0.0])
         self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        # {micro, k, clear_next, sync_now} of the accumulation window (msr3d_accum_tick)
+        if self.accum_steps > 1:
+            assert self.world_size == 1 or self.p2p is not None, "gradient accumulation at N > 1 needs the P2P exchange"
+        self.accum_state = torch.tensor([0, self.accum_steps, 1, 1 if self.accum_steps == 1 else 0], dtype=torch.int32, device=dev)
+        if self.accum_steps > 1 and self.p2p is not None:
+            for d in self.p2p["desc"]:
+                d.gate = self.accum_state.data_ptr() + 12
         self.loss_buf = torch.zeros(2, dtype=torch.float32, device=dev)   # double-buffered (async read-back)
         self._loss_i = 0
         self.seed_counter = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -328,6 +345,7 @@ class FusedPrompter:
                 for q in range(self.world_size):
                     d.buf[q], d.flags[q], d.partials[q] = out["grad_ptrs"][q], out["flags_ptrs"][q], out["partials_ptrs"][q]
                 d.epoch, d.rank, d.world, d.channel = out["epoch"].data_ptr(), out["rank"], self.world_size, ch
+                d.gate = None          # set by __init__ when gradients are accumulated over several micro-steps
                 descs.append(d)
             out["desc"] = descs
             return out
@@ -353,12 +371,30 @@ class FusedPrompter:
         """Clip + AdamW on gradients reduced by _allreduce_p2p: the norm partials came with the data."""
         st = torch.cuda.current_stream().cuda_stream
         ex = self.extra_sumsq.data_ptr() if self.extra_sumsq is not None else None
+        acc = self.accum_steps > 1
+        gate = self.accum_state.data_ptr() + 12 if acc else None        # sync_now
+        scale = 1.0 / (self.world_size * self.accum_steps)
         _C.call("msr3d_grad_norm_finalize_f32", self.p2p["partials"].data_ptr(), self.world_size, nb0, nb1,
-                1.0 / self.world_size, ex, self.opt_state.data_ptr(), self.seed_counter.data_ptr(), st)
+                scale, ex, self.opt_state.data_ptr(), None if acc else self.seed_counter.data_ptr(), gate, st)
         n, (d0, d1) = self.n_opt, self.decay_range
         _C.call("msr3d_adamw_apply_f32", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                n, d0, d1, 1.0 / self.world_size, self.opt_state.data_ptr(),
-                self.flat_big.data_ptr() if split else None, self.flat_small.data_ptr() if split else None, st)
+                n, d0, d1, scale, self.opt_state.data_ptr(),
+                self.flat_big.data_ptr() if split else None, self.flat_small.data_ptr() if split else None, gate, st)
+
+    def _accum_tick(self, phase):
+        if self.accum_steps > 1:
+            _C.call("msr3d_accum_tick", self.accum_state.data_ptr(), self.seed_counter.data_ptr(), phase,
+                    torch.cuda.current_stream().cuda_stream)
+
+    def _optimizer_accum(self, split):
+        """Single-GPU clip + AdamW of an accumulation window: norm and update gated by sync_now."""
+        n, (d0, d1) = self.n_opt, self.decay_range
+        ex = self.extra_sumsq.data_ptr() if self.extra_sumsq is not None else None
+        _C.call("msr3d_adamw_clip_step_gated_f32", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(),
+                self.v.data_ptr(), n, d0, d1, 1.0 / (self.world_size * self.accum_steps), self.opt_state.data_ptr(),
+                self.ticket.data_ptr(), ex, self.flat_big.data_ptr() if split else None,
+                self.flat_small.data_ptr() if split else None, self.accum_state.data_ptr() + 12,
+                torch.cuda.current_stream().cuda_stream)
 
     def P(self, name):  # device pointer of a parameter / its gradient
         return self.flat_p.data_ptr() + 4 * self.offs[name]
@@ -702,7 +738,11 @@ class FusedPrompter:
         # and the gradient buffer is cleared beside the input encoders (first written by the backward pass)
         # ... and the weight images were written by the optimiser of the previous step (refresh_split() after any other
         # change of the parameters)
-        self.pre_prog_nogeo = [e for e in pre_prog if e[3] not in ("geometry", "split_w")] + [("memset", None, (self.flat_g,), None, 2)]
+        clear = ("memset", None, (self.flat_g,), None, 2)
+        if self.accum_steps > 1:
+            clear = ("msr3d_zero_gated_f32", _C.lib().msr3d_zero_gated_f32,
+                     (self.flat_g.data_ptr(), (self.n_opt + 3) // 4 * 4, self.accum_state.data_ptr() + 8), "grad_clear", 2)
+        self.pre_prog_nogeo = [e for e in pre_prog if e[3] not in ("geometry", "split_w")] + [clear]
         return pre_prog, fwd, bwd
 
     def _run(self, prog):
@@ -817,6 +857,7 @@ class FusedPrompter:
             self._run(self.bwd_prog[self.bwd_split:])
             return
         if depth2:
+            self._accum_tick(0)
             # ONE launch moves every staged input one generation on (csrc/stage.cu)
             rc = _C.lib().msr3d_stage_step(ctypes.byref(self._stage_desc(slot)), main.cuda_stream)
             if rc != 0:
@@ -863,6 +904,7 @@ class FusedPrompter:
                     self.backward()
                     self._allreduce_p2p(0, 0, self.n_opt, AR_MAX_BLOCKS, main)
                     self._optimizer_after_p2p(AR_MAX_BLOCKS, 0, split_w)
+                self._accum_tick(1)
             else:
                 if self.ddp_buckets and e1 > e0:
                     self._run(self.bwd_prog[:self.bwd_split])
@@ -879,7 +921,11 @@ class FusedPrompter:
         else:
             self.backward()
             if self.world_size == 1:
-                self.optimizer_step(split=depth2 and self.attn_block_active)
+                if depth2 and self.accum_steps > 1:
+                    self._optimizer_accum(self.attn_block_active)
+                    self._accum_tick(1)
+                else:
+                    self.optimizer_step(split=depth2 and self.attn_block_active)
         if with_encoder:
             main.wait_stream(self.enc_stream)  # join
 
@@ -1027,7 +1073,8 @@ class FusedPrompter:
         keys = [k + lv for k in ("obj_locs", "obj_masks", "anchor_locs", "anchor_ori", "upstream")
                 for lv in ("", "_n", "_q0", "_q1")]
         keys += ["pw", "ff", "sz", "pw_n", "ff_n", "sz_n"]
-        saved = [t.clone() for t in (self.flat_p, self.m, self.v, self.opt_state, self.seed_counter, w["emb"], w["emb_next"])]
+        saved = [t.clone() for t in (self.flat_p, self.m, self.v, self.opt_state, self.seed_counter, w["emb"], w["emb_next"],
+                                     self.accum_state)]
         saved_in = {k: w[k].clone() for k in keys}
         torch.cuda.synchronize()
         for slot in (0, 1):
@@ -1048,7 +1095,8 @@ class FusedPrompter:
             with torch.cuda.graph(g, stream=self.hi_stream, capture_error_mode="thread_local"):
                 self._pipelined_body(part=2)
             self.graph_prefetch_tail = g
-        for dst, src in zip((self.flat_p, self.m, self.v, self.opt_state, self.seed_counter, w["emb"], w["emb_next"]), saved):
+        for dst, src in zip((self.flat_p, self.m, self.v, self.opt_state, self.seed_counter, w["emb"], w["emb_next"],
+                             self.accum_state), saved):
             dst.copy_(src)
         for k in keys:
             w[k].copy_(saved_in[k])

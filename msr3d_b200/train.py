@@ -32,10 +32,11 @@ class HotPathTrainer:
     def __init__(self, model: torch.nn.Module, B: int, O: int, P: int, lr: float = 3e-5,
                  weight_decay: float = 0.05, betas=(0.9, 0.999), grad_norm: float = 5.0,
                  world_size: int = 1, split: int = 6, use_graph: bool = True, pipeline: bool = True,
-                 chain_sms: Optional[int] = None, extra_params=None):
+                 chain_sms: Optional[int] = None, extra_params=None, accum_steps: int = 1):
         self.engine = FusedPrompter(model, lr=lr, weight_decay=weight_decay, betas=betas,
                                     grad_norm=grad_norm, world_size=world_size, split=split, chain_sms=chain_sms,
-                                    extra_params=extra_params)
+                                    extra_params=extra_params, accum_steps=accum_steps)
+        assert accum_steps == 1 or pipeline == "prefetch", "gradient accumulation is built into the prefetch schedule"
         self.engine.prepare(B, O, P, training=model.training)
         self.use_graph = use_graph
         self.pipeline = pipeline
