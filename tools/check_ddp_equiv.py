@@ -44,6 +44,25 @@ for mode in ("sequential", "prefetch_graph", "prefetch_eager"):
     ref = res[mode].clone()
     dist.broadcast(ref, 0)
     assert torch.equal(ref, res[mode]), f"{mode}: replicas diverged on rank {rank}"
+# gradient accumulation over 2 micro-steps with the gated peer-memory exchange: two updates from four batches, replicas identical
+model = helpers.build_prompter(seed, device=dev)
+tr = HotPathTrainer(model, B, O, P, lr=1e-4, world_size=world, use_graph=True, pipeline="prefetch", accum_steps=2)
+if tr.engine.p2p is not None:
+    tr.engine.prime2(batches[0], ups[0], batches[1], ups[1])
+    tr.engine.capture_prefetch()
+    tr._calls = 2
+    for b, u in zip(batches[2:], ups[2:]):
+        tr.step(b, u)
+    tr.flush()
+    torch.cuda.synchronize()
+    assert float(tr.engine.opt_state[1]) == 2.0 and int(tr.engine.accum_state[0]) == 0
+    acc = tr.engine.flat_p.clone()
+    ref = acc.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(ref, acc), f"accumulation: replicas diverged on rank {rank}"
+    assert torch.isfinite(acc).all() and not torch.equal(acc, res["sequential"])
+    if rank == 0:
+        print("accumulation (k = 2) under the peer-memory exchange: 2 updates, replicas identical")
 for mode in ("prefetch_graph", "prefetch_eager"):
     e = helpers.rel_err(res[mode], res["sequential"])
     if rank == 0:
