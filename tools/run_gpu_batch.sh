@@ -1,2 +1,8 @@
 cd $GRAFT_REPO_ROOT
-timeout 300 python -m pytest tests/test_ddp_gpu.py -x -q 2>&1 | tail -6
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29592 bench.py --gpus 2 --steps 60 --warmup 5 --fast > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err
+echo "rc=$?"
+python -c "
+import json
+d=json.loads(open('gpurun_out/r2_bench_n2.json').read().strip().splitlines()[-1])
+print(d['n_gpus'], d['ms_per_step'], d['value'], d['e2e']['value'])
+"
