@@ -300,6 +300,26 @@ int msr3d_attn_fwd_f32(const float *qkvc, int ldq, const float *pw, const unsign
 int msr3d_attn_bwd_f32(const float *dctx, int ldc, const float *qkvc, int ldq, const float *pw,
                        const float *P, const float *LOC, int B, int L, int H, float *dqkvc,
                        msr3d_stream_t stream);
+/* The other fusions of MultiHeadAttentionSpatial (modules/layers/transformers.py:207-244).
+ * fusion: 0 cond (= the two calls above), 1 mul, 2 bias (and ctx), 3 add.  The location term is always
+ * z[l,t] = sw[0] + sw[1:6] . pw[l,t,:] with sw read from the last H*6 columns of the qkvc row of token l —
+ * written by the QKV+cond GEMM for `cond`, by msr3d_spatial_weights_fwd_f32 otherwise.  `add` saves
+ * softmax(S) in P and softmax(z) in LOC (the fused attention is their mean); `bias` / `ctx` leave LOC untouched. */
+int msr3d_attn_fusion_fwd_f32(const float *qkvc, int ldq, const float *pw, const unsigned char *key_pad, int B,
+                              int L, int H, int fusion, float *P, float *LOC, float *ctx, int ldc,
+                              msr3d_stream_t stream);
+int msr3d_attn_fusion_bwd_f32(const float *dctx, int ldc, const float *qkvc, int ldq, const float *pw,
+                              const float *P, const float *LOC, int B, int L, int H, int fusion, float *dqkvc,
+                              msr3d_stream_t stream);
+/* pairwise_loc_fc (transformers.py:189-192) as spatial weights in the qkvc rows.  ctx_mode 0 (mul / bias / add):
+ * W (spatial_n_head, 5), b (spatial_n_head), multihead = spatial_n_head == H.  ctx_mode 1 (ctx): W (H*32, 5),
+ * b (H*32); sw = q_h . [b_h | W_h] / sqrt(32) (reads the q columns of the same row).  The backward reads
+ * d(sw) from dqkvc, ACCUMULATES dW / db (deterministic) and, for ctx, adds the q gradient into dqkvc. */
+int msr3d_spatial_weights_fwd_f32(const float *W, const float *b, int ctx_mode, int multihead, float *qkvc, int ldq,
+                                  int M, int H, msr3d_stream_t stream);
+int msr3d_spatial_weights_bwd_f32(const float *W, const float *b, int ctx_mode, int multihead, const float *qkvc,
+                                  float *dqkvc, int ldq, int M, int H, float *dW, float *db,
+                                  msr3d_stream_t stream);
 /* Same contract as msr3d_attn_bwd_f32 on the tensor cores (csrc/attn_block.cu: dP, dq, dk, dv as tcgen05 kind::tf32
  * 3xTF32 products, one CTA per (head, scene)); requires L <= 64, 8 heads, ldq = 816. */
 int msr3d_attn_bwd_tc_f32(const float *dctx, int ldc, const float *qkvc, int ldq, const float *pw, const float *P,

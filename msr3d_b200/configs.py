@@ -54,12 +54,20 @@ def load_spec():
         return [tuple(x) for x in json.load(fh)]
 
 
-def build_prompter(seed: int, situation_type="as_transform_for_objects", device="cpu"):
-    """Drop-in OSE3DSituation of the shipped configuration with seeded synthetic weights (eval mode)."""
+def build_prompter(seed: int, situation_type="as_transform_for_objects", device="cpu", fusion="cond", **spatial_over):
+    """Drop-in OSE3DSituation of the shipped configuration with seeded synthetic weights (eval mode).
+    Other fusions / situation modes own a different set of keys; values are keyed by NAME
+    (synthetic.make_state_dict), so every key shared with the shipped model gets the same tensor."""
     import msr3d_b200
-    from . import synthetic
-    model = msr3d_b200.build_model(prompter_cfg(situation_type))
-    sd = synthetic.make_state_dict(load_spec(), seed)
-    # other situation modes own a subset of the shipped model's keys; values are keyed by name
-    model.load_state_dict({k: sd[k] for k in model.state_dict()}, strict=True)
+    model = msr3d_b200.build_model(prompter_cfg(situation_type, fusion, **spatial_over))
+    model.load_state_dict(model_state_dict(model, seed), strict=True)
     return model.to(device).eval()
+
+
+def model_state_dict(model, seed: int) -> dict:
+    """Seeded synthetic tensors for exactly the keys of `model` (what tests/golden/gen_golden.py loads into the
+    reference model of the same configuration)."""
+    from . import synthetic
+    spec = [(k, list(v.shape), "int64" if str(v.dtype) == "torch.int64" else "float32")
+            for k, v in model.state_dict().items()]
+    return synthetic.make_state_dict(spec, seed)

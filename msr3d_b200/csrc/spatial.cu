@@ -442,6 +442,15 @@ constexpr size_t kOnePerSmBytes = 116 * 1024;   // more than half of the 227 KB 
 constexpr int kAttnMaxWarps = 16;    // launch bound; the warp count itself is a launch-time choice
 constexpr int kKeysPerLane = kMaxL / 32;  // 4
 
+// FUSION selects how the pairwise-location term z = sw[0] + sw[1:] . pw[l,t,:] enters (transformers.py:207-244):
+//   kFuseCond  logits = log(clamp(sigmoid(z), 1e-6)) + S      (sw = lang_cond_fc(x), per token and head)
+//   kFuseMul   logits = log(clamp(relu(z), 1e-6)) + S         (sw = pairwise_loc_fc rows, the same for every token)
+//   kFuseBias  logits = z + S                                 (`bias`; `ctx` too, with sw derived from q: spatial_weights_*)
+//   kFuseAdd   P = (softmax(S) + softmax(z)) / 2              (both softmaxes saved: P buffer <- softmax(S), LOC <- softmax(z))
+// masked keys: S = -inf; loc = 0 (cond, mul) / z = -inf (bias, ctx, add).
+enum { kFuseCond = 0, kFuseMul = 1, kFuseBias = 2, kFuseAdd = 3 };
+
+template <int FUSION>
 __global__ void __launch_bounds__(kAttnMaxWarps * 32)
 attn_fwd_kernel(const float *__restrict__ qkvc, int ldq, const float *__restrict__ pw,
                 const unsigned char *__restrict__ key_pad, int L, int H, float *__restrict__ P,
@@ -485,7 +494,7 @@ attn_fwd_kernel(const float *__restrict__ qkvc, int ldq, const float *__restrict
         if (j < nj) s[j] += q * kT[d * LT + lane + 32 * j];
     }
     const float *pwr = pw + ((size_t)b * L + l) * L * 5;
-    float mx = -INFINITY;
+    float mx = -INFINITY, mz = -INFINITY;
 #pragma unroll
     for (int j = 0; j < kKeysPerLane; ++j) {
       const int t = lane + 32 * j;
@@ -494,15 +503,25 @@ attn_fwd_kernel(const float *__restrict__ qkvc, int ldq, const float *__restrict
         float z = sw[0];
 #pragma unroll
         for (int d = 0; d < 5; ++d) z += sw[1 + d] * g[d];
-        float lc = 1.f / (1.f + __expf(-z));
-        float sc = s[j] * scale;
-        if (key_pad != nullptr && key_pad[(size_t)b * L + t]) { sc = -INFINITY; lc = 0.f; }
-        s[j] = __logf(fmaxf(lc, 1e-6f)) + sc;
-        loc[j] = lc;
+        const bool masked = key_pad != nullptr && key_pad[(size_t)b * L + t];
+        float sc = masked ? -INFINITY : s[j] * scale;
+        if (FUSION == kFuseCond || FUSION == kFuseMul) {
+          float lc = FUSION == kFuseCond ? 1.f / (1.f + __expf(-z)) : fmaxf(z, 0.f);
+          if (masked) lc = 0.f;
+          s[j] = __logf(fmaxf(lc, 1e-6f)) + sc;
+          loc[j] = lc;
+        } else if (FUSION == kFuseBias) {
+          s[j] = z + sc;
+          loc[j] = 0.f;
+        } else {
+          s[j] = sc;
+          loc[j] = masked ? -INFINITY : z;
+          mz = fmaxf(mz, loc[j]);
+        }
         mx = fmaxf(mx, s[j]);
       } else {
         s[j] = -INFINITY;
-        loc[j] = 0.f;
+        loc[j] = FUSION == kFuseAdd ? -INFINITY : 0.f;
       }
     }
     mx = warp_max(mx);
@@ -514,13 +533,29 @@ attn_fwd_kernel(const float *__restrict__ qkvc, int ldq, const float *__restrict
       sum += s[j];
     }
     const float inv = 1.f / warp_sum(sum);
+    float invz = 0.f;
+    if (FUSION == kFuseAdd) {       // second softmax, over the location logits alone
+      mz = warp_max(mz);
+      float sumz = 0.f;
+#pragma unroll
+      for (int j = 0; j < kKeysPerLane; ++j) {
+        loc[j] = __expf(loc[j] - mz);
+        sumz += loc[j];
+      }
+      invz = 1.f / warp_sum(sumz);
+    }
     float *Pr = P + (((size_t)b * H + h) * L + l) * L;
     float *Lr = LOC + (((size_t)b * H + h) * L + l) * L;
 #pragma unroll
     for (int j = 0; j < kKeysPerLane; ++j) {
       s[j] *= inv;
+      if (FUSION == kFuseAdd) loc[j] *= invz;
       const int t = lane + 32 * j;
-      if (j < nj && t < L) { Pr[t] = s[j]; Lr[t] = loc[j]; }
+      if (j < nj && t < L) {
+        Pr[t] = s[j];
+        if (FUSION != kFuseBias) Lr[t] = loc[j];
+      }
+      if (FUSION == kFuseAdd) s[j] = 0.5f * (s[j] + loc[j]);   // the fused attention that weights v
     }
     float acc = 0.f;  // lane = output dim
 #pragma unroll
@@ -546,6 +581,7 @@ attn_fwd_kernel(const float *__restrict__ qkvc, int ldq, const float *__restrict
 //            (no atomics, no zero-fill, deterministic).
 // With 32 (head, scene) pairs a one-CTA-per-pair kernel filled 32 SMs and walked 8 rows per warp in
 // each phase (40 us); a cluster of 4 x 16 warps does one row per warp per phase.
+template <int FUSION>
 __global__ void __launch_bounds__(kAttnMaxWarps * 32)
 attn_bwd_kernel(const float *__restrict__ dctx, int ldc, const float *__restrict__ qkvc, int ldq,
                 const float *__restrict__ pw, const float *__restrict__ P,
@@ -601,31 +637,51 @@ attn_bwd_kernel(const float *__restrict__ dctx, int ldc, const float *__restrict
     const float *Pr = P + (((size_t)b * H + h) * L + l) * L;
     const float *Lr = LOC + (((size_t)b * H + h) * L + l) * L;
     const float *pwr = pw + ((size_t)b * L + l) * L * 5;
-    float rowdot = 0.f;
+    float rowdot = 0.f, rowdot_z = 0.f;
+    float pz[kKeysPerLane];   // kFuseAdd: softmax of the location logits (LOC buffer)
 #pragma unroll
     for (int j = 0; j < kKeysPerLane; ++j) {
       const int t = lane + 32 * j;
       p[j] = (j < nj && t < L) ? Pr[t] : 0.f;
       rowdot += dp[j] * p[j];
+      pz[j] = 0.f;
+      if (FUSION == kFuseAdd) {
+        pz[j] = (j < nj && t < L) ? Lr[t] : 0.f;
+        rowdot_z += dp[j] * pz[j];
+      }
     }
     rowdot = warp_sum(rowdot);
+    if (FUSION == kFuseAdd) rowdot_z = warp_sum(rowdot_z);
     float dsw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < kKeysPerLane; ++j) {
       const int t = lane + 32 * j;
-      const float dl = p[j] * (dp[j] - rowdot);   // d logits
+      // d logits of the content term (kFuseAdd: of softmax(S), which carries half of the fused attention)
+      const float dl = (FUSION == kFuseAdd ? 0.5f : 1.f) * p[j] * (dp[j] - rowdot);
+      const float dz_add = 0.5f * pz[j] * (dp[j] - rowdot_z);
       dp[j] = dl;
       if (j < nj && t < L) {
         dS[ll * LP + t] = dl;
-        Ps[ll * LP + t] = p[j];
-        const float lc = Lr[t];
+        Ps[ll * LP + t] = FUSION == kFuseAdd ? 0.5f * (p[j] + pz[j]) : p[j];
         const float *g = pwr + t * 5;
-        // log(clamp(sigmoid(z), 1e-6)): d/dz = (loc >= 1e-6) * (1 - loc); 1 - sigmoid(z) is evaluated as
-        // sigmoid(-z) from the recomputed z (no cancellation near loc ~ 1); masked keys have loc = 0
-        float z = sw[0];
+        float gz;
+        if (FUSION == kFuseCond) {
+          // log(clamp(sigmoid(z), 1e-6)): d/dz = (loc >= 1e-6) * (1 - loc); 1 - sigmoid(z) is evaluated as
+          // sigmoid(-z) from the recomputed z (no cancellation near loc ~ 1); masked keys have loc = 0
+          const float lc = Lr[t];
+          float z = sw[0];
 #pragma unroll
-        for (int d = 0; d < 5; ++d) z += sw[1 + d] * g[d];
-        const float gz = lc >= 1e-6f ? dl / (1.f + __expf(z)) : 0.f;
+          for (int d = 0; d < 5; ++d) z += sw[1 + d] * g[d];
+          gz = lc >= 1e-6f ? dl / (1.f + __expf(z)) : 0.f;
+        } else if (FUSION == kFuseMul) {
+          // log(clamp(relu(z), 1e-6)): d/dz = 1 / loc where loc = relu(z) >= 1e-6 (which implies z > 0)
+          const float lc = Lr[t];
+          gz = lc >= 1e-6f ? dl / lc : 0.f;
+        } else if (FUSION == kFuseBias) {
+          gz = dl;                  // logits = z + S; masked keys have P = 0, hence dl = 0
+        } else {
+          gz = dz_add;
+        }
         dsw[0] += gz;
 #pragma unroll
         for (int d = 0; d < 5; ++d) dsw[1 + d] += gz * g[d];
@@ -665,6 +721,97 @@ attn_bwd_kernel(const float *__restrict__ dctx, int ldc, const float *__restrict
     o[2 * D + h * kDh + lane] = dv;
   }
   cluster.sync();   // nobody exits while a peer may still be reading its shared memory
+}
+
+// ---------------------------------------------------------------------------
+// Spatial weights of the fusions whose location term does not come out of the QKV+cond GEMM
+// (transformers.py:207-221).  They are written into the `cond` columns of the qkvc rows,
+// [bias, w0..w4] per (token, head), so that the attention kernels above read every fusion the same way:
+//   mul / bias / add   sw[m, h, :] = [b[hs], W[hs, 0..4]],  pairwise_loc_fc = Linear(5, spatial_n_head), hs = h or 0
+//   ctx                loc[l,t] = q_h(l) . (Wc_h pw[l,t] + bc_h) / sqrt(dh)   (pairwise_loc_fc = Linear(5, d_model))
+//                      = sw . [1, pw]  with  sw[m, h, 0] = q_h(m) . bc_h / sqrt(dh),  sw[m, h, 1+d] = q_h(m) . Wc_h[:, d] / sqrt(dh)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+spatial_weights_fwd_kernel(const float *__restrict__ W, const float *__restrict__ bvec, int ctx_mode, int multihead,
+                           float *__restrict__ qkvc, int ldq, int M, int H) {
+  pdl_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (token, head)
+  if (i >= M * H) return;
+  const int m = i / H, h = i % H;
+  float *o = qkvc + (size_t)m * ldq + 3 * H * kDh + h * 6;
+  if (!ctx_mode) {
+    const int hs = multihead ? h : 0;
+    o[0] = bvec[hs];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) o[1 + d] = W[hs * 5 + d];
+    return;
+  }
+  const float *q = qkvc + (size_t)m * ldq + h * kDh;
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < kDh; ++k) {
+    const float qk = q[k];
+    const float *w = W + (size_t)(h * kDh + k) * 5;
+    acc[0] += qk * bvec[h * kDh + k];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) acc[1 + d] += qk * w[d];
+  }
+  const float scale = rsqrtf((float)kDh);
+#pragma unroll
+  for (int d = 0; d < 6; ++d) o[d] = acc[d] * scale;
+}
+
+// Backward of the above from d(sw) = dqkvc[:, 3 D + 6 h + j] (written by attn_bwd_kernel).  Deterministic: fixed
+// summation order, no atomics; parameter gradients ACCUMULATE into dW / db (flat gradient buffer).
+//   mul / bias / add: one CTA; column sums over the tokens, heads folded when the layer is not multi-head.
+//   ctx: CTA m < M adds the q gradient of token m (thread = (head, k)); CTA M reduces dWc, dbc over the tokens.
+__global__ void __launch_bounds__(256)
+spatial_weights_bwd_kernel(const float *__restrict__ W, const float *__restrict__ bvec, int ctx_mode, int multihead,
+                           const float *__restrict__ qkvc, float *__restrict__ dqkvc, int ldq, int M, int H,
+                           float *__restrict__ dW, float *__restrict__ db) {
+  pdl_sync();
+  const int D = H * kDh;
+  if (!ctx_mode) {
+    __shared__ float part[4][64];
+    const int c = threadIdx.x & 63, r = threadIdx.x >> 6;     // column of d(sw), row group
+    float s = 0.f;
+    if (c < H * 6)
+      for (int m = r; m < M; m += 4) s += dqkvc[(size_t)m * ldq + 3 * D + c];
+    part[r][c] = s;
+    __syncthreads();
+    const int nsh = multihead ? H : 1;
+    if (threadIdx.x < nsh * 6) {
+      const int hs = threadIdx.x / 6, j = threadIdx.x % 6;
+      float t = 0.f;
+      for (int h = multihead ? hs : 0; h < (multihead ? hs + 1 : H); ++h)
+        t += (part[0][h * 6 + j] + part[1][h * 6 + j]) + (part[2][h * 6 + j] + part[3][h * 6 + j]);
+      if (j == 0) db[hs] += t;
+      else dW[hs * 5 + j - 1] += t;
+    }
+    return;
+  }
+  const float scale = rsqrtf((float)kDh);
+  const int hk = threadIdx.x;            // blockDim = D = 256
+  if (hk >= D) return;
+  const int h = hk / kDh;
+  if ((int)blockIdx.x < M) {
+    const int m = blockIdx.x;
+    const float *ds = dqkvc + (size_t)m * ldq + 3 * D + h * 6;
+    float g = ds[0] * bvec[hk];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) g += ds[1 + d] * W[(size_t)hk * 5 + d];
+    dqkvc[(size_t)m * ldq + hk] += g * scale;
+    return;
+  }
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int m = 0; m < M; ++m) {
+    const float q = qkvc[(size_t)m * ldq + hk];
+    const float *ds = dqkvc + (size_t)m * ldq + 3 * D + h * 6;
+#pragma unroll
+    for (int d = 0; d < 6; ++d) acc[d] += q * ds[d];
+  }
+  db[hk] += acc[0] * scale;
+#pragma unroll
+  for (int d = 0; d < 5; ++d) dW[(size_t)hk * 5 + d] += acc[1 + d] * scale;
 }
 
 __global__ void dropout_mask_kernel(Dropout drop, unsigned site, long long n, float *out) {
@@ -828,13 +975,9 @@ MSR3D_API int msr3d_colsum_add_f32(const float *src, long long ld, int M, int N,
   return check_launch("colsum");
 }
 
-MSR3D_API int msr3d_attn_fwd_f32(const float *qkvc, int ldq, const float *pw,
-                                 const unsigned char *key_pad, int B, int L, int H, float *P,
-                                 float *LOC, float *ctx, int ldc, msr3d_stream_t stream) {
-  MSR3D_REQUIRE(qkvc && pw && P && LOC && ctx, "attn_fwd: null pointer");
-  MSR3D_REQUIRE(L >= 1 && L <= kMaxL && H >= 1 && ldq >= 3 * H * kDh + H * 6 && ldc >= H * kDh,
-                "attn_fwd: bad sizes L=%d H=%d", L, H);
-  if (B == 0) return MSR3D_OK;
+template <int FUSION>
+static int launch_attn_fwd(const float *qkvc, int ldq, const float *pw, const unsigned char *key_pad, int B, int L,
+                           int H, float *P, float *LOC, float *ctx, int ldc, msr3d_stream_t stream) {
   const int LT = ((L + 31) / 32) * 32;
   size_t smem = ((size_t)kDh * LT + (size_t)L * kDh) * sizeof(float);
   // ONE CTA PER SM: with programmatic dependent launch the CTAs of this kernel are placed while the GEMM in front
@@ -843,7 +986,7 @@ MSR3D_API int msr3d_attn_fwd_f32(const float *qkvc, int ldq, const float *pw,
   // chain (tools/chain_profile.py).  Asking for more than half of the shared memory forces one CTA per SM.
   static bool configured = false;
   if (!configured) {
-    MSR3D_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOnePerSmBytes));
+    MSR3D_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<FUSION>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOnePerSmBytes));
     configured = true;
   }
   if (g_tune[TUNE_ATTN_PACK] == 2 && smem < kOnePerSmBytes) smem = kOnePerSmBytes;   // A/B knob; default: pack (r2 sweep, SM partition)
@@ -852,17 +995,36 @@ MSR3D_API int msr3d_attn_fwd_f32(const float *qkvc, int ldq, const float *pw,
   warps = max(1, min(kAttnMaxWarps, warps));
   int zr = g_tune[TUNE_ATTN_FWD_ZSPLIT] > 0 ? g_tune[TUNE_ATTN_FWD_ZSPLIT] : ceil_div(L, warps);
   zr = max(1, min(zr, 8));
-  launch_pdl(attn_fwd_kernel, dim3(dim3(H, B, zr)), dim3(warps * 32), smem, (cudaStream_t)stream, 
+  launch_pdl(attn_fwd_kernel<FUSION>, dim3(dim3(H, B, zr)), dim3(warps * 32), smem, (cudaStream_t)stream,
       qkvc, ldq, pw, key_pad, L, H, P, LOC, ctx, ldc);
   return check_launch("attn_fwd");
 }
 
-MSR3D_API int msr3d_attn_bwd_f32(const float *dctx, int ldc, const float *qkvc, int ldq,
-                                 const float *pw, const float *P, const float *LOC, int B, int L,
-                                 int H, float *dqkvc, msr3d_stream_t stream) {
-  MSR3D_REQUIRE(dctx && qkvc && pw && P && LOC && dqkvc, "attn_bwd: null pointer");
-  MSR3D_REQUIRE(L >= 1 && L <= kMaxL && H >= 1, "attn_bwd: bad sizes");
+MSR3D_API int msr3d_attn_fusion_fwd_f32(const float *qkvc, int ldq, const float *pw,
+                                        const unsigned char *key_pad, int B, int L, int H, int fusion, float *P,
+                                        float *LOC, float *ctx, int ldc, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(qkvc && pw && P && LOC && ctx, "attn_fwd: null pointer");
+  MSR3D_REQUIRE(L >= 1 && L <= kMaxL && H >= 1 && ldq >= 3 * H * kDh + H * 6 && ldc >= H * kDh,
+                "attn_fwd: bad sizes L=%d H=%d", L, H);
+  MSR3D_REQUIRE(fusion >= 0 && fusion <= 3, "attn_fwd: fusion %d (0 cond, 1 mul, 2 bias / ctx, 3 add)", fusion);
   if (B == 0) return MSR3D_OK;
+  switch (fusion) {
+    case kFuseMul: return launch_attn_fwd<kFuseMul>(qkvc, ldq, pw, key_pad, B, L, H, P, LOC, ctx, ldc, stream);
+    case kFuseBias: return launch_attn_fwd<kFuseBias>(qkvc, ldq, pw, key_pad, B, L, H, P, LOC, ctx, ldc, stream);
+    case kFuseAdd: return launch_attn_fwd<kFuseAdd>(qkvc, ldq, pw, key_pad, B, L, H, P, LOC, ctx, ldc, stream);
+    default: return launch_attn_fwd<kFuseCond>(qkvc, ldq, pw, key_pad, B, L, H, P, LOC, ctx, ldc, stream);
+  }
+}
+
+MSR3D_API int msr3d_attn_fwd_f32(const float *qkvc, int ldq, const float *pw,
+                                 const unsigned char *key_pad, int B, int L, int H, float *P,
+                                 float *LOC, float *ctx, int ldc, msr3d_stream_t stream) {
+  return msr3d_attn_fusion_fwd_f32(qkvc, ldq, pw, key_pad, B, L, H, kFuseCond, P, LOC, ctx, ldc, stream);
+}
+
+template <int FUSION>
+static int launch_attn_bwd(const float *dctx, int ldc, const float *qkvc, int ldq, const float *pw, const float *P,
+                           const float *LOC, int B, int L, int H, float *dqkvc, msr3d_stream_t stream) {
   // cluster of `nz` CTAs per (head, scene): rows per CTA = ceil(L / nz); `warps` rows in flight per CTA
   int nz = g_tune[TUNE_ATTN_BWD_CLUSTER] > 0 ? g_tune[TUNE_ATTN_BWD_CLUSTER] : 4;
   nz = max(1, min(nz, 8));
@@ -876,14 +1038,57 @@ MSR3D_API int msr3d_attn_bwd_f32(const float *dctx, int ldc, const float *qkvc, 
   static bool configured = false;
   if (!configured) {
     const size_t mx = bytes(kMaxL, 1) > kOnePerSmBytes ? bytes(kMaxL, 1) : kOnePerSmBytes;
-    MSR3D_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+    MSR3D_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<FUSION>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
     configured = true;
   }
   size_t smem_bwd = bytes(L, nz);
   if (g_tune[TUNE_ATTN_PACK] == 2 && smem_bwd < kOnePerSmBytes) smem_bwd = kOnePerSmBytes;   // one CTA per SM, see attn_fwd
-  launch_pdl_cluster(attn_bwd_kernel, dim3(H, B, nz), dim3(warps * 32), smem_bwd, (cudaStream_t)stream,
+  launch_pdl_cluster(attn_bwd_kernel<FUSION>, dim3(H, B, nz), dim3(warps * 32), smem_bwd, (cudaStream_t)stream,
                      dim3(1, 1, nz), dctx, ldc, qkvc, ldq, pw, P, LOC, L, H, dqkvc);
   return check_launch("attn_bwd");
+}
+
+MSR3D_API int msr3d_attn_fusion_bwd_f32(const float *dctx, int ldc, const float *qkvc, int ldq,
+                                        const float *pw, const float *P, const float *LOC, int B, int L,
+                                        int H, int fusion, float *dqkvc, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(dctx && qkvc && pw && P && LOC && dqkvc, "attn_bwd: null pointer");
+  MSR3D_REQUIRE(L >= 1 && L <= kMaxL && H >= 1, "attn_bwd: bad sizes");
+  MSR3D_REQUIRE(fusion >= 0 && fusion <= 3, "attn_bwd: fusion %d (0 cond, 1 mul, 2 bias / ctx, 3 add)", fusion);
+  if (B == 0) return MSR3D_OK;
+  switch (fusion) {
+    case kFuseMul: return launch_attn_bwd<kFuseMul>(dctx, ldc, qkvc, ldq, pw, P, LOC, B, L, H, dqkvc, stream);
+    case kFuseBias: return launch_attn_bwd<kFuseBias>(dctx, ldc, qkvc, ldq, pw, P, LOC, B, L, H, dqkvc, stream);
+    case kFuseAdd: return launch_attn_bwd<kFuseAdd>(dctx, ldc, qkvc, ldq, pw, P, LOC, B, L, H, dqkvc, stream);
+    default: return launch_attn_bwd<kFuseCond>(dctx, ldc, qkvc, ldq, pw, P, LOC, B, L, H, dqkvc, stream);
+  }
+}
+
+MSR3D_API int msr3d_attn_bwd_f32(const float *dctx, int ldc, const float *qkvc, int ldq,
+                                 const float *pw, const float *P, const float *LOC, int B, int L,
+                                 int H, float *dqkvc, msr3d_stream_t stream) {
+  return msr3d_attn_fusion_bwd_f32(dctx, ldc, qkvc, ldq, pw, P, LOC, B, L, H, kFuseCond, dqkvc, stream);
+}
+
+MSR3D_API int msr3d_spatial_weights_fwd_f32(const float *W, const float *b, int ctx_mode, int multihead, float *qkvc,
+                                            int ldq, int M, int H, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(W && b && qkvc, "spatial_weights_fwd: null pointer");
+  MSR3D_REQUIRE(H >= 1 && H <= 10 && ldq >= 3 * H * kDh + H * 6, "spatial_weights_fwd: bad sizes H=%d ldq=%d", H, ldq);
+  if (M <= 0) return MSR3D_OK;
+  launch_pdl(spatial_weights_fwd_kernel, dim3(ceil_div(M * H, 256)), dim3(256), 0, (cudaStream_t)stream, W, b, ctx_mode,
+             multihead, qkvc, ldq, M, H);
+  return check_launch("spatial_weights_fwd");
+}
+
+MSR3D_API int msr3d_spatial_weights_bwd_f32(const float *W, const float *b, int ctx_mode, int multihead,
+                                            const float *qkvc, float *dqkvc, int ldq, int M, int H, float *dW,
+                                            float *db, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(W && b && qkvc && dqkvc && dW && db, "spatial_weights_bwd: null pointer");
+  MSR3D_REQUIRE(H >= 1 && H <= 10 && ldq >= 3 * H * kDh + H * 6, "spatial_weights_bwd: bad sizes H=%d ldq=%d", H, ldq);
+  MSR3D_REQUIRE(!ctx_mode || H * kDh == 256, "spatial_weights_bwd: ctx fusion needs d_model = 256");
+  if (M <= 0) return MSR3D_OK;
+  launch_pdl(spatial_weights_bwd_kernel, dim3(ctx_mode ? M + 1 : 1), dim3(256), 0, (cudaStream_t)stream, W, b,
+             ctx_mode, multihead, qkvc, dqkvc, ldq, M, H, dW, db);
+  return check_launch("spatial_weights_bwd");
 }
 
 /* Test hook: the multiplicative mask (0 or 1/(1-p)) every kernel applies at `site` to element

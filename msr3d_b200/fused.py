@@ -106,6 +106,10 @@ _C.register_protos({
     "msr3d_ffn_tail_bwd_ps_f32": [c_vp, c_int, c_vp, c_ull, c_vp, c_float, c_uint, c_vp, c_vp,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_attn_block_supported": [c_int, c_int, c_int],
+    "msr3d_attn_fusion_fwd_f32": [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp],
+    "msr3d_attn_fusion_bwd_f32": [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "msr3d_spatial_weights_fwd_f32": [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp],
+    "msr3d_spatial_weights_bwd_f32": [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     "msr3d_attn_block_fwd_f32": [c_vp] * 9 + [c_int, c_int] + [c_vp] * 4 + [c_ull, c_vp, c_float, c_uint, c_uint]
                                 + [c_vp] * 9 + [c_vp],
 })
@@ -118,6 +122,9 @@ def _os_env(name, default):
 H = 256          # hidden size the fused kernels are built for
 NHEAD = 8
 QKVC = 3 * H + NHEAD * 6
+# spatial_attn_fusion -> `fusion` argument of msr3d_attn_fusion_{fwd,bwd}_f32 (`ctx` is `bias` with spatial weights
+# derived from q: msr3d_spatial_weights_fwd_f32 ctx_mode 1)
+FUSION_CODE = {"cond": 0, "mul": 1, "bias": 2, "ctx": 2, "add": 3}
 
 
 def supported(model) -> Optional[str]:
@@ -128,7 +135,8 @@ def supported(model) -> Optional[str]:
         (c.hidden_size == H, "hidden_size != 256"),
         (se.num_attention_heads == NHEAD, "heads != 8"),
         (bool(c.use_spatial_attn), "use_spatial_attn is off"),
-        (se.spatial_attn_fusion == "cond" and bool(se.spatial_multihead) and se.spatial_dim == 5, "fusion != cond/multihead/dim5"),
+        (se.spatial_attn_fusion in FUSION_CODE and se.spatial_dim == 5, "spatial_attn_fusion / spatial_dim != 5"),
+        (se.spatial_attn_fusion != "cond" or bool(se.spatial_multihead), "cond fusion without spatial_multihead"),
         (se.pairwise_rel_type == "center", "pairwise_rel_type != center"),
         (se.activation == "gelu", "activation != gelu"),
         (se.obj_loc_encoding in ("same_all", "same_0"), "obj_loc_encoding == diff_all"),
@@ -203,6 +211,11 @@ class FusedPrompter:
         se = model.cfg.spatial_encoder
         self.nl, self.F = se.num_layers, se.dim_feedforward
         self.same_all = se.obj_loc_encoding == "same_all"
+        # attention fusion (modules/layers/transformers.py:207-244): `cond` (every shipped config) has the one-launch
+        # attention block and the tensor-core backward; mul / bias / ctx / add run the four-launch path with the
+        # fusion-templated attention kernels and pairwise_loc_fc as spatial weights (csrc/spatial.cu)
+        self.fusion = se.spatial_attn_fusion
+        self.multihead = int(bool(se.spatial_multihead))
         self.dist_norm = int(bool(se.spatial_dist_norm))
         self.p_drop = float(se.dropout)
         self._rehome()
@@ -575,7 +588,9 @@ class FusedPrompter:
                    ptr(w["xhat_l"]), ptr(w["rstd_l"]), ptr(w["xhat_s"]), ptr(w["rstd_s"]), ptr(w["qpos"]), ptr(w["qpos0"]),
                    ptr(w["x_in"][0]), tag="qpos", side=True)
         pre_prog[1:1] = geo                              # geometry first on the side stream
-        use_ab = self.attn_block and bool(_C.lib().msr3d_attn_block_supported(L, NHEAD, H))
+        cond = self.fusion == "cond"
+        fcode, NQ = FUSION_CODE[self.fusion], (QKVC if cond else 3 * H)
+        use_ab = cond and self.attn_block and bool(_C.lib().msr3d_attn_block_supported(L, NHEAD, H))
         self.attn_block_active = use_ab
         if use_ab:
             # operand images of the weights: once per step, beside the input encoders
@@ -609,10 +624,14 @@ class FusedPrompter:
                            ptr(w["xhat_a"][i]), ptr(w["rstd_a"][i]), ptr(w["xhat_1"][i]), ptr(w["rstd_1"][i]),
                            ptr(w["y2"][i]), tag="attn_block")
             else:
-                self._gemm(fwd, x_in, (H, 1), P(sa + "w_qs.weight"), (H, 1), M, QKVC, H, ptr(w["qkvc"][i]), QKVC,
+                self._gemm(fwd, x_in, (H, 1), P(sa + "w_qs.weight"), (H, 1), M, NQ, H, ptr(w["qkvc"][i]), QKVC,
                            bias=P(sa + "w_qs.bias"), accumulate=2, ksplit=ks_h, tag="qkvc")
-                self._call(fwd, "msr3d_attn_fwd_f32", ptr(w["qkvc"][i]), QKVC, ptr(w["pw"]), ptr(w["key_pad"]), B, L, NHEAD,
-                           ptr(w["P"][i]), ptr(w["LOC"][i]), ptr(w["ctx"][i]), H, tag="attn_core")
+                if not cond:      # pairwise_loc_fc -> the spatial-weight columns of the qkvc rows
+                    self._call(fwd, "msr3d_spatial_weights_fwd_f32", P(sa + "pairwise_loc_fc.weight"),
+                               P(sa + "pairwise_loc_fc.bias"), int(self.fusion == "ctx"), self.multihead,
+                               ptr(w["qkvc"][i]), QKVC, M, NHEAD, tag="spatial_w")
+                self._call(fwd, "msr3d_attn_fusion_fwd_f32", ptr(w["qkvc"][i]), QKVC, ptr(w["pw"]), ptr(w["key_pad"]), B, L,
+                           NHEAD, fcode, ptr(w["P"][i]), ptr(w["LOC"][i]), ptr(w["ctx"][i]), H, tag="attn_core")
                 self._gemm(fwd, ptr(w["ctx"][i]), (H, 1), P(sa + "fc.weight"), (H, 1), M, H, H, ptr(w["o"][i]), H,
                            bias=P(sa + "fc.bias"), accumulate=2, ksplit=ks_h, tag="out_proj")
                 self._call(fwd, "msr3d_attn_tail_fwd_f32", ptr(w["o"][i]), x_in, M, P(sa + "layer_norm.weight"),
@@ -704,16 +723,25 @@ class FusedPrompter:
                        accumulate=2, ksplit=ks_h, tag="dctx")
             # attention backward: tensor-core kernel (one CTA per head and scene, csrc/attn_block.cu) when L <= 64
             bwd_tc = self.attn_block_active and _os_env("MSR3D_ATTN_BWD_TC", "1") == "1"
-            self._call(bwd, "msr3d_attn_bwd_tc_f32" if bwd_tc else "msr3d_attn_bwd_f32", ptr(w["dctx"][i]), H,
-                       ptr(w["qkvc"][i]), QKVC, ptr(w["pw"]), ptr(w["P"][i]), ptr(w["LOC"][i]), B, L, NHEAD, dqkvc,
-                       tag="attn_core_bwd")
-            # dWqkvc (816 x H) += dqkvc^T . x_in ; bias [side] ; dx += dqkvc . Wqkvc
-            self._gemm(bwd, dqkvc, (1, QKVC), ptr(w["x_in"][i]), (1, H), QKVC, H, M, G(sa + "w_qs.weight"), H,
+            if cond:
+                self._call(bwd, "msr3d_attn_bwd_tc_f32" if bwd_tc else "msr3d_attn_bwd_f32", ptr(w["dctx"][i]), H,
+                           ptr(w["qkvc"][i]), QKVC, ptr(w["pw"]), ptr(w["P"][i]), ptr(w["LOC"][i]), B, L, NHEAD, dqkvc,
+                           tag="attn_core_bwd")
+            else:
+                self._call(bwd, "msr3d_attn_fusion_bwd_f32", ptr(w["dctx"][i]), H, ptr(w["qkvc"][i]), QKVC, ptr(w["pw"]),
+                           ptr(w["P"][i]), ptr(w["LOC"][i]), B, L, NHEAD, fcode, dqkvc, tag="attn_core_bwd")
+                # d(spatial weights) -> pairwise_loc_fc gradients (ctx: plus its share of dq)
+                self._call(bwd, "msr3d_spatial_weights_bwd_f32", P(sa + "pairwise_loc_fc.weight"),
+                           P(sa + "pairwise_loc_fc.bias"), int(self.fusion == "ctx"), self.multihead, ptr(w["qkvc"][i]),
+                           dqkvc, QKVC, M, NHEAD, G(sa + "pairwise_loc_fc.weight"), G(sa + "pairwise_loc_fc.bias"),
+                           tag="spatial_w_bwd")
+            # dWqkvc (816 x H) += dqkvc^T . x_in ; bias [side] ; dx += dqkvc . Wqkvc     (768 rows without `cond`)
+            self._gemm(bwd, dqkvc, (1, QKVC), ptr(w["x_in"][i]), (1, H), NQ, H, M, G(sa + "w_qs.weight"), H,
                        accumulate=2, ksplit=4, tag="dWqkvc", wgrad=True, side=2)
-            self._call(bwd, "msr3d_colsum_add_f32", dqkvc, QKVC, M, QKVC, G(sa + "w_qs.bias"), None, None,
+            self._call(bwd, "msr3d_colsum_add_f32", dqkvc, QKVC, M, NQ, G(sa + "w_qs.bias"), None, None,
                        tag="dbqkvc", side=2)
-            self._gemm(bwd, dqkvc, (QKVC, 1), P(sa + "w_qs.weight"), (1, H), M, H, QKVC, dx, H,
-                       accumulate=2, ksplit=max(1, -(-QKVC // 64)), tag="dx")
+            self._gemm(bwd, dqkvc, (QKVC, 1), P(sa + "w_qs.weight"), (1, H), M, H, NQ, dx, H,
+                       accumulate=2, ksplit=max(1, -(-NQ // 64)), tag="dx")
             dy3 = dx
         dx0 = ptr(w["dx"][0])
         # x_in0 = emb Wp^T + bp + orientation_feat + type_emb[0] + qpos

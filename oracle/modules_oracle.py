@@ -257,7 +257,8 @@ def ose3d_situation(sd: SD, data: dict, *, n_head: int = 8, num_layers: int = 3,
                     activation: str = "gelu", spatial_dist_norm: bool = True,
                     sa_n_points=(32, 16, None), sa_n_samples=(32, 32, None),
                     sa_radii=(0.2, 0.4, None), obj_embeds: Optional[torch.Tensor] = None,
-                    trace: Optional[dict] = None, layer_masks: Optional[list] = None):
+                    trace: Optional[dict] = None, layer_masks: Optional[list] = None,
+                    spatial_multihead: bool = True):
     """OSE3DSituation.forward (model/ose3d_situation.py:288-454) for vision_backbone
     'gtpcd', use_spatial_attn/use_anchor/use_orientation True, attn_flat off, and
     situation_type in {'as_transform_for_objects' (shipped, configs/msr3d.yaml:177),
@@ -302,7 +303,8 @@ def ose3d_situation(sd: SD, data: dict, *, n_head: int = 8, num_layers: int = 3,
         if obj_loc_encoding in ("same_all", "diff_all") or i == 0:
             x = x + qpos
         x, att = spatial_encoder_layer(sd, f"spatial_encoder.{i}", x, pairwise, mask, n_head,
-                                       fusion, activation, masks=layer_masks[i] if layer_masks else None)
+                                       fusion, activation, spatial_multihead,
+                                       masks=layer_masks[i] if layer_masks else None)
         if trace is not None:
             trace[f"layer{i}.out"] = x
             trace[f"layer{i}.attn"] = att

@@ -66,8 +66,8 @@ def build_model(ref, situation_type, seed, fusion="cond"):
     return model, spec
 
 
-def run_case(ref, name, B, O, P, seed, situation_type="as_transform_for_objects", with_grad=True):
-    model, spec = build_model(ref, situation_type, seed)
+def run_case(ref, name, B, O, P, seed, situation_type="as_transform_for_objects", with_grad=True, fusion="cond"):
+    model, spec = build_model(ref, situation_type, seed, fusion)
     batch = synthetic.make_batch(B, O, P, seed=seed)
     log, orig_ext = record_ext(ref)
     layer_out = []
@@ -108,7 +108,8 @@ def run_case(ref, name, B, O, P, seed, situation_type="as_transform_for_objects"
                 names.append(n)
                 norms.append(float(p.grad.norm()))
                 sums.append(float(p.grad.double().sum()))
-                if p.numel() <= 4096 or n in ("spatial_encoder.0.self_attn.lang_cond_fc.weight",):
+                if p.numel() <= 4096 or n in ("spatial_encoder.0.self_attn.lang_cond_fc.weight",) \
+                        or n.endswith("pairwise_loc_fc.weight"):
                     fix["grad:" + n] = p.grad.numpy().copy()
         fix["grad_names"] = np.array(names)
         fix["grad_norms"] = np.array(norms, dtype=np.float64)
@@ -145,8 +146,18 @@ def run_mha_cases(ref):
     print("mha_fusions ok")
 
 
+def run_fusion_cases(ref):
+    """Whole prompter (forward + backward) with the four fusions no shipped config uses: the fixtures the
+    fused engine's fusion-templated attention kernels are checked against (tests/test_modes_gpu.py)."""
+    for k, fusion in enumerate(("mul", "bias", "ctx", "add")):
+        run_case(ref, f"prompter_fusion_{fusion}", 1, 8, 256, seed=5005 + k, fusion=fusion)
+
+
 def main():
     ref = refshim.load()
+    if "--fusions" in sys.argv:          # only the fixtures added in round 2 (the others stay byte-stable)
+        run_fusion_cases(ref)
+        return
     spec = run_case(ref, "prompter_cfg1", 1, 8, 256, seed=1001)
     with open(os.path.join(HERE, "state_dict_spec.json"), "w") as fh:
         json.dump(spec, fh, indent=0)

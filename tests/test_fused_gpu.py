@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
-def _oracle_grads(sd, batch, up, layer_masks=None, obj_embeds=None, dtype=torch.float64):
+def _oracle_grads(sd, batch, up, layer_masks=None, obj_embeds=None, dtype=torch.float64, **okw):
     """Oracle forward + autograd.  The frozen encoder runs in fp32 (as the reference does); the
     trainable transformer half runs in `dtype` — float64 by default, because some gradients
     (lang_cond_fc: sums of softmax-logit gradients that cancel to ~0 per row) are ill-conditioned
@@ -27,7 +27,7 @@ def _oracle_grads(sd, batch, up, layer_masks=None, obj_embeds=None, dtype=torch.
     data = {k: cast(v) for k, v in batch.as_dict().items()}
     if layer_masks is not None:
         layer_masks = [{k: cast(v) for k, v in m.items()} for m in layer_masks]
-    tokens, _ = mo.ose3d_situation(sdg, data, layer_masks=layer_masks, obj_embeds=cast(obj_embeds))
+    tokens, _ = mo.ose3d_situation(sdg, data, layer_masks=layer_masks, obj_embeds=cast(obj_embeds), **okw)
     (tokens * cast(up)).sum().backward()
     grads = {k: (v.grad.float() if v.grad is not None else None) for k, v in sdg.items()
              if isinstance(v, torch.Tensor) and v.requires_grad}

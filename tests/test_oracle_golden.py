@@ -43,6 +43,31 @@ def test_prompter_forward_matches_reference(golden_dir, sd_spec, name):
     np.testing.assert_array_equal(masks.numpy(), fx["obj_masks_out"])
 
 
+@pytest.mark.parametrize("fusion", ["mul", "bias", "ctx", "add"])
+def test_prompter_other_fusions_match_reference(golden_dir, fusion):
+    """Whole prompter, forward + backward, with the fusions no shipped config uses against the
+    unmodified reference (gen_golden.py --fusions)."""
+    from msr3d_b200 import configs
+    fx = _load(golden_dir, f"prompter_fusion_{fusion}")
+    seed = int(fx["seed"])
+    sd = configs.model_state_dict(configs.build_prompter(0, fusion=fusion), seed)
+    frozen = lambda k: k.startswith("obj_encoder.") or k == "anchor_size"
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not frozen(k) else v) for k, v in sd.items()}
+    batch = synthetic.make_batch(int(fx["B"]), int(fx["O"]), int(fx["P"]), seed=seed)
+    ext_oracle.set_threads(4)
+    tokens, _ = mo.ose3d_situation(sd, batch.as_dict(), fusion=fusion)
+    np.testing.assert_allclose(tokens.detach().numpy(), fx["obj_tokens"], rtol=1e-4, atol=1e-4)
+    G = torch.randn(tokens.shape, generator=torch.Generator().manual_seed(seed + 77))
+    (tokens * G).sum().backward()
+    for n, norm in zip([str(n) for n in fx["grad_names"]], fx["grad_norms"]):
+        assert sd[n].grad is not None, n
+        assert abs(float(sd[n].grad.norm()) - norm) <= 1e-3 * max(norm, 1e-3), n
+    for key in fx.files:
+        if key.startswith("grad:"):
+            ref = fx[key]
+            assert np.abs(sd[key[5:]].grad.numpy() - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-3), key
+
+
 def test_encoder_outputs_match_reference(golden_dir, sd_spec):
     fx = _load(golden_dir, "prompter_cfg1")
     seed = int(fx["seed"])
