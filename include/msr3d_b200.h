@@ -320,6 +320,29 @@ int msr3d_spatial_weights_fwd_f32(const float *W, const float *b, int ctx_mode, 
 int msr3d_spatial_weights_bwd_f32(const float *W, const float *b, int ctx_mode, int multihead, const float *qkvc,
                                   float *dqkvc, int ldq, int M, int H, float *dW, float *db,
                                   msr3d_stream_t stream);
+/* Situation modes with an agent token in front of the objects: as_object, as_object_add_loc
+ * (model/ose3d_situation.py:334-363, 385-396; csrc/modes.cu).  Tokens per scene L + 1, row 0 = the agent.
+ *   anchor_inputs:  all_loc (B, L+1, 6) = [(anchor_locs, anchor_size); obj_locs], key_pad (B, L+1) = [0; !obj_masks]
+ *   loc_layer_*:    qpos = LN(Linear_6(all_loc)) (loc_layers[0]); forward also stores qpos as the first term of x0
+ *   anchor_assemble:    x0[object row] += proj + object_orientation_feat + type_embedding[0];
+ *                       x0[agent row]  += anchor_feat + orientation_encoder(fourier(anchor_orientation)) + type_embedding[1]
+ *   anchor_disassemble: dproj (B*L, 256) = object rows of dx0; ACCUMULATES d anchor_feat, d type_embedding[1],
+ *                       d orientation_encoder.{weight (256, 84), bias} from the agent rows (fixed order). */
+int msr3d_anchor_inputs(const float *obj_locs, const unsigned char *obj_masks, const float *anchor_locs,
+                        const float *anchor_size, int B, int L, float *all_loc, unsigned char *key_pad,
+                        msr3d_stream_t stream);
+int msr3d_loc_layer_fwd_f32(const float *all_loc, int M, const float *W6, const float *b6, const float *gamma,
+                            const float *beta, float *xhat, float *rstd, float *qpos, float *x0,
+                            msr3d_stream_t stream);
+int msr3d_loc_layer_bwd_f32(const float *dq, const float *dq1, const float *dq2, const float *all_loc, int M,
+                            const float *gamma, const float *xhat, const float *rstd, float *dgamma, float *dbeta,
+                            float *dW6, float *db6, msr3d_stream_t stream);
+int msr3d_anchor_assemble_f32(float *x0, const float *proj, const float *ori_feat, const float *type_w,
+                              const float *anchor_feat, const float *W_ori, const float *b_ori,
+                              const float *anchor_ori, int B, int L, msr3d_stream_t stream);
+int msr3d_anchor_disassemble_f32(const float *dx0, const float *anchor_ori, int B, int L, float *dproj,
+                                 float *d_anchor_feat, float *d_type1, float *dW_ori, float *db_ori,
+                                 msr3d_stream_t stream);
 /* Same contract as msr3d_attn_bwd_f32 on the tensor cores (csrc/attn_block.cu: dP, dq, dk, dv as tcgen05 kind::tf32
  * 3xTF32 products, one CTA per (head, scene)); requires L <= 64, 8 heads, ldq = 816. */
 int msr3d_attn_bwd_tc_f32(const float *dctx, int ldc, const float *qkvc, int ldq, const float *pw, const float *P,

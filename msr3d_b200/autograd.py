@@ -106,3 +106,10 @@ def fused_forward(module, data_dict) -> torch.Tensor:
     params = [eng.by_name[n] for n in eng.autograd_names]
     return _FusedPrompterFn.apply(module, eng, data_dict["obj_fts"], data_dict["obj_locs"], data_dict["obj_masks"],
                                   data_dict["anchor_locs"], data_dict["anchor_orientation"], *params)
+
+
+def token_masks(module, data_dict) -> torch.Tensor:
+    """obj_masks of the call's output (ose3d_situation.py:452): the input's, with the agent token in front in the
+    as_object / as_object_add_loc modes."""
+    eng = _engine(module)
+    return eng.token_masks().clone() if eng.n_anchor else data_dict["obj_masks"].clone()

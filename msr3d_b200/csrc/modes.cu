@@ -1,0 +1,265 @@
+// Situation modes with an agent ("anchor") token in front of the objects: as_object and as_object_add_loc
+// (model/ose3d_situation.py:334-363, 385-395, 429-431).  The transformer layers are the ones of the
+// shipped mode with L + 1 tokens per scene; what differs is the input assembly and its backward:
+//   all_loc   = [ (anchor_locs, anchor_size) ; obj_locs ]                       (B, L+1, 6)
+//   key_pad   = [ 0 ; !obj_masks ]                                             (B, L+1)
+//   x_in0 row = projected embedding + object_orientation_feat + type_embedding[0] + qpos        (object rows)
+//             = anchor_feat + orientation_encoder(fourier(anchor_orientation)) + type_embedding[1] + qpos   (row 0)
+//   qpos      = LN(Linear_6(all_loc))  (as_object: loc_layers[0])  |  the Fourier + size encoders without the
+//               agent-frame transform (as_object_add_loc: geometry_kernel use_agent_frame = 0 + qpos_fwd_kernel)
+// All kernels: one warp per token row of kD = 256 values (rowops.cuh), deterministic parameter gradients apart
+// from the per-column shared-memory accumulators the shipped mode uses too.
+#include "common.cuh"
+#include "rowops.cuh"
+
+namespace msr3d {
+
+constexpr int kOriFeat = 84;   // generate_fourier_features of a quaternion: 4 + 4 * 10 * 2 (ose3d_situation.py:31-59)
+
+// Fourier features of the scene's anchor quaternion, [q(4) | sin(pi q_d f_j) d-major (40) | cos (40)], by one warp.
+__device__ __forceinline__ void anchor_fourier(const float *q, int lane, float *f /* shared [84] */) {
+  for (int e = lane; e < 40; e += 32) {
+    const int d = e / 10, j = e % 10;
+    const float kPi = 3.14159265358979323846f;
+    const float step = 14.f / 9.f;     // torch.linspace(1, 15, 10), as in geometry_kernel
+    const float fr = j < 5 ? 1.f + j * step : 15.f - (9 - j) * step;
+    float sn, cs;
+    sincosf(kPi * (q[d] * fr), &sn, &cs);
+    f[4 + e] = sn;
+    f[44 + e] = cs;
+  }
+  if (lane < 4) f[lane] = q[lane];
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(256)
+anchor_inputs_kernel(const float *__restrict__ obj_locs, const unsigned char *__restrict__ obj_masks,
+                     const float *__restrict__ anchor_locs, const float *__restrict__ anchor_size, int B, int L,
+                     float *__restrict__ all_loc, unsigned char *__restrict__ key_pad) {
+  pdl_sync();
+  const int Lt = L + 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;    // token
+  if (i >= B * Lt) return;
+  const int b = i / Lt, t = i % Lt;
+  float *o = all_loc + (size_t)i * 6;
+  if (t == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { o[d] = anchor_locs[b * 3 + d]; o[3 + d] = anchor_size[d]; }
+    key_pad[i] = 0;
+  } else {
+    const float *p = obj_locs + ((size_t)b * L + t - 1) * 6;
+#pragma unroll
+    for (int d = 0; d < 6; ++d) o[d] = p[d];
+    key_pad[i] = obj_masks[b * L + t - 1] ? 0 : 1;
+  }
+}
+
+// qpos = LN(W6 loc + b6) for every token (as_object: loc_layers[0], ose3d_situation.py:396); x0 (zero-filled layer-0
+// input) receives it as its first term.
+__global__ void __launch_bounds__(kLnWarps * 32)
+loc_layer_fwd_kernel(const float *__restrict__ all_loc, int M, const float *__restrict__ W6,
+                     const float *__restrict__ b6, LnParams ln, float *__restrict__ xhat, float *__restrict__ rstd,
+                     float *__restrict__ qpos, float *__restrict__ x0) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const size_t base = (size_t)row * kD;
+  float l[6];
+#pragma unroll
+  for (int d = 0; d < 6; ++d) l[d] = all_loc[(size_t)row * 6 + d];
+  Row8 a;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = col8(lane, i);
+    float s = b6[c];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) s += W6[c * 6 + d] * l[d];
+    a.v[i] = s;
+  }
+  float r;
+  const Row8 y = ln_forward(a, ln.gamma, ln.beta, lane, r);
+  row_store(xhat + base, lane, a);
+  row_store(qpos + base, lane, y);
+  row_store(x0 + base, lane, y);
+  if (lane == 0) rstd[row] = r;
+}
+
+// Backward: g = sum of the per-layer gradients wrt qpos; dgamma, dbeta, dW6 (256 x 6), db6.
+__global__ void __launch_bounds__(kLnWarps * 32)
+loc_layer_bwd_kernel(const float *__restrict__ dq, const float *__restrict__ dq1, const float *__restrict__ dq2,
+                     const float *__restrict__ all_loc, int M, LnParams ln, const float *__restrict__ xhat,
+                     const float *__restrict__ rstd, float *__restrict__ dgamma, float *__restrict__ dbeta,
+                     float *__restrict__ dW6, float *__restrict__ db6) {
+  pdl_sync();
+  __shared__ float s_acc[9 * kD];
+  ColAcc acc{s_acc};
+  acc.zero(9, threadIdx.x);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row < M) {
+    const size_t base = (size_t)row * kD;
+    Row8 g = row_load(dq + base, lane);
+    if (dq1 != nullptr) {
+      const Row8 e = row_load(dq1 + base, lane);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g.v[i] += e.v[i];
+    }
+    if (dq2 != nullptr) {
+      const Row8 e = row_load(dq2 + base, lane);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g.v[i] += e.v[i];
+    }
+    const Row8 h = row_load(xhat + base, lane);
+    Row8 t;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t.v[i] = g.v[i] * h.v[i];
+    acc.add(0, lane, t);
+    acc.add(1, lane, g);
+    const Row8 d1 = ln_backward(g, h, ln.gamma, lane, rstd[row]);
+    acc.add(2, lane, d1);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+      const float ld = all_loc[(size_t)row * 6 + d];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t.v[i] = d1.v[i] * ld;
+      acc.add(3 + d, lane, t);
+    }
+  }
+  __syncthreads();
+  acc.flush(0, dgamma, threadIdx.x);
+  acc.flush(1, dbeta, threadIdx.x);
+  acc.flush(2, db6, threadIdx.x);
+  for (int c = threadIdx.x; c < kD; c += kLnWarps * 32)
+#pragma unroll
+    for (int d = 0; d < 6; ++d) atomicAdd(dW6 + c * 6 + d, acc.get(3 + d, c));
+}
+
+// x0[token] += the mode's constant terms (+ the projected embedding for object rows).  Runs after the projection
+// GEMM and the query-position kernels (stream order), so a plain read-modify-write is enough.
+__global__ void __launch_bounds__(kLnWarps * 32)
+anchor_assemble_kernel(float *__restrict__ x0, const float *__restrict__ proj, const float *__restrict__ ori_feat,
+                       const float *__restrict__ type_w, const float *__restrict__ anchor_feat,
+                       const float *__restrict__ W_ori, const float *__restrict__ b_ori,
+                       const float *__restrict__ anchor_ori, int B, int L) {
+  pdl_sync();
+  __shared__ float s_f[kLnWarps][kOriFeat];
+  const int Lt = L + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * kLnWarps + warp;
+  if (row >= B * Lt) return;
+  const int b = row / Lt, t = row % Lt;
+  const size_t base = (size_t)row * kD;
+  Row8 x = row_load(x0 + base, lane);
+  if (t > 0) {
+    const Row8 p = row_load(proj + ((size_t)b * L + t - 1) * kD, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = col8(lane, i);
+      x.v[i] += (p.v[i] + ori_feat[c]) + type_w[c];
+    }
+  } else {
+    float *f = s_f[warp];
+    anchor_fourier(anchor_ori + (size_t)b * 4, lane, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = col8(lane, i);
+      float s = b_ori[c];
+      for (int j = 0; j < kOriFeat; ++j) s += W_ori[(size_t)c * kOriFeat + j] * f[j];
+      x.v[i] += (anchor_feat[c] + s) + type_w[kD + c];
+    }
+  }
+  row_store(x0 + base, lane, x);
+}
+
+// Backward of the assembly.  CTAs 0 .. n-1: object rows of dx0 -> compact dproj (B*L, 256) (operand of the projection's
+// weight-gradient GEMM and of the column sums behind its bias / object_orientation_feat / type_embedding[0]).
+// Last CTA (thread = column): anchor rows -> d anchor_feat, d type_embedding[1], d orientation_encoder (weight, bias),
+// summed over the scenes in a fixed order.
+__global__ void __launch_bounds__(kLnWarps * 32)
+anchor_disassemble_kernel(const float *__restrict__ dx0, const float *__restrict__ anchor_ori, int B, int L,
+                          float *__restrict__ dproj, float *__restrict__ d_anchor_feat, float *__restrict__ d_type1,
+                          float *__restrict__ dW_ori, float *__restrict__ db_ori) {
+  pdl_sync();
+  const int Lt = L + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (blockIdx.x + 1 < gridDim.x) {
+    const int r = blockIdx.x * kLnWarps + warp;      // object row
+    if (r >= B * L) return;
+    const int b = r / L, o = r % L;
+    row_store(dproj + (size_t)r * kD, lane, row_load(dx0 + ((size_t)b * Lt + 1 + o) * kD, lane));
+    return;
+  }
+  __shared__ float s_f[kOriFeat];
+  const int c = threadIdx.x;             // kLnWarps * 32 = 256 = kD
+  float gsum = 0.f;
+  for (int b = 0; b < B; ++b) {
+    __syncthreads();
+    if (warp == 0) anchor_fourier(anchor_ori + (size_t)b * 4, lane, s_f);
+    __syncthreads();
+    const float g = dx0[(size_t)b * Lt * kD + c];
+    gsum += g;
+    for (int j = 0; j < kOriFeat; ++j) dW_ori[(size_t)c * kOriFeat + j] += g * s_f[j];
+  }
+  d_anchor_feat[c] += gsum;
+  d_type1[c] += gsum;
+  db_ori[c] += gsum;
+}
+
+}  // namespace msr3d
+
+using namespace msr3d;
+
+MSR3D_API int msr3d_anchor_inputs(const float *obj_locs, const unsigned char *obj_masks, const float *anchor_locs,
+                                  const float *anchor_size, int B, int L, float *all_loc, unsigned char *key_pad,
+                                  msr3d_stream_t stream) {
+  MSR3D_REQUIRE(obj_locs && obj_masks && anchor_locs && anchor_size && all_loc && key_pad, "anchor_inputs: null pointer");
+  MSR3D_REQUIRE(B >= 0 && L >= 1 && L + 1 <= kMaxL, "anchor_inputs: L=%d must be in [1,%d]", L, kMaxL - 1);
+  if (B == 0) return MSR3D_OK;
+  launch_pdl(anchor_inputs_kernel, dim3(ceil_div(B * (L + 1), 256)), dim3(256), 0, (cudaStream_t)stream, obj_locs,
+             obj_masks, anchor_locs, anchor_size, B, L, all_loc, key_pad);
+  return check_launch("anchor_inputs");
+}
+
+MSR3D_API int msr3d_loc_layer_fwd_f32(const float *all_loc, int M, const float *W6, const float *b6,
+                                      const float *gamma, const float *beta, float *xhat, float *rstd, float *qpos,
+                                      float *x0, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(all_loc && W6 && b6 && gamma && beta && xhat && rstd && qpos && x0, "loc_layer_fwd: null pointer");
+  if (M <= 0) return MSR3D_OK;
+  launch_pdl(loc_layer_fwd_kernel, dim3(ceil_div(M, kLnWarps)), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, all_loc, M,
+             W6, b6, LnParams{gamma, beta}, xhat, rstd, qpos, x0);
+  return check_launch("loc_layer_fwd");
+}
+
+MSR3D_API int msr3d_loc_layer_bwd_f32(const float *dq, const float *dq1, const float *dq2, const float *all_loc, int M,
+                                      const float *gamma, const float *xhat, const float *rstd, float *dgamma,
+                                      float *dbeta, float *dW6, float *db6, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(dq && all_loc && gamma && xhat && rstd && dgamma && dbeta && dW6 && db6, "loc_layer_bwd: null pointer");
+  if (M <= 0) return MSR3D_OK;
+  launch_pdl(loc_layer_bwd_kernel, dim3(ceil_div(M, kLnWarps)), dim3(kLnWarps * 32), 0, (cudaStream_t)stream, dq, dq1,
+             dq2, all_loc, M, LnParams{gamma, nullptr}, xhat, rstd, dgamma, dbeta, dW6, db6);
+  return check_launch("loc_layer_bwd");
+}
+
+MSR3D_API int msr3d_anchor_assemble_f32(float *x0, const float *proj, const float *ori_feat, const float *type_w,
+                                        const float *anchor_feat, const float *W_ori, const float *b_ori,
+                                        const float *anchor_ori, int B, int L, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(x0 && proj && ori_feat && type_w && anchor_feat && W_ori && b_ori && anchor_ori,
+                "anchor_assemble: null pointer");
+  if (B <= 0) return MSR3D_OK;
+  launch_pdl(anchor_assemble_kernel, dim3(ceil_div(B * (L + 1), kLnWarps)), dim3(kLnWarps * 32), 0, (cudaStream_t)stream,
+             x0, proj, ori_feat, type_w, anchor_feat, W_ori, b_ori, anchor_ori, B, L);
+  return check_launch("anchor_assemble");
+}
+
+MSR3D_API int msr3d_anchor_disassemble_f32(const float *dx0, const float *anchor_ori, int B, int L, float *dproj,
+                                           float *d_anchor_feat, float *d_type1, float *dW_ori, float *db_ori,
+                                           msr3d_stream_t stream) {
+  MSR3D_REQUIRE(dx0 && anchor_ori && dproj && d_anchor_feat && d_type1 && dW_ori && db_ori,
+                "anchor_disassemble: null pointer");
+  if (B <= 0) return MSR3D_OK;
+  launch_pdl(anchor_disassemble_kernel, dim3(ceil_div(B * L, kLnWarps) + 1), dim3(kLnWarps * 32), 0,
+             (cudaStream_t)stream, dx0, anchor_ori, B, L, dproj, d_anchor_feat, d_type1, dW_ori, db_ori);
+  return check_launch("anchor_disassemble");
+}

@@ -17,7 +17,8 @@ import torch.distributed as dist
 UNUSED_IN_SHIPPED_MODE = ("anchor_feat", "orientation_encoder.", "loc_layers.")
 
 
-def flat_order(names: Sequence[str], num_layers: int) -> Tuple[List[str], List[str], List[str]]:
+def flat_order(names: Sequence[str], num_layers: int,
+               unused: Sequence[str] = UNUSED_IN_SHIPPED_MODE) -> Tuple[List[str], List[str], List[str]]:
     """Order of the trainable parameters in the flat buffers: (weights, biases, never-used).  The four
     input projections of each attention block are adjacent so QKV+cond is a single GEMM.  Weights and
     biases are kept in separate ranges so that the OPT-IN no-decay rule (names containing 'bias',
@@ -35,7 +36,7 @@ def flat_order(names: Sequence[str], num_layers: int) -> Tuple[List[str], List[s
     for n in names:
         if n in taken:
             continue
-        if n.startswith(UNUSED_IN_SHIPPED_MODE):
+        if unused and n.startswith(tuple(unused)):
             order_u.append(n)
         elif "bias" in n:
             order_b.append(n)
@@ -52,7 +53,8 @@ def is_late(name: str) -> bool:
     return (not name.startswith("spatial_encoder.")) or name.startswith("spatial_encoder.0.")
 
 
-def flat_layout(names: Sequence[str], numel: Dict[str, int], num_layers: int, no_decay_bias: bool = False) -> dict:
+def flat_layout(names: Sequence[str], numel: Dict[str, int], num_layers: int, no_decay_bias: bool = False,
+                unused: Sequence[str] = UNUSED_IN_SHIPPED_MODE) -> dict:
     """Layout of the flat parameter / gradient buffers:
 
         [ late biases | late weights | early weights | early biases | never-used ]
@@ -66,7 +68,7 @@ def flat_layout(names: Sequence[str], numel: Dict[str, int], num_layers: int, no
     model/msr3d/msr3d.py:165-172 -> AdamW(weight_decay=0.05), optim/build.py:7-17), i.e. biases and
     LayerNorm parameters decay too: decay = (0, n_opt).  no_decay_bias=True restricts it to the weight
     range (what optim/utils.py:no_decay_param_group would do if the reference called it)."""
-    w, b, u = flat_order(names, num_layers)
+    w, b, u = flat_order(names, num_layers, unused)
     b_late, b_early = [n for n in b if is_late(n)], [n for n in b if not is_late(n)]
     w_late, w_early = [n for n in w if is_late(n)], [n for n in w if not is_late(n)]
     order = b_late + w_late + w_early + b_early + u

@@ -106,6 +106,11 @@ _C.register_protos({
     "msr3d_ffn_tail_bwd_ps_f32": [c_vp, c_int, c_vp, c_ull, c_vp, c_float, c_uint, c_vp, c_vp,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_attn_block_supported": [c_int, c_int, c_int],
+    "msr3d_anchor_inputs": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp],
+    "msr3d_loc_layer_fwd_f32": [c_vp, c_int] + [c_vp] * 8 + [c_vp],
+    "msr3d_loc_layer_bwd_f32": [c_vp, c_vp, c_vp, c_vp, c_int] + [c_vp] * 7 + [c_vp],
+    "msr3d_anchor_assemble_f32": [c_vp] * 8 + [c_int, c_int, c_vp],
+    "msr3d_anchor_disassemble_f32": [c_vp, c_vp, c_int, c_int] + [c_vp] * 5 + [c_vp],
     "msr3d_attn_fusion_fwd_f32": [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp],
     "msr3d_attn_fusion_bwd_f32": [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
     "msr3d_spatial_weights_fwd_f32": [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp],
@@ -124,6 +129,8 @@ NHEAD = 8
 QKVC = 3 * H + NHEAD * 6
 # spatial_attn_fusion -> `fusion` argument of msr3d_attn_fusion_{fwd,bwd}_f32 (`ctx` is `bias` with spatial weights
 # derived from q: msr3d_spatial_weights_fwd_f32 ctx_mode 1)
+# situation modes that put an agent ("anchor") token in front of the objects (ose3d_situation.py:334-357; csrc/modes.cu)
+ANCHOR_MODES = ("as_object", "as_object_add_loc")
 FUSION_CODE = {"cond": 0, "mul": 1, "bias": 2, "ctx": 2, "add": 3}
 
 
@@ -140,11 +147,13 @@ def supported(model) -> Optional[str]:
         (se.pairwise_rel_type == "center", "pairwise_rel_type != center"),
         (se.activation == "gelu", "activation != gelu"),
         (se.obj_loc_encoding in ("same_all", "same_0"), "obj_loc_encoding == diff_all"),
-        (model.situation_type == "as_transform_for_objects", f"situation_type {model.situation_type}"),
+        (model.situation_type in ("as_transform_for_objects",) + ANCHOR_MODES, f"situation_type {model.situation_type}"),
+        (model.situation_type not in ANCHOR_MODES or bool(c.use_anchor), "anchor mode without use_anchor"),
+        (model.situation_type == "as_object" or c.loc_fourier_dim == 63, "loc_fourier_dim != 63"),
+        (model.situation_type != "as_object" or se.dim_loc == 6, "dim_loc != 6"),
         (not c.attn_flat.use_attn_flat, "attn_flat on"),
         (bool(c.use_orientation), "use_orientation off"),
         (c.vision.name == "PcdObjEncoder", "vision backbone is not PcdObjEncoder"),
-        (c.loc_fourier_dim == 63, "loc_fourier_dim != 63"),
         (se.dim_feedforward % 64 == 0, "dim_feedforward % 64"),
         # the engine runs the encoder without autograd: an unfrozen encoder must use the module tree
         (hasattr(model, "obj_encoder") and all(not p.requires_grad for p in model.obj_encoder.parameters()),
@@ -215,6 +224,9 @@ class FusedPrompter:
         # attention block and the tensor-core backward; mul / bias / ctx / add run the four-launch path with the
         # fusion-templated attention kernels and pairwise_loc_fc as spatial weights (csrc/spatial.cu)
         self.fusion = se.spatial_attn_fusion
+        # situation mode: the shipped as_transform_for_objects, or one of the agent-token modes (tokens per scene = L + 1)
+        self.stype = model.situation_type
+        self.n_anchor = 1 if self.stype in ANCHOR_MODES else 0
         self.multihead = int(bool(se.spatial_multihead))
         self.dist_norm = int(bool(se.spatial_dist_norm))
         self.p_drop = float(se.dropout)
@@ -289,8 +301,10 @@ class FusedPrompter:
         n_model = len(named)
         named += [("ext." + k, p) for k, p in self.extra_params.items() if p.requires_grad]
         by_name = dict(named)
+        # parameters the configured situation mode never touches (neither reduced nor updated)
+        unused = {"as_object": (), "as_object_add_loc": ("loc_layers.",)}.get(self.stype, _dist.UNUSED_IN_SHIPPED_MODE)
         lay = _dist.flat_layout([n for n, _ in named], {n: p.numel() for n, p in named}, self.nl,
-                                no_decay_bias=self.no_decay_bias)
+                                no_decay_bias=self.no_decay_bias, unused=unused)
         self.order, offs, total = lay["order"], lay["offs"], lay["total"]
         self.decay_range = lay["decay"]          # [d0, d1): decayed elements (everything optimised by default)
         self.bucket_early = lay["early"]         # gradients of layers >= 1: complete before layer 0's backward
@@ -428,13 +442,18 @@ class FusedPrompter:
 
     def _build(self, B, L, O_pts):
         """Allocate static buffers and pre-bind every launch for (B scenes, L objects, P points)."""
+        Lo = L                       # objects per scene; L = tokens per scene from here on
+        L = Lo + self.n_anchor
         M, F, nl = B * L, self.F, self.nl
         f = self._buf
         w = self.ws = {}
-        w["obj_fts"] = f(B, L, O_pts, 6)
-        w["obj_locs"] = f(B, L, 6)
-        w["obj_masks"] = torch.ones(B, L, dtype=torch.bool, device=self.dev)
+        w["obj_fts"] = f(B, Lo, O_pts, 6)
+        w["obj_locs"] = f(B, Lo, 6)
+        w["obj_masks"] = torch.ones(B, Lo, dtype=torch.bool, device=self.dev)
         w["key_pad"] = torch.zeros(B, L, dtype=torch.uint8, device=self.dev)
+        if self.n_anchor:
+            w["all_loc"] = f(B, L, 6)
+            w["proj"], w["dproj"] = f(B * Lo, H), f(B * Lo, H)
         w["anchor_locs"] = f(B, 3)
         w["anchor_ori"] = f(B, 4)
         w["upstream"] = f(M, H)
@@ -491,17 +510,17 @@ class FusedPrompter:
         w["dx"] = [f(M, H) for _ in range(nl)]
         # pipelined mode: the frozen encoder of the NEXT batch overlaps the transformer step of the current one
         w["emb_next"] = None   # allocated in prepare() once the embedding width is known
-        w["obj_locs_n"], w["anchor_locs_n"], w["anchor_ori_n"] = f(B, L, 6), f(B, 3), f(B, 4)
-        w["obj_masks_n"] = torch.ones(B, L, dtype=torch.bool, device=self.dev)
+        w["obj_locs_n"], w["anchor_locs_n"], w["anchor_ori_n"] = f(B, Lo, 6), f(B, 3), f(B, 4)
+        w["obj_masks_n"] = torch.ones(B, Lo, dtype=torch.bool, device=self.dev)
         w["upstream_n"] = f(M, H)
         # prefetch mode (two batches in flight ahead of the transformer step): a second point-cloud slot
         # filled by an asynchronous H2D copy, and a second level of staged per-scene inputs
-        w["obj_fts_b"] = f(B, L, O_pts, 6)
+        w["obj_fts_b"] = f(B, Lo, O_pts, 6)
         for q in ("_q0", "_q1"):    # one per slot: the copy stream fills one while the step reads the other
-            w["obj_locs" + q], w["anchor_locs" + q], w["anchor_ori" + q] = f(B, L, 6), f(B, 3), f(B, 4)
-            w["obj_masks" + q] = torch.ones(B, L, dtype=torch.bool, device=self.dev)
+            w["obj_locs" + q], w["anchor_locs" + q], w["anchor_ori" + q] = f(B, Lo, 6), f(B, 3), f(B, 4)
+            w["obj_masks" + q] = torch.ones(B, Lo, dtype=torch.bool, device=self.dev)
             w["upstream" + q] = f(M, H)
-        self._shape = (B, L, O_pts)
+        self._shape = (B, Lo, O_pts)
         self.graph = None
         self.graph_pipelined = None
         self.graph_prefetch = [None, None]
@@ -554,8 +573,10 @@ class FusedPrompter:
 
     def _programs(self, training: bool):
         """(forward, backward) launch lists for the current static buffers."""
-        B, L, _ = self._shape
-        M, F, nl, w = B * L, self.F, self.nl, self.ws
+        B, Lo, _ = self._shape
+        L = Lo + self.n_anchor           # tokens per scene
+        M, Mo, F, nl, w = B * L, B * Lo, self.F, self.nl, self.ws
+        anchor, as_object = bool(self.n_anchor), self.stype == "as_object"
         self._p = self.p_drop if training else 0.0
         p, seed, sptr = self._p, self.seed, self.seed_counter.data_ptr()
         P, G = self.P, self.G
@@ -569,25 +590,41 @@ class FusedPrompter:
         ks_h = max(1, -(-H // 64))
         pre_prog.append(("memset", None, (w["arena_f"],), None, False))
         geo: List = []
-        self._call(geo, "msr3d_spatial_geometry_f32", ptr(w["obj_locs"]), ptr(w["anchor_locs"]), ptr(w["anchor_ori"]),
-                   B, L, self.dist_norm, 1, ptr(w["pw"]), ptr(w["ff"]), ptr(w["sz"]), tag="geometry", side=True)
+        if anchor:
+            # agent-token modes: all_loc / key_pad with the agent in row 0, geometry of the raw centres (no agent frame)
+            self._call(geo, "msr3d_anchor_inputs", ptr(w["obj_locs"]), ptr(w["obj_masks"]), ptr(w["anchor_locs"]),
+                       self.model.anchor_size.data_ptr(), B, Lo, ptr(w["all_loc"]), ptr(w["key_pad"]), tag="anchor_inputs",
+                       side=True)
+            self._call(geo, "msr3d_spatial_geometry_f32", ptr(w["all_loc"]), ptr(w["anchor_locs"]), ptr(w["anchor_ori"]),
+                       B, L, self.dist_norm, 0, ptr(w["pw"]), ptr(w["ff"]), ptr(w["sz"]), tag="geometry", side=True)
+        else:
+            self._call(geo, "msr3d_spatial_geometry_f32", ptr(w["obj_locs"]), ptr(w["anchor_locs"]), ptr(w["anchor_ori"]),
+                       B, L, self.dist_norm, 1, ptr(w["pw"]), ptr(w["ff"]), ptr(w["sz"]), tag="geometry", side=True)
         # prefetch schedule: geometry of the batch in point-cloud slot s, from its freshly copied inputs, for the NEXT step
         self.geo_prog = []
-        for q in ("_q0", "_q1"):
+        for q in (() if anchor else ("_q0", "_q1")):
             gq: List = []
             self._call(gq, "msr3d_spatial_geometry_f32", ptr(w["obj_locs" + q]), ptr(w["anchor_locs" + q]), ptr(w["anchor_ori" + q]),
                        B, L, self.dist_norm, 1, ptr(w["pw_n"]), ptr(w["ff_n"]), ptr(w["sz_n"]), tag="geometry")
             self.geo_prog.append(gq)
-        self._gemm(pre_prog, ptr(w["ff"]), (64, 1), P("loc_embedding_encoder.0.weight"), (63, 1), M, H, 63, ptr(w["h1"]), H,
-                   bias=P("loc_embedding_encoder.0.bias"), tag="loc_fc", side=True)
-        # qpos0 is reduced into the (zero-filled) layer-0 input together with the split-K partial sums of the projection
-        self._call(pre_prog, "msr3d_qpos_fwd_acc_f32", ptr(w["h1"]), ptr(w["sz"]), M, P("size_embedding_encoder.0.weight"),
-                   P("size_embedding_encoder.0.bias"), P("loc_embedding_encoder.1.weight"), P("loc_embedding_encoder.1.bias"),
-                   P("size_embedding_encoder.1.weight"), P("size_embedding_encoder.1.bias"),
-                   P("object_orientation_feat"), P("object_type_embedding.weight"),
-                   ptr(w["xhat_l"]), ptr(w["rstd_l"]), ptr(w["xhat_s"]), ptr(w["rstd_s"]), ptr(w["qpos"]), ptr(w["qpos0"]),
-                   ptr(w["x_in"][0]), tag="qpos", side=True)
+        if as_object:
+            # qpos = loc_layers[0](all_loc) (ose3d_situation.py:396), stored as the first term of the layer-0 input
+            self._call(pre_prog, "msr3d_loc_layer_fwd_f32", ptr(w["all_loc"]), M, P("loc_layers.0.0.weight"),
+                       P("loc_layers.0.0.bias"), P("loc_layers.0.1.weight"), P("loc_layers.0.1.bias"), ptr(w["xhat_l"]),
+                       ptr(w["rstd_l"]), ptr(w["qpos"]), ptr(w["x_in"][0]), tag="qpos", side=True)
+        else:
+            self._gemm(pre_prog, ptr(w["ff"]), (64, 1), P("loc_embedding_encoder.0.weight"), (63, 1), M, H, 63, ptr(w["h1"]), H,
+                       bias=P("loc_embedding_encoder.0.bias"), tag="loc_fc", side=True)
+            # qpos0 is reduced into the (zero-filled) layer-0 input together with the split-K partial sums of the projection
+            # (agent-token modes: qpos alone; the other terms differ per row and come from anchor_assemble)
+            self._call(pre_prog, "msr3d_qpos_fwd_acc_f32", ptr(w["h1"]), ptr(w["sz"]), M, P("size_embedding_encoder.0.weight"),
+                       P("size_embedding_encoder.0.bias"), P("loc_embedding_encoder.1.weight"), P("loc_embedding_encoder.1.bias"),
+                       P("size_embedding_encoder.1.weight"), P("size_embedding_encoder.1.bias"),
+                       None if anchor else P("object_orientation_feat"), None if anchor else P("object_type_embedding.weight"),
+                       ptr(w["xhat_l"]), ptr(w["rstd_l"]), ptr(w["xhat_s"]), ptr(w["rstd_s"]), ptr(w["qpos"]), ptr(w["qpos0"]),
+                       ptr(w["x_in"][0]), tag="qpos", side=True)
         pre_prog[1:1] = geo                              # geometry first on the side stream
+        assert pre_prog[0][0] == "memset"
         cond = self.fusion == "cond"
         fcode, NQ = FUSION_CODE[self.fusion], (QKVC if cond else 3 * H)
         use_ab = cond and self.attn_block and bool(_C.lib().msr3d_attn_block_supported(L, NHEAD, H))
@@ -598,9 +635,17 @@ class FusedPrompter:
                        self.flat_small.data_ptr(), self.n_split, tag="split_w", side=2)
         E = self.emb_dim
         # the projection runs beside the query-position kernels (side stream); both reduce into x_in[0]
-        self._gemm(fwd, self.emb_ptr, (E, 1), P("obj_linear_projection.weight"), (E, 1), M, H, E, ptr(w["x_in"][0]), H,
-                   bias=P("obj_linear_projection.bias"), accumulate=2, ksplit=max(1, -(-E // 64)), tag="obj_proj")
-        fwd.append(("join", None, (), None, False))
+        if anchor:
+            self._gemm(fwd, self.emb_ptr, (E, 1), P("obj_linear_projection.weight"), (E, 1), Mo, H, E, ptr(w["proj"]), H,
+                       bias=P("obj_linear_projection.bias"), tag="obj_proj")
+            fwd.append(("join", None, (), None, False))
+            self._call(fwd, "msr3d_anchor_assemble_f32", ptr(w["x_in"][0]), ptr(w["proj"]), P("object_orientation_feat"),
+                       P("object_type_embedding.weight"), P("anchor_feat"), P("orientation_encoder.weight"),
+                       P("orientation_encoder.bias"), ptr(w["anchor_ori"]), B, Lo, tag="anchor_assemble")
+        else:
+            self._gemm(fwd, self.emb_ptr, (E, 1), P("obj_linear_projection.weight"), (E, 1), M, H, E, ptr(w["x_in"][0]), H,
+                       bias=P("obj_linear_projection.bias"), accumulate=2, ksplit=max(1, -(-E // 64)), tag="obj_proj")
+            fwd.append(("join", None, (), None, False))
         for i in range(nl):
             pre = f"spatial_encoder.{i}."
             sa = pre + "self_attn."
@@ -744,23 +789,35 @@ class FusedPrompter:
                        accumulate=2, ksplit=max(1, -(-NQ // 64)), tag="dx")
             dy3 = dx
         dx0 = ptr(w["dx"][0])
-        # x_in0 = emb Wp^T + bp + orientation_feat + type_emb[0] + qpos
-        self._call(bwd, "msr3d_colsum_add_f32", dx0, H, M, H, G("obj_linear_projection.bias"),
+        dpr = dx0
+        if anchor:
+            # object rows of dx0 -> compact dproj; agent rows -> anchor_feat, type_embedding[1], orientation_encoder
+            dpr = ptr(w["dproj"])
+            self._call(bwd, "msr3d_anchor_disassemble_f32", dx0, ptr(w["anchor_ori"]), B, Lo, dpr, G("anchor_feat"),
+                       G("object_type_embedding.weight") + 4 * H, G("orientation_encoder.weight"),
+                       G("orientation_encoder.bias"), tag="anchor_disassemble")
+        # x_in0 = emb Wp^T + bp + orientation_feat + type_emb[0] + qpos     (object rows)
+        self._call(bwd, "msr3d_colsum_add_f32", dpr, H, Mo, H, G("obj_linear_projection.bias"),
                    G("object_orientation_feat"), G("object_type_embedding.weight"), tag="dbias_proj", side=True)
         E = self.emb_dim
-        self._gemm(bwd, dx0, (1, H), self.emb_ptr, (1, E), H, E, M, G("obj_linear_projection.weight"), E,
+        self._gemm(bwd, dpr, (1, H), self.emb_ptr, (1, E), H, E, Mo, G("obj_linear_projection.weight"), E,
                    accumulate=2, ksplit=4, tag="dWproj", wgrad=True, side=True)
         dq = [ptr(w["dx"][i]) for i in range(nl)] if self.same_all else [dx0]
         dq += [None] * (3 - len(dq))
         assert len(dq) == 3, "fused qpos backward sums at most three layers"
-        self._call(bwd, "msr3d_qpos_bwd_f32", dq[0], dq[1], dq[2], ptr(w["sz"]), M, P("loc_embedding_encoder.1.weight"),
-                   P("size_embedding_encoder.1.weight"), ptr(w["xhat_l"]), ptr(w["rstd_l"]), ptr(w["xhat_s"]),
-                   ptr(w["rstd_s"]), ptr(w["dh1"]), G("loc_embedding_encoder.1.weight"), G("loc_embedding_encoder.1.bias"),
-                   G("size_embedding_encoder.1.weight"), G("size_embedding_encoder.1.bias"),
-                   G("size_embedding_encoder.0.weight"), G("size_embedding_encoder.0.bias"),
-                   G("loc_embedding_encoder.0.bias"), tag="qpos_bwd")
-        self._gemm(bwd, ptr(w["dh1"]), (1, H), ptr(w["ff"]), (1, 64), H, 63, M, G("loc_embedding_encoder.0.weight"), 63,
-                   accumulate=2, ksplit=4, tag="dWloc", wgrad=True)
+        if as_object:
+            self._call(bwd, "msr3d_loc_layer_bwd_f32", dq[0], dq[1], dq[2], ptr(w["all_loc"]), M, P("loc_layers.0.1.weight"),
+                       ptr(w["xhat_l"]), ptr(w["rstd_l"]), G("loc_layers.0.1.weight"), G("loc_layers.0.1.bias"),
+                       G("loc_layers.0.0.weight"), G("loc_layers.0.0.bias"), tag="qpos_bwd")
+        else:
+            self._call(bwd, "msr3d_qpos_bwd_f32", dq[0], dq[1], dq[2], ptr(w["sz"]), M, P("loc_embedding_encoder.1.weight"),
+                       P("size_embedding_encoder.1.weight"), ptr(w["xhat_l"]), ptr(w["rstd_l"]), ptr(w["xhat_s"]),
+                       ptr(w["rstd_s"]), ptr(w["dh1"]), G("loc_embedding_encoder.1.weight"), G("loc_embedding_encoder.1.bias"),
+                       G("size_embedding_encoder.1.weight"), G("size_embedding_encoder.1.bias"),
+                       G("size_embedding_encoder.0.weight"), G("size_embedding_encoder.0.bias"),
+                       G("loc_embedding_encoder.0.bias"), tag="qpos_bwd")
+            self._gemm(bwd, ptr(w["dh1"]), (1, H), ptr(w["ff"]), (1, 64), H, 63, M, G("loc_embedding_encoder.0.weight"), 63,
+                       accumulate=2, ksplit=4, tag="dWloc", wgrad=True)
         bwd.append(("join", None, (), None, False))
         # prefetch schedule: the geometry was computed beside the encoder of the previous step
         # and the gradient buffer is cleared beside the input encoders (first written by the backward pass)
@@ -870,6 +927,7 @@ class FusedPrompter:
 
     def prime(self, batch, upstream):
         """Fill the pipeline: encode `batch` now; its transformer step happens in the next call."""
+        assert not self.n_anchor, "agent-token situation modes run the sequential schedule (forward / backward / train_step)"
         self.stage_points(batch)
         self._encode("emb_next")
         self.stage_scene(batch, upstream)
@@ -989,8 +1047,7 @@ class FusedPrompter:
             from . import dist as _dist
             _dist.allreduce_sum_(self.flat_g[:self.n_opt])
             self.optimizer_step()
-        B, L = self.ws["obj_locs"].shape[:2]
-        return self.ws["tokens"].view(B, L, H)
+        return self._tokens()
 
     def capture_pipelined(self):
         """CUDA graph of one pipelined step.  Warm-up replays leave parameters untouched."""
@@ -1032,6 +1089,7 @@ class FusedPrompter:
 
     def prime2(self, batch0, up0, batch1, up1):
         """Fill both stages: encode batch0 now, park batch1's points in slot 1."""
+        assert not self.n_anchor, "agent-token situation modes run the sequential schedule (forward / backward / train_step)"
         main = torch.cuda.current_stream()
         self._slot_free[0].record()
         self._slot_free[1].record()
@@ -1091,8 +1149,7 @@ class FusedPrompter:
                 w_early.wait()
             w_late.wait()
             self.optimizer_step(split=self.attn_block_active)
-        B, L = self.ws["obj_locs"].shape[:2]
-        return self.ws["tokens"].view(B, L, H)
+        return self._tokens()
 
     def capture_prefetch(self):
         """Two CUDA graphs (one per point-cloud slot).  Warm-up runs leave parameters and staged inputs untouched."""
@@ -1135,12 +1192,21 @@ class FusedPrompter:
     def forward(self):
         """Encoder + transformer forward on the static buffers; returns tokens (B, L, 256) view."""
         w = self.ws
-        torch.logical_not(w["obj_masks"], out=w["key_pad"].view(torch.bool))
+        if not self.n_anchor:         # agent-token modes: msr3d_anchor_inputs writes key_pad (first launch of pre_prog)
+            torch.logical_not(w["obj_masks"], out=w["key_pad"].view(torch.bool))
         self._run(self.pre_prog)      # geometry + query positions on the side stream ...
         self._encode()                # ... while the encoder runs on the main stream
         self._run(self.fwd_prog)      # starts with a join
-        B, L = w["obj_locs"].shape[:2]
-        return w["tokens"].view(B, L, H)
+        return self._tokens()
+
+    def _tokens(self):
+        """(B, tokens per scene, 256) view of the output buffer (tokens per scene = objects + 1 in the agent-token modes)."""
+        B, L = self.ws["key_pad"].shape
+        return self.ws["tokens"].view(B, L, H)
+
+    def token_masks(self) -> torch.Tensor:
+        """obj_masks as OSE3DSituation returns them (ose3d_situation.py:452): True = valid token, agent token included."""
+        return self.ws["key_pad"] == 0
 
     def backward(self):
         """Backward from ws['upstream']; accumulates into the flat gradient buffer."""
@@ -1189,8 +1255,7 @@ class FusedPrompter:
         n0 = _C.launch_count()
         self._train_step_eager()
         self._launches = _C.launch_count() - n0
-        B, L = self.ws["obj_locs"].shape[:2]
-        return self.ws["tokens"].view(B, L, H)
+        return self._tokens()
 
     def _train_step_eager(self):
         self.flat_g.zero_()
@@ -1232,8 +1297,7 @@ class FusedPrompter:
             from . import dist as _dist
             _dist.allreduce_sum_(self.flat_g[:self.n_opt])
             self.optimizer_step()
-        B, L = self.ws["obj_locs"].shape[:2]
-        return self.ws["tokens"].view(B, L, H)
+        return self._tokens()
 
     def loss(self):
         """Surrogate scalar <tokens, upstream> (what bench.py reads back): one deterministic single-CTA

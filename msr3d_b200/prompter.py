@@ -180,7 +180,7 @@ class OSE3DSituation(BaseModel):
             if _ag.eligible(self, data_dict) is None:
                 data_dict["obj_tokens"] = _ag.fused_forward(self, data_dict)
                 data_dict["oatt"] = None
-                data_dict["obj_masks"] = data_dict["obj_masks"].clone()
+                data_dict["obj_masks"] = _ag.token_masks(self, data_dict)
                 return data_dict
         feat = self.forward_gtpcd(data_dict)
         mask = ~data_dict["obj_masks"]          # True = padded
