@@ -246,6 +246,37 @@ int msr3d_preprocess_objects_f32(const float *points, const int32_t *offsets, co
  * coordinates.  Outputs fps_idx (B,m) i32, new_xyz (B,m,3), ball_idx (B,m,nsample) i32. */
 int msr3d_sa_group_f32(const float *xyz, int ld, int B, int N, int m, float radius, int nsample,
                        int32_t *fps_idx, float *new_xyz, int32_t *ball_idx, msr3d_stream_t stream);
+/* ------------------------------------------------------------------ group B2
+ * Unfrozen-encoder training path (modules/vision/pcd_pointnet_encoder.py:58-62,
+ * pytorch_utils.py:39-58 BatchNorm2d in training mode, pointnet2_utils.py:176-224 GroupingOperation.backward ->
+ * _ext_src/src/group_points_gpu.cu:43-75).  Everything is row-major [row][channel], row = (cloud, centre, sample):
+ * the operand layout of msr3d_gemm_tc_f32, which runs the 1x1 convolutions (Z = X W^T), their data gradients
+ * (dX = dZ W) and weight gradients (dW = dZ^T X) on the tensor cores.  csrc/sa_train.cu.
+ *   sa_group_rows      X (rows, 3 + C) = [xyz[idx] - new_xyz | feat[idx]]; idx == NULL: GroupAll (rows = points, raw xyz)
+ *   bn_train_fwd       Y = relu(BN(Z)); batch_stats 1: statistics of this batch (deterministic two-stage reduction),
+ *                      running statistics updated in place (momentum, unbiased variance); 0: running statistics.
+ *                      stats (2, C) = mean, rstd (kept for the backward); partial: scratch of
+ *                      2 * C * msr3d_sa_train_stat_chunks(rows) floats
+ *   bn_train_bwd       from dY (grad wrt Y): dgamma / dbeta ACCUMULATED, dZ (may alias dY); bstat (2, C) scratch
+ *   maxpool_rows(_bwd) max over the S consecutive rows of a group (first index wins ties), arg (groups, C) int32
+ *   sa_group_rows_bwd  dfeat (B, N, C) = segmented sum of dX[:, col0 : col0 + C] over idx (B, pairs) — one CTA per
+ *                      cloud, fixed order, no atomics */
+int msr3d_sa_train_stat_chunks(long long rows);
+int msr3d_sa_group_rows_f32(const float *xyz, int ld_xyz, const float *feat, int ld_feat, int C, const float *new_xyz,
+                            const int32_t *idx, int N, int groups_per_cloud, int nsample, long long rows, float *X,
+                            msr3d_stream_t stream);
+int msr3d_bn_train_fwd_f32(const float *Z, long long rows, int C, const float *gamma, const float *beta,
+                           float *running_mean, float *running_var, int batch_stats, float eps, float momentum,
+                           float *partial, float *stats, float *Y, msr3d_stream_t stream);
+int msr3d_bn_train_bwd_f32(const float *dY, const float *Y, const float *Z, long long rows, int C, const float *gamma,
+                           const float *stats, int batch_stats, float *partial, float *bstat, float *dgamma,
+                           float *dbeta, float *dZ, msr3d_stream_t stream);
+int msr3d_maxpool_rows_f32(const float *Y, long long groups, int S, int C, float *out, long long ld_out, int32_t *arg,
+                           msr3d_stream_t stream);
+int msr3d_maxpool_rows_bwd_f32(const float *dOut, long long ld_dout, const int32_t *arg, long long groups, int S,
+                               int C, float *dY, msr3d_stream_t stream);
+int msr3d_sa_group_rows_bwd_f32(const float *dX, int ldx, int col0, const int32_t *idx, int B, int pairs, int N, int C,
+                                float *dfeat, msr3d_stream_t stream);
 /* Writes xyz (rows,3) into columns [col0,col0+3) of a (rows, ld_dst) matrix: the xyz
  * channels GroupAll concatenates (pointnet2_utils.py:407), in the operand of SA3. */
 int msr3d_scatter_xyz_cols_f32(const float *xyz, float *dst, long long ld_dst, int col0, int rows,

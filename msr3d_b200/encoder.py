@@ -17,9 +17,11 @@ Two execution paths, both on this repo's CUDA kernels:
   [conv1x1+BN+ReLU] + max-pool); GroupAll level and `fc` on the tcgen05 GEMM.
   Tensors between levels are point-major, BatchNorm is folded into the packed
   weights, the grouped (B,C,npoint,nsample) tensors never exist.
-* layer-wise (unfrozen encoder / training-mode BatchNorm / odd hyper-parameters):
-  the module tree below, built from the `_ext` operators of msr3d_b200.ext with
-  autograd, and torch for conv/BN.
+* training (unfrozen encoder, pcd_pointnet_encoder.py:58-62): msr3d_b200/encoder_train.py — one autograd
+  Function over row-major kernels (training-mode BatchNorm with batch statistics, tensor-core GEMMs
+  for the convolutions and every gradient, atomic-free grouping gradient).
+* layer-wise (odd hyper-parameters, A/B): the module tree below, built from the `_ext` operators of
+  msr3d_b200.ext with autograd, and torch for conv/BN.
 """
 from __future__ import annotations
 
@@ -312,6 +314,8 @@ class PointNetPP(nn.Module):
         self._pack_key = None
         self._packed = None
         self._ws = {}
+        # False: the unfrozen encoder runs the layer-wise module tree (torch conv / BN over the _ext operators)
+        self.train_kernels = __import__("os").environ.get("MSR3D_ENCODER_TRAIN_KERNELS", "1") == "1"
 
     # ---- layer-wise path (autograd, training-mode BN allowed)
     def forward_layerwise(self, pc):
@@ -438,6 +442,12 @@ class PointNetPP(nn.Module):
         frozen = not torch.is_grad_enabled() or not any(p.requires_grad for p in self.parameters())
         if features.is_cuda and frozen and self.fused_supported(features):
             return self.forward_fused(features.contiguous().float())
+        if features.is_cuda and not frozen and self.train_kernels:
+            # unfrozen encoder (pcd_pointnet_encoder.py:58-62): training- or eval-mode BatchNorm with autograd, forward
+            # and hand-written backward on this repo's kernels (msr3d_b200/encoder_train.py)
+            from . import encoder_train
+            if encoder_train.supported(self, features):
+                return encoder_train.forward_train(self, features)
         return self.forward_layerwise(features)
 
 

@@ -30,17 +30,25 @@ SD = Dict[str, torch.Tensor]
 # --------------------------------------------------------------------------
 # PointNet++ object encoder
 # --------------------------------------------------------------------------
-def shared_mlp(sd: SD, prefix: str, x: torch.Tensor) -> torch.Tensor:
-    """SharedMLP of (conv1x1 no-bias -> BatchNorm2d(eval) -> ReLU) blocks.
+def shared_mlp(sd: SD, prefix: str, x: torch.Tensor, bn_stats: Optional[dict] = None) -> torch.Tensor:
+    """SharedMLP of (conv1x1 no-bias -> BatchNorm2d -> ReLU) blocks.
 
     pytorch_utils.py:11-36 (SharedMLP), :67-120 (_ConvBase order conv, bn, act),
     :39-58 (BatchNorm2d wrapper => key `...bn.bn.*`).  x: (B, C, npoint, nsample).
+    bn_stats None: eval BatchNorm (running statistics; the frozen encoder).  A dict: TRAINING-mode BatchNorm
+    (unfrozen encoder, pcd_pointnet_encoder.py:58-62 — batch statistics, nn.BatchNorm2d defaults momentum 0.1,
+    eps 1e-5); the updated running_mean / running_var are returned in it, `sd` is left untouched.
     """
     i = 0
     while f"{prefix}.layer{i}.conv.weight" in sd:
         p = f"{prefix}.layer{i}"
         x = F.conv2d(x, sd[f"{p}.conv.weight"], sd.get(f"{p}.conv.bias"))
-        if f"{p}.bn.bn.weight" in sd:
+        if f"{p}.bn.bn.weight" in sd and bn_stats is not None:
+            rm = sd[f"{p}.bn.bn.running_mean"].detach().clone()
+            rv = sd[f"{p}.bn.bn.running_var"].detach().clone()
+            x = F.batch_norm(x, rm, rv, sd[f"{p}.bn.bn.weight"], sd[f"{p}.bn.bn.bias"], True, 0.1, 1e-5)
+            bn_stats[f"{p}.bn.bn.running_mean"], bn_stats[f"{p}.bn.bn.running_var"] = rm, rv
+        elif f"{p}.bn.bn.weight" in sd:
             x = F.batch_norm(x, sd[f"{p}.bn.bn.running_mean"], sd[f"{p}.bn.bn.running_var"],
                              sd[f"{p}.bn.bn.weight"], sd[f"{p}.bn.bn.bias"], False, 0.0, 1e-5)
         x = F.relu(x)
@@ -74,7 +82,7 @@ def group_all(xyz, feats):
 
 
 def sa_module(sd: SD, prefix: str, xyz, feats, npoint: Optional[int], radius, nsample,
-              trace: Optional[dict] = None):
+              trace: Optional[dict] = None, bn_stats: Optional[dict] = None):
     """_PointnetSAModuleBase.forward, single-scale (pointnet2_modules.py:34-75)."""
     if npoint is not None:
         fps_idx = ext.furthest_point_sampling(xyz.contiguous(), npoint)  # :54-58
@@ -87,7 +95,7 @@ def sa_module(sd: SD, prefix: str, xyz, feats, npoint: Optional[int], radius, ns
     else:
         new_xyz = None
         grouped = group_all(xyz, feats)
-    h = shared_mlp(sd, f"{prefix}.mlps.0", grouped)
+    h = shared_mlp(sd, f"{prefix}.mlps.0", grouped, bn_stats)
     h = h.max(dim=3).values  # F.max_pool2d(kernel=[1,nsample]) + squeeze, :68-71
     if trace is not None:
         trace[prefix + ".features"] = h
@@ -95,13 +103,13 @@ def sa_module(sd: SD, prefix: str, xyz, feats, npoint: Optional[int], radius, ns
 
 
 def pointnetpp(sd: SD, prefix: str, pc: torch.Tensor, sa_n_points: Sequence, sa_n_samples: Sequence,
-               sa_radii: Sequence, trace: Optional[dict] = None) -> torch.Tensor:
+               sa_radii: Sequence, trace: Optional[dict] = None, bn_stats: Optional[dict] = None) -> torch.Tensor:
     """PointNetPP.forward (modules/layers/pointnet.py:55-63) incl. break_up_pc (:6-19)."""
     xyz = pc[..., 0:3].contiguous()
     feats = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
     for i in range(len(sa_n_points)):
         xyz, feats = sa_module(sd, f"{prefix}.encoder.{i}", xyz, feats, sa_n_points[i],
-                               sa_radii[i], sa_n_samples[i], trace)
+                               sa_radii[i], sa_n_samples[i], trace, bn_stats)
     flat = feats.reshape(feats.size(0), -1)
     return F.linear(flat, sd[f"{prefix}.fc.weight"], sd[f"{prefix}.fc.bias"])
 

@@ -158,3 +158,62 @@ def test_preprocess_objects_matches_reference(golden_dir, case):
     np.testing.assert_array_equal(masks, g("obj_masks"))
     # the degenerate object (all points equal) is left unscaled, the padding rows are ones / zeros / False
     assert np.all(fts[~masks] == 1.0) and np.all(locs[~masks] == 0.0)
+
+
+def _encoder_train_case(golden_dir, case):
+    """Inputs of one case of tests/golden/encoder_train.npz: (fixture, state dict with grads enabled, batch, G)."""
+    fx = _load(golden_dir, "encoder_train")
+    B, O, P, seed, bn_train = (int(v) for v in fx[f"{case}:meta"])
+    names = [k.split(":", 2)[2] for k in fx.files if k.startswith(f"{case}:grad")]
+    bufs = [k.split(":", 2)[2] for k in fx.files if k.startswith(f"{case}:buf:")]
+    return fx, B, O, P, seed, bool(bn_train), sorted(set(names)), bufs
+
+
+def check_encoder_grads(fx, case, grads: dict, tol=1e-4):
+    """grads: name (relative to pcd_net) -> numpy gradient; compared with the reference's, full or subsampled."""
+    worst = ("", 0.0)
+    for key in fx.files:
+        if key.startswith(f"{case}:grad:"):
+            n, ref, got = key.split(":", 2)[2], fx[key], None
+            got = grads[n]
+        elif key.startswith(f"{case}:gradsub:"):
+            n, ref = key.split(":", 2)[2], fx[key]
+            got = grads[n].reshape(-1)[::37]
+            st = fx[f"{case}:gradstat:{n}"]
+            assert abs(np.linalg.norm(grads[n].astype(np.float64)) - st[0]) <= 10 * tol * max(st[0], 1e-6), n
+        else:
+            continue
+        err = np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-6)
+        if err > worst[1]:
+            worst = (n, err)
+        assert err <= tol, (n, err)
+    return worst
+
+
+@pytest.mark.parametrize("case", ["train", "evalbn"])
+def test_unfrozen_encoder_matches_reference(golden_dir, case):
+    """oracle.pointnetpp with training-mode BatchNorm and autograd vs the unmodified reference PcdObjEncoder(freeze=False)
+    (SURVEY 8f-2): embeddings, gradients of all 29 PointNet++ parameters, updated running statistics."""
+    from msr3d_b200 import configs
+    fx, B, O, P, seed, bn_train, names, bufs = _encoder_train_case(golden_dir, case)
+    enc = configs.build_prompter(0).obj_encoder
+    spec = [(k, list(v.shape), "int64" if v.dtype == torch.int64 else "float32") for k, v in enc.state_dict().items()]
+    sd = synthetic.make_state_dict(spec, seed)
+    sd = {"e." + k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+          for k, v in sd.items()}
+    batch = synthetic.make_batch(B, O, P, seed=seed)
+    ext_oracle.set_threads(4)
+    stats = {} if bn_train else None
+    flat = batch.obj_fts.reshape(B * O, P, 6)
+    emb = mo.pointnetpp(sd, "e.pcd_net", flat, (32, 16, None), (32, 32, None), (0.2, 0.4, None), bn_stats=stats)
+    np.testing.assert_allclose(emb.detach().numpy().reshape(B, O, -1), fx[f"{case}:emb"], rtol=1e-4, atol=1e-4)
+    G = torch.randn(B, O, emb.shape[-1], generator=torch.Generator().manual_seed(seed + 77))
+    (emb.view(B, O, -1) * G).sum().backward()
+    grads = {n: sd["e.pcd_net." + n].grad.numpy() for n in names}
+    worst = check_encoder_grads(fx, case, grads)
+    print(case, "worst grad", worst)
+    for n in bufs:
+        if "num_batches" in n:
+            continue
+        got = (stats or {}).get("e.pcd_net." + n, sd["e.pcd_net." + n]).detach().numpy()
+        np.testing.assert_allclose(got, fx[f"{case}:buf:{n}"], rtol=1e-4, atol=1e-6)
