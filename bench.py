@@ -173,6 +173,46 @@ def cpu_baseline(args):
             "sample": f"{n} full steps of {args.config} (B={B}) after 1 warm-up; oracle port: torch CPU fp32 + C/OpenMP pointnet2 ops"}
 
 
+def bench_unfrozen_encoder(dev, B, O, P, flush):
+    """forward + backward of the UNFROZEN PointNet++ encoder (vision.args.freeze False, training-mode
+    BatchNorm) at the bench configuration's clouds — this repo's kernel path (msr3d_b200/encoder_train.py) and, beside
+    it, the layer-wise torch module tree (cuDNN convolutions / ATen BatchNorm over the same index kernels)."""
+    from msr3d_b200 import synthetic
+    from msr3d_b200.encoder import PcdObjEncoder
+    batch = synthetic.make_batch(B, O, P, seed=2100).to(dev)
+    G = torch.randn(B, O, 768, device=dev, generator=torch.Generator(dev).manual_seed(3))
+    res = {"workload": f"{B * O} clouds x {P} points, training-mode BatchNorm, fwd + bwd, inputs resident, L2 flushed"}
+    for key, kernels in (("kernels_ms", True), ("torch_module_tree_ms", False)):
+        enc = PcdObjEncoder(freeze=False)
+        spec = [(k, list(v.shape), "int64" if v.dtype == torch.int64 else "float32") for k, v in enc.state_dict().items()]
+        enc.load_state_dict(synthetic.make_state_dict(spec, 5))
+        enc = enc.to(dev).train()
+        enc.pcd_net.train_kernels = kernels
+        ts = []
+        for i in range(7):
+            for p in enc.parameters():
+                p.grad = None
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            emb = enc.encode(batch.obj_fts)
+            emb.backward(G)
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(a.elapsed_time(b))
+        res[key] = round(statistics.median(ts), 3)
+        del enc
+        torch.cuda.empty_cache()
+    # algorithmic work: 113.5 MFLOP per cloud forward (SURVEY 8d), data + weight gradients twice that
+    gflop = 3 * 113.5e-3 * B * O
+    res["algorithmic_gflop"] = round(gflop, 1)
+    res["kernels_tflops"] = round(gflop / res["kernels_ms"], 2)
+    res["note"] = ("fp32-grade split-bf16 products (six MMAs per product) in the generic GEMM kernel of round 1: correct "
+                   "first, not yet a tuned kernel; the module tree runs cuDNN with TF32 allowed")
+    return res
+
+
 def bench_splice(dev, B, L, flush, cores):
     """SURVEY.md §8f-1 (the step after the path): llm_proj + fp16 scatter into the LLM input and its
     backward, at config-2 shapes (T = 204 prompt positions, D = 4096).  Per-call CUDA-event times with
@@ -357,7 +397,8 @@ def main():
             for key, fn in (("gpu_baseline", lambda: gpu_baseline(args, dev, flush)),
                             ("secondary", lambda: secondary_configs(args, dev, world, flush)),
                             ("llm_context", lambda: llm_context(dev, B, O, ms_step)),
-                            ("next_rows", lambda: {"scene_splice (SURVEY 8f-1)": bench_splice(dev, B, O, flush, os.cpu_count() or 1)})):
+                            ("next_rows", lambda: {"scene_splice (SURVEY 8f-1)": bench_splice(dev, B, O, flush, os.cpu_count() or 1),
+                                                   "unfrozen_encoder (SURVEY 8f-2)": bench_unfrozen_encoder(dev, B, O, P, flush)})):
                 try:
                     line[key] = fn()
                 except Exception as e:  # noqa: BLE001

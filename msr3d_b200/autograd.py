@@ -56,18 +56,22 @@ def _engine(module):
 
 class _FusedPrompterFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, engine, obj_fts, obj_locs, obj_masks, anchor_locs, anchor_ori, *params):
+    def forward(ctx, module, engine, obj_fts, obj_locs, obj_masks, anchor_locs, anchor_ori, emb, *params):
+        # emb: None (frozen encoder: computed here, without autograd) or the embeddings of an UNFROZEN encoder, computed
+        # by the caller with autograd (encoder_train.py) — backward then hands d(emb) back to it
         B, L, P = obj_fts.shape[:3]
         engine.prepare(B, L, P, training=module.training)
         if module.training:
             engine.seed_counter.add_(1)            # fresh dropout masks per call (the engine's own optimiser is not used)
         w = engine.ws
-        w["obj_fts"].copy_(obj_fts)
+        if emb is None:
+            w["obj_fts"].copy_(obj_fts)
         w["obj_locs"].copy_(obj_locs)
         w["obj_masks"].copy_(obj_masks)
         w["anchor_locs"].copy_(anchor_locs)
         w["anchor_ori"].copy_(anchor_ori)
-        tokens = engine.forward()
+        tokens = engine.forward(emb.detach() if emb is not None else None)
+        ctx.need_d_emb = emb is not None and emb.requires_grad
         ctx.engine = engine
         ctx.n_params = len(params)
         ctx.key = engine._key
@@ -84,7 +88,7 @@ class _FusedPrompterFn(torch.autograd.Function):
         # engine-API engines alias p.grad to flat_g: keep what autograd has accumulated there so far
         saved = e.flat_g[:e.n_opt].clone() if e.alias_grads else None
         e.flat_g.zero_()
-        e.backward()
+        d_emb = e.backward(need_d_emb=ctx.need_d_emb)
         flat = e.flat_g[:e.n_opt].clone()          # fresh storage: autograd may keep / steal what we return
         if saved is not None:
             e.flat_g[:e.n_opt].copy_(saved)
@@ -96,16 +100,25 @@ class _FusedPrompterFn(torch.autograd.Function):
                 grads.append(None)                 # parameters the shipped mode never touches
             else:
                 grads.append(flat[off:off + p.numel()].view_as(p))
-        return (None,) * 7 + tuple(grads)
+        if d_emb is not None:
+            B, L = e.ws["obj_locs"].shape[:2]
+            d_emb = d_emb.view(B, L, -1)
+        return (None,) * 7 + (d_emb,) + tuple(grads)
 
 
 def fused_forward(module, data_dict) -> torch.Tensor:
     """obj_tokens (B, O, 256) of `module(data_dict)` through the fused engine, differentiable w.r.t. the
     module's trainable parameters."""
+    from .fused import encoder_frozen
     eng = _engine(module)
     params = [eng.by_name[n] for n in eng.autograd_names]
+    emb = None
+    if not encoder_frozen(module):
+        # vision.args.freeze False (pcd_pointnet_encoder.py:58-62): the encoder's own autograd Function (training- or
+        # eval-mode BatchNorm, encoder_train.py) in front of the transformer's
+        emb = module.obj_encoder.encode(data_dict["obj_fts"])
     return _FusedPrompterFn.apply(module, eng, data_dict["obj_fts"], data_dict["obj_locs"], data_dict["obj_masks"],
-                                  data_dict["anchor_locs"], data_dict["anchor_orientation"], *params)
+                                  data_dict["anchor_locs"], data_dict["anchor_orientation"], emb, *params)
 
 
 def token_masks(module, data_dict) -> torch.Tensor:

@@ -28,7 +28,7 @@ def to_attr(o):
     return o
 
 
-def prompter_cfg(situation_type="as_transform_for_objects", fusion="cond", **spatial_over):
+def prompter_cfg(situation_type="as_transform_for_objects", fusion="cond", freeze=True, **spatial_over):
     """configs/msr3d.yaml:174-217 as a plain attribute dict (what hydra hands the reference)."""
     se = {"dim_loc": 6, "num_attention_heads": 8, "dim_feedforward": 2048, "dropout": 0.1,
           "activation": "gelu", "spatial_multihead": True, "spatial_dim": 5, "spatial_dist_norm": True,
@@ -44,7 +44,7 @@ def prompter_cfg(situation_type="as_transform_for_objects", fusion="cond", **spa
         "vision": {"name": "PcdObjEncoder", "args": {
             "sa_n_points": [32, 16, None], "sa_n_samples": [32, 32, None], "sa_radii": [0.2, 0.4, None],
             "sa_mlps": [[3, 64, 64, 128], [128, 128, 128, 256], [256, 256, 512, 768]],
-            "dropout": 0.1, "freeze": True, "path": None}},
+            "dropout": 0.1, "freeze": bool(freeze), "path": None}},
         "spatial_encoder": se}})
 
 
@@ -54,12 +54,13 @@ def load_spec():
         return [tuple(x) for x in json.load(fh)]
 
 
-def build_prompter(seed: int, situation_type="as_transform_for_objects", device="cpu", fusion="cond", **spatial_over):
+def build_prompter(seed: int, situation_type="as_transform_for_objects", device="cpu", fusion="cond", freeze=True,
+                   **spatial_over):
     """Drop-in OSE3DSituation of the shipped configuration with seeded synthetic weights (eval mode).
     Other fusions / situation modes own a different set of keys; values are keyed by NAME
     (synthetic.make_state_dict), so every key shared with the shipped model gets the same tensor."""
     import msr3d_b200
-    model = msr3d_b200.build_model(prompter_cfg(situation_type, fusion, **spatial_over))
+    model = msr3d_b200.build_model(prompter_cfg(situation_type, fusion, freeze, **spatial_over))
     model.load_state_dict(model_state_dict(model, seed), strict=True)
     return model.to(device).eval()
 

@@ -134,8 +134,15 @@ ANCHOR_MODES = ("as_object", "as_object_add_loc")
 FUSION_CODE = {"cond": 0, "mul": 1, "bias": 2, "ctx": 2, "add": 3}
 
 
+def encoder_frozen(model) -> bool:
+    return all(not p.requires_grad for p in model.obj_encoder.parameters())
+
+
 def supported(model) -> Optional[str]:
-    """None if `model` (an OSE3DSituation) can run on the fused engine, else the reason."""
+    """None if `model` (an OSE3DSituation) can run on the fused engine, else the reason.  An UNFROZEN object encoder
+    (vision.args.freeze False) is fine for the transformer half: the module call (autograd.py) then runs the encoder's
+    own training path (encoder_train.py) in front of it and receives d(embeddings) from `backward(need_d_emb=True)`;
+    the engine's own optimiser schedules (train_step*, prefetch) encode without autograd and refuse it."""
     c = model.cfg
     se = c.spatial_encoder
     checks = [
@@ -155,9 +162,7 @@ def supported(model) -> Optional[str]:
         (bool(c.use_orientation), "use_orientation off"),
         (c.vision.name == "PcdObjEncoder", "vision backbone is not PcdObjEncoder"),
         (se.dim_feedforward % 64 == 0, "dim_feedforward % 64"),
-        # the engine runs the encoder without autograd: an unfrozen encoder must use the module tree
-        (hasattr(model, "obj_encoder") and all(not p.requires_grad for p in model.obj_encoder.parameters()),
-         "object encoder is not frozen"),
+        (hasattr(model, "obj_encoder"), "no object encoder"),
     ]
     for ok, why in checks:
         if not ok:
@@ -297,7 +302,9 @@ class FusedPrompter:
     # ------------------------------------------------------------------ parameters
     def _rehome(self):
         from . import dist as _dist
-        named = [(n, p) for n, p in self.model.named_parameters() if p.requires_grad]
+        # the object encoder's parameters (trainable only with vision.args.freeze False) stay where they are: their
+        # forward / backward is encoder_train.py's, driven by autograd
+        named = [(n, p) for n, p in self.model.named_parameters() if p.requires_grad and not n.startswith("obj_encoder.")]
         n_model = len(named)
         named += [("ext." + k, p) for k, p in self.extra_params.items() if p.requires_grad]
         by_name = dict(named)
@@ -902,6 +909,9 @@ class FusedPrompter:
             w["upstream"].copy_(upstream.reshape(w["upstream"].shape), non_blocking=non_blocking)
 
     def _encode(self, out_key="emb", src_key="obj_fts"):
+        if not encoder_frozen(self.model):
+            raise NotImplementedError("fused prompter: the engine's own schedules run the object encoder frozen; with "
+                                      "vision.args.freeze False call the module (OSE3DSituation.forward + autograd)")
         w = self.ws
         enc = self.model.obj_encoder
         B, L, Pn, _ = w[src_key].shape
@@ -1189,13 +1199,16 @@ class FusedPrompter:
             self.refresh_split()
         torch.cuda.synchronize()
 
-    def forward(self):
+    def forward(self, emb: Optional[torch.Tensor] = None):
         """Encoder + transformer forward on the static buffers; returns tokens (B, L, 256) view."""
         w = self.ws
         if not self.n_anchor:         # agent-token modes: msr3d_anchor_inputs writes key_pad (first launch of pre_prog)
             torch.logical_not(w["obj_masks"], out=w["key_pad"].view(torch.bool))
         self._run(self.pre_prog)      # geometry + query positions on the side stream ...
-        self._encode()                # ... while the encoder runs on the main stream
+        if emb is None:
+            self._encode()            # ... while the encoder runs on the main stream
+        else:                         # embeddings computed by the caller (unfrozen encoder, autograd.py)
+            w["emb"].copy_(emb.reshape(w["emb"].shape))
         self._run(self.fwd_prog)      # starts with a join
         return self._tokens()
 
@@ -1208,9 +1221,18 @@ class FusedPrompter:
         """obj_masks as OSE3DSituation returns them (ose3d_situation.py:452): True = valid token, agent token included."""
         return self.ws["key_pad"] == 0
 
-    def backward(self):
-        """Backward from ws['upstream']; accumulates into the flat gradient buffer."""
+    def backward(self, need_d_emb: bool = False):
+        """Backward from ws['upstream']; accumulates into the flat gradient buffer.  need_d_emb: also returns the
+        gradient wrt the object embeddings (B * objects, E) = d(projection output) . W_proj — what an unfrozen encoder
+        back-propagates (tensor-core GEMM, msr3d_gemm_tc_f32)."""
         self._run(self.bwd_prog)
+        if not need_d_emb:
+            return None
+        w = self.ws
+        dpr = w["dproj"] if self.n_anchor else w["dx"][0]
+        Wp = self.by_name["obj_linear_projection.weight"].detach()
+        with torch.cuda.device(self.dev):
+            return gemm_tc(dpr, Wp.t(), split=6)
 
     def refresh_split(self):
         """tf32 big / small images of the parameters (after anything but optimizer_step(split=True) changed them)."""

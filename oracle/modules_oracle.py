@@ -123,11 +123,11 @@ def mlp_head(sd: SD, prefix: str, x: torch.Tensor) -> torch.Tensor:
 
 def pcd_obj_encoder(sd: SD, prefix: str, obj_pcds: torch.Tensor, sa_n_points=(32, 16, None),
                     sa_n_samples=(32, 32, None), sa_radii=(0.2, 0.4, None),
-                    trace: Optional[dict] = None):
+                    trace: Optional[dict] = None, bn_stats: Optional[dict] = None):
     """PcdObjEncoder.forward (modules/vision/pcd_pointnet_encoder.py:48-74)."""
     B, O = obj_pcds.shape[:2]
     flat = obj_pcds.reshape(B * O, obj_pcds.shape[2], obj_pcds.shape[3])
-    emb = pointnetpp(sd, f"{prefix}.pcd_net", flat, sa_n_points, sa_n_samples, sa_radii, trace)
+    emb = pointnetpp(sd, f"{prefix}.pcd_net", flat, sa_n_points, sa_n_samples, sa_radii, trace, bn_stats)
     emb = emb.reshape(B, O, -1)
     return emb, mlp_head(sd, f"{prefix}.obj3d_clf_pre_head", emb)
 
@@ -266,7 +266,7 @@ def ose3d_situation(sd: SD, data: dict, *, n_head: int = 8, num_layers: int = 3,
                     sa_n_points=(32, 16, None), sa_n_samples=(32, 32, None),
                     sa_radii=(0.2, 0.4, None), obj_embeds: Optional[torch.Tensor] = None,
                     trace: Optional[dict] = None, layer_masks: Optional[list] = None,
-                    spatial_multihead: bool = True):
+                    spatial_multihead: bool = True, unfrozen_bn_stats: Optional[dict] = None):
     """OSE3DSituation.forward (model/ose3d_situation.py:288-454) for vision_backbone
     'gtpcd', use_spatial_attn/use_anchor/use_orientation True, attn_flat off, and
     situation_type in {'as_transform_for_objects' (shipped, configs/msr3d.yaml:177),
@@ -275,8 +275,10 @@ def ose3d_situation(sd: SD, data: dict, *, n_head: int = 8, num_layers: int = 3,
     Returns (obj_tokens (B,N',H), obj_masks (B,N') bool with True = valid)."""
     if obj_embeds is None:
         obj_embeds = pcd_obj_encoder(sd, "obj_encoder", data["obj_fts"], sa_n_points,
-                                     sa_n_samples, sa_radii, trace)[0]
-        obj_embeds = obj_embeds.detach()  # frozen encoder, pcd_pointnet_encoder.py:50-57
+                                     sa_n_samples, sa_radii, trace, unfrozen_bn_stats)[0]
+        if unfrozen_bn_stats is None:
+            obj_embeds = obj_embeds.detach()  # frozen encoder, pcd_pointnet_encoder.py:50-57
+        # else: vision.args.freeze False (:58-62) — training-mode BatchNorm, gradients flow into the encoder
     feat = F.linear(obj_embeds, sd["obj_linear_projection.weight"], sd["obj_linear_projection.bias"])
     B, N, H = feat.shape
     mask = ~data["obj_masks"]  # True = padded (:315)
