@@ -182,7 +182,10 @@ def bench_unfrozen_encoder(dev, B, O, P, flush):
     batch = synthetic.make_batch(B, O, P, seed=2100).to(dev)
     G = torch.randn(B, O, 768, device=dev, generator=torch.Generator(dev).manual_seed(3))
     res = {"workload": f"{B * O} clouds x {P} points, training-mode BatchNorm, fwd + bwd, inputs resident, L2 flushed"}
-    for key, kernels in (("kernels_ms", True), ("torch_module_tree_ms", False)):
+    tf32_was = torch.backends.cudnn.allow_tf32
+    for key, kernels, tf32 in (("kernels_ms", True, tf32_was), ("torch_module_tree_tf32_ms", False, True),
+                               ("torch_module_tree_fp32_ms", False, False)):
+        torch.backends.cudnn.allow_tf32 = tf32
         enc = PcdObjEncoder(freeze=False)
         spec = [(k, list(v.shape), "int64" if v.dtype == torch.int64 else "float32") for k, v in enc.state_dict().items()]
         enc.load_state_dict(synthetic.make_state_dict(spec, 5))
@@ -204,12 +207,15 @@ def bench_unfrozen_encoder(dev, B, O, P, flush):
         res[key] = round(statistics.median(ts), 3)
         del enc
         torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32 = tf32_was
     # algorithmic work: 113.5 MFLOP per cloud forward, data + weight gradients twice that
     gflop = 3 * 113.5e-3 * B * O
     res["algorithmic_gflop"] = round(gflop, 1)
     res["kernels_tflops"] = round(gflop / res["kernels_ms"], 2)
-    res["note"] = ("fp32-grade split-bf16 products (six MMAs per product) in the generic GEMM kernel of round 1: correct "
-                   "first, not yet a tuned kernel; the module tree runs cuDNN with TF32 allowed")
+    res["note"] = ("fp32-grade 3xTF32 products through the TMA-fed tcgen05 GEMM of the transformer (csrc/gemm3x.cu), "
+                   "BatchNorm statistics / apply / pooling as separate HBM passes (about 8 GB per step): not yet fused into "
+                   "the GEMM prologues and epilogues; module tree = cuDNN convolutions + ATen BatchNorm over this repo's "
+                   "index kernels, with TF32 allowed (torch default) and in fp32")
     return res
 
 

@@ -252,7 +252,8 @@ int msr3d_sa_group_f32(const float *xyz, int ld, int B, int N, int m, float radi
  * _ext_src/src/group_points_gpu.cu:43-75).  Everything is row-major [row][channel], row = (cloud, centre, sample):
  * the operand layout of msr3d_gemm_tc_f32, which runs the 1x1 convolutions (Z = X W^T), their data gradients
  * (dX = dZ W) and weight gradients (dW = dZ^T X) on the tensor cores.  csrc/sa_train.cu.
- *   sa_group_rows      X (rows, 3 + C) = [xyz[idx] - new_xyz | feat[idx]]; idx == NULL: GroupAll (rows = points, raw xyz)
+ *   sa_group_rows      X (rows, ldx >= 3 + C) = [xyz[idx] - new_xyz | feat[idx] | 0 pad]; idx == NULL: GroupAll (rows =
+ *                      points, raw xyz); ldx rounded up to a multiple of 4 makes X a TMA operand
  *   bn_train_fwd       Y = relu(BN(Z)); batch_stats 1: statistics of this batch (deterministic two-stage reduction),
  *                      running statistics updated in place (momentum, unbiased variance); 0: running statistics.
  *                      stats (2, C) = mean, rstd (kept for the backward); partial: scratch of
@@ -264,7 +265,7 @@ int msr3d_sa_group_f32(const float *xyz, int ld, int B, int N, int m, float radi
 int msr3d_sa_train_stat_chunks(long long rows);
 int msr3d_sa_group_rows_f32(const float *xyz, int ld_xyz, const float *feat, int ld_feat, int C, const float *new_xyz,
                             const int32_t *idx, int N, int groups_per_cloud, int nsample, long long rows, float *X,
-                            msr3d_stream_t stream);
+                            int ldx, msr3d_stream_t stream);
 int msr3d_bn_train_fwd_f32(const float *Z, long long rows, int C, const float *gamma, const float *beta,
                            float *running_mean, float *running_var, int batch_stats, float eps, float momentum,
                            float *partial, float *stats, float *Y, msr3d_stream_t stream);

@@ -28,12 +28,11 @@ constexpr int kStatLanes = 8;      // row lanes per CTA (256 threads)
 __global__ void __launch_bounds__(256)
 group_rows_kernel(const float *__restrict__ xyz, int ld_xyz, const float *__restrict__ feat, int ld_feat, int C,
                   const float *__restrict__ new_xyz, const int *__restrict__ idx, int N, int groups_per_cloud,
-                  int nsample, long long rows, float *__restrict__ X) {
+                  int nsample, long long rows, float *__restrict__ X, int ldx) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const int ldx = 3 + C;
   long long b, src;
   float cx = 0.f, cy = 0.f, cz = 0.f;
   if (idx != nullptr) {
@@ -52,6 +51,7 @@ group_rows_kernel(const float *__restrict__ xyz, int ld_xyz, const float *__rest
   }
   const float *f = feat + src * ld_feat;
   for (int c = lane; c < C; c += 32) o[3 + c] = f[c];
+  if (lane < ldx - (3 + C)) o[3 + C + lane] = 0.f;      // pad columns (row pitch rounded up for TMA): zero
 }
 
 // partial[chunk][0][c] = sum_rows Z, partial[chunk][1][c] = sum_rows Z^2 over the rows of the chunk
@@ -276,13 +276,13 @@ MSR3D_API int msr3d_sa_train_stat_chunks(long long rows) {
 
 MSR3D_API int msr3d_sa_group_rows_f32(const float *xyz, int ld_xyz, const float *feat, int ld_feat, int C,
                                       const float *new_xyz, const int32_t *idx, int N, int groups_per_cloud,
-                                      int nsample, long long rows, float *X, msr3d_stream_t stream) {
-  MSR3D_REQUIRE(xyz && feat && X && C >= 1, "sa_group_rows: null pointer / bad C");
+                                      int nsample, long long rows, float *X, int ldx, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(xyz && feat && X && C >= 1 && ldx >= 3 + C && ldx < 3 + C + 32, "sa_group_rows: null pointer / bad C / ldx");
   MSR3D_REQUIRE((idx == nullptr) == (new_xyz == nullptr), "sa_group_rows: idx and new_xyz come together");
   MSR3D_REQUIRE(idx == nullptr || (N >= 1 && groups_per_cloud >= 1 && nsample >= 1), "sa_group_rows: bad sizes");
   if (rows <= 0) return MSR3D_OK;
   launch_pdl(group_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, xyz, ld_xyz, feat,
-             ld_feat, C, new_xyz, (const int *)idx, N, groups_per_cloud, nsample, rows, X);
+             ld_feat, C, new_xyz, (const int *)idx, N, groups_per_cloud, nsample, rows, X, ldx);
   return check_launch("sa_group_rows");
 }
 

@@ -30,7 +30,7 @@ c_int, c_ll, c_float, c_vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ct
 
 _C.register_protos({
     "msr3d_sa_train_stat_chunks": [c_ll],
-    "msr3d_sa_group_rows_f32": [c_vp, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int, c_ll, c_vp, c_vp],
+    "msr3d_sa_group_rows_f32": [c_vp, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int, c_ll, c_vp, c_int, c_vp],
     "msr3d_bn_train_fwd_f32": [c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_float, c_float, c_vp, c_vp, c_vp, c_vp],
     "msr3d_bn_train_bwd_f32": [c_vp, c_vp, c_vp, c_ll, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_maxpool_rows_f32": [c_vp, c_ll, c_int, c_int, c_vp, c_ll, c_vp, c_vp],
@@ -46,6 +46,44 @@ BN_EPS, BN_MOMENTUM = 1e-5, 0.1       # nn.BatchNorm2d defaults (pytorch_utils.p
 # by 10 % while all norms agree to 1e-4).  MSR3D_ENC_TRAIN_SPLIT=3 trades that for speed.
 FWD_SPLIT = int(__import__("os").environ.get("MSR3D_ENC_TRAIN_SPLIT", "6"))
 WGRAD_SPLIT = 6
+DGRAD_SPLIT = 3      # data gradients decide nothing discrete: two-way split (1.5e-5) is ample
+
+
+# GEMM kernel: "tf32x3" = the TMA-fed tcgen05 kind::tf32 big / small kernel of the transformer (csrc/gemm3x.cu, fp32-grade,
+# operands fetched by tensor-map TMA straight from the row-major activations; row pitches are padded to multiples of
+# 4 floats for it), "bf16" = the register-path split-bf16 kernel of round 1 (csrc/linear_tc.cu; FWD_SPLIT applies)
+GEMM_IMPL = __import__("os").environ.get("MSR3D_ENC_TRAIN_GEMM", "tf32x3")
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def _tma_ok(t: torch.Tensor) -> bool:
+    if t.data_ptr() % 16:
+        return False
+    if t.stride(1) == 1:
+        return t.stride(0) % 4 == 0 and t.stride(0) >= t.shape[1]
+    return t.stride(0) == 1 and t.stride(1) % 4 == 0 and t.stride(1) >= t.shape[0]
+
+
+def _gemm(A, Bm, split, **kw):
+    """out = A @ Bm^T through the configured tensor-core kernel (falls back to the register-path kernel for operands
+    the TMA path cannot address)."""
+    out = kw.get("out")
+    if GEMM_IMPL == "tf32x3" and _tma_ok(A) and _tma_ok(Bm) and (out is None or out.stride(0) % 4 == 0):
+        return gemm_tc(A, Bm, split=split, impl="tf32x3", **kw)
+    return gemm_tc(A, Bm, split=split, **kw)
+
+
+def _weight(W2):
+    """(cout, cin) weight with the row pitch padded to a multiple of 4 floats (zero columns), matching the padded X."""
+    cout, cin = W2.shape
+    if cin % 4 == 0:
+        return W2
+    Wp = torch.zeros(cout, _pad4(cin), dtype=W2.dtype, device=W2.device)
+    Wp[:, :cin] = W2
+    return Wp
 
 
 def _st() -> int:
@@ -89,7 +127,7 @@ def _mlp_forward(lv: _Level, X, layers, training_bn: List[bool]):
     a = X
     for (W, gamma, beta, rmean, rvar), bn_train in zip(layers, training_bn):
         cout = W.shape[0]
-        Z = gemm_tc(a, W.view(cout, -1), split=FWD_SPLIT)
+        Z = _gemm(a, _weight(W.view(cout, -1)), FWD_SPLIT)
         chunks = _C.lib().msr3d_sa_train_stat_chunks(rows)
         partial = torch.empty(2 * cout * max(1, chunks), dtype=torch.float32, device=dev)
         stats = torch.empty(2, cout, dtype=torch.float32, device=dev)
@@ -123,7 +161,7 @@ def _mlp_backward(lv: _Level, d_pool, layers, grads, need_dx: bool):
     for j in reversed(range(len(layers))):
         W, gamma, beta, _, _ = layers[j]
         cout = W.shape[0]
-        W2 = W.view(cout, -1)
+        W2 = _weight(W.view(cout, -1))          # (cout, cin padded to the pitch of X)
         x_in = lv.X if j == 0 else lv.Y[j - 1]
         chunks = _C.lib().msr3d_sa_train_stat_chunks(rows)
         partial = torch.empty(2 * cout * max(1, chunks), dtype=torch.float32, device=dev)
@@ -138,10 +176,12 @@ def _mlp_backward(lv: _Level, d_pool, layers, grads, need_dx: bool):
         cin = W2.shape[1]
         dW = torch.zeros(cout, cin, dtype=torch.float32, device=dev)
         tiles = -(-cout // 128) * -(-cin // 64)
-        gemm_tc(dZ.t(), x_in.t(), split=WGRAD_SPLIT, out=dW, accumulate=2, ksplit=_ksplit_for(rows, tiles))
-        grads[id(W)], grads[id(gamma)], grads[id(beta)] = dW.view_as(W), dgamma, dbeta
+        _gemm(dZ.t(), x_in.t(), WGRAD_SPLIT, out=dW, accumulate=2, ksplit=_ksplit_for(rows, tiles))
+        cin_real = W.numel() // cout
+        grads[id(W)] = (dW if cin_real == cin else dW[:, :cin_real].contiguous()).view_as(W)
+        grads[id(gamma)], grads[id(beta)] = dgamma, dbeta
         if j > 0 or need_dx:
-            dY = gemm_tc(dZ, W2.t(), split=FWD_SPLIT)          # dX (rows, cin) = dZ W
+            dY = _gemm(dZ, W2.t(), DGRAD_SPLIT)                # dX (rows, cin) = dZ W
             if j == 0:
                 dX = dY
     return dX
@@ -169,29 +209,29 @@ class _PointNetPPTrainFn(torch.autograd.Function):
             _, xyz1, ball1 = ops.sa_group(pc, np1, net.sa_radii[0], S1)
             l1 = _Level()
             rows1 = Bc * np1 * S1
-            X1 = torch.empty(rows1, 6, dtype=torch.float32, device=dev)
+            X1 = torch.empty(rows1, _pad4(6), dtype=torch.float32, device=dev)
             _C.call("msr3d_sa_group_rows_f32", pc.data_ptr(), 6, pc.data_ptr() + 12, 6, 3, xyz1.data_ptr(),
-                    ball1.data_ptr(), P, np1, S1, rows1, X1.data_ptr(), _st())
+                    ball1.data_ptr(), P, np1, S1, rows1, X1.data_ptr(), X1.shape[1], _st())
             f1 = _pool(l1, _mlp_forward(l1, X1, layer_sets[0], bn_mode[0]), S1)          # (Bc * np1, C1)
             C1 = f1.shape[1]
             # ---- level 2
             _, xyz2, ball2 = ops.sa_group(xyz1, np2, net.sa_radii[1], S2)
             l2 = _Level()
             rows2 = Bc * np2 * S2
-            X2 = torch.empty(rows2, 3 + C1, dtype=torch.float32, device=dev)
+            X2 = torch.empty(rows2, _pad4(3 + C1), dtype=torch.float32, device=dev)
             _C.call("msr3d_sa_group_rows_f32", xyz1.data_ptr(), 3, f1.data_ptr(), C1, C1, xyz2.data_ptr(),
-                    ball2.data_ptr(), np1, np2, S2, rows2, X2.data_ptr(), _st())
+                    ball2.data_ptr(), np1, np2, S2, rows2, X2.data_ptr(), X2.shape[1], _st())
             l2.idx, l2.n_src, l2.pairs = ball2, np1, np2 * S2
             f2 = _pool(l2, _mlp_forward(l2, X2, layer_sets[1], bn_mode[1]), S2)          # (Bc * np2, C2)
             C2 = f2.shape[1]
             # ---- level 3 (GroupAll): rows = the np2 remaining points of every cloud, raw xyz
             l3 = _Level()
             rows3 = Bc * np2
-            X3 = torch.empty(rows3, 3 + C2, dtype=torch.float32, device=dev)
+            X3 = torch.empty(rows3, _pad4(3 + C2), dtype=torch.float32, device=dev)
             _C.call("msr3d_sa_group_rows_f32", xyz2.data_ptr(), 3, f2.data_ptr(), C2, C2, None, None, np2, 1, 1, rows3,
-                    X3.data_ptr(), _st())
+                    X3.data_ptr(), X3.shape[1], _st())
             g = _pool(l3, _mlp_forward(l3, X3, layer_sets[2], bn_mode[2]), np2)          # (Bc, C3)
-            out = gemm_tc(g, net.fc.weight.detach(), bias=net.fc.bias.detach(), split=FWD_SPLIT)
+            out = _gemm(g, net.fc.weight.detach(), FWD_SPLIT, bias=net.fc.bias.detach())
         for sa, modes in zip(net.encoder, bn_mode):
             for blk, tr in zip(sa.mlps[0], modes):
                 if tr:
@@ -210,15 +250,15 @@ class _PointNetPPTrainFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             Wfc = net.fc.weight.detach()
             dWfc = torch.zeros_like(Wfc)
-            gemm_tc(d_out.t(), g.t(), split=WGRAD_SPLIT, out=dWfc, accumulate=2, ksplit=1)
+            _gemm(d_out.t(), g.t(), WGRAD_SPLIT, out=dWfc, accumulate=2, ksplit=1)
             grads[id(net.fc.weight)] = dWfc
             dbfc = torch.zeros_like(net.fc.bias)
             _C.call("msr3d_colsum_add_f32", d_out.data_ptr(), d_out.stride(0), d_out.shape[0], d_out.shape[1],
                     dbfc.data_ptr(), None, None, _st())
             grads[id(net.fc.bias)] = dbfc
-            dg = gemm_tc(d_out, Wfc.t(), split=FWD_SPLIT)                                   # (Bc, C3)
+            dg = _gemm(d_out, Wfc.t(), DGRAD_SPLIT)                                        # (Bc, C3)
             dX3 = _mlp_backward(l3, dg, layer_sets[2], grads, need_dx=True)                # (Bc * np2, 3 + C2)
-            d_f2 = dX3[:, 3:]                                                              # GroupAll: rows = points
+            d_f2 = dX3[:, 3:3 + C2]                                                        # GroupAll: rows = points
             dX2 = _mlp_backward(l2, d_f2, layer_sets[1], grads, need_dx=True)              # (Bc * np2 * S2, 3 + C1)
             d_f1 = torch.empty(Bc * np1, C1, dtype=torch.float32, device=dev)
             _C.call("msr3d_sa_group_rows_bwd_f32", dX2.data_ptr(), dX2.shape[1], 3, l2.idx.data_ptr(), Bc, l2.pairs,

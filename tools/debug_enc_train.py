@@ -35,6 +35,18 @@ def main():
         err = float((p.grad - q.grad).abs().max() / q.grad.abs().max().clamp_min(1e-12))
         nerr = float((p.grad - q.grad).norm() / q.grad.norm().clamp_min(1e-20))
         print(f"{n:45s} |g| {float(q.grad.abs().max()):10.3e}  max err {err:9.2e}  norm err {nerr:9.2e}")
+    import time
+    for name, enc in (("kernels", a), ("module tree", b)):
+        ts = []
+        for i in range(5):
+            for p in enc.parameters():
+                p.grad = None
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            (enc.encode(batch.obj_fts) * G).sum().backward()
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        print(f"{name}: fwd + bwd {min(ts):.3f} ms (best of 5, wall clock)")
     for (n, p), (_, q) in zip(a.pcd_net.named_buffers(), b.pcd_net.named_buffers()):
         if p.is_floating_point():
             print(f"{n:45s} buffer rel err {float((p - q).abs().max() / q.abs().max().clamp_min(1e-12)):9.2e}")
