@@ -4,9 +4,12 @@
 // the host and are inputs, so results can be compared with the reference draw for draw.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 namespace msr3d {
 
 constexpr int kPreThreads = 256;
+constexpr int kPreCluster = 8;     // CTAs per object slot (thread-block cluster): pass 1 walks up to ~100 k points
 
 __device__ __forceinline__ float block_reduce(float v, float *s_red, int op) {  // 0 sum, 1 min, 2 max
 #pragma unroll
@@ -23,25 +26,34 @@ __device__ __forceinline__ float block_reduce(float v, float *s_red, int op) {  
   return r;
 }
 
-// One CTA per output object slot.  Slots >= n_obj are padding: points of ones, zero location, mask 0.
-//   pass 1 (all points of the object): rotate, centre = mean, size = max - min          -> obj_locs
-//   pass 2 (the P sampled points): rotate, subtract their mean, divide by the largest norm
+// One CLUSTER of kPreCluster CTAs per output object slot.  Slots >= n_obj are padding: points of ones, zero
+// location, mask 0.
+//   pass 1 (all points of the object, split over the CTAs of the cluster; partial sums / bounds meet in rank 0
+//          through distributed shared memory, fixed order): rotate, centre = mean, size = max - min   -> obj_locs
+//   pass 2 (the P sampled points, rank 0): rotate, subtract their mean, divide by the largest norm
 //          (1 when it is < 1e-6)                                                        -> obj_fts
 // Sums are accumulated in double per thread (numpy's pairwise float32 sums are within 1 ulp of that).
+// Round 1 ran one CTA per slot: 60 CTAs on 148 SMs, the largest object (tens of thousands of points) on one SM —
+// 10 % of the HBM roof (profiles/r1_next_rows.md).
 __global__ void __launch_bounds__(kPreThreads)
 preprocess_objects_kernel(const float *__restrict__ points, const int *__restrict__ offsets,
                           const int *__restrict__ sample_idx, const float *__restrict__ rot, int n_obj, int P,
                           float *__restrict__ obj_fts, float *__restrict__ obj_locs,
                           unsigned char *__restrict__ obj_masks) {
   pdl_sync();
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), nz = (int)cluster.num_blocks();
   extern __shared__ float s_xyz[];      // [P][3] rotated coordinates of the sampled points
   __shared__ float s_red[kPreThreads / 32];
+  __shared__ double s_sum[3];           // this CTA's partial sums of pass 1
+  __shared__ float s_mm[6];             // ... and bounds (min xyz, max xyz)
   const int o = blockIdx.x, tid = threadIdx.x;
   float *fo = obj_fts + (size_t)o * P * 6;
-  if (o >= n_obj) {
-    for (int i = tid; i < P * 6; i += kPreThreads) fo[i] = 1.f;
-    if (tid < 6) obj_locs[(size_t)o * 6 + tid] = 0.f;
-    if (tid == 0) obj_masks[o] = 0;
+  if (o >= n_obj) {                     // the whole cluster takes this branch (same slot)
+    for (int i = rank * kPreThreads + tid; i < P * 6; i += nz * kPreThreads) fo[i] = 1.f;
+    if (rank == 0 && tid < 6) obj_locs[(size_t)o * 6 + tid] = 0.f;
+    if (rank == 0 && tid == 0) obj_masks[o] = 0;
     return;
   }
   float r[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
@@ -62,7 +74,7 @@ preprocess_objects_kernel(const float *__restrict__ points, const int *__restric
   const float *src = points + (size_t)p0 * 6;
   double sx = 0.0, sy = 0.0, sz = 0.0;
   float mnx = INFINITY, mny = INFINITY, mnz = INFINITY, mxx = -INFINITY, mxy = -INFINITY, mxz = -INFINITY;
-  for (int i = tid; i < n; i += kPreThreads) {
+  for (int i = rank * kPreThreads + tid; i < n; i += nz * kPreThreads) {
     float x, y, z;
     rotate(src[(size_t)i * 6], src[(size_t)i * 6 + 1], src[(size_t)i * 6 + 2], x, y, z);
     sx += x; sy += y; sz += z;
@@ -74,15 +86,36 @@ preprocess_objects_kernel(const float *__restrict__ points, const int *__restric
     const float hi = (float)v, lo = (float)(v - (double)hi);
     return (double)block_reduce(hi, s_red, 0) + (double)block_reduce(lo, s_red, 0);
   };
-  const double tx = reduce_d(sx), ty = reduce_d(sy), tz = reduce_d(sz);
-  const float lox = block_reduce(mnx, s_red, 1), loy = block_reduce(mny, s_red, 1), loz = block_reduce(mnz, s_red, 1);
-  const float hix = block_reduce(mxx, s_red, 2), hiy = block_reduce(mxy, s_red, 2), hiz = block_reduce(mxz, s_red, 2);
-  if (tid == 0) {
+  {
+    const double tx = reduce_d(sx), ty = reduce_d(sy), tz = reduce_d(sz);
+    const float lox = block_reduce(mnx, s_red, 1), loy = block_reduce(mny, s_red, 1), loz = block_reduce(mnz, s_red, 1);
+    const float hix = block_reduce(mxx, s_red, 2), hiy = block_reduce(mxy, s_red, 2), hiz = block_reduce(mxz, s_red, 2);
+    if (tid == 0) {
+      s_sum[0] = tx; s_sum[1] = ty; s_sum[2] = tz;
+      s_mm[0] = lox; s_mm[1] = loy; s_mm[2] = loz; s_mm[3] = hix; s_mm[4] = hiy; s_mm[5] = hiz;
+    }
+  }
+  cluster.sync();                       // every CTA's partials are visible cluster-wide
+  if (rank == 0 && tid == 0) {
+    double t[3] = {0.0, 0.0, 0.0};
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int q = 0; q < nz; ++q) {      // fixed order: deterministic
+      const double *ps = cluster.map_shared_rank(s_sum, q);
+      const float *pm = cluster.map_shared_rank(s_mm, q);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        t[d] += ps[d];
+        lo[d] = fminf(lo[d], pm[d]);
+        hi[d] = fmaxf(hi[d], pm[3 + d]);
+      }
+    }
     float *l = obj_locs + (size_t)o * 6;
-    l[0] = (float)(tx / n); l[1] = (float)(ty / n); l[2] = (float)(tz / n);
-    l[3] = hix - lox; l[4] = hiy - loy; l[5] = hiz - loz;
+    l[0] = (float)(t[0] / n); l[1] = (float)(t[1] / n); l[2] = (float)(t[2] / n);
+    l[3] = hi[0] - lo[0]; l[4] = hi[1] - lo[1]; l[5] = hi[2] - lo[2];
     obj_masks[o] = 1;
   }
+  cluster.sync();                       // nobody exits while rank 0 may still be reading its shared memory
+  if (rank != 0) return;                // the P sampled points are one CTA's work
   // ---- the sampled points
   const int *si = sample_idx + (size_t)o * P;
   double ax = 0.0, ay = 0.0, az = 0.0;
@@ -128,7 +161,7 @@ MSR3D_API int msr3d_preprocess_objects_f32(const float *points, const int32_t *o
     MSR3D_CUDA(cudaFuncSetAttribute(preprocess_objects_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     configured = true;
   }
-  launch_pdl(preprocess_objects_kernel, dim3(o_max), dim3(kPreThreads), smem, (cudaStream_t)stream, points, offsets,
-             sample_idx, rot, n_obj, P, obj_fts, obj_locs, obj_masks);
+  launch_pdl_cluster(preprocess_objects_kernel, dim3(o_max, 1, kPreCluster), dim3(kPreThreads), smem, (cudaStream_t)stream,
+                     dim3(1, 1, kPreCluster), points, offsets, sample_idx, rot, n_obj, P, obj_fts, obj_locs, obj_masks);
   return check_launch("preprocess_objects");
 }
