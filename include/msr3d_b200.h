@@ -375,6 +375,20 @@ int msr3d_anchor_assemble_f32(float *x0, const float *proj, const float *ori_fea
 int msr3d_anchor_disassemble_f32(const float *dx0, const float *anchor_ori, int B, int L, float *dproj,
                                  float *d_anchor_feat, float *d_type1, float *dW_ori, float *db_ori,
                                  msr3d_stream_t stream);
+/* as_embedding (ose3d_situation.py:385-393): s_b = loc_embedding_encoder(fourier(anchor_locs[b])) +
+ * orientation_encoder(fourier(anchor_orientation[b])) added to the query position of every object of scene b.
+ * Forward: qpos (B*L, 256) += s_b (plain) and x0 += s_b (red.add: the projection GEMM reduces into x0 concurrently);
+ * saves xhat_sit (B, 256) / rstd_sit (B) of the LayerNorm.  Backward: from the per-layer qpos gradients (dq1 / dq2
+ * nullable) ACCUMULATES the gradients of loc_embedding_encoder.{0.weight (256, 63), 0.bias, 1.weight, 1.bias} and
+ * orientation_encoder.{weight (256, 84), bias}. */
+int msr3d_situation_embed_fwd_f32(const float *anchor_locs, const float *anchor_ori, int B, int L, const float *Wl,
+                                  const float *bl, const float *gamma_l, const float *beta_l, const float *W_ori,
+                                  const float *b_ori, float *xhat_sit, float *rstd_sit, float *qpos, float *x0,
+                                  msr3d_stream_t stream);
+int msr3d_situation_embed_bwd_f32(const float *dq, const float *dq1, const float *dq2, const float *anchor_locs,
+                                  const float *anchor_ori, int B, int L, const float *gamma_l, const float *xhat_sit,
+                                  const float *rstd_sit, float *dWl, float *dbl, float *dgamma_l, float *dbeta_l,
+                                  float *dW_ori, float *db_ori, msr3d_stream_t stream);
 /* Same contract as msr3d_attn_bwd_f32 on the tensor cores (csrc/attn_block.cu: dP, dq, dk, dv as tcgen05 kind::tf32
  * 3xTF32 products, one CTA per (head, scene)); requires L <= 64, 8 heads, ldq = 816. */
 int msr3d_attn_bwd_tc_f32(const float *dctx, int ldc, const float *qkvc, int ldq, const float *pw, const float *P,

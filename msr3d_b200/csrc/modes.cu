@@ -207,6 +207,113 @@ anchor_disassemble_kernel(const float *__restrict__ dx0, const float *__restrict
   db_ori[c] += gsum;
 }
 
+// ---------------------------------------------------------------------------
+// as_embedding (ose3d_situation.py:385-393): the situation enters as one embedding per scene,
+//   s_b = loc_embedding_encoder(fourier(anchor_loc_b)) + orientation_encoder(fourier(anchor_orientation_b)),
+// added to the query position of EVERY object of the scene (no agent token, no agent-frame transform).
+// Forward: one CTA per scene, thread = column; s_b goes into qpos (read again by the later layers) and, with
+// red.add, into the layer-0 input that the projection GEMM is reducing into at the same time.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum256(float v, float *s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += s_red[i];
+  return t;
+}
+
+// [p(3) | sin(pi p_d f_j) d-major (30) | cos (30)] of a position, by one warp (geometry_kernel's layout)
+__device__ __forceinline__ void loc_fourier(const float *p, int lane, float *f /* shared [64] */) {
+  if (lane < 30) {
+    const int d = lane / 10, j = lane % 10;
+    const float kPi = 3.14159265358979323846f;
+    const float step = 14.f / 9.f;
+    const float fr = j < 5 ? 1.f + j * step : 15.f - (9 - j) * step;
+    float sn, cs;
+    sincosf(kPi * (p[d] * fr), &sn, &cs);
+    f[3 + lane] = sn;
+    f[33 + lane] = cs;
+  }
+  if (lane < 3) f[lane] = p[lane];
+  if (lane == 31) f[63] = 0.f;
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(256)
+situation_embed_fwd_kernel(const float *__restrict__ anchor_locs, const float *__restrict__ anchor_ori, int L,
+                           const float *__restrict__ Wl, const float *__restrict__ bl, LnParams lnl,
+                           const float *__restrict__ W_ori, const float *__restrict__ b_ori,
+                           float *__restrict__ xhat_sit, float *__restrict__ rstd_sit, float *__restrict__ qpos,
+                           float *__restrict__ x0) {
+  pdl_sync();
+  __shared__ float f_loc[64], f_ori[kOriFeat], s_red[8];
+  const int b = blockIdx.x, c = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) loc_fourier(anchor_locs + (size_t)b * 3, lane, f_loc);
+  if (warp == 1) anchor_fourier(anchor_ori + (size_t)b * 4, lane, f_ori);
+  __syncthreads();
+  float h = bl[c];
+  for (int j = 0; j < 63; ++j) h += Wl[(size_t)c * 63 + j] * f_loc[j];
+  const float mean = block_sum256(h, s_red) * (1.f / kD);
+  const float xc = h - mean;
+  const float rstd = rsqrtf(block_sum256(xc * xc, s_red) * (1.f / kD) + kLnEps);
+  const float xh = xc * rstd;
+  float s = xh * lnl.gamma[c] + lnl.beta[c] + b_ori[c];
+  for (int j = 0; j < kOriFeat; ++j) s += W_ori[(size_t)c * kOriFeat + j] * f_ori[j];
+  xhat_sit[(size_t)b * kD + c] = xh;
+  if (c == 0) rstd_sit[b] = rstd;
+  for (int t = 0; t < L; ++t) {
+    const size_t i = ((size_t)b * L + t) * kD + c;
+    qpos[i] += s;
+    atomicAdd(x0 + i, s);
+  }
+}
+
+// Backward: ONE CTA walks the scenes in order (deterministic); parameter gradients accumulate with atomics because
+// loc_embedding_encoder also receives the objects' contributions (qpos_bwd_kernel, the dWloc GEMM).
+__global__ void __launch_bounds__(256)
+situation_embed_bwd_kernel(const float *__restrict__ dq, const float *__restrict__ dq1, const float *__restrict__ dq2,
+                           const float *__restrict__ anchor_locs, const float *__restrict__ anchor_ori, int B, int L,
+                           const float *__restrict__ gamma_l, const float *__restrict__ xhat_sit,
+                           const float *__restrict__ rstd_sit, float *__restrict__ dWl, float *__restrict__ dbl,
+                           float *__restrict__ dgamma_l, float *__restrict__ dbeta_l, float *__restrict__ dW_ori,
+                           float *__restrict__ db_ori) {
+  pdl_sync();
+  __shared__ float f_loc[64], f_ori[kOriFeat], s_red[8];
+  const int c = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float a_gamma = 0.f, a_beta = 0.f, a_bl = 0.f;
+  for (int b = 0; b < B; ++b) {
+    __syncthreads();
+    if (warp == 0) loc_fourier(anchor_locs + (size_t)b * 3, lane, f_loc);
+    if (warp == 1) anchor_fourier(anchor_ori + (size_t)b * 4, lane, f_ori);
+    __syncthreads();
+    float g = 0.f;
+    for (int t = 0; t < L; ++t) {
+      const size_t i = ((size_t)b * L + t) * kD + c;
+      g += dq[i];
+      if (dq1 != nullptr) g += dq1[i];
+      if (dq2 != nullptr) g += dq2[i];
+    }
+    const float xh = xhat_sit[(size_t)b * kD + c];
+    a_gamma += g * xh;
+    a_beta += g;
+    for (int j = 0; j < kOriFeat; ++j) atomicAdd(dW_ori + (size_t)c * kOriFeat + j, g * f_ori[j]);
+    const float gg = g * gamma_l[c];
+    const float s1 = block_sum256(gg, s_red) * (1.f / kD);
+    const float s2 = block_sum256(gg * xh, s_red) * (1.f / kD);
+    const float dh = rstd_sit[b] * (gg - s1 - xh * s2);
+    a_bl += dh;
+    for (int j = 0; j < 63; ++j) atomicAdd(dWl + (size_t)c * 63 + j, dh * f_loc[j]);
+  }
+  atomicAdd(dgamma_l + c, a_gamma);
+  atomicAdd(dbeta_l + c, a_beta);
+  atomicAdd(db_ori + c, a_beta);
+  atomicAdd(dbl + c, a_bl);
+}
+
 }  // namespace msr3d
 
 using namespace msr3d;
@@ -262,4 +369,29 @@ MSR3D_API int msr3d_anchor_disassemble_f32(const float *dx0, const float *anchor
   launch_pdl(anchor_disassemble_kernel, dim3(ceil_div(B * L, kLnWarps) + 1), dim3(kLnWarps * 32), 0,
              (cudaStream_t)stream, dx0, anchor_ori, B, L, dproj, d_anchor_feat, d_type1, dW_ori, db_ori);
   return check_launch("anchor_disassemble");
+}
+
+MSR3D_API int msr3d_situation_embed_fwd_f32(const float *anchor_locs, const float *anchor_ori, int B, int L,
+                                            const float *Wl, const float *bl, const float *gamma_l, const float *beta_l,
+                                            const float *W_ori, const float *b_ori, float *xhat_sit, float *rstd_sit,
+                                            float *qpos, float *x0, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(anchor_locs && anchor_ori && Wl && bl && gamma_l && beta_l && W_ori && b_ori && xhat_sit && rstd_sit &&
+                    qpos && x0, "situation_embed_fwd: null pointer");
+  if (B <= 0 || L <= 0) return MSR3D_OK;
+  launch_pdl(situation_embed_fwd_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, anchor_locs, anchor_ori, L, Wl, bl,
+             LnParams{gamma_l, beta_l}, W_ori, b_ori, xhat_sit, rstd_sit, qpos, x0);
+  return check_launch("situation_embed_fwd");
+}
+
+MSR3D_API int msr3d_situation_embed_bwd_f32(const float *dq, const float *dq1, const float *dq2, const float *anchor_locs,
+                                            const float *anchor_ori, int B, int L, const float *gamma_l,
+                                            const float *xhat_sit, const float *rstd_sit, float *dWl, float *dbl,
+                                            float *dgamma_l, float *dbeta_l, float *dW_ori, float *db_ori,
+                                            msr3d_stream_t stream) {
+  MSR3D_REQUIRE(dq && anchor_locs && anchor_ori && gamma_l && xhat_sit && rstd_sit && dWl && dbl && dgamma_l && dbeta_l &&
+                    dW_ori && db_ori, "situation_embed_bwd: null pointer");
+  if (B <= 0 || L <= 0) return MSR3D_OK;
+  launch_pdl(situation_embed_bwd_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, dq, dq1, dq2, anchor_locs, anchor_ori,
+             B, L, gamma_l, xhat_sit, rstd_sit, dWl, dbl, dgamma_l, dbeta_l, dW_ori, db_ori);
+  return check_launch("situation_embed_bwd");
 }

@@ -111,6 +111,8 @@ _C.register_protos({
     "msr3d_loc_layer_bwd_f32": [c_vp, c_vp, c_vp, c_vp, c_int] + [c_vp] * 7 + [c_vp],
     "msr3d_anchor_assemble_f32": [c_vp] * 8 + [c_int, c_int, c_vp],
     "msr3d_anchor_disassemble_f32": [c_vp, c_vp, c_int, c_int] + [c_vp] * 5 + [c_vp],
+    "msr3d_situation_embed_fwd_f32": [c_vp, c_vp, c_int, c_int] + [c_vp] * 10 + [c_vp],
+    "msr3d_situation_embed_bwd_f32": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int] + [c_vp] * 9 + [c_vp],
     "msr3d_attn_fusion_fwd_f32": [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp],
     "msr3d_attn_fusion_bwd_f32": [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
     "msr3d_spatial_weights_fwd_f32": [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp],
@@ -154,7 +156,8 @@ def supported(model) -> Optional[str]:
         (se.pairwise_rel_type == "center", "pairwise_rel_type != center"),
         (se.activation == "gelu", "activation != gelu"),
         (se.obj_loc_encoding in ("same_all", "same_0"), "obj_loc_encoding == diff_all"),
-        (model.situation_type in ("as_transform_for_objects",) + ANCHOR_MODES, f"situation_type {model.situation_type}"),
+        (model.situation_type in ("as_transform_for_objects", "as_embedding") + ANCHOR_MODES,
+         f"situation_type {model.situation_type}"),
         (model.situation_type not in ANCHOR_MODES or bool(c.use_anchor), "anchor mode without use_anchor"),
         (model.situation_type == "as_object" or c.loc_fourier_dim == 63, "loc_fourier_dim != 63"),
         (model.situation_type != "as_object" or se.dim_loc == 6, "dim_loc != 6"),
@@ -232,6 +235,8 @@ class FusedPrompter:
         # situation mode: the shipped as_transform_for_objects, or one of the agent-token modes (tokens per scene = L + 1)
         self.stype = model.situation_type
         self.n_anchor = 1 if self.stype in ANCHOR_MODES else 0
+        # as_embedding: one situation embedding per scene added to every object's query position (csrc/modes.cu)
+        self.sit_embed = self.stype == "as_embedding"
         self.multihead = int(bool(se.spatial_multihead))
         self.dist_norm = int(bool(se.spatial_dist_norm))
         self.p_drop = float(se.dropout)
@@ -309,7 +314,8 @@ class FusedPrompter:
         named += [("ext." + k, p) for k, p in self.extra_params.items() if p.requires_grad]
         by_name = dict(named)
         # parameters the configured situation mode never touches (neither reduced nor updated)
-        unused = {"as_object": (), "as_object_add_loc": ("loc_layers.",)}.get(self.stype, _dist.UNUSED_IN_SHIPPED_MODE)
+        unused = {"as_object": (), "as_object_add_loc": ("loc_layers.",),
+                  "as_embedding": ("anchor_feat", "loc_layers.")}.get(self.stype, _dist.UNUSED_IN_SHIPPED_MODE)
         lay = _dist.flat_layout([n for n, _ in named], {n: p.numel() for n, p in named}, self.nl,
                                 no_decay_bias=self.no_decay_bias, unused=unused)
         self.order, offs, total = lay["order"], lay["offs"], lay["total"]
@@ -461,6 +467,8 @@ class FusedPrompter:
         if self.n_anchor:
             w["all_loc"] = f(B, L, 6)
             w["proj"], w["dproj"] = f(B * Lo, H), f(B * Lo, H)
+        if self.sit_embed:
+            w["xhat_sit"], w["rstd_sit"] = f(B, H), f(B)
         w["anchor_locs"] = f(B, 3)
         w["anchor_ori"] = f(B, 4)
         w["upstream"] = f(M, H)
@@ -605,11 +613,13 @@ class FusedPrompter:
             self._call(geo, "msr3d_spatial_geometry_f32", ptr(w["all_loc"]), ptr(w["anchor_locs"]), ptr(w["anchor_ori"]),
                        B, L, self.dist_norm, 0, ptr(w["pw"]), ptr(w["ff"]), ptr(w["sz"]), tag="geometry", side=True)
         else:
+            # as_embedding: Fourier features of the raw centres (the situation enters through its own embedding)
             self._call(geo, "msr3d_spatial_geometry_f32", ptr(w["obj_locs"]), ptr(w["anchor_locs"]), ptr(w["anchor_ori"]),
-                       B, L, self.dist_norm, 1, ptr(w["pw"]), ptr(w["ff"]), ptr(w["sz"]), tag="geometry", side=True)
+                       B, L, self.dist_norm, 0 if self.sit_embed else 1, ptr(w["pw"]), ptr(w["ff"]), ptr(w["sz"]),
+                       tag="geometry", side=True)
         # prefetch schedule: geometry of the batch in point-cloud slot s, from its freshly copied inputs, for the NEXT step
         self.geo_prog = []
-        for q in (() if anchor else ("_q0", "_q1")):
+        for q in (() if (anchor or self.sit_embed) else ("_q0", "_q1")):
             gq: List = []
             self._call(gq, "msr3d_spatial_geometry_f32", ptr(w["obj_locs" + q]), ptr(w["anchor_locs" + q]), ptr(w["anchor_ori" + q]),
                        B, L, self.dist_norm, 1, ptr(w["pw_n"]), ptr(w["ff_n"]), ptr(w["sz_n"]), tag="geometry")
@@ -630,6 +640,12 @@ class FusedPrompter:
                        None if anchor else P("object_orientation_feat"), None if anchor else P("object_type_embedding.weight"),
                        ptr(w["xhat_l"]), ptr(w["rstd_l"]), ptr(w["xhat_s"]), ptr(w["rstd_s"]), ptr(w["qpos"]), ptr(w["qpos0"]),
                        ptr(w["x_in"][0]), tag="qpos", side=True)
+            if self.sit_embed:
+                self._call(pre_prog, "msr3d_situation_embed_fwd_f32", ptr(w["anchor_locs"]), ptr(w["anchor_ori"]), B, L,
+                           P("loc_embedding_encoder.0.weight"), P("loc_embedding_encoder.0.bias"),
+                           P("loc_embedding_encoder.1.weight"), P("loc_embedding_encoder.1.bias"),
+                           P("orientation_encoder.weight"), P("orientation_encoder.bias"), ptr(w["xhat_sit"]),
+                           ptr(w["rstd_sit"]), ptr(w["qpos"]), ptr(w["x_in"][0]), tag="situation_embed", side=True)
         pre_prog[1:1] = geo                              # geometry first on the side stream
         assert pre_prog[0][0] == "memset"
         cond = self.fusion == "cond"
@@ -825,6 +841,12 @@ class FusedPrompter:
                        G("loc_embedding_encoder.0.bias"), tag="qpos_bwd")
             self._gemm(bwd, ptr(w["dh1"]), (1, H), ptr(w["ff"]), (1, 64), H, 63, M, G("loc_embedding_encoder.0.weight"), 63,
                        accumulate=2, ksplit=4, tag="dWloc", wgrad=True)
+            if self.sit_embed:
+                self._call(bwd, "msr3d_situation_embed_bwd_f32", dq[0], dq[1], dq[2], ptr(w["anchor_locs"]),
+                           ptr(w["anchor_ori"]), B, L, P("loc_embedding_encoder.1.weight"), ptr(w["xhat_sit"]),
+                           ptr(w["rstd_sit"]), G("loc_embedding_encoder.0.weight"), G("loc_embedding_encoder.0.bias"),
+                           G("loc_embedding_encoder.1.weight"), G("loc_embedding_encoder.1.bias"),
+                           G("orientation_encoder.weight"), G("orientation_encoder.bias"), tag="situation_embed_bwd")
         bwd.append(("join", None, (), None, False))
         # prefetch schedule: the geometry was computed beside the encoder of the previous step
         # and the gradient buffer is cleared beside the input encoders (first written by the backward pass)
@@ -937,7 +959,8 @@ class FusedPrompter:
 
     def prime(self, batch, upstream):
         """Fill the pipeline: encode `batch` now; its transformer step happens in the next call."""
-        assert not self.n_anchor, "agent-token situation modes run the sequential schedule (forward / backward / train_step)"
+        assert not (self.n_anchor or self.sit_embed), \
+            "the non-shipped situation modes run the sequential schedule (forward / backward / train_step)"
         self.stage_points(batch)
         self._encode("emb_next")
         self.stage_scene(batch, upstream)
@@ -1099,7 +1122,8 @@ class FusedPrompter:
 
     def prime2(self, batch0, up0, batch1, up1):
         """Fill both stages: encode batch0 now, park batch1's points in slot 1."""
-        assert not self.n_anchor, "agent-token situation modes run the sequential schedule (forward / backward / train_step)"
+        assert not (self.n_anchor or self.sit_embed), \
+            "the non-shipped situation modes run the sequential schedule (forward / backward / train_step)"
         main = torch.cuda.current_stream()
         self._slot_free[0].record()
         self._slot_free[1].record()

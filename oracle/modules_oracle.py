@@ -270,7 +270,7 @@ def ose3d_situation(sd: SD, data: dict, *, n_head: int = 8, num_layers: int = 3,
     """OSE3DSituation.forward (model/ose3d_situation.py:288-454) for vision_backbone
     'gtpcd', use_spatial_attn/use_anchor/use_orientation True, attn_flat off, and
     situation_type in {'as_transform_for_objects' (shipped, configs/msr3d.yaml:177),
-    'as_object' (LEO baseline, configs/leo_3_dataset.yaml:180-181), 'as_object_add_loc'}.
+    'as_object' (LEO baseline, configs/leo_3_dataset.yaml:180-181), 'as_object_add_loc', 'as_embedding'}.
 
     Returns (obj_tokens (B,N',H), obj_masks (B,N') bool with True = valid)."""
     if obj_embeds is None:
@@ -304,6 +304,14 @@ def ose3d_situation(sd: SD, data: dict, *, n_head: int = 8, num_layers: int = 3,
         elif situation_type == "as_object_add_loc":
             qpos = linear_ln(sd, "loc_embedding_encoder", fourier_features(loc[..., :3])) + \
                 linear_ln(sd, "size_embedding_encoder", loc[..., 3:])
+        elif situation_type == "as_embedding":  # :385-393 situation embedding added to every object
+            n_tok = loc.size(1)
+            s_loc = linear_ln(sd, "loc_embedding_encoder",
+                              fourier_features(data["anchor_locs"].unsqueeze(1).expand(-1, n_tok, -1)))
+            s_ori = F.linear(fourier_features(data["anchor_orientation"].unsqueeze(1).expand(-1, n_tok, -1)),
+                             sd["orientation_encoder.weight"], sd["orientation_encoder.bias"])
+            qpos = linear_ln(sd, "loc_embedding_encoder", fourier_features(loc[..., :3])) + \
+                linear_ln(sd, "size_embedding_encoder", loc[..., 3:]) + s_ori + s_loc
         elif situation_type == "as_transform_for_objects":  # :399-404
             tl = to_agent_frame(loc[..., :3], data["anchor_locs"], data["anchor_orientation"])
             qpos = linear_ln(sd, "loc_embedding_encoder", fourier_features(tl)) + \

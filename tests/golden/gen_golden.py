@@ -158,6 +158,9 @@ def main():
     if "--fusions" in sys.argv:          # only the fixtures added in round 2 (the others stay byte-stable)
         run_fusion_cases(ref)
         return
+    if "--as-embedding" in sys.argv:
+        run_case(ref, "prompter_as_embedding", 2, 7, 256, seed=7007, situation_type="as_embedding")
+        return
     spec = run_case(ref, "prompter_cfg1", 1, 8, 256, seed=1001)
     with open(os.path.join(HERE, "state_dict_spec.json"), "w") as fh:
         json.dump(spec, fh, indent=0)

@@ -162,3 +162,23 @@ def test_module_call_as_object_runs_on_the_kernels():
     up = torch.randn(out["obj_tokens"].shape, generator=torch.Generator().manual_seed(seed + 77))
     (out["obj_tokens"] * up.cuda()).sum().backward()
     _check_fixture(model, out["obj_tokens"].detach(), fx)
+
+
+def test_engine_as_embedding_matches_reference_and_oracle():
+    """as_embedding: the situation as one embedding per scene added to every object's query position."""
+    fx = helpers.golden("prompter_as_embedding")
+    seed, B, O, P = int(fx["seed"]), int(fx["B"]), int(fx["O"]), int(fx["P"])
+    model = configs.build_prompter(seed, "as_embedding", device="cuda")
+    sd = configs.model_state_dict(model, seed)
+    batch = synthetic.make_batch(B, O, P, seed=seed)
+    up = torch.randn(B, O, 256, generator=torch.Generator().manual_seed(seed + 77))
+    eng, tokens = _run_engine(model, batch, up)
+    e, worst_fx = _check_fixture(model, tokens, fx)
+    emb = eng.ws["emb"].cpu().view(B, O, -1)
+    want_tokens, want = _oracle_grads(sd, batch, up, obj_embeds=emb, situation_type="as_embedding")
+    e64 = helpers.rel_err(tokens.cpu(), want_tokens)
+    worst = _check_grads(model, want, tol=3e-4)
+    own = _check_grads_own_scale(model, want, tol=2e-3)
+    print(f"as_embedding: tokens vs reference {e:.2e} (grads {worst_fx:.2e}), vs fp64 oracle {e64:.2e}; worst grad "
+          f"{worst[0]} {worst[1]:.2e}, own scale {own[0]} {own[1]:.2e}")
+    assert e64 < 1e-4

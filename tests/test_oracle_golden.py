@@ -15,6 +15,7 @@ CASES = {
     "prompter_mid": "as_transform_for_objects",
     "prompter_as_object": "as_object",
     "prompter_add_loc": "as_object_add_loc",
+    "prompter_as_embedding": "as_embedding",
 }
 
 
@@ -80,7 +81,7 @@ def test_encoder_outputs_match_reference(golden_dir, sd_spec):
     np.testing.assert_allclose(cls.numpy(), fx["obj_sem_cls"], rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("name", ["prompter_cfg1", "prompter_as_object"])
+@pytest.mark.parametrize("name", ["prompter_cfg1", "prompter_as_object", "prompter_as_embedding"])
 def test_prompter_backward_matches_reference(golden_dir, sd_spec, name):
     fx = _load(golden_dir, name)
     seed = int(fx["seed"])
