@@ -35,7 +35,7 @@ int set_error(int code, const char *fmt, ...) {
 }  // namespace msr3d
 
 MSR3D_API const char *msr3d_last_error(void) { return msr3d::g_err; }
-MSR3D_API int msr3d_abi_version(void) { return 3; }
+MSR3D_API int msr3d_abi_version(void) { return 4; }
 MSR3D_API unsigned long long msr3d_launch_count(void) {
   return msr3d::g_launches.load(std::memory_order_relaxed);
 }

@@ -14,7 +14,7 @@ def test_gemm_desc_mirror_matches_library():
     lib = _C.lib()
     lib.msr3d_sizeof_gemm_desc.restype = ctypes.c_int
     assert ctypes.sizeof(GemmDesc) == lib.msr3d_sizeof_gemm_desc()
-    assert lib.msr3d_abi_version() == 3
+    assert lib.msr3d_abi_version() == 4
 
 
 def test_splice_rejects_cpu_tensors():
