@@ -520,6 +520,12 @@ int msr3d_allreduce_sum_f32(const msr3d_allreduce_desc *d, long long begin, long
 int msr3d_grad_norm_finalize_f32(const float *partials, int world, int nblocks0, int nblocks1, float grad_scale,
                                  const float *extra_sumsq, float *state, unsigned long long *seed_counter,
                                  const int *gate, msr3d_stream_t stream);
+/* Single-GPU counterpart of the norm partials msr3d_allreduce_sum_f32 pushes along: squared norm of g[begin, end)
+ * (float4-aligned range) as `nblocks` block partials of rank 0, channel `channel`, in the layout
+ * msr3d_grad_norm_finalize_f32(world = 1) sums.  The early gradient bucket can be done on a side stream under the
+ * backward of layer 0. */
+int msr3d_sumsq_partials_f32(const float *g, long long begin, long long end, int nblocks, float *partials, int channel,
+                             msr3d_stream_t stream);
 /* Input staging of a pipelined step in one launch (csrc/stage.cu): rotate k: a[i] <- b[i]; b[i] <- c[i] (c nullable)
  * over rot_n[k] floats; copy k: dst[i] <- src[i]; masks (bytes): the same rotation and key_pad[i] <- !a[i]. */
 #define MSR3D_STAGE_MAX 8

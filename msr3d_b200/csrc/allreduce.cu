@@ -162,6 +162,33 @@ grad_norm_finalize_kernel(const float *__restrict__ partials, int world, int nb0
   }
 }
 
+// Squared norm of g[begin, end) as `nblocks` block partials in the layout grad_norm_finalize_kernel reads (rank 0 of
+// channel `channel`): the single-GPU counterpart of the partials the exchange kernel pushes along — lets the norm of the
+// early gradient bucket be taken on a side stream under the backward of layer 0, so that only the late bucket is left for
+// the tail of the step.  Deterministic (fixed order inside a block, fixed block -> slot mapping).
+__global__ void __launch_bounds__(256)
+sumsq_partials_kernel(const float *__restrict__ g, long long begin, long long end, float *__restrict__ partials,
+                      int channel) {
+  pdl_sync();
+  __shared__ float w[8];
+  const long long n4 = (end - begin) >> 2;
+  const float4 *g4 = reinterpret_cast<const float4 *>(g + begin);
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 q = g4[i];
+    s += (q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += w[i];
+    partials[((size_t)channel * kArMaxWorld + 0) * kArMaxBlocks + blockIdx.x] = t;
+  }
+}
+
 }  // namespace msr3d
 
 using namespace msr3d;
@@ -192,4 +219,14 @@ MSR3D_API int msr3d_grad_norm_finalize_f32(const float *partials, int world, int
   launch_pdl(grad_norm_finalize_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, partials, world, nblocks0, nblocks1, grad_scale,
              extra_sumsq, state, seed_counter, gate);
   return check_launch("grad_norm_finalize");
+}
+
+MSR3D_API int msr3d_sumsq_partials_f32(const float *g, long long begin, long long end, int nblocks, float *partials,
+                                       int channel, msr3d_stream_t stream) {
+  MSR3D_REQUIRE(g && partials && channel >= 0 && channel < 2 && nblocks >= 1 && nblocks <= kArMaxBlocks,
+                "sumsq_partials: bad arguments");
+  MSR3D_REQUIRE(begin >= 0 && end >= begin && (begin & 3) == 0 && ((end - begin) & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(g) & 15) == 0, "sumsq_partials: range must be float4 aligned");
+  launch_pdl(sumsq_partials_kernel, dim3(nblocks), dim3(256), 0, (cudaStream_t)stream, g, begin, end, partials, channel);
+  return check_launch("sumsq_partials");
 }

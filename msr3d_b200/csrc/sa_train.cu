@@ -22,8 +22,8 @@
 
 namespace msr3d {
 
-constexpr int kStatCols = 32;      // columns per CTA of the statistics kernels
-constexpr int kStatLanes = 8;      // row lanes per CTA (256 threads)
+constexpr int kStatCols = 32;      // columns per CTA of the statistics kernels (8 threads x one float4)
+constexpr int kStatLanes = 32;     // row lanes per CTA (256 threads)
 
 __global__ void __launch_bounds__(256)
 group_rows_kernel(const float *__restrict__ xyz, int ld_xyz, const float *__restrict__ feat, int ld_feat, int C,
@@ -54,32 +54,49 @@ group_rows_kernel(const float *__restrict__ xyz, int ld_xyz, const float *__rest
   if (lane < ldx - (3 + C)) o[3 + C + lane] = 0.f;      // pad columns (row pitch rounded up for TMA): zero
 }
 
+// Column sums over a chunk of rows.  Thread = (row lane 0..31, column quad 0..7): one 16 B load per row, four rows of
+// 128 B per warp instruction, the row loop unrolled so that several loads are in flight; the 32 row lanes meet in
+// shared memory.  (The first version read one float per thread with 8 row lanes and 64 chunks: 15-25 % of the HBM
+// rate on the 126 MB activations of SA1, tools/profile_enc_train.py.)
+template <int NARR>
+__device__ __forceinline__ void stat_reduce_store(const float4 (&acc)[NARR], float *__restrict__ partial, int C, int c0) {
+  __shared__ float s[NARR][kStatLanes][kStatCols + 1];
+  const int cq = threadIdx.x & 7, rl = threadIdx.x >> 3;
+#pragma unroll
+  for (int a = 0; a < NARR; ++a) {
+    s[a][rl][cq * 4 + 0] = acc[a].x; s[a][rl][cq * 4 + 1] = acc[a].y;
+    s[a][rl][cq * 4 + 2] = acc[a].z; s[a][rl][cq * 4 + 3] = acc[a].w;
+  }
+  __syncthreads();
+  if (threadIdx.x < kStatCols * NARR) {
+    const int a = threadIdx.x / kStatCols, col = threadIdx.x % kStatCols;
+    if (c0 + col < C) {
+      float t = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < kStatLanes; ++i) t += s[a][i][col];      // fixed order: deterministic
+      partial[((size_t)blockIdx.y * NARR + a) * C + c0 + col] = t;
+    }
+  }
+}
+
 // partial[chunk][0][c] = sum_rows Z, partial[chunk][1][c] = sum_rows Z^2 over the rows of the chunk
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const float *__restrict__ Z, long long rows, int C, int rows_per_chunk, float *__restrict__ partial) {
   pdl_sync();
-  __shared__ float s1[kStatLanes][kStatCols], s2[kStatLanes][kStatCols];
-  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const int c = blockIdx.x * kStatCols + cl;
+  const int cq = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * kStatCols, c = c0 + cq * 4;
   const long long r0 = (long long)blockIdx.y * rows_per_chunk;
   const long long r1 = min(rows, r0 + rows_per_chunk);
-  float a = 0.f, q = 0.f;
-  if (c < C)
+  float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+  if (c < C) {
+#pragma unroll 4
     for (long long r = r0 + rl; r < r1; r += kStatLanes) {
-      const float v = Z[r * C + c];
-      a += v;
-      q += v * v;
+      const float4 v = *reinterpret_cast<const float4 *>(Z + r * C + c);
+      acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+      acc[1].x += v.x * v.x; acc[1].y += v.y * v.y; acc[1].z += v.z * v.z; acc[1].w += v.w * v.w;
     }
-  s1[rl][cl] = a;
-  s2[rl][cl] = q;
-  __syncthreads();
-  if (rl == 0 && c < C) {
-    float ta = 0.f, tq = 0.f;
-#pragma unroll
-    for (int i = 0; i < kStatLanes; ++i) { ta += s1[i][cl]; tq += s2[i][cl]; }
-    partial[((size_t)blockIdx.y * 2 + 0) * C + c] = ta;
-    partial[((size_t)blockIdx.y * 2 + 1) * C + c] = tq;
   }
+  stat_reduce_store<2>(acc, partial, C, c0);
 }
 
 // stats[0][c] = mean, stats[1][c] = rstd; running statistics as nn.BatchNorm2d (momentum m, unbiased variance)
@@ -118,10 +135,11 @@ __global__ void bn_running_stats_kernel(const float *__restrict__ running_mean, 
 
 __global__ void __launch_bounds__(256)
 bn_relu_kernel(const float *__restrict__ Z, const float *__restrict__ stats, const float *__restrict__ gamma,
-               const float *__restrict__ beta, long long n4, int C, float *__restrict__ Y) {
+               const float *__restrict__ beta, long long n4_, int C, float *__restrict__ Y) {
   pdl_sync();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)((i * 4) % C);
+  const unsigned n4 = (unsigned)n4_, cols4 = (unsigned)C >> 2;       // 32-bit index arithmetic (n4 < 2^31 checked on the host)
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const int c = (int)((i % cols4) << 2);
     const float4 z = reinterpret_cast<const float4 *>(Z)[i];
     const float zz[4] = {z.x, z.y, z.z, z.w};
     float y[4];
@@ -153,18 +171,26 @@ maxpool_rows_kernel(const float *__restrict__ Y, long long groups, int S, int C,
   arg[i] = bi;
 }
 
-// dY[row, c] = dOut[group, c] if this row won the max (and the ReLU in front of the pool was active) else 0
+// dY[row, c] = dOut[group, c] if this row won the max (and the ReLU in front of the pool was active) else 0.
+// Thread = (row, column quad): one 16 B arg-max load, one 16 B store; 32-bit index arithmetic (the first version did
+// four 64-bit divisions per element and ran at a quarter of the store rate).
 __global__ void __launch_bounds__(256)
 maxpool_rows_bwd_kernel(const float *__restrict__ dOut, long long ld_dout, const int *__restrict__ arg,
-                        long long rows, int S, int C, float *__restrict__ dY) {
+                        long long rows_, int S, int C, float *__restrict__ dY) {
   pdl_sync();
-  const long long n = rows * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / C;
-    const int c = (int)(i % C);
-    const long long g = row / S;
-    const int s = (int)(row % S);
-    dY[i] = arg[g * C + c] == s ? dOut[g * ld_dout + c] : 0.f;
+  const unsigned cols4 = (unsigned)C >> 2, n4 = (unsigned)rows_ * cols4, uS = (unsigned)S;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const unsigned row = i / cols4, c = (i - row * cols4) << 2;
+    const unsigned g = row / uS;
+    const int s = (int)(row - g * uS);
+    const int4 a = *reinterpret_cast<const int4 *>(arg + (size_t)g * C + c);
+    const float *d = dOut + (size_t)g * ld_dout + c;          // may be a column slice of a wider matrix: scalar loads
+    float4 o;
+    o.x = a.x == s ? d[0] : 0.f;
+    o.y = a.y == s ? d[1] : 0.f;
+    o.z = a.z == s ? d[2] : 0.f;
+    o.w = a.w == s ? d[3] : 0.f;
+    *reinterpret_cast<float4 *>(dY + (size_t)row * C + c) = o;
   }
 }
 
@@ -174,30 +200,25 @@ bn_bwd_stats_kernel(const float *__restrict__ dY, const float *__restrict__ Y, c
                     const float *__restrict__ stats, long long rows, int C, int rows_per_chunk,
                     float *__restrict__ partial) {
   pdl_sync();
-  __shared__ float s1[kStatLanes][kStatCols], s2[kStatLanes][kStatCols];
-  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const int c = blockIdx.x * kStatCols + cl;
+  const int cq = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * kStatCols, c = c0 + cq * 4;
   const long long r0 = (long long)blockIdx.y * rows_per_chunk;
   const long long r1 = min(rows, r0 + rows_per_chunk);
-  float a = 0.f, q = 0.f;
+  float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
   if (c < C) {
-    const float mean = stats[c], rstd = stats[C + c];
+    const float4 mean = *reinterpret_cast<const float4 *>(stats + c), rstd = *reinterpret_cast<const float4 *>(stats + C + c);
+#pragma unroll 2
     for (long long r = r0 + rl; r < r1; r += kStatLanes) {
-      const float g = Y[r * C + c] > 0.f ? dY[r * C + c] : 0.f;
-      a += g;
-      q += g * ((Z[r * C + c] - mean) * rstd);
+      const float4 d = *reinterpret_cast<const float4 *>(dY + r * C + c);
+      const float4 y = *reinterpret_cast<const float4 *>(Y + r * C + c);
+      const float4 z = *reinterpret_cast<const float4 *>(Z + r * C + c);
+      const float gx = y.x > 0.f ? d.x : 0.f, gy = y.y > 0.f ? d.y : 0.f, gz = y.z > 0.f ? d.z : 0.f, gw = y.w > 0.f ? d.w : 0.f;
+      acc[0].x += gx; acc[0].y += gy; acc[0].z += gz; acc[0].w += gw;
+      acc[1].x += gx * ((z.x - mean.x) * rstd.x); acc[1].y += gy * ((z.y - mean.y) * rstd.y);
+      acc[1].z += gz * ((z.z - mean.z) * rstd.z); acc[1].w += gw * ((z.w - mean.w) * rstd.w);
     }
   }
-  s1[rl][cl] = a;
-  s2[rl][cl] = q;
-  __syncthreads();
-  if (rl == 0 && c < C) {
-    float ta = 0.f, tq = 0.f;
-#pragma unroll
-    for (int i = 0; i < kStatLanes; ++i) { ta += s1[i][cl]; tq += s2[i][cl]; }
-    partial[((size_t)blockIdx.y * 2 + 0) * C + c] = ta;
-    partial[((size_t)blockIdx.y * 2 + 1) * C + c] = tq;
-  }
+  stat_reduce_store<2>(acc, partial, C, c0);
 }
 
 // bstat[0][c] = mean(g), bstat[1][c] = mean(g xhat) (zero for eval-mode BN); dgamma += sum g xhat, dbeta += sum g
@@ -221,10 +242,11 @@ __global__ void bn_bwd_finalize_kernel(const float *__restrict__ partial, int ch
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float *dY /* may alias dZ */, const float *__restrict__ Y, const float *__restrict__ Z,
                     const float *__restrict__ stats, const float *__restrict__ bstat,
-                    const float *__restrict__ gamma, long long n4, int C, float *dZ) {
+                    const float *__restrict__ gamma, long long n4_, int C, float *dZ) {
   pdl_sync();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)((i * 4) % C);
+  const unsigned n4 = (unsigned)n4_, cols4 = (unsigned)C >> 2;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const int c = (int)((i % cols4) << 2);
     const float4 d4 = reinterpret_cast<const float4 *>(dY)[i];
     const float4 y4 = reinterpret_cast<const float4 *>(Y)[i];
     const float4 z4 = reinterpret_cast<const float4 *>(Z)[i];
@@ -241,26 +263,47 @@ bn_bwd_apply_kernel(const float *dY /* may alias dZ */, const float *__restrict_
   }
 }
 
-// d feat[b, j, 0:C] = sum over pairs p of cloud b with idx[b, p] == j of dX[b, p, col0 : col0 + C]
-__global__ void __launch_bounds__(256)
+// d feat[b, j, 0:C] = sum over pairs p of cloud b with idx[b, p] == j of dX[b, p, col0 : col0 + C].
+// One CTA per cloud.  The pairs are cut into `nsl` consecutive slices, each with its own [N][C] accumulator in shared
+// memory; a thread owns (slice, channel), walks its slice in order with eight loads in flight, and the slices are added
+// in a fixed order at the end: deterministic, no atomics.  (One slice and one load in flight: 214 us for 240 clouds.)
+__global__ void __launch_bounds__(512)
 group_rows_bwd_kernel(const float *__restrict__ dX, int ldx, int col0, const int *__restrict__ idx, int pairs, int N,
-                      int C, float *__restrict__ dfeat) {
+                      int C, int nsl, float *__restrict__ dfeat) {
   pdl_sync();
-  extern __shared__ float acc[];     // [N][C]
+  extern __shared__ float acc[];     // [nsl][N][C], then int idx[pairs]
+  int *s_idx = reinterpret_cast<int *>(acc + (size_t)nsl * N * C);
   const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < N * C; i += blockDim.x) acc[i] = 0.f;
+  for (int i = threadIdx.x; i < nsl * N * C; i += blockDim.x) acc[i] = 0.f;
+  for (int i = threadIdx.x; i < pairs; i += blockDim.x) s_idx[i] = idx[(size_t)b * pairs + i];
   __syncthreads();
-  const int *ib = idx + (size_t)b * pairs;
+  const int tps = blockDim.x / nsl;                   // threads per slice
+  const int sl = threadIdx.x / tps, t = threadIdx.x % tps;
+  const int pps = (pairs + nsl - 1) / nsl;
+  const int p0 = sl * pps, p1 = min(pairs, p0 + pps);
   const float *xb = dX + (size_t)b * pairs * ldx + col0;
-  for (int c = threadIdx.x; c < C; c += blockDim.x)      // thread owns its channels: no conflicts, fixed order
-    for (int p = 0; p < pairs; ++p) acc[ib[p] * C + c] += xb[(size_t)p * ldx + c];
+  float *a = acc + (size_t)sl * N * C;
+  for (int c = t; c < C; c += tps) {
+    for (int p = p0; p < p1; p += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = p + u < p1 ? xb[(size_t)(p + u) * ldx + c] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (p + u < p1) a[s_idx[p + u] * C + c] += v[u];
+    }
+  }
   __syncthreads();
   float *o = dfeat + (size_t)b * N * C;
-  for (int i = threadIdx.x; i < N * C; i += blockDim.x) o[i] = acc[i];
+  for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
+    float tsum = acc[i];
+    for (int q = 1; q < nsl; ++q) tsum += acc[(size_t)q * N * C + i];
+    o[i] = tsum;
+  }
 }
 
 static inline int stat_chunks(long long rows, int *rows_per_chunk) {
-  int chunks = (int)std::min<long long>(64, std::max<long long>(1, rows / 256));
+  int chunks = (int)std::min<long long>(512, std::max<long long>(1, rows / 256));
   *rows_per_chunk = (int)((rows + chunks - 1) / chunks);
   return chunks;
 }
@@ -290,7 +333,7 @@ MSR3D_API int msr3d_bn_train_fwd_f32(const float *Z, long long rows, int C, cons
                                      float *running_mean, float *running_var, int batch_stats, float eps,
                                      float momentum, float *partial, float *stats, float *Y, msr3d_stream_t stream) {
   MSR3D_REQUIRE(Z && gamma && beta && partial && stats && Y, "bn_train_fwd: null pointer");
-  MSR3D_REQUIRE(rows >= 1 && C >= 4 && C % 4 == 0, "bn_train_fwd: rows=%lld C=%d (C %% 4)", rows, C);
+  MSR3D_REQUIRE(rows >= 1 && C >= 4 && C % 4 == 0 && rows * C / 4 < (1ll << 31), "bn_train_fwd: rows=%lld C=%d (C %% 4, rows * C < 2^33)", rows, C);
   MSR3D_REQUIRE(batch_stats || (running_mean && running_var), "bn_train_fwd: eval mode needs running statistics");
   cudaStream_t st = (cudaStream_t)stream;
   if (batch_stats) {
@@ -313,7 +356,7 @@ MSR3D_API int msr3d_bn_train_bwd_f32(const float *dY, const float *Y, const floa
                                      const float *gamma, const float *stats, int batch_stats, float *partial,
                                      float *bstat, float *dgamma, float *dbeta, float *dZ, msr3d_stream_t stream) {
   MSR3D_REQUIRE(dY && Y && Z && gamma && stats && partial && bstat && dgamma && dbeta && dZ, "bn_train_bwd: null pointer");
-  MSR3D_REQUIRE(rows >= 1 && C >= 4 && C % 4 == 0, "bn_train_bwd: rows=%lld C=%d (C %% 4)", rows, C);
+  MSR3D_REQUIRE(rows >= 1 && C >= 4 && C % 4 == 0 && rows * C / 4 < (1ll << 31), "bn_train_bwd: rows=%lld C=%d (C %% 4, rows * C < 2^33)", rows, C);
   cudaStream_t st = (cudaStream_t)stream;
   int rpc;
   const int chunks = stat_chunks(rows, &rpc);
@@ -338,7 +381,8 @@ MSR3D_API int msr3d_maxpool_rows_f32(const float *Y, long long groups, int S, in
 
 MSR3D_API int msr3d_maxpool_rows_bwd_f32(const float *dOut, long long ld_dout, const int32_t *arg, long long groups,
                                          int S, int C, float *dY, msr3d_stream_t stream) {
-  MSR3D_REQUIRE(dOut && arg && dY && S >= 1 && C >= 1 && ld_dout >= C, "maxpool_rows_bwd: bad args");
+  MSR3D_REQUIRE(dOut && arg && dY && S >= 1 && C >= 4 && C % 4 == 0 && ld_dout >= C && groups * S * C / 4 < (1ll << 31),
+                "maxpool_rows_bwd: bad args (C %% 4, rows * C < 2^33)");
   if (groups <= 0) return MSR3D_OK;
   const long long n = groups * S * C;
   const int grid = (int)std::min<long long>((n + 255) / 256, kNumSMs * 8);
@@ -351,15 +395,18 @@ MSR3D_API int msr3d_sa_group_rows_bwd_f32(const float *dX, int ldx, int col0, co
                                           int N, int C, float *dfeat, msr3d_stream_t stream) {
   MSR3D_REQUIRE(dX && idx && dfeat && pairs >= 1 && N >= 1 && C >= 1 && col0 >= 0 && col0 + C <= ldx,
                 "sa_group_rows_bwd: bad args");
-  const size_t smem = (size_t)N * C * sizeof(float);
-  MSR3D_REQUIRE(smem <= 200 * 1024, "sa_group_rows_bwd: N*C = %d floats do not fit in shared memory", N * C);
+  const size_t one = (size_t)N * C * sizeof(float), idx_bytes = (size_t)pairs * sizeof(int);
+  MSR3D_REQUIRE(one + idx_bytes <= 200 * 1024, "sa_group_rows_bwd: N*C = %d floats do not fit in shared memory", N * C);
   if (B <= 0) return MSR3D_OK;
+  int nsl = 4;
+  while (nsl > 1 && nsl * one + idx_bytes > 200 * 1024) nsl >>= 1;
+  const size_t smem = nsl * one + idx_bytes;
   static bool configured = false;
   if (!configured) {
     MSR3D_CUDA(cudaFuncSetAttribute(group_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  launch_pdl(group_rows_bwd_kernel, dim3(B), dim3(256), smem, (cudaStream_t)stream, dX, ldx, col0, (const int *)idx, pairs,
-             N, C, dfeat);
+  launch_pdl(group_rows_bwd_kernel, dim3(B), dim3(512), smem, (cudaStream_t)stream, dX, ldx, col0, (const int *)idx, pairs,
+             N, C, nsl, dfeat);
   return check_launch("sa_group_rows_bwd");
 }

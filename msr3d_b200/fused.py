@@ -99,6 +99,7 @@ _C.register_protos({
     "msr3d_allreduce_sum_f32": [ctypes.POINTER(AllreduceDesc), c_ll, c_ll, c_int, c_vp],
     "msr3d_grad_norm_finalize_f32": [c_vp, c_int, c_int, c_int, c_float, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_split_tf32_f32": [c_vp, c_vp, c_vp, c_ll, c_vp],
+    "msr3d_sumsq_partials_f32": [c_vp, c_ll, c_ll, c_int, c_vp, c_int, c_vp],
     "msr3d_ffn_pair_fwd_ps_f32": [c_vp] * 8 + [c_int, c_int, c_ull, c_vp, c_float, c_uint, c_vp, c_vp, c_vp, c_int, c_vp],
     "msr3d_ffn_pair_bwd_ps_f32": [c_vp] * 7 + [c_int, c_int, c_vp, c_vp, c_int, c_vp],
     "msr3d_attn_block_fwd_ps_f32": [c_vp] * 9 + [c_int, c_int] + [c_vp] * 4 + [c_ull, c_vp, c_float, c_uint, c_uint]
@@ -298,6 +299,13 @@ class FusedPrompter:
         # host in between: +64 us per step already at 2 GPUs).  MSR3D_DDP_IN_GRAPH=0 restores that.
         self.ddp_in_graph = _os.environ.get("MSR3D_DDP_IN_GRAPH", "1") == "1"
         self.comm_stream = torch.cuda.Stream(device=dev) if world_size > 1 else None
+        # single GPU, prefetch schedule: squared-norm partials of the early gradient bucket (layers >= 1) on a side stream
+        # under the backward of layer 0; the tail of the step then sums 1.4 M instead of 4.2 M gradients before AdamW
+        # (the peer-memory exchange does the same at N > 1).  A/B: MSR3D_EARLY_NORM=0/1
+        self.early_norm = _os.environ.get("MSR3D_EARLY_NORM", "0") == "1" and world_size == 1 and self.accum_steps == 1
+        if self.early_norm:
+            self.norm_stream = (self.partition.stream(0) if self.partition is not None else torch.cuda.Stream(device=dev))
+            self.norm_partials = torch.zeros(2 * AR_MAX_WORLD * AR_MAX_BLOCKS, dtype=torch.float32, device=dev)
         self._side_pending = [False, False]
         self.extra_sumsq: Optional[torch.Tensor] = None   # see optimizer_step()
         # one engine per model: the drop-in module call (autograd.py) reuses this one instead of re-homing
@@ -401,6 +409,28 @@ class FusedPrompter:
         for k, side in enumerate((self.side_stream, self.side_stream2)):
             if self._side_pending[k]:
                 self.comm_stream.wait_stream(side)
+
+    def _backward_optimizer_early_norm(self, main, split):
+        """Single-GPU tail of the prefetch step with the early bucket's norm taken beside the backward of layer 0."""
+        (e0, e1), (l0, l1) = self.bucket_early, self.bucket_late
+        nb0, nb1 = 48, 32
+        ns, st = self.norm_stream, self.opt_state
+        self._run(self.bwd_prog[:self.bwd_split])
+        ns.wait_stream(main)
+        for k, side in enumerate((self.side_stream, self.side_stream2)):
+            if self._side_pending[k]:
+                ns.wait_stream(side)
+        _C.call("msr3d_sumsq_partials_f32", self.flat_g.data_ptr(), e0, e1, nb0, self.norm_partials.data_ptr(), 0, ns.cuda_stream)
+        self._run(self.bwd_prog[self.bwd_split:])          # ends with a join of the weight-gradient streams
+        _C.call("msr3d_sumsq_partials_f32", self.flat_g.data_ptr(), l0, l1, nb1, self.norm_partials.data_ptr(), 1, main.cuda_stream)
+        main.wait_stream(ns)
+        ex = self.extra_sumsq.data_ptr() if self.extra_sumsq is not None else None
+        _C.call("msr3d_grad_norm_finalize_f32", self.norm_partials.data_ptr(), 1, nb0, nb1, 1.0, ex, st.data_ptr(),
+                self.seed_counter.data_ptr(), None, main.cuda_stream)
+        n, (d0, d1) = self.n_opt, self.decay_range
+        _C.call("msr3d_adamw_apply_f32", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                n, d0, d1, 1.0, st.data_ptr(), self.flat_big.data_ptr() if split else None,
+                self.flat_small.data_ptr() if split else None, None, main.cuda_stream)
 
     def _allreduce_p2p(self, channel, begin, end, nblocks, stream):
         rc = _C.lib().msr3d_allreduce_sum_f32(ctypes.byref(self.p2p["desc"][channel]), begin, end, nblocks, stream.cuda_stream)
@@ -1037,6 +1067,8 @@ class FusedPrompter:
                     self.backward()
                     dist.all_reduce(self.flat_g[:self.n_opt])
                 self.optimizer_step(split=split_w)
+        elif self.world_size == 1 and depth2 and self.early_norm and self.bucket_early[1] > self.bucket_early[0]:
+            self._backward_optimizer_early_norm(main, split=self.attn_block_active)
         else:
             self.backward()
             if self.world_size == 1:
