@@ -99,18 +99,39 @@ bn_stats_kernel(const float *__restrict__ Z, long long rows, int C, int rows_per
   stat_reduce_store<2>(acc, partial, C, c0);
 }
 
-// stats[0][c] = mean, stats[1][c] = rstd; running statistics as nn.BatchNorm2d (momentum m, unbiased variance)
-__global__ void bn_finalize_kernel(const float *__restrict__ partial, int chunks, int C, long long rows, float eps,
-                                   float momentum, float *__restrict__ stats, float *__restrict__ running_mean,
-                                   float *__restrict__ running_var) {
-  pdl_sync();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double a = 0.0, q = 0.0;
-  for (int k = 0; k < chunks; ++k) {
-    a += (double)partial[((size_t)k * 2 + 0) * C + c];
-    q += (double)partial[((size_t)k * 2 + 1) * C + c];
+// Sum of the chunk partials of 32 columns: thread = (column, lane of 8); lane l adds chunks l, l + 8, ... in double
+// (independent loads), the eight lanes meet in shared memory in a fixed order.  (One thread per column walking all
+// chunks was a chain of dependent L2 round trips: 68 us per BatchNorm layer for a kernel that moves 0.5 MB, ncu.)
+__device__ __forceinline__ void sum_partials(const float *__restrict__ partial, int chunks, int C, int c, double &a,
+                                             double &q) {
+  __shared__ double s_a[8][kStatCols], s_q[8][kStatCols];
+  const int col = threadIdx.x & 31, l = threadIdx.x >> 5;
+  double ta = 0.0, tq = 0.0;
+  if (c < C) {
+#pragma unroll 4
+    for (int k = l; k < chunks; k += 8) {
+      ta += (double)partial[((size_t)k * 2 + 0) * C + c];
+      tq += (double)partial[((size_t)k * 2 + 1) * C + c];
+    }
   }
+  s_a[l][col] = ta;
+  s_q[l][col] = tq;
+  __syncthreads();
+  a = 0.0; q = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a += s_a[i][col]; q += s_q[i][col]; }
+}
+
+// stats[0][c] = mean, stats[1][c] = rstd; running statistics as nn.BatchNorm2d (momentum m, unbiased variance)
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float *__restrict__ partial, int chunks, int C, long long rows, float eps,
+                   float momentum, float *__restrict__ stats, float *__restrict__ running_mean,
+                   float *__restrict__ running_var) {
+  pdl_sync();
+  const int c = blockIdx.x * kStatCols + (threadIdx.x & 31);
+  double a, q;
+  sum_partials(partial, chunks, C, c, a, q);
+  if (c >= C || threadIdx.x >= kStatCols) return;
   const double mean = a / (double)rows;
   double var = q / (double)rows - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -138,6 +159,7 @@ bn_relu_kernel(const float *__restrict__ Z, const float *__restrict__ stats, con
                const float *__restrict__ beta, long long n4_, int C, float *__restrict__ Y) {
   pdl_sync();
   const unsigned n4 = (unsigned)n4_, cols4 = (unsigned)C >> 2;       // 32-bit index arithmetic (n4 < 2^31 checked on the host)
+#pragma unroll 4
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     const int c = (int)((i % cols4) << 2);
     const float4 z = reinterpret_cast<const float4 *>(Z)[i];
@@ -222,17 +244,15 @@ bn_bwd_stats_kernel(const float *__restrict__ dY, const float *__restrict__ Y, c
 }
 
 // bstat[0][c] = mean(g), bstat[1][c] = mean(g xhat) (zero for eval-mode BN); dgamma += sum g xhat, dbeta += sum g
-__global__ void bn_bwd_finalize_kernel(const float *__restrict__ partial, int chunks, int C, long long rows,
-                                       int batch_stats, float *__restrict__ bstat, float *__restrict__ dgamma,
-                                       float *__restrict__ dbeta) {
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float *__restrict__ partial, int chunks, int C, long long rows,
+                       int batch_stats, float *__restrict__ bstat, float *__restrict__ dgamma,
+                       float *__restrict__ dbeta) {
   pdl_sync();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double a = 0.0, q = 0.0;
-  for (int k = 0; k < chunks; ++k) {
-    a += (double)partial[((size_t)k * 2 + 0) * C + c];
-    q += (double)partial[((size_t)k * 2 + 1) * C + c];
-  }
+  const int c = blockIdx.x * kStatCols + (threadIdx.x & 31);
+  double a, q;
+  sum_partials(partial, chunks, C, c, a, q);
+  if (c >= C || threadIdx.x >= kStatCols) return;
   dbeta[c] += (float)a;
   dgamma[c] += (float)q;
   bstat[c] = batch_stats ? (float)(a / (double)rows) : 0.f;
@@ -245,6 +265,7 @@ bn_bwd_apply_kernel(const float *dY /* may alias dZ */, const float *__restrict_
                     const float *__restrict__ gamma, long long n4_, int C, float *dZ) {
   pdl_sync();
   const unsigned n4 = (unsigned)n4_, cols4 = (unsigned)C >> 2;
+#pragma unroll 2
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     const int c = (int)((i % cols4) << 2);
     const float4 d4 = reinterpret_cast<const float4 *>(dY)[i];
@@ -303,7 +324,7 @@ group_rows_bwd_kernel(const float *__restrict__ dX, int ldx, int col0, const int
 }
 
 static inline int stat_chunks(long long rows, int *rows_per_chunk) {
-  int chunks = (int)std::min<long long>(512, std::max<long long>(1, rows / 256));
+  int chunks = (int)std::min<long long>(256, std::max<long long>(1, rows / 256));
   *rows_per_chunk = (int)((rows + chunks - 1) / chunks);
   return chunks;
 }
@@ -340,7 +361,7 @@ MSR3D_API int msr3d_bn_train_fwd_f32(const float *Z, long long rows, int C, cons
     int rpc;
     const int chunks = stat_chunks(rows, &rpc);
     launch_pdl(bn_stats_kernel, dim3(ceil_div(C, kStatCols), chunks), dim3(256), 0, st, Z, rows, C, rpc, partial);
-    launch_pdl(bn_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, st, (const float *)partial, chunks, C, rows, eps,
+    launch_pdl(bn_finalize_kernel, dim3(ceil_div(C, kStatCols)), dim3(256), 0, st, (const float *)partial, chunks, C, rows, eps,
                momentum, stats, running_mean, running_var);
   } else {
     launch_pdl(bn_running_stats_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, st, (const float *)running_mean,
@@ -362,7 +383,7 @@ MSR3D_API int msr3d_bn_train_bwd_f32(const float *dY, const float *Y, const floa
   const int chunks = stat_chunks(rows, &rpc);
   launch_pdl(bn_bwd_stats_kernel, dim3(ceil_div(C, kStatCols), chunks), dim3(256), 0, st, dY, Y, Z, stats, rows, C, rpc,
              partial);
-  launch_pdl(bn_bwd_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, st, (const float *)partial, chunks, C, rows,
+  launch_pdl(bn_bwd_finalize_kernel, dim3(ceil_div(C, kStatCols)), dim3(256), 0, st, (const float *)partial, chunks, C, rows,
              batch_stats, bstat, dgamma, dbeta);
   const long long n4 = rows * C / 4;
   const int grid = (int)std::min<long long>((n4 + 255) / 256, kNumSMs * 8);

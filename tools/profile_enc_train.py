@@ -12,13 +12,18 @@ from msr3d_b200.encoder import PcdObjEncoder  # noqa: E402
 
 
 def main():
-    B, O, P = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (4, 60, 1024)
+    nums = [a for a in sys.argv[1:] if a.isdigit()]
+    B, O, P = (int(a) for a in nums[:3]) if len(nums) >= 3 else (4, 60, 1024)
     enc = PcdObjEncoder(freeze=False)
     spec = [(k, list(v.shape), "int64" if v.dtype == torch.int64 else "float32") for k, v in enc.state_dict().items()]
     enc.load_state_dict(synthetic.make_state_dict(spec, 7))
     enc = enc.cuda().train()
     batch = synthetic.make_batch(B, O, P, seed=7).to("cuda")
     G = torch.randn(B, O, 768, device="cuda")
+    if "--plain" in sys.argv:            # one forward + backward without CUPTI (to be wrapped in ncu)
+        enc.encode(batch.obj_fts).backward(G)
+        torch.cuda.synchronize()
+        return
     for _ in range(3):
         enc.encode(batch.obj_fts).backward(G)
     torch.cuda.synchronize()
