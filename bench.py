@@ -219,6 +219,39 @@ def bench_unfrozen_encoder(dev, B, O, P, flush):
     return res
 
 
+def bench_module_call(dev, B, O, P, flush):
+    """The drop-in call a trainer makes (north star: same nn.Module signature): OSE3DSituation.forward(data_dict) +
+    loss.backward() through msr3d_b200/autograd.py, per micro-batch, inputs resident — with the two programs replayed as
+    CUDA graphs (default) and launched eagerly through ctypes."""
+    import msr3d_b200
+    from msr3d_b200 import synthetic
+    model = msr3d_b200.build_model(prompter_cfg())
+    model.load_state_dict(synthetic.make_state_dict(load_spec(), 0), strict=True)
+    model = model.to(dev).train()
+    batch = synthetic.make_batch(B, O, P, seed=2200).to(dev)
+    up = torch.randn(B, O, 256, device=dev, generator=torch.Generator(dev).manual_seed(4))
+    res = {"workload": f"model(data_dict)['obj_tokens'] + backward, {B} x {O} x {P}, training mode, L2 flushed"}
+    for key, flag in (("graphs_ms", "1"), ("eager_ms", "0")):
+        os.environ["MSR3D_MODULE_GRAPH"] = flag
+        ts = []
+        for i in range(13):
+            for p in model.parameters():
+                p.grad = None
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = model(batch.as_dict())["obj_tokens"]
+            out.backward(up)
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(a.elapsed_time(b))
+        res[key] = round(statistics.median(ts), 4)
+    os.environ["MSR3D_MODULE_GRAPH"] = "1"
+    res["samples_per_s_graphs"] = round(B / (res["graphs_ms"] * 1e-3), 1)
+    return res
+
+
 def bench_splice(dev, B, L, flush, cores):
     """SURVEY.md §8f-1 (the step after the path): llm_proj + fp16 scatter into the LLM input and its
     backward, at config-2 shapes (T = 204 prompt positions, D = 4096).  Per-call CUDA-event times with
@@ -404,7 +437,8 @@ def main():
                             ("secondary", lambda: secondary_configs(args, dev, world, flush)),
                             ("llm_context", lambda: llm_context(dev, B, O, ms_step)),
                             ("next_rows", lambda: {"scene_splice (SURVEY 8f-1)": bench_splice(dev, B, O, flush, os.cpu_count() or 1),
-                                                   "unfrozen_encoder (SURVEY 8f-2)": bench_unfrozen_encoder(dev, B, O, P, flush)})):
+                                                   "unfrozen_encoder (SURVEY 8f-2)": bench_unfrozen_encoder(dev, B, O, P, flush),
+                                                   "module_call (drop-in nn.Module + autograd)": bench_module_call(dev, B, O, P, flush)})):
                 try:
                     line[key] = fn()
                 except Exception as e:  # noqa: BLE001

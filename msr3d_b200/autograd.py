@@ -70,8 +70,16 @@ class _FusedPrompterFn(torch.autograd.Function):
         w["obj_masks"].copy_(obj_masks)
         w["anchor_locs"].copy_(anchor_locs)
         w["anchor_ori"].copy_(anchor_ori)
-        tokens = engine.forward(emb.detach() if emb is not None else None)
+        g = engine.module_graph("fwd", emb is not None)
+        if g is None:
+            tokens = engine.forward(emb.detach() if emb is not None else None)
+        else:                                   # the captured forward program (fused.py: module_graph)
+            if emb is not None:
+                w["emb"].copy_(emb.detach().reshape(w["emb"].shape))
+            g.replay()
+            tokens = engine._tokens()
         ctx.need_d_emb = emb is not None and emb.requires_grad
+        ctx.external_emb = emb is not None
         ctx.engine = engine
         ctx.n_params = len(params)
         ctx.key = engine._key
@@ -87,8 +95,13 @@ class _FusedPrompterFn(torch.autograd.Function):
         e.ws["upstream"].copy_(grad_tokens.reshape(e.ws["upstream"].shape))
         # engine-API engines alias p.grad to flat_g: keep what autograd has accumulated there so far
         saved = e.flat_g[:e.n_opt].clone() if e.alias_grads else None
-        e.flat_g.zero_()
-        d_emb = e.backward(need_d_emb=ctx.need_d_emb)
+        g = e.module_graph("bwd", ctx.external_emb)
+        if g is None:
+            e.flat_g.zero_()
+            d_emb = e.backward(need_d_emb=ctx.need_d_emb)
+        else:
+            g.replay()
+            d_emb = e.d_emb() if ctx.need_d_emb else None
         flat = e.flat_g[:e.n_opt].clone()          # fresh storage: autograd may keep / steal what we return
         if saved is not None:
             e.flat_g[:e.n_opt].copy_(saved)

@@ -348,9 +348,12 @@ class PointNetPP(nn.Module):
         bns = [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)]
         return all(not m.training for m in bns)
 
-    def _packed_weights(self):
+    def _packed_weights_key(self):
         params = list(self.parameters()) + list(self.buffers())
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        return tuple((p.data_ptr(), p._version) for p in params)
+
+    def _packed_weights(self):
+        key = self._packed_weights_key()
         if key != self._pack_key:
             sd = {k: v.detach() for k, v in self.state_dict().items()}
             packed = {}

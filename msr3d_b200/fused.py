@@ -1277,18 +1277,69 @@ class FusedPrompter:
         """obj_masks as OSE3DSituation returns them (ose3d_situation.py:452): True = valid token, agent token included."""
         return self.ws["key_pad"] == 0
 
+    # ------------------------------------------------------------------ drop-in module call as CUDA graphs
+    # OSE3DSituation.forward / loss.backward() (autograd.py) launch ~40 / ~45 kernels through ctypes: at config 2 the host
+    # needs longer to issue them than the GPU to run them.  The two programs are therefore captured once per
+    # (shape, mode) and replayed; inputs, parameters, saved activations and the upstream gradient all live in static
+    # buffers already.  The packed weights of the frozen encoder are part of the capture: a change of the encoder's
+    # parameters (checkpoint load) invalidates the graphs.
+    def module_graph(self, which: str, external_emb: bool):
+        import os
+        if os.environ.get("MSR3D_MODULE_GRAPH", "1") != "1":
+            return None
+        cache = self.__dict__.setdefault("_module_graphs", {})
+        enc_key = None if external_emb else self.model.obj_encoder.pcd_net._packed_weights_key()
+        key = (which, self._key, external_emb)
+        hit = cache.get(key)
+        if hit is not None and hit[0] == enc_key and hit[2] is self.ws:
+            return hit[1]
+
+        def body():
+            if which == "fwd":
+                w = self.ws
+                if not self.n_anchor:
+                    torch.logical_not(w["obj_masks"], out=w["key_pad"].view(torch.bool))
+                self._run(self.pre_prog)
+                if not external_emb:
+                    self._encode()
+                self._run(self.fwd_prog)
+            else:
+                self.flat_g.zero_()
+                self._run(self.bwd_prog)
+        saved_g = self.flat_g.clone()
+        s_ = torch.cuda.Stream(device=self.dev)
+        s_.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s_):
+            body()                          # warm-up: lazy allocations (encoder workspaces, packed weights) happen here
+        torch.cuda.current_stream().wait_stream(s_)
+        torch.cuda.synchronize()
+        if not external_emb:
+            enc_key = self.model.obj_encoder.pcd_net._packed_weights_key()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            body()
+        if which == "bwd":
+            self.flat_g.copy_(saved_g)
+        cache[key] = (enc_key, g, self.ws)
+        return g
+
     def backward(self, need_d_emb: bool = False):
         """Backward from ws['upstream']; accumulates into the flat gradient buffer.  need_d_emb: also returns the
         gradient wrt the object embeddings (B * objects, E) = d(projection output) . W_proj — what an unfrozen encoder
         back-propagates (tensor-core GEMM, msr3d_gemm_tc_f32)."""
         self._run(self.bwd_prog)
-        if not need_d_emb:
-            return None
+        return self.d_emb() if need_d_emb else None
+
+    def d_emb(self):
+        """Gradient wrt the object embeddings from the finished backward (see backward)."""
         w = self.ws
         dpr = w["dproj"] if self.n_anchor else w["dx"][0]
         Wp = self.by_name["obj_linear_projection.weight"].detach()
         with torch.cuda.device(self.dev):
             return gemm_tc(dpr, Wp.t(), split=6)
+
+    def _tokens_after_replay(self):
+        return self._tokens()
 
     def refresh_split(self):
         """tf32 big / small images of the parameters (after anything but optimizer_step(split=True) changed them)."""
