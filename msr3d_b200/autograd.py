@@ -105,14 +105,14 @@ class _FusedPrompterFn(torch.autograd.Function):
         flat = e.flat_g[:e.n_opt].clone()          # fresh storage: autograd may keep / steal what we return
         if saved is not None:
             e.flat_g[:e.n_opt].copy_(saved)
-        grads = []
-        for n in e.autograd_names:
-            off = e.offs.get(n)
-            p = e.by_name[n]
-            if off is None or off >= e.n_opt:
-                grads.append(None)                 # parameters the shipped mode never touches
-            else:
-                grads.append(flat[off:off + p.numel()].view_as(p))
+        plan = e.__dict__.get("_grad_plan")
+        if plan is None:                           # (offset, numel, shape) per autograd input, None = never touched
+            plan = []
+            for n in e.autograd_names:
+                off, p = e.offs.get(n), e.by_name[n]
+                plan.append(None if off is None or off >= e.n_opt else (off, p.numel(), p.shape))
+            e.__dict__["_grad_plan"] = plan
+        grads = [None if t is None else flat[t[0]:t[0] + t[1]].view(t[2]) for t in plan]
         if d_emb is not None:
             B, L = e.ws["obj_locs"].shape[:2]
             d_emb = d_emb.view(B, L, -1)

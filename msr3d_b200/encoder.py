@@ -349,7 +349,10 @@ class PointNetPP(nn.Module):
         return all(not m.training for m in bns)
 
     def _packed_weights_key(self):
-        params = list(self.parameters()) + list(self.buffers())
+        params = self.__dict__.get("_pk_tensors")
+        if params is None or len(params) != self.__dict__.get("_pk_count", -1):
+            params = list(self.parameters()) + list(self.buffers())
+            self.__dict__["_pk_tensors"], self.__dict__["_pk_count"] = params, len(params)
         return tuple((p.data_ptr(), p._version) for p in params)
 
     def _packed_weights(self):

@@ -1288,11 +1288,14 @@ class FusedPrompter:
         if os.environ.get("MSR3D_MODULE_GRAPH", "1") != "1":
             return None
         cache = self.__dict__.setdefault("_module_graphs", {})
-        enc_key = None if external_emb else self.model.obj_encoder.pcd_net._packed_weights_key()
+        with_enc = which == "fwd" and not external_emb      # only the forward program contains the encoder
+        enc_key = self.model.obj_encoder.pcd_net._packed_weights_key() if with_enc else None
         key = (which, self._key, external_emb)
         hit = cache.get(key)
         if hit is not None and hit[0] == enc_key and hit[2] is self.ws:
             return hit[1]
+        if torch.cuda.is_current_stream_capturing():
+            return None
 
         def body():
             if which == "fwd":
@@ -1313,11 +1316,18 @@ class FusedPrompter:
             body()                          # warm-up: lazy allocations (encoder workspaces, packed weights) happen here
         torch.cuda.current_stream().wait_stream(s_)
         torch.cuda.synchronize()
-        if not external_emb:
+        if with_enc:
             enc_key = self.model.obj_encoder.pcd_net._packed_weights_key()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, capture_error_mode="thread_local"):
-            body()
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                body()
+        except Exception as e:  # noqa: BLE001 — e.g. called while another capture is under way: stay on eager launches
+            import warnings
+            warnings.warn(f"msr3d_b200: module-call graph capture failed ({type(e).__name__}: {e}); launching eagerly")
+            for k in range(2):
+                self._side_pending[k] = False
+            g = None
         if which == "bwd":
             self.flat_g.copy_(saved_g)
         cache[key] = (enc_key, g, self.ws)
