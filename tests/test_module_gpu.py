@@ -72,3 +72,45 @@ def test_module_call_falls_back_to_the_module_tree_when_unsupported():
     assert ag.eligible(model, batch.as_dict()) is not None
     out = model(batch.as_dict())
     assert out["obj_tokens"].shape == (1, 8, 256)
+
+
+def test_module_call_graph_replay_equals_eager_and_follows_weight_changes(monkeypatch):
+    """The captured forward / backward programs of the drop-in call (fused.module_graph) give the eager launches'
+    results bit for bit, see parameter updates (static buffers), and are re-captured when the frozen encoder changes."""
+    def run(model, batch, up):
+        for p in model.parameters():
+            p.grad = None
+        out = model(batch.as_dict())["obj_tokens"]
+        out.backward(up)
+        return out.detach().clone(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    batch = synthetic.make_batch(2, 12, 256, seed=6).to("cuda")
+    up = torch.randn(2, 12, 256, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+    model = helpers.build_prompter(6, device="cuda")                      # eval mode: no dropout, deterministic masks
+    monkeypatch.setenv("MSR3D_MODULE_GRAPH", "0")
+    t_eager, g_eager = run(model, batch, up)
+    monkeypatch.setenv("MSR3D_MODULE_GRAPH", "1")
+    t_graph, g_graph = run(model, batch, up)                              # captures
+    t_graph2, g_graph2 = run(model, batch, up)                            # replays
+    assert len(model._fused_engine._module_graphs) == 2
+    # split-K reductions (red.add) are not bit-reproducible run to run: same tolerance as graph-vs-eager elsewhere
+    assert helpers.rel_err(t_graph, t_eager) < 2e-4 and helpers.rel_err(t_graph2, t_eager) < 2e-4
+    gmax = max(float(g.abs().max()) for g in g_eager.values())
+    for n, g in g_eager.items():
+        scale = max(float(g.abs().max()), 1e-3 * gmax)       # d w_ks.bias is analytically zero: floor the scale
+        assert float((g_graph2[n] - g).abs().max()) / scale < 2e-3, n
+    # a parameter update is seen by the replay (parameters are static views)
+    with torch.no_grad():
+        model.spatial_encoder[0].linear1.weight.mul_(1.5)
+    t_new, _ = run(model, batch, up)
+    assert helpers.rel_err(t_new, t_graph2) > 1e-4
+    # a change of the frozen encoder's weights re-captures the forward graph (its packed weights are part of it)
+    before = model._fused_engine._module_graphs[("fwd", model._fused_engine._key, False)][1]
+    with torch.no_grad():
+        model.obj_encoder.pcd_net.fc.bias.add_(0.25)
+    t_enc, _ = run(model, batch, up)
+    after = model._fused_engine._module_graphs[("fwd", model._fused_engine._key, False)][1]
+    assert after is not before and helpers.rel_err(t_enc, t_new) > 1e-4
+    monkeypatch.setenv("MSR3D_MODULE_GRAPH", "0")
+    t_chk, _ = run(model, batch, up)
+    assert helpers.rel_err(t_enc, t_chk) < 2e-4
