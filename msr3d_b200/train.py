@@ -74,9 +74,13 @@ class HotPathTrainer:
         loss = self._step(batch, upstream)
         if loss_out is not None:
             if self.pipeline == "prefetch":
+                # its own stream: on the H2D copy stream the 4-byte read-back (which waits for the end of this step)
+                # sat in front of the next batch's point-cloud copy and pushed it a whole step back (+12 us per step,
+                # tools/e2e_gap.py)
                 ev = torch.cuda.Event()
                 ev.record()
-                cs = self.engine.copy_stream
+                cs = self.engine.__dict__.setdefault("d2h_stream", None) or torch.cuda.Stream(device=self.engine.dev)
+                self.engine.d2h_stream = cs
                 cs.wait_event(ev)
                 with torch.cuda.stream(cs):
                     loss_out.copy_(loss, non_blocking=True)
