@@ -391,8 +391,10 @@ class PointNetPP(nn.Module):
 
     @torch.no_grad()
     def forward_fused(self, pc, split: Optional[int] = None, trace: Optional[dict] = None,
-                      out: Optional[torch.Tensor] = None):
-        """pc: (B', P, 6) contiguous CUDA f32 -> (B', C_out).  11 kernel launches."""
+                      out: Optional[torch.Tensor] = None, aux_stream: Optional[torch.cuda.Stream] = None):
+        """pc: (B', P, 6) contiguous CUDA f32 -> (B', C_out).  11 kernel launches.
+        aux_stream: the grouping of level 2 (FPS + ball query on the 32 centres of level 1) depends on the centres only,
+        not on level 1's MLP — it is issued there, beside the SA1 kernel, and joined in front of SA2."""
         pk = self._packed_weights()
         Bc, P, _ = pc.shape
         dev = pc.device
@@ -401,9 +403,19 @@ class PointNetPP(nn.Module):
         # level 1: neighbours are the raw (x,y,z,r,g,b) records
         fps1, xyz1, ball1 = ops.sa_group(pc, np1, self.sa_radii[0], 32, tag="sa1_group")
         f1 = self._workspace("f1", (Bc, np1, w1[-1]), dev)
+        if aux_stream is not None:
+            main = torch.cuda.current_stream()
+            aux_stream.wait_stream(main)
+            with torch.cuda.stream(aux_stream):
+                fps2, xyz2, ball2 = ops.sa_group(xyz1, np2, self.sa_radii[1], 32, tag="sa2_group")
+            for t in (fps2, xyz2, ball2):
+                t.record_stream(main)
         ops.sa_mlp_fused(pc[..., 3:], 3, pc, xyz1, ball1, pk["sa1"][0], pk["sa1"][1], w1[1:], f1, split, tag="sa1_mlp")
         # level 2
-        fps2, xyz2, ball2 = ops.sa_group(xyz1, np2, self.sa_radii[1], 32, tag="sa2_group")
+        if aux_stream is not None:
+            torch.cuda.current_stream().wait_stream(aux_stream)
+        else:
+            fps2, xyz2, ball2 = ops.sa_group(xyz1, np2, self.sa_radii[1], 32, tag="sa2_group")
         k3 = w2[-1] + 3
         ld3 = -(-k3 // 16) * 16
         x3 = self._workspace("x3", (Bc, np2, ld3), dev, zero=True)   # [feat | xyz | 0]: GroupAll operand

@@ -968,7 +968,20 @@ class FusedPrompter:
         enc = self.model.obj_encoder
         B, L, Pn, _ = w[src_key].shape
         enc.freeze_bn(enc.pcd_net)
-        enc.pcd_net.forward_fused(w[src_key].view(B * L, Pn, 6), self.enc_split, out=w[out_key])
+        enc.pcd_net.forward_fused(w[src_key].view(B * L, Pn, 6), self.enc_split, out=w[out_key], aux_stream=self._enc_aux())
+
+    def _enc_aux(self):
+        """Second stream of the encoder (same SM partition when there is one): level 2's grouping runs beside SA1's MLP.
+        A/B: MSR3D_ENC_FORK=0/1."""
+        if "_enc_aux_stream" not in self.__dict__:
+            import os
+            if os.environ.get("MSR3D_ENC_FORK", "0") != "1":
+                self._enc_aux_stream = None
+            elif self.partition is not None:
+                self._enc_aux_stream = self.partition.stream(1)
+            else:
+                self._enc_aux_stream = torch.cuda.Stream(device=self.dev)
+        return self._enc_aux_stream
 
     # ------------------------------------------------------------------ pipelined mode
     # The encoder is frozen, so the embedding of batch i+1 does not depend on the update made with
