@@ -147,3 +147,32 @@ def test_unfrozen_prompter_module_call_end_to_end():
         worst = max(worst, (n, err), key=lambda t: t[1])
     print(f"unfrozen prompter end to end: tokens {e:.2e}, worst grad (norm) {worst[0]} {worst[1]:.2e}")
     assert e < TOL and worst[1] < 2e-3
+
+
+@pytest.mark.parametrize("clouds,P", [(1, 64), (3, 32), (2, 2048)])
+def test_unfrozen_encoder_edge_shapes(clouds, P):
+    """One cloud (batch statistics over a single cloud), P = 32 = npoint of level 1 (every point is a centre, ball
+    queries padded with the first hit), P = 2048 (config 4) against the oracle's autograd."""
+    from oracle import ext_oracle as eo, modules_oracle as mo
+    seed = 40 + clouds + P
+    enc = _encoder(seed)
+    batch = synthetic.make_batch(1, clouds, P, seed=seed, pad_frac=0.0)
+    G = torch.randn(1, clouds, 768, generator=torch.Generator().manual_seed(seed + 77))
+    sd0 = {k: v.detach().cpu().clone() for k, v in enc.state_dict().items()}
+    emb = enc.encode(batch.obj_fts.cuda())
+    (emb * G.cuda()).sum().backward()
+    eo.set_threads(8); torch.set_num_threads(8)
+    sd = {"e." + k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+          for k, v in sd0.items()}
+    stats = {}
+    want = mo.pointnetpp(sd, "e.pcd_net", batch.obj_fts.reshape(clouds, P, 6), (32, 16, None), (32, 32, None),
+                         (0.2, 0.4, None), bn_stats=stats)
+    (want.view(1, clouds, -1) * G).sum().backward()
+    e = helpers.rel_err(emb.detach().cpu(), want.detach().view(1, clouds, -1))
+    worst = ("", 0.0)
+    for n, p in enc.pcd_net.named_parameters():
+        w = sd["e.pcd_net." + n].grad
+        err = float((p.grad.cpu() - w).norm() / w.norm().clamp_min(1e-12))
+        worst = max(worst, (n, err), key=lambda t: t[1])
+    print(f"unfrozen encoder {clouds} x {P}: emb {e:.2e}, worst grad (norm) {worst[0]} {worst[1]:.2e}")
+    assert e < TOL and worst[1] < 1e-2

@@ -182,3 +182,61 @@ def test_engine_as_embedding_matches_reference_and_oracle():
     print(f"as_embedding: tokens vs reference {e:.2e} (grads {worst_fx:.2e}), vs fp64 oracle {e64:.2e}; worst grad "
           f"{worst[0]} {worst[1]:.2e}, own scale {own[0]} {own[1]:.2e}")
     assert e64 < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Edge cases of the round-2 rows: ragged / extreme token counts, a single valid key, both attention paths of the
+# agent-token modes.
+# ---------------------------------------------------------------------------------------------------------------
+def _engine_vs_oracle(model, batch, up, tol_tokens=1e-4, tol_grad=TOL, **okw):
+    B, O = batch.obj_fts.shape[:2]
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    eng, tokens = _run_engine(model, batch, up)
+    emb = eng.ws["emb"].cpu().view(B, O, -1)
+    want_tokens, want = _oracle_grads(sd, batch, up, obj_embeds=emb, **okw)
+    e = helpers.rel_err(tokens.cpu(), want_tokens)
+    worst = _check_grads(model, want, tol=tol_grad)
+    assert e < tol_tokens, e
+    return eng, e, worst
+
+
+@pytest.mark.parametrize("fusion,O", [("mul", 1), ("add", 1), ("ctx", 37), ("add", 37), ("bias", 100), ("mul", 128)])
+def test_other_fusions_ragged_and_extreme_token_counts(fusion, O):
+    """1 object (softmax over one key), 37 (not a multiple of the warp width), 100 and 128 = kMaxL tokens."""
+    seed = 900 + O
+    model = configs.build_prompter(seed, device="cuda", fusion=fusion)
+    batch = synthetic.make_batch(1, O, 64, seed=seed)
+    up = torch.randn(1, O, 256, generator=torch.Generator().manual_seed(seed + 77))
+    eng, e, worst = _engine_vs_oracle(model, batch, up, fusion=fusion)
+    print(f"fusion {fusion} O={O}: tokens {e:.2e}, worst grad {worst[0]} {worst[1]:.2e}")
+
+
+@pytest.mark.parametrize("fusion", ["cond", "mul", "bias", "ctx", "add"])
+def test_single_valid_key_per_scene(fusion):
+    """Every object but one is padding (obj_masks False): each softmax has one live key; padded QUERY rows still produce
+    finite tokens exactly as the reference does."""
+    seed, B, O = 515, 2, 12
+    model = configs.build_prompter(seed, device="cuda", fusion=fusion)
+    batch = synthetic.make_batch(B, O, 64, seed=seed)
+    batch.obj_masks[:] = False
+    batch.obj_masks[0, 3] = True
+    batch.obj_masks[1, 0] = True
+    up = torch.randn(B, O, 256, generator=torch.Generator().manual_seed(seed + 77))
+    eng, e, worst = _engine_vs_oracle(model, batch, up, fusion=fusion)
+    assert torch.isfinite(eng.ws["tokens"]).all()
+    print(f"single valid key, fusion {fusion}: tokens {e:.2e}, worst grad {worst[0]} {worst[1]:.2e}")
+
+
+@pytest.mark.parametrize("stype,O", [("as_object", 63), ("as_object", 64), ("as_object_add_loc", 64), ("as_embedding", 64)])
+def test_situation_modes_on_both_attention_paths(stype, O):
+    """63 objects + agent = 64 tokens: the last size the one-launch attention block and the tensor-core attention
+    backward take; 64 objects + agent = 65 tokens: the four-launch path with the cluster backward."""
+    seed = 700 + O
+    model = configs.build_prompter(seed, stype, device="cuda")
+    batch = synthetic.make_batch(1, O, 64, seed=seed)
+    n_tok = O + (1 if stype.startswith("as_object") else 0)
+    up = torch.randn(1, n_tok, 256, generator=torch.Generator().manual_seed(seed + 77))
+    eng, e, worst = _engine_vs_oracle(model, batch, up, situation_type=stype)
+    assert eng.attn_block_active == (n_tok <= 64)
+    print(f"{stype} O={O} ({n_tok} tokens, attention block {eng.attn_block_active}): tokens {e:.2e}, "
+          f"worst grad {worst[0]} {worst[1]:.2e}")
