@@ -149,7 +149,15 @@ def _pool(lv: _Level, Y, S):
     return out
 
 
-def _mlp_backward(lv: _Level, d_pool, layers, grads, need_dx: bool):
+def _sink(sinks, key_tensor, like):
+    """Destination of a parameter gradient: the caller's buffer (accumulated into: the engine's flat gradient views) or a
+    fresh zero tensor (autograd mode)."""
+    if sinks is not None and id(key_tensor) in sinks:
+        return sinks[id(key_tensor)]
+    return torch.zeros_like(like)
+
+
+def _mlp_backward(lv: _Level, d_pool, layers, grads, need_dx: bool, sinks=None):
     """d_pool (groups, C_last) -> parameter gradients of the level's three blocks (+ dX if needed)."""
     dev = d_pool.device
     rows = lv.X.shape[0]
@@ -166,7 +174,7 @@ def _mlp_backward(lv: _Level, d_pool, layers, grads, need_dx: bool):
         chunks = _C.lib().msr3d_sa_train_stat_chunks(rows)
         partial = torch.empty(2 * cout * max(1, chunks), dtype=torch.float32, device=dev)
         bstat = torch.empty(2, cout, dtype=torch.float32, device=dev)
-        dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(beta)
+        dgamma, dbeta = _sink(sinks, gamma, gamma), _sink(sinks, beta, beta)
         # ReLU + BatchNorm backward, in place: dY becomes dZ
         _C.call("msr3d_bn_train_bwd_f32", dY.data_ptr(), lv.Y[j].data_ptr(), lv.Z[j].data_ptr(), rows, cout,
                 gamma.data_ptr(), lv.stats[j].data_ptr(), int(lv.batch_stats[j]), partial.data_ptr(), bstat.data_ptr(),
@@ -174,11 +182,14 @@ def _mlp_backward(lv: _Level, d_pool, layers, grads, need_dx: bool):
         dZ = dY
         # dW (cout, cin) = dZ^T X: contraction over every row -> split-K with red.add into a zeroed buffer
         cin = W2.shape[1]
-        dW = torch.zeros(cout, cin, dtype=torch.float32, device=dev)
+        cin_real = W.numel() // cout
+        dst = _sink(sinks, W, W).view(cout, cin_real)
+        dW = dst if cin_real == cin else torch.zeros(cout, cin, dtype=torch.float32, device=dev)
         tiles = -(-cout // 128) * -(-cin // 64)
         _gemm(dZ.t(), x_in.t(), WGRAD_SPLIT, out=dW, accumulate=2, ksplit=_ksplit_for(rows, tiles))
-        cin_real = W.numel() // cout
-        grads[id(W)] = (dW if cin_real == cin else dW[:, :cin_real].contiguous()).view_as(W)
+        if dW is not dst:
+            dst.add_(dW[:, :cin_real])            # padded pitch (first layer of a level): fold the real columns in
+        grads[id(W)] = dst.view_as(W)
         grads[id(gamma)], grads[id(beta)] = dgamma, dbeta
         if j > 0 or need_dx:
             dY = _gemm(dZ, W2.t(), DGRAD_SPLIT)                # dX (rows, cin) = dZ W
@@ -187,96 +198,124 @@ def _mlp_backward(lv: _Level, d_pool, layers, grads, need_dx: bool):
     return dX
 
 
+class _State:
+    """Everything the backward needs from one forward (explicit API: the engine keeps it; autograd mode: the ctx)."""
+    __slots__ = ("levels", "layer_sets", "g", "dims")
+
+
+def forward_explicit(net, pc: torch.Tensor):
+    """(B', P, 6) -> ((B', C_out) embeddings, state) without autograd bookkeeping."""
+    pc = pc.contiguous().float()
+    Bc, P, _ = pc.shape
+    dev = pc.device
+    np1, np2 = net.sa_n_points[0], net.sa_n_points[1]
+    S1, S2 = net.sa_n_samples[0], net.sa_n_samples[1]
+    layer_sets = []
+    for sa in net.encoder:
+        ls = []
+        for blk in sa.mlps[0]:
+            bn = blk[1][0]
+            ls.append((blk[0].weight.detach(), bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var))
+        layer_sets.append(ls)
+    bn_mode = [[blk[1][0].training for blk in sa.mlps[0]] for sa in net.encoder]
+    with torch.cuda.device(dev):
+        # ---- level 1: neighbours are the raw (x, y, z, r, g, b) records
+        _, xyz1, ball1 = ops.sa_group(pc, np1, net.sa_radii[0], S1)
+        l1 = _Level()
+        rows1 = Bc * np1 * S1
+        X1 = torch.empty(rows1, _pad4(6), dtype=torch.float32, device=dev)
+        _C.call("msr3d_sa_group_rows_f32", pc.data_ptr(), 6, pc.data_ptr() + 12, 6, 3, xyz1.data_ptr(),
+                ball1.data_ptr(), P, np1, S1, rows1, X1.data_ptr(), X1.shape[1], _st())
+        f1 = _pool(l1, _mlp_forward(l1, X1, layer_sets[0], bn_mode[0]), S1)          # (Bc * np1, C1)
+        C1 = f1.shape[1]
+        # ---- level 2
+        _, xyz2, ball2 = ops.sa_group(xyz1, np2, net.sa_radii[1], S2)
+        l2 = _Level()
+        rows2 = Bc * np2 * S2
+        X2 = torch.empty(rows2, _pad4(3 + C1), dtype=torch.float32, device=dev)
+        _C.call("msr3d_sa_group_rows_f32", xyz1.data_ptr(), 3, f1.data_ptr(), C1, C1, xyz2.data_ptr(),
+                ball2.data_ptr(), np1, np2, S2, rows2, X2.data_ptr(), X2.shape[1], _st())
+        l2.idx, l2.n_src, l2.pairs = ball2, np1, np2 * S2
+        f2 = _pool(l2, _mlp_forward(l2, X2, layer_sets[1], bn_mode[1]), S2)          # (Bc * np2, C2)
+        C2 = f2.shape[1]
+        # ---- level 3 (GroupAll): rows = the np2 remaining points of every cloud, raw xyz
+        l3 = _Level()
+        rows3 = Bc * np2
+        X3 = torch.empty(rows3, _pad4(3 + C2), dtype=torch.float32, device=dev)
+        _C.call("msr3d_sa_group_rows_f32", xyz2.data_ptr(), 3, f2.data_ptr(), C2, C2, None, None, np2, 1, 1, rows3,
+                X3.data_ptr(), X3.shape[1], _st())
+        g = _pool(l3, _mlp_forward(l3, X3, layer_sets[2], bn_mode[2]), np2)          # (Bc, C3)
+        out = _gemm(g, net.fc.weight.detach(), FWD_SPLIT, bias=net.fc.bias.detach())
+    for sa, modes in zip(net.encoder, bn_mode):
+        for blk, tr in zip(sa.mlps[0], modes):
+            if tr:
+                blk[1][0].num_batches_tracked += 1
+    st = _State()
+    st.levels, st.layer_sets, st.g, st.dims = (l1, l2, l3), layer_sets, g, (Bc, np1, np2, C1, C2)
+    return out, st
+
+
+def backward_explicit(net, st: _State, d_out: torch.Tensor, sinks=None) -> dict:
+    """Gradients of the 29 PointNet++ parameters from d(embeddings): {id(parameter): gradient}.  `sinks` maps
+    id(parameter) to a tensor the gradient is ACCUMULATED into (the engine's views of its flat gradient buffer, already
+    zeroed); without it every gradient is a fresh tensor."""
+    (l1, l2, l3), layer_sets, g = st.levels, st.layer_sets, st.g
+    Bc, np1, np2, C1, C2 = st.dims
+    d_out = d_out.contiguous().float()
+    dev = d_out.device
+    grads = {}
+    by_detached = {}        # sinks are keyed by the module's parameters; the layer sets hold detached aliases
+    if sinks is not None:
+        for sa, ls in zip(net.encoder, layer_sets):
+            for blk, (W, gamma, beta, _, _) in zip(sa.mlps[0], ls):
+                bn = blk[1][0]
+                for alias, p in ((W, blk[0].weight), (gamma, bn.weight), (beta, bn.bias)):
+                    if id(p) in sinks:
+                        by_detached[id(alias)] = sinks[id(p)]
+        for p in (net.fc.weight, net.fc.bias):
+            if id(p) in sinks:
+                by_detached[id(p)] = sinks[id(p)]
+    sk = by_detached if sinks is not None else None
+    with torch.cuda.device(dev):
+        Wfc = net.fc.weight.detach()
+        dWfc = _sink(sk, net.fc.weight, Wfc)
+        _gemm(d_out.t(), g.t(), WGRAD_SPLIT, out=dWfc, accumulate=2, ksplit=1)
+        grads[id(net.fc.weight)] = dWfc
+        dbfc = _sink(sk, net.fc.bias, net.fc.bias)
+        _C.call("msr3d_colsum_add_f32", d_out.data_ptr(), d_out.stride(0), d_out.shape[0], d_out.shape[1],
+                dbfc.data_ptr(), None, None, _st())
+        grads[id(net.fc.bias)] = dbfc
+        dg = _gemm(d_out, Wfc.t(), DGRAD_SPLIT)                                        # (Bc, C3)
+        dX3 = _mlp_backward(l3, dg, layer_sets[2], grads, True, sk)                    # (Bc * np2, 3 + C2)
+        d_f2 = dX3[:, 3:3 + C2]                                                        # GroupAll: rows = points
+        dX2 = _mlp_backward(l2, d_f2, layer_sets[1], grads, True, sk)                  # (Bc * np2 * S2, 3 + C1)
+        d_f1 = torch.empty(Bc * np1, C1, dtype=torch.float32, device=dev)
+        _C.call("msr3d_sa_group_rows_bwd_f32", dX2.data_ptr(), dX2.shape[1], 3, l2.idx.data_ptr(), Bc, l2.pairs,
+                l2.n_src, C1, d_f1.data_ptr(), _st())
+        _mlp_backward(l1, d_f1, layer_sets[0], grads, False, sk)                       # inputs need no gradient
+    out = {}
+    for sa, ls in zip(net.encoder, layer_sets):
+        for blk, (W, gamma, beta, _, _) in zip(sa.mlps[0], ls):
+            bn = blk[1][0]
+            out[id(blk[0].weight)] = grads[id(W)]
+            out[id(bn.weight)] = grads[id(gamma)]
+            out[id(bn.bias)] = grads[id(beta)]
+    out[id(net.fc.weight)] = grads[id(net.fc.weight)]
+    out[id(net.fc.bias)] = grads[id(net.fc.bias)]
+    return out
+
+
 class _PointNetPPTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, pc, *params):
-        pc = pc.contiguous().float()
-        Bc, P, _ = pc.shape
-        dev = pc.device
-        np1, np2 = net.sa_n_points[0], net.sa_n_points[1]
-        S1, S2 = net.sa_n_samples[0], net.sa_n_samples[1]
-        levels = []
-        layer_sets = []
-        for sa in net.encoder:
-            ls = []
-            for blk in sa.mlps[0]:
-                bn = blk[1][0]
-                ls.append((blk[0].weight.detach(), bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var))
-            layer_sets.append(ls)
-        bn_mode = [[blk[1][0].training for blk in sa.mlps[0]] for sa in net.encoder]
-        with torch.cuda.device(dev):
-            # ---- level 1: neighbours are the raw (x, y, z, r, g, b) records
-            _, xyz1, ball1 = ops.sa_group(pc, np1, net.sa_radii[0], S1)
-            l1 = _Level()
-            rows1 = Bc * np1 * S1
-            X1 = torch.empty(rows1, _pad4(6), dtype=torch.float32, device=dev)
-            _C.call("msr3d_sa_group_rows_f32", pc.data_ptr(), 6, pc.data_ptr() + 12, 6, 3, xyz1.data_ptr(),
-                    ball1.data_ptr(), P, np1, S1, rows1, X1.data_ptr(), X1.shape[1], _st())
-            f1 = _pool(l1, _mlp_forward(l1, X1, layer_sets[0], bn_mode[0]), S1)          # (Bc * np1, C1)
-            C1 = f1.shape[1]
-            # ---- level 2
-            _, xyz2, ball2 = ops.sa_group(xyz1, np2, net.sa_radii[1], S2)
-            l2 = _Level()
-            rows2 = Bc * np2 * S2
-            X2 = torch.empty(rows2, _pad4(3 + C1), dtype=torch.float32, device=dev)
-            _C.call("msr3d_sa_group_rows_f32", xyz1.data_ptr(), 3, f1.data_ptr(), C1, C1, xyz2.data_ptr(),
-                    ball2.data_ptr(), np1, np2, S2, rows2, X2.data_ptr(), X2.shape[1], _st())
-            l2.idx, l2.n_src, l2.pairs = ball2, np1, np2 * S2
-            f2 = _pool(l2, _mlp_forward(l2, X2, layer_sets[1], bn_mode[1]), S2)          # (Bc * np2, C2)
-            C2 = f2.shape[1]
-            # ---- level 3 (GroupAll): rows = the np2 remaining points of every cloud, raw xyz
-            l3 = _Level()
-            rows3 = Bc * np2
-            X3 = torch.empty(rows3, _pad4(3 + C2), dtype=torch.float32, device=dev)
-            _C.call("msr3d_sa_group_rows_f32", xyz2.data_ptr(), 3, f2.data_ptr(), C2, C2, None, None, np2, 1, 1, rows3,
-                    X3.data_ptr(), X3.shape[1], _st())
-            g = _pool(l3, _mlp_forward(l3, X3, layer_sets[2], bn_mode[2]), np2)          # (Bc, C3)
-            out = _gemm(g, net.fc.weight.detach(), FWD_SPLIT, bias=net.fc.bias.detach())
-        for sa, modes in zip(net.encoder, bn_mode):
-            for blk, tr in zip(sa.mlps[0], modes):
-                if tr:
-                    blk[1][0].num_batches_tracked += 1
-        ctx.net, ctx.levels, ctx.layer_sets, ctx.g, ctx.dims = net, (l1, l2, l3), layer_sets, g, (Bc, np1, np2, C1, C2)
-        ctx.params = params
+        out, st = forward_explicit(net, pc)
+        ctx.net, ctx.st, ctx.params = net, st, params
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        net, (l1, l2, l3), layer_sets, g = ctx.net, ctx.levels, ctx.layer_sets, ctx.g
-        Bc, np1, np2, C1, C2 = ctx.dims
-        d_out = d_out.contiguous().float()
-        dev = d_out.device
-        grads = {}
-        with torch.cuda.device(dev):
-            Wfc = net.fc.weight.detach()
-            dWfc = torch.zeros_like(Wfc)
-            _gemm(d_out.t(), g.t(), WGRAD_SPLIT, out=dWfc, accumulate=2, ksplit=1)
-            grads[id(net.fc.weight)] = dWfc
-            dbfc = torch.zeros_like(net.fc.bias)
-            _C.call("msr3d_colsum_add_f32", d_out.data_ptr(), d_out.stride(0), d_out.shape[0], d_out.shape[1],
-                    dbfc.data_ptr(), None, None, _st())
-            grads[id(net.fc.bias)] = dbfc
-            dg = _gemm(d_out, Wfc.t(), DGRAD_SPLIT)                                        # (Bc, C3)
-            dX3 = _mlp_backward(l3, dg, layer_sets[2], grads, need_dx=True)                # (Bc * np2, 3 + C2)
-            d_f2 = dX3[:, 3:3 + C2]                                                        # GroupAll: rows = points
-            dX2 = _mlp_backward(l2, d_f2, layer_sets[1], grads, need_dx=True)              # (Bc * np2 * S2, 3 + C1)
-            d_f1 = torch.empty(Bc * np1, C1, dtype=torch.float32, device=dev)
-            _C.call("msr3d_sa_group_rows_bwd_f32", dX2.data_ptr(), dX2.shape[1], 3, l2.idx.data_ptr(), Bc, l2.pairs,
-                    l2.n_src, C1, d_f1.data_ptr(), _st())
-            _mlp_backward(l1, d_f1, layer_sets[0], grads, need_dx=False)                   # inputs need no gradient
-        out = []
-        by_detached = {}
-        for sa, ls in zip(net.encoder, layer_sets):
-            for blk, (W, gamma, beta, _, _) in zip(sa.mlps[0], ls):
-                bn = blk[1][0]
-                by_detached[id(blk[0].weight)] = grads[id(W)]
-                by_detached[id(bn.weight)] = grads[id(gamma)]
-                by_detached[id(bn.bias)] = grads[id(beta)]
-        by_detached[id(net.fc.weight)] = grads[id(net.fc.weight)]
-        by_detached[id(net.fc.bias)] = grads[id(net.fc.bias)]
-        for p in ctx.params:
-            out.append(by_detached.get(id(p)))
-        return (None, None) + tuple(out)
+        grads = backward_explicit(ctx.net, ctx.st, d_out)
+        return (None, None) + tuple(grads.get(id(p)) for p in ctx.params)
 
 
 def forward_train(net, pc: torch.Tensor) -> torch.Tensor:

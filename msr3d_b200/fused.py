@@ -317,13 +317,20 @@ class FusedPrompter:
         from . import dist as _dist
         # the object encoder's parameters (trainable only with vision.args.freeze False) stay where they are: their
         # forward / backward is encoder_train.py's, driven by autograd
-        named = [(n, p) for n, p in self.model.named_parameters() if p.requires_grad and not n.startswith("obj_encoder.")]
+        # ... unless this engine optimises them itself (engine API, vision.args.freeze False): then the 29 PointNet++
+        # parameters join the flat buffers (late bucket: their gradients are the last to be final), so the ONE gradient
+        # exchange, clip and AdamW cover "the trainable encoder / adapter parameters" of the north star; the 607-way head
+        # the prompter never evaluates goes to the never-touched segment
+        self.train_encoder = self.alias_grads and not encoder_frozen(self.model)
+        named = [(n, p) for n, p in self.model.named_parameters()
+                 if p.requires_grad and (self.train_encoder or not n.startswith("obj_encoder."))]
         n_model = len(named)
         named += [("ext." + k, p) for k, p in self.extra_params.items() if p.requires_grad]
         by_name = dict(named)
         # parameters the configured situation mode never touches (neither reduced nor updated)
         unused = {"as_object": (), "as_object_add_loc": ("loc_layers.",),
                   "as_embedding": ("anchor_feat", "loc_layers.")}.get(self.stype, _dist.UNUSED_IN_SHIPPED_MODE)
+        unused = tuple(unused) + ("obj_encoder.obj3d_clf_pre_head.",)
         lay = _dist.flat_layout([n for n, _ in named], {n: p.numel() for n, p in named}, self.nl,
                                 no_decay_bias=self.no_decay_bias, unused=unused)
         self.order, offs, total = lay["order"], lay["offs"], lay["total"]
@@ -961,10 +968,18 @@ class FusedPrompter:
             w["upstream"].copy_(upstream.reshape(w["upstream"].shape), non_blocking=non_blocking)
 
     def _encode(self, out_key="emb", src_key="obj_fts"):
-        if not encoder_frozen(self.model):
-            raise NotImplementedError("fused prompter: the engine's own schedules run the object encoder frozen; with "
-                                      "vision.args.freeze False call the module (OSE3DSituation.forward + autograd)")
         w = self.ws
+        if getattr(self, "train_encoder", False):
+            # unfrozen encoder, engine API: explicit forward of the training path (encoder_train.py), state kept for backward()
+            assert out_key == "emb", "the unfrozen encoder runs the sequential schedule (train_step_eager)"
+            from . import encoder_train
+            B, L, Pn, _ = w[src_key].shape
+            out, self._enc_state = encoder_train.forward_explicit(self.model.obj_encoder.pcd_net, w[src_key].view(B * L, Pn, 6))
+            w[out_key].copy_(out)
+            return
+        if not encoder_frozen(self.model):
+            raise NotImplementedError("fused prompter: this engine was built for the module call (alias_grads=False); with "
+                                      "vision.args.freeze False either call the module or build the engine with alias_grads=True")
         enc = self.model.obj_encoder
         B, L, Pn, _ = w[src_key].shape
         enc.freeze_bn(enc.pcd_net)
@@ -1351,6 +1366,13 @@ class FusedPrompter:
         gradient wrt the object embeddings (B * objects, E) = d(projection output) . W_proj — what an unfrozen encoder
         back-propagates (tensor-core GEMM, msr3d_gemm_tc_f32)."""
         self._run(self.bwd_prog)
+        if getattr(self, "train_encoder", False):
+            # d(embeddings) -> the encoder's hand-written backward, gradients accumulated straight into the flat buffer
+            from . import encoder_train
+            net = self.model.obj_encoder.pcd_net
+            sinks = {id(p): p.grad for p in net.parameters() if p.grad is not None}
+            encoder_train.backward_explicit(net, self._enc_state, self.d_emb(), sinks)
+            self._enc_state = None
         return self.d_emb() if need_d_emb else None
 
     def d_emb(self):
@@ -1421,6 +1443,7 @@ class FusedPrompter:
 
     def capture(self):
         """Capture forward+backward (and, single-GPU, the optimiser) into one CUDA graph."""
+        assert not getattr(self, "train_encoder", False), "the unfrozen encoder runs eager steps (train_step_eager)"
         for _ in range(2):       # warm-up on a side stream: lazy attribute setup must not happen in capture
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())

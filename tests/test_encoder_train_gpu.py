@@ -176,3 +176,54 @@ def test_unfrozen_encoder_edge_shapes(clouds, P):
         worst = max(worst, (n, err), key=lambda t: t[1])
     print(f"unfrozen encoder {clouds} x {P}: emb {e:.2e}, worst grad (norm) {worst[0]} {worst[1]:.2e}")
     assert e < TOL and worst[1] < 1e-2
+
+
+def test_engine_api_trains_the_unfrozen_encoder_through_the_flat_buffers():
+    """vision.args.freeze False with the ENGINE API (FusedPrompter: fused clip + AdamW, one gradient exchange): the 29
+    PointNet++ parameters live in the flat parameter / gradient buffers next to the prompter's, forward / backward run the
+    encoder's training kernels, and every gradient matches the oracle's autograd."""
+    from msr3d_b200 import configs
+    from msr3d_b200.fused import FusedPrompter
+    from oracle import ext_oracle as eo, modules_oracle as mo
+    seed, B, O, P = 654, 2, 8, 256
+    model = configs.build_prompter(seed, device="cuda", freeze=False, dropout=0.0)
+    sd0 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    model.train()
+    eng = FusedPrompter(model)
+    assert eng.train_encoder and eng.n_trainable > 5_000_000          # 4.2 M prompter + 1.7 M encoder parameters
+    enc_names = [n for n in eng.order if n.startswith("obj_encoder.pcd_net.")]
+    assert len(enc_names) == 29 and all(eng.offs[n] < eng.n_opt for n in enc_names)
+    assert all(eng.offs[n] >= eng.n_opt for n in eng.order if n.startswith("obj_encoder.obj3d_clf_pre_head."))
+    eng.prepare(B, O, P, training=True)
+    batch = synthetic.make_batch(B, O, P, seed=seed)
+    up = torch.randn(B, O, 256, generator=torch.Generator().manual_seed(seed + 77))
+    eng.load_inputs(batch.to("cuda"), up.cuda())
+    eng.flat_g.zero_()
+    tokens = eng.forward().clone()
+    eng.backward()
+    torch.cuda.synchronize()
+    eo.set_threads(16); torch.set_num_threads(16)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and k != "anchor_size" else v)
+          for k, v in sd0.items()}
+    want, _ = mo.ose3d_situation(sd, batch.as_dict(), unfrozen_bn_stats={})
+    (want * up).sum().backward()
+    e = helpers.rel_err(tokens.cpu(), want.detach())
+    gnorm = max(float(v.grad.norm()) for v in sd.values() if isinstance(v, torch.Tensor) and v.grad is not None)
+    worst = ("", 0.0)
+    for n, p in model.named_parameters():
+        w = sd[n].grad
+        if w is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+            continue
+        err = float((p.grad.detach().cpu() - w).norm() / max(float(w.norm()), 1e-4 * gnorm))
+        worst = max(worst, (n, err), key=lambda t: t[1])
+    print(f"engine API, unfrozen encoder: tokens {e:.2e}, worst grad (norm) {worst[0]} {worst[1]:.2e}")
+    assert e < TOL and worst[1] < 2e-3
+    before = model.obj_encoder.pcd_net.encoder[0].mlps[0][0][0].weight.detach().clone()
+    eng.optimizer_step()
+    torch.cuda.synchronize()
+    assert not torch.equal(before, model.obj_encoder.pcd_net.encoder[0].mlps[0][0][0].weight.detach())
+    # a second full step through the public entry point
+    eng.train_step_eager()
+    torch.cuda.synchronize()
+    assert torch.isfinite(eng.flat_p).all()
