@@ -174,3 +174,31 @@ def test_flat_layout_with_attached_caller_parameters(sd_spec):
     # 4 224 144 trainable prompter parameters, 24 320 of them never used in the shipped mode (outside n_opt), + 9 449 472
     assert lay["total"] == 13_673_616 and lay["n_opt"] == 13_673_616 - 24_320
     assert l1 == e0 and l0 == 0
+
+
+@pytest.mark.parametrize("stype,unused", [("as_transform_for_objects", mdist.UNUSED_IN_SHIPPED_MODE),
+                                          ("as_object", ()), ("as_embedding", ("anchor_feat", "loc_layers."))])
+def test_flat_layout_per_mode_and_with_the_unfrozen_encoder(stype, unused):
+    """Layout properties for the round-2 cases: per-mode never-touched segment, and the PointNet++ parameters of an
+    unfrozen encoder inside the optimised range (late bucket) with the unevaluated 607-way head outside it."""
+    from msr3d_b200 import configs
+    model = configs.build_prompter(0, stype, freeze=False)
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    numel = {n: p.numel() for n, p in named}
+    lay = mdist.flat_layout([n for n, _ in named], numel, 3, unused=tuple(unused) + ("obj_encoder.obj3d_clf_pre_head.",))
+    offs, n_opt = lay["offs"], lay["n_opt"]
+    (l0, l1), (e0, e1) = lay["late"], lay["early"]
+    assert l0 == 0 and l1 == e0 and e1 == n_opt and lay["decay"] == (0, n_opt)
+    for n, _ in named:
+        assert offs[n] % 4 == 0
+        touched = not n.startswith(tuple(unused) + ("obj_encoder.obj3d_clf_pre_head.",))
+        assert (offs[n] < n_opt) == touched, n
+        if n.startswith("obj_encoder.pcd_net."):
+            assert offs[n] < l1, n                    # encoder gradients are the last to be final: late bucket
+        if n.startswith(("spatial_encoder.1.", "spatial_encoder.2.")):
+            assert e0 <= offs[n] < e1, n
+    # the attention projections of a layer stay adjacent (one QKV (+cond) GEMM)
+    for i in range(3):
+        pre = f"spatial_encoder.{i}.self_attn."
+        assert offs[pre + "w_ks.weight"] == offs[pre + "w_qs.weight"] + numel[pre + "w_qs.weight"]
+        assert offs[pre + "w_vs.weight"] == offs[pre + "w_ks.weight"] + numel[pre + "w_ks.weight"]
