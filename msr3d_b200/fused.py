@@ -1,20 +1,23 @@
-"""Fused execution engine for the trainable half of the MSR3D prompter.
+"""Fused execution engine for the MSR3D prompter.
 
-`FusedPrompter` takes a (drop-in) `OSE3DSituation` and runs its forward, backward and optimiser
-step as a fixed program of ~95 launches of this repo's kernels (tensor-core GEMMs from
-csrc/linear_tc.cu, everything else from csrc/spatial.cu, csrc/optim.cu, and the fused PointNet++
-encoder), optionally replayed as ONE CUDA graph per step.  It replaces what the reference does
-with ~500 ATen launches plus a host sync per layer.
+`FusedPrompter` takes a (drop-in) `OSE3DSituation` and runs its forward, backward and optimiser step as a fixed
+program of ~70 launches of this repo's kernels (TMA-fed 3xTF32 tcgen05 GEMMs from csrc/gemm3x.cu, the one-launch
+attention block of csrc/attn_block.cu, everything else from csrc/spatial.cu, csrc/modes.cu, csrc/optim.cu, and the
+fused PointNet++ encoder), replayed as ONE CUDA graph per step in the pipelined schedules.  It replaces what the
+reference does with ~500 ATen launches plus a host sync per layer.
 
 Parameters are re-homed into one flat fp32 buffer (each `p.data` becomes a view) laid out as
-[ weights | biases | parameters the shipped mode never touches ] with the
-four input projections of every attention block (w_qs, w_ks, w_vs, lang_cond_fc) adjacent, so
-that QKV+cond is a single (816 x 256) GEMM, its weight gradient another one, and the gradient
-all-reduce and AdamW are single flat operations.  State-dict keys and shapes are unchanged.
+[ late biases | late weights | early weights | early biases | parameters the configured mode never touches ]
+(dist.flat_layout) with the input projections of every attention block (w_qs, w_ks, w_vs, lang_cond_fc) adjacent, so
+that QKV+cond is a single (816 x 256) GEMM, its weight gradient another one, and the gradient all-reduce and AdamW are
+single flat operations.  State-dict keys and shapes are unchanged.
 
-Supported (= every shipped config, configs/*.yaml): situation_type as_transform_for_objects or
-as_object_add_loc-style query positions are NOT both covered — see `supported()`; anything else
-keeps running through the module tree in spatial.py / prompter.py.
+Covered (`supported()`): hidden 256 / 8 heads / spatial_dim 5 / gelu, obj_loc_encoding same_all or same_0,
+spatial_attn_fusion cond (every shipped config) | mul | bias | ctx | add, situation_type as_transform_for_objects
+(shipped) | as_object | as_object_add_loc | as_embedding, encoder frozen (shipped) or unfrozen (encoder_train.py).
+Anything else (as_cross_attention, diff_all, attn_flat, no spatial attention) keeps running through the module tree
+in spatial.py / prompter.py.  The pipelined / prefetch / data-parallel schedules serve the shipped situation mode with
+the frozen encoder; the other modes and the unfrozen encoder run the sequential schedule or the module call.
 """
 from __future__ import annotations
 

@@ -156,3 +156,20 @@ print("ok")
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=helpers.ROOT, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_which_configurations_the_fused_engine_covers():
+    """fused.supported() is host logic: the shipped configuration, every attention fusion, four situation modes and
+    the unfrozen encoder are on the engine; the rest names its reason and stays on the module tree."""
+    from msr3d_b200 import configs, fused
+    ok = [dict(), dict(fusion="mul"), dict(fusion="bias"), dict(fusion="ctx"), dict(fusion="add"),
+          dict(situation_type="as_object"), dict(situation_type="as_object_add_loc"), dict(situation_type="as_embedding"),
+          dict(freeze=False), dict(fusion="add", spatial_multihead=False), dict(obj_loc_encoding="same_0")]
+    for kw in ok:
+        assert fused.supported(configs.build_prompter(0, **kw)) is None, kw
+    no = [(dict(situation_type="as_cross_attention"), "situation_type"), (dict(obj_loc_encoding="diff_all"), "diff_all"),
+          (dict(activation="relu"), "gelu"), (dict(spatial_multihead=False), "multihead"), (dict(num_attention_heads=4), "heads")]
+    for kw, why in no:
+        reason = fused.supported(configs.build_prompter(0, **kw))
+        assert reason is not None and why in reason, (kw, reason)
+    assert fused.encoder_frozen(configs.build_prompter(0)) and not fused.encoder_frozen(configs.build_prompter(0, freeze=False))
