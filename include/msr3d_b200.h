@@ -355,7 +355,9 @@ int msr3d_spatial_weights_bwd_f32(const float *W, const float *b, int ctx_mode, 
 /* Situation modes with an agent token in front of the objects: as_object, as_object_add_loc
  * (model/ose3d_situation.py:334-363, 385-396; csrc/modes.cu).  Tokens per scene L + 1, row 0 = the agent.
  *   anchor_inputs:  all_loc (B, L+1, 6) = [(anchor_locs, anchor_size); obj_locs], key_pad (B, L+1) = [0; !obj_masks]
- *   loc_layer_*:    qpos = LN(Linear_6(all_loc)) (loc_layers[0]); forward also stores qpos as the first term of x0
+ *   loc_layer_*:    qpos = LN(Linear_6(all_loc)) (loc_layers[0]); forward also stores qpos (+ extra_a + extra_b, both
+ *                   nullable (256): object_orientation_feat / type_embedding[0] when no agent row exists) as the first
+ *                   term of x0
  *   anchor_assemble:    x0[object row] += proj + object_orientation_feat + type_embedding[0];
  *                       x0[agent row]  += anchor_feat + orientation_encoder(fourier(anchor_orientation)) + type_embedding[1]
  *   anchor_disassemble: dproj (B*L, 256) = object rows of dx0; ACCUMULATES d anchor_feat, d type_embedding[1],
@@ -365,7 +367,7 @@ int msr3d_anchor_inputs(const float *obj_locs, const unsigned char *obj_masks, c
                         msr3d_stream_t stream);
 int msr3d_loc_layer_fwd_f32(const float *all_loc, int M, const float *W6, const float *b6, const float *gamma,
                             const float *beta, float *xhat, float *rstd, float *qpos, float *x0,
-                            msr3d_stream_t stream);
+                            const float *extra_a, const float *extra_b, msr3d_stream_t stream);
 int msr3d_loc_layer_bwd_f32(const float *dq, const float *dq1, const float *dq2, const float *all_loc, int M,
                             const float *gamma, const float *xhat, const float *rstd, float *dgamma, float *dbeta,
                             float *dW6, float *db6, msr3d_stream_t stream);
@@ -378,17 +380,49 @@ int msr3d_anchor_disassemble_f32(const float *dx0, const float *anchor_ori, int 
 /* as_embedding (ose3d_situation.py:385-393): s_b = loc_embedding_encoder(fourier(anchor_locs[b])) +
  * orientation_encoder(fourier(anchor_orientation[b])) added to the query position of every object of scene b.
  * Forward: qpos (B*L, 256) += s_b (plain) and x0 += s_b (red.add: the projection GEMM reduces into x0 concurrently);
- * saves xhat_sit (B, 256) / rstd_sit (B) of the LayerNorm.  Backward: from the per-layer qpos gradients (dq1 / dq2
+ * saves xhat_sit (B, 256) / rstd_sit (B) of the LayerNorm; qpos = x0 = NULL with s_out (B, 256): only the vector
+ * itself (as_cross_attention).  Backward: from the per-layer qpos gradients (dq1 / dq2
  * nullable) ACCUMULATES the gradients of loc_embedding_encoder.{0.weight (256, 63), 0.bias, 1.weight, 1.bias} and
  * orientation_encoder.{weight (256, 84), bias}. */
 int msr3d_situation_embed_fwd_f32(const float *anchor_locs, const float *anchor_ori, int B, int L, const float *Wl,
                                   const float *bl, const float *gamma_l, const float *beta_l, const float *W_ori,
                                   const float *b_ori, float *xhat_sit, float *rstd_sit, float *qpos, float *x0,
-                                  msr3d_stream_t stream);
+                                  float *s_out, msr3d_stream_t stream);
 int msr3d_situation_embed_bwd_f32(const float *dq, const float *dq1, const float *dq2, const float *anchor_locs,
                                   const float *anchor_ori, int B, int L, const float *gamma_l, const float *xhat_sit,
                                   const float *rstd_sit, float *dWl, float *dbl, float *dgamma_l, float *dbeta_l,
                                   float *dW_ori, float *db_ori, msr3d_stream_t stream);
+/* as_cross_attention (ose3d_situation.py:411-418; CrossAttentionLayer, transformers.py:22-73, prenorm): every key /
+ * value of a scene is the same situation vector s_b, so the attention output of head h is scale * v_h with
+ * v = W_v s_b + b_v and scale[b, h, n] = mean over the keys of the attention-dropout mask (csrc/modes.cu explains why
+ * W_q, W_k and norm1 receive exactly zero gradient).  Per layer:
+ *   cross_vec_fwd          v (B, 256), P (B, 8, 256) = per-head slices of W_o v
+ *   cross_residual_ln_fwd  xa = x + drop_2(b_o + sum_h scale P_h);  t3 = LN_3(xa)   (scale (M, 8), xhat3, rstd3 saved)
+ *   [msr3d_ffn_pair_fwd_f32 on t3]
+ *   cross_ffn_residual_fwd out = xa + drop_3(f)
+ *   cross_ffn_residual_bwd df = drop_3 mask * d out;  d linear2.bias ACCUMULATED
+ *   [msr3d_ffn_pair_bwd_f32, weight-gradient GEMMs]
+ *   cross_ln_bwd           dxa = d out + LN_3 backward(dt3);  g_attn = drop_2 mask * dxa;  d norm3, d b_o ACCUMULATED
+ *   cross_vec_bwd          d W_o, d W_v, d b_v ACCUMULATED; ds (B, 256) += W_v^T dv  (the situation vector's gradient,
+ *                          summed over the layers and fed to msr3d_situation_embed_bwd_f32 with L = 1) */
+int msr3d_cross_vec_fwd_f32(const float *s, const float *Wv, const float *bv, const float *Wo, int B, float *v, float *P,
+                            msr3d_stream_t stream);
+int msr3d_cross_residual_ln_fwd_f32(const float *x, const float *P, const float *bo, int M, int L, const float *gamma3,
+                                    const float *beta3, unsigned long long seed, const unsigned long long *seed_ptr,
+                                    float p, unsigned site_attn, unsigned site_2, float *scale, float *xa, float *xhat3,
+                                    float *rstd3, float *t3, msr3d_stream_t stream);
+int msr3d_cross_ffn_residual_fwd_f32(const float *xa, const float *f, int M, unsigned long long seed,
+                                     const unsigned long long *seed_ptr, float p, unsigned site_3, float *out,
+                                     msr3d_stream_t stream);
+int msr3d_cross_ffn_residual_bwd_f32(const float *dx, int M, unsigned long long seed, const unsigned long long *seed_ptr,
+                                     float p, unsigned site_3, float *df, float *db2, msr3d_stream_t stream);
+int msr3d_cross_ln_bwd_f32(const float *dt3, const float *dx, int M, const float *gamma3, unsigned long long seed,
+                           const unsigned long long *seed_ptr, float p, unsigned site_2, const float *xhat3,
+                           const float *rstd3, float *dxa, float *g_attn, float *dgamma3, float *dbeta3, float *dbo,
+                           msr3d_stream_t stream);
+int msr3d_cross_vec_bwd_f32(const float *g_attn, const float *scale, int B, int L, const float *v, const float *s,
+                            const float *Wv, const float *Wo, float *dWo, float *dWv, float *dbv, float *ds,
+                            msr3d_stream_t stream);
 /* Same contract as msr3d_attn_bwd_f32 on the tensor cores (csrc/attn_block.cu: dP, dq, dk, dv as tcgen05 kind::tf32
  * 3xTF32 products, one CTA per (head, scene)); requires L <= 64, 8 heads, ldq = 816. */
 int msr3d_attn_bwd_tc_f32(const float *dctx, int ldc, const float *qkvc, int ldq, const float *pw, const float *P,

@@ -14,8 +14,8 @@ single flat operations.  State-dict keys and shapes are unchanged.
 
 Covered (`supported()`): hidden 256 / 8 heads / spatial_dim 5 / gelu, obj_loc_encoding same_all or same_0,
 spatial_attn_fusion cond (every shipped config) | mul | bias | ctx | add, situation_type as_transform_for_objects
-(shipped) | as_object | as_object_add_loc | as_embedding, encoder frozen (shipped) or unfrozen (encoder_train.py).
-Anything else (as_cross_attention, diff_all, attn_flat, no spatial attention) keeps running through the module tree
+(shipped) | as_object | as_object_add_loc | as_embedding | as_cross_attention, encoder frozen (shipped) or unfrozen
+(encoder_train.py).  Anything else (diff_all, attn_flat, no spatial attention) keeps running through the module tree
 in spatial.py / prompter.py.  The pipelined / prefetch / data-parallel schedules serve the shipped situation mode with
 the frozen encoder; the other modes and the unfrozen encoder run the sequential schedule or the module call.
 """
@@ -111,11 +111,19 @@ _C.register_protos({
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "msr3d_attn_block_supported": [c_int, c_int, c_int],
     "msr3d_anchor_inputs": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp],
-    "msr3d_loc_layer_fwd_f32": [c_vp, c_int] + [c_vp] * 8 + [c_vp],
+    "msr3d_loc_layer_fwd_f32": [c_vp, c_int] + [c_vp] * 10 + [c_vp],
+    "msr3d_cross_vec_fwd_f32": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp],
+    "msr3d_cross_residual_ln_fwd_f32": [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_ull, c_vp, c_float, c_uint, c_uint,
+                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "msr3d_cross_ffn_residual_fwd_f32": [c_vp, c_vp, c_int, c_ull, c_vp, c_float, c_uint, c_vp, c_vp],
+    "msr3d_cross_ffn_residual_bwd_f32": [c_vp, c_int, c_ull, c_vp, c_float, c_uint, c_vp, c_vp, c_vp],
+    "msr3d_cross_ln_bwd_f32": [c_vp, c_vp, c_int, c_vp, c_ull, c_vp, c_float, c_uint, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                               c_vp, c_vp],
+    "msr3d_cross_vec_bwd_f32": [c_vp, c_vp, c_int, c_int] + [c_vp] * 8 + [c_vp],
     "msr3d_loc_layer_bwd_f32": [c_vp, c_vp, c_vp, c_vp, c_int] + [c_vp] * 7 + [c_vp],
     "msr3d_anchor_assemble_f32": [c_vp] * 8 + [c_int, c_int, c_vp],
     "msr3d_anchor_disassemble_f32": [c_vp, c_vp, c_int, c_int] + [c_vp] * 5 + [c_vp],
-    "msr3d_situation_embed_fwd_f32": [c_vp, c_vp, c_int, c_int] + [c_vp] * 10 + [c_vp],
+    "msr3d_situation_embed_fwd_f32": [c_vp, c_vp, c_int, c_int] + [c_vp] * 11 + [c_vp],
     "msr3d_situation_embed_bwd_f32": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int] + [c_vp] * 9 + [c_vp],
     "msr3d_attn_fusion_fwd_f32": [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp],
     "msr3d_attn_fusion_bwd_f32": [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
@@ -160,11 +168,11 @@ def supported(model) -> Optional[str]:
         (se.pairwise_rel_type == "center", "pairwise_rel_type != center"),
         (se.activation == "gelu", "activation != gelu"),
         (se.obj_loc_encoding in ("same_all", "same_0"), "obj_loc_encoding == diff_all"),
-        (model.situation_type in ("as_transform_for_objects", "as_embedding") + ANCHOR_MODES,
+        (model.situation_type in ("as_transform_for_objects", "as_embedding", "as_cross_attention") + ANCHOR_MODES,
          f"situation_type {model.situation_type}"),
         (model.situation_type not in ANCHOR_MODES or bool(c.use_anchor), "anchor mode without use_anchor"),
         (model.situation_type == "as_object" or c.loc_fourier_dim == 63, "loc_fourier_dim != 63"),
-        (model.situation_type != "as_object" or se.dim_loc == 6, "dim_loc != 6"),
+        (model.situation_type not in ("as_object", "as_cross_attention") or se.dim_loc == 6, "dim_loc != 6"),
         (not c.attn_flat.use_attn_flat, "attn_flat on"),
         (bool(c.use_orientation), "use_orientation off"),
         (c.vision.name == "PcdObjEncoder", "vision backbone is not PcdObjEncoder"),
@@ -241,6 +249,10 @@ class FusedPrompter:
         self.n_anchor = 1 if self.stype in ANCHOR_MODES else 0
         # as_embedding: one situation embedding per scene added to every object's query position (csrc/modes.cu)
         self.sit_embed = self.stype == "as_embedding"
+        # as_cross_attention: a pre-norm cross-attention + FFN block on the situation vector in front of every spatial
+        # layer (csrc/modes.cu: cross_* kernels; the FFN on the fused pair kernels)
+        self.cross = self.stype == "as_cross_attention"
+        assert not self.cross or self.ffn_pair, "as_cross_attention needs the fused FFN pair kernels (gemm_impl tf32x3)"
         self.multihead = int(bool(se.spatial_multihead))
         self.dist_norm = int(bool(se.spatial_dist_norm))
         self.p_drop = float(se.dropout)
@@ -332,7 +344,12 @@ class FusedPrompter:
         by_name = dict(named)
         # parameters the configured situation mode never touches (neither reduced nor updated)
         unused = {"as_object": (), "as_object_add_loc": ("loc_layers.",),
-                  "as_embedding": ("anchor_feat", "loc_layers.")}.get(self.stype, _dist.UNUSED_IN_SHIPPED_MODE)
+                  "as_embedding": ("anchor_feat", "loc_layers."),
+                  # nn.MultiheadAttention's q / k projections and norm1 get exactly zero gradients (all keys are one
+                  # vector) and are optimised like the reference does; norm2 is never evaluated
+                  "as_cross_attention": ("anchor_feat", "size_embedding_encoder.") + tuple(
+                      f"situation_condition_layer.{i}.norm2." for i in range(self.nl)),
+                  }.get(self.stype, _dist.UNUSED_IN_SHIPPED_MODE)
         unused = tuple(unused) + ("obj_encoder.obj3d_clf_pre_head.",)
         lay = _dist.flat_layout([n for n, _ in named], {n: p.numel() for n, p in named}, self.nl,
                                 no_decay_bias=self.no_decay_bias, unused=unused)
@@ -523,9 +540,10 @@ class FusedPrompter:
             w[k] = f(M)
         # split-K GEMM outputs (accumulated with red.add): carved out of two arenas that are zeroed with
         # one memset each per step (forward: x_in[0], qkvc, o, f of every layer; backward: dctx)
-        n_f = M * H + nl * (M * QKVC + 2 * M * H)
+        cross = self.cross
+        n_f = M * H + nl * (M * QKVC + 2 * M * H) + (nl * M * H if cross else 0)
         w["arena_f"] = f(n_f)
-        w["arena_b"] = f(nl * M * H)
+        w["arena_b"] = f(nl * M * H + ((nl * M * H + B * H) if cross else 0))
         cur = [0]
 
         def carve(arena, *shape):
@@ -535,13 +553,35 @@ class FusedPrompter:
             t = arena[cur[0]:cur[0] + n].view(*shape)
             cur[0] += n
             return t
-        w["x_in"] = [carve(w["arena_f"], M, H)] + [f(M, H) for _ in range(nl - 1)]
+        if cross:
+            # x_pre[i]: input of layer i's cross-attention block (i = 0: the assembled layer-0 input, reduced into a
+            # zeroed buffer); x_in[i]: its output = input of spatial layer i
+            w["x_pre"] = [carve(w["arena_f"], M, H)] + [f(M, H) for _ in range(nl - 1)]
+            w["x_in"] = [f(M, H) for _ in range(nl)]
+        else:
+            w["x_in"] = [carve(w["arena_f"], M, H)] + [f(M, H) for _ in range(nl - 1)]
         w["qkvc"] = [carve(w["arena_f"], M, QKVC) for _ in range(nl)]
         w["o"] = [carve(w["arena_f"], M, H) for _ in range(nl)]
         w["f"] = [carve(w["arena_f"], M, H) for _ in range(nl)]
+        if cross:
+            w["f_c"] = [carve(w["arena_f"], M, H) for _ in range(nl)]
         assert cur[0] == n_f
         cur[0] = 0
         w["dctx"] = [carve(w["arena_b"], M, H) for _ in range(nl)]
+        if cross:
+            w["dt3"] = [carve(w["arena_b"], M, H) for _ in range(nl)]
+            w["ds_sit"] = carve(w["arena_b"], B, H)
+            w["s_sit"], w["xhat_sit"], w["rstd_sit"] = f(B, H), f(B, H), f(B)
+            w["v_c"] = [f(B, H) for _ in range(nl)]
+            w["P_c"] = [f(B, NHEAD, H) for _ in range(nl)]
+            w["scale_c"] = [f(M, NHEAD) for _ in range(nl)]
+            for k in ("xa", "xhat3", "t3", "df_c", "dxa"):
+                w[k] = [f(M, H) for _ in range(nl)]
+            w["rstd3"] = [f(M) for _ in range(nl)]
+            w["h_c"] = [f(M, F) for _ in range(nl)]
+            w["gp_c"] = [f(M, F) for _ in range(nl)]
+            w["du_c"] = [f(M, F) for _ in range(nl)]
+            w["g_attn"] = f(M, H)
         w["P"] = [f(B, NHEAD, L, L) for _ in range(nl)]
         w["LOC"] = [f(B, NHEAD, L, L) for _ in range(nl)]
         w["ctx"] = [f(M, H) for _ in range(nl)]
@@ -631,7 +671,8 @@ class FusedPrompter:
         B, Lo, _ = self._shape
         L = Lo + self.n_anchor           # tokens per scene
         M, Mo, F, nl, w = B * L, B * Lo, self.F, self.nl, self.ws
-        anchor, as_object = bool(self.n_anchor), self.stype == "as_object"
+        anchor, as_object, cross = bool(self.n_anchor), self.stype == "as_object", self.cross
+        x0_buf = w["x_pre"][0] if cross else w["x_in"][0]        # the zero-filled buffer the layer-0 input is reduced into
         self._p = self.p_drop if training else 0.0
         p, seed, sptr = self._p, self.seed, self.seed_counter.data_ptr()
         P, G = self.P, self.G
@@ -659,16 +700,25 @@ class FusedPrompter:
                        tag="geometry", side=True)
         # prefetch schedule: geometry of the batch in point-cloud slot s, from its freshly copied inputs, for the NEXT step
         self.geo_prog = []
-        for q in (() if (anchor or self.sit_embed) else ("_q0", "_q1")):
+        for q in (() if (anchor or self.sit_embed or cross) else ("_q0", "_q1")):
             gq: List = []
             self._call(gq, "msr3d_spatial_geometry_f32", ptr(w["obj_locs" + q]), ptr(w["anchor_locs" + q]), ptr(w["anchor_ori" + q]),
                        B, L, self.dist_norm, 1, ptr(w["pw_n"]), ptr(w["ff_n"]), ptr(w["sz_n"]), tag="geometry")
             self.geo_prog.append(gq)
-        if as_object:
-            # qpos = loc_layers[0](all_loc) (ose3d_situation.py:396), stored as the first term of the layer-0 input
-            self._call(pre_prog, "msr3d_loc_layer_fwd_f32", ptr(w["all_loc"]), M, P("loc_layers.0.0.weight"),
-                       P("loc_layers.0.0.bias"), P("loc_layers.0.1.weight"), P("loc_layers.0.1.bias"), ptr(w["xhat_l"]),
-                       ptr(w["rstd_l"]), ptr(w["qpos"]), ptr(w["x_in"][0]), tag="qpos", side=True)
+        if as_object or cross:
+            # qpos = loc_layers[0](loc) (ose3d_situation.py:396), stored as the first term of the layer-0 input; without an
+            # agent row (as_cross_attention) the objects' constant terms ride along
+            self._call(pre_prog, "msr3d_loc_layer_fwd_f32", ptr(w["all_loc"] if as_object else w["obj_locs"]), M,
+                       P("loc_layers.0.0.weight"), P("loc_layers.0.0.bias"), P("loc_layers.0.1.weight"),
+                       P("loc_layers.0.1.bias"), ptr(w["xhat_l"]), ptr(w["rstd_l"]), ptr(w["qpos"]), ptr(x0_buf),
+                       P("object_orientation_feat") if cross else None, P("object_type_embedding.weight") if cross else None,
+                       tag="qpos", side=True)
+            if cross:       # the situation vector s_b (B, 256): keys and values of every cross-attention layer
+                self._call(pre_prog, "msr3d_situation_embed_fwd_f32", ptr(w["anchor_locs"]), ptr(w["anchor_ori"]), B, L,
+                           P("loc_embedding_encoder.0.weight"), P("loc_embedding_encoder.0.bias"),
+                           P("loc_embedding_encoder.1.weight"), P("loc_embedding_encoder.1.bias"),
+                           P("orientation_encoder.weight"), P("orientation_encoder.bias"), ptr(w["xhat_sit"]),
+                           ptr(w["rstd_sit"]), None, None, ptr(w["s_sit"]), tag="situation_vec", side=True)
         else:
             self._gemm(pre_prog, ptr(w["ff"]), (64, 1), P("loc_embedding_encoder.0.weight"), (63, 1), M, H, 63, ptr(w["h1"]), H,
                        bias=P("loc_embedding_encoder.0.bias"), tag="loc_fc", side=True)
@@ -685,7 +735,7 @@ class FusedPrompter:
                            P("loc_embedding_encoder.0.weight"), P("loc_embedding_encoder.0.bias"),
                            P("loc_embedding_encoder.1.weight"), P("loc_embedding_encoder.1.bias"),
                            P("orientation_encoder.weight"), P("orientation_encoder.bias"), ptr(w["xhat_sit"]),
-                           ptr(w["rstd_sit"]), ptr(w["qpos"]), ptr(w["x_in"][0]), tag="situation_embed", side=True)
+                           ptr(w["rstd_sit"]), ptr(w["qpos"]), ptr(w["x_in"][0]), None, tag="situation_embed", side=True)
         pre_prog[1:1] = geo                              # geometry first on the side stream
         assert pre_prog[0][0] == "memset"
         cond = self.fusion == "cond"
@@ -706,13 +756,31 @@ class FusedPrompter:
                        P("object_type_embedding.weight"), P("anchor_feat"), P("orientation_encoder.weight"),
                        P("orientation_encoder.bias"), ptr(w["anchor_ori"]), B, Lo, tag="anchor_assemble")
         else:
-            self._gemm(fwd, self.emb_ptr, (E, 1), P("obj_linear_projection.weight"), (E, 1), M, H, E, ptr(w["x_in"][0]), H,
+            if cross:       # qpos is STORED into the layer-0 input (loc_layer_fwd): the projection reduces into it afterwards
+                fwd.append(("join", None, (), None, False))
+            self._gemm(fwd, self.emb_ptr, (E, 1), P("obj_linear_projection.weight"), (E, 1), M, H, E, ptr(x0_buf), H,
                        bias=P("obj_linear_projection.bias"), accumulate=2, ksplit=max(1, -(-E // 64)), tag="obj_proj")
             fwd.append(("join", None, (), None, False))
         for i in range(nl):
             pre = f"spatial_encoder.{i}."
             sa = pre + "self_attn."
             s0 = i * 8
+            if cross:
+                # situation_condition_layer[i] (ose3d_situation.py:411-418): x_pre[i] -> x_in[i]
+                pc = f"situation_condition_layer.{i}."
+                Wv = P(pc + "multihead_attn.in_proj_weight") + 4 * 2 * H * H
+                bv = P(pc + "multihead_attn.in_proj_bias") + 4 * 2 * H
+                self._call(fwd, "msr3d_cross_vec_fwd_f32", ptr(w["s_sit"]), Wv, bv, P(pc + "multihead_attn.out_proj.weight"), B,
+                           ptr(w["v_c"][i]), ptr(w["P_c"][i]), tag="cross_vec")
+                self._call(fwd, "msr3d_cross_residual_ln_fwd_f32", ptr(w["x_pre"][i]), ptr(w["P_c"][i]),
+                           P(pc + "multihead_attn.out_proj.bias"), M, L, P(pc + "norm3.weight"), P(pc + "norm3.bias"), seed, sptr,
+                           p, s0 + 4, s0 + 5, ptr(w["scale_c"][i]), ptr(w["xa"][i]), ptr(w["xhat3"][i]), ptr(w["rstd3"][i]),
+                           ptr(w["t3"][i]), tag="cross_ln")
+                self._call(fwd, "msr3d_ffn_pair_fwd_f32", ptr(w["t3"][i]), P(pc + "linear1.weight"), P(pc + "linear1.bias"),
+                           P(pc + "linear2.weight"), P(pc + "linear2.bias"), M, F, seed, sptr, p, s0 + 6, ptr(w["h_c"][i]),
+                           ptr(w["gp_c"][i]), ptr(w["f_c"][i]), self.ffn_slice, tag="cross_ffn_pair")
+                self._call(fwd, "msr3d_cross_ffn_residual_fwd_f32", ptr(w["xa"][i]), ptr(w["f_c"][i]), M, seed, sptr, p, s0 + 7,
+                           ptr(w["x_in"][i]), tag="cross_out")
             x_in = ptr(w["x_in"][i])
             use_ps = use_ab and self.ffn_presplit
             if use_ab and use_ps:
@@ -770,7 +838,7 @@ class FusedPrompter:
             self._call(fwd, "msr3d_ffn_tail_fwd_f32", ptr(w["f"][i]), ptr(w["y2"][i]), M, P(pre + "norm2.weight"),
                        P(pre + "norm2.bias"), seed, sptr, p, s0 + 3, add or None, ptr(w["xhat_2"][i]),
                        ptr(w["rstd_2"][i]), ptr(w["tokens"]) if last else None,
-                       None if last else ptr(w["x_in"][i + 1]), tag="ffn_tail")
+                       None if last else ptr((w["x_pre"] if cross else w["x_in"])[i + 1]), tag="ffn_tail")
         # ---------------- backward (gradients accumulate into the flat buffer)
         dy3 = ptr(w["upstream"])
         bwd.append(("memset", None, (w["arena_b"],), None, False))
@@ -851,7 +919,29 @@ class FusedPrompter:
             self._gemm(bwd, dqkvc, (QKVC, 1), P(sa + "w_qs.weight"), (1, H), M, H, NQ, dx, H,
                        accumulate=2, ksplit=max(1, -(-NQ // 64)), tag="dx")
             dy3 = dx
-        dx0 = ptr(w["dx"][0])
+            if cross:
+                # backward of situation_condition_layer[i]: dx (grad wrt x_in[i]) -> dxa[i] (grad wrt x_pre[i])
+                pc = f"situation_condition_layer.{i}."
+                df_c, du_c = ptr(w["df_c"][i]), ptr(w["du_c"][i])
+                self._call(bwd, "msr3d_cross_ffn_residual_bwd_f32", dx, M, seed, sptr, p, s0 + 7, df_c, G(pc + "linear2.bias"),
+                           tag="cross_out_bwd")
+                self._gemm(bwd, df_c, (1, H), ptr(w["h_c"][i]), (1, F), H, F, M, G(pc + "linear2.weight"), F,
+                           accumulate=2, ksplit=2, tag="dW2c", wgrad=True, side=True)
+                self._call(bwd, "msr3d_ffn_pair_bwd_f32", df_c, P(pc + "linear1.weight"), P(pc + "linear2.weight"),
+                           ptr(w["gp_c"][i]), M, F, du_c, ptr(w["dt3"][i]), self.ffn_slice, tag="cross_ffn_pair_bwd")
+                self._gemm(bwd, du_c, (1, F), ptr(w["t3"][i]), (1, H), F, H, M, G(pc + "linear1.weight"), H,
+                           accumulate=2, ksplit=2, tag="dW1c", wgrad=True, side=2)
+                self._call(bwd, "msr3d_colsum_add_f32", du_c, F, M, F, G(pc + "linear1.bias"), None, None, tag="db1c", side=2)
+                self._call(bwd, "msr3d_cross_ln_bwd_f32", ptr(w["dt3"][i]), dx, M, P(pc + "norm3.weight"), seed, sptr, p, s0 + 5,
+                           ptr(w["xhat3"][i]), ptr(w["rstd3"][i]), ptr(w["dxa"][i]), ptr(w["g_attn"]), G(pc + "norm3.weight"),
+                           G(pc + "norm3.bias"), G(pc + "multihead_attn.out_proj.bias"), tag="cross_ln_bwd")
+                self._call(bwd, "msr3d_cross_vec_bwd_f32", ptr(w["g_attn"]), ptr(w["scale_c"][i]), B, L, ptr(w["v_c"][i]),
+                           ptr(w["s_sit"]), P(pc + "multihead_attn.in_proj_weight") + 4 * 2 * H * H,
+                           P(pc + "multihead_attn.out_proj.weight"), G(pc + "multihead_attn.out_proj.weight"),
+                           G(pc + "multihead_attn.in_proj_weight") + 4 * 2 * H * H,
+                           G(pc + "multihead_attn.in_proj_bias") + 4 * 2 * H, ptr(w["ds_sit"]), tag="cross_vec_bwd")
+                dy3 = ptr(w["dxa"][i])
+        dx0 = ptr(w["dxa"][0]) if cross else ptr(w["dx"][0])
         dpr = dx0
         if anchor:
             # object rows of dx0 -> compact dproj; agent rows -> anchor_feat, type_embedding[1], orientation_encoder
@@ -865,13 +955,19 @@ class FusedPrompter:
         E = self.emb_dim
         self._gemm(bwd, dpr, (1, H), self.emb_ptr, (1, E), H, E, Mo, G("obj_linear_projection.weight"), E,
                    accumulate=2, ksplit=4, tag="dWproj", wgrad=True, side=True)
-        dq = [ptr(w["dx"][i]) for i in range(nl)] if self.same_all else [dx0]
+        dq = [ptr((w["dxa"] if cross else w["dx"])[i]) for i in range(nl)] if self.same_all else [dx0]
         dq += [None] * (3 - len(dq))
         assert len(dq) == 3, "fused qpos backward sums at most three layers"
-        if as_object:
-            self._call(bwd, "msr3d_loc_layer_bwd_f32", dq[0], dq[1], dq[2], ptr(w["all_loc"]), M, P("loc_layers.0.1.weight"),
-                       ptr(w["xhat_l"]), ptr(w["rstd_l"]), G("loc_layers.0.1.weight"), G("loc_layers.0.1.bias"),
-                       G("loc_layers.0.0.weight"), G("loc_layers.0.0.bias"), tag="qpos_bwd")
+        if as_object or cross:
+            self._call(bwd, "msr3d_loc_layer_bwd_f32", dq[0], dq[1], dq[2], ptr(w["all_loc"] if as_object else w["obj_locs"]),
+                       M, P("loc_layers.0.1.weight"), ptr(w["xhat_l"]), ptr(w["rstd_l"]), G("loc_layers.0.1.weight"),
+                       G("loc_layers.0.1.bias"), G("loc_layers.0.0.weight"), G("loc_layers.0.0.bias"), tag="qpos_bwd")
+            if cross:       # d(situation vector), summed over the layers -> loc_embedding_encoder / orientation_encoder
+                self._call(bwd, "msr3d_situation_embed_bwd_f32", ptr(w["ds_sit"]), None, None, ptr(w["anchor_locs"]),
+                           ptr(w["anchor_ori"]), B, 1, P("loc_embedding_encoder.1.weight"), ptr(w["xhat_sit"]),
+                           ptr(w["rstd_sit"]), G("loc_embedding_encoder.0.weight"), G("loc_embedding_encoder.0.bias"),
+                           G("loc_embedding_encoder.1.weight"), G("loc_embedding_encoder.1.bias"),
+                           G("orientation_encoder.weight"), G("orientation_encoder.bias"), tag="situation_vec_bwd")
         else:
             self._call(bwd, "msr3d_qpos_bwd_f32", dq[0], dq[1], dq[2], ptr(w["sz"]), M, P("loc_embedding_encoder.1.weight"),
                        P("size_embedding_encoder.1.weight"), ptr(w["xhat_l"]), ptr(w["rstd_l"]), ptr(w["xhat_s"]),
@@ -1020,7 +1116,7 @@ class FusedPrompter:
 
     def prime(self, batch, upstream):
         """Fill the pipeline: encode `batch` now; its transformer step happens in the next call."""
-        assert not (self.n_anchor or self.sit_embed), \
+        assert not (self.n_anchor or self.sit_embed or self.cross), \
             "the non-shipped situation modes run the sequential schedule (forward / backward / train_step)"
         self.stage_points(batch)
         self._encode("emb_next")
@@ -1185,7 +1281,7 @@ class FusedPrompter:
 
     def prime2(self, batch0, up0, batch1, up1):
         """Fill both stages: encode batch0 now, park batch1's points in slot 1."""
-        assert not (self.n_anchor or self.sit_embed), \
+        assert not (self.n_anchor or self.sit_embed or self.cross), \
             "the non-shipped situation modes run the sequential schedule (forward / backward / train_step)"
         main = torch.cuda.current_stream()
         self._slot_free[0].record()

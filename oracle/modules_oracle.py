@@ -259,6 +259,40 @@ def spatial_encoder_layer(sd: SD, prefix: str, x, pairwise, key_padding_mask, n_
     return x, att
 
 
+def cross_attention_layer(sd: SD, prefix: str, tgt: torch.Tensor, memory: torch.Tensor, n_head: int,
+                          activation: str = "gelu", masks: Optional[dict] = None) -> torch.Tensor:
+    """CrossAttentionLayer.forward, prenorm (modules/layers/transformers.py:22-73) around nn.MultiheadAttention
+    (batch_first, kdim = vdim = d_model: packed in_proj).  The reference passes neither an attention mask nor a key
+    padding mask (ose3d_situation.py:418 hands `tgt_key_padding_mask`, which the layer never forwards).
+    masks (training-mode checks): 'attn' (B, h, L, T) on the attention probabilities, 'd2', 'ffn', 'd3'."""
+    B, L, D = tgt.shape
+    T = memory.shape[1]
+    dh = D // n_head
+    mk = masks or {}
+    W, b = sd[f"{prefix}.multihead_attn.in_proj_weight"], sd[f"{prefix}.multihead_attn.in_proj_bias"]
+    t2 = F.layer_norm(tgt, (D,), sd[f"{prefix}.norm1.weight"], sd[f"{prefix}.norm1.bias"], 1e-5)
+    q = F.linear(t2, W[:D], b[:D]).view(B, L, n_head, dh).transpose(1, 2)
+    k = F.linear(memory, W[D:2 * D], b[D:2 * D]).view(B, T, n_head, dh).transpose(1, 2)
+    v = F.linear(memory, W[2 * D:], b[2 * D:]).view(B, T, n_head, dh).transpose(1, 2)
+    att = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(dh), -1)
+    if "attn" in mk:
+        att = att * mk["attn"]
+    o = torch.matmul(att, v).transpose(1, 2).reshape(B, L, D)
+    o = F.linear(o, sd[f"{prefix}.multihead_attn.out_proj.weight"], sd[f"{prefix}.multihead_attn.out_proj.bias"])
+    if "d2" in mk:
+        o = o * mk["d2"]
+    x = tgt + o
+    t3 = F.layer_norm(x, (D,), sd[f"{prefix}.norm3.weight"], sd[f"{prefix}.norm3.bias"], 1e-5)
+    act = {"gelu": F.gelu, "relu": F.relu}[activation]
+    hid = act(F.linear(t3, sd[f"{prefix}.linear1.weight"], sd[f"{prefix}.linear1.bias"]))
+    if "ffn" in mk:
+        hid = hid * mk["ffn"]
+    h = F.linear(hid, sd[f"{prefix}.linear2.weight"], sd[f"{prefix}.linear2.bias"])
+    if "d3" in mk:
+        h = h * mk["d3"]
+    return x + h
+
+
 def ose3d_situation(sd: SD, data: dict, *, n_head: int = 8, num_layers: int = 3,
                     situation_type: str = "as_transform_for_objects",
                     obj_loc_encoding: str = "same_all", fusion: str = "cond",
@@ -266,11 +300,13 @@ def ose3d_situation(sd: SD, data: dict, *, n_head: int = 8, num_layers: int = 3,
                     sa_n_points=(32, 16, None), sa_n_samples=(32, 32, None),
                     sa_radii=(0.2, 0.4, None), obj_embeds: Optional[torch.Tensor] = None,
                     trace: Optional[dict] = None, layer_masks: Optional[list] = None,
-                    spatial_multihead: bool = True, unfrozen_bn_stats: Optional[dict] = None):
+                    spatial_multihead: bool = True, unfrozen_bn_stats: Optional[dict] = None,
+                    cross_masks: Optional[list] = None):
     """OSE3DSituation.forward (model/ose3d_situation.py:288-454) for vision_backbone
     'gtpcd', use_spatial_attn/use_anchor/use_orientation True, attn_flat off, and
     situation_type in {'as_transform_for_objects' (shipped, configs/msr3d.yaml:177),
-    'as_object' (LEO baseline, configs/leo_3_dataset.yaml:180-181), 'as_object_add_loc', 'as_embedding'}.
+    'as_object' (LEO baseline, configs/leo_3_dataset.yaml:180-181), 'as_object_add_loc', 'as_embedding',
+    'as_cross_attention'}.
 
     Returns (obj_tokens (B,N',H), obj_masks (B,N') bool with True = valid)."""
     if obj_embeds is None:
@@ -320,6 +356,14 @@ def ose3d_situation(sd: SD, data: dict, *, n_head: int = 8, num_layers: int = 3,
             qpos = linear_ln(sd, "loc_layers.0", loc)
         if obj_loc_encoding in ("same_all", "diff_all") or i == 0:
             x = x + qpos
+        if situation_type == "as_cross_attention":  # :411-418 situation as the memory of a cross-attention layer
+            n_tok = loc.size(1)
+            s_feat = linear_ln(sd, "loc_embedding_encoder",
+                               fourier_features(data["anchor_locs"].unsqueeze(1).expand(-1, n_tok, -1))) + \
+                F.linear(fourier_features(data["anchor_orientation"].unsqueeze(1).expand(-1, n_tok, -1)),
+                         sd["orientation_encoder.weight"], sd["orientation_encoder.bias"])
+            x = cross_attention_layer(sd, f"situation_condition_layer.{i}", x, s_feat, n_head, activation,
+                                      masks=cross_masks[i] if cross_masks else None)
         x, att = spatial_encoder_layer(sd, f"spatial_encoder.{i}", x, pairwise, mask, n_head,
                                        fusion, activation, spatial_multihead,
                                        masks=layer_masks[i] if layer_masks else None)

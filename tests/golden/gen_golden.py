@@ -109,7 +109,7 @@ def run_case(ref, name, B, O, P, seed, situation_type="as_transform_for_objects"
                 norms.append(float(p.grad.norm()))
                 sums.append(float(p.grad.double().sum()))
                 if p.numel() <= 4096 or n in ("spatial_encoder.0.self_attn.lang_cond_fc.weight",) \
-                        or n.endswith("pairwise_loc_fc.weight"):
+                        or n.endswith("pairwise_loc_fc.weight") or n.endswith("1.multihead_attn.out_proj.weight"):
                     fix["grad:" + n] = p.grad.numpy().copy()
         fix["grad_names"] = np.array(names)
         fix["grad_norms"] = np.array(norms, dtype=np.float64)
@@ -160,6 +160,9 @@ def main():
         return
     if "--as-embedding" in sys.argv:
         run_case(ref, "prompter_as_embedding", 2, 7, 256, seed=7007, situation_type="as_embedding")
+        return
+    if "--as-cross-attention" in sys.argv:
+        run_case(ref, "prompter_as_cross_attention", 2, 6, 256, seed=8008, situation_type="as_cross_attention")
         return
     spec = run_case(ref, "prompter_cfg1", 1, 8, 256, seed=1001)
     with open(os.path.join(HERE, "state_dict_spec.json"), "w") as fh:

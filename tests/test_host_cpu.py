@@ -159,15 +159,16 @@ print("ok")
 
 
 def test_which_configurations_the_fused_engine_covers():
-    """fused.supported() is host logic: the shipped configuration, every attention fusion, four situation modes and
+    """fused.supported() is host logic: the shipped configuration, every attention fusion, five situation modes and
     the unfrozen encoder are on the engine; the rest names its reason and stays on the module tree."""
     from msr3d_b200 import configs, fused
     ok = [dict(), dict(fusion="mul"), dict(fusion="bias"), dict(fusion="ctx"), dict(fusion="add"),
           dict(situation_type="as_object"), dict(situation_type="as_object_add_loc"), dict(situation_type="as_embedding"),
+          dict(situation_type="as_cross_attention"),
           dict(freeze=False), dict(fusion="add", spatial_multihead=False), dict(obj_loc_encoding="same_0")]
     for kw in ok:
         assert fused.supported(configs.build_prompter(0, **kw)) is None, kw
-    no = [(dict(situation_type="as_cross_attention"), "situation_type"), (dict(obj_loc_encoding="diff_all"), "diff_all"),
+    no = [(dict(obj_loc_encoding="diff_all"), "diff_all"),
           (dict(activation="relu"), "gelu"), (dict(spatial_multihead=False), "multihead"), (dict(num_attention_heads=4), "heads")]
     for kw, why in no:
         reason = fused.supported(configs.build_prompter(0, **kw))

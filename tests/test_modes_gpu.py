@@ -240,3 +240,74 @@ def test_situation_modes_on_both_attention_paths(stype, O):
     assert eng.attn_block_active == (n_tok <= 64)
     print(f"{stype} O={O} ({n_tok} tokens, attention block {eng.attn_block_active}): tokens {e:.2e}, "
           f"worst grad {worst[0]} {worst[1]:.2e}")
+
+
+def test_engine_as_cross_attention_matches_reference_and_oracle():
+    """as_cross_attention: a pre-norm cross-attention + FFN block on the (repeated) situation vector in front of every
+    spatial layer; the kernels use the collapsed form (uniform softmax over identical keys), the fixture and the oracle
+    the reference's general nn.MultiheadAttention arithmetic."""
+    fx = helpers.golden("prompter_as_cross_attention")
+    seed, B, O, P = int(fx["seed"]), int(fx["B"]), int(fx["O"]), int(fx["P"])
+    model = configs.build_prompter(seed, "as_cross_attention", device="cuda")
+    sd = configs.model_state_dict(model, seed)
+    batch = synthetic.make_batch(B, O, P, seed=seed)
+    up = torch.randn(B, O, 256, generator=torch.Generator().manual_seed(seed + 77))
+    eng, tokens = _run_engine(model, batch, up)
+    e, worst_fx = _check_fixture(model, tokens, fx)
+    emb = eng.ws["emb"].cpu().view(B, O, -1)
+    want_tokens, want = _oracle_grads(sd, batch, up, obj_embeds=emb, situation_type="as_cross_attention")
+    e64 = helpers.rel_err(tokens.cpu(), want_tokens)
+    worst = _check_grads(model, want, tol=3e-4)
+    print(f"as_cross_attention: tokens vs reference {e:.2e} (grads {worst_fx:.2e}), vs fp64 oracle {e64:.2e}; worst grad "
+          f"{worst[0]} {worst[1]:.2e}")
+    assert e64 < 1e-4
+    # the query / key projections and norm1 of the cross-attention get exactly zero gradient, norm2 none at all
+    D = 256
+    for i in range(3):
+        pre = f"situation_condition_layer.{i}."
+        g = dict(model.named_parameters())[pre + "multihead_attn.in_proj_weight"].grad
+        assert float(g[:2 * D].abs().max()) == 0.0 and float(g[2 * D:].abs().max()) > 0.0
+        assert float(dict(model.named_parameters())[pre + "norm1.weight"].grad.abs().max()) == 0.0
+
+
+def test_as_cross_attention_training_mode_with_replayed_dropout_masks():
+    """Training mode (p = 0.1), 60 objects: the library's dropout masks — attention probabilities of the cross-attention
+    included — are exported and replayed in the oracle's general formulation."""
+    from msr3d_b200 import _C
+    from msr3d_b200.fused import FusedPrompter
+    seed, B, O, P, F = 97, 2, 60, 128, 2048
+    model = configs.build_prompter(seed, "as_cross_attention", device="cuda")
+    sd = configs.model_state_dict(model, seed)
+    model.train()
+    eng = FusedPrompter(model)
+    eng.prepare(B, O, P, training=True)
+    batch = synthetic.make_batch(B, O, P, seed=seed)
+    up = torch.randn(B, O, 256, generator=torch.Generator().manual_seed(5))
+    M = B * O
+
+    def mask(site, n):
+        out = torch.empty(n, device="cuda")
+        _C.call("msr3d_dropout_mask_f32", eng.seed, eng.seed_counter.data_ptr(), eng.p_drop, site, n,
+                out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return out.cpu()
+    layer_masks, cross_masks = [], []
+    for i in range(3):
+        s0 = i * 8
+        layer_masks.append({"fc": mask(s0, M * 256).view(B, O, 256), "d1": mask(s0 + 1, M * 256).view(B, O, 256),
+                            "ffn": mask(s0 + 2, M * F).view(B, O, F), "d2": mask(s0 + 3, M * 256).view(B, O, 256)})
+        cross_masks.append({"attn": mask(s0 + 4, M * 8 * O).view(B, O, 8, O).permute(0, 2, 1, 3).contiguous(),
+                            "d2": mask(s0 + 5, M * 256).view(B, O, 256), "ffn": mask(s0 + 6, M * F).view(B, O, F),
+                            "d3": mask(s0 + 7, M * 256).view(B, O, 256)})
+    eng.load_inputs(batch.to("cuda"), up.cuda())
+    eng.flat_g.zero_()
+    tokens = eng.forward()
+    eng.backward()
+    torch.cuda.synchronize()
+    emb = eng.ws["emb"].cpu().view(B, O, -1)
+    cm = [{k: v.double() for k, v in m.items()} for m in cross_masks]
+    want_tokens, want = _oracle_grads(sd, batch, up, layer_masks=layer_masks, obj_embeds=emb,
+                                      situation_type="as_cross_attention", cross_masks=cm)
+    e = helpers.rel_err(tokens.cpu(), want_tokens)
+    worst = _check_grads(model, want, tol=TOL)
+    print(f"as_cross_attention, dropout on, 2 x 60: tokens {e:.2e}, worst grad {worst[0]} {worst[1]:.2e}")
+    assert e < 1e-4

@@ -65,9 +65,14 @@ def test_module_call_runs_fused_kernels_and_matches_oracle(B, O, P):
     assert not torch.allclose(out2, tokens)
 
 
+def configs_build(seed, **kw):
+    from msr3d_b200 import configs
+    return configs.build_prompter(seed, device="cuda", **kw)
+
+
 def test_module_call_falls_back_to_the_module_tree_when_unsupported():
     from msr3d_b200 import autograd as ag
-    model = helpers.build_prompter(5, situation_type="as_cross_attention", device="cuda")    # not on the engine (module tree)
+    model = configs_build(5, obj_loc_encoding="diff_all")              # not on the engine (module tree)
     batch = synthetic.make_batch(1, 8, 256, seed=5).to("cuda")
     assert ag.eligible(model, batch.as_dict()) is not None
     out = model(batch.as_dict())

@@ -16,6 +16,7 @@ CASES = {
     "prompter_as_object": "as_object",
     "prompter_add_loc": "as_object_add_loc",
     "prompter_as_embedding": "as_embedding",
+    "prompter_as_cross_attention": "as_cross_attention",
 }
 
 
@@ -23,11 +24,20 @@ def _load(golden_dir, name):
     return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
 
 
+def _state_dict(sd_spec, name, seed):
+    """Weights by NAME (synthetic.make_state_dict): the shipped model's spec, or — for modes that own parameters the
+    shipped model does not have — the spec of that mode's drop-in model."""
+    if name == "prompter_as_cross_attention":
+        from msr3d_b200 import configs
+        return configs.model_state_dict(configs.build_prompter(0, CASES[name]), seed)
+    return synthetic.make_state_dict(sd_spec, seed)
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_prompter_forward_matches_reference(golden_dir, sd_spec, name):
     fx = _load(golden_dir, name)
     seed = int(fx["seed"])
-    sd = synthetic.make_state_dict(sd_spec, seed)
+    sd = _state_dict(sd_spec, name, seed)
     batch = synthetic.make_batch(int(fx["B"]), int(fx["O"]), int(fx["P"]), seed=seed)
     trace = {}
     ext_oracle.set_threads(4)
@@ -81,11 +91,12 @@ def test_encoder_outputs_match_reference(golden_dir, sd_spec):
     np.testing.assert_allclose(cls.numpy(), fx["obj_sem_cls"], rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("name", ["prompter_cfg1", "prompter_as_object", "prompter_as_embedding"])
+@pytest.mark.parametrize("name", ["prompter_cfg1", "prompter_as_object", "prompter_as_embedding",
+                                  "prompter_as_cross_attention"])
 def test_prompter_backward_matches_reference(golden_dir, sd_spec, name):
     fx = _load(golden_dir, name)
     seed = int(fx["seed"])
-    sd = synthetic.make_state_dict(sd_spec, seed)
+    sd = _state_dict(sd_spec, name, seed)
     frozen = lambda k: k.startswith("obj_encoder.") or k == "anchor_size"
     sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not frozen(k) else v)
           for k, v in sd.items()}
