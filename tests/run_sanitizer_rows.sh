@@ -19,6 +19,8 @@ for fusion in ("mul", "ctx", "add"):
     print("fusion", fusion, run(configs.build_prompter(3, device="cuda", fusion=fusion), 1, 6, 128))
 for st in ("as_object", "as_object_add_loc"):
     print(st, run(configs.build_prompter(3, st, device="cuda"), 2, 5, 128, extra=1))
+for st in ("as_embedding", "as_cross_attention"):
+    print(st, run(configs.build_prompter(3, st, device="cuda"), 2, 5, 128))
 from msr3d_b200.encoder import PcdObjEncoder
 enc = PcdObjEncoder(freeze=False).cuda().train()
 pc = synthetic.make_batch(1, 3, 128, seed=4).to("cuda")
@@ -27,5 +29,5 @@ print("unfrozen encoder ok", float(emb.abs().sum()), float(enc.pcd_net.fc.weight
 '
 for tool in memcheck racecheck; do
   timeout 600 compute-sanitizer --tool $tool --print-limit 20 python -c "$SCRIPT" > gpurun_out/sanitizer_rows_$tool.log 2>&1
-  echo "== $tool: exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|fusion|as_object|unfrozen|Error|hazard" gpurun_out/sanitizer_rows_$tool.log | head -14
+  echo "== $tool: exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|fusion|as_|unfrozen|Error|hazard" gpurun_out/sanitizer_rows_$tool.log | head -14
 done
