@@ -37,8 +37,8 @@ def eligible(module, data_dict) -> Optional[str]:
     fts = data_dict["obj_fts"]
     if not fts.is_cuda or fts.dim() != 4 or fts.shape[-1] != 6 or fts.dtype != torch.float32:
         return "obj_fts must be a (B, O, P, 6) fp32 CUDA tensor"
-    if fts.shape[1] > 128:
-        return "more than 128 objects per scene"
+    if fts.shape[1] + (1 if module.situation_type in fused.ANCHOR_MODES else 0) > 128:
+        return "more than 128 tokens per scene"
     p0 = next(module.parameters())
     if not p0.is_cuda or p0.dtype != torch.float32:
         return "parameters must be fp32 CUDA tensors"
