@@ -12,10 +12,10 @@ Parameters are re-homed into one flat fp32 buffer (each `p.data` becomes a view)
 that QKV+cond is a single (816 x 256) GEMM, its weight gradient another one, and the gradient all-reduce and AdamW are
 single flat operations.  State-dict keys and shapes are unchanged.
 
-Covered (`supported()`): hidden 256 / 8 heads / spatial_dim 5 / gelu, obj_loc_encoding same_all or same_0,
+Covered (`supported()`): hidden 256 / 8 heads / spatial_dim 5 / gelu, obj_loc_encoding same_all, same_0 or diff_all,
 spatial_attn_fusion cond (every shipped config) | mul | bias | ctx | add, situation_type as_transform_for_objects
 (shipped) | as_object | as_object_add_loc | as_embedding | as_cross_attention, encoder frozen (shipped) or unfrozen
-(encoder_train.py).  Anything else (diff_all, attn_flat, no spatial attention) keeps running through the module tree
+(encoder_train.py).  Anything else (attn_flat, no spatial attention) keeps running through the module tree
 in spatial.py / prompter.py.  The pipelined / prefetch / data-parallel schedules serve the shipped situation mode with
 the frozen encoder; the other modes and the unfrozen encoder run the sequential schedule or the module call.
 """
@@ -167,7 +167,8 @@ def supported(model) -> Optional[str]:
         (se.spatial_attn_fusion != "cond" or bool(se.spatial_multihead), "cond fusion without spatial_multihead"),
         (se.pairwise_rel_type == "center", "pairwise_rel_type != center"),
         (se.activation == "gelu", "activation != gelu"),
-        (se.obj_loc_encoding in ("same_all", "same_0"), "obj_loc_encoding == diff_all"),
+        (se.obj_loc_encoding in ("same_all", "same_0", "diff_all"), f"obj_loc_encoding {se.obj_loc_encoding}"),
+        (se.obj_loc_encoding != "diff_all" or se.dim_loc == 6, "dim_loc != 6"),
         (model.situation_type in ("as_transform_for_objects", "as_embedding", "as_cross_attention") + ANCHOR_MODES,
          f"situation_type {model.situation_type}"),
         (model.situation_type not in ANCHOR_MODES or bool(c.use_anchor), "anchor mode without use_anchor"),
@@ -240,6 +241,9 @@ class FusedPrompter:
         se = model.cfg.spatial_encoder
         self.nl, self.F = se.num_layers, se.dim_feedforward
         self.same_all = se.obj_loc_encoding == "same_all"
+        # diff_all (ose3d_situation.py:379-381): layer i adds its OWN loc_layers[i](loc) = LN(Linear_6(loc)) as the query
+        # position, whatever the situation mode (the modes' Fourier / size encoders are then never evaluated)
+        self.diff_all = se.obj_loc_encoding == "diff_all"
         # attention fusion (modules/layers/transformers.py:207-244): `cond` (every shipped config) has the one-launch
         # attention block and the tensor-core backward; mul / bias / ctx / add run the four-launch path with the
         # fusion-templated attention kernels and pairwise_loc_fc as spatial weights (csrc/spatial.cu)
@@ -343,14 +347,28 @@ class FusedPrompter:
         named += [("ext." + k, p) for k, p in self.extra_params.items() if p.requires_grad]
         by_name = dict(named)
         # parameters the configured situation mode never touches (neither reduced nor updated)
-        unused = {"as_object": (), "as_object_add_loc": ("loc_layers.",),
-                  "as_embedding": ("anchor_feat", "loc_layers."),
-                  # nn.MultiheadAttention's q / k projections and norm1 get exactly zero gradients (all keys are one
-                  # vector) and are optimised like the reference does; norm2 is never evaluated
-                  "as_cross_attention": ("anchor_feat", "size_embedding_encoder.") + tuple(
-                      f"situation_condition_layer.{i}.norm2." for i in range(self.nl)),
-                  }.get(self.stype, _dist.UNUSED_IN_SHIPPED_MODE)
-        unused = tuple(unused) + ("obj_encoder.obj3d_clf_pre_head.",)
+        # What the configured (situation mode, obj_loc_encoding) evaluates; every other trainable parameter goes to the
+        # never-touched segment (what DDP's find_unused_parameters achieves in the reference).  In as_cross_attention
+        # nn.MultiheadAttention's q / k projections and norm1 get exactly zero gradients (all keys are one vector) and are
+        # optimised like the reference does; norm2 is never evaluated.
+        st = self.stype
+        used = ["obj_linear_projection.", "object_orientation_feat", "object_type_embedding.", "spatial_encoder.", "ext.",
+                "obj_encoder.pcd_net."]
+        if st in ANCHOR_MODES:
+            used += ["anchor_feat", "orientation_encoder."]
+        if self.diff_all:
+            used += ["loc_layers."]
+        elif st in ("as_object", "as_cross_attention"):
+            used += ["loc_layers.0."]
+        else:
+            used += ["loc_embedding_encoder.", "size_embedding_encoder."]
+        if st == "as_embedding" and not self.diff_all:
+            used += ["orientation_encoder."]
+        if st == "as_cross_attention":
+            used += ["loc_embedding_encoder.", "orientation_encoder."]
+            used += [f"situation_condition_layer.{i}.{part}" for i in range(self.nl)
+                     for part in ("multihead_attn.", "linear1.", "linear2.", "norm1.", "norm3.")]
+        unused = tuple(n for n, _ in named if not n.startswith(tuple(used)))
         lay = _dist.flat_layout([n for n, _ in named], {n: p.numel() for n, p in named}, self.nl,
                                 no_decay_bias=self.no_decay_bias, unused=unused)
         self.order, offs, total = lay["order"], lay["offs"], lay["total"]
@@ -526,6 +544,11 @@ class FusedPrompter:
             w["proj"], w["dproj"] = f(B * Lo, H), f(B * Lo, H)
         if self.sit_embed:
             w["xhat_sit"], w["rstd_sit"] = f(B, H), f(B)
+        if self.diff_all:
+            w["qpos_l"] = [f(M, H) for _ in range(nl)]
+            w["xhat_q"] = [f(M, H) for _ in range(nl)]
+            w["rstd_q"] = [f(M) for _ in range(nl)]
+            w["x0_scratch"] = f(M, H)
         w["anchor_locs"] = f(B, 3)
         w["anchor_ori"] = f(B, 4)
         w["upstream"] = f(M, H)
@@ -700,12 +723,30 @@ class FusedPrompter:
                        tag="geometry", side=True)
         # prefetch schedule: geometry of the batch in point-cloud slot s, from its freshly copied inputs, for the NEXT step
         self.geo_prog = []
-        for q in (() if (anchor or self.sit_embed or cross) else ("_q0", "_q1")):
+        for q in (() if (anchor or self.sit_embed or cross or self.diff_all) else ("_q0", "_q1")):
             gq: List = []
             self._call(gq, "msr3d_spatial_geometry_f32", ptr(w["obj_locs" + q]), ptr(w["anchor_locs" + q]), ptr(w["anchor_ori" + q]),
                        B, L, self.dist_norm, 1, ptr(w["pw_n"]), ptr(w["ff_n"]), ptr(w["sz_n"]), tag="geometry")
             self.geo_prog.append(gq)
-        if as_object or cross:
+        diff_all = self.diff_all
+        store_qpos = as_object or cross or diff_all      # qpos is STORED into the layer-0 input: the projection follows it
+        if diff_all:
+            # loc_layers[i](loc) for every layer (ose3d_situation.py:379-381); layer 0's also starts the layer-0 input
+            for i in range(nl):
+                first = i == 0
+                self._call(pre_prog, "msr3d_loc_layer_fwd_f32", ptr(w["all_loc"] if anchor else w["obj_locs"]), M,
+                           P(f"loc_layers.{i}.0.weight"), P(f"loc_layers.{i}.0.bias"), P(f"loc_layers.{i}.1.weight"),
+                           P(f"loc_layers.{i}.1.bias"), ptr(w["xhat_q"][i]), ptr(w["rstd_q"][i]), ptr(w["qpos_l"][i]),
+                           ptr(x0_buf if first else w["x0_scratch"]),
+                           P("object_orientation_feat") if (first and not anchor) else None,
+                           P("object_type_embedding.weight") if (first and not anchor) else None, tag="qpos", side=True)
+            if cross:
+                self._call(pre_prog, "msr3d_situation_embed_fwd_f32", ptr(w["anchor_locs"]), ptr(w["anchor_ori"]), B, L,
+                           P("loc_embedding_encoder.0.weight"), P("loc_embedding_encoder.0.bias"),
+                           P("loc_embedding_encoder.1.weight"), P("loc_embedding_encoder.1.bias"),
+                           P("orientation_encoder.weight"), P("orientation_encoder.bias"), ptr(w["xhat_sit"]),
+                           ptr(w["rstd_sit"]), None, None, ptr(w["s_sit"]), tag="situation_vec", side=True)
+        elif as_object or cross:
             # qpos = loc_layers[0](loc) (ose3d_situation.py:396), stored as the first term of the layer-0 input; without an
             # agent row (as_cross_attention) the objects' constant terms ride along
             self._call(pre_prog, "msr3d_loc_layer_fwd_f32", ptr(w["all_loc"] if as_object else w["obj_locs"]), M,
@@ -756,7 +797,7 @@ class FusedPrompter:
                        P("object_type_embedding.weight"), P("anchor_feat"), P("orientation_encoder.weight"),
                        P("orientation_encoder.bias"), ptr(w["anchor_ori"]), B, Lo, tag="anchor_assemble")
         else:
-            if cross:       # qpos is STORED into the layer-0 input (loc_layer_fwd): the projection reduces into it afterwards
+            if store_qpos:  # qpos is STORED into the layer-0 input (loc_layer_fwd): the projection reduces into it afterwards
                 fwd.append(("join", None, (), None, False))
             self._gemm(fwd, self.emb_ptr, (E, 1), P("obj_linear_projection.weight"), (E, 1), M, H, E, ptr(x0_buf), H,
                        bias=P("obj_linear_projection.bias"), accumulate=2, ksplit=max(1, -(-E // 64)), tag="obj_proj")
@@ -834,7 +875,7 @@ class FusedPrompter:
                 self._gemm(fwd, ptr(w["h"][i]), (F, 1), P(pre + "linear2.weight"), (F, 1), M, H, F, ptr(w["f"][i]), H,
                            bias=P(pre + "linear2.bias"), accumulate=2, ksplit=16, tag="ffn2")
             last = i == nl - 1
-            add = 0 if (last or not self.same_all) else ptr(w["qpos"])
+            add = 0 if (last or not (self.same_all or diff_all)) else ptr(w["qpos_l"][i + 1] if diff_all else w["qpos"])
             self._call(fwd, "msr3d_ffn_tail_fwd_f32", ptr(w["f"][i]), ptr(w["y2"][i]), M, P(pre + "norm2.weight"),
                        P(pre + "norm2.bias"), seed, sptr, p, s0 + 3, add or None, ptr(w["xhat_2"][i]),
                        ptr(w["rstd_2"][i]), ptr(w["tokens"]) if last else None,
@@ -958,7 +999,19 @@ class FusedPrompter:
         dq = [ptr((w["dxa"] if cross else w["dx"])[i]) for i in range(nl)] if self.same_all else [dx0]
         dq += [None] * (3 - len(dq))
         assert len(dq) == 3, "fused qpos backward sums at most three layers"
-        if as_object or cross:
+        if diff_all:
+            for i in range(nl):          # every layer's own loc_layers[i] from the gradient of that layer's input
+                self._call(bwd, "msr3d_loc_layer_bwd_f32", ptr((w["dxa"] if cross else w["dx"])[i]), None, None,
+                           ptr(w["all_loc"] if anchor else w["obj_locs"]), M, P(f"loc_layers.{i}.1.weight"),
+                           ptr(w["xhat_q"][i]), ptr(w["rstd_q"][i]), G(f"loc_layers.{i}.1.weight"), G(f"loc_layers.{i}.1.bias"),
+                           G(f"loc_layers.{i}.0.weight"), G(f"loc_layers.{i}.0.bias"), tag="qpos_bwd")
+            if cross:
+                self._call(bwd, "msr3d_situation_embed_bwd_f32", ptr(w["ds_sit"]), None, None, ptr(w["anchor_locs"]),
+                           ptr(w["anchor_ori"]), B, 1, P("loc_embedding_encoder.1.weight"), ptr(w["xhat_sit"]),
+                           ptr(w["rstd_sit"]), G("loc_embedding_encoder.0.weight"), G("loc_embedding_encoder.0.bias"),
+                           G("loc_embedding_encoder.1.weight"), G("loc_embedding_encoder.1.bias"),
+                           G("orientation_encoder.weight"), G("orientation_encoder.bias"), tag="situation_vec_bwd")
+        elif as_object or cross:
             self._call(bwd, "msr3d_loc_layer_bwd_f32", dq[0], dq[1], dq[2], ptr(w["all_loc"] if as_object else w["obj_locs"]),
                        M, P("loc_layers.0.1.weight"), ptr(w["xhat_l"]), ptr(w["rstd_l"]), G("loc_layers.0.1.weight"),
                        G("loc_layers.0.1.bias"), G("loc_layers.0.0.weight"), G("loc_layers.0.0.bias"), tag="qpos_bwd")
@@ -1116,7 +1169,7 @@ class FusedPrompter:
 
     def prime(self, batch, upstream):
         """Fill the pipeline: encode `batch` now; its transformer step happens in the next call."""
-        assert not (self.n_anchor or self.sit_embed or self.cross), \
+        assert not (self.n_anchor or self.sit_embed or self.cross or self.diff_all), \
             "the non-shipped situation modes run the sequential schedule (forward / backward / train_step)"
         self.stage_points(batch)
         self._encode("emb_next")
@@ -1281,7 +1334,7 @@ class FusedPrompter:
 
     def prime2(self, batch0, up0, batch1, up1):
         """Fill both stages: encode batch0 now, park batch1's points in slot 1."""
-        assert not (self.n_anchor or self.sit_embed or self.cross), \
+        assert not (self.n_anchor or self.sit_embed or self.cross or self.diff_all), \
             "the non-shipped situation modes run the sequential schedule (forward / backward / train_step)"
         main = torch.cuda.current_stream()
         self._slot_free[0].record()

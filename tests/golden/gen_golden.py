@@ -54,9 +54,11 @@ def record_ext(ref):
     return log, ext
 
 
-def build_model(ref, situation_type, seed, fusion="cond"):
+def build_model(ref, situation_type, seed, fusion="cond", obj_loc_encoding=None):
     cfg = refshim.msr3d_prompter_cfg(situation_type=situation_type)
     cfg.model.spatial_encoder.spatial_attn_fusion = fusion
+    if obj_loc_encoding is not None:
+        cfg.model.spatial_encoder.obj_loc_encoding = obj_loc_encoding
     model = ref.ose3d_situation.OSE3DSituation(cfg)
     spec = [(k, list(v.shape), "int64" if v.dtype == torch.int64 else "float32")
             for k, v in model.state_dict().items()]
@@ -66,8 +68,9 @@ def build_model(ref, situation_type, seed, fusion="cond"):
     return model, spec
 
 
-def run_case(ref, name, B, O, P, seed, situation_type="as_transform_for_objects", with_grad=True, fusion="cond"):
-    model, spec = build_model(ref, situation_type, seed, fusion)
+def run_case(ref, name, B, O, P, seed, situation_type="as_transform_for_objects", with_grad=True, fusion="cond",
+             obj_loc_encoding=None):
+    model, spec = build_model(ref, situation_type, seed, fusion, obj_loc_encoding)
     batch = synthetic.make_batch(B, O, P, seed=seed)
     log, orig_ext = record_ext(ref)
     layer_out = []
@@ -160,6 +163,11 @@ def main():
         return
     if "--as-embedding" in sys.argv:
         run_case(ref, "prompter_as_embedding", 2, 7, 256, seed=7007, situation_type="as_embedding")
+        return
+    if "--diff-all" in sys.argv:       # obj_loc_encoding: diff_all (a loc layer per transformer layer)
+        run_case(ref, "prompter_diff_all", 2, 7, 256, seed=9009, obj_loc_encoding="diff_all")
+        run_case(ref, "prompter_diff_all_as_object", 1, 6, 256, seed=9010, situation_type="as_object",
+                 obj_loc_encoding="diff_all")
         return
     if "--as-cross-attention" in sys.argv:
         run_case(ref, "prompter_as_cross_attention", 2, 6, 256, seed=8008, situation_type="as_cross_attention")

@@ -165,11 +165,11 @@ def test_which_configurations_the_fused_engine_covers():
     ok = [dict(), dict(fusion="mul"), dict(fusion="bias"), dict(fusion="ctx"), dict(fusion="add"),
           dict(situation_type="as_object"), dict(situation_type="as_object_add_loc"), dict(situation_type="as_embedding"),
           dict(situation_type="as_cross_attention"),
-          dict(freeze=False), dict(fusion="add", spatial_multihead=False), dict(obj_loc_encoding="same_0")]
+          dict(freeze=False), dict(fusion="add", spatial_multihead=False), dict(obj_loc_encoding="same_0"),
+          dict(obj_loc_encoding="diff_all"), dict(situation_type="as_object", obj_loc_encoding="diff_all")]
     for kw in ok:
         assert fused.supported(configs.build_prompter(0, **kw)) is None, kw
-    no = [(dict(obj_loc_encoding="diff_all"), "diff_all"),
-          (dict(activation="relu"), "gelu"), (dict(spatial_multihead=False), "multihead"), (dict(num_attention_heads=4), "heads")]
+    no = [(dict(activation="relu"), "gelu"), (dict(spatial_multihead=False), "multihead"), (dict(num_attention_heads=4), "heads")]
     for kw, why in no:
         reason = fused.supported(configs.build_prompter(0, **kw))
         assert reason is not None and why in reason, (kw, reason)

@@ -311,3 +311,37 @@ def test_as_cross_attention_training_mode_with_replayed_dropout_masks():
     worst = _check_grads(model, want, tol=TOL)
     print(f"as_cross_attention, dropout on, 2 x 60: tokens {e:.2e}, worst grad {worst[0]} {worst[1]:.2e}")
     assert e < 1e-4
+
+
+@pytest.mark.parametrize("name,stype", [("prompter_diff_all", "as_transform_for_objects"),
+                                        ("prompter_diff_all_as_object", "as_object")])
+def test_engine_diff_all_matches_reference_and_oracle(name, stype):
+    """obj_loc_encoding: diff_all — every layer adds its own loc_layers[i](loc)."""
+    fx = helpers.golden(name)
+    seed, B, O, P = int(fx["seed"]), int(fx["B"]), int(fx["O"]), int(fx["P"])
+    model = configs.build_prompter(seed, stype, device="cuda", obj_loc_encoding="diff_all")
+    sd = configs.model_state_dict(model, seed)
+    batch = synthetic.make_batch(B, O, P, seed=seed)
+    n_tok = O + (1 if stype == "as_object" else 0)
+    up = torch.randn(B, n_tok, 256, generator=torch.Generator().manual_seed(seed + 77))
+    eng, tokens = _run_engine(model, batch, up)
+    e, worst_fx = _check_fixture(model, tokens, fx)
+    emb = eng.ws["emb"].cpu().view(B, O, -1)
+    want_tokens, want = _oracle_grads(sd, batch, up, obj_embeds=emb, situation_type=stype, obj_loc_encoding="diff_all")
+    e64 = helpers.rel_err(tokens.cpu(), want_tokens)
+    worst = _check_grads(model, want, tol=3e-4)
+    print(f"diff_all {stype}: tokens vs reference {e:.2e} (grads {worst_fx:.2e}), vs fp64 oracle {e64:.2e}; worst grad "
+          f"{worst[0]} {worst[1]:.2e}")
+    assert e64 < 1e-4
+
+
+@pytest.mark.parametrize("stype", ["as_embedding", "as_cross_attention", "as_object_add_loc"])
+def test_engine_diff_all_with_the_other_situation_modes(stype):
+    """diff_all bypasses the modes' own query-position encoders; the agent token / the cross-attention blocks stay."""
+    seed, B, O, P = 313, 2, 9, 64
+    model = configs.build_prompter(seed, stype, device="cuda", obj_loc_encoding="diff_all")
+    batch = synthetic.make_batch(B, O, P, seed=seed)
+    n_tok = O + (1 if stype == "as_object_add_loc" else 0)
+    up = torch.randn(B, n_tok, 256, generator=torch.Generator().manual_seed(seed + 77))
+    eng, e, worst = _engine_vs_oracle(model, batch, up, tol_grad=3e-4, situation_type=stype, obj_loc_encoding="diff_all")
+    print(f"diff_all {stype}: tokens {e:.2e}, worst grad {worst[0]} {worst[1]:.2e}")

@@ -72,7 +72,7 @@ def configs_build(seed, **kw):
 
 def test_module_call_falls_back_to_the_module_tree_when_unsupported():
     from msr3d_b200 import autograd as ag
-    model = configs_build(5, obj_loc_encoding="diff_all")              # not on the engine (module tree)
+    model = configs_build(5, activation="relu")                        # not on the engine (module tree)
     batch = synthetic.make_batch(1, 8, 256, seed=5).to("cuda")
     assert ag.eligible(model, batch.as_dict()) is not None
     out = model(batch.as_dict())

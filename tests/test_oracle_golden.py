@@ -229,3 +229,26 @@ def test_unfrozen_encoder_matches_reference(golden_dir, case):
             continue
         got = (stats or {}).get("e.pcd_net." + n, sd["e.pcd_net." + n]).detach().numpy()
         np.testing.assert_allclose(got, fx[f"{case}:buf:{n}"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,stype", [("prompter_diff_all", "as_transform_for_objects"),
+                                        ("prompter_diff_all_as_object", "as_object")])
+def test_prompter_diff_all_matches_reference(golden_dir, name, stype):
+    """obj_loc_encoding: diff_all (a loc layer per transformer layer, ose3d_situation.py:379-381), forward + backward."""
+    from msr3d_b200 import configs
+    fx = _load(golden_dir, name)
+    seed = int(fx["seed"])
+    sd = configs.model_state_dict(configs.build_prompter(0, stype, obj_loc_encoding="diff_all"), seed)
+    frozen = lambda k: k.startswith("obj_encoder.") or k == "anchor_size"
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not frozen(k) else v) for k, v in sd.items()}
+    batch = synthetic.make_batch(int(fx["B"]), int(fx["O"]), int(fx["P"]), seed=seed)
+    ext_oracle.set_threads(4)
+    tokens, _ = mo.ose3d_situation(sd, batch.as_dict(), situation_type=stype, obj_loc_encoding="diff_all")
+    np.testing.assert_allclose(tokens.detach().numpy(), fx["obj_tokens"], rtol=1e-4, atol=1e-4)
+    G = torch.randn(tokens.shape, generator=torch.Generator().manual_seed(seed + 77))
+    (tokens * G).sum().backward()
+    names = [str(n) for n in fx["grad_names"]]
+    for n, norm in zip(names, fx["grad_norms"]):
+        assert sd[n].grad is not None and abs(float(sd[n].grad.norm()) - norm) <= 1e-3 * max(norm, 1e-3), n
+    with_grad = {n for n in sd if isinstance(sd[n], torch.Tensor) and sd[n].requires_grad and sd[n].grad is not None}
+    assert with_grad == set(names)
