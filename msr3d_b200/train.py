@@ -7,7 +7,7 @@ zero_grad -> backward (DDP all-reduce, find_unused_parameters=True) -> clip_grad
 replaced by a fixed upstream gradient dL/d(obj_tokens): the frozen LLM is out of scope and
 only ever hands the prompter that tensor.
 
-Execution is the fused engine of msr3d_b200/fused.py: ~85 launches of this repo's kernels per
+Execution is the fused engine of msr3d_b200/fused.py: ~70 launches of this repo's kernels per
 step, replayed as one CUDA graph.  Gradients live in ONE flat fp32 buffer, so the data-parallel
 exchange is a single all-reduce and parameters that receive no gradient in the shipped mode
 (anchor_feat, orientation_encoder.*, loc_layers.* — SURVEY.md §8a) need no unused-parameter
