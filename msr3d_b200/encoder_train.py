@@ -260,7 +260,7 @@ def backward_explicit(net, st: _State, d_out: torch.Tensor, sinks=None) -> dict:
     id(parameter) to a tensor the gradient is ACCUMULATED into (the engine's views of its flat gradient buffer, already
     zeroed); without it every gradient is a fresh tensor."""
     (l1, l2, l3), layer_sets, g = st.levels, st.layer_sets, st.g
-    Bc, np1, np2, C1, C2 = st.dims
+    Bc, np1, _, C1, C2 = st.dims
     d_out = d_out.contiguous().float()
     dev = d_out.device
     grads = {}

@@ -1535,9 +1535,6 @@ class FusedPrompter:
         with torch.cuda.device(self.dev):
             return gemm_tc(dpr, Wp.t(), split=6)
 
-    def _tokens_after_replay(self):
-        return self._tokens()
-
     def refresh_split(self):
         """tf32 big / small images of the parameters (after anything but optimizer_step(split=True) changed them)."""
         _C.call("msr3d_split_tf32_f32", self.flat_p.data_ptr(), self.flat_big.data_ptr(), self.flat_small.data_ptr(),
